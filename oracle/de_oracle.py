@@ -1,0 +1,476 @@
+"""CPU restatement (numpy) of mystic's DifferentialEvolutionSolver2 generation step.
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+`cpu_baseline` / `--impl reference` legs of bench.py.  The product package
+`mystic_b200` never imports anything from oracle/.
+
+PARITY PINNED: every function below is checked bit-for-bit against recordings of the
+unmodified reference (tests/golden/*.npz, produced by oracle/record_reference.py from
+/root/reference) in tests/test_oracle_golden.py, plus the known-answer vectors of
+SURVEY.md 8(c).
+
+All citations are file:line under /root/reference/.  Layout: population [NP, D] float64
+row-major (the reference's list-of-lists, abstract_solver.py:118-120), energies [NP].
+"""
+import math
+
+import numpy as np
+
+# ----------------------------------------------------------------------------------------
+# strategies: name -> (device id, number of donors k, base kind, crossover kind)
+# mystic/strategy.py: Best1Exp 34-59, Best1Bin 61-88, Rand1Exp 90-115, RandToBest1Exp 119-145,
+# Best2Exp 147-173, Rand2Exp 175-201, Rand1Bin 203-227, RandToBest1Bin 229-255,
+# Best2Bin 257-283, Rand2Bin 285-311.  Only Best1Bin is binomial; the other "Bin" names
+# run the exponential loop (code, not docstring, is the semantics).
+# ----------------------------------------------------------------------------------------
+BASE_BEST1, BASE_RAND1, BASE_RANDTOBEST1, BASE_BEST2, BASE_RAND2 = range(5)
+XOVER_EXP, XOVER_BIN = 0, 1
+
+STRATEGIES = {
+    'Best1Exp':       (0, 2, BASE_BEST1, XOVER_EXP),
+    'Best1Bin':       (1, 2, BASE_BEST1, XOVER_BIN),
+    'Rand1Exp':       (2, 3, BASE_RAND1, XOVER_EXP),
+    'RandToBest1Exp': (3, 2, BASE_RANDTOBEST1, XOVER_EXP),
+    'Best2Exp':       (4, 4, BASE_BEST2, XOVER_EXP),
+    'Rand2Exp':       (5, 5, BASE_RAND2, XOVER_EXP),
+    'Rand1Bin':       (6, 3, BASE_RAND1, XOVER_EXP),
+    'RandToBest1Bin': (7, 2, BASE_RANDTOBEST1, XOVER_EXP),
+    'Best2Bin':       (8, 4, BASE_BEST2, XOVER_EXP),
+    'Rand2Bin':       (9, 5, BASE_RAND2, XOVER_EXP),
+}
+
+BOUNDS_NONE, BOUNDS_REJECT, BOUNDS_CLAMP = 0, 1, 2
+
+PTYPES = {'quadratic_equality': 0, 'linear_equality': 1,
+          'quadratic_inequality': 2, 'linear_inequality': 3}
+
+
+# ----------------------------------------------------------------------------------------
+# cost models (a4)
+# ----------------------------------------------------------------------------------------
+def cost_rosen(x):
+    """mystic/models/dejong.py:98-101: numpy elementwise terms, then numpy.sum (pairwise)."""
+    x = np.asarray(x, dtype=np.float64)
+    x = np.atleast_2d(x)
+    if x.shape[1] < 2:
+        return np.zeros(x.shape[0])
+    return np.sum(100.0 * (x[:, 1:] - x[:, :-1] ** 2.0) ** 2.0 + (1 - x[:, :-1]) ** 2.0, axis=-1)
+
+
+_pow = np.frompyfunc(math.pow, 2, 1)
+_cos = np.frompyfunc(math.cos, 1, 1)
+
+
+def cost_corana(x):
+    """mystic/models/storn.py:77-96.  len>=4 uses x[0..3] only; shorter inputs are scattered
+    through _d=[0,3,1,2] (x[_d.index(i)] = _x[i]); strictly sequential accumulation; math.pow."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    n, D = x.shape
+    d = [1., 1000., 10., 100.]
+    _d = [0, 3, 1, 2]
+    if D < 4:
+        _x = np.zeros((n, 4))
+        _x[:, :D] = x
+        xx = np.zeros((n, 4))
+        for i in range(4):
+            xx[:, _d.index(i)] = _x[:, i]
+    else:
+        xx = x[:, :4]
+    r = np.zeros(n)
+    for j in range(4):
+        xj = xx[:, j]
+        zj = np.floor(np.abs(xj / 0.2) + 0.49999) * np.sign(xj) * 0.2
+        near = np.abs(xj - zj) < 0.05
+        a = 0.15 * _pow(zj - 0.05 * np.sign(zj), 2).astype(np.float64) * d[j]
+        b = d[j] * xj * xj
+        r = r + np.where(near, a, b)
+    return r
+
+
+def cost_griewangk(x):
+    """mystic/models/storn.py:135-139: sum([c*c for c in coeffs])/4000., running product of
+    math.cos(c_i/sqrt(i+1.0)), term1 - term2 + 1.
+
+    NOTE on `sum`: the restatement accumulates plainly left to right, which is what the
+    reference computes under Python <= 3.11, and under 3.12 whenever the row holds numpy
+    scalars (rows that came out of ndarray population rows: strict ranges, Best* mutants).
+    CPython 3.12's builtin sum() switches to Neumaier-compensated accumulation for runs of
+    exact Python floats (Python/bltinmodule.c), so under the recording interpreter some
+    reference energies differ from this restatement in the last bit (<= 2 ulp observed).
+    tests/test_oracle_golden.py therefore checks griewangk ENERGIES to 1e-14 relative and
+    everything else (trial vectors, selections, populations, best solutions) bit for bit."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    n, D = x.shape
+    s = np.zeros(n)
+    for i in range(D):
+        s = s + x[:, i] * x[:, i]
+    term1 = s / 4000.
+    term2 = np.ones(n)
+    for i in range(D):
+        term2 = term2 * _cos(x[:, i] / math.sqrt(i + 1.0)).astype(np.float64)
+    return term1 - term2 + 1
+
+
+def cost_zimmermann(x):
+    """mystic/models/storn.py:182-191 (D == 2)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    x0, x1 = x[:, 0], x[:, 1]
+    f8 = 9 - x0 - x1
+    c0 = np.where(x0 < 0, -100 * x0, 0.0)
+    c1 = np.where(x1 < 0, -100 * x1, 0.0)
+    xx = (x0 - 3.) * (x0 - 3) + (x1 - 2.) * (x1 - 2)
+    c2 = np.where(xx > 16, 100 * (xx - 16), 0.0)
+    c3 = np.where(x0 * x1 > 14, 100 * (x0 * x1 - 14.), 0.0)
+    # python max(f8,c0,c1,c2,c3): first maximal element; values only, so np.maximum is equal
+    return np.maximum(np.maximum(np.maximum(np.maximum(f8, c0), c1), c2), c3)
+
+
+CHEBYSHEV_TARGETS = {  # mystic/models/_model_helper.py:10-14
+    2: [2., 0., -1.],
+    4: [8., 0., -8., 0., 1.],
+    6: [32., 0., -48., 0., 18., 0., -1.],
+    8: [128., 0., -256., 0., 160., 0., -32., 0., 1.],
+    16: [32768., 0., -131072., 0., 212992., 0., -180224., 0., 84480., 0., -21504., 0., 2688., 0., -128., 0., 1],
+}
+
+
+def _polyeval(coeffs, x):
+    """mystic/math/poly.py:37-39: val = 0*x; for c in coeffs: val = c + val*x."""
+    val = 0 * x
+    for j in range(coeffs.shape[1]):
+        val = coeffs[:, j] + val * x
+    return val
+
+
+def chebyshev_points(M):
+    """x_i as the reference accumulates them: x=-1.0; x += 2.0/(M-1) (_model_helper.py:19-25)."""
+    xs = np.empty(M)
+    x = -1.0
+    dx = 2.0 / (M - 1)
+    for i in range(M):
+        xs[i] = x
+        x += dx
+    return xs
+
+
+def cost_chebyshev(x, order=8, M=61):
+    """mystic/models/_model_helper.py:16-33 with target = chebyshev{order}coeffs."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    n = x.shape[0]
+    target = np.asarray(CHEBYSHEV_TARGETS[order], dtype=np.float64)[None, :]
+    result = np.zeros(n)
+    for xi in chebyshev_points(int(M)):
+        px = _polyeval(x, xi)
+        out = (px < -1) | (px > 1)
+        result = result + np.where(out, (1 - px) * (1 - px), 0.0)
+    for xe in (1.2, -1.2):
+        px = _polyeval(x, xe) - _polyeval(target, xe)
+        result = result + np.where(px < 0, px * px, 0.0)
+    return result
+
+
+def make_cost(name, extra_args=()):
+    """name -> f(X[NP,D]) -> [NP]; names as exported by mystic.models / mystic.models.poly."""
+    if name == 'rosen':
+        return cost_rosen
+    if name == 'corana':
+        return cost_corana
+    if name == 'griewangk':
+        return cost_griewangk
+    if name == 'zimmermann':
+        return cost_zimmermann
+    if name.startswith('chebyshev') and name.endswith('cost'):
+        order = int(name[len('chebyshev'):-len('cost')])
+        M = int(extra_args[0]) if extra_args else 61
+        return lambda X: cost_chebyshev(X, order, M)
+    raise KeyError(name)
+
+
+# ----------------------------------------------------------------------------------------
+# penalty (a5): mystic/penalty.py:41-157, 341-457 stacked decorators; tools.py:380-389
+# ----------------------------------------------------------------------------------------
+def penalty_value(x, terms):
+    """terms[0] is the innermost decorator.  Outermost is evaluated first and the inner
+    result is added to it: t_last + (... + (t_0 + 0.0)).  condition = sequential dot - h
+    (oracle/host_callables.py)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    n, D = x.shape
+    total = np.zeros(n)  # the undecorated penalty returns 0.0
+    for t in terms:
+        G = np.asarray(t['G'], dtype=np.float64)
+        acc = np.zeros(n)
+        for j in range(D):
+            acc = acc + G[j] * x[:, j]
+        pf = acc - float(t['h'])
+        _k = t.get('k', 100) * pow(t.get('hpow', 5), t.get('n', 0))
+        ptype = t['ptype']
+        if ptype == 'quadratic_equality':      # penalty.py:88
+            v = float(_k) * _pow(pf, 2).astype(np.float64)
+        elif ptype == 'linear_equality':       # penalty.py:147
+            v = float(_k) * np.abs(pf)
+        elif ptype == 'quadratic_inequality':  # penalty.py:388
+            v = float(2 * _k) * _pow(np.maximum(0., pf), 2).astype(np.float64)
+        elif ptype == 'linear_inequality':     # penalty.py:447
+            v = float(2 * _k) * np.abs(np.maximum(0., pf))
+        else:
+            raise KeyError(ptype)
+        total = v + total
+    return total
+
+
+# ----------------------------------------------------------------------------------------
+# Philox4x32-10 counter RNG (Salmon et al., SC'11; Random123 v1.14 philox.h) and the draw
+# protocol shared with the device kernels (mystic_b200/csrc/philox.cuh).
+# ----------------------------------------------------------------------------------------
+_M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+_W0, _W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+_MASK32 = np.uint64(0xFFFFFFFF)
+
+STREAM_DONORS, STREAM_XOVER, STREAM_INIT = 0, 1, 2
+
+
+def philox4x32(c0, c1, c2, c3, k0, k1):
+    """vectorised Philox4x32-10; all args uint32 arrays (broadcastable). Returns 4 uint32 arrays."""
+    c0, c1, c2, c3 = [np.asarray(c, dtype=np.uint32) for c in (c0, c1, c2, c3)]
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0 = np.uint32(k0)
+    k1 = np.uint32(k1)
+    with np.errstate(over='ignore'):
+        for _ in range(10):
+            p0 = c0.astype(np.uint64) * _M0
+            p1 = c2.astype(np.uint64) * _M1
+            hi0 = (p0 >> np.uint64(32)).astype(np.uint32)
+            lo0 = (p0 & _MASK32).astype(np.uint32)
+            hi1 = (p1 >> np.uint64(32)).astype(np.uint32)
+            lo1 = (p1 & _MASK32).astype(np.uint32)
+            c0, c1, c2, c3 = hi1 ^ c1 ^ k0, lo1, hi0 ^ c3 ^ k1, lo0
+            k0 = np.uint32(k0 + _W0)
+            k1 = np.uint32(k1 + _W1)
+    return c0, c1, c2, c3
+
+
+def _mulhi64(a, b):
+    """floor(a*b / 2^64) for uint64 arrays a and python int / uint64 b (b < 2^32 here)."""
+    a = np.asarray(a, dtype=np.uint64)
+    b = np.uint64(b)
+    a_lo = a & _MASK32
+    a_hi = a >> np.uint64(32)
+    # b < 2^32 so b_hi = 0:  a*b = a_hi*b*2^32 + a_lo*b
+    lo = a_lo * b
+    mid = a_hi * b + (lo >> np.uint64(32))
+    return mid >> np.uint64(32)
+
+
+def philox_donors(seed, generation, cand, NP, D, k):
+    """Donor indices [n,k] (distinct, != cand, uniform over ordered k-tuples) and start index.
+
+    stream STREAM_DONORS, counter (block, cand, generation, stream); block b supplies the
+    64-bit words r_{2b} = x0<<32|x1 and r_{2b+1} = x2<<32|x3.  Donor i uses r_i:
+    t = mulhi64(r_i, NP-1-i) is a rank among the not-yet-excluded indices, converted to an index by
+    walking the sorted exclusion list {cand, earlier donors}.  nstart = mulhi64(r_k, D).
+    Replaces random.sample(...)/random.randrange(D) (strategy.py:27,42) in Philox mode."""
+    cand = np.asarray(cand, dtype=np.int64)
+    n = cand.shape[0]
+    k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    words = []
+    for b in range((k + 1 + 1) // 2):
+        x0, x1, x2, x3 = philox4x32(np.uint32(b), cand.astype(np.uint32), np.uint32(generation),
+                                    np.uint32(STREAM_DONORS), k0, k1)
+        words.append((x0.astype(np.uint64) << np.uint64(32)) | x1.astype(np.uint64))
+        words.append((x2.astype(np.uint64) << np.uint64(32)) | x3.astype(np.uint64))
+    donors = np.zeros((n, k), dtype=np.int64)
+    excl = np.full((n, k + 1), np.iinfo(np.int64).max, dtype=np.int64)  # sorted ascending, padded
+    excl[:, 0] = cand
+    for i in range(k):
+        t = _mulhi64(words[i], NP - 1 - i).astype(np.int64)
+        idx = t.copy()
+        for e in range(i + 1):
+            idx = idx + (idx >= excl[:, e]).astype(np.int64)
+        donors[:, i] = idx
+        excl[:, i + 1] = idx
+        excl.sort(axis=1)
+    nstart = _mulhi64(words[k], D).astype(np.int64)
+    return donors, nstart
+
+
+def crossover_threshold(CR):
+    """Bernoulli(CR) as `x < thr` on a 32-bit Philox word, thr in [0, 2^32] (64-bit compare)."""
+    cr = min(max(float(CR), 0.0), 1.0)
+    return int(math.floor(cr * 4294967296.0))
+
+
+def philox_xover_words(seed, generation, cand, D):
+    """[n, 4*ceil(D/4)] uint32 crossover words: word i = block i//4, lane i%4 of stream 1."""
+    cand = np.asarray(cand, dtype=np.int64)
+    k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    nblk = (D + 3) // 4
+    b = np.arange(nblk, dtype=np.uint32)[None, :]
+    x = philox4x32(b, cand.astype(np.uint32)[:, None], np.uint32(generation), np.uint32(STREAM_XOVER), k0, k1)
+    return np.stack(x, axis=-1).reshape(cand.shape[0], nblk * 4)
+
+
+def philox_init_population(seed, NP, lo, hi, offset=0):
+    """Device-side SetRandomInitialPoints (abstract_solver.py:532-534, distributionally):
+    pop[c][j] = lo[j] + (hi[j]-lo[j]) * u,  u = (r64 >> 11) * 2^-53, r64 from stream 2,
+    block j//2 (word pair j%2), counter (block, c, 0, STREAM_INIT)."""
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    D = lo.shape[0]
+    cand = (np.arange(NP, dtype=np.int64) + offset)
+    k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
+    nblk = (D + 1) // 2
+    b = np.arange(nblk, dtype=np.uint32)[None, :]
+    x0, x1, x2, x3 = philox4x32(b, cand.astype(np.uint32)[:, None], np.uint32(0), np.uint32(STREAM_INIT), k0, k1)
+    r_even = (x0.astype(np.uint64) << np.uint64(32)) | x1.astype(np.uint64)
+    r_odd = (x2.astype(np.uint64) << np.uint64(32)) | x3.astype(np.uint64)
+    r = np.stack([r_even, r_odd], axis=-1).reshape(NP, nblk * 2)[:, :D]
+    u = (r >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+    return lo[None, :] + (hi - lo)[None, :] * u
+
+
+# ----------------------------------------------------------------------------------------
+# the generation step (a1, a2, a3, a6, a7)
+# ----------------------------------------------------------------------------------------
+def crossover_mask_replay(xover, D, nstart, uni, CR):
+    """[n, D] bool mask from the reference's own uniforms (NaN = not drawn).
+    Bin (strategy.py:77-85): i==n or u_i < CR.  Exp (strategy.py:48-56): L = number of leading
+    draws with u < CR, capped at D; dims n, n+1, ... (mod D)."""
+    n = nstart.shape[0]
+    idx = np.arange(D)[None, :]
+    if xover == XOVER_BIN:
+        with np.errstate(invalid='ignore'):
+            return (idx == nstart[:, None]) | (uni[:, :D] < CR)
+    with np.errstate(invalid='ignore'):
+        ok = uni[:, :D] < CR                      # NaN -> False
+    L = np.where(ok.all(axis=1), D, np.argmin(ok, axis=1))
+    rel = (idx - nstart[:, None]) % D
+    return rel < L[:, None]
+
+
+def crossover_mask_philox(xover, D, nstart, words, CR):
+    thr = np.uint64(crossover_threshold(CR))
+    ok = words.astype(np.uint64) < thr
+    n = nstart.shape[0]
+    idx = np.arange(D)[None, :]
+    if xover == XOVER_BIN:
+        return (idx == nstart[:, None]) | ok[:, :D]
+    okD = ok[:, :D]
+    L = np.where(okD.all(axis=1), D, np.argmin(okD, axis=1))
+    rel = (idx - nstart[:, None]) % D
+    return rel < L[:, None]
+
+
+def mutate(base, pop, best, donors, F):
+    """Mutant vector for every dimension, with the reference's evaluation order (no FMA)."""
+    p = [pop[donors[:, i]] for i in range(donors.shape[1])]
+    b = best[None, :]
+    if base == BASE_BEST1:       # strategy.py:52-54, 83-85
+        return b + F * (p[0] - p[1])
+    if base == BASE_RAND1:       # strategy.py:108-110, 220-222
+        return p[0] + F * (p[1] - p[2])
+    if base == BASE_RANDTOBEST1:  # strategy.py:137-140, 247-250: t += F*(best-t) + F*(p1-p2)
+        return pop + (F * (b - pop) + F * (p[0] - p[1]))
+    if base == BASE_BEST2:       # strategy.py:164-168, 274-278
+        return b + F * (p[0] + p[1] - p[2] - p[3])
+    if base == BASE_RAND2:       # strategy.py:192-196, 302-306
+        return p[0] + F * (p[1] + p[2] - p[3] - p[4])
+    raise KeyError(base)
+
+
+class DEState(object):
+    """Solver state the step reads/writes (names follow abstract_solver.py:112-122)."""
+
+    def __init__(self, population, lo=None, hi=None, bounds_mode=BOUNDS_NONE):
+        self.population = np.array(population, dtype=np.float64)
+        NP, D = self.population.shape
+        self.popEnergy = np.full(NP, np.inf)
+        self.bestEnergy = np.inf
+        self.bestSolution = self.population[0].copy()
+        self.bestIndex = -1          # index of the member that last became best (-1: none yet)
+        self.evaluations = 0
+        self.generation = -1         # last generation evaluated (0 = initial population)
+        self.bounds_mode = bounds_mode
+        self.lo = None if lo is None else np.asarray(lo, dtype=np.float64)
+        self.hi = None if hi is None else np.asarray(hi, dtype=np.float64)
+        self.trialSolution = None
+        self.trialEnergy = None
+        self.accepted = None
+
+
+def evaluate(trial, cost, state, penalty_terms=()):
+    """wrap_penalty(wrap_bounds(wrap_function(raw))) -- differential_evolution.py:515-521,
+    tools.py:386-389, 420-426: OOB -> inf without calling the cost, then + penalty."""
+    if state.bounds_mode != BOUNDS_NONE:
+        oob = ((trial < state.lo[None, :]) | (trial > state.hi[None, :])).any(axis=1)
+    else:
+        oob = np.zeros(trial.shape[0], dtype=bool)
+    raw = np.full(trial.shape[0], np.inf)
+    if (~oob).any():
+        raw[~oob] = cost(trial[~oob])
+    if penalty_terms:
+        with np.errstate(invalid='ignore'):
+            return raw + penalty_value(trial, penalty_terms)
+    return raw + 0.0
+
+
+def select(state, trial, trialE):
+    """differential_evolution.py:596-613."""
+    state.evaluations += int(trialE.shape[0] - np.isinf(trialE).sum())
+    accept = trialE < state.popEnergy
+    state.popEnergy = np.where(accept, trialE, state.popEnergy)
+    state.population = np.where(accept[:, None], trial, state.population)
+    cand = np.where(accept & (trialE < state.bestEnergy), trialE, np.inf)
+    i = int(np.argmin(cand))              # first occurrence = lowest index (strict '<' scan)
+    if cand[i] < state.bestEnergy:
+        state.bestEnergy = float(cand[i])
+        state.bestSolution = trial[i].copy()
+        state.bestIndex = i
+    state.trialSolution = trial
+    state.trialEnergy = trialE
+    state.accepted = accept
+
+
+def apply_bounds(trial, state):
+    """Mode B (tight=True): x[i]=max(lo,x[i]); x[i]=min(hi,x[i]) (symbolic.py:1139-1144)."""
+    if state.bounds_mode == BOUNDS_CLAMP:
+        return np.minimum(np.maximum(trial, state.lo[None, :]), state.hi[None, :])
+    return trial
+
+
+def step0(state, cost, penalty_terms=()):
+    """Generation 0: differential_evolution.py:516-520 (clip population into the strict range,
+    at=True), :559-567, :575-582 with strategy=None, :589, :603-613."""
+    if state.bounds_mode != BOUNDS_NONE:
+        state.population = state.population.clip(state.lo, state.hi)
+    state.bestSolution = state.population[0].copy()
+    state.bestEnergy = np.inf
+    trial = apply_bounds(state.population.copy(), state)
+    trialE = evaluate(trial, cost, state, penalty_terms)
+    select(state, trial, trialE)
+    state.generation = 0
+
+
+def step(state, strategy, CR, F, cost, penalty_terms=(), replay=None, philox=None):
+    """One generation g >= 1.  Exactly one of:
+       replay = dict(donors[NP,>=k], nstart[NP], uni[NP,D+1])  -- the reference's recorded draws
+       philox = dict(seed=int, offset=int)                      -- counter RNG (generation = g)"""
+    _, k, base, xover = STRATEGIES[strategy]
+    pop = state.population
+    NP, D = pop.shape
+    g = state.generation + 1
+    if replay is not None:
+        donors = np.asarray(replay['donors'])[:, :k].astype(np.int64)
+        nstart = np.asarray(replay['nstart']).astype(np.int64)
+        mask = crossover_mask_replay(xover, D, nstart, np.asarray(replay['uni']), CR)
+    else:
+        cand = np.arange(NP, dtype=np.int64) + int(philox.get('offset', 0))
+        donors, nstart = philox_donors(philox['seed'], g, cand, NP, D, k)
+        words = philox_xover_words(philox['seed'], g, cand, D)
+        mask = crossover_mask_philox(xover, D, nstart, words, CR)
+    mutant = mutate(base, pop, state.bestSolution, donors, F)
+    trial = np.where(mask, mutant, pop)
+    trial = apply_bounds(trial, state)
+    trialE = evaluate(trial, cost, state, penalty_terms)
+    select(state, trial, trialE)
+    state.generation = g
+    return donors, nstart, mask

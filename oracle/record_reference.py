@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Record golden vectors from the UNMODIFIED reference (mystic @ /root/reference).
+
+TEST INFRASTRUCTURE ONLY.  Runs in the build container (the reference cannot travel
+to the GPU box); writes small .npz fixtures into tests/golden/.  Usage:
+
+    python oracle/record_reference.py            # all cases
+    python oracle/record_reference.py c1_rosen3  # one case
+
+How the recording works, without touching reference code:
+  * mystic/strategy.py:19 does `import random` and calls random.sample /
+    random.randrange / random.random (strategy.py:27,42,49,...).  We set
+    `mystic.strategy.random = Recorder()`, an object with those three methods that
+    delegates to the stdlib generator and logs every value returned.  Per candidate
+    the draw order is sample(k) -> randrange(D) -> uniforms (Best1Bin: randrange
+    comes after the trial copy, but still before the uniforms).
+  * trial vectors / trial energies are captured by a recording `map` installed with
+    SetMapper (the only place the reference evaluates the cost,
+    mystic/differential_evolution.py:589).
+  * per-generation solver state is snapshotted from the `callback` hook
+    (differential_evolution.py:622).
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, '_shim'))
+sys.path.insert(1, '/root/reference')
+sys.path.insert(2, REPO)
+
+import random as _stdlib_random  # noqa: E402
+import numpy as np  # noqa: E402
+
+KMAX = 5
+
+
+class Recorder(object):
+    """Stand-in for the `random` module seen by mystic.strategy."""
+
+    def __init__(self):
+        self.cands = []  # one dict per strategy call
+
+    def sample(self, population, k):
+        out = _stdlib_random.sample(population, k)
+        self.cands.append({'donors': list(out), 'n': None, 'u': []})
+        return out
+
+    def randrange(self, *args):
+        out = _stdlib_random.randrange(*args)
+        self.cands[-1]['n'] = out
+        return out
+
+    def random(self):
+        out = _stdlib_random.random()
+        self.cands[-1]['u'].append(out)
+        return out
+
+
+class RecordingMap(object):
+    """indexable-result map (differential_evolution.py:592 needs trialEnergy[0])."""
+
+    def __init__(self):
+        self.trials = []
+        self.energies = []
+
+    def __call__(self, f, seq, **kwds):
+        self.trials.append(np.array([list(map(float, row)) for row in seq], dtype=np.float64))
+        out = [f(row) for row in seq]
+        self.energies.append(np.array(out, dtype=np.float64))
+        return out
+
+
+def _cost(name):
+    import importlib
+    import mystic.models as mm
+    if hasattr(mm, name):
+        return getattr(mm, name)
+    # `mystic.models.poly` the attribute is a Polynomial() instance (models/__init__.py),
+    # so fetch the module itself from sys.modules
+    importlib.import_module('mystic.models.poly')
+    return getattr(sys.modules['mystic.models.poly'], name)
+
+
+def _termination(spec):
+    import mystic.termination as mt
+    if spec is None:
+        return None
+    kind = spec[0]
+    return getattr(mt, kind)(*spec[1:])
+
+
+def record(case):
+    import mystic.strategy as mstrategy
+    from mystic.solvers import DifferentialEvolutionSolver2
+    from mystic.tools import random_seed
+    from oracle.host_callables import build_reference_penalty
+
+    dim, NP = case['dim'], case['NP']
+    random_seed(case['seed'])
+    # NOTE (reference quirk, differential_evolution.py:676-692 + abstract_solver.py:1171):
+    # CrossProbability/ScalingFactor given to Solve() are overwritten by the stale
+    # 'cross'/'scale' entries of `settings` on the first Step, so they only take effect when
+    # given to the constructor (or to Step directly).  via='solve' records that quirk
+    # (BASELINE config 1 as literally specified); via='ctor' really runs with CR/F.
+    via = case.get('via', 'ctor')
+    if via == 'ctor':
+        solver = DifferentialEvolutionSolver2(dim, NP, CrossProbability=case['CR'], ScalingFactor=case['F'])
+    else:
+        solver = DifferentialEvolutionSolver2(dim, NP)
+    NP = solver.nPop
+    init = case['init']
+    if init[0] == 'random':
+        solver.SetRandomInitialPoints(list(init[1]), list(init[2]))
+    else:
+        solver.SetInitialPoints(list(init[1]), init[2])
+    bounds = case.get('bounds')
+    if bounds is not None:
+        lo, hi, tight = bounds
+        if tight:
+            solver.SetStrictRanges(list(lo), list(hi), tight=True)
+        else:
+            solver.SetStrictRanges(list(lo), list(hi))
+    pen = case.get('penalty')
+    if pen:
+        solver.SetPenalty(build_reference_penalty(pen))
+    solver.SetEvaluationLimits(generations=case['maxgen'])
+    rmap = RecordingMap()
+    solver.SetMapper(rmap)
+
+    pop0 = np.array([list(map(float, r)) for r in solver.population], dtype=np.float64)
+
+    rec = Recorder()
+    snaps = []
+
+    def callback(best):
+        snaps.append({
+            'pop': np.array([list(map(float, r)) for r in solver.population], dtype=np.float64),
+            'popE': np.array(solver.popEnergy, dtype=np.float64),
+            'bestE': float(solver.bestEnergy),
+            'bestX': np.array(solver.bestSolution, dtype=np.float64).copy(),
+            'evals': int(solver.evaluations),
+        })
+
+    saved = mstrategy.random
+    mstrategy.random = rec
+    try:
+        strategy = getattr(mstrategy, case['strategy'])
+        term = _termination(case.get('termination'))
+        if term is None:
+            import mystic.termination as mt
+            term = mt.VTR(-1.0)  # never satisfied for the non-negative costs used here
+        extra = tuple(case['ExtraArgs']) if case.get('ExtraArgs') else None
+        if via == 'ctor':
+            solver.Solve(_cost(case['cost']), term, ExtraArgs=extra, strategy=strategy,
+                         callback=callback)
+        else:
+            solver.Solve(_cost(case['cost']), term, ExtraArgs=extra, strategy=strategy,
+                         CrossProbability=case['CR'], ScalingFactor=case['F'],
+                         callback=callback)
+    finally:
+        mstrategy.random = saved
+
+    G = len(snaps) - 1  # generations after generation 0
+    assert len(rmap.trials) == G + 1, (len(rmap.trials), G)
+    assert len(rec.cands) == G * NP, (len(rec.cands), G, NP)
+    assert solver.generations == G
+
+    donors = -np.ones((G, NP, KMAX), dtype=np.int32)
+    nstart = np.zeros((G, NP), dtype=np.int32)
+    nuni = np.zeros((G, NP), dtype=np.int32)
+    uni = np.full((G, NP, dim + 1), np.nan, dtype=np.float64)
+    for g in range(G):
+        for c in range(NP):
+            e = rec.cands[g * NP + c]
+            donors[g, c, :len(e['donors'])] = e['donors']
+            nstart[g, c] = e['n']
+            nuni[g, c] = len(e['u'])
+            uni[g, c, :len(e['u'])] = e['u']
+
+    out = {
+        'meta': json.dumps(dict(case, NP=NP, generations=G, evaluations=int(solver.evaluations),
+                                via=via, CR_eff=float(solver.probability), F_eff=float(solver.scale),
+                                stop=str(solver.Terminated(info=True)),
+                                python=sys.version.split()[0], numpy=np.__version__)),
+        'pop0': pop0,
+        'trial': np.stack(rmap.trials),          # [G+1, NP, D]  (index 0 = generation 0)
+        'trialE': np.stack(rmap.energies),       # [G+1, NP]
+        'pop': np.stack([s['pop'] for s in snaps]),    # after selection, per generation
+        'popE': np.stack([s['popE'] for s in snaps]),
+        'bestE': np.array([s['bestE'] for s in snaps]),
+        'bestX': np.stack([s['bestX'] for s in snaps]),
+        'evals': np.array([s['evals'] for s in snaps], dtype=np.int64),
+        'energy_history': np.array(solver.energy_history, dtype=np.float64),
+        'donors': donors, 'nstart': nstart, 'nuni': nuni, 'uni': uni,
+    }
+    return out
+
+
+ALL_STRATEGIES = ['Best1Exp', 'Best1Bin', 'Rand1Exp', 'RandToBest1Exp', 'Best2Exp', 'Rand2Exp',
+                  'Rand1Bin', 'RandToBest1Bin', 'Best2Bin', 'Rand2Bin']
+
+
+def cases():
+    cs = {}
+    # BASELINE config 1 as literally specified (SURVEY.md 8c golden vector)
+    cs['c1_rosen3_best1exp'] = dict(dim=3, NP=40, strategy='Best1Exp', cost='rosen', CR=0.5, F=0.6,
+                                    seed=123, init=('random', [0.] * 3, [2.] * 3), maxgen=99999,
+                                    termination=('VTR', 1e-4), via='solve')
+    # same problem with CR/F really in effect (given to the constructor)
+    cs['c1b_rosen3_best1exp_ctor'] = dict(dim=3, NP=40, strategy='Best1Exp', cost='rosen', CR=0.5, F=0.6,
+                                          seed=123, init=('random', [0.] * 3, [2.] * 3), maxgen=99999,
+                                          termination=('VTR', 1e-4), via='ctor')
+    # every strategy name, unconstrained rosen
+    for i, s in enumerate(ALL_STRATEGIES):
+        cs['strat_%s_rosen8' % s] = dict(dim=8, NP=24, strategy=s, cost='rosen', CR=0.9, F=0.8,
+                                         seed=1000 + i, init=('random', [-2.] * 8, [2.] * 8), maxgen=10)
+    # bounds mode A: default SetStrictRanges -> out-of-bounds trials get inf (tools.py:420-426)
+    cs['boundsA_best1bin_rosen16'] = dict(dim=16, NP=32, strategy='Best1Bin', cost='rosen', CR=0.9, F=0.8,
+                                          seed=7, init=('random', [-1.5] * 16, [1.5] * 16),
+                                          bounds=([-1.5] * 16, [1.5] * 16, False), maxgen=12)
+    # bounds mode B: tight=True -> symbolic clamp (symbolic.py:1139-1144)
+    cs['boundsB_best1bin_rosen16'] = dict(dim=16, NP=32, strategy='Best1Bin', cost='rosen', CR=0.9, F=0.8,
+                                          seed=7, init=('random', [-1.5] * 16, [1.5] * 16),
+                                          bounds=([-1.5] * 16, [1.5] * 16, True), maxgen=12)
+    cs['boundsB_rand1exp_rosen16'] = dict(dim=16, NP=32, strategy='Rand1Exp', cost='rosen', CR=0.9, F=0.8,
+                                          seed=8, init=('random', [-1.5] * 16, [1.5] * 16),
+                                          bounds=([-1.5] * 16, [1.5] * 16, True), maxgen=12)
+    # population initialised outside the strict range: generation-0 clamp
+    # (differential_evolution.py:516-520)
+    cs['boundsA_init_outside_rosen4'] = dict(dim=4, NP=16, strategy='Rand1Bin', cost='rosen', CR=0.9, F=0.8,
+                                             seed=11, init=('random', [-4.] * 4, [4.] * 4),
+                                             bounds=([-2.] * 4, [2.] * 4, False), maxgen=8)
+    # corana: reference uses only x[0..3] (storn.py:87-88); clamp bounds + penalty (BASELINE config 4 shape)
+    cs['corana8_rand1exp_pen'] = dict(dim=8, NP=32, strategy='Rand1Exp', cost='corana', CR=0.9, F=0.8,
+                                      seed=21, init=('random', [-1000.] * 8, [1000.] * 8),
+                                      bounds=([-1000.] * 8, [1000.] * 8, True),
+                                      penalty=[dict(ptype='quadratic_inequality', G=[1.] * 8, h=100., k=100, hpow=5)],
+                                      maxgen=12)
+    cs['corana4_rand1bin'] = dict(dim=4, NP=40, strategy='Rand1Bin', cost='corana', CR=0.9, F=0.8,
+                                  seed=123, init=('random', [-1000.] * 4, [1000.] * 4),
+                                  bounds=([-1000.] * 4, [1000.] * 4, False), maxgen=25)
+    cs['corana2_best1exp'] = dict(dim=2, NP=12, strategy='Best1Exp', cost='corana', CR=0.7, F=0.8,
+                                  seed=22, init=('random', [-10.] * 2, [10.] * 2), maxgen=10)
+    # griewangk
+    cs['griewangk10_best1bin'] = dict(dim=10, NP=40, strategy='Best1Bin', cost='griewangk', CR=0.9, F=0.8,
+                                      seed=31, init=('random', [-400.] * 10, [400.] * 10),
+                                      bounds=([-400.] * 10, [400.] * 10, True), maxgen=15)
+    cs['griewangk10_rand1exp'] = dict(dim=10, NP=50, strategy='Rand1Exp', cost='griewangk', CR=0.3, F=1.0,
+                                      seed=32, init=('random', [-400.] * 10, [400.] * 10),
+                                      bounds=([-400.] * 10, [400.] * 10, False), maxgen=15)
+    # zimmermann (2-D only)
+    cs['zimmermann_rand1bin'] = dict(dim=2, NP=40, strategy='Rand1Bin', cost='zimmermann', CR=0.9, F=0.8,
+                                     seed=321, init=('random', [0.] * 2, [5.] * 2),
+                                     bounds=([0.] * 2, [5.] * 2, False), maxgen=20)
+    cs['zimmermann_best2bin'] = dict(dim=2, NP=20, strategy='Best2Bin', cost='zimmermann', CR=0.9, F=0.8,
+                                     seed=322, init=('random', [-5.] * 2, [10.] * 2), maxgen=15)
+    # chebyshev polynomial fit (examples/test_ffit.py:72-81: Best1Exp CR=1.0 F=0.9, init +-100)
+    cs['cheb8_best1exp'] = dict(dim=9, NP=36, strategy='Best1Exp', cost='chebyshev8cost', CR=1.0, F=0.9,
+                                seed=41, init=('random', [-100.] * 9, [100.] * 9), maxgen=12)
+    cs['cheb8_M128_best1bin'] = dict(dim=9, NP=36, strategy='Best1Bin', cost='chebyshev8cost', CR=0.9, F=0.8,
+                                     seed=42, init=('random', [-100.] * 9, [100.] * 9), maxgen=8,
+                                     ExtraArgs=[128])
+    cs['cheb4_rand2exp'] = dict(dim=5, NP=20, strategy='Rand2Exp', cost='chebyshev4cost', CR=0.8, F=0.7,
+                                seed=43, init=('random', [-10.] * 5, [10.] * 5), maxgen=8)
+    # stacked penalties of all four device-expressible kinds
+    cs['rosen6_stacked_pen'] = dict(dim=6, NP=24, strategy='RandToBest1Exp', cost='rosen', CR=0.9, F=0.8,
+                                    seed=51, init=('random', [-2.] * 6, [2.] * 6),
+                                    penalty=[dict(ptype='quadratic_inequality', G=[1., 1., 1., 1., 1., 1.], h=2., k=100, hpow=5),
+                                             dict(ptype='linear_equality', G=[1., -1., 0., 0., 0., 0.], h=0., k=10, hpow=5),
+                                             dict(ptype='quadratic_equality', G=[0., 0., 1., 0., 0., -2.], h=0.5, k=50, hpow=5),
+                                             dict(ptype='linear_inequality', G=[0., 0., 0., 1., 1., 0.], h=1., k=100, hpow=5)],
+                                    maxgen=10)
+    # edge cases: CR extremes, SetInitialPoints, NP raised to max(NP, dim, 4)
+    cs['edge_cr0_best1bin'] = dict(dim=5, NP=12, strategy='Best1Bin', cost='rosen', CR=0.0, F=0.8,
+                                   seed=61, init=('random', [-2.] * 5, [2.] * 5), maxgen=6)
+    cs['edge_cr0_rand1exp'] = dict(dim=5, NP=12, strategy='Rand1Exp', cost='rosen', CR=0.0, F=0.8,
+                                   seed=62, init=('random', [-2.] * 5, [2.] * 5), maxgen=6)
+    cs['edge_cr1_best2exp'] = dict(dim=5, NP=12, strategy='Best2Exp', cost='rosen', CR=1.0, F=0.5,
+                                   seed=63, init=('random', [-2.] * 5, [2.] * 5), maxgen=6)
+    cs['edge_x0_rosen2'] = dict(dim=2, NP=40, strategy='Rand1Bin', cost='rosen', CR=0.9, F=0.8,
+                                seed=123, init=('x0', [2., 3.], 0.05),
+                                bounds=([-5.] * 2, [5.] * 2, False), maxgen=30)
+    cs['edge_np_raised'] = dict(dim=7, NP=2, strategy='Rand2Bin', cost='rosen', CR=0.9, F=0.8,
+                                seed=64, init=('random', [-2.] * 7, [2.] * 7), maxgen=6)
+    cs['edge_dim1'] = dict(dim=1, NP=8, strategy='Best1Bin', cost='griewangk', CR=0.9, F=0.8,
+                           seed=65, init=('random', [-10.], [10.]), maxgen=6)
+    # wide rows (exercise multi-chunk row handling in the kernels): D not a multiple of 32/64
+    cs['wide_rosen100_best1bin'] = dict(dim=100, NP=100, strategy='Best1Bin', cost='rosen', CR=0.9, F=0.8,
+                                        seed=71, init=('random', [-5.] * 100, [5.] * 100),
+                                        bounds=([-5.] * 100, [5.] * 100, True), maxgen=4)
+    cs['wide_griewangk70_randtobest'] = dict(dim=70, NP=72, strategy='RandToBest1Bin', cost='griewangk', CR=0.9,
+                                             F=0.8, seed=72, init=('random', [-400.] * 70, [400.] * 70),
+                                             bounds=([-400.] * 70, [400.] * 70, False), maxgen=4)
+    cs['wide_corana64_rand1exp_pen'] = dict(dim=64, NP=64, strategy='Rand1Exp', cost='corana', CR=0.9, F=0.8,
+                                            seed=73, init=('random', [-1000.] * 64, [1000.] * 64),
+                                            bounds=([-1000.] * 64, [1000.] * 64, True),
+                                            penalty=[dict(ptype='quadratic_inequality', G=[1.] * 64, h=100., k=100, hpow=5)],
+                                            maxgen=4)
+    return cs
+
+
+def main(argv):
+    outdir = os.path.join(REPO, 'tests', 'golden')
+    os.makedirs(outdir, exist_ok=True)
+    cs = cases()
+    names = argv[1:] or sorted(cs)
+    for name in names:
+        data = record(cs[name])
+        path = os.path.join(outdir, name + '.npz')
+        np.savez_compressed(path, **data)
+        meta = json.loads(str(data['meta']))
+        print('%-32s G=%3d evals=%6d bestE=%.17g  %6.1f KiB' % (
+            name, meta['generations'], meta['evaluations'], data['bestE'][-1], os.path.getsize(path) / 1024.))
+
+
+if __name__ == '__main__':
+    main(sys.argv)

@@ -1,0 +1,42 @@
+"""Helpers shared by the oracle and GPU parity tests: load a recorded reference run."""
+import json
+import os
+
+import numpy as np
+
+from oracle import de_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def names():
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith('.npz'))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN, name + '.npz'))
+    meta = json.loads(str(z['meta']))
+    return meta, z
+
+
+def bounds_of(meta):
+    b = meta.get('bounds')
+    if b is None:
+        return None, None, orc.BOUNDS_NONE
+    lo, hi, tight = b
+    return np.asarray(lo, float), np.asarray(hi, float), (orc.BOUNDS_CLAMP if tight else orc.BOUNDS_REJECT)
+
+
+def bits(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64)).view(np.uint64)
+
+
+def assert_bits_equal(a, b, what=''):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    same = (bits(a) == bits(b)) | (np.isnan(a) & np.isnan(b)) | ((a == 0) & (b == 0))
+    if not same.all():
+        bad = np.argwhere(~same)
+        i = tuple(bad[0])
+        raise AssertionError('%s: %d mismatches, first at %s: %r vs %r' % (what, len(bad), i, a[i], b[i]))

@@ -1,0 +1,96 @@
+"""The CPU oracle (oracle/de_oracle.py) against recordings of the unmodified reference.
+
+Free-running: the oracle starts from the recorded initial population, consumes the
+reference's recorded draws generation by generation and must reproduce, BIT FOR BIT,
+every trial vector, trial energy, population, energy vector, best energy / solution and
+the evaluation counter of mystic.DifferentialEvolutionSolver2."""
+import numpy as np
+import pytest
+
+from oracle import de_oracle as orc
+from tests import _golden as G
+
+
+@pytest.mark.parametrize('name', G.names())
+def test_oracle_reproduces_reference(name):
+    meta, z = G.load(name)
+    lo, hi, mode = G.bounds_of(meta)
+    cost = orc.make_cost(meta['cost'], tuple(meta.get('ExtraArgs') or ()))
+    pen = meta.get('penalty') or ()
+    st = orc.DEState(z['pop0'], lo, hi, mode)
+    orc.step0(st, cost, pen)
+    ngen = meta['generations']
+    for g in range(ngen + 1):
+        if g > 0:
+            replay = dict(donors=z['donors'][g - 1], nstart=z['nstart'][g - 1], uni=z['uni'][g - 1])
+            orc.step(st, meta['strategy'], meta['CR_eff'], meta['F_eff'], cost, pen, replay=replay)
+        G.assert_bits_equal(st.trialSolution, z['trial'][g], '%s gen %d trial' % (name, g))
+        G.assert_bits_equal(st.population, z['pop'][g], '%s gen %d pop' % (name, g))
+        if meta['cost'] == 'griewangk':
+            # builtin sum() of the recording interpreter (3.12) is compensated for runs of
+            # exact floats; see oracle/de_oracle.py:cost_griewangk
+            for a, b in ((st.trialEnergy, z['trialE'][g]), (st.popEnergy, z['popE'][g]),
+                         (st.bestEnergy, z['bestE'][g])):
+                np.testing.assert_allclose(a, b, rtol=1e-14, atol=0)
+        else:
+            G.assert_bits_equal(st.trialEnergy, z['trialE'][g], '%s gen %d trialE' % (name, g))
+            G.assert_bits_equal(st.popEnergy, z['popE'][g], '%s gen %d popE' % (name, g))
+            G.assert_bits_equal(st.bestEnergy, z['bestE'][g], '%s gen %d bestE' % (name, g))
+        G.assert_bits_equal(st.bestSolution, z['bestX'][g], '%s gen %d bestX' % (name, g))
+        assert st.evaluations == int(z['evals'][g]), (name, g)
+    assert st.evaluations == meta['evaluations']
+
+
+def test_model_known_answers():
+    """SURVEY.md 8(c) known-answer vectors, produced by the reference in the build container."""
+    f = orc.make_cost
+    assert f('rosen')([[0.8, 1.2, 0.7]])[0] == 86.19999999999997
+    assert f('rosen')([[1., 1., 1.]])[0] == 0.0
+    assert f('rosen')([np.linspace(-2, 2, 7)])[0] == 3608.567901234568
+    assert f('corana')([[0.3, -0.7, 1.234, 5.0]])[0] == 859.6112499999999
+    assert f('corana')([[0.3, -0.7, 1.234, 5.0] + [9.0] * 60])[0] == 859.6112499999999
+    assert f('corana')([[0.04, -0.04, 0.01, 0.0]])[0] == 0.0
+    assert f('griewangk')([[1., 2., 3.]])[0] == 1.0170279701835734
+    assert f('griewangk')([[0.] * 10])[0] == 0.0
+    assert f('griewangk')([np.linspace(-400, 400, 10)])[0] == 164.05614975873598
+    assert f('zimmermann')([[7., 2.]])[0] == 0.0
+    assert f('zimmermann')([[1., 1.]])[0] == 7.0
+    assert f('zimmermann')([[-1., 6.]])[0] == 1600.0
+    assert f('chebyshev8cost')([orc.CHEBYSHEV_TARGETS[8]])[0] == 0.0
+    assert f('chebyshev8cost')([[1.] * 9])[0] == 7823.744334789609
+    assert f('chebyshev8cost', (4096,))([[1.] * 9])[0] == 22615.651073208195
+    assert f('chebyshev8cost', (4096,))([[100, -50, 3, 7, -20, 1, 0.5, -2, 1]])[0] == 2014464.4595239898
+    pen = [dict(ptype='quadratic_inequality', G=[1., 1., 1.], h=1.0, k=100, hpow=5)]
+    assert orc.penalty_value([[1., 1., 1.]], pen)[0] == 800.0
+    assert orc.penalty_value([[0., 0., 0.]], pen)[0] == 0.0
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in kat:
+        got = orc.philox4x32(*[np.uint32(c) for c in ctr], key[0], key[1])
+        assert tuple(int(g) for g in got) == want
+
+
+def test_philox_donors_are_valid_and_uniform():
+    NP, D = 11, 7
+    cand = np.arange(NP)
+    counts = np.zeros((NP, NP))
+    for gen in range(1, 400):
+        donors, nstart = orc.philox_donors(0x5EED, gen, cand, NP, D, 5)
+        assert ((donors >= 0) & (donors < NP)).all()
+        assert (donors != cand[:, None]).all()
+        srt = np.sort(donors, axis=1)
+        assert (srt[:, 1:] != srt[:, :-1]).all()
+        assert ((nstart >= 0) & (nstart < D)).all()
+        for c in range(NP):
+            counts[c, donors[c, 0]] += 1
+    off = counts[~np.eye(NP, dtype=bool)]
+    assert abs(off.mean() - 399 / 10.) < 1e-9
+    assert off.min() > 15 and off.max() < 70
