@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""Benchmark of the DE generation hot path (BASELINE.json metric: DE candidate-evals/sec,
+gen+cost+select).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3|c4|c5] [--impl reference]
+
+A "step" is one generation over the whole (per-GPU) population: trial generation + bounds + cost +
+penalty + selection + generation best (+ the best exchange when N > 1).  Prints ONE JSON line.
+Workloads:
+  c2  Rosenbrock 1024-D, NP=65536 per GPU, Best1Bin, bounds +-5 clamped (tight=True)   [default]
+  c4  Corana 64-D, NP=1M per GPU, Rand1Exp, clamp +-1000 + quadratic_inequality(sum(x)-100)
+  c5  Griewangk 256-D, NP=2M per GPU, Best1Bin, clamp +-400
+  c3  chebyshev8cost M=4096, D=9, NP=1M per GPU, Best1Exp CR=1.0 F=0.9 (Horner path)
+N > 1 shards by candidate, one rank per GPU, weak scaling (NP per GPU fixed), per-generation
+all-gather of the shard bests over NCCL.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    'c2': dict(desc='Rosenbrock 1024-D, NP=65536/GPU, Best1Bin CR=0.9 F=0.8, SetStrictRanges(+-5, tight=True)',
+               cost='rosen', extra=(), dim=1024, np=65536, strategy='Best1Bin', CR=0.9, F=0.8, lo=-5., hi=5.,
+               bounds='clamp', penalty=None, k=2),
+    'c2a': dict(desc='Rosenbrock 1024-D, NP=65536/GPU, Best1Bin, SetStrictRanges(+-5) reject mode (OOB -> inf)',
+                cost='rosen', extra=(), dim=1024, np=65536, strategy='Best1Bin', CR=0.9, F=0.8, lo=-5., hi=5.,
+                bounds='reject', penalty=None, k=2),
+    'c4': dict(desc='Corana 64-D, NP=1048576/GPU, Rand1Exp CR=0.9 F=0.8, clamp +-1000, quadratic_inequality(sum(x)-100)',
+               cost='corana', extra=(), dim=64, np=1048576, strategy='Rand1Exp', CR=0.9, F=0.8, lo=-1000., hi=1000.,
+               bounds='clamp', penalty=dict(G=1.0, h=100., k=100, hpow=5), k=3),
+    'c5': dict(desc='Griewangk 256-D, NP=2097152/GPU, Best1Bin CR=0.9 F=0.8, clamp +-400',
+               cost='griewangk', extra=(), dim=256, np=2097152, strategy='Best1Bin', CR=0.9, F=0.8, lo=-400.,
+               hi=400., bounds='clamp', penalty=None, k=2),
+    'c3': dict(desc='chebyshev8cost M=4096, 9 coeffs, NP=1048576/GPU, Best1Exp CR=1.0 F=0.9, init +-100 (Horner)',
+               cost='chebyshev8cost', extra=(4096,), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
+               lo=-100., hi=100., bounds=None, penalty=None, k=2),
+}
+
+BIN_STRATEGIES = ('Best1Bin',)
+
+
+def algorithmic_bytes_per_candidate(w):
+    """population double buffered; parent + k donor rows read, new row written,
+    energy read + written.  Exponential crossover reads only E[L] donor elements."""
+    D, k, CR = w['dim'], w['k'], w['CR']
+    if w['strategy'] in BIN_STRATEGIES:
+        return 8.0 * D * (k + 2) + 16.0
+    EL = float(D) if CR >= 1.0 else CR * (1.0 - CR ** D) / (1.0 - CR)
+    return 16.0 * D + 8.0 * k * EL + 16.0
+
+
+def algorithmic_flops_per_candidate(w):
+    if w['cost'].startswith('chebyshev'):
+        return 2.0 * w['dim'] * (w['extra'][0] + 2)
+    return None
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        super(ClockSampler, self).__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                      '--format=csv,noheader,nounits'], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, universal_newlines=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.splitlines()[0].split(',')])
+            except Exception:
+                pass
+            self._halt.wait(0.1)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return {'hbm_gbs': 6650.0}, 'fallback (B200_PROFILING.md)'
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle port on the host cores, bounded sample
+# ------------------------------------------------------------------------------------------
+def oracle_setup(w, NP, seed):
+    from oracle import de_oracle as orc
+    D = w['dim']
+    lo, hi = np.full(D, w['lo']), np.full(D, w['hi'])
+    mode = {None: orc.BOUNDS_NONE, 'clamp': orc.BOUNDS_CLAMP, 'reject': orc.BOUNDS_REJECT}[w['bounds']]
+    pen = ()
+    if w['penalty']:
+        p = w['penalty']
+        pen = [dict(ptype='quadratic_inequality', G=[p['G']] * D, h=p['h'], k=p['k'], hpow=p['hpow'])]
+    pop0 = orc.philox_init_population(seed, NP, lo, hi)
+    st = orc.DEState(pop0, lo if mode else None, hi if mode else None, mode)
+    cost = orc.make_cost(w['cost'], w['extra'])
+    orc.step0(st, cost, pen)
+    return orc, st, cost, pen
+
+
+def time_oracle(w, NP, steps, warmup, seed=0x5EED):
+    """-> (cand-evals/s, seconds per step, kind, cores, sample description)"""
+    try:
+        from oracle import c_port
+        if c_port.available():
+            return c_port.time_workload(w, NP, steps, warmup, seed)
+    except ImportError:
+        pass
+    orc, st, cost, pen = oracle_setup(w, NP, seed)
+    for _ in range(warmup):
+        orc.step(st, w['strategy'], w['CR'], w['F'], cost, pen, philox=dict(seed=seed, offset=0))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.step(st, w['strategy'], w['CR'], w['F'], cost, pen, philox=dict(seed=seed, offset=0))
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return NP / dt, dt, 'port', 1, 'numpy oracle port (oracle/de_oracle.py), NP=%d of %d rows, %d generations' % (
+        NP, w['np'], steps)
+
+
+def run_reference_arm(args, w):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    NP = min(w['np'], args.ref_np)
+    steps = max(1, args.steps)
+    value, dt, kind, cores, sample = time_oracle(w, NP, steps, max(1, min(args.warmup, 2)))
+    line = {
+        'impl': 'reference', 'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': value,
+        'unit': 'candidate-evals/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': w['desc'], 'sample_rows': NP},
+        'cpu_baseline': {'value': value, 'unit': 'candidate-evals/s', 'cores': cores, 'kind': kind, 'sample': sample},
+        'e2e': {'value': value, 'unit': 'candidate-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+def build_solver(w, NP_global, distributed, seed):
+    from mystic_b200 import DifferentialEvolutionSolver2, penalty
+    D = w['dim']
+    s = DifferentialEvolutionSolver2(D, NP_global, rng='philox', seed=seed, distributed=distributed,
+                                     CrossProbability=w['CR'], ScalingFactor=w['F'], strategy=w['strategy'])
+    if w['bounds'] == 'clamp':
+        s.SetStrictRanges([w['lo']] * D, [w['hi']] * D, tight=True)
+    elif w['bounds'] == 'reject':
+        s.SetStrictRanges([w['lo']] * D, [w['hi']] * D)
+    if w['penalty']:
+        p = w['penalty']
+
+        @penalty.quadratic_inequality(penalty.linear([p['G']] * D, p['h']), k=p['k'], h=p['hpow'])
+        def pen(x):
+            return 0.0
+        s.SetPenalty(pen)
+    s.SetEvaluationLimits(generations=10 ** 9, evaluations=10 ** 18)
+    return s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--np', type=int, default=0, help='override rows per GPU (testing)')
+    ap.add_argument('--ref-np', type=int, default=4096, help='rows of the bounded CPU sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.np:
+        w['np'] = args.np
+
+    if args.impl == 'reference':
+        run_reference_arm(args, w)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mystic_b200 import models, termination
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the engine has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+    warmup = max(3, args.warmup)
+    steps = max(1, args.steps)
+    NP_local = w['np']
+    NP_global = NP_local * world
+    D = w['dim']
+    seed = 0x5EED
+    cost = getattr(models, w['cost'])
+    extra = tuple(w['extra']) or None
+    never = termination.VTR(-1.0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-resident throughput: population generated on the device, K generations timed
+    s = build_solver(w, NP_global, distributed, seed)
+    s.SetRandomInitialPoints([w['lo']] * D, [w['hi']] * D)
+    s.SetTermination(never)
+    s.Step(cost, ExtraArgs=extra)               # generation 0 (allocates, initialises, evaluates)
+    for _ in range(warmup):
+        s.Step()
+    eng = s._engine
+    grid, block, smem = eng.launch_info()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        eng.step()                               # K2 + K3 on torch's current stream
+        if distributed:
+            s._exchange_best()
+    ev1.record()
+    barrier()
+    launches = eng.launch_count() - launches0
+    dev_ms = ev0.elapsed_time(ev1)
+    # ---- the same K generations through the public API (Step(): + D2H of the best, bookkeeping,
+    #      termination checks, monitor) -- used for e2e below together with the H2D of the population
+    t = torch.tensor([dev_ms], dtype=torch.float64, device='cuda')
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    inf_frac = s._last[0] / float(NP_global) if s._last else 0.0
+    acc_frac = s._last[1] / float(NP_global) if s._last else 0.0
+    clocks = sampler.stop() if sampler else None
+    del s, eng
+    torch.cuda.empty_cache()
+
+    # ---- end to end: host population (pinned) -> H2D -> generation 0 -> K x Step() with the result
+    #      of every step read back to the host
+    host_pop = torch.empty((NP_local, D), dtype=torch.float64).pin_memory()
+    rng = np.random.default_rng(seed + rank)
+    hp = host_pop.numpy()
+    chunk = max(1, (1 << 24) // D)
+    for i in range(0, NP_local, chunk):
+        hp[i:i + chunk] = rng.uniform(w['lo'], w['hi'], size=(min(chunk, NP_local - i), D))
+    s2 = build_solver(w, NP_global, distributed, seed)
+    s2.SetTermination(never)
+    barrier()
+    t0 = time.perf_counter()
+    s2.SetPopulation(hp, local=True)             # this rank's rows; pinned, uploaded as is
+    s2.Step(cost, ExtraArgs=extra)               # H2D upload + generation 0
+    for _ in range(steps):
+        s2.Step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    d2h_per_step = 8 * D + 40
+    h2d_per_step = NP_local * D * 8.0 / steps
+    del s2
+    torch.cuda.empty_cache()
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return
+
+    value = NP_global * steps / (dev_ms * 1e-3)
+    peaks, peaks_src = measured_peaks()
+    bpc = algorithmic_bytes_per_candidate(w)
+    step_s = dev_ms * 1e-3 / steps
+    achieved = bpc * NP_local / step_s / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks_src,
+                'algorithmic_bytes_per_candidate': bpc,
+                'kernel': 'de_step_kernel (fused generation) + de_finalize_kernel, per generation, per GPU'}
+    flops = algorithmic_flops_per_candidate(w)
+    if flops:
+        roofline['fp64_tflops_achieved'] = flops * NP_local / step_s / 1e12
+
+    line = {
+        'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': value, 'unit': 'candidate-evals/s',
+        'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': w['desc'], 'np_per_gpu': NP_local, 'np_total': NP_global, 'dim': D,
+                   'rng': 'philox4x32-10 in-kernel', 'l2': 'inputs larger than L2 (population %.0f MiB per buffer)'
+                   % (NP_local * D * 8 / 2 ** 20), 'grid': grid, 'block': block, 'smem_bytes': smem,
+                   'inf_fraction': inf_frac, 'accept_fraction': acc_frac,
+                   'parallelism': 'candidate-sharded x%d, all-gather best per generation' % world if distributed
+                   else 'single GPU'},
+        'roofline': roofline,
+        'e2e': {'value': NP_global * steps / e2e_s, 'unit': 'candidate-evals/s',
+                'h2d_bytes_per_step': h2d_per_step, 'd2h_bytes_per_step': d2h_per_step,
+                'what': 'pinned host population -> H2D -> generation 0 -> %d x solver.Step() (best read back to the '
+                        'host, termination + monitor every step); only the %d generations are counted' % (steps, steps)},
+        'gpu_launches': int(launches),
+        'clocks': clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, dt, kind, cores, sample = time_oracle(w, min(w['np'], args.ref_np), 3, 1)
+        line['cpu_baseline'] = {'value': v, 'unit': 'candidate-evals/s', 'cores': cores, 'kind': kind, 'sample': sample}
+    print(json.dumps(line))
+    if distributed:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,171 @@
+/*
+ * mystic_b200.h -- C ABI of the B200-native differential-evolution generation engine.
+ *
+ * Drop-in boundary for the hot path of mystic's DifferentialEvolutionSolver2
+ * (reference: mystic/differential_evolution.py:531-625, `_Step`).  The reference has no
+ * FFI of its own (it is pure Python); this header is what a binding for that path binds.
+ * Each entry point cites the reference code it replaces (paths relative to the mystic
+ * repository root).  The Python host mirror (mystic_b200/solver.py) calls exactly these
+ * symbols through ctypes; see INTEGRATION.md for the reference-side stub.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative MB2_E* code on failure; the message is
+ *     available from mb2_last_error() (thread local).  No exceptions cross the boundary.
+ *   - `*_dev` pointers are device pointers owned by the caller (torch tensors in the Python
+ *     host); `*_host` pointers are host pointers and are copied before the call returns.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls that
+ *     take a stream are asynchronous on it unless stated otherwise.
+ *   - a context is bound to one device and used from one host thread at a time.
+ *   - all floating-point data is IEEE binary64; the population is [np_local, dim] row-major
+ *     (the reference's list-of-lists `population[NP][D]`, mystic/abstract_solver.py:118-120).
+ */
+#ifndef MYSTIC_B200_H
+#define MYSTIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MB2_ABI_VERSION 1
+
+/* error codes */
+#define MB2_OK 0
+#define MB2_EINVAL (-1)   /* bad argument / unsupported combination */
+#define MB2_ECUDA (-2)    /* a CUDA runtime call failed */
+#define MB2_ESTATE (-3)   /* call order violated (e.g. step before bind_buffers) */
+
+/* mystic/strategy.py -- ids in file order.  Only Best1Bin is binomial in the reference; the
+ * other *Bin names run the exponential loop (strategy.py:203-311). */
+enum mb2_strategy {
+  MB2_BEST1EXP = 0,       /* strategy.py:34-59   */
+  MB2_BEST1BIN = 1,       /* strategy.py:61-88   */
+  MB2_RAND1EXP = 2,       /* strategy.py:90-115  */
+  MB2_RANDTOBEST1EXP = 3, /* strategy.py:119-145 */
+  MB2_BEST2EXP = 4,       /* strategy.py:147-173 */
+  MB2_RAND2EXP = 5,       /* strategy.py:175-201 */
+  MB2_RAND1BIN = 6,       /* strategy.py:203-227 */
+  MB2_RANDTOBEST1BIN = 7, /* strategy.py:229-255 */
+  MB2_BEST2BIN = 8,       /* strategy.py:257-283 */
+  MB2_RAND2BIN = 9        /* strategy.py:285-311 */
+};
+
+/* mystic/models -- batched device cost functions */
+enum mb2_cost {
+  MB2_COST_ROSEN = 0,      /* models/dejong.py:89-101 */
+  MB2_COST_CORANA = 1,     /* models/storn.py:57-96   */
+  MB2_COST_GRIEWANGK = 2,  /* models/storn.py:120-139 */
+  MB2_COST_ZIMMERMANN = 3, /* models/storn.py:161-191 */
+  MB2_COST_CHEBYSHEV = 4,  /* models/_model_helper.py:16-33, Horner (math/poly.py:37-39), bit-faithful px */
+  MB2_COST_CHEBYSHEV_MMA = 5 /* same cost, [NP x D]*[D x M] contraction on FP64 tensor cores (DMMA) */
+};
+
+/* SetStrictRanges modes (abstract_solver.py:334-448, tools.py:404-430) */
+enum mb2_bounds {
+  MB2_BOUNDS_NONE = 0,   /* no strict range */
+  MB2_BOUNDS_REJECT = 1, /* default SetStrictRanges: out-of-range trial -> energy inf, cost not evaluated */
+  MB2_BOUNDS_CLAMP = 2   /* tight=True: x[i]=max(lo,x[i]); x[i]=min(hi,x[i]) before the cost (symbolic.py:1139-1144) */
+};
+
+/* mystic/penalty.py decorators whose condition is linear, G.x - h */
+enum mb2_penalty {
+  MB2_PEN_QUADRATIC_EQUALITY = 0,   /* penalty.py:41-98   : k*pf^2        */
+  MB2_PEN_LINEAR_EQUALITY = 1,      /* penalty.py:100-157 : k*|pf|        */
+  MB2_PEN_QUADRATIC_INEQUALITY = 2, /* penalty.py:341-398 : 2k*max(0,pf)^2 */
+  MB2_PEN_LINEAR_INEQUALITY = 3     /* penalty.py:400-457 : 2k*|max(0,pf)| */
+};
+
+typedef struct mb2_ctx mb2_ctx;
+
+/* result of one generation, as the host part of `_Step` needs it
+ * (differential_evolution.py:596-617: fcalls bookkeeping, bestEnergy, stepmon) */
+typedef struct mb2_result {
+  double best_energy;   /* solver.bestEnergy after the generation                               */
+  int64_t best_index;   /* GLOBAL index of the member that last became best, -1 if none yet      */
+  int64_t n_inf;        /* trial energies equal to +-inf in this generation (:601 `isinf().sum()`) */
+  int64_t n_accepted;   /* trials that replaced their parent (:604)                               */
+  int64_t generation;   /* 0 = initial population evaluated                                      */
+} mb2_result;
+
+int mb2_abi_version(void);
+const char* mb2_last_error(void);
+
+/* One context per device shard.  Replaces the per-solver state of AbstractSolver.__init__
+ * (abstract_solver.py:92-150): nDim, nPop, popEnergy=[inf]*NP, bestEnergy, bestSolution.
+ * np_local rows live on this device; they are rows [global_offset, global_offset+np_local)
+ * of a population of np_global rows (single GPU: np_local == np_global, offset 0). */
+int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset,
+               mb2_ctx** out);
+int mb2_destroy(mb2_ctx* ctx);
+
+/* Double-buffered population and energies (the reference keeps `population` and
+ * `trialSolution`, abstract_map_solver.py:113-114).  pop_a is the current generation. */
+int mb2_bind_buffers(mb2_ctx* ctx, double* pop_a_dev, double* pop_b_dev, double* energy_a_dev,
+                     double* energy_b_dev);
+/* device pointers of the CURRENT generation (they swap every step) */
+int mb2_current(mb2_ctx* ctx, double** pop_dev, double** energy_dev);
+
+/* differential_evolution.py:460-462, 676-693: strategy, ScalingFactor, CrossProbability */
+int mb2_set_strategy(mb2_ctx* ctx, int strategy, double scale, double cross);
+/* abstract_solver.py:334-405 SetStrictRanges; lo/hi have `dim` entries (ignored for NONE) */
+int mb2_set_bounds(mb2_ctx* ctx, int mode, const double* lo_host, const double* hi_host);
+/* cost(x, *ExtraArgs): params for CHEBYSHEV* = {M, order, target coeffs[order+1]} */
+int mb2_set_cost(mb2_ctx* ctx, int cost, const double* params_host, int32_t nparams);
+/* stacked penalty decorators, term 0 innermost (penalty.py:80-98 `dec`); G is [nterms, dim],
+ * kscale[i] = k*h**n (the decorator's current multiplier before the inequality factor 2) */
+int mb2_set_penalty(mb2_ctx* ctx, int32_t nterms, const int32_t* ptype_host, const double* G_host,
+                    const double* h_host, const double* kscale_host);
+
+/* Random draws.  Philox4x32-10 counter RNG keyed by `seed`, counter = (block, global candidate,
+ * generation, stream) -- replaces random.sample / random.randrange / random.random of
+ * strategy.py:27,42,49 in production mode. */
+int mb2_set_rng_philox(mb2_ctx* ctx, uint64_t seed);
+/* Validation mode: consume the reference's own recorded draws for the NEXT mb2_step call.
+ * donors [np_local,5] int32 (unused = -1), nstart [np_local] int32, uniforms [np_local, dim+1]
+ * float64 with NaN for draws the reference did not make. */
+int mb2_set_rng_replay(mb2_ctx* ctx, const int32_t* donors_dev, const int32_t* nstart_dev,
+                       const double* uniforms_dev);
+
+/* abstract_solver.py:508-535 SetRandomInitialPoints, generated on the device (Philox stream 2)
+ * into the current population buffer; resets energies to +inf. */
+int mb2_init_population(mb2_ctx* ctx, uint64_t seed, const double* lo_host, const double* hi_host,
+                        void* stream);
+/* host population [np_local, dim] -> current buffer (validation / small problems); resets
+ * energies to +inf.  Synchronous w.r.t. the host buffer. */
+int mb2_upload_population(mb2_ctx* ctx, const double* pop_host, void* stream);
+/* optional capture of every trial vector / trial energy of the next steps (NULL disables) */
+int mb2_set_capture(mb2_ctx* ctx, double* trial_dev, double* trial_energy_dev);
+
+/* generation 0: differential_evolution.py:516-520 (clip into the strict range), :559-567,
+ * :575-582 with strategy=None, :589, :603-613 */
+int mb2_eval_initial(mb2_ctx* ctx, void* stream);
+/* one generation g>=1: trial generation (:574-582 + strategy.py), bounds, cost (:589),
+ * penalty, selection and generation best (:603-613) in ONE fused kernel + a 1-CTA argmin */
+int mb2_step(mb2_ctx* ctx, void* stream);
+
+/* multi-GPU best exchange (Best and RandToBest strategies read the global best,
+ * strategy.py:52,83,137,164,247,274): pack this shard's [best_energy, best_index(global),
+ * n_inf, n_accepted, bestSolution[dim]] (dim+4 doubles) for an all-gather, then merge the
+ * gathered [world, dim+4] records: lowest energy wins, ties to the lowest global index
+ * (differential_evolution.py:611 strict '<' in ascending candidate order). */
+int mb2_pack_best(mb2_ctx* ctx, double* record_dev, void* stream);
+int mb2_merge_best(mb2_ctx* ctx, const double* records_dev, int32_t world, void* stream);
+
+/* synchronises `stream`, then returns the generation result and bestSolution (dim doubles;
+ * x_host may be NULL) */
+int mb2_read_result(mb2_ctx* ctx, mb2_result* out, double* x_host, void* stream);
+
+/* the decorated cost of differential_evolution.py:515-525 for n arbitrary rows:
+ * (inf if out of the strict range else cost(x)) + penalty(x).  x_dev [n, dim], out_dev [n]. */
+int mb2_eval_cost(mb2_ctx* ctx, const double* x_dev, int64_t n, double* out_dev, void* stream);
+
+/* launch geometry of the fused kernel (for bench.py / profiling): CTAs, threads, dynamic smem */
+int mb2_launch_info(mb2_ctx* ctx, int32_t* grid, int32_t* block, int32_t* smem_bytes);
+/* number of kernels this library has launched through the context (bench.py gpu_launches) */
+int64_t mb2_launch_count(mb2_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MYSTIC_B200_H */

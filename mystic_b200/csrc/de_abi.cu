@@ -1,0 +1,584 @@
+// C ABI of the engine (include/mystic_b200.h): context management, launch geometry and the
+// dispatch of the fused generation kernel over <base vector, crossover, cost, vector width>.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/mystic_b200.h"
+#include "de_kernels.cuh"
+
+using namespace mb2;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess)                                                                      \
+      return fail(MB2_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+struct StrategyInfo {
+  int base, xover, k;
+};
+
+bool strategy_info(int s, StrategyInfo* out) {
+  switch (s) {
+    case MB2_BEST1EXP: *out = {BASE_BEST1, XOVER_EXP, 2}; return true;
+    case MB2_BEST1BIN: *out = {BASE_BEST1, XOVER_BIN, 2}; return true;
+    case MB2_RAND1EXP:
+    case MB2_RAND1BIN: *out = {BASE_RAND1, XOVER_EXP, 3}; return true;
+    case MB2_RANDTOBEST1EXP:
+    case MB2_RANDTOBEST1BIN: *out = {BASE_RANDTOBEST1, XOVER_EXP, 2}; return true;
+    case MB2_BEST2EXP:
+    case MB2_BEST2BIN: *out = {BASE_BEST2, XOVER_EXP, 4}; return true;
+    case MB2_RAND2EXP:
+    case MB2_RAND2BIN: *out = {BASE_RAND2, XOVER_EXP, 5}; return true;
+  }
+  return false;
+}
+
+}  // namespace
+
+struct mb2_ctx {
+  int device = 0;
+  int sm_count = 0;
+  int64_t np = 0, np_global = 0, offset = 0;
+  int dim = 0, dim_pad = 0;
+  double* pop[2] = {nullptr, nullptr};
+  double* en[2] = {nullptr, nullptr};
+  int cur = 0;
+  int strategy = MB2_BEST1BIN;
+  StrategyInfo sinfo = {BASE_BEST1, XOVER_BIN, 2};
+  double F = 0.8, CR = 0.9;
+  int bounds_mode = BOUNDS_NONE;
+  double* lo = nullptr;
+  double* hi = nullptr;
+  int cost = MB2_COST_ROSEN;
+  CostParams cp = {0, nullptr, 0.0, 0.0};
+  double* cheb_x = nullptr;
+  PenaltyParams pp = {0, nullptr, nullptr, nullptr, nullptr};
+  int* pen_type = nullptr;
+  double* pen_G = nullptr;
+  double* pen_h = nullptr;
+  double* pen_k = nullptr;
+  uint64_t seed = 0;
+  int replay = 0;
+  const int32_t* r_donors = nullptr;
+  const int32_t* r_nstart = nullptr;
+  const double* r_uni = nullptr;
+  double* best_x = nullptr;
+  DeviceState* st = nullptr;
+  double* part_e = nullptr;
+  int64_t* part_idx = nullptr;
+  unsigned long long* part_ninf = nullptr;
+  unsigned long long* part_nacc = nullptr;
+  int parts_cap = 0;
+  double* cap_trial = nullptr;
+  double* cap_energy = nullptr;
+  DeviceState* h_st = nullptr;  // pinned
+  double* h_best_x = nullptr;   // pinned
+  int64_t generation = -1;      // last generation evaluated
+  int64_t launches = 0;
+  // launch geometry of the fused kernel
+  int wpc = 8, grid = 0, smem = 0;
+};
+
+namespace {
+
+typedef void (*StepKernel)(const StepParams);
+
+template <int BASE, int XOVER, int COST>
+StepKernel pick_vec(bool vec) {
+  return vec ? (StepKernel)de_step_kernel<BASE, XOVER, COST, true> : (StepKernel)de_step_kernel<BASE, XOVER, COST, false>;
+}
+
+template <int BASE, int XOVER>
+StepKernel pick_cost(int cost, bool vec) {
+  switch (cost) {
+    case MB2_COST_ROSEN: return pick_vec<BASE, XOVER, COST_ROSEN>(vec);
+    case MB2_COST_CORANA: return pick_vec<BASE, XOVER, COST_CORANA>(vec);
+    case MB2_COST_GRIEWANGK: return pick_vec<BASE, XOVER, COST_GRIEWANGK>(vec);
+    case MB2_COST_ZIMMERMANN: return pick_vec<BASE, XOVER, COST_ZIMMERMANN>(vec);
+    case MB2_COST_CHEBYSHEV: return pick_vec<BASE, XOVER, COST_CHEBYSHEV>(vec);
+  }
+  return nullptr;
+}
+
+StepKernel pick_kernel(const StrategyInfo& s, int cost, bool vec) {
+  if (s.xover == XOVER_BIN) return pick_cost<BASE_BEST1, XOVER_BIN>(cost, vec);
+  switch (s.base) {
+    case BASE_BEST1: return pick_cost<BASE_BEST1, XOVER_EXP>(cost, vec);
+    case BASE_RAND1: return pick_cost<BASE_RAND1, XOVER_EXP>(cost, vec);
+    case BASE_RANDTOBEST1: return pick_cost<BASE_RANDTOBEST1, XOVER_EXP>(cost, vec);
+    case BASE_BEST2: return pick_cost<BASE_BEST2, XOVER_EXP>(cost, vec);
+    case BASE_RAND2: return pick_cost<BASE_RAND2, XOVER_EXP>(cost, vec);
+  }
+  return nullptr;
+}
+
+// warps per CTA and dynamic shared memory for a row length
+void geometry(int dim_pad, int* wpc, int* smem) {
+  const size_t row = (size_t)dim_pad * sizeof(double);
+  int w = kWarpsPerCtaMax;
+  // keep >= 2 CTAs per SM resident when the rows allow it (227 KB per SM)
+  while (w > 1 && (size_t)(w + 1) * row > 100 * 1024) w >>= 1;
+  *wpc = w;
+  *smem = (int)((size_t)(w + 1) * row);
+}
+
+int ensure_parts(mb2_ctx* c, int n) {
+  if (n <= c->parts_cap) return MB2_OK;
+  cudaFree(c->part_e);
+  cudaFree(c->part_idx);
+  cudaFree(c->part_ninf);
+  cudaFree(c->part_nacc);
+  c->part_e = nullptr;
+  c->part_idx = nullptr;
+  c->part_ninf = nullptr;
+  c->part_nacc = nullptr;
+  c->parts_cap = 0;
+  CUDA_TRY(cudaMalloc(&c->part_e, sizeof(double) * n));
+  CUDA_TRY(cudaMalloc(&c->part_idx, sizeof(int64_t) * n));
+  CUDA_TRY(cudaMalloc(&c->part_ninf, sizeof(unsigned long long) * n));
+  CUDA_TRY(cudaMalloc(&c->part_nacc, sizeof(unsigned long long) * n));
+  c->parts_cap = n;
+  return MB2_OK;
+}
+
+// configure + launch the fused kernel in `mode` over `np` rows
+int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out,
+                int64_t np, cudaStream_t stream) {
+  const bool vec = (c->dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(in_rows) & 15) == 0) &&
+                   (out_rows == nullptr || (reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
+  StrategyInfo s = c->sinfo;
+  if (mode != MODE_STEP) s = {BASE_RAND1, XOVER_EXP, 3};  // no best/donors needed; any instance
+  StepKernel k = pick_kernel(s, c->cost, vec);
+  if (k == nullptr) return fail(MB2_EINVAL, "no kernel for strategy %d cost %d", c->strategy, c->cost);
+
+  int wpc, smem;
+  geometry(c->dim_pad, &wpc, &smem);
+  if (smem > 227 * 1024) return fail(MB2_EINVAL, "dim %d too large for one warp-resident row", c->dim);
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int occ = 0;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));
+  if (occ < 1) return fail(MB2_EINVAL, "kernel does not fit on an SM (smem %d)", smem);
+  int64_t need = (np + wpc - 1) / wpc;
+  int64_t grid = (int64_t)c->sm_count * occ;
+  if (grid > need) grid = need;
+  if (grid < 1) grid = 1;
+  if (int rc = ensure_parts(c, (int)grid)) return rc;
+
+  StepParams P;
+  memset(&P, 0, sizeof(P));
+  P.pop_cur = in_rows;
+  P.pop_next = out_rows;
+  P.e_cur = e_in;
+  P.e_next = e_out;
+  P.best_x = c->best_x;
+  P.lo = c->lo;
+  P.hi = c->hi;
+  P.np = np;
+  P.global_offset = c->offset;
+  P.dim = c->dim;
+  P.dim_pad = c->dim_pad;
+  P.mode = mode;
+  P.bounds_mode = c->bounds_mode;
+  P.F = c->F;
+  P.CR = c->CR;
+  P.replay = (mode == MODE_STEP) ? c->replay : 0;
+  P.key0 = (uint32_t)(c->seed & 0xffffffffu);
+  P.key1 = (uint32_t)(c->seed >> 32);
+  P.generation = (uint32_t)(c->generation + 1);
+  P.thr = crossover_threshold(c->CR);
+  P.r_donors = c->r_donors;
+  P.r_nstart = c->r_nstart;
+  P.r_uni = c->r_uni;
+  P.cost = c->cp;
+  P.pen = c->pp;
+  P.part_e = c->part_e;
+  P.part_idx = c->part_idx;
+  P.part_ninf = c->part_ninf;
+  P.part_nacc = c->part_nacc;
+  P.cap_trial = c->cap_trial;
+  P.cap_energy = c->cap_energy;
+
+  c->wpc = wpc;
+  c->grid = (int)grid;
+  c->smem = smem;
+  k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
+}
+
+int launch_finalize(mb2_ctx* c, int gen0, cudaStream_t stream) {
+  de_finalize_kernel<<<1, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
+                                            c->pop[c->cur ^ 1], c->dim, c->offset, gen0, c->generation + 1,
+                                            c->best_x, c->st);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mb2_abi_version(void) { return MB2_ABI_VERSION; }
+
+const char* mb2_last_error(void) { return g_err; }
+
+int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset, mb2_ctx** out) {
+  if (out == nullptr) return fail(MB2_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (np_local < 1 || dim < 1 || np_global < np_local || global_offset < 0 || global_offset + np_local > np_global)
+    return fail(MB2_EINVAL, "bad shape np_local=%lld dim=%d np_global=%lld offset=%lld", (long long)np_local, dim,
+                (long long)np_global, (long long)global_offset);
+  if (np_global > 0xffffffffll) return fail(MB2_EINVAL, "np_global exceeds the 32-bit Philox candidate counter");
+  CUDA_TRY(cudaSetDevice(device));
+  mb2_ctx* c = new (std::nothrow) mb2_ctx();
+  if (c == nullptr) return fail(MB2_EINVAL, "out of host memory");
+  c->device = device;
+  c->np = np_local;
+  c->np_global = np_global;
+  c->offset = global_offset;
+  c->dim = dim;
+  c->dim_pad = (dim + 3) & ~3;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    delete c;
+    return fail(MB2_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  }
+  c->sm_count = prop.multiProcessorCount;
+  bool ok = cudaMalloc(&c->best_x, sizeof(double) * dim) == cudaSuccess &&
+            cudaMalloc(&c->st, sizeof(DeviceState)) == cudaSuccess &&
+            cudaMalloc(&c->lo, sizeof(double) * dim) == cudaSuccess &&
+            cudaMalloc(&c->hi, sizeof(double) * dim) == cudaSuccess &&
+            cudaMallocHost(&c->h_st, sizeof(DeviceState)) == cudaSuccess &&
+            cudaMallocHost(&c->h_best_x, sizeof(double) * dim) == cudaSuccess;
+  if (ok) {
+    DeviceState init = {INFINITY, -1, 0, 0, -1};
+    ok = cudaMemcpy(c->st, &init, sizeof(init), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemset(c->best_x, 0, sizeof(double) * dim) == cudaSuccess;
+  }
+  if (!ok) {
+    const char* msg = cudaGetErrorString(cudaGetLastError());
+    mb2_destroy(c);
+    return fail(MB2_ECUDA, "context allocation failed: %s", msg);
+  }
+  *out = c;
+  return MB2_OK;
+}
+
+int mb2_destroy(mb2_ctx* c) {
+  if (c == nullptr) return MB2_OK;
+  cudaSetDevice(c->device);
+  cudaFree(c->best_x);
+  cudaFree(c->st);
+  cudaFree(c->lo);
+  cudaFree(c->hi);
+  cudaFree(c->cheb_x);
+  cudaFree(c->pen_type);
+  cudaFree(c->pen_G);
+  cudaFree(c->pen_h);
+  cudaFree(c->pen_k);
+  cudaFree(c->part_e);
+  cudaFree(c->part_idx);
+  cudaFree(c->part_ninf);
+  cudaFree(c->part_nacc);
+  cudaFreeHost(c->h_st);
+  cudaFreeHost(c->h_best_x);
+  delete c;
+  return MB2_OK;
+}
+
+int mb2_bind_buffers(mb2_ctx* c, double* pop_a, double* pop_b, double* e_a, double* e_b) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (!pop_a || !pop_b || !e_a || !e_b || pop_a == pop_b || e_a == e_b)
+    return fail(MB2_EINVAL, "need four distinct device buffers");
+  c->pop[0] = pop_a;
+  c->pop[1] = pop_b;
+  c->en[0] = e_a;
+  c->en[1] = e_b;
+  c->cur = 0;
+  c->generation = -1;
+  return MB2_OK;
+}
+
+int mb2_current(mb2_ctx* c, double** pop, double** energy) {
+  if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
+  if (pop) *pop = c->pop[c->cur];
+  if (energy) *energy = c->en[c->cur];
+  return MB2_OK;
+}
+
+int mb2_set_strategy(mb2_ctx* c, int strategy, double scale, double cross) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  StrategyInfo s;
+  if (!strategy_info(strategy, &s)) return fail(MB2_EINVAL, "unknown strategy id %d", strategy);
+  if (c->np < s.k + 1)
+    return fail(MB2_EINVAL, "strategy needs %d distinct donors but the shard has only %lld other members", s.k,
+                (long long)(c->np - 1));
+  c->strategy = strategy;
+  c->sinfo = s;
+  c->F = scale;
+  c->CR = cross;
+  return MB2_OK;
+}
+
+int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (mode < BOUNDS_NONE || mode > BOUNDS_CLAMP) return fail(MB2_EINVAL, "unknown bounds mode %d", mode);
+  if (mode != BOUNDS_NONE) {
+    if (!lo || !hi) return fail(MB2_EINVAL, "bounds arrays are NULL");
+    for (int i = 0; i < c->dim; ++i)
+      if (lo[i] > hi[i]) return fail(MB2_EINVAL, "each min[i] must be <= the corresponding max[i]");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMemcpy(c->lo, lo, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->hi, hi, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
+  }
+  c->bounds_mode = mode;
+  return MB2_OK;
+}
+
+int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (cost < MB2_COST_ROSEN || cost > MB2_COST_CHEBYSHEV_MMA) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (cost == MB2_COST_ZIMMERMANN && c->dim != 2) return fail(MB2_EINVAL, "zimmermann requires dim == 2");
+  if (cost == MB2_COST_CHEBYSHEV_MMA) return fail(MB2_EINVAL, "chebyshev DMMA cost is not available in this build");
+  if (cost == MB2_COST_CHEBYSHEV) {
+    if (!params || nparams < 3) return fail(MB2_EINVAL, "chebyshev params = {M, order, target[order+1]}");
+    const int M = (int)params[0], order = (int)params[1];
+    if (M < 2 || order < 0 || nparams != order + 3) return fail(MB2_EINVAL, "bad chebyshev params (M=%d order=%d)", M, order);
+    // abscissae exactly as the reference accumulates them (_model_helper.py:19-25)
+    std::vector<double> xs(M);
+    volatile double x = -1.0;
+    const double dx = 2.0 / (double)(M - 1);
+    for (int i = 0; i < M; ++i) {
+      xs[i] = x;
+      x = x + dx;
+    }
+    // polyeval(target, +-1.2), math/poly.py:37-39
+    double tp, tm;
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      const double xe = sgn ? -1.2 : 1.2;
+      volatile double val = 0.0 * xe;
+      for (int j = 0; j <= order; ++j) {
+        volatile double prod = val * xe;
+        val = params[2 + j] + prod;
+      }
+      if (sgn) tm = val; else tp = val;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    cudaFree(c->cheb_x);
+    c->cheb_x = nullptr;
+    CUDA_TRY(cudaMalloc(&c->cheb_x, sizeof(double) * M));
+    CUDA_TRY(cudaMemcpy(c->cheb_x, xs.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
+    c->cp.cheb_M = M;
+    c->cp.cheb_x = c->cheb_x;
+    c->cp.cheb_tp = tp;
+    c->cp.cheb_tm = tm;
+  }
+  c->cost = cost;
+  return MB2_OK;
+}
+
+int mb2_set_penalty(mb2_ctx* c, int32_t nterms, const int32_t* ptype, const double* G, const double* h,
+                    const double* kscale) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (nterms < 0) return fail(MB2_EINVAL, "nterms < 0");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaFree(c->pen_type);
+  cudaFree(c->pen_G);
+  cudaFree(c->pen_h);
+  cudaFree(c->pen_k);
+  c->pen_type = nullptr;
+  c->pen_G = nullptr;
+  c->pen_h = nullptr;
+  c->pen_k = nullptr;
+  c->pp = {0, nullptr, nullptr, nullptr, nullptr};
+  if (nterms == 0) return MB2_OK;
+  if (!ptype || !G || !h || !kscale) return fail(MB2_EINVAL, "penalty arrays are NULL");
+  for (int i = 0; i < nterms; ++i)
+    if (ptype[i] < 0 || ptype[i] > 3) return fail(MB2_EINVAL, "unknown penalty type %d", ptype[i]);
+  CUDA_TRY(cudaMalloc(&c->pen_type, sizeof(int) * nterms));
+  CUDA_TRY(cudaMalloc(&c->pen_G, sizeof(double) * nterms * c->dim));
+  CUDA_TRY(cudaMalloc(&c->pen_h, sizeof(double) * nterms));
+  CUDA_TRY(cudaMalloc(&c->pen_k, sizeof(double) * nterms));
+  CUDA_TRY(cudaMemcpy(c->pen_type, ptype, sizeof(int) * nterms, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->pen_G, G, sizeof(double) * nterms * c->dim, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->pen_h, h, sizeof(double) * nterms, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->pen_k, kscale, sizeof(double) * nterms, cudaMemcpyHostToDevice));
+  c->pp = {nterms, c->pen_type, c->pen_G, c->pen_h, c->pen_k};
+  return MB2_OK;
+}
+
+int mb2_set_rng_philox(mb2_ctx* c, uint64_t seed) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  c->seed = seed;
+  c->replay = 0;
+  return MB2_OK;
+}
+
+int mb2_set_rng_replay(mb2_ctx* c, const int32_t* donors, const int32_t* nstart, const double* uni) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (!donors || !nstart || !uni) return fail(MB2_EINVAL, "replay buffers are NULL");
+  c->r_donors = donors;
+  c->r_nstart = nstart;
+  c->r_uni = uni;
+  c->replay = 1;
+  return MB2_OK;
+}
+
+int mb2_set_capture(mb2_ctx* c, double* trial, double* energy) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if ((trial == nullptr) != (energy == nullptr)) return fail(MB2_EINVAL, "capture needs both buffers or neither");
+  c->cap_trial = trial;
+  c->cap_energy = energy;
+  return MB2_OK;
+}
+
+int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const double* hi, void* stream) {
+  if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
+  if (!lo || !hi) return fail(MB2_EINVAL, "init bounds are NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  double *dlo = nullptr, *dhi = nullptr;
+  CUDA_TRY(cudaMalloc(&dlo, sizeof(double) * c->dim));
+  CUDA_TRY(cudaMalloc(&dhi, sizeof(double) * c->dim));
+  CUDA_TRY(cudaMemcpyAsync(dlo, lo, sizeof(double) * c->dim, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(dhi, hi, sizeof(double) * c->dim, cudaMemcpyHostToDevice, s));
+  const int64_t total = c->np * ((c->dim + 1) / 2);
+  int64_t grid = (total + 255) / 256;
+  const int64_t cap = (int64_t)c->sm_count * 16;
+  if (grid > cap) grid = cap;
+  de_init_population_kernel<<<(unsigned)grid, 256, 0, s>>>(c->pop[c->cur], c->en[c->cur], c->np, c->dim, c->offset, dlo,
+                                                           dhi, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  CUDA_TRY(cudaStreamSynchronize(s));  // lo/hi are pageable host buffers and dlo/dhi are freed here
+  cudaFree(dlo);
+  cudaFree(dhi);
+  c->generation = -1;
+  return MB2_OK;
+}
+
+int mb2_upload_population(mb2_ctx* c, const double* pop_host, void* stream) {
+  if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
+  if (!pop_host) return fail(MB2_EINVAL, "pop_host is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(c->pop[c->cur], pop_host, sizeof(double) * c->np * c->dim, cudaMemcpyHostToDevice, s));
+  int64_t grid = (c->np + 255) / 256;
+  if (grid > (int64_t)c->sm_count * 16) grid = (int64_t)c->sm_count * 16;
+  fill_kernel<<<(unsigned)grid, 256, 0, s>>>(c->en[c->cur], c->np, INFINITY);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  CUDA_TRY(cudaStreamSynchronize(s));
+  c->generation = -1;
+  return MB2_OK;
+}
+
+int mb2_eval_initial(mb2_ctx* c, void* stream) {
+  if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  c->generation = -1;
+  if (int rc = launch_step(c, MODE_GEN0, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s))
+    return rc;
+  if (int rc = launch_finalize(c, 1, s)) return rc;
+  c->cur ^= 1;
+  c->generation = 0;
+  return MB2_OK;
+}
+
+int mb2_step(mb2_ctx* c, void* stream) {
+  if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
+  if (c->generation < 0) return fail(MB2_ESTATE, "mb2_eval_initial must run before mb2_step");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (int rc = launch_step(c, MODE_STEP, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s))
+    return rc;
+  if (int rc = launch_finalize(c, 0, s)) return rc;
+  c->cur ^= 1;
+  c->generation += 1;
+  c->replay = 0;  // recorded draws are consumed by exactly one generation
+  return MB2_OK;
+}
+
+int mb2_pack_best(mb2_ctx* c, double* record, void* stream) {
+  if (c == nullptr || record == nullptr) return fail(MB2_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  pack_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c->st, c->best_x, c->dim, record);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
+}
+
+int mb2_merge_best(mb2_ctx* c, const double* records, int32_t world, void* stream) {
+  if (c == nullptr || records == nullptr || world < 1) return fail(MB2_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  merge_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(records, world, c->dim, c->best_x, c->st);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
+}
+
+int mb2_read_result(mb2_ctx* c, mb2_result* out, double* x_host, void* stream) {
+  if (c == nullptr || out == nullptr) return fail(MB2_EINVAL, "NULL argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, s));
+  if (x_host) CUDA_TRY(cudaMemcpyAsync(c->h_best_x, c->best_x, sizeof(double) * c->dim, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  out->best_energy = c->h_st->best_e;
+  out->best_index = c->h_st->best_idx;
+  out->n_inf = c->h_st->n_inf;
+  out->n_accepted = c->h_st->n_acc;
+  out->generation = c->h_st->generation;
+  if (x_host) memcpy(x_host, c->h_best_x, sizeof(double) * c->dim);
+  return MB2_OK;
+}
+
+int mb2_eval_cost(mb2_ctx* c, const double* x, int64_t n, double* out, void* stream) {
+  if (c == nullptr || x == nullptr || out == nullptr || n < 1) return fail(MB2_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int64_t saved_gen = c->generation;
+  const int saved_grid = c->grid;
+  double* cap_t = c->cap_trial;
+  c->cap_trial = nullptr;
+  int rc = launch_step(c, MODE_EVAL, x, nullptr, nullptr, out, n, (cudaStream_t)stream);
+  c->cap_trial = cap_t;
+  c->generation = saved_gen;
+  c->grid = saved_grid;
+  return rc;
+}
+
+int mb2_launch_info(mb2_ctx* c, int32_t* grid, int32_t* block, int32_t* smem) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (grid) *grid = c->grid;
+  if (block) *block = c->wpc * 32;
+  if (smem) *smem = c->smem;
+  return MB2_OK;
+}
+
+int64_t mb2_launch_count(mb2_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,227 @@
+// Device-side building blocks of the fused DE generation kernel: unfused FP64 arithmetic,
+// streaming loads, warp reductions, the mystic.models cost functions and the penalty terms.
+// Reference citations are relative to the mystic repository root.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <math_constants.h>
+
+#include "philox.cuh"
+
+namespace mb2 {
+
+// ---- unfused arithmetic: python evaluates a + F*(b-c) with separately rounded operations;
+// nvcc would contract to FMA, so the reference-order formulas use the _rn intrinsics.
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+
+// ---- streaming global loads (read once per generation: do not allocate in L1)
+__device__ __forceinline__ double2 ld_stream2(const double* p) {
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ double ld_stream1(const double* p) {
+  double r;
+  asm volatile("ld.global.nc.L1::no_allocate.f64 %0, [%1];" : "=d"(r) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream2(double* p, double a, double b) {
+  asm volatile("st.global.L1::no_allocate.v2.f64 [%0], {%1, %2};" ::"l"(p), "d"(a), "d"(b) : "memory");
+}
+
+// 4 consecutive elements starting at i0 (multiple of 4) of a row of length D.
+// VEC: D is even, the row base is 16-byte aligned.  Missing elements read as 0.
+template <bool VEC>
+__device__ __forceinline__ void load4(const double* __restrict__ row, int i0, int D, double (&v)[4]) {
+  if (VEC) {
+    double2 a = ld_stream2(row + i0);
+    v[0] = a.x;
+    v[1] = a.y;
+    if (i0 + 2 < D) {
+      double2 b = ld_stream2(row + i0 + 2);
+      v[2] = b.x;
+      v[3] = b.y;
+    } else {
+      v[2] = 0.0;
+      v[3] = 0.0;
+    }
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = (i0 + e < D) ? ld_stream1(row + i0 + e) : 0.0;
+  }
+}
+
+template <bool VEC>
+__device__ __forceinline__ void store4(double* __restrict__ row, int i0, int D, const double (&v)[4]) {
+  if (VEC) {
+    st_stream2(row + i0, v[0], v[1]);
+    if (i0 + 2 < D) st_stream2(row + i0 + 2, v[2], v[3]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (i0 + e < D) row[i0 + e] = v[e];
+  }
+}
+
+// ---- warp reductions (fixed xor tree: deterministic)
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = dmul(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---- cost parameters
+struct CostParams {
+  // chebyshev (models/_model_helper.py:16-33)
+  int cheb_M;             // number of points in [-1, 1]
+  const double* cheb_x;   // [M] the reference's accumulated abscissae (x=-1; x+=dx)
+  double cheb_tp, cheb_tm;  // polyeval(target, +1.2), polyeval(target, -1.2)
+};
+
+enum : int { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4 };
+
+// Horner exactly as mystic/math/poly.py:37-39: val = 0*x; for c in coeffs: val = c + val*x
+__device__ __forceinline__ double horner(const double* __restrict__ c, int n, double x) {
+  double val = dmul(0.0, x);
+  for (int j = 0; j < n; ++j) val = dadd(c[j], dmul(val, x));
+  return val;
+}
+
+// Warp-cooperative cost of one row `xs` (shared memory, D entries).  Every lane returns the
+// same value.  Per-element terms follow the reference's operation order without FMA, so each
+// term is bit-identical to the reference; only the summation tree differs (<= 1e-12 relative).
+template <int COST>
+__device__ __forceinline__ double warp_cost(const double* xs, int D, int lane, const CostParams& cp) {
+  if (COST == COST_ROSEN) {
+    // dejong.py:98-101: sum(100*(x[1:]-x[:-1]**2)**2 + (1-x[:-1])**2)
+    double acc = 0.0;
+    for (int i = lane; i < D - 1; i += 32) {
+      const double a = xs[i], b = xs[i + 1];
+      const double t = dsub(b, dmul(a, a));
+      const double u = dsub(1.0, a);
+      acc = dadd(acc, dadd(dmul(100.0, dmul(t, t)), dmul(u, u)));
+    }
+    return warp_sum(acc);
+  } else if (COST == COST_CORANA) {
+    // storn.py:77-96, strictly sequential over 4 terms; lanes compute redundantly
+    const double d[4] = {1., 1000., 10., 100.};
+    double x[4] = {0., 0., 0., 0.};
+    if (D >= 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = xs[j];
+    } else {
+      // x[_d.index(i)] = _x[i] with _d = [0,3,1,2]: 1 -> x0; 2 -> x0,x2; 3 -> x0,x2,x3
+      if (D >= 1) x[0] = xs[0];
+      if (D >= 2) x[2] = xs[1];
+      if (D >= 3) x[3] = xs[2];
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double xj = x[j];
+      const double sg = (xj > 0.0) ? 1.0 : ((xj < 0.0) ? -1.0 : 0.0);  // numpy.sign
+      const double zj = dmul(dmul(floor(dadd(fabs(xj / 0.2), 0.49999)), sg), 0.2);
+      double term;
+      if (fabs(dsub(xj, zj)) < 0.05) {
+        const double sz = (zj > 0.0) ? 1.0 : ((zj < 0.0) ? -1.0 : 0.0);
+        const double w = dsub(zj, dmul(0.05, sz));
+        term = dmul(dmul(0.15, dmul(w, w)), d[j]);  // 0.15 * pow(w,2) * d[j]
+      } else {
+        term = dmul(dmul(d[j], xj), xj);  // d[j]*x[j]*x[j]
+      }
+      r = dadd(r, term);
+    }
+    return r;
+  } else if (COST == COST_GRIEWANGK) {
+    // storn.py:135-139: sum(c*c)/4000 - prod(cos(c_i/sqrt(i+1))) + 1
+    double s = 0.0, p = 1.0;
+    for (int i = lane; i < D; i += 32) {
+      const double c = xs[i];
+      s = dadd(s, dmul(c, c));
+      p = dmul(p, cos(c / sqrt((double)i + 1.0)));
+    }
+    s = warp_sum(s);
+    p = warp_prod(p);
+    return dadd(dsub(s / 4000.0, p), 1.0);
+  } else if (COST == COST_ZIMMERMANN) {
+    // storn.py:182-191 (D == 2)
+    const double x0 = xs[0], x1 = (D > 1) ? xs[1] : 0.0;
+    const double f8 = dsub(dsub(9.0, x0), x1);
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    if (x0 < 0.0) c0 = dmul(-100.0, x0);
+    if (x1 < 0.0) c1 = dmul(-100.0, x1);
+    const double a = dsub(x0, 3.0), b = dsub(x1, 2.0);
+    const double xx = dadd(dmul(a, a), dmul(b, b));
+    if (xx > 16.0) c2 = dmul(100.0, dsub(xx, 16.0));
+    const double pr = dmul(x0, x1);
+    if (pr > 14.0) c3 = dmul(100.0, dsub(pr, 14.0));
+    double m = f8;  // python max(f8,c0,c1,c2,c3): replace only when strictly greater
+    if (c0 > m) m = c0;
+    if (c1 > m) m = c1;
+    if (c2 > m) m = c2;
+    if (c3 > m) m = c3;
+    return m;
+  } else {  // COST_CHEBYSHEV
+    // _model_helper.py:16-33
+    double acc = 0.0;
+    const int M = cp.cheb_M;
+    for (int i = lane; i < M; i += 32) {
+      const double px = horner(xs, D, __ldg(cp.cheb_x + i));
+      if (px < -1.0 || px > 1.0) {
+        const double u = dsub(1.0, px);
+        acc = dadd(acc, dmul(u, u));
+      }
+    }
+    acc = warp_sum(acc);
+    double px = dsub(horner(xs, D, 1.2), cp.cheb_tp);
+    if (px < 0.0) acc = dadd(acc, dmul(px, px));
+    px = dsub(horner(xs, D, -1.2), cp.cheb_tm);
+    if (px < 0.0) acc = dadd(acc, dmul(px, px));
+    return acc;
+  }
+}
+
+// ---- penalty: stacked mystic.penalty decorators with linear conditions G.x - h
+struct PenaltyParams {
+  int n;                // number of terms (0 = no penalty: `lambda x: 0.0`, abstract_solver.py:140)
+  const int* ptype;     // [n]
+  const double* G;      // [n, D]
+  const double* h;      // [n]
+  const double* kscale; // [n]  k*h**n
+};
+
+// term 0 innermost; value = t_{n-1} + (... + (t_0 + 0.0))  (penalty.py:88,147,388,447)
+__device__ __forceinline__ double warp_penalty(const double* xs, int D, int lane, const PenaltyParams& pp) {
+  double total = 0.0;
+  for (int t = 0; t < pp.n; ++t) {
+    const double* g = pp.G + (int64_t)t * D;
+    double acc = 0.0;
+    for (int i = lane; i < D; i += 32) acc = dadd(acc, dmul(__ldg(g + i), xs[i]));
+    const double pf = dsub(warp_sum(acc), __ldg(pp.h + t));
+    const double k = __ldg(pp.kscale + t);
+    const int ty = __ldg(pp.ptype + t);
+    double v;
+    if (ty == 0) {
+      v = dmul(k, dmul(pf, pf));
+    } else if (ty == 1) {
+      v = dmul(k, fabs(pf));
+    } else if (ty == 2) {
+      const double m = (pf > 0.0) ? pf : 0.0;  // python max(0., pf)
+      v = dmul(2.0 * k, dmul(m, m));
+    } else {
+      const double m = (pf > 0.0) ? pf : 0.0;
+      v = dmul(2.0 * k, fabs(m));
+    }
+    total = dadd(v, total);
+  }
+  return total;
+}
+
+}  // namespace mb2

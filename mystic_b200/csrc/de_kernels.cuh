@@ -1,0 +1,475 @@
+// The fused differential-evolution generation kernel (K2 of SURVEY.md section 7) and its
+// 1-CTA argmin epilogue (K3).  One warp owns one candidate row at a time; a persistent grid
+// strides over the shard so that the per-CTA (energy, index) partials stay few.
+//
+// Reference semantics reproduced (paths relative to the mystic repository root):
+//   trial generation   mystic/differential_evolution.py:574-582 + mystic/strategy.py:34-311
+//   bounds             mystic/tools.py:420-426 (reject -> inf), mystic/symbolic.py:1139-1144 (clamp)
+//   cost + penalty     mystic/differential_evolution.py:515-525, mystic/tools.py:386-389
+//   selection + best   mystic/differential_evolution.py:603-613
+#pragma once
+#include "de_device.cuh"
+
+namespace mb2 {
+
+enum : int { BASE_BEST1 = 0, BASE_RAND1 = 1, BASE_RANDTOBEST1 = 2, BASE_BEST2 = 3, BASE_RAND2 = 4 };
+enum : int { XOVER_EXP = 0, XOVER_BIN = 1 };
+enum : int { MODE_STEP = 0, MODE_GEN0 = 1, MODE_EVAL = 2 };
+enum : int { BOUNDS_NONE = 0, BOUNDS_REJECT = 1, BOUNDS_CLAMP = 2 };
+
+constexpr int kWarpsPerCtaMax = 8;
+
+struct StepParams {
+  // population (double buffered) and energies
+  const double* pop_cur;
+  double* pop_next;
+  const double* e_cur;
+  double* e_next;
+  const double* best_x;  // bestSolution of the previous generation [D]
+  const double* lo;      // [D] (bounds_mode != NONE)
+  const double* hi;
+  int64_t np;             // rows on this shard
+  int64_t global_offset;  // global index of row 0
+  int dim;
+  int dim_pad;  // dim rounded up to a multiple of 4
+  int mode;     // MODE_*
+  int bounds_mode;
+  double F, CR;
+  // RNG
+  int replay;  // 1: consume recorded draws
+  uint32_t key0, key1, generation;
+  uint64_t thr;  // crossover threshold on 32-bit words
+  const int32_t* r_donors;  // [np,5]
+  const int32_t* r_nstart;  // [np]
+  const double* r_uni;      // [np, dim+1]
+  CostParams cost;
+  PenaltyParams pen;
+  // per-CTA partials
+  double* part_e;
+  int64_t* part_idx;
+  unsigned long long* part_ninf;
+  unsigned long long* part_nacc;
+  // optional capture
+  double* cap_trial;
+  double* cap_energy;
+};
+
+template <int BASE>
+struct NumDonors {
+  static constexpr int value = (BASE == BASE_BEST1 || BASE == BASE_RANDTOBEST1) ? 2 : (BASE == BASE_RAND1 ? 3 : (BASE == BASE_BEST2 ? 4 : 5));
+};
+
+// mutant value for one dimension, reference operation order, no FMA.
+//   parent t, best b, donors p0..p4 (strategy.py formulas)
+template <int BASE>
+__device__ __forceinline__ double mutant(double t, double b, const double (&p)[5], double F) {
+  if (BASE == BASE_BEST1) return dadd(b, dmul(F, dsub(p[0], p[1])));
+  if (BASE == BASE_RAND1) return dadd(p[0], dmul(F, dsub(p[1], p[2])));
+  if (BASE == BASE_RANDTOBEST1) return dadd(t, dadd(dmul(F, dsub(b, t)), dmul(F, dsub(p[0], p[1]))));
+  if (BASE == BASE_BEST2) return dadd(b, dmul(F, dsub(dsub(dadd(p[0], p[1]), p[2]), p[3])));
+  return dadd(p[0], dmul(F, dsub(dsub(dadd(p[1], p[2]), p[3]), p[4])));
+}
+
+// Exponential crossover length L in [0, D]: number of leading draws < CR, capped at D
+// (strategy.py:48-56: `if random.random() >= CR or i == D: break`).  Warp-cooperative.
+__device__ __forceinline__ int exp_length_replay(const double* __restrict__ uni, int D, double CR, int lane) {
+  for (int base = 0; base < D; base += 32) {
+    const int i = base + lane;
+    bool fail = true;
+    if (i < D) fail = !(__ldg(uni + i) < CR);  // NaN (not drawn) -> stop
+    const unsigned m = __ballot_sync(0xffffffffu, fail);
+    if (m) return base + __ffs(m) - 1;
+  }
+  return D;
+}
+
+__device__ __forceinline__ int exp_length_philox(uint32_t k0, uint32_t k1, uint32_t gen, uint32_t cand, int D,
+                                                 uint64_t thr, int lane) {
+  for (int base = 0; base < D; base += 128) {
+    const int i0 = base + 4 * lane;
+    int first = 4;  // first failing word of this lane's block
+    if (i0 < D) {
+      const u32x4 w = philox4x32_10((uint32_t)(i0 >> 2), cand, gen, STREAM_XOVER, k0, k1);
+      if (!((uint64_t)w.w < thr)) first = 3;
+      if (!((uint64_t)w.z < thr)) first = 2;
+      if (!((uint64_t)w.y < thr)) first = 1;
+      if (!((uint64_t)w.x < thr)) first = 0;
+    } else {
+      first = 0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, first < 4);
+    if (m) {
+      const int src = __ffs(m) - 1;
+      const int f = __shfl_sync(0xffffffffu, first, src);
+      const int L = base + 4 * src + f;
+      return L < D ? L : D;
+    }
+  }
+  return D;
+}
+
+template <int BASE, int XOVER, int COST, bool VEC>
+__global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
+    de_step_kernel(const __grid_constant__ StepParams P) {
+  extern __shared__ __align__(16) double smem[];
+  constexpr int K = NumDonors<BASE>::value;
+  constexpr bool kNeedsBest = (BASE == BASE_BEST1 || BASE == BASE_RANDTOBEST1 || BASE == BASE_BEST2);
+  const int D = P.dim;
+  const int Dp = P.dim_pad;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  double* s_best = smem;                              // [Dp]
+  double* s_trial = smem + Dp + (size_t)warp * Dp;   // [Dp] per warp
+
+  if (P.mode == MODE_STEP && kNeedsBest) {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
+  }
+  __syncthreads();
+
+  double w_best_e = CUDART_INF;
+  int64_t w_best_idx = INT64_MAX;
+  unsigned long long w_ninf = 0, w_nacc = 0;
+
+  const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
+  const int64_t nw = (int64_t)gridDim.x * wpc;
+  for (int64_t c = gw; c < P.np; c += nw) {
+    const double* __restrict__ prow = P.pop_cur + c * D;
+    bool oob = false;
+
+    if (P.mode == MODE_STEP) {
+      // ---- random draws for this candidate
+      int64_t r[5] = {0, 0, 0, 0, 0};
+      int nstart;
+      const uint32_t cand_g = (uint32_t)(P.global_offset + c);
+      if (P.replay) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) r[j] = __ldg(P.r_donors + c * 5 + j);
+        nstart = __ldg(P.r_nstart + c);
+      } else {
+        draw_donors<K>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart);
+      }
+      int L = 0;
+      if (XOVER == XOVER_EXP) {
+        L = P.replay ? exp_length_replay(P.r_uni + c * (int64_t)(D + 1), D, P.CR, lane)
+                     : exp_length_philox(P.key0, P.key1, P.generation, cand_g, D, P.thr, lane);
+      }
+      const double* __restrict__ d0 = P.pop_cur + r[0] * D;
+      const double* __restrict__ d1 = P.pop_cur + r[1] * D;
+      const double* __restrict__ d2 = P.pop_cur + r[2] * D;
+      const double* __restrict__ d3 = P.pop_cur + r[3] * D;
+      const double* __restrict__ d4 = P.pop_cur + r[4] * D;
+
+      // ---- trial vector: 4 consecutive dimensions per lane per trip
+      for (int i0 = lane * 4; i0 < D; i0 += 128) {
+        double x[4];
+        load4<VEC>(prow, i0, D, x);
+        bool cross[4];
+        if (XOVER == XOVER_BIN) {
+          // strategy.py:79-85: i==n or random() < CR, one draw per dimension
+          if (P.replay) {
+            const double* u = P.r_uni + c * (int64_t)(D + 1) + i0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cross[e] = (i0 + e < D) && ((i0 + e == nstart) || (__ldg(u + e) < P.CR));
+          } else {
+            const u32x4 w = philox4x32_10((uint32_t)(i0 >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+            cross[0] = (i0 == nstart) || ((uint64_t)w.x < P.thr);
+            cross[1] = (i0 + 1 < D) && ((i0 + 1 == nstart) || ((uint64_t)w.y < P.thr));
+            cross[2] = (i0 + 2 < D) && ((i0 + 2 == nstart) || ((uint64_t)w.z < P.thr));
+            cross[3] = (i0 + 3 < D) && ((i0 + 3 == nstart) || ((uint64_t)w.w < P.thr));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int rel = i0 + e - nstart;
+            if (rel < 0) rel += D;
+            cross[e] = (i0 + e < D) && (rel < L);
+          }
+        }
+        if (cross[0] | cross[1] | cross[2] | cross[3]) {
+          double q[5][4];
+          load4<VEC>(d0, i0, D, q[0]);
+          load4<VEC>(d1, i0, D, q[1]);
+          if (K > 2) load4<VEC>(d2, i0, D, q[2]);
+          if (K > 3) load4<VEC>(d3, i0, D, q[3]);
+          if (K > 4) load4<VEC>(d4, i0, D, q[4]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (cross[e]) {
+              double p[5];
+#pragma unroll
+              for (int j = 0; j < 5; ++j) p[j] = (j < K) ? q[j][e] : 0.0;
+              const double b = kNeedsBest ? s_best[i0 + e] : 0.0;
+              x[e] = mutant<BASE>(x[e], b, p, P.F);
+            }
+          }
+        }
+        // ---- bounds on the trial (constraints applied before the cost, :582)
+        if (P.bounds_mode != BOUNDS_NONE) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (i0 + e < D) {
+              const double l = __ldg(P.lo + i0 + e), h = __ldg(P.hi + i0 + e);
+              if (P.bounds_mode == BOUNDS_CLAMP) {
+                x[e] = (x[e] > l) ? x[e] : l;  // python max(lo, x)
+                x[e] = (x[e] < h) ? x[e] : h;  // python min(hi, x)
+              }
+              oob |= (x[e] < l) || (x[e] > h);
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_trial[i0 + e] = x[e];
+      }
+    } else {
+      // MODE_GEN0: evaluate the initial population, clipped into the strict range
+      //            (differential_evolution.py:516-520, numpy clip = min(max(x,lo),hi))
+      // MODE_EVAL: evaluate arbitrary rows as given
+      for (int i0 = lane * 4; i0 < D; i0 += 128) {
+        double x[4];
+        load4<VEC>(prow, i0, D, x);
+        if (P.bounds_mode != BOUNDS_NONE) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (i0 + e < D) {
+              const double l = __ldg(P.lo + i0 + e), h = __ldg(P.hi + i0 + e);
+              if (P.mode == MODE_GEN0) x[e] = fmin(fmax(x[e], l), h);
+              oob |= (x[e] < l) || (x[e] > h);
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_trial[i0 + e] = x[e];
+      }
+    }
+    oob = __any_sync(0xffffffffu, oob);
+    __syncwarp();
+
+    // ---- energy = (inf if out of range else cost(x)) + penalty(x)
+    double E = CUDART_INF;
+    if (!oob) E = warp_cost<COST>(s_trial, D, lane, P.cost);
+    E = dadd(E, warp_penalty(s_trial, D, lane, P.pen));
+
+    if (P.cap_trial != nullptr && P.mode != MODE_EVAL) {
+      for (int i = lane; i < D; i += 32) P.cap_trial[c * D + i] = s_trial[i];
+      if (lane == 0) P.cap_energy[c] = E;
+    }
+
+    if (P.mode == MODE_EVAL) {
+      if (lane == 0) P.e_next[c] = E;
+    } else {
+      // ---- greedy selection (:603-609) and write of the next generation
+      const double e_old = (P.mode == MODE_GEN0) ? CUDART_INF : __ldg(P.e_cur + c);
+      const bool acc = E < e_old;
+      double* __restrict__ nrow = P.pop_next + c * D;
+      if (acc || P.mode == MODE_GEN0) {
+        for (int i0 = lane * 4; i0 < D; i0 += 128) {
+          double x[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = s_trial[i0 + e];
+          store4<VEC>(nrow, i0, D, x);
+        }
+      } else {
+        for (int i0 = lane * 4; i0 < D; i0 += 128) {
+          double x[4];
+          load4<VEC>(prow, i0, D, x);
+          store4<VEC>(nrow, i0, D, x);
+        }
+      }
+      if (lane == 0) P.e_next[c] = acc ? E : e_old;
+      // generation best among accepted trials; c ascends within the warp, strict '<' keeps
+      // the lowest index (:610-613)
+      if (acc) {
+        ++w_nacc;
+        if (E < w_best_e) {
+          w_best_e = E;
+          w_best_idx = c;
+        }
+      }
+      if (isinf(E)) ++w_ninf;
+    }
+    __syncwarp();  // s_trial is reused by the next row
+  }
+
+  if (P.mode == MODE_EVAL) return;
+
+  // ---- per-CTA (energy, index) argmin, lowest index on ties; counters
+  __shared__ double sh_e[kWarpsPerCtaMax];
+  __shared__ int64_t sh_i[kWarpsPerCtaMax];
+  __shared__ unsigned long long sh_ninf[kWarpsPerCtaMax], sh_nacc[kWarpsPerCtaMax];
+  if (lane == 0) {
+    sh_e[warp] = w_best_e;
+    sh_i[warp] = w_best_idx;
+    sh_ninf[warp] = w_ninf;
+    sh_nacc[warp] = w_nacc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double be = sh_e[0];
+    int64_t bi = sh_i[0];
+    unsigned long long ni = sh_ninf[0], na = sh_nacc[0];
+    for (int w = 1; w < wpc; ++w) {
+      if (sh_e[w] < be || (sh_e[w] == be && sh_i[w] < bi)) {
+        be = sh_e[w];
+        bi = sh_i[w];
+      }
+      ni += sh_ninf[w];
+      na += sh_nacc[w];
+    }
+    P.part_e[blockIdx.x] = be;
+    P.part_idx[blockIdx.x] = bi;
+    P.part_ninf[blockIdx.x] = ni;
+    P.part_nacc[blockIdx.x] = na;
+  }
+}
+
+// device-resident solver state shared by the kernels of one context
+struct DeviceState {
+  double best_e;       // bestEnergy
+  int64_t best_idx;    // GLOBAL index of the member that last became best (-1: none)
+  int64_t n_inf;       // of the last generation
+  int64_t n_acc;
+  int64_t generation;
+};
+
+// K3: reduce the per-CTA partials, update bestEnergy/bestSolution if the generation best beats
+// the previous best (strict '<', :610), publish counters.  One CTA.
+__global__ void __launch_bounds__(256)
+    de_finalize_kernel(const double* __restrict__ part_e, const int64_t* __restrict__ part_idx,
+                       const unsigned long long* __restrict__ part_ninf,
+                       const unsigned long long* __restrict__ part_nacc, int nparts,
+                       const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
+                       int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st) {
+  __shared__ double sh_e[256];
+  __shared__ int64_t sh_i[256];
+  __shared__ unsigned long long sh_a[256], sh_b[256];
+  __shared__ int64_t sh_winner;
+  double be = CUDART_INF;
+  int64_t bi = INT64_MAX;
+  unsigned long long ni = 0, na = 0;
+  for (int k = threadIdx.x; k < nparts; k += blockDim.x) {
+    const double e = part_e[k];
+    const int64_t i = part_idx[k];
+    if (e < be || (e == be && i < bi)) {
+      be = e;
+      bi = i;
+    }
+    ni += part_ninf[k];
+    na += part_nacc[k];
+  }
+  sh_e[threadIdx.x] = be;
+  sh_i[threadIdx.x] = bi;
+  sh_a[threadIdx.x] = ni;
+  sh_b[threadIdx.x] = na;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double e = sh_e[threadIdx.x + s];
+      const int64_t i = sh_i[threadIdx.x + s];
+      if (e < sh_e[threadIdx.x] || (e == sh_e[threadIdx.x] && i < sh_i[threadIdx.x])) {
+        sh_e[threadIdx.x] = e;
+        sh_i[threadIdx.x] = i;
+      }
+      sh_a[threadIdx.x] += sh_a[threadIdx.x + s];
+      sh_b[threadIdx.x] += sh_b[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double prev = gen0 ? CUDART_INF : st->best_e;
+    int64_t winner = -1;
+    if (sh_i[0] != INT64_MAX && sh_e[0] < prev) {
+      winner = sh_i[0];
+      st->best_e = sh_e[0];
+      st->best_idx = global_offset + winner;
+    } else if (gen0) {
+      // nothing finite yet: bestSolution stays population[0], bestEnergy = popEnergy[0] = inf (:559-567)
+      st->best_e = CUDART_INF;
+      st->best_idx = -1;
+      winner = -2;  // copy row 0
+    }
+    st->n_inf = (int64_t)sh_a[0];
+    st->n_acc = (int64_t)sh_b[0];
+    st->generation = generation;
+    sh_winner = winner;
+  }
+  __syncthreads();
+  const int64_t w = sh_winner;
+  if (w != -1) {
+    const double* src = pop_next + (w == -2 ? 0 : w) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = src[i];
+  }
+}
+
+// K0: device-side SetRandomInitialPoints (abstract_solver.py:532-534): pop[c][j] = lo + (hi-lo)*u
+__global__ void __launch_bounds__(256)
+    de_init_population_kernel(double* __restrict__ pop, double* __restrict__ energy, int64_t np, int D,
+                              int64_t global_offset, const double* __restrict__ lo, const double* __restrict__ hi,
+                              uint32_t k0, uint32_t k1) {
+  const int64_t nblk = (D + 1) / 2;  // philox blocks per row (2 doubles each)
+  const int64_t total = np * nblk;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / nblk;
+    const int b = (int)(t - c * nblk);
+    const u32x4 v = philox4x32_10((uint32_t)b, (uint32_t)(global_offset + c), 0u, STREAM_INIT, k0, k1);
+    const int j = 2 * b;
+    const double u0 = u64_to_unit(((uint64_t)v.x << 32) | v.y);
+    const double u1 = u64_to_unit(((uint64_t)v.z << 32) | v.w);
+    pop[c * D + j] = dadd(lo[j], dmul(dsub(hi[j], lo[j]), u0));
+    if (j + 1 < D) pop[c * D + j + 1] = dadd(lo[j + 1], dmul(dsub(hi[j + 1], lo[j + 1]), u1));
+    if (b == 0) energy[c] = CUDART_INF;
+  }
+}
+
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
+}
+
+// multi-GPU best exchange records: [best_e, best_idx(global), n_inf, n_acc, x[D]]
+__global__ void pack_best_kernel(const DeviceState* __restrict__ st, const double* __restrict__ best_x, int D,
+                                 double* __restrict__ rec) {
+  if (threadIdx.x == 0) {
+    rec[0] = st->best_e;
+    rec[1] = (double)st->best_idx;
+    rec[2] = (double)st->n_inf;
+    rec[3] = (double)st->n_acc;
+  }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) rec[4 + i] = best_x[i];
+}
+
+__global__ void merge_best_kernel(const double* __restrict__ recs, int world, int D, double* __restrict__ best_x,
+                                  DeviceState* __restrict__ st) {
+  __shared__ int sh_w;
+  if (threadIdx.x == 0) {
+    int w = -1;
+    double be = CUDART_INF;
+    double bi = 0.0;
+    double ninf = 0.0, nacc = 0.0;
+    for (int r = 0; r < world; ++r) {
+      const double* rec = recs + (int64_t)r * (D + 4);
+      ninf += rec[2];
+      nacc += rec[3];
+      if (rec[1] < 0.0) continue;  // shard has no best yet
+      if (w < 0 || rec[0] < be || (rec[0] == be && rec[1] < bi)) {
+        w = r;
+        be = rec[0];
+        bi = rec[1];
+      }
+    }
+    if (w >= 0) {
+      st->best_e = be;
+      st->best_idx = (int64_t)bi;
+    }
+    st->n_inf = (int64_t)ninf;
+    st->n_acc = (int64_t)nacc;
+    sh_w = w;
+  }
+  __syncthreads();
+  const int w = sh_w;
+  if (w >= 0) {
+    const double* rec = recs + (int64_t)w * (D + 4);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = rec[4 + i];
+  }
+}
+
+}  // namespace mb2

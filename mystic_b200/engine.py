@@ -1,0 +1,193 @@
+"""Python face of the C ABI: one `DeviceEngine` per population shard on one GPU.
+
+PyTorch owns the big device buffers (population double buffer, energies, replay draws) and the
+stream; every computation is a call into libmystic_b200.so (include/mystic_b200.h).  There is
+no CPU path: constructing an engine without a CUDA device raises.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _native
+from ._native import check, lib
+
+BOUNDS_NONE, BOUNDS_REJECT, BOUNDS_CLAMP = 0, 1, 2
+
+
+def _dptr(arr):
+    return arr.ctypes.data_as(_native.c_double_p)
+
+
+class DeviceEngine(object):
+    """Device-resident state of one shard: rows [offset, offset+np_local) of np_global."""
+
+    def __init__(self, np_local, dim, np_global=None, offset=0, device=None, keep_trials=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError('mystic_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+        if device is None:
+            device = torch.cuda.current_device()
+        self.device = torch.device('cuda', device if isinstance(device, int) else torch.device(device).index or 0)
+        self.np_local = int(np_local)
+        self.dim = int(dim)
+        self.np_global = int(np_global if np_global is not None else np_local)
+        self.offset = int(offset)
+        f64 = dict(dtype=torch.float64, device=self.device)
+        self._pop = [torch.empty((self.np_local, self.dim), **f64) for _ in range(2)]
+        self._en = [torch.full((self.np_local,), float('inf'), **f64) for _ in range(2)]
+        self._ctx = ctypes.c_void_p()
+        check(lib.mb2_create(self.device.index, self.np_local, self.dim, self.np_global, self.offset,
+                             ctypes.byref(self._ctx)))
+        check(lib.mb2_bind_buffers(self._ctx, self._pop[0].data_ptr(), self._pop[1].data_ptr(),
+                                   self._en[0].data_ptr(), self._en[1].data_ptr()))
+        self._trial = self._trial_e = None
+        if keep_trials:
+            self._trial = torch.zeros((self.np_local, self.dim), **f64)
+            self._trial_e = torch.full((self.np_local,), float('inf'), **f64)
+            check(lib.mb2_set_capture(self._ctx, self._trial.data_ptr(), self._trial_e.data_ptr()))
+        self._replay = None  # keeps the uploaded draw tensors alive until consumed
+        self._record = torch.empty((self.dim + 4,), **f64)
+        self._xbuf = np.empty(self.dim, dtype=np.float64)
+
+    def close(self):
+        if getattr(self, '_ctx', None) is not None and self._ctx.value:
+            lib.mb2_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- configuration -------------------------------------------------------------------
+    def set_strategy(self, strategy_id, scale, cross):
+        check(lib.mb2_set_strategy(self._ctx, int(strategy_id), float(scale), float(cross)))
+
+    def set_bounds(self, mode, lo=None, hi=None):
+        if mode == BOUNDS_NONE:
+            check(lib.mb2_set_bounds(self._ctx, BOUNDS_NONE, None, None))
+            return
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        check(lib.mb2_set_bounds(self._ctx, int(mode), _dptr(lo), _dptr(hi)))
+
+    def set_cost(self, cost_id, params=()):
+        p = np.ascontiguousarray(params, dtype=np.float64)
+        check(lib.mb2_set_cost(self._ctx, int(cost_id), _dptr(p) if p.size else None, int(p.size)))
+
+    def set_penalty(self, ptypes=(), G=(), h=(), kscale=()):
+        n = len(ptypes)
+        if n == 0:
+            check(lib.mb2_set_penalty(self._ctx, 0, None, None, None, None))
+            return
+        pt = np.ascontiguousarray(ptypes, dtype=np.int32)
+        Gm = np.ascontiguousarray(G, dtype=np.float64).reshape(n, self.dim)
+        hv = np.ascontiguousarray(h, dtype=np.float64)
+        kv = np.ascontiguousarray(kscale, dtype=np.float64)
+        check(lib.mb2_set_penalty(self._ctx, n, pt.ctypes.data_as(_native.c_int32_p), _dptr(Gm), _dptr(hv), _dptr(kv)))
+
+    def set_rng_philox(self, seed):
+        check(lib.mb2_set_rng_philox(self._ctx, int(seed) & 0xFFFFFFFFFFFFFFFF))
+
+    def set_rng_replay(self, donors, nstart, uniforms):
+        """recorded draws for the next step: donors [np,<=5], nstart [np], uniforms [np, dim+1] (NaN = not drawn)"""
+        d = np.full((self.np_local, 5), -1, dtype=np.int32)
+        donors = np.asarray(donors)
+        d[:, :donors.shape[1]] = donors[:, :5]
+        u = np.full((self.np_local, self.dim + 1), np.nan, dtype=np.float64)
+        uniforms = np.asarray(uniforms, dtype=np.float64)
+        u[:, :uniforms.shape[1]] = uniforms[:, :self.dim + 1]
+        t = (torch.from_numpy(d).to(self.device), torch.from_numpy(np.ascontiguousarray(nstart, dtype=np.int32)).to(self.device),
+             torch.from_numpy(u).to(self.device))
+        self._replay = t
+        check(lib.mb2_set_rng_replay(self._ctx, t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr()))
+
+    # ---- population ----------------------------------------------------------------------
+    def init_population(self, seed, lo, hi):
+        lo = np.ascontiguousarray(lo, dtype=np.float64)
+        hi = np.ascontiguousarray(hi, dtype=np.float64)
+        check(lib.mb2_init_population(self._ctx, int(seed) & 0xFFFFFFFFFFFFFFFF, _dptr(lo), _dptr(hi), self._stream()))
+
+    def upload_population(self, pop):
+        pop = np.ascontiguousarray(pop, dtype=np.float64)
+        if pop.shape != (self.np_local, self.dim):
+            raise ValueError('population shape %r != %r' % (pop.shape, (self.np_local, self.dim)))
+        check(lib.mb2_upload_population(self._ctx, pop.ctypes.data_as(ctypes.c_void_p), self._stream()))
+
+    def _current(self):
+        p, e = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib.mb2_current(self._ctx, ctypes.byref(p), ctypes.byref(e)))
+        i = 0 if p.value == self._pop[0].data_ptr() else 1
+        return self._pop[i], self._en[i]
+
+    def population_tensor(self):
+        return self._current()[0]
+
+    def energy_tensor(self):
+        return self._current()[1]
+
+    def population(self):
+        return self._current()[0].cpu().numpy()
+
+    def energies(self):
+        return self._current()[1].cpu().numpy()
+
+    def trials(self):
+        if self._trial is None:
+            raise RuntimeError('trial vectors are not kept; construct the solver with keep_trials=True')
+        return self._trial.cpu().numpy(), self._trial_e.cpu().numpy()
+
+    # ---- the hot path --------------------------------------------------------------------
+    def eval_initial(self):
+        check(lib.mb2_eval_initial(self._ctx, self._stream()))
+
+    def step(self):
+        check(lib.mb2_step(self._ctx, self._stream()))
+
+    def pack_best(self):
+        check(lib.mb2_pack_best(self._ctx, self._record.data_ptr(), self._stream()))
+        return self._record
+
+    def merge_best(self, records):
+        world = records.shape[0]
+        check(lib.mb2_merge_best(self._ctx, records.data_ptr(), int(world), self._stream()))
+
+    def read_result(self):
+        """-> (best_energy, best_index, n_inf, n_accepted, generation, bestSolution ndarray); synchronises"""
+        r = _native.Result()
+        check(lib.mb2_read_result(self._ctx, ctypes.byref(r), _dptr(self._xbuf), self._stream()))
+        self._replay = None
+        return r.best_energy, r.best_index, r.n_inf, r.n_accepted, r.generation, self._xbuf.copy()
+
+    def eval_cost(self, x):
+        x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64)).to(self.device)
+        out = torch.empty((x.shape[0],), dtype=torch.float64, device=self.device)
+        check(lib.mb2_eval_cost(self._ctx, x.data_ptr(), int(x.shape[0]), out.data_ptr(), self._stream()))
+        return out.cpu().numpy()
+
+    def launch_info(self):
+        g, b, s = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        check(lib.mb2_launch_info(self._ctx, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
+        return g.value, b.value, s.value
+
+    def launch_count(self):
+        return int(lib.mb2_launch_count(self._ctx))
+
+
+def evaluate_rows(cost, X, extra_args=(), bounds=None, penalty=None):
+    """cost(x) for every row of X [n, D], on the device (mb2_eval_cost)."""
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    eng = DeviceEngine(X.shape[0], X.shape[1])
+    try:
+        eng.set_cost(cost.cost_id, cost.params(tuple(extra_args)))
+        if bounds is not None:
+            eng.set_bounds(*bounds)
+        if penalty is not None:
+            eng.set_penalty(*penalty.device_terms(X.shape[1]))
+        return eng.eval_cost(X)
+    finally:
+        eng.close()

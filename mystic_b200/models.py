@@ -1,0 +1,92 @@
+"""Device cost descriptors with the names of mystic.models.
+
+    rosen       mystic/models/dejong.py:89-101
+    corana      mystic/models/storn.py:57-96
+    griewangk   mystic/models/storn.py:120-139
+    zimmermann  mystic/models/storn.py:161-191
+    chebyshev{2,4,6,8,16}cost   mystic/models/poly.py:124-149, mystic/models/_model_helper.py:10-33
+
+A descriptor names a cost function compiled into the fused kernel.  `resolve()` also recognises
+the unmodified reference callables (mystic.models.rosen is `Rosenbrock().function`, etc.) so
+user scripts written against mystic keep working.  Arbitrary Python callables are rejected
+with TypeError: the engine has no CPU path.
+"""
+
+COST_ROSEN, COST_CORANA, COST_GRIEWANGK, COST_ZIMMERMANN, COST_CHEBYSHEV, COST_CHEBYSHEV_MMA = range(6)
+
+CHEBYSHEV_TARGETS = {  # mystic/models/_model_helper.py:10-14
+    2: [2., 0., -1.],
+    4: [8., 0., -8., 0., 1.],
+    6: [32., 0., -48., 0., 18., 0., -1.],
+    8: [128., 0., -256., 0., 160., 0., -32., 0., 1.],
+    16: [32768., 0., -131072., 0., 212992., 0., -180224., 0., 84480., 0., -21504., 0., 2688., 0., -128., 0., 1.],
+}
+
+
+class DeviceCost(object):
+    """A cost function that exists as a device function of the fused kernel."""
+
+    def __init__(self, name, cost_id, order=None, doc=''):
+        self.__name__ = name
+        self.cost_id = cost_id
+        self.order = order
+        self.__doc__ = doc
+
+    def params(self, extra_args=()):
+        """numeric parameter vector handed to mb2_set_cost"""
+        if self.cost_id in (COST_CHEBYSHEV, COST_CHEBYSHEV_MMA):
+            M = int(extra_args[0]) if extra_args else 61  # chebyshevNcost(trial, M=61), poly.py:124-149
+            return [float(M), float(self.order)] + [float(c) for c in CHEBYSHEV_TARGETS[self.order]]
+        if extra_args:
+            raise TypeError('%s() takes no ExtraArgs' % self.__name__)
+        return []
+
+    def __call__(self, x, *extra_args):
+        """Evaluate on the device (one row, or a [n, D] batch) through mb2_eval_cost."""
+        from .engine import evaluate_rows
+        import numpy as np
+        arr = np.asarray(x, dtype=np.float64)
+        out = evaluate_rows(self, np.atleast_2d(arr), extra_args)
+        return float(out[0]) if arr.ndim == 1 else out
+
+    def __repr__(self):
+        return '<mystic_b200 device cost %s>' % self.__name__
+
+
+rosen = DeviceCost('rosen', COST_ROSEN, doc="Rosenbrock's saddle, sum(100*(x[1:]-x[:-1]**2)**2 + (1-x[:-1])**2)")
+corana = DeviceCost('corana', COST_CORANA, doc="Corana's parabola (first four coordinates)")
+griewangk = DeviceCost('griewangk', COST_GRIEWANGK, doc="Griewangk's function")
+zimmermann = DeviceCost('zimmermann', COST_ZIMMERMANN, doc="Zimmermann's function (2-D)")
+chebyshev2cost = DeviceCost('chebyshev2cost', COST_CHEBYSHEV, 2, 'order-2 Chebyshev fitting cost')
+chebyshev4cost = DeviceCost('chebyshev4cost', COST_CHEBYSHEV, 4, 'order-4 Chebyshev fitting cost')
+chebyshev6cost = DeviceCost('chebyshev6cost', COST_CHEBYSHEV, 6, 'order-6 Chebyshev fitting cost')
+chebyshev8cost = DeviceCost('chebyshev8cost', COST_CHEBYSHEV, 8, 'order-8 Chebyshev fitting cost')
+chebyshev16cost = DeviceCost('chebyshev16cost', COST_CHEBYSHEV, 16, 'order-16 Chebyshev fitting cost')
+
+_BY_NAME = dict((c.__name__, c) for c in (rosen, corana, griewangk, zimmermann, chebyshev2cost, chebyshev4cost,
+                                          chebyshev6cost, chebyshev8cost, chebyshev16cost))
+_BY_REFERENCE_CLASS = {'Rosenbrock': rosen, 'Corana': corana, 'Griewangk': griewangk, 'Zimmermann': zimmermann}
+
+
+def resolve(cost):
+    """DeviceCost | reference callable | name -> DeviceCost, else TypeError."""
+    if isinstance(cost, DeviceCost):
+        return cost
+    if isinstance(cost, str) and cost in _BY_NAME:
+        return _BY_NAME[cost]
+    mod = getattr(cost, '__module__', '') or ''
+    owner = getattr(cost, '__self__', None)
+    if owner is not None and getattr(cost, '__name__', '') == 'function':
+        # mystic.models.rosen = Rosenbrock().function (dejong.py:288), storn.py:201-203
+        kls = type(owner).__name__
+        if type(owner).__module__.startswith('mystic.models') and kls in _BY_REFERENCE_CLASS:
+            if kls == 'Rosenbrock' and getattr(owner, 'axis', None) is not None:
+                raise TypeError('Rosenbrock(axis=...) is not supported on the device')
+            return _BY_REFERENCE_CLASS[kls]
+    name = getattr(cost, '__name__', None)
+    if mod.startswith('mystic.models') and name in _BY_NAME:
+        return _BY_NAME[name]  # mystic.models.poly.chebyshev8cost etc.
+    raise TypeError(
+        "cost %r is not a device cost function: the B200 engine evaluates the cost inside the fused "
+        "CUDA kernel and has no CPU path. Use mystic_b200.models.{rosen,corana,griewangk,zimmermann,"
+        "chebyshevNcost} or the corresponding mystic.models objects." % (cost,))

@@ -1,0 +1,226 @@
+"""Termination conditions for solvers without a mystic installation.
+
+Unmodified `mystic.termination` objects work on the B200 solver as they are: they only read
+solver attributes (`energy_history`, `generations`, `_fcalls`, `population`, `popEnergy`,
+`bestSolution`; mystic/termination.py:181-408).  This module provides the same factories
+(same names, arguments and `__doc__` convention "<Name> with {kwds}") so the engine also runs
+where mystic is absent, e.g. on the GPU box.  Each condition is `cond(solver, info=False)`,
+returning bool, or the describing string / '' when info is true.
+"""
+import time as _time
+
+import numpy as np
+
+inf = float('inf')
+EARLYEXIT = 0
+
+
+def _condition(name, kwds, test):
+    doc = '%s with %s' % (name, kwds)
+
+    def cond(inst, info=False):
+        met = test(inst)
+        if info:
+            return doc if met else ''
+        return bool(met)
+    cond.__doc__ = doc
+    cond.__name__ = '_' + name
+    return cond
+
+
+def VTR(tolerance=0.005, target=0.0):
+    """abs(cost[-1] - target) <= tolerance   (mystic/termination.py:181-196)"""
+    def test(inst):
+        hist = inst.energy_history
+        return bool(len(hist)) and abs(hist[-1] - target) <= tolerance
+    return _condition('VTR', {'tolerance': tolerance, 'target': target}, test)
+
+
+def _lookback(generations):
+    return 0 if generations is None else int(generations)
+
+
+def ChangeOverGeneration(tolerance=1e-6, generations=30):
+    """cost[-g] - cost[-1] <= tolerance   (mystic/termination.py:198-217)"""
+    def test(inst):
+        hist = inst.energy_history
+        g = _lookback(generations)
+        if not len(hist) or len(hist) <= g:
+            return False
+        return (hist[-g] - hist[-1]) <= tolerance or hist[-g] == hist[-1]
+    return _condition('ChangeOverGeneration', {'tolerance': tolerance, 'generations': generations}, test)
+
+
+def NormalizedChangeOverGeneration(tolerance=1e-4, generations=10):
+    """2*(cost[-g]-cost[-1]) <= tolerance*(|cost[-g]|+|cost[-1]|) + 1e-20   (termination.py:219-240)"""
+    def test(inst):
+        hist = inst.energy_history
+        g = _lookback(generations)
+        if not len(hist) or len(hist) <= g:
+            return False
+        if hist[-g] == hist[-1]:
+            return True
+        return 2.0 * (hist[-g] - hist[-1]) <= tolerance * (abs(hist[-g]) + abs(hist[-1])) + 1e-20
+    return _condition('NormalizedChangeOverGeneration', {'tolerance': tolerance, 'generations': generations}, test)
+
+
+def VTRChangeOverGeneration(ftol=0.005, gtol=1e-6, generations=30, target=0.0):
+    """cost[-g] - cost[-1] <= gtol or abs(cost[-1] - target) <= ftol   (termination.py:320-342)"""
+    def test(inst):
+        hist = inst.energy_history
+        if not len(hist):
+            return False
+        g = _lookback(generations)
+        if len(hist) > g and ((hist[-g] - hist[-1]) <= gtol or hist[-g] == hist[-1]):
+            return True
+        return abs(hist[-1] - target) <= ftol
+    return _condition('VTRChangeOverGeneration',
+                      {'ftol': ftol, 'gtol': gtol, 'generations': generations, 'target': target}, test)
+
+
+def NormalizedCostTarget(fval=None, tolerance=1e-6, generations=30):
+    """abs(cost[-1]-fval) <= abs(tolerance*fval), or no improvement over g iterations (termination.py:290-318)"""
+    def test(inst):
+        hist = inst.energy_history
+        if not len(hist):
+            return False
+        g = _lookback(generations)
+        if g and fval is None:
+            return len(hist) > g and ((hist[-g] - hist[-1]) <= 0 or hist[-g] == hist[-1])
+        if not g and fval is None:
+            return True
+        return abs(hist[-1] - fval) <= abs(tolerance * fval)
+    return _condition('NormalizedCostTarget', {'fval': fval, 'tolerance': tolerance, 'generations': generations}, test)
+
+
+def CandidateRelativeTolerance(xtol=1e-4, ftol=1e-4):
+    """abs(xi-x0) <= xtol & abs(fi-f0) <= ftol; reads the whole population (termination.py:242-267)"""
+    def test(inst):
+        sim = np.array(inst.population)
+        fsim = np.array(inst.popEnergy)
+        if len(fsim) < 2:
+            return False
+        with np.errstate(invalid='ignore'):
+            return bool(np.max(np.abs(sim[1:] - sim[0])) <= xtol and np.max(np.abs(fsim[0] - fsim[1:])) <= ftol)
+    return _condition('CandidateRelativeTolerance', {'xtol': xtol, 'ftol': ftol}, test)
+
+
+def PopulationSpread(tolerance=1e-6):
+    """abs(params - params[0]) <= abs(tolerance*params[0]); reads the whole population (termination.py:344-361)"""
+    def test(inst):
+        sim = np.array(inst.population)
+        return bool(np.all(np.abs(sim - sim[0]) <= np.abs(tolerance * sim[0])))
+    return _condition('PopulationSpread', {'tolerance': tolerance}, test)
+
+
+def EvaluationLimits(generations=None, evaluations=None):
+    """iterations >= generations or fcalls >= evaluations   (termination.py:386-408)"""
+    maxiter = inf if generations is None else generations
+    maxfun = inf if evaluations is None else evaluations
+
+    def test(inst):
+        return inst._fcalls[0] >= maxfun or inst.generations >= maxiter
+    return _condition('EvaluationLimits', {'generations': generations, 'evaluations': evaluations}, test)
+
+
+def TimeLimits(seconds=86400, system=None):
+    """elapsed time >= seconds   (termination.py:410-437)"""
+    timer = _time.time if system is None else (_time.perf_counter if system else _time.process_time)
+    start = [timer()]
+    delta = inf if seconds is None else getattr(seconds, 'total_seconds', lambda: abs(seconds))()
+
+    def test(inst):
+        return (timer() - start[0]) >= delta
+    cond = _condition('TimeLimits', {'seconds': seconds, 'system': system}, test)
+    cond.reset = lambda: start.__setitem__(0, timer())
+    return cond
+
+
+def SolverInterrupt():
+    """_EARLYEXIT == True   (termination.py:439-451)"""
+    return _condition('SolverInterrupt', {}, lambda inst: bool(inst._EARLYEXIT))
+
+
+class When(tuple):
+    """terminate when the given condition is satisfied (termination.py:63-108)"""
+
+    def __new__(cls, arg):
+        if isinstance(arg, tuple) and len(arg) == 1:
+            arg = arg[0]
+        if not getattr(arg, '__len__', None):
+            arg = [arg]
+        return tuple.__new__(cls, arg)
+
+    def _results(self, solver, info):
+        return dict((f, f(solver, info)) for f in self)
+
+    def _met(self, values):
+        return all(values)
+
+    def _satisfied(self, stop, met):
+        return stop if met else {}
+
+    def __call__(self, solver, info=False):
+        if info == 'not':
+            return tuple(set(f for f in self if f not in self(solver, 'self')))
+        stop = self._results(solver, info)
+        met = self._met(stop.values())
+        if not info:
+            return met
+        satisfied = self._satisfied(stop, met)
+        if info == 'self':
+            return tuple(set(satisfied.keys()))
+        if not satisfied:
+            return ''
+        return '; '.join(sorted(set('; '.join(str(v) for v in satisfied.values()).split('; '))))
+
+    def __repr__(self):
+        return 'When(%s)' % str(self[0])
+
+
+class And(When):
+    """terminate when all given conditions are satisfied (termination.py:110-131)"""
+
+    def __new__(cls, *args):
+        if len(args) == 1:
+            args = args[0]
+        if not getattr(args, '__len__', None):
+            args = [args]
+        return tuple.__new__(cls, args)
+
+    def __repr__(self):
+        return 'And%s' % str(tuple(f for f in self))
+
+
+class Or(When):
+    """terminate when any of the given conditions is satisfied (termination.py:134-176)"""
+
+    def __new__(cls, *args):
+        if len(args) == 1:
+            args = args[0]
+        if not getattr(args, '__len__', None):
+            args = [args]
+        return tuple.__new__(cls, args)
+
+    def _met(self, values):
+        return any(values)
+
+    def _satisfied(self, stop, met):
+        return dict((k, v) for k, v in stop.items() if v)
+
+    def __repr__(self):
+        return 'Or%s' % str(tuple(f for f in self))
+
+
+def state(condition):
+    """{doc: kwds} of every leaf condition (termination.py:30-47)"""
+    out = {}
+    for term in (condition if isinstance(condition, tuple) else (condition,)):
+        doc = term.__doc__
+        if doc is None:
+            continue
+        if isinstance(term, tuple):
+            out.update(state(term))
+        elif ' with ' in doc:
+            out[doc] = eval(doc.split(' with ', 1)[1], {'inf': inf, 'nan': float('nan')})
+    return out

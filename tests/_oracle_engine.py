@@ -1,0 +1,151 @@
+"""TEST-ONLY engine: the CPU oracle (oracle/de_oracle.py) behind the DeviceEngine interface.
+
+It lets the `-m "not gpu"` suite exercise the HOST logic of mystic_b200.solver (Step / Solve /
+termination / keyword handling / sharding and the best exchange over gloo) where no GPU exists.
+It lives under tests/ and is only ever injected explicitly (`engine=OracleEngine`); the product
+never selects it -- without the CUDA library and a GPU, mystic_b200 raises.
+"""
+import numpy as np
+import torch
+
+from oracle import de_oracle as orc
+
+_STRATEGY_BY_ID = dict((v[0], k) for k, v in orc.STRATEGIES.items())
+_COST_NAMES = {0: 'rosen', 1: 'corana', 2: 'griewangk', 3: 'zimmermann'}
+_PTYPE_BY_ID = dict((v, k) for k, v in orc.PTYPES.items())
+
+
+class OracleEngine(object):
+    def __init__(self, np_local, dim, np_global=None, offset=0, device=None, keep_trials=False):
+        self.np_local, self.dim = int(np_local), int(dim)
+        self.np_global = int(np_global if np_global is not None else np_local)
+        self.offset = int(offset)
+        self._pop = np.zeros((self.np_local, self.dim))
+        self.state = None
+        self.strategy, self.F, self.CR = 'Best1Bin', 0.8, 0.9
+        self.bounds = (orc.BOUNDS_NONE, None, None)
+        self.cost = None
+        self.pen = ()
+        self.seed = 0
+        self.replay = None
+        self.n_inf = self.n_acc = 0
+        self.best_idx = -1
+        self.launches = 0
+
+    def close(self):
+        pass
+
+    def set_strategy(self, sid, scale, cross):
+        self.strategy, self.F, self.CR = _STRATEGY_BY_ID[sid], float(scale), float(cross)
+
+    def set_bounds(self, mode, lo=None, hi=None):
+        self.bounds = (mode, None if lo is None else np.array(lo, float), None if hi is None else np.array(hi, float))
+        if self.state is not None:
+            self.state.bounds_mode, self.state.lo, self.state.hi = self.bounds
+
+    def set_cost(self, cost_id, params=()):
+        if cost_id in _COST_NAMES:
+            self.cost = orc.make_cost(_COST_NAMES[cost_id])
+        else:
+            M, order = int(params[0]), int(params[1])
+            self.cost = orc.make_cost('chebyshev%dcost' % order, (M,))
+
+    def set_penalty(self, ptypes=(), G=(), h=(), kscale=()):
+        self.pen = [dict(ptype=_PTYPE_BY_ID[int(p)], G=list(g), h=float(hh), k=float(k), hpow=1, n=0)
+                    for p, g, hh, k in zip(ptypes, G, h, kscale)]
+
+    def set_rng_philox(self, seed):
+        self.seed = int(seed)
+
+    def set_rng_replay(self, donors, nstart, uniforms):
+        self.replay = dict(donors=np.asarray(donors), nstart=np.asarray(nstart), uni=np.asarray(uniforms))
+
+    def init_population(self, seed, lo, hi):
+        self._pop = orc.philox_init_population(int(seed), self.np_local, lo, hi, offset=self.offset)
+        self.state = None
+
+    def upload_population(self, pop):
+        self._pop = np.array(pop, dtype=np.float64)
+        self.state = None
+
+    def population_tensor(self):
+        arr = self._pop if self.state is None else self.state.population
+        return torch.from_numpy(arr)
+
+    def population(self):
+        return (self._pop if self.state is None else self.state.population).copy()
+
+    def energies(self):
+        return np.full(self.np_local, np.inf) if self.state is None else self.state.popEnergy.copy()
+
+    def trials(self):
+        return self.state.trialSolution.copy(), self.state.trialEnergy.copy()
+
+    def _after(self):
+        st = self.state
+        self.n_inf = int(np.isinf(st.trialEnergy).sum())
+        self.n_acc = int(st.accepted.sum())
+        if st.bestIndex >= 0:   # select() found a new best in this generation
+            self.best_idx = self.offset + st.bestIndex
+        self.launches += 2
+
+    def eval_initial(self):
+        mode, lo, hi = self.bounds
+        self.state = orc.DEState(self._pop, lo, hi, mode)
+        self.best_idx = -1
+        orc.step0(self.state, self.cost, self.pen)
+        self._after()
+
+    def step(self):
+        st = self.state
+        st.bestIndex = -1
+        if self.replay is not None:
+            orc.step(st, self.strategy, self.CR, self.F, self.cost, self.pen, replay=self.replay)
+            self.replay = None
+        else:
+            orc.step(st, self.strategy, self.CR, self.F, self.cost, self.pen,
+                     philox=dict(seed=self.seed, offset=self.offset))
+        self._after()
+
+    def pack_best(self):
+        st = self.state
+        rec = np.concatenate([[st.bestEnergy, float(self.best_idx), float(self.n_inf), float(self.n_acc)],
+                              st.bestSolution])
+        return torch.from_numpy(rec)
+
+    def merge_best(self, records):
+        """same rule as merge_best_kernel (mystic_b200/csrc/de_kernels.cuh)"""
+        recs = records.numpy()
+        D = self.dim
+        w, be, bi = -1, np.inf, 0.0
+        ninf = nacc = 0.0
+        for r in range(recs.shape[0]):
+            rec = recs[r]
+            ninf += rec[2]
+            nacc += rec[3]
+            if rec[1] < 0:
+                continue
+            if w < 0 or rec[0] < be or (rec[0] == be and rec[1] < bi):
+                w, be, bi = r, rec[0], rec[1]
+        st = self.state
+        if w >= 0:
+            st.bestEnergy = float(be)
+            st.bestSolution = recs[w][4:4 + D].copy()
+            self.best_idx = int(bi)
+        self.n_inf, self.n_acc = int(ninf), int(nacc)
+
+    def read_result(self):
+        st = self.state
+        return float(st.bestEnergy), int(self.best_idx), self.n_inf, self.n_acc, st.generation, st.bestSolution.copy()
+
+    def eval_cost(self, x):
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        mode, lo, hi = self.bounds
+        tmp = orc.DEState(x, lo, hi, mode)
+        return orc.evaluate(x, self.cost, tmp, self.pen)
+
+    def launch_info(self):
+        return (0, 0, 0)
+
+    def launch_count(self):
+        return self.launches

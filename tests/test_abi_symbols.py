@@ -1,0 +1,49 @@
+"""The C-ABI library builds, loads and exports every symbol include/mystic_b200.h declares.
+No compute calls (no GPU needed)."""
+import ctypes
+import os
+import re
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(REPO, 'include', 'mystic_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    return sorted(set(re.findall(r'\b(mb2_[a-z_0-9]+)\s*\(', src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mystic_b200.build import build
+    path = build()
+    lib = ctypes.CDLL(path)
+    names = declared_symbols()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), 'missing export %s' % n
+    from mystic_b200 import _native
+    assert sorted(_native.EXPORTS) == names
+    assert _native.lib.mb2_abi_version() == 1
+
+
+def test_product_does_not_import_the_oracle():
+    """the oracle is test infrastructure: nothing under mystic_b200/ may reference it"""
+    pkg = os.path.join(REPO, 'mystic_b200')
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh', '.h')):
+                text = open(os.path.join(root, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle\b', text, flags=re.M), f
+                assert 'de_oracle' not in text.replace('oracle/de_oracle.py', ''), f
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        return
+    import pytest
+    from mystic_b200 import DifferentialEvolutionSolver2, models
+    s = DifferentialEvolutionSolver2(3, 8)
+    s.SetRandomInitialPoints([-1.] * 3, [1.] * 3)
+    with pytest.raises(RuntimeError):
+        s.Step(models.rosen)

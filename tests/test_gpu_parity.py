@@ -1,0 +1,286 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the recorded reference runs.
+
+Bars (north_star): trial vectors, selections (populations) and best-member indices bit-exact in
+validation (replay) mode; energies within 1e-12 relative.  For griewangk the tolerance is
+|dE| <= 1e-12 * max(|f|, term1 + |term2| + 1) because term1 - term2 + 1 cancels near the optimum
+and CUDA's cos differs from glibc's by <= 2 ulp (hard parts)."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import de_oracle as orc
+from tests import _golden as G
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-12
+
+
+def energy_close(dev, ref, x=None, cost=None, what=''):
+    dev = np.asarray(dev, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert dev.shape == ref.shape, what
+    both_inf = np.isinf(dev) & np.isinf(ref) & (np.sign(dev) == np.sign(ref))
+    assert (np.isinf(dev) == np.isinf(ref)).all(), '%s: inf pattern differs' % what
+    scale = np.abs(ref)
+    if cost == 'griewangk' and x is not None:
+        xx = np.atleast_2d(x)
+        scale = np.maximum(scale, (xx * xx).sum(axis=1) / 4000. + 2.0)
+    ok = both_inf | (np.abs(dev - ref) <= RTOL * scale)
+    if not ok.all():
+        i = int(np.argmax(~ok))
+        raise AssertionError('%s: energy mismatch at %d: %r vs %r' % (what, i, dev[i], ref[i]))
+
+
+def configure(eng, meta):
+    from mystic_b200 import models, penalty
+    lo, hi, mode = G.bounds_of(meta)
+    eng.set_bounds(mode, lo, hi)
+    cost = getattr(models, meta['cost'])
+    eng.set_cost(cost.cost_id, cost.params(tuple(meta.get('ExtraArgs') or ())))
+    if meta.get('penalty'):
+        def pen(x):
+            return 0.0
+        for t in meta['penalty']:
+            pen = getattr(penalty, t['ptype'])(penalty.linear(t['G'], t['h']), k=t['k'], h=t['hpow'])(pen)
+        eng.set_penalty(*pen.device_terms(meta['dim']))
+    sid = orc.STRATEGIES[meta['strategy']][0]
+    eng.set_strategy(sid, meta['F_eff'], meta['CR_eff'])
+
+
+@pytest.mark.parametrize('name', G.names())
+def test_engine_replay_matches_reference_recording(name):
+    """free-running: recorded initial population + recorded draws in; every generation's trial
+    vectors / populations / best solution bit-exact, energies <= 1e-12, evaluation counts exact"""
+    from mystic_b200.engine import DeviceEngine
+    meta, z = G.load(name)
+    NP, D = z['pop0'].shape
+    eng = DeviceEngine(NP, D, keep_trials=True)
+    configure(eng, meta)
+    eng.upload_population(z['pop0'])
+    evals = 0
+    for g in range(meta['generations'] + 1):
+        if g == 0:
+            eng.eval_initial()
+        else:
+            eng.set_rng_replay(z['donors'][g - 1], z['nstart'][g - 1], z['uni'][g - 1])
+            eng.step()
+        best_e, best_idx, n_inf, n_acc, gen, best_x = eng.read_result()
+        assert gen == g
+        trial, trial_e = eng.trials()
+        tag = '%s gen %d' % (name, g)
+        G.assert_bits_equal(trial, z['trial'][g], tag + ' trial')
+        energy_close(trial_e, z['trialE'][g], trial, meta['cost'], tag + ' trialE')
+        G.assert_bits_equal(eng.population(), z['pop'][g], tag + ' population')
+        energy_close(eng.energies(), z['popE'][g], eng.population(), meta['cost'], tag + ' popE')
+        energy_close([best_e], [z['bestE'][g]], best_x, meta['cost'], tag + ' bestE')
+        G.assert_bits_equal(best_x, z['bestX'][g], tag + ' bestX')
+        evals += NP - n_inf
+        assert evals == int(z['evals'][g]), tag
+        prev = z['popE'][g - 1] if g else np.full(NP, np.inf)
+        assert n_acc == int((z['trialE'][g] < prev).sum()), tag
+        if g == 0 or z['bestE'][g] < z['bestE'][g - 1]:
+            # the member that became best is where the kernel says it is
+            assert best_idx >= 0 and np.array_equal(eng.population()[best_idx], best_x), tag
+    eng.close()
+
+
+def _solver_case(meta, z, rng):
+    from tests.test_host_solver import make_solver
+    return make_solver(meta, z, rng, engine=None)
+
+
+@pytest.mark.parametrize('name', ['c1_rosen3_best1exp', 'c1b_rosen3_best1exp_ctor', 'strat_Best1Bin_rosen8',
+                                  'strat_Rand2Exp_rosen8', 'corana4_rand1bin', 'edge_x0_rosen2',
+                                  'zimmermann_rand1bin', 'edge_np_raised', 'corana8_rand1exp_pen',
+                                  'boundsB_best1bin_rosen16', 'cheb8_best1exp'])
+def test_solver_reference_rng_reproduces_seeded_reference_run(name):
+    """the drop-in solver on the GPU, rng='reference', same random_seed() as the reference run:
+    same generations, evaluations, stop message, bestSolution (bit-exact) and energy history"""
+    from tests.test_host_solver import solve
+    meta, z = G.load(name)
+    random.seed(meta['seed'])
+    s = _solver_case(meta, z, 'reference')
+    if meta['init'][0] == 'random':
+        s.SetRandomInitialPoints(list(meta['init'][1]), list(meta['init'][2]))
+    else:
+        s.SetInitialPoints(list(meta['init'][1]), meta['init'][2])
+    solve(s, meta)
+    assert s.generations == meta['generations']
+    assert s.evaluations == meta['evaluations']
+    assert str(s.Terminated(info=True)) == meta['stop']
+    np.testing.assert_allclose(np.array(s.energy_history), z['energy_history'], rtol=RTOL)
+    G.assert_bits_equal(np.array(s.bestSolution), z['bestX'][-1], 'bestSolution')
+    G.assert_bits_equal(s.population, z['pop'][-1], 'population')
+
+
+def test_baseline_config1_on_device():
+    from mystic_b200 import DifferentialEvolutionSolver2, models, strategy, termination
+    random.seed(123)
+    s = DifferentialEvolutionSolver2(3, 40, rng='reference')
+    s.SetRandomInitialPoints([0.] * 3, [2.] * 3)
+    s.SetEvaluationLimits(generations=99999)
+    s.Solve(models.rosen, termination.VTR(1e-4), strategy=strategy.Best1Exp, CrossProbability=0.5, ScalingFactor=0.6)
+    assert s.generations == 39 and s.evaluations == 1600
+    assert abs(s.bestEnergy - 7.710567500336223e-05) <= RTOL * 7.710567500336223e-05
+    assert list(s.bestSolution) == [1.0012335280875173, 1.0029551101232417, 1.0052618377557658]
+
+
+PHILOX_CASES = [
+    # (dim, NP, strategy, cost, extra, bounds(lo,hi,mode), penalty terms, CR, F, gens)
+    (16, 64, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 12),
+    (16, 64, 'Best1Bin', 'rosen', (), (-2., 2., orc.BOUNDS_REJECT), None, 0.9, 0.8, 12),
+    (7, 33, 'Rand1Exp', 'rosen', (), None, None, 0.9, 0.8, 12),
+    (130, 40, 'Best1Exp', 'rosen', (), None, None, 0.99, 0.8, 6),
+    (300, 36, 'RandToBest1Exp', 'griewangk', (), (-400., 400., orc.BOUNDS_CLAMP), None, 1.0, 0.8, 4),
+    (64, 128, 'Rand1Exp', 'corana', (), (-1000., 1000., orc.BOUNDS_CLAMP),
+     [dict(ptype='quadratic_inequality', G=[1.] * 64, h=100., k=100, hpow=5)], 0.9, 0.8, 8),
+    (9, 48, 'Best2Exp', 'chebyshev8cost', (200,), None, None, 1.0, 0.9, 6),
+    (2, 24, 'Rand2Bin', 'zimmermann', (), (0., 5., orc.BOUNDS_REJECT), None, 0.9, 0.8, 10),
+    (5, 20, 'Best2Bin', 'rosen', (), None, None, 0.0, 0.8, 5),
+    (1024, 96, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
+    (256, 80, 'Best1Bin', 'griewangk', (), (-400., 400., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
+]
+
+
+@pytest.mark.parametrize('case', PHILOX_CASES, ids=lambda c: '%s-%s-D%d' % (c[2], c[3], c[0]))
+def test_philox_mode_matches_oracle_philox(case):
+    """production RNG: device-side population init, donors and crossover masks follow the same
+    Philox protocol as the oracle, so whole trajectories are comparable bit for bit"""
+    from mystic_b200 import models, penalty
+    from mystic_b200.engine import DeviceEngine
+    dim, NP, strat, cost, extra, bounds, pen, CR, F, gens = case
+    seed = 0x5EED0000 + dim * 131 + NP
+    lo = hi = None
+    mode = orc.BOUNDS_NONE
+    if bounds:
+        lo, hi, mode = np.full(dim, bounds[0]), np.full(dim, bounds[1]), bounds[2]
+    ilo = np.full(dim, -3.0) if bounds is None else lo * 1.25   # start partly outside: gen-0 clip
+    ihi = np.full(dim, 3.0) if bounds is None else hi * 1.25
+
+    eng = DeviceEngine(NP, dim, keep_trials=True)
+    c = getattr(models, cost)
+    eng.set_cost(c.cost_id, c.params(extra))
+    eng.set_bounds(mode, lo, hi)
+    terms = pen or ()
+    if pen:
+        def p(x):
+            return 0.0
+        for t in pen:
+            p = getattr(penalty, t['ptype'])(penalty.linear(t['G'], t['h']), k=t['k'], h=t['hpow'])(p)
+        eng.set_penalty(*p.device_terms(dim))
+    eng.set_strategy(orc.STRATEGIES[strat][0], F, CR)
+    eng.set_rng_philox(seed)
+    eng.init_population(seed, ilo, ihi)
+
+    pop0 = orc.philox_init_population(seed, NP, ilo, ihi)
+    G.assert_bits_equal(eng.population(), pop0, 'philox init population')
+    st = orc.DEState(pop0, lo, hi, mode)
+    ocost = orc.make_cost(cost, extra)
+    for g in range(gens + 1):
+        if g == 0:
+            eng.eval_initial()
+            orc.step0(st, ocost, terms)
+        else:
+            eng.step()
+            orc.step(st, strat, CR, F, ocost, terms, philox=dict(seed=seed, offset=0))
+        best_e, best_idx, n_inf, n_acc, gen, best_x = eng.read_result()
+        tag = 'gen %d' % g
+        trial, trial_e = eng.trials()
+        G.assert_bits_equal(trial, st.trialSolution, tag + ' trial')
+        energy_close(trial_e, st.trialEnergy, trial, cost, tag + ' trialE')
+        G.assert_bits_equal(eng.population(), st.population, tag + ' population')
+        G.assert_bits_equal(best_x, st.bestSolution, tag + ' bestX')
+        energy_close([best_e], [st.bestEnergy], best_x, cost, tag + ' bestE')
+        assert n_inf == int(np.isinf(st.trialEnergy).sum())
+        assert n_acc == int(st.accepted.sum())
+    eng.close()
+
+
+def test_device_cost_callable_known_answers():
+    """SURVEY 8(c) known answers through mb2_eval_cost (DeviceCost.__call__)"""
+    from mystic_b200 import models
+    def close(a, b):
+        assert abs(a - b) <= RTOL * max(abs(b), 1e-300) or a == b, (a, b)
+    close(models.rosen([0.8, 1.2, 0.7]), 86.19999999999997)
+    assert models.rosen([1., 1., 1.]) == 0.0
+    close(models.rosen(np.linspace(-2, 2, 7)), 3608.567901234568)
+    close(models.corana([0.3, -0.7, 1.234, 5.0]), 859.6112499999999)
+    close(models.corana([0.3, -0.7, 1.234, 5.0] + [9.0] * 60), 859.6112499999999)
+    assert models.corana([0.04, -0.04, 0.01, 0.0]) == 0.0
+    close(models.griewangk([1., 2., 3.]), 1.0170279701835734)
+    assert abs(models.griewangk([0.] * 10)) <= 1e-15
+    close(models.griewangk(np.linspace(-400, 400, 10)), 164.05614975873598)
+    assert models.zimmermann([7., 2.]) == 0.0
+    assert models.zimmermann([1., 1.]) == 7.0
+    assert models.zimmermann([-1., 6.]) == 1600.0
+    assert models.chebyshev8cost(models.CHEBYSHEV_TARGETS[8]) == 0.0
+    close(models.chebyshev8cost([1.] * 9), 7823.744334789609)
+    close(models.chebyshev8cost([1.] * 9, 4096), 22615.651073208195)
+    close(models.chebyshev8cost([100, -50, 3, 7, -20, 1, 0.5, -2, 1], 4096), 2014464.4595239898)
+
+
+def test_costs_random_batches_match_oracle():
+    """every device cost on random batches, several row lengths (vector and scalar load paths)"""
+    from mystic_b200 import models
+    rng = np.random.default_rng(7)
+    for name, dims, span, extra in (('rosen', (2, 3, 8, 31, 64, 257, 1024), 3., ()),
+                                    ('corana', (1, 2, 3, 4, 9, 64), 1000., ()),
+                                    ('griewangk', (1, 5, 10, 63, 256), 400., ()),
+                                    ('zimmermann', (2,), 8., ()),
+                                    ('chebyshev8cost', (9,), 100., (61,)),
+                                    ('chebyshev8cost', (9,), 3., (4096,)),
+                                    ('chebyshev16cost', (17,), 2., (333,))):
+        for D in dims:
+            X = rng.uniform(-span, span, size=(97, D))
+            got = getattr(models, name)(X, *extra)
+            want = orc.make_cost(name, extra)(X)
+            energy_close(got, want, X, name, '%s D=%d' % (name, D))
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size (Rosenbrock 1024-D, NP=65536, Best1Bin, clamp bounds):
+    size-independent properties instead of an oracle run."""
+    from mystic_b200 import models
+    from mystic_b200.engine import DeviceEngine
+    import torch
+    NP, D = 65536, 1024
+    lo, hi = np.full(D, -5.), np.full(D, 5.)
+    runs = []
+    for rep in range(2):
+        eng = DeviceEngine(NP, D)
+        eng.set_cost(models.rosen.cost_id, [])
+        eng.set_bounds(orc.BOUNDS_CLAMP, lo, hi)
+        eng.set_strategy(orc.STRATEGIES['Best1Bin'][0], 0.8, 0.9)
+        eng.set_rng_philox(0x5EED)
+        eng.init_population(0x5EED, lo, hi)
+        eng.eval_initial()
+        hist = [eng.read_result()]
+        e_prev = eng.energy_tensor().clone()
+        for g in range(4):
+            eng.step()
+            r = eng.read_result()
+            e_now = eng.energy_tensor()
+            assert bool((e_now <= e_prev).all())                       # greedy selection never worsens a member
+            assert int((e_now < e_prev).sum()) == r[3]                  # n_accepted
+            assert r[0] == float(e_now.min())                           # bestEnergy = min(popEnergy)
+            assert r[0] <= hist[-1][0]
+            idx = int(torch.argmin(e_now))                              # torch.argmin: first minimal index
+            pop = eng.population_tensor()
+            assert bool((pop >= -5.).all()) and bool((pop <= 5.).all())  # clamp respected
+            if r[1] >= 0 and r[0] < hist[-1][0]:
+                assert r[1] == idx
+                assert np.array_equal(pop[idx].cpu().numpy(), r[5])     # bestSolution is that member
+            hist.append(r)
+            e_prev = e_now.clone()
+        # stored energies are the cost of the stored members (idempotence of evaluation)
+        sample = torch.arange(0, NP, 997, device=pop.device)
+        re = eng.eval_cost(pop[sample].cpu().numpy())
+        assert np.array_equal(re, e_now[sample].cpu().numpy())
+        # spot check against the oracle
+        sub = pop[sample[:16]].cpu().numpy()
+        energy_close(re[:16], orc.cost_rosen(sub), sub, 'rosen', 'oracle spot check')
+        runs.append((eng.population_tensor().clone(), [h[0] for h in hist]))
+        eng.close()
+    assert torch.equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]   # deterministic

@@ -1,0 +1,191 @@
+"""Host logic of mystic_b200.solver (CPU, no GPU): Step/Solve/termination/keyword handling and
+the reference's bookkeeping, checked against recordings of the unmodified reference.  The
+generation step itself is supplied by the test-only OracleEngine (tests/_oracle_engine.py); the
+CUDA path has the same tests in tests/test_gpu_parity.py."""
+import random
+
+import numpy as np
+import pytest
+
+import mystic_b200
+from mystic_b200 import models, penalty, strategy, termination
+from mystic_b200.solver import DifferentialEvolutionSolver2
+from tests import _golden as G
+from tests._oracle_engine import OracleEngine
+
+
+def make_solver(meta, z, rng, engine=OracleEngine, **extra):
+    kw = dict(rng=rng, engine=engine)
+    kw.update(extra)
+    if meta['via'] == 'ctor':
+        kw.update(CrossProbability=meta['CR'], ScalingFactor=meta['F'])
+    s = DifferentialEvolutionSolver2(meta['dim'], meta['NP'], **kw)
+    assert s.nPop == z['pop0'].shape[0]
+    if meta.get('bounds'):
+        lo, hi, tight = meta['bounds']
+        if tight:
+            s.SetStrictRanges(lo, hi, tight=True)
+        else:
+            s.SetStrictRanges(lo, hi)
+    if meta.get('penalty'):
+        def pen(x):
+            return 0.0
+        for t in meta['penalty']:
+            pen = getattr(penalty, t['ptype'])(penalty.linear(t['G'], t['h']), k=t['k'], h=t['hpow'])(pen)
+        s.SetPenalty(pen)
+    s.SetEvaluationLimits(generations=meta['maxgen'])
+    return s
+
+
+def solve(s, meta):
+    term = getattr(termination, meta['termination'][0])(*meta['termination'][1:]) if meta.get('termination') \
+        else termination.VTR(-1.0)
+    extra = tuple(meta['ExtraArgs']) if meta.get('ExtraArgs') else None
+    kw = dict(strategy=getattr(strategy, meta['strategy']))
+    if meta['via'] == 'solve':
+        kw.update(CrossProbability=meta['CR'], ScalingFactor=meta['F'])
+    s.Solve(getattr(models, meta['cost']), term, ExtraArgs=extra, **kw)
+
+
+def replay_draws(z):
+    for g in range(z['donors'].shape[0]):
+        yield z['donors'][g], z['nstart'][g], z['uni'][g]
+
+
+def check_against_reference(s, meta, z, exact_energy=True):
+    assert s.generations == meta['generations']
+    assert s.evaluations == meta['evaluations']
+    if exact_energy:
+        G.assert_bits_equal(np.array(s.energy_history), z['energy_history'], 'energy_history')
+    else:
+        np.testing.assert_allclose(np.array(s.energy_history), z['energy_history'], rtol=1e-14)
+    G.assert_bits_equal(np.array(s.bestSolution), z['bestX'][-1], 'bestSolution')
+    G.assert_bits_equal(s.population, z['pop'][-1], 'population')
+    assert str(s.Terminated(info=True)) == meta['stop']
+    # bookkeeping invariants of mystic/tests/test_solver_sanity.py:77-90
+    assert s.generations == len(s._stepmon._y) - 1
+    assert list(s.bestSolution) == list(s._stepmon.x[-1])
+    assert s.bestEnergy == s._stepmon.y[-1]
+
+
+@pytest.mark.parametrize('name', G.names())
+def test_solve_replay_matches_reference(name):
+    """recorded draws in, the reference's whole solve out (counters, histories, stop message)"""
+    meta, z = G.load(name)
+    s = make_solver(meta, z, 'replay')
+    s.SetPopulation(z['pop0'])
+    s.SetReplayDraws(replay_draws(z))
+    solve(s, meta)
+    check_against_reference(s, meta, z, exact_energy=(meta['cost'] != 'griewangk'))
+
+
+@pytest.mark.parametrize('name', ['c1_rosen3_best1exp', 'c1b_rosen3_best1exp_ctor', 'strat_Best1Bin_rosen8',
+                                  'strat_Rand2Exp_rosen8', 'corana4_rand1bin', 'edge_x0_rosen2',
+                                  'zimmermann_rand1bin', 'edge_np_raised'])
+def test_solve_reference_rng_reproduces_seeded_reference_run(name):
+    """rng='reference': same random_seed() => the reference's trajectory, draws made on the host by the
+    same stdlib calls in the same order (no recording involved)"""
+    meta, z = G.load(name)
+    random.seed(meta['seed'])
+    s = make_solver(meta, z, 'reference')
+    if meta['init'][0] == 'random':
+        s.SetRandomInitialPoints(list(meta['init'][1]), list(meta['init'][2]))
+    else:
+        s.SetInitialPoints(list(meta['init'][1]), meta['init'][2])
+    G.assert_bits_equal(s.population, z['pop0'], 'initial population')
+    solve(s, meta)
+    check_against_reference(s, meta, z)
+
+
+def test_baseline_config1_golden_values():
+    """BASELINE config 1 / SURVEY 8(c): 39 generations, 1600 evaluations, bestEnergy 7.710567500336223e-05"""
+    meta, z = G.load('c1_rosen3_best1exp')
+    random.seed(123)
+    s = DifferentialEvolutionSolver2(3, 40, rng='reference', engine=OracleEngine)
+    s.SetRandomInitialPoints([0.] * 3, [2.] * 3)
+    s.SetEvaluationLimits(generations=99999)
+    s.Solve(models.rosen, termination.VTR(1e-4), strategy=strategy.Best1Exp, CrossProbability=0.5, ScalingFactor=0.6)
+    assert s.generations == 39 and s.evaluations == 1600
+    assert s.bestEnergy == 7.710567500336223e-05
+    assert list(s.bestSolution) == [1.0012335280875173, 1.0029551101232417, 1.0052618377557658]
+    assert list(s.energy_history[:5]) == [17.784260845848216, 17.784260845848216, 2.4416751888867902,
+                                          2.4416751888867902, 1.5646391444680794]
+    # the reference quirk: Solve(CrossProbability=...) does not survive the first Step
+    assert (s.probability, s.scale) == (0.9, 0.8)
+
+
+def test_keyword_handling():
+    s = DifferentialEvolutionSolver2(3, 8, engine=OracleEngine, cross=0.3, scale=0.4, strategy='Rand1Exp')
+    assert (s.probability, s.scale, s.strategy) == (0.3, 0.4, 'Rand1Exp')
+    with pytest.raises(KeyError):
+        DifferentialEvolutionSolver2(3, 8, cross=0.3, CrossProbability=0.2)
+    with pytest.raises(KeyError):
+        DifferentialEvolutionSolver2(3, 8, scale=0.3, ScalingFactor=0.2)
+    assert DifferentialEvolutionSolver2(10, 2).nPop == 10      # NP = max(NP, dim, 4)
+    assert DifferentialEvolutionSolver2(2, 1).nPop == 4
+    # Step() keywords are honoured and sticky
+    s.SetRandomInitialPoints([-1.] * 3, [1.] * 3)
+    s.Step(models.rosen, CrossProbability=0.25)
+    assert s.probability == 0.25
+    s.Step()
+    assert s.probability == 0.25
+    # unknown strategy names fall back to Best1Bin (differential_evolution.py:682)
+    s2 = DifferentialEvolutionSolver2(3, 8, engine=OracleEngine, strategy='NoSuchStrategy')
+    s2.SetRandomInitialPoints([-1.] * 3, [1.] * 3)
+    s2.Step(models.rosen)
+    assert s2.strategy == 'Best1Bin'
+
+
+def test_setter_errors_match_reference():
+    s = DifferentialEvolutionSolver2(3, 8, engine=OracleEngine)
+    with pytest.raises(ValueError):
+        s.SetStrictRanges([0, 0, 0], [1, -1, 1])
+    with pytest.raises(ValueError):
+        s.SetStrictRanges([0, 0], [1, 1])
+    with pytest.raises(ValueError):
+        s.SetStrictRanges([0, 0, 0], [1, 1, 1], tight=False, clip=True)
+    with pytest.raises(TypeError):
+        s.SetConstraints(5)
+    with pytest.raises(TypeError):
+        s.SetPenalty(5)
+    with pytest.raises(TypeError):
+        s.SetConstraints(lambda x: x)      # host callables cannot run on the device
+    with pytest.raises(TypeError):
+        s.SetPenalty(lambda x: 0.0)
+    with pytest.raises(TypeError):
+        s.SetObjective(lambda x: sum(x))   # no CPU cost path
+    with pytest.raises(ValueError):
+        s.SetInitialPoints([1., 2.])
+    with pytest.raises(ValueError):
+        s.SetRandomInitialPoints([0.], [1.])
+    s.SetConstraints(None)
+    s.SetPenalty(None)
+
+
+def test_maxiter_limits():
+    """mystic/tests/test_solver_sanity.py:258-276: maxiter in {0,1,2}"""
+    for maxiter in (0, 1, 2):
+        random.seed(111)
+        s = DifferentialEvolutionSolver2(2, 40, rng='reference', engine=OracleEngine)
+        s.SetRandomInitialPoints([-5.] * 2, [5.] * 2)
+        s.SetStrictRanges([-5.] * 2, [5.] * 2)
+        s.SetEvaluationLimits(generations=maxiter)
+        s.Solve(models.rosen, termination.VTR(1e-10))
+        assert s.generations == maxiter
+        assert 0 < s.evaluations <= (maxiter + 1) * 40
+        assert s.generations == len(s._stepmon._y) - 1
+
+
+def test_generation_monitor_prepend_and_null():
+    from mystic_b200.monitors import Monitor, Null, VerboseMonitor
+    s = DifferentialEvolutionSolver2(3, 8, engine=OracleEngine)
+    s.SetRandomInitialPoints([-1.] * 3, [1.] * 3)
+    s.Step(models.rosen)
+    s.Step()
+    m = Monitor()
+    s.SetGenerationMonitor(m)
+    assert len(m) == 2 and s.generations == 1
+    s.SetGenerationMonitor(Null())     # Null is not allowed as a generation monitor: replaced by Monitor
+    assert len(s._stepmon) == 2
+    s.SetGenerationMonitor(VerboseMonitor(1000), new=True)
+    assert len(s._stepmon) == 0
