@@ -1,0 +1,442 @@
+/*
+ * de_oracle.c -- plain C restatement of mystic's DifferentialEvolutionSolver2 generation step.
+ *
+ * TEST INFRASTRUCTURE ONLY (checker and CPU baseline; see oracle/README.md).  Nothing in the
+ * product package mystic_b200/ links or loads this file.  It follows oracle/de_oracle.py
+ * function by function and is checked bit-for-bit against it and against the recordings of the
+ * unmodified reference (tests/test_oracle_c.py), so: PARITY PINNED.
+ *
+ * Citations are file:line in the mystic repository.  OpenMP parallelises over candidates; the
+ * arithmetic of every candidate is sequential and compiled with -ffp-contract=off, so results
+ * do not depend on the thread count.
+ *
+ * build: make -C oracle   (gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+enum { BASE_BEST1 = 0, BASE_RAND1 = 1, BASE_RANDTOBEST1 = 2, BASE_BEST2 = 3, BASE_RAND2 = 4 };
+enum { XOVER_EXP = 0, XOVER_BIN = 1 };
+enum { BOUNDS_NONE = 0, BOUNDS_REJECT = 1, BOUNDS_CLAMP = 2 };
+enum { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4 };
+
+typedef struct {
+  int32_t dim;
+  int32_t strategy; /* ids of mystic/strategy.py in file order, 0..9 */
+  int64_t np;
+  double F, CR;
+  int32_t bounds_mode;
+  int32_t cost;
+  const double* lo;
+  const double* hi;
+  /* chebyshev (_model_helper.py:16-33) */
+  int32_t cheb_M;
+  int32_t cheb_order;
+  const double* cheb_target;
+  /* stacked linear penalties, term 0 innermost (penalty.py) */
+  int32_t n_pen;
+  int32_t pad_;
+  const int32_t* pen_type;
+  const double* pen_G;
+  const double* pen_h;
+  const double* pen_k; /* k*h**n */
+} orc_config;
+
+/* strategy id -> base, crossover, donors (strategy.py:34-311; only Best1Bin is binomial) */
+static void strategy_info(int s, int* base, int* xover, int* k) {
+  static const int B[10] = {BASE_BEST1, BASE_BEST1, BASE_RAND1, BASE_RANDTOBEST1, BASE_BEST2,
+                            BASE_RAND2, BASE_RAND1, BASE_RANDTOBEST1, BASE_BEST2, BASE_RAND2};
+  static const int K[5] = {2, 3, 2, 4, 5};
+  *base = B[s];
+  *xover = (s == 1) ? XOVER_BIN : XOVER_EXP;
+  *k = K[*base];
+}
+
+/* ---------------------------------------------------------------- Philox4x32-10 */
+static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    c1 = (uint32_t)p1;
+    c3 = (uint32_t)p0;
+    c0 = n0;
+    c2 = n2;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+static uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
+
+static void draw_donors(uint64_t seed, uint32_t gen, uint32_t cand_global, int64_t cand, int64_t np, int dim, int k,
+                        int64_t* donors, int* nstart) {
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  uint64_t r[6];
+  for (int b = 0; b < (k + 2) / 2; ++b) {
+    uint32_t v[4];
+    philox((uint32_t)b, cand_global, gen, 0u, k0, k1, v);
+    r[2 * b] = ((uint64_t)v[0] << 32) | v[1];
+    r[2 * b + 1] = ((uint64_t)v[2] << 32) | v[3];
+  }
+  int64_t ex[6];
+  int nex = 1;
+  ex[0] = cand;
+  for (int i = 0; i < k; ++i) {
+    int64_t idx = (int64_t)mulhi64(r[i], (uint64_t)(np - 1 - i));
+    for (int e = 0; e < nex; ++e)
+      if (idx >= ex[e]) ++idx;
+    donors[i] = idx;
+    int pos = nex;
+    while (pos > 0 && ex[pos - 1] > idx) {
+      ex[pos] = ex[pos - 1];
+      --pos;
+    }
+    ex[pos] = idx;
+    ++nex;
+  }
+  *nstart = (int)mulhi64(r[k], (uint64_t)dim);
+}
+
+static uint64_t crossover_threshold(double cr) {
+  if (!(cr > 0.0)) return 0;
+  if (cr >= 1.0) return 4294967296ull;
+  return (uint64_t)floor(cr * 4294967296.0);
+}
+
+/* ---------------------------------------------------------------- costs */
+/* numpy.sum of a contiguous double vector: pairwise, 8-lane blocks of 128
+ * (numpy/core/src/umath/loops_utils.h.src DOUBLE_pairwise_sum) */
+static double np_pairwise_sum(const double* a, int64_t n) {
+  if (n < 8) {
+    double res = 0.;
+    for (int64_t i = 0; i < n; ++i) res += a[i];
+    return res;
+  } else if (n <= 128) {
+    double r[8];
+    int64_t i;
+    for (int j = 0; j < 8; ++j) r[j] = a[j];
+    for (i = 8; i < n - (n % 8); i += 8)
+      for (int j = 0; j < 8; ++j) r[j] += a[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res += a[i];
+    return res;
+  } else {
+    int64_t n2 = n / 2;
+    n2 -= n2 % 8;
+    return np_pairwise_sum(a, n2) + np_pairwise_sum(a + n2, n - n2);
+  }
+}
+
+static double cost_rosen(const double* x, int D, double* scratch) {
+  /* dejong.py:98-101 */
+  if (D < 2) return 0.0;
+  for (int i = 0; i < D - 1; ++i) {
+    double t = x[i + 1] - x[i] * x[i];
+    double u = 1 - x[i];
+    scratch[i] = 100.0 * (t * t) + u * u;
+  }
+  return np_pairwise_sum(scratch, D - 1);
+}
+
+static double sign_(double v) { return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : 0.0); }
+
+static double cost_corana(const double* c, int D) {
+  /* storn.py:77-96 */
+  static const double d[4] = {1., 1000., 10., 100.};
+  double x[4] = {0., 0., 0., 0.};
+  if (D >= 4) {
+    for (int j = 0; j < 4; ++j) x[j] = c[j];
+  } else {
+    if (D >= 1) x[0] = c[0];
+    if (D >= 2) x[2] = c[1];
+    if (D >= 3) x[3] = c[2];
+  }
+  double r = 0.0;
+  for (int j = 0; j < 4; ++j) {
+    double zj = floor(fabs(x[j] / 0.2) + 0.49999) * sign_(x[j]) * 0.2;
+    if (fabs(x[j] - zj) < 0.05)
+      r += 0.15 * pow(zj - 0.05 * sign_(zj), 2) * d[j];
+    else
+      r += d[j] * x[j] * x[j];
+  }
+  return r;
+}
+
+static double cost_griewangk(const double* c, int D) {
+  /* storn.py:135-139 (plain left-to-right sum; see oracle/de_oracle.py:cost_griewangk) */
+  double s = 0.0, p = 1.0;
+  for (int i = 0; i < D; ++i) s += c[i] * c[i];
+  for (int i = 0; i < D; ++i) p = p * cos(c[i] / sqrt(i + 1.0));
+  return s / 4000. - p + 1;
+}
+
+static double cost_zimmermann(const double* c) {
+  /* storn.py:182-191 */
+  double x0 = c[0], x1 = c[1];
+  double f8 = 9 - x0 - x1;
+  double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  if (x0 < 0) c0 = -100 * x0;
+  if (x1 < 0) c1 = -100 * x1;
+  double xx = (x0 - 3.) * (x0 - 3) + (x1 - 2.) * (x1 - 2);
+  if (xx > 16) c2 = 100 * (xx - 16);
+  if (x0 * x1 > 14) c3 = 100 * (x0 * x1 - 14.);
+  double m = f8;
+  if (c0 > m) m = c0;
+  if (c1 > m) m = c1;
+  if (c2 > m) m = c2;
+  if (c3 > m) m = c3;
+  return m;
+}
+
+static double polyeval(const double* c, int n, double x) {
+  /* math/poly.py:37-39 */
+  double val = 0 * x;
+  for (int j = 0; j < n; ++j) val = c[j] + val * x;
+  return val;
+}
+
+static double cost_chebyshev(const double* c, int D, const orc_config* cfg) {
+  /* _model_helper.py:16-33 */
+  double result = 0.0, x = -1.0;
+  const int M = cfg->cheb_M;
+  const double dx = 2.0 / (M - 1);
+  for (int i = 0; i < M; ++i) {
+    double px = polyeval(c, D, x);
+    if (px < -1 || px > 1) result += (1 - px) * (1 - px);
+    x += dx;
+  }
+  double px = polyeval(c, D, 1.2) - polyeval(cfg->cheb_target, cfg->cheb_order + 1, 1.2);
+  if (px < 0) result += px * px;
+  px = polyeval(c, D, -1.2) - polyeval(cfg->cheb_target, cfg->cheb_order + 1, -1.2);
+  if (px < 0) result += px * px;
+  return result;
+}
+
+static double penalty_value(const double* x, int D, const orc_config* cfg) {
+  double total = 0.0;
+  for (int t = 0; t < cfg->n_pen; ++t) {
+    const double* g = cfg->pen_G + (int64_t)t * D;
+    double acc = 0.0;
+    for (int j = 0; j < D; ++j) acc = acc + g[j] * x[j];
+    double pf = acc - cfg->pen_h[t];
+    double k = cfg->pen_k[t], v;
+    switch (cfg->pen_type[t]) {
+      case 0: v = k * pow(pf, 2); break;                        /* penalty.py:88  */
+      case 1: v = k * fabs(pf); break;                          /* penalty.py:147 */
+      case 2: { double m = pf > 0. ? pf : 0.; v = (2 * k) * pow(m, 2); break; }  /* :388 */
+      default: { double m = pf > 0. ? pf : 0.; v = (2 * k) * fabs(m); break; }   /* :447 */
+    }
+    total = v + total;
+  }
+  return total;
+}
+
+/* (inf if out of range else cost) + penalty: differential_evolution.py:515-525, tools.py:386-389,420-426 */
+static double energy_of(const double* x, const orc_config* cfg, double* scratch) {
+  const int D = cfg->dim;
+  int oob = 0;
+  if (cfg->bounds_mode != BOUNDS_NONE)
+    for (int i = 0; i < D; ++i) oob |= (x[i] < cfg->lo[i]) || (x[i] > cfg->hi[i]);
+  double raw = INFINITY;
+  if (!oob) {
+    switch (cfg->cost) {
+      case COST_ROSEN: raw = cost_rosen(x, D, scratch); break;
+      case COST_CORANA: raw = cost_corana(x, D); break;
+      case COST_GRIEWANGK: raw = cost_griewangk(x, D); break;
+      case COST_ZIMMERMANN: raw = cost_zimmermann(x); break;
+      default: raw = cost_chebyshev(x, D, cfg); break;
+    }
+  }
+  return raw + penalty_value(x, D, cfg);
+}
+
+/* selection + best: differential_evolution.py:603-613.  Sequential (ascending candidate). */
+static void select_best(int64_t np, int D, const double* trial_e, const double* e_cur, const double* pop_next,
+                        double* best_e, int64_t* best_idx, double* best_x, int64_t* n_inf, int64_t* n_acc) {
+  int64_t ninf = 0, nacc = 0, w = -1;
+  double be = *best_e;
+  for (int64_t c = 0; c < np; ++c) {
+    if (isinf(trial_e[c])) ++ninf;
+    if (trial_e[c] < e_cur[c]) {
+      ++nacc;
+      if (trial_e[c] < be) {
+        be = trial_e[c];
+        w = c;
+      }
+    }
+  }
+  if (w >= 0) {
+    *best_e = be;
+    *best_idx = w;
+    memcpy(best_x, pop_next + w * D, sizeof(double) * D);
+  } else {
+    *best_idx = -1;
+  }
+  *n_inf = ninf;
+  *n_acc = nacc;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* generation 0: clip into the strict range (differential_evolution.py:516-520), evaluate, select.
+ * pop_next receives the (clipped) population, e_next its energies; trial_e_out [np] scratch/out. */
+int orc_step0(const orc_config* cfg, const double* pop_cur, double* pop_next, double* e_next, double* best_x,
+              double* best_e, int64_t* best_idx, double* trial_e_out, int64_t* n_inf, int64_t* n_acc) {
+  const int D = cfg->dim;
+  const int64_t np = cfg->np;
+#pragma omp parallel
+  {
+    double* scratch = (double*)malloc(sizeof(double) * (D + 1));
+#pragma omp for schedule(static)
+    for (int64_t c = 0; c < np; ++c) {
+      double* row = pop_next + c * D;
+      for (int i = 0; i < D; ++i) {
+        double v = pop_cur[c * D + i];
+        if (cfg->bounds_mode != BOUNDS_NONE) v = fmin(fmax(v, cfg->lo[i]), cfg->hi[i]);
+        row[i] = v;
+      }
+      double E = energy_of(row, cfg, scratch);
+      trial_e_out[c] = E;
+      e_next[c] = (E < INFINITY) ? E : INFINITY;
+    }
+    free(scratch);
+  }
+  double* inf_cur = (double*)malloc(sizeof(double) * np);
+  for (int64_t c = 0; c < np; ++c) inf_cur[c] = INFINITY;
+  *best_e = INFINITY;
+  memcpy(best_x, pop_next, sizeof(double) * D);
+  select_best(np, D, trial_e_out, inf_cur, pop_next, best_e, best_idx, best_x, n_inf, n_acc);
+  free(inf_cur);
+  return 0;
+}
+
+/* one generation g >= 1.  rng_mode 0: Philox(seed, generation, offset); 1: replayed draws
+ * (donors [np,5] int32, nstart [np] int32, uni [np, dim+1] double, NaN = not drawn).
+ * trial_out [np,dim] and trial_e_out [np] receive every trial (trial_out may be NULL). */
+int orc_step(const orc_config* cfg, const double* pop_cur, double* pop_next, const double* e_cur, double* e_next,
+             double* best_x, double* best_e, int64_t* best_idx, int rng_mode, uint64_t seed, uint32_t generation,
+             int64_t offset, const int32_t* r_donors, const int32_t* r_nstart, const double* r_uni,
+             double* trial_out, double* trial_e_out, int64_t* n_inf, int64_t* n_acc) {
+  const int D = cfg->dim;
+  const int64_t np = cfg->np;
+  int base, xover, k;
+  strategy_info(cfg->strategy, &base, &xover, &k);
+  const double F = cfg->F, CR = cfg->CR;
+  const uint64_t thr = crossover_threshold(CR);
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma omp parallel
+  {
+    double* t = (double*)malloc(sizeof(double) * (D + 1));
+    double* scratch = (double*)malloc(sizeof(double) * (D + 1));
+    unsigned char* mask = (unsigned char*)malloc(D);
+#pragma omp for schedule(static)
+    for (int64_t c = 0; c < np; ++c) {
+      int64_t r[5] = {0, 0, 0, 0, 0};
+      int n;
+      const uint32_t cg = (uint32_t)(offset + c);
+      if (rng_mode == 1) {
+        for (int j = 0; j < k; ++j) r[j] = r_donors[c * 5 + j];
+        n = r_nstart[c];
+      } else {
+        draw_donors(seed, generation, cg, c, np, D, k, r, &n);
+      }
+      /* crossover mask */
+      if (xover == XOVER_BIN) {
+        /* strategy.py:79-85 */
+        for (int i = 0; i < D; ++i) {
+          int hit;
+          if (rng_mode == 1) {
+            hit = r_uni[c * (int64_t)(D + 1) + i] < CR;
+          } else {
+            uint32_t v[4];
+            philox((uint32_t)(i >> 2), cg, generation, 1u, k0, k1, v);
+            hit = (uint64_t)v[i & 3] < thr;
+          }
+          mask[i] = (unsigned char)(hit || i == n);
+        }
+      } else {
+        /* strategy.py:48-56: L leading successes, capped at D */
+        int L = 0;
+        uint32_t v[4];
+        while (L < D) {
+          int ok;
+          if (rng_mode == 1) {
+            ok = r_uni[c * (int64_t)(D + 1) + L] < CR;
+          } else {
+            if ((L & 3) == 0) philox((uint32_t)(L >> 2), cg, generation, 1u, k0, k1, v);
+            ok = (uint64_t)v[L & 3] < thr;
+          }
+          if (!ok) break;
+          ++L;
+        }
+        memset(mask, 0, D);
+        for (int j = 0; j < L; ++j) mask[(n + j) % D] = 1;
+      }
+      /* mutation, reference operation order (strategy.py formulas) */
+      const double* p = pop_cur + c * D;
+      const double* p0 = pop_cur + r[0] * D;
+      const double* p1 = pop_cur + r[1] * D;
+      const double* p2 = pop_cur + r[2] * D;
+      const double* p3 = pop_cur + r[3] * D;
+      const double* p4 = pop_cur + r[4] * D;
+      for (int i = 0; i < D; ++i) {
+        double v = p[i];
+        if (mask[i]) {
+          switch (base) {
+            case BASE_BEST1: v = best_x[i] + F * (p0[i] - p1[i]); break;
+            case BASE_RAND1: v = p0[i] + F * (p1[i] - p2[i]); break;
+            case BASE_RANDTOBEST1: v = p[i] + (F * (best_x[i] - p[i]) + F * (p0[i] - p1[i])); break;
+            case BASE_BEST2: v = best_x[i] + F * (p0[i] + p1[i] - p2[i] - p3[i]); break;
+            default: v = p0[i] + F * (p1[i] + p2[i] - p3[i] - p4[i]); break;
+          }
+        }
+        if (cfg->bounds_mode == BOUNDS_CLAMP) { /* symbolic.py:1139-1144 */
+          v = (v > cfg->lo[i]) ? v : cfg->lo[i];
+          v = (v < cfg->hi[i]) ? v : cfg->hi[i];
+        }
+        t[i] = v;
+      }
+      const double E = energy_of(t, cfg, scratch);
+      trial_e_out[c] = E;
+      if (trial_out) memcpy(trial_out + c * D, t, sizeof(double) * D);
+      const int acc = E < e_cur[c];
+      e_next[c] = acc ? E : e_cur[c];
+      memcpy(pop_next + c * D, acc ? t : p, sizeof(double) * D);
+    }
+    free(t);
+    free(scratch);
+    free(mask);
+  }
+  select_best(np, D, trial_e_out, e_cur, pop_next, best_e, best_idx, best_x, n_inf, n_acc);
+  return 0;
+}
+
+/* Philox stream 2: device-side SetRandomInitialPoints twin (abstract_solver.py:532-534) */
+int orc_init_population(double* pop, int64_t np, int D, int64_t offset, const double* lo, const double* hi,
+                        uint64_t seed) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma omp parallel for schedule(static)
+  for (int64_t c = 0; c < np; ++c) {
+    for (int b = 0; b < (D + 1) / 2; ++b) {
+      uint32_t v[4];
+      philox((uint32_t)b, (uint32_t)(offset + c), 0u, 2u, k0, k1, v);
+      uint64_t r0 = ((uint64_t)v[0] << 32) | v[1], r1 = ((uint64_t)v[2] << 32) | v[3];
+      int j = 2 * b;
+      pop[c * D + j] = lo[j] + (hi[j] - lo[j]) * ((double)(r0 >> 11) * (1.0 / 9007199254740992.0));
+      if (j + 1 < D) pop[c * D + j + 1] = lo[j + 1] + (hi[j + 1] - lo[j + 1]) * ((double)(r1 >> 11) * (1.0 / 9007199254740992.0));
+    }
+  }
+  return 0;
+}

@@ -143,6 +143,10 @@ def record(case):
             'evals': int(solver.evaluations),
         })
 
+    # Mersenne-Twister state right before Solve(): building the symbolic bounds constraint in
+    # SetStrictRanges(tight=True) consumes stdlib draws inside mystic.symbolic.simplify
+    # (symbolic.py:575-812), so seed + setter order alone does not determine it.
+    mt_state = np.array(_stdlib_random.getstate()[1], dtype=np.uint32)
     saved = mstrategy.random
     mstrategy.random = rec
     try:
@@ -193,7 +197,7 @@ def record(case):
         'bestX': np.stack([s['bestX'] for s in snaps]),
         'evals': np.array([s['evals'] for s in snaps], dtype=np.int64),
         'energy_history': np.array(solver.energy_history, dtype=np.float64),
-        'donors': donors, 'nstart': nstart, 'nuni': nuni, 'uni': uni,
+        'donors': donors, 'nstart': nstart, 'nuni': nuni, 'uni': uni, 'mt_state': mt_state,
     }
     return out
 

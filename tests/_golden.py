@@ -40,3 +40,9 @@ def assert_bits_equal(a, b, what=''):
         bad = np.argwhere(~same)
         i = tuple(bad[0])
         raise AssertionError('%s: %d mismatches, first at %s: %r vs %r' % (what, len(bad), i, a[i], b[i]))
+
+
+def restore_mt_state(z):
+    """put stdlib `random` into the state the reference had right before Solve()"""
+    import random
+    random.setstate((3, tuple(int(v) for v in z['mt_state']), None))

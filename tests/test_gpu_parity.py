@@ -91,13 +91,11 @@ def _solver_case(meta, z, rng):
     return make_solver(meta, z, rng, engine=None)
 
 
-@pytest.mark.parametrize('name', ['c1_rosen3_best1exp', 'c1b_rosen3_best1exp_ctor', 'strat_Best1Bin_rosen8',
-                                  'strat_Rand2Exp_rosen8', 'corana4_rand1bin', 'edge_x0_rosen2',
-                                  'zimmermann_rand1bin', 'edge_np_raised', 'corana8_rand1exp_pen',
-                                  'boundsB_best1bin_rosen16', 'cheb8_best1exp'])
+@pytest.mark.parametrize('name', G.names())
 def test_solver_reference_rng_reproduces_seeded_reference_run(name):
-    """the drop-in solver on the GPU, rng='reference', same random_seed() as the reference run:
-    same generations, evaluations, stop message, bestSolution (bit-exact) and energy history"""
+    """the drop-in solver on the GPU, rng='reference', same seed and Mersenne-Twister state as the
+    reference run: same generations, evaluations, stop message, bestSolution (bit-exact) and
+    energy history"""
     from tests.test_host_solver import solve
     meta, z = G.load(name)
     random.seed(meta['seed'])
@@ -106,11 +104,13 @@ def test_solver_reference_rng_reproduces_seeded_reference_run(name):
         s.SetRandomInitialPoints(list(meta['init'][1]), list(meta['init'][2]))
     else:
         s.SetInitialPoints(list(meta['init'][1]), meta['init'][2])
+    G.restore_mt_state(z)
     solve(s, meta)
     assert s.generations == meta['generations']
     assert s.evaluations == meta['evaluations']
     assert str(s.Terminated(info=True)) == meta['stop']
-    np.testing.assert_allclose(np.array(s.energy_history), z['energy_history'], rtol=RTOL)
+    energy_close(np.array(s.energy_history), z['energy_history'], np.array(s.solution_history), meta['cost'],
+                 'energy_history')
     G.assert_bits_equal(np.array(s.bestSolution), z['bestX'][-1], 'bestSolution')
     G.assert_bits_equal(s.population, z['pop'][-1], 'population')
 
