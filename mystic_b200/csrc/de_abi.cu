@@ -5,12 +5,14 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
 
 #include "../../include/mystic_b200.h"
 #include "de_kernels.cuh"
+#include "de_tma.cuh"
 
 using namespace mb2;
 
@@ -161,6 +163,49 @@ int ensure_parts(mb2_ctx* c, int n) {
   return MB2_OK;
 }
 
+typedef void (*TmaKernel)(const StepParams, int);
+
+TmaKernel pick_tma_kernel(int cost) {
+  switch (cost) {
+    case MB2_COST_ROSEN: return de_step_best1bin_tma_kernel<COST_ROSEN>;
+    case MB2_COST_CORANA: return de_step_best1bin_tma_kernel<COST_CORANA>;
+    case MB2_COST_GRIEWANGK: return de_step_best1bin_tma_kernel<COST_GRIEWANGK>;
+    case MB2_COST_ZIMMERMANN: return de_step_best1bin_tma_kernel<COST_ZIMMERMANN>;
+    case MB2_COST_CHEBYSHEV: return de_step_best1bin_tma_kernel<COST_CHEBYSHEV>;
+  }
+  return nullptr;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return (v && *v) ? atoi(v) : dflt;
+}
+
+// Ring geometry of the TMA kernel: warps per CTA, stages per warp, dynamic smem.  Returns false
+// when a row does not fit (the LDG kernel is used instead).
+bool tma_geometry(int dim, int* warps, int* stages, int* smem) {
+  const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
+  const size_t budget = 220 * 1024;
+  if (row * 4 > budget) return false;
+  const size_t slots = (budget - row) / (3 * row);  // (warp, stage) buffers that fit
+  int w, st;
+  if (slots >= 32) { w = 8; st = 4; }
+  else if (slots >= 16) { w = 8; st = 2; }
+  else if (slots >= 8) { w = 8; st = 1; }
+  else if (slots >= 4) { w = 4; st = 1; }
+  else if (slots >= 2) { w = 2; st = 1; }
+  else { w = 1; st = 1; }
+  const int ew = env_int("MB2_TMA_WARPS", 0), es = env_int("MB2_TMA_STAGES", 0);
+  if (ew >= 1 && ew <= kTmaMaxWarps && es >= 1 && es <= kTmaMaxStages && (size_t)ew * es <= slots) {
+    w = ew;
+    st = es;
+  }
+  *warps = w;
+  *stages = st;
+  *smem = (int)(row + (size_t)w * st * 3 * row);
+  return true;
+}
+
 // configure + launch the fused kernel in `mode` over `np` rows
 int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out,
                 int64_t np, cudaStream_t stream) {
@@ -171,12 +216,26 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   StepKernel k = pick_kernel(s, c->cost, vec);
   if (k == nullptr) return fail(MB2_EINVAL, "no kernel for strategy %d cost %d", c->strategy, c->cost);
 
+  // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
+  TmaKernel kt = nullptr;
+  int tw = 0, ts = 0, tsmem = 0;
+  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 &&
+      tma_geometry(c->dim, &tw, &ts, &tsmem))
+    kt = pick_tma_kernel(c->cost);
+
   int wpc, smem;
-  geometry(c->dim_pad, &wpc, &smem);
-  if (smem > 227 * 1024) return fail(MB2_EINVAL, "dim %d too large for one warp-resident row", c->dim);
-  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int occ = 0;
-  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));
+  if (kt != nullptr) {
+    wpc = tw;
+    smem = tsmem;
+    CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt, wpc * 32, smem));
+  } else {
+    geometry(c->dim_pad, &wpc, &smem);
+    if (smem > 227 * 1024) return fail(MB2_EINVAL, "dim %d too large for one warp-resident row", c->dim);
+    CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));
+  }
   if (occ < 1) return fail(MB2_EINVAL, "kernel does not fit on an SM (smem %d)", smem);
   int64_t need = (np + wpc - 1) / wpc;
   int64_t grid = (int64_t)c->sm_count * occ;
@@ -221,7 +280,10 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->wpc = wpc;
   c->grid = (int)grid;
   c->smem = smem;
-  k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
+  if (kt != nullptr)
+    kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
+  else
+    k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
   return MB2_OK;

@@ -1,0 +1,267 @@
+// Full-row (binomial crossover) generation kernel with TMA bulk staging.
+//
+// Best1Bin reads whole rows: the parent and two donors, 8*D bytes each, contiguous in HBM.  Each
+// warp owns a private ring of `stages` buffers in shared memory; one elected lane issues three
+// `cp.async.bulk` global->shared copies per candidate (SASS: UBLKCP) that complete on the warp's
+// mbarrier, so (stages x warps x 3 rows) are in flight per SM without holding registers.  The
+// trial vector is built in place over the first donor's buffer, the cost is evaluated from shared
+// memory, and the selected row (trial or parent) leaves with one bulk shared->global copy.
+// No CTA-wide barrier is used after start-up: warps are independent pipelines.
+//
+// Semantics are those of de_step_kernel<BASE_BEST1, XOVER_BIN, COST> (de_kernels.cuh); the same
+// device functions produce the numbers, so both kernels agree bit for bit.
+#pragma once
+#include "de_kernels.cuh"
+
+namespace mb2 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on `bar` (size multiple of 16, 16-B aligned)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global bulk copy (bulk async-group)
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int kTmaMaxWarps = 8;
+constexpr int kTmaMaxStages = 4;
+
+// donors + start index of candidate c (replayed or Philox), uniform across the warp
+__device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int64_t (&r)[2], int* nstart) {
+  if (P.replay) {
+    r[0] = __ldg(P.r_donors + c * 5 + 0);
+    r[1] = __ldg(P.r_donors + c * 5 + 1);
+    *nstart = __ldg(P.r_nstart + c);
+  } else {
+    draw_donors<2>(P.key0, P.key1, P.generation, (uint32_t)(P.global_offset + c), c, P.np, P.dim, r, nstart);
+  }
+}
+
+// requires: dim even (rows are 16-byte multiples), MODE_STEP.
+template <int COST>
+__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
+    de_step_best1bin_tma_kernel(const __grid_constant__ StepParams P, int stages) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[kTmaMaxWarps * kTmaMaxStages];
+  __shared__ double sh_e[kTmaMaxWarps];
+  __shared__ int64_t sh_i[kTmaMaxWarps];
+  __shared__ unsigned long long sh_ninf[kTmaMaxWarps], sh_nacc[kTmaMaxWarps];
+
+  const int D = P.dim;
+  const unsigned row_bytes = (unsigned)D * 8u;
+  const size_t row_stride = ((size_t)row_bytes + 127) & ~(size_t)127;  // keep every buffer 128-B aligned
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+
+  double* s_best = reinterpret_cast<double*>(smem_raw);
+  unsigned char* s_ring = smem_raw + row_stride + (size_t)warp * stages * 3 * row_stride;
+  uint64_t* bars = s_bar + warp * kTmaMaxStages;
+
+  for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
+  if (lane == 0) {
+    for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
+  const int64_t nw = (int64_t)gridDim.x * wpc;
+
+  // issue the three row loads of candidate c into stage s (lane 0 only)
+  auto issue = [&](int64_t c, int s) {
+    int64_t r[2];
+    int nstart;
+    best1_draws(P, c, r, &nstart);
+    unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
+    mbar_expect_tx(bars + s, 3u * row_bytes);
+    bulk_g2s(buf, P.pop_cur + c * D, row_bytes, bars + s);
+    bulk_g2s(buf + row_stride, P.pop_cur + r[0] * D, row_bytes, bars + s);
+    bulk_g2s(buf + 2 * row_stride, P.pop_cur + r[1] * D, row_bytes, bars + s);
+  };
+
+  if (lane == 0) {
+    for (int s = 0; s < stages; ++s) {
+      const int64_t c = gw + (int64_t)s * nw;
+      if (c < P.np) issue(c, s);
+    }
+  }
+  __syncwarp();
+
+  double w_best_e = CUDART_INF;
+  int64_t w_best_idx = INT64_MAX;
+  unsigned long long w_ninf = 0, w_nacc = 0;
+  const int npairs = D >> 1;  // double2 chunks per row
+
+  int s = 0;
+  unsigned parity = 0;
+  for (int64_t c = gw; c < P.np; c += nw) {
+    unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
+    const double2* s_par = reinterpret_cast<const double2*>(buf);
+    double2* s_d0 = reinterpret_cast<double2*>(buf + row_stride);  // becomes the trial vector
+    const double2* s_d1 = reinterpret_cast<const double2*>(buf + 2 * row_stride);
+    const double2* s_b2 = reinterpret_cast<const double2*>(s_best);
+
+    int64_t r[2];
+    int nstart;
+    best1_draws(P, c, r, &nstart);
+    const uint32_t cand_g = (uint32_t)(P.global_offset + c);
+
+    mbar_wait(bars + s, parity);
+
+    // ---- trial vector (strategy.py:77-85), two conflict-free double2 chunks per lane per trip:
+    //      chunk pA = trip*64 + lane and pB = pA + 32.  Crossover words: block q covers dims 4q..4q+3,
+    //      i.e. chunks 2q and 2q+1, so the lane pair (2m, 2m+1) shares blocks qA and qB; the even
+    //      lane computes qA, the odd lane qB, and they swap halves with one shuffle each.
+    bool oob = false;
+    for (int base = 0; base < npairs; base += 64) {
+      const int pA = base + lane, pB = base + 32 + lane;
+      bool cx[4];  // crossover decisions for dims 2pA, 2pA+1, 2pB, 2pB+1
+      if (P.replay) {
+        const double* u = P.r_uni + c * (int64_t)(D + 1);
+        cx[0] = (pA < npairs) && ((2 * pA == nstart) || (__ldg(u + 2 * pA) < P.CR));
+        cx[1] = (pA < npairs) && ((2 * pA + 1 == nstart) || (__ldg(u + 2 * pA + 1) < P.CR));
+        cx[2] = (pB < npairs) && ((2 * pB == nstart) || (__ldg(u + 2 * pB) < P.CR));
+        cx[3] = (pB < npairs) && ((2 * pB + 1 == nstart) || (__ldg(u + 2 * pB + 1) < P.CR));
+      } else {
+        const int q = (base >> 1) + (lane >> 1) + ((lane & 1) ? 16 : 0);  // even lane: qA, odd lane: qB
+        const u32x4 w = philox4x32_10((uint32_t)q, cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+        // even lane keeps (x,y) of qA for pA and needs (x,y) of qB from its odd neighbour;
+        // odd lane keeps (z,w) of qB for pB and needs (z,w) of qA from its even neighbour.
+        const uint32_t send0 = (lane & 1) ? w.x : w.z;
+        const uint32_t send1 = (lane & 1) ? w.y : w.w;
+        const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1);
+        const uint32_t got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
+        const uint32_t a0 = (lane & 1) ? got0 : w.x, a1 = (lane & 1) ? got1 : w.y;  // words for chunk pA
+        const uint32_t b0 = (lane & 1) ? w.z : got0, b1 = (lane & 1) ? w.w : got1;  // words for chunk pB
+        cx[0] = (pA < npairs) && ((2 * pA == nstart) || ((uint64_t)a0 < P.thr));
+        cx[1] = (pA < npairs) && ((2 * pA + 1 == nstart) || ((uint64_t)a1 < P.thr));
+        cx[2] = (pB < npairs) && ((2 * pB == nstart) || ((uint64_t)b0 < P.thr));
+        cx[3] = (pB < npairs) && ((2 * pB + 1 == nstart) || ((uint64_t)b1 < P.thr));
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int p = h ? pB : pA;
+        if (p < npairs) {
+          double2 x = s_par[p];
+          const double2 a = s_d0[p], b = s_d1[p], bs = s_b2[p];
+          if (cx[2 * h]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
+          if (cx[2 * h + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
+          if (P.bounds_mode != BOUNDS_NONE) {
+            const double l0 = __ldg(P.lo + 2 * p), l1 = __ldg(P.lo + 2 * p + 1);
+            const double h0 = __ldg(P.hi + 2 * p), h1 = __ldg(P.hi + 2 * p + 1);
+            if (P.bounds_mode == BOUNDS_CLAMP) {
+              x.x = (x.x > l0) ? x.x : l0;
+              x.x = (x.x < h0) ? x.x : h0;
+              x.y = (x.y > l1) ? x.y : l1;
+              x.y = (x.y < h1) ? x.y : h1;
+            }
+            oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);
+          }
+          s_d0[p] = x;
+        }
+      }
+    }
+    oob = __any_sync(0xffffffffu, oob);
+    __syncwarp();
+
+    const double* s_trial = reinterpret_cast<const double*>(s_d0);
+    double E = CUDART_INF;
+    if (!oob) E = warp_cost<COST>(s_trial, D, lane, P.cost);
+    E = dadd(E, warp_penalty(s_trial, D, lane, P.pen));
+
+    if (P.cap_trial != nullptr) {
+      for (int i = lane; i < D; i += 32) P.cap_trial[c * D + i] = s_trial[i];
+      if (lane == 0) P.cap_energy[c] = E;
+    }
+
+    const double e_old = __ldg(P.e_cur + c);
+    const bool acc = E < e_old;
+    // make the generic-proxy writes of the trial visible to the async proxy, then one lane stores
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      bulk_s2g(P.pop_next + c * D, acc ? (const void*)s_d0 : (const void*)s_par, row_bytes);
+      bulk_commit();
+      P.e_next[c] = acc ? E : e_old;
+    }
+    if (acc) {
+      ++w_nacc;
+      if (E < w_best_e) {
+        w_best_e = E;
+        w_best_idx = c;
+      }
+    }
+    if (isinf(E)) ++w_ninf;
+
+    // refill this stage with the row it serves next, once the store has finished reading it
+    const int64_t cn = c + (int64_t)stages * nw;
+    if (lane == 0) {
+      bulk_wait_read0();
+      if (cn < P.np) issue(cn, s);
+    }
+    __syncwarp();
+    if (++s == stages) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane == 0) bulk_wait_all0();
+
+  if (lane == 0) {
+    sh_e[warp] = w_best_e;
+    sh_i[warp] = w_best_idx;
+    sh_ninf[warp] = w_ninf;
+    sh_nacc[warp] = w_nacc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double be = sh_e[0];
+    int64_t bi = sh_i[0];
+    unsigned long long ni = sh_ninf[0], na = sh_nacc[0];
+    for (int w = 1; w < wpc; ++w) {
+      if (sh_e[w] < be || (sh_e[w] == be && sh_i[w] < bi)) {
+        be = sh_e[w];
+        bi = sh_i[w];
+      }
+      ni += sh_ninf[w];
+      na += sh_nacc[w];
+    }
+    P.part_e[blockIdx.x] = be;
+    P.part_idx[blockIdx.x] = bi;
+    P.part_ninf[blockIdx.x] = ni;
+    P.part_nacc[blockIdx.x] = na;
+  }
+}
+
+}  // namespace mb2
