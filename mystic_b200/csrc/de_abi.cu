@@ -69,6 +69,8 @@ struct mb2_ctx {
   StrategyInfo sinfo = {BASE_BEST1, XOVER_BIN, 2};
   double F = 0.8, CR = 0.9;
   int bounds_mode = BOUNDS_NONE;
+  int bounds_uniform = 0;
+  double lo_s = 0.0, hi_s = 0.0;
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
@@ -163,7 +165,7 @@ int ensure_parts(mb2_ctx* c, int n) {
   return MB2_OK;
 }
 
-typedef void (*TmaKernel)(const StepParams, int);
+typedef void (*TmaKernel)(const StepParams, int, int);
 
 TmaKernel pick_tma_kernel(int cost) {
   switch (cost) {
@@ -181,28 +183,32 @@ int env_int(const char* name, int dflt) {
   return (v && *v) ? atoi(v) : dflt;
 }
 
-// Ring geometry of the TMA kernel: warps per CTA, stages per warp, dynamic smem.  Returns false
-// when a row does not fit (the LDG kernel is used instead).
-bool tma_geometry(int dim, int* warps, int* stages, int* smem) {
+// Ring geometry of the TMA kernel: groups per CTA, warps per group, stages per group, dynamic
+// smem.  Returns false when a row does not fit (the LDG kernel is used instead).
+bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
   const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
   const size_t budget = 220 * 1024;
   if (row * 4 > budget) return false;
-  const size_t slots = (budget - row) / (3 * row);  // (warp, stage) buffers that fit
-  int w, st;
-  if (slots >= 32) { w = 8; st = 4; }
-  else if (slots >= 16) { w = 8; st = 2; }
-  else if (slots >= 8) { w = 8; st = 1; }
-  else if (slots >= 4) { w = 4; st = 1; }
-  else if (slots >= 2) { w = 2; st = 1; }
-  else { w = 1; st = 1; }
-  const int ew = env_int("MB2_TMA_WARPS", 0), es = env_int("MB2_TMA_STAGES", 0);
-  if (ew >= 1 && ew <= kTmaMaxWarps && es >= 1 && es <= kTmaMaxStages && (size_t)ew * es <= slots) {
-    w = ew;
+  const size_t slots = (budget - row) / (3 * row);  // (group, stage) buffers that fit on one SM
+  // warps per row: enough threads that a row is at most two trips of the mutation loop
+  int gw = 1;
+  while (gw < 8 && (size_t)dim > (size_t)gw * 32 * 8) gw <<= 1;
+  int maxg = kTmaMaxThreads / (gw * 32);
+  if (maxg > kTmaMaxGroups) maxg = kTmaMaxGroups;
+  int g = maxg, st = 1;
+  while (g > 1 && (size_t)g > slots) g >>= 1;
+  while (st < kTmaMaxStages && (size_t)g * (st * 2) <= slots) st *= 2;
+  const int eg = env_int("MB2_TMA_GROUPS", 0), ew = env_int("MB2_TMA_GWARPS", 0), es = env_int("MB2_TMA_STAGES", 0);
+  if (eg >= 1 && eg <= kTmaMaxGroups && (ew == 1 || ew == 2 || ew == 4 || ew == 8) && es >= 1 &&
+      es <= kTmaMaxStages && (size_t)eg * es <= slots && eg * ew * 32 <= kTmaMaxThreads) {
+    g = eg;
+    gw = ew;
     st = es;
   }
-  *warps = w;
+  *groups = g;
+  *gwarps = gw;
   *stages = st;
-  *smem = (int)(row + (size_t)w * st * 3 * row);
+  *smem = (int)(row + (size_t)g * st * 3 * row);
   return true;
 }
 
@@ -218,26 +224,29 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
-  int tw = 0, ts = 0, tsmem = 0;
+  int tg = 0, tw = 0, ts = 0, tsmem = 0;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 &&
-      tma_geometry(c->dim, &tw, &ts, &tsmem))
+      tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost);
 
   int wpc, smem;
   int occ = 0;
+  int rows_per_cta;
   if (kt != nullptr) {
-    wpc = tw;
+    wpc = tg * tw;
+    rows_per_cta = tg;
     smem = tsmem;
     CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt, wpc * 32, smem));
   } else {
     geometry(c->dim_pad, &wpc, &smem);
+    rows_per_cta = wpc;
     if (smem > 227 * 1024) return fail(MB2_EINVAL, "dim %d too large for one warp-resident row", c->dim);
     CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, wpc * 32, smem));
   }
   if (occ < 1) return fail(MB2_EINVAL, "kernel does not fit on an SM (smem %d)", smem);
-  int64_t need = (np + wpc - 1) / wpc;
+  int64_t need = (np + rows_per_cta - 1) / rows_per_cta;
   int64_t grid = (int64_t)c->sm_count * occ;
   if (grid > need) grid = need;
   if (grid < 1) grid = 1;
@@ -258,6 +267,9 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   P.dim_pad = c->dim_pad;
   P.mode = mode;
   P.bounds_mode = c->bounds_mode;
+  P.bounds_uniform = c->bounds_uniform;
+  P.lo_s = c->lo_s;
+  P.hi_s = c->hi_s;
   P.F = c->F;
   P.CR = c->CR;
   P.replay = (mode == MODE_STEP) ? c->replay : 0;
@@ -281,7 +293,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->grid = (int)grid;
   c->smem = smem;
   if (kt != nullptr)
-    kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
+    kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts, tw);
   else
     k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
@@ -415,6 +427,11 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
     CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpy(c->lo, lo, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->hi, hi, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
+    bool uni = true;
+    for (int i = 1; i < c->dim; ++i) uni = uni && lo[i] == lo[0] && hi[i] == hi[0];
+    c->bounds_uniform = uni ? 1 : 0;
+    c->lo_s = lo[0];
+    c->hi_s = hi[0];
   }
   c->bounds_mode = mode;
   return MB2_OK;

@@ -65,16 +65,69 @@ __device__ __forceinline__ void store4(double* __restrict__ row, int i0, int D, 
   }
 }
 
-// ---- warp reductions (fixed xor tree: deterministic)
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = dadd(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+// ---- cooperative groups of G warps (G in {1,2,4,8}) that own one candidate row ------------
+// Reductions are CANONICAL: element i belongs to virtual thread j = i mod 256; virtual thread
+// sums are combined by a fixed xor tree over the 32 lanes and then over the 8 virtual warps as
+// ((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7)).  A group of G warps emulates the 256 virtual threads with
+// M = 8/G accumulators per thread, so every kernel (any G) produces bit-identical energies.
+struct Group {
+  int tig;        // thread index in the group
+  int nthreads;   // 32 * G
+  int wig;        // warp index in the group
+  int lane;
+  int M;          // 256 / nthreads: accumulators per thread
+  int bar_id;     // named barrier of the group (unused when G == 1)
+  double* scratch;  // 16 doubles of shared memory per group
+};
+
+__device__ __forceinline__ void group_sync(const Group& g) {
+  if (g.nthreads == 32)
+    __syncwarp();
+  else
+    asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "r"(g.nthreads) : "memory");
 }
-__device__ __forceinline__ double warp_prod(double v) {
+
+// barrier + OR reduction of a predicate over the group
+__device__ __forceinline__ bool group_any(const Group& g, bool v) {
+  if (g.nthreads == 32) return __any_sync(0xffffffffu, v);
+  unsigned r;
+  asm volatile(
+      "{\n"
+      ".reg .pred p, q;\n"
+      "setp.ne.u32 q, %1, 0;\n"
+      "bar.red.or.pred p, %2, %3, q;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"((unsigned)v), "r"(g.bar_id), "r"(g.nthreads)
+      : "memory");
+  return r != 0;
+}
+
+template <bool PROD>
+__device__ __forceinline__ double group_reduce(const Group& g, const double (&acc)[8], int slot) {
+  const int G = g.nthreads >> 5;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = dmul(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
+  for (int m = 0; m < 8; ++m) {
+    if (m < g.M) {
+      double v = acc[m];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = PROD ? dmul(v, w) : dadd(v, w);
+      }
+      if (g.lane == 0) g.scratch[slot * 8 + g.wig + G * m] = v;
+    }
+  }
+  group_sync(g);
+  const double* s = g.scratch + slot * 8;
+  double r;
+  if (PROD)
+    r = dmul(dmul(dmul(s[0], s[1]), dmul(s[2], s[3])), dmul(dmul(s[4], s[5]), dmul(s[6], s[7])));
+  else
+    r = dadd(dadd(dadd(s[0], s[1]), dadd(s[2], s[3])), dadd(dadd(s[4], s[5]), dadd(s[6], s[7])));
+  group_sync(g);  // scratch may be reused by the next reduction
+  return r;
 }
 
 // ---- cost parameters
@@ -94,23 +147,31 @@ __device__ __forceinline__ double horner(const double* __restrict__ c, int n, do
   return val;
 }
 
-// Warp-cooperative cost of one row `xs` (shared memory, D entries).  Every lane returns the
-// same value.  Per-element terms follow the reference's operation order without FMA, so each
-// term is bit-identical to the reference; only the summation tree differs (<= 1e-12 relative).
+// Group-cooperative cost of one row `xs` (shared memory, D entries).  Every thread of the group
+// returns the same value.  Per-element terms follow the reference's operation order without
+// FMA, so each term is bit-identical to the reference; only the summation tree differs
+// (<= 1e-12 relative).
 template <int COST>
-__device__ __forceinline__ double warp_cost(const double* xs, int D, int lane, const CostParams& cp) {
+__device__ __forceinline__ double group_cost(const Group& g, const double* xs, int D, const CostParams& cp) {
   if (COST == COST_ROSEN) {
     // dejong.py:98-101: sum(100*(x[1:]-x[:-1]**2)**2 + (1-x[:-1])**2)
-    double acc = 0.0;
-    for (int i = lane; i < D - 1; i += 32) {
-      const double a = xs[i], b = xs[i + 1];
-      const double t = dsub(b, dmul(a, a));
-      const double u = dsub(1.0, a);
-      acc = dadd(acc, dadd(dmul(100.0, dmul(t, t)), dmul(u, u)));
+    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    const int n = D - 1;
+    for (int i0 = g.tig; i0 < n; i0 += 256) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int i = i0 + m * g.nthreads;
+        if (m < g.M && i < n) {
+          const double a = xs[i], b = xs[i + 1];
+          const double t = dsub(b, dmul(a, a));
+          const double u = dsub(1.0, a);
+          acc[m] = dadd(acc[m], dadd(dmul(100.0, dmul(t, t)), dmul(u, u)));
+        }
+      }
     }
-    return warp_sum(acc);
+    return group_reduce<false>(g, acc, 0);
   } else if (COST == COST_CORANA) {
-    // storn.py:77-96, strictly sequential over 4 terms; lanes compute redundantly
+    // storn.py:77-96, strictly sequential over 4 terms; threads compute redundantly
     const double d[4] = {1., 1000., 10., 100.};
     double x[4] = {0., 0., 0., 0.};
     if (D >= 4) {
@@ -141,14 +202,21 @@ __device__ __forceinline__ double warp_cost(const double* xs, int D, int lane, c
     return r;
   } else if (COST == COST_GRIEWANGK) {
     // storn.py:135-139: sum(c*c)/4000 - prod(cos(c_i/sqrt(i+1))) + 1
-    double s = 0.0, p = 1.0;
-    for (int i = lane; i < D; i += 32) {
-      const double c = xs[i];
-      s = dadd(s, dmul(c, c));
-      p = dmul(p, cos(c / sqrt((double)i + 1.0)));
+    double sa[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    double pa[8] = {1., 1., 1., 1., 1., 1., 1., 1.};
+    for (int i0 = g.tig; i0 < D; i0 += 256) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int i = i0 + m * g.nthreads;
+        if (m < g.M && i < D) {
+          const double c = xs[i];
+          sa[m] = dadd(sa[m], dmul(c, c));
+          pa[m] = dmul(pa[m], cos(c / sqrt((double)i + 1.0)));
+        }
+      }
     }
-    s = warp_sum(s);
-    p = warp_prod(p);
+    const double s = group_reduce<false>(g, sa, 0);
+    const double p = group_reduce<true>(g, pa, 1);
     return dadd(dsub(s / 4000.0, p), 1.0);
   } else if (COST == COST_ZIMMERMANN) {
     // storn.py:182-191 (D == 2)
@@ -170,21 +238,27 @@ __device__ __forceinline__ double warp_cost(const double* xs, int D, int lane, c
     return m;
   } else {  // COST_CHEBYSHEV
     // _model_helper.py:16-33
-    double acc = 0.0;
+    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
     const int M = cp.cheb_M;
-    for (int i = lane; i < M; i += 32) {
-      const double px = horner(xs, D, __ldg(cp.cheb_x + i));
-      if (px < -1.0 || px > 1.0) {
-        const double u = dsub(1.0, px);
-        acc = dadd(acc, dmul(u, u));
+    for (int i0 = g.tig; i0 < M; i0 += 256) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int i = i0 + m * g.nthreads;
+        if (m < g.M && i < M) {
+          const double px = horner(xs, D, __ldg(cp.cheb_x + i));
+          if (px < -1.0 || px > 1.0) {
+            const double u = dsub(1.0, px);
+            acc[m] = dadd(acc[m], dmul(u, u));
+          }
+        }
       }
     }
-    acc = warp_sum(acc);
+    double r = group_reduce<false>(g, acc, 0);
     double px = dsub(horner(xs, D, 1.2), cp.cheb_tp);
-    if (px < 0.0) acc = dadd(acc, dmul(px, px));
+    if (px < 0.0) r = dadd(r, dmul(px, px));
     px = dsub(horner(xs, D, -1.2), cp.cheb_tm);
-    if (px < 0.0) acc = dadd(acc, dmul(px, px));
-    return acc;
+    if (px < 0.0) r = dadd(r, dmul(px, px));
+    return r;
   }
 }
 
@@ -198,13 +272,19 @@ struct PenaltyParams {
 };
 
 // term 0 innermost; value = t_{n-1} + (... + (t_0 + 0.0))  (penalty.py:88,147,388,447)
-__device__ __forceinline__ double warp_penalty(const double* xs, int D, int lane, const PenaltyParams& pp) {
+__device__ __forceinline__ double group_penalty(const Group& g, const double* xs, int D, const PenaltyParams& pp) {
   double total = 0.0;
   for (int t = 0; t < pp.n; ++t) {
-    const double* g = pp.G + (int64_t)t * D;
-    double acc = 0.0;
-    for (int i = lane; i < D; i += 32) acc = dadd(acc, dmul(__ldg(g + i), xs[i]));
-    const double pf = dsub(warp_sum(acc), __ldg(pp.h + t));
+    const double* gr = pp.G + (int64_t)t * D;
+    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    for (int i0 = g.tig; i0 < D; i0 += 256) {
+#pragma unroll
+      for (int m = 0; m < 8; ++m) {
+        const int i = i0 + m * g.nthreads;
+        if (m < g.M && i < D) acc[m] = dadd(acc[m], dmul(__ldg(gr + i), xs[i]));
+      }
+    }
+    const double pf = dsub(group_reduce<false>(g, acc, 0), __ldg(pp.h + t));
     const double k = __ldg(pp.kscale + t);
     const int ty = __ldg(pp.ptype + t);
     double v;

@@ -34,6 +34,8 @@ struct StepParams {
   int dim_pad;  // dim rounded up to a multiple of 4
   int mode;     // MODE_*
   int bounds_mode;
+  int bounds_uniform;  // 1: every dimension has the same [lo_s, hi_s] (no per-dimension loads)
+  double lo_s, hi_s;
   double F, CR;
   // RNG
   int replay;  // 1: consume recorded draws
@@ -119,8 +121,10 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
+  __shared__ double s_scratch[kWarpsPerCtaMax * 16];
   double* s_best = smem;                              // [Dp]
   double* s_trial = smem + Dp + (size_t)warp * Dp;   // [Dp] per warp
+  const Group grp = {lane, 32, 0, lane, 8, 0, s_scratch + warp * 16};  // one warp per row
 
   if (P.mode == MODE_STEP && kNeedsBest) {
     for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
@@ -209,7 +213,8 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (i0 + e < D) {
-              const double l = __ldg(P.lo + i0 + e), h = __ldg(P.hi + i0 + e);
+              const double l = P.bounds_uniform ? P.lo_s : __ldg(P.lo + i0 + e);
+              const double h = P.bounds_uniform ? P.hi_s : __ldg(P.hi + i0 + e);
               if (P.bounds_mode == BOUNDS_CLAMP) {
                 x[e] = (x[e] > l) ? x[e] : l;  // python max(lo, x)
                 x[e] = (x[e] < h) ? x[e] : h;  // python min(hi, x)
@@ -232,7 +237,8 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             if (i0 + e < D) {
-              const double l = __ldg(P.lo + i0 + e), h = __ldg(P.hi + i0 + e);
+              const double l = P.bounds_uniform ? P.lo_s : __ldg(P.lo + i0 + e);
+              const double h = P.bounds_uniform ? P.hi_s : __ldg(P.hi + i0 + e);
               if (P.mode == MODE_GEN0) x[e] = fmin(fmax(x[e], l), h);
               oob |= (x[e] < l) || (x[e] > h);
             }
@@ -247,8 +253,8 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
 
     // ---- energy = (inf if out of range else cost(x)) + penalty(x)
     double E = CUDART_INF;
-    if (!oob) E = warp_cost<COST>(s_trial, D, lane, P.cost);
-    E = dadd(E, warp_penalty(s_trial, D, lane, P.pen));
+    if (!oob) E = group_cost<COST>(grp, s_trial, D, P.cost);
+    E = dadd(E, group_penalty(grp, s_trial, D, P.pen));
 
     if (P.cap_trial != nullptr && P.mode != MODE_EVAL) {
       for (int i = lane; i < D; i += 32) P.cap_trial[c * D + i] = s_trial[i];

@@ -1,12 +1,14 @@
 // Full-row (binomial crossover) generation kernel with TMA bulk staging.
 //
-// Best1Bin reads whole rows: the parent and two donors, 8*D bytes each, contiguous in HBM.  Each
-// warp owns a private ring of `stages` buffers in shared memory; one elected lane issues three
-// `cp.async.bulk` global->shared copies per candidate (SASS: UBLKCP) that complete on the warp's
-// mbarrier, so (stages x warps x 3 rows) are in flight per SM without holding registers.  The
-// trial vector is built in place over the first donor's buffer, the cost is evaluated from shared
-// memory, and the selected row (trial or parent) leaves with one bulk shared->global copy.
-// No CTA-wide barrier is used after start-up: warps are independent pipelines.
+// Best1Bin reads whole rows: the parent and two donors, 8*D bytes each, contiguous in HBM.  A
+// GROUP of G warps (G in {1,2,4,8}) owns one candidate row at a time and a private ring of
+// `stages` buffers in shared memory; the group's leader thread issues three `cp.async.bulk`
+// global->shared copies per candidate (SASS: UBLKCP) that complete on the group's mbarrier, so
+// (groups x stages x 3 rows) are in flight per SM without holding registers.  The trial vector
+// is built in place over the first donor's buffer, the cost is evaluated from shared memory with
+// the canonical reduction of de_device.cuh, and the selected row (trial or parent) leaves with
+// one bulk shared->global copy.  Groups synchronise on their own named barrier; there is no
+// CTA-wide barrier after start-up.
 //
 // Semantics are those of de_step_kernel<BASE_BEST1, XOVER_BIN, COST> (de_kernels.cuh); the same
 // device functions produce the numbers, so both kernels agree bit for bit.
@@ -53,10 +55,11 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kTmaMaxWarps = 8;
+constexpr int kTmaMaxGroups = 16;  // groups per CTA (named barriers 1..15 serve groups of more than one warp)
 constexpr int kTmaMaxStages = 4;
+constexpr int kTmaMaxThreads = 512;
 
-// donors + start index of candidate c (replayed or Philox), uniform across the warp
+// donors + start index of candidate c (replayed or Philox), uniform across the group
 __device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int64_t (&r)[2], int* nstart) {
   if (P.replay) {
     r[0] = __ldg(P.r_donors + c * 5 + 0);
@@ -67,38 +70,43 @@ __device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int6
   }
 }
 
-// requires: dim even (rows are 16-byte multiples), MODE_STEP.
+// requires: dim even (rows are 16-byte multiples), MODE_STEP.  blockDim = groups * gwarps * 32.
 template <int COST>
-__global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
-    de_step_best1bin_tma_kernel(const __grid_constant__ StepParams P, int stages) {
+__global__ void __launch_bounds__(kTmaMaxThreads, 1)
+    de_step_best1bin_tma_kernel(const __grid_constant__ StepParams P, int stages, int gwarps) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar[kTmaMaxWarps * kTmaMaxStages];
-  __shared__ double sh_e[kTmaMaxWarps];
-  __shared__ int64_t sh_i[kTmaMaxWarps];
-  __shared__ unsigned long long sh_ninf[kTmaMaxWarps], sh_nacc[kTmaMaxWarps];
+  __shared__ __align__(8) uint64_t s_bar[kTmaMaxGroups * kTmaMaxStages];
+  __shared__ double s_scratch[kTmaMaxGroups * 16];
+  __shared__ double sh_e[kTmaMaxGroups];
+  __shared__ int64_t sh_i[kTmaMaxGroups];
+  __shared__ unsigned long long sh_ninf[kTmaMaxGroups], sh_nacc[kTmaMaxGroups];
 
   const int D = P.dim;
   const unsigned row_bytes = (unsigned)D * 8u;
   const size_t row_stride = ((size_t)row_bytes + 127) & ~(size_t)127;  // keep every buffer 128-B aligned
+  const int gthreads = gwarps * 32;
+  const int group = threadIdx.x / gthreads;
+  const int ngroups = blockDim.x / gthreads;
+  const int tig = threadIdx.x - group * gthreads;
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
-  const int wpc = blockDim.x >> 5;
+  const bool leader = (tig == 0);
+  const Group grp = {tig, gthreads, tig >> 5, lane, 256 / gthreads, 1 + group, s_scratch + group * 16};
 
   double* s_best = reinterpret_cast<double*>(smem_raw);
-  unsigned char* s_ring = smem_raw + row_stride + (size_t)warp * stages * 3 * row_stride;
-  uint64_t* bars = s_bar + warp * kTmaMaxStages;
+  unsigned char* s_ring = smem_raw + row_stride + (size_t)group * stages * 3 * row_stride;
+  uint64_t* bars = s_bar + group * kTmaMaxStages;
 
   for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
-  if (lane == 0) {
+  if (leader) {
     for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
-  const int64_t nw = (int64_t)gridDim.x * wpc;
+  const int64_t g0 = (int64_t)blockIdx.x * ngroups + group;
+  const int64_t ng = (int64_t)gridDim.x * ngroups;
 
-  // issue the three row loads of candidate c into stage s (lane 0 only)
+  // issue the three row loads of candidate c into stage s (group leader only)
   auto issue = [&](int64_t c, int s) {
     int64_t r[2];
     int nstart;
@@ -110,42 +118,47 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
     bulk_g2s(buf + 2 * row_stride, P.pop_cur + r[1] * D, row_bytes, bars + s);
   };
 
-  if (lane == 0) {
+  if (leader) {
     for (int s = 0; s < stages; ++s) {
-      const int64_t c = gw + (int64_t)s * nw;
+      const int64_t c = g0 + (int64_t)s * ng;
       if (c < P.np) issue(c, s);
     }
   }
-  __syncwarp();
 
-  double w_best_e = CUDART_INF;
-  int64_t w_best_idx = INT64_MAX;
-  unsigned long long w_ninf = 0, w_nacc = 0;
+  double g_best_e = CUDART_INF;
+  int64_t g_best_idx = INT64_MAX;
+  unsigned long long g_ninf = 0, g_nacc = 0;
   const int npairs = D >> 1;  // double2 chunks per row
+  const bool uni_b = P.bounds_uniform != 0;
 
   int s = 0;
   unsigned parity = 0;
-  for (int64_t c = gw; c < P.np; c += nw) {
+  for (int64_t c = g0; c < P.np; c += ng) {
     unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
     const double2* s_par = reinterpret_cast<const double2*>(buf);
     double2* s_d0 = reinterpret_cast<double2*>(buf + row_stride);  // becomes the trial vector
     const double2* s_d1 = reinterpret_cast<const double2*>(buf + 2 * row_stride);
     const double2* s_b2 = reinterpret_cast<const double2*>(s_best);
 
-    int64_t r[2];
     int nstart;
-    best1_draws(P, c, r, &nstart);
+    if (P.replay) {
+      nstart = __ldg(P.r_nstart + c);
+    } else {
+      int64_t r[2];
+      best1_draws(P, c, r, &nstart);
+    }
     const uint32_t cand_g = (uint32_t)(P.global_offset + c);
 
     mbar_wait(bars + s, parity);
 
-    // ---- trial vector (strategy.py:77-85), two conflict-free double2 chunks per lane per trip:
-    //      chunk pA = trip*64 + lane and pB = pA + 32.  Crossover words: block q covers dims 4q..4q+3,
-    //      i.e. chunks 2q and 2q+1, so the lane pair (2m, 2m+1) shares blocks qA and qB; the even
-    //      lane computes qA, the odd lane qB, and they swap halves with one shuffle each.
+    // ---- trial vector (strategy.py:77-85), two conflict-free double2 chunks per thread per trip:
+    //      chunk pA = base + tig and pB = pA + gthreads.  Crossover words: Philox block q covers
+    //      dims 4q..4q+3, i.e. chunks 2q and 2q+1, so the thread pair (2m, 2m+1) shares blocks qA and
+    //      qB; the even thread computes qA, the odd thread qB, and they swap halves by shuffle.
     bool oob = false;
-    for (int base = 0; base < npairs; base += 64) {
-      const int pA = base + lane, pB = base + 32 + lane;
+#pragma unroll 2
+    for (int base = 0; base < npairs; base += 2 * gthreads) {
+      const int pA = base + tig, pB = base + gthreads + tig;
       bool cx[4];  // crossover decisions for dims 2pA, 2pA+1, 2pB, 2pB+1
       if (P.replay) {
         const double* u = P.r_uni + c * (int64_t)(D + 1);
@@ -154,16 +167,16 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
         cx[2] = (pB < npairs) && ((2 * pB == nstart) || (__ldg(u + 2 * pB) < P.CR));
         cx[3] = (pB < npairs) && ((2 * pB + 1 == nstart) || (__ldg(u + 2 * pB + 1) < P.CR));
       } else {
-        const int q = (base >> 1) + (lane >> 1) + ((lane & 1) ? 16 : 0);  // even lane: qA, odd lane: qB
+        const int q = ((tig & 1) ? pB : pA) >> 1;  // even thread: qA, odd thread: qB
         const u32x4 w = philox4x32_10((uint32_t)q, cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-        // even lane keeps (x,y) of qA for pA and needs (x,y) of qB from its odd neighbour;
-        // odd lane keeps (z,w) of qB for pB and needs (z,w) of qA from its even neighbour.
-        const uint32_t send0 = (lane & 1) ? w.x : w.z;
-        const uint32_t send1 = (lane & 1) ? w.y : w.w;
+        // even thread keeps (x,y) of qA for pA and needs (x,y) of qB from its odd neighbour;
+        // odd thread keeps (z,w) of qB for pB and needs (z,w) of qA from its even neighbour.
+        const uint32_t send0 = (tig & 1) ? w.x : w.z;
+        const uint32_t send1 = (tig & 1) ? w.y : w.w;
         const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1);
         const uint32_t got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-        const uint32_t a0 = (lane & 1) ? got0 : w.x, a1 = (lane & 1) ? got1 : w.y;  // words for chunk pA
-        const uint32_t b0 = (lane & 1) ? w.z : got0, b1 = (lane & 1) ? w.w : got1;  // words for chunk pB
+        const uint32_t a0 = (tig & 1) ? got0 : w.x, a1 = (tig & 1) ? got1 : w.y;  // words for chunk pA
+        const uint32_t b0 = (tig & 1) ? w.z : got0, b1 = (tig & 1) ? w.w : got1;  // words for chunk pB
         cx[0] = (pA < npairs) && ((2 * pA == nstart) || ((uint64_t)a0 < P.thr));
         cx[1] = (pA < npairs) && ((2 * pA + 1 == nstart) || ((uint64_t)a1 < P.thr));
         cx[2] = (pB < npairs) && ((2 * pB == nstart) || ((uint64_t)b0 < P.thr));
@@ -178,8 +191,8 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
           if (cx[2 * h]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
           if (cx[2 * h + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
           if (P.bounds_mode != BOUNDS_NONE) {
-            const double l0 = __ldg(P.lo + 2 * p), l1 = __ldg(P.lo + 2 * p + 1);
-            const double h0 = __ldg(P.hi + 2 * p), h1 = __ldg(P.hi + 2 * p + 1);
+            const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p + 1);
+            const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p + 1);
             if (P.bounds_mode == BOUNDS_CLAMP) {
               x.x = (x.x > l0) ? x.x : l0;
               x.x = (x.x < h0) ? x.x : h0;
@@ -192,64 +205,58 @@ __global__ void __launch_bounds__(kTmaMaxWarps * 32, 1)
         }
       }
     }
-    oob = __any_sync(0xffffffffu, oob);
-    __syncwarp();
+    oob = group_any(grp, oob);  // also the barrier that publishes the trial vector to the group
 
     const double* s_trial = reinterpret_cast<const double*>(s_d0);
     double E = CUDART_INF;
-    if (!oob) E = warp_cost<COST>(s_trial, D, lane, P.cost);
-    E = dadd(E, warp_penalty(s_trial, D, lane, P.pen));
+    if (!oob) E = group_cost<COST>(grp, s_trial, D, P.cost);
+    E = dadd(E, group_penalty(grp, s_trial, D, P.pen));
 
     if (P.cap_trial != nullptr) {
-      for (int i = lane; i < D; i += 32) P.cap_trial[c * D + i] = s_trial[i];
-      if (lane == 0) P.cap_energy[c] = E;
+      for (int i = tig; i < D; i += gthreads) P.cap_trial[c * D + i] = s_trial[i];
+      if (leader) P.cap_energy[c] = E;
     }
 
     const double e_old = __ldg(P.e_cur + c);
     const bool acc = E < e_old;
-    // make the generic-proxy writes of the trial visible to the async proxy, then one lane stores
+    // generic-proxy writes of the trial -> visible to the async proxy; all reads of this stage done
     fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
+    group_sync(grp);
+    if (acc) {
+      ++g_nacc;
+      if (E < g_best_e) {
+        g_best_e = E;
+        g_best_idx = c;
+      }
+    }
+    if (isinf(E)) ++g_ninf;
+    if (leader) {
       bulk_s2g(P.pop_next + c * D, acc ? (const void*)s_d0 : (const void*)s_par, row_bytes);
       bulk_commit();
       P.e_next[c] = acc ? E : e_old;
-    }
-    if (acc) {
-      ++w_nacc;
-      if (E < w_best_e) {
-        w_best_e = E;
-        w_best_idx = c;
-      }
-    }
-    if (isinf(E)) ++w_ninf;
-
-    // refill this stage with the row it serves next, once the store has finished reading it
-    const int64_t cn = c + (int64_t)stages * nw;
-    if (lane == 0) {
+      // refill this stage with the row it serves next, once the store has finished reading it
+      const int64_t cn = c + (int64_t)stages * ng;
       bulk_wait_read0();
       if (cn < P.np) issue(cn, s);
     }
-    __syncwarp();
     if (++s == stages) {
       s = 0;
       parity ^= 1u;
     }
   }
-  if (lane == 0) bulk_wait_all0();
-
-  if (lane == 0) {
-    sh_e[warp] = w_best_e;
-    sh_i[warp] = w_best_idx;
-    sh_ninf[warp] = w_ninf;
-    sh_nacc[warp] = w_nacc;
+  if (leader) {
+    bulk_wait_all0();
+    sh_e[group] = g_best_e;
+    sh_i[group] = g_best_idx;
+    sh_ninf[group] = g_ninf;
+    sh_nacc[group] = g_nacc;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     double be = sh_e[0];
     int64_t bi = sh_i[0];
     unsigned long long ni = sh_ninf[0], na = sh_nacc[0];
-    for (int w = 1; w < wpc; ++w) {
+    for (int w = 1; w < ngroups; ++w) {
       if (sh_e[w] < be || (sh_e[w] == be && sh_i[w] < bi)) {
         be = sh_e[w];
         bi = sh_i[w];

@@ -727,9 +727,9 @@ class DifferentialEvolutionSolver2(object):
         import torch
         import torch.distributed as dist
         rec = self._engine.pack_best()
-        gathered = torch.empty((self._world, rec.shape[0]), dtype=rec.dtype, device=rec.device)
-        dist.all_gather_into_tensor(gathered, rec)
-        self._engine.merge_best(gathered)
+        gathered = torch.empty((self._world * rec.shape[0],), dtype=rec.dtype, device=rec.device)
+        dist.all_gather_into_tensor(gathered, rec)   # flat output: accepted by both NCCL and gloo
+        self._engine.merge_best(gathered.view(self._world, rec.shape[0]))
 
     def _Step(self, cost=None, ExtraArgs=None, **kwds):
         """One generation (differential_evolution.py:531-625)."""
