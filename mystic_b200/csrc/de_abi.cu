@@ -165,15 +165,28 @@ int ensure_parts(mb2_ctx* c, int n) {
   return MB2_OK;
 }
 
-typedef void (*TmaKernel)(const StepParams, int, int);
+typedef void (*TmaKernel)(const StepParams, int);
 
-TmaKernel pick_tma_kernel(int cost) {
+template <int GW, int MAXT>
+TmaKernel pick_tma_cost(int cost) {
   switch (cost) {
-    case MB2_COST_ROSEN: return de_step_best1bin_tma_kernel<COST_ROSEN>;
-    case MB2_COST_CORANA: return de_step_best1bin_tma_kernel<COST_CORANA>;
-    case MB2_COST_GRIEWANGK: return de_step_best1bin_tma_kernel<COST_GRIEWANGK>;
-    case MB2_COST_ZIMMERMANN: return de_step_best1bin_tma_kernel<COST_ZIMMERMANN>;
-    case MB2_COST_CHEBYSHEV: return de_step_best1bin_tma_kernel<COST_CHEBYSHEV>;
+    case MB2_COST_ROSEN: return de_step_best1bin_tma_kernel<COST_ROSEN, GW, MAXT>;
+    case MB2_COST_CORANA: return de_step_best1bin_tma_kernel<COST_CORANA, GW, MAXT>;
+    case MB2_COST_GRIEWANGK: return de_step_best1bin_tma_kernel<COST_GRIEWANGK, GW, MAXT>;
+    case MB2_COST_ZIMMERMANN: return de_step_best1bin_tma_kernel<COST_ZIMMERMANN, GW, MAXT>;
+    case MB2_COST_CHEBYSHEV: return de_step_best1bin_tma_kernel<COST_CHEBYSHEV, GW, MAXT>;
+  }
+  return nullptr;
+}
+
+// threads <= 512 use the 128-register build, larger CTAs the 64-register build
+TmaKernel pick_tma_kernel(int cost, int gwarps, int threads) {
+  const bool big = threads > 512;
+  switch (gwarps) {
+    case 1: return big ? pick_tma_cost<1, 1024>(cost) : pick_tma_cost<1, 512>(cost);
+    case 2: return big ? pick_tma_cost<2, 1024>(cost) : pick_tma_cost<2, 512>(cost);
+    case 4: return big ? pick_tma_cost<4, 1024>(cost) : pick_tma_cost<4, 512>(cost);
+    case 8: return big ? pick_tma_cost<8, 1024>(cost) : pick_tma_cost<8, 512>(cost);
   }
   return nullptr;
 }
@@ -185,21 +198,23 @@ int env_int(const char* name, int dflt) {
 
 // Ring geometry of the TMA kernel: groups per CTA, warps per group, stages per group, dynamic
 // smem.  Returns false when a row does not fit (the LDG kernel is used instead).
+// Measured on B200 at D=1024 (profiles/README.md): concurrency across rows matters most (8 groups
+// beat 4 groups with deeper rings), then warps per row, then stages.
 bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
   const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
   const size_t budget = 220 * 1024;
   if (row * 4 > budget) return false;
   const size_t slots = (budget - row) / (3 * row);  // (group, stage) buffers that fit on one SM
-  // warps per row: enough threads that a row is at most two trips of the mutation loop
-  int gw = 1;
-  while (gw < 8 && (size_t)dim > (size_t)gw * 32 * 8) gw <<= 1;
-  int maxg = kTmaMaxThreads / (gw * 32);
-  if (maxg > kTmaMaxGroups) maxg = kTmaMaxGroups;
-  int g = maxg, st = 1;
+  int g = kTmaMaxGroups;
   while (g > 1 && (size_t)g > slots) g >>= 1;
+  // warps per row: every thread should own at least one pair of 16-byte chunks (4 dimensions)
+  int gw = 1;
+  while (gw < 8 && g * (gw * 2) * 32 <= kTmaMaxThreads && (gw * 2) * 32 * 4 <= dim) gw <<= 1;
+  if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
+  int st = 1;
   while (st < kTmaMaxStages && (size_t)g * (st * 2) <= slots) st *= 2;
   const int eg = env_int("MB2_TMA_GROUPS", 0), ew = env_int("MB2_TMA_GWARPS", 0), es = env_int("MB2_TMA_STAGES", 0);
-  if (eg >= 1 && eg <= kTmaMaxGroups && (ew == 1 || ew == 2 || ew == 4 || ew == 8) && es >= 1 &&
+  if (eg >= 1 && eg <= kTmaMaxGroups && (ew == 1 || (ew == 2 || ew == 4 || ew == 8) && eg <= 15) && es >= 1 &&
       es <= kTmaMaxStages && (size_t)eg * es <= slots && eg * ew * 32 <= kTmaMaxThreads) {
     g = eg;
     gw = ew;
@@ -227,7 +242,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 &&
       tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
-    kt = pick_tma_kernel(c->cost);
+    kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
 
   int wpc, smem;
   int occ = 0;
@@ -293,7 +308,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->grid = (int)grid;
   c->smem = smem;
   if (kt != nullptr)
-    kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts, tw);
+    kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
   else
     k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());

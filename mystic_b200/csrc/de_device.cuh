@@ -70,26 +70,30 @@ __device__ __forceinline__ void store4(double* __restrict__ row, int i0, int D, 
 // sums are combined by a fixed xor tree over the 32 lanes and then over the 8 virtual warps as
 // ((w0+w1)+(w2+w3))+((w4+w5)+(w6+w7)).  A group of G warps emulates the 256 virtual threads with
 // M = 8/G accumulators per thread, so every kernel (any G) produces bit-identical energies.
+template <int GW>
 struct Group {
+  static constexpr int kWarps = GW;          // warps per group (1, 2, 4 or 8)
+  static constexpr int kThreads = 32 * GW;
+  static constexpr int kAcc = 8 / GW;        // accumulators per thread (virtual threads emulated)
   int tig;        // thread index in the group
-  int nthreads;   // 32 * G
   int wig;        // warp index in the group
   int lane;
-  int M;          // 256 / nthreads: accumulators per thread
-  int bar_id;     // named barrier of the group (unused when G == 1)
+  int bar_id;     // named barrier of the group (unused when GW == 1)
   double* scratch;  // 16 doubles of shared memory per group
 };
 
-__device__ __forceinline__ void group_sync(const Group& g) {
-  if (g.nthreads == 32)
+template <int GW>
+__device__ __forceinline__ void group_sync(const Group<GW>& g) {
+  if (GW == 1)
     __syncwarp();
   else
-    asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "r"(g.nthreads) : "memory");
+    asm volatile("bar.sync %0, %1;" ::"r"(g.bar_id), "n"(32 * GW) : "memory");
 }
 
 // barrier + OR reduction of a predicate over the group
-__device__ __forceinline__ bool group_any(const Group& g, bool v) {
-  if (g.nthreads == 32) return __any_sync(0xffffffffu, v);
+template <int GW>
+__device__ __forceinline__ bool group_any(const Group<GW>& g, bool v) {
+  if (GW == 1) return __any_sync(0xffffffffu, v);
   unsigned r;
   asm volatile(
       "{\n"
@@ -99,17 +103,17 @@ __device__ __forceinline__ bool group_any(const Group& g, bool v) {
       "selp.u32 %0, 1, 0, p;\n"
       "}\n"
       : "=r"(r)
-      : "r"((unsigned)v), "r"(g.bar_id), "r"(g.nthreads)
+      : "r"((unsigned)v), "r"(g.bar_id), "n"(32 * GW)
       : "memory");
   return r != 0;
 }
 
-template <bool PROD>
-__device__ __forceinline__ double group_reduce(const Group& g, const double (&acc)[8], int slot) {
-  const int G = g.nthreads >> 5;
+template <bool PROD, int GW>
+__device__ __forceinline__ double group_reduce(const Group<GW>& g, const double (&acc)[8 / GW], int slot) {
+  constexpr int G = GW;
 #pragma unroll
-  for (int m = 0; m < 8; ++m) {
-    if (m < g.M) {
+  for (int m = 0; m < 8 / GW; ++m) {
+    {
       double v = acc[m];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -151,17 +155,21 @@ __device__ __forceinline__ double horner(const double* __restrict__ c, int n, do
 // returns the same value.  Per-element terms follow the reference's operation order without
 // FMA, so each term is bit-identical to the reference; only the summation tree differs
 // (<= 1e-12 relative).
-template <int COST>
-__device__ __forceinline__ double group_cost(const Group& g, const double* xs, int D, const CostParams& cp) {
+template <int COST, int GW>
+__device__ __forceinline__ double group_cost(const Group<GW>& g, const double* xs, int D, const CostParams& cp) {
+  constexpr int NA = 8 / GW;       // accumulators per thread
+  constexpr int NT = 32 * GW;      // threads per group
   if (COST == COST_ROSEN) {
     // dejong.py:98-101: sum(100*(x[1:]-x[:-1]**2)**2 + (1-x[:-1])**2)
-    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    double acc[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) acc[m] = 0.0;
     const int n = D - 1;
     for (int i0 = g.tig; i0 < n; i0 += 256) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int i = i0 + m * g.nthreads;
-        if (m < g.M && i < n) {
+      for (int m = 0; m < NA; ++m) {
+        const int i = i0 + m * NT;
+        if (i < n) {
           const double a = xs[i], b = xs[i + 1];
           const double t = dsub(b, dmul(a, a));
           const double u = dsub(1.0, a);
@@ -169,7 +177,7 @@ __device__ __forceinline__ double group_cost(const Group& g, const double* xs, i
         }
       }
     }
-    return group_reduce<false>(g, acc, 0);
+    return group_reduce<false, GW>(g, acc, 0);
   } else if (COST == COST_CORANA) {
     // storn.py:77-96, strictly sequential over 4 terms; threads compute redundantly
     const double d[4] = {1., 1000., 10., 100.};
@@ -202,21 +210,25 @@ __device__ __forceinline__ double group_cost(const Group& g, const double* xs, i
     return r;
   } else if (COST == COST_GRIEWANGK) {
     // storn.py:135-139: sum(c*c)/4000 - prod(cos(c_i/sqrt(i+1))) + 1
-    double sa[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
-    double pa[8] = {1., 1., 1., 1., 1., 1., 1., 1.};
+    double sa[NA], pa[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+      sa[m] = 0.0;
+      pa[m] = 1.0;
+    }
     for (int i0 = g.tig; i0 < D; i0 += 256) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int i = i0 + m * g.nthreads;
-        if (m < g.M && i < D) {
+      for (int m = 0; m < NA; ++m) {
+        const int i = i0 + m * NT;
+        if (i < D) {
           const double c = xs[i];
           sa[m] = dadd(sa[m], dmul(c, c));
           pa[m] = dmul(pa[m], cos(c / sqrt((double)i + 1.0)));
         }
       }
     }
-    const double s = group_reduce<false>(g, sa, 0);
-    const double p = group_reduce<true>(g, pa, 1);
+    const double s = group_reduce<false, GW>(g, sa, 0);
+    const double p = group_reduce<true, GW>(g, pa, 1);
     return dadd(dsub(s / 4000.0, p), 1.0);
   } else if (COST == COST_ZIMMERMANN) {
     // storn.py:182-191 (D == 2)
@@ -238,13 +250,15 @@ __device__ __forceinline__ double group_cost(const Group& g, const double* xs, i
     return m;
   } else {  // COST_CHEBYSHEV
     // _model_helper.py:16-33
-    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    double acc[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) acc[m] = 0.0;
     const int M = cp.cheb_M;
     for (int i0 = g.tig; i0 < M; i0 += 256) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int i = i0 + m * g.nthreads;
-        if (m < g.M && i < M) {
+      for (int m = 0; m < NA; ++m) {
+        const int i = i0 + m * NT;
+        if (i < M) {
           const double px = horner(xs, D, __ldg(cp.cheb_x + i));
           if (px < -1.0 || px > 1.0) {
             const double u = dsub(1.0, px);
@@ -253,7 +267,7 @@ __device__ __forceinline__ double group_cost(const Group& g, const double* xs, i
         }
       }
     }
-    double r = group_reduce<false>(g, acc, 0);
+    double r = group_reduce<false, GW>(g, acc, 0);
     double px = dsub(horner(xs, D, 1.2), cp.cheb_tp);
     if (px < 0.0) r = dadd(r, dmul(px, px));
     px = dsub(horner(xs, D, -1.2), cp.cheb_tm);
@@ -272,19 +286,24 @@ struct PenaltyParams {
 };
 
 // term 0 innermost; value = t_{n-1} + (... + (t_0 + 0.0))  (penalty.py:88,147,388,447)
-__device__ __forceinline__ double group_penalty(const Group& g, const double* xs, int D, const PenaltyParams& pp) {
+template <int GW>
+__device__ __forceinline__ double group_penalty(const Group<GW>& g, const double* xs, int D, const PenaltyParams& pp) {
+  constexpr int NA = 8 / GW;
+  constexpr int NT = 32 * GW;
   double total = 0.0;
   for (int t = 0; t < pp.n; ++t) {
     const double* gr = pp.G + (int64_t)t * D;
-    double acc[8] = {0., 0., 0., 0., 0., 0., 0., 0.};
+    double acc[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) acc[m] = 0.0;
     for (int i0 = g.tig; i0 < D; i0 += 256) {
 #pragma unroll
-      for (int m = 0; m < 8; ++m) {
-        const int i = i0 + m * g.nthreads;
-        if (m < g.M && i < D) acc[m] = dadd(acc[m], dmul(__ldg(gr + i), xs[i]));
+      for (int m = 0; m < NA; ++m) {
+        const int i = i0 + m * NT;
+        if (i < D) acc[m] = dadd(acc[m], dmul(__ldg(gr + i), xs[i]));
       }
     }
-    const double pf = dsub(group_reduce<false>(g, acc, 0), __ldg(pp.h + t));
+    const double pf = dsub(group_reduce<false, GW>(g, acc, 0), __ldg(pp.h + t));
     const double k = __ldg(pp.kscale + t);
     const int ty = __ldg(pp.ptype + t);
     double v;

@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
   __shared__ double s_scratch[kWarpsPerCtaMax * 16];
   double* s_best = smem;                              // [Dp]
   double* s_trial = smem + Dp + (size_t)warp * Dp;   // [Dp] per warp
-  const Group grp = {lane, 32, 0, lane, 8, 0, s_scratch + warp * 16};  // one warp per row
+  const Group<1> grp = {lane, 0, lane, 0, s_scratch + warp * 16};  // one warp per row
 
   if (P.mode == MODE_STEP && kNeedsBest) {
     for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
               if (P.bounds_mode == BOUNDS_CLAMP) {
                 x[e] = (x[e] > l) ? x[e] : l;  // python max(lo, x)
                 x[e] = (x[e] < h) ? x[e] : h;  // python min(hi, x)
-              }
-              oob |= (x[e] < l) || (x[e] > h);
+              } else
+                oob |= (x[e] < l) || (x[e] > h);  // after a clamp nothing is out of range
             }
           }
         }

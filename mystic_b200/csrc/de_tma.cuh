@@ -57,7 +57,7 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 
 constexpr int kTmaMaxGroups = 16;  // groups per CTA (named barriers 1..15 serve groups of more than one warp)
 constexpr int kTmaMaxStages = 4;
-constexpr int kTmaMaxThreads = 512;
+constexpr int kTmaMaxThreads = 1024;
 
 // donors + start index of candidate c (replayed or Philox), uniform across the group
 __device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int64_t (&r)[2], int* nstart) {
@@ -70,10 +70,10 @@ __device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int6
   }
 }
 
-// requires: dim even (rows are 16-byte multiples), MODE_STEP.  blockDim = groups * gwarps * 32.
-template <int COST>
-__global__ void __launch_bounds__(kTmaMaxThreads, 1)
-    de_step_best1bin_tma_kernel(const __grid_constant__ StepParams P, int stages, int gwarps) {
+// requires: dim even (rows are 16-byte multiples), MODE_STEP.  blockDim = groups * GW * 32 <= MAXT.
+template <int COST, int GW, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+    de_step_best1bin_tma_kernel(const __grid_constant__ StepParams P, int stages) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[kTmaMaxGroups * kTmaMaxStages];
   __shared__ double s_scratch[kTmaMaxGroups * 16];
@@ -84,13 +84,13 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1)
   const int D = P.dim;
   const unsigned row_bytes = (unsigned)D * 8u;
   const size_t row_stride = ((size_t)row_bytes + 127) & ~(size_t)127;  // keep every buffer 128-B aligned
-  const int gthreads = gwarps * 32;
+  constexpr int gthreads = GW * 32;
   const int group = threadIdx.x / gthreads;
   const int ngroups = blockDim.x / gthreads;
   const int tig = threadIdx.x - group * gthreads;
   const int lane = threadIdx.x & 31;
   const bool leader = (tig == 0);
-  const Group grp = {tig, gthreads, tig >> 5, lane, 256 / gthreads, 1 + group, s_scratch + group * 16};
+  const Group<GW> grp = {tig, tig >> 5, lane, 1 + group, s_scratch + group * 16};
 
   double* s_best = reinterpret_cast<double*>(smem_raw);
   unsigned char* s_ring = smem_raw + row_stride + (size_t)group * stages * 3 * row_stride;
@@ -198,8 +198,9 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1)
               x.x = (x.x < h0) ? x.x : h0;
               x.y = (x.y > l1) ? x.y : l1;
               x.y = (x.y < h1) ? x.y : h1;
+            } else {
+              oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);  // nothing is out of range after a clamp
             }
-            oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);
           }
           s_d0[p] = x;
         }
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kTmaMaxThreads, 1)
 
     const double* s_trial = reinterpret_cast<const double*>(s_d0);
     double E = CUDART_INF;
-    if (!oob) E = group_cost<COST>(grp, s_trial, D, P.cost);
+    if (!oob) E = group_cost<COST, GW>(grp, s_trial, D, P.cost);
     E = dadd(E, group_penalty(grp, s_trial, D, P.pen));
 
     if (P.cap_trial != nullptr) {
