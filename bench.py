@@ -209,6 +209,7 @@ def main():
     ap.add_argument('--np', type=int, default=0, help='override rows per GPU (testing)')
     ap.add_argument('--ref-np', type=int, default=4096, help='rows of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--sustain', type=float, default=0.7, help='seconds of un-timed load before the timed region')
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
     if args.np:
@@ -259,6 +260,16 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    # un-timed sustain phase (~0.7 s of back-to-back generations): the timed region below is only a
+    # few milliseconds, too short for nvidia-smi to sample, so clocks / throttle reasons are sampled
+    # from here through the end of the timed region, under the same load.
+    t_sus = time.perf_counter()
+    while time.perf_counter() - t_sus < args.sustain:
+        for _ in range(10):
+            eng.step()
+            if distributed:
+                s._exchange_best()
+        torch.cuda.synchronize()
     barrier()
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
