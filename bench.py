@@ -257,6 +257,22 @@ def main():
         s.Step()
     eng = s._engine
     grid, block, smem = eng.launch_info()
+    def timed(nsteps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(nsteps):
+            eng.step()                           # K2 + K3 on torch's current stream
+            if distributed:
+                s._exchange_best()
+        e1.record()
+        barrier()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
+        if distributed:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    burst_ms = timed(steps)                      # cold clocks/power state: a burst figure, reported beside `value`
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -270,24 +286,9 @@ def main():
             if distributed:
                 s._exchange_best()
         torch.cuda.synchronize()
-    barrier()
     launches0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(steps):
-        eng.step()                               # K2 + K3 on torch's current stream
-        if distributed:
-            s._exchange_best()
-    ev1.record()
-    barrier()
+    dev_ms = timed(steps)                        # the reported value: K generations under sustained load
     launches = eng.launch_count() - launches0
-    dev_ms = ev0.elapsed_time(ev1)
-    # ---- the same K generations through the public API (Step(): + D2H of the best, bookkeeping,
-    #      termination checks, monitor) -- used for e2e below together with the H2D of the population
-    t = torch.tensor([dev_ms], dtype=torch.float64, device='cuda')
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
     inf_frac = s._last[0] / float(NP_global) if s._last else 0.0
     acc_frac = s._last[1] / float(NP_global) if s._last else 0.0
     clocks = sampler.stop() if sampler else None
@@ -338,6 +339,7 @@ def main():
     achieved = bpc * NP_local / step_s / 1e9
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks_src,
+                'frac_burst': bpc * NP_local / (burst_ms * 1e-3 / steps) / 1e9 / peaks['hbm_gbs'],
                 'algorithmic_bytes_per_candidate': bpc,
                 'kernel': 'de_step_kernel (fused generation) + de_finalize_kernel, per generation, per GPU'}
     flops = algorithmic_flops_per_candidate(w)
@@ -352,6 +354,7 @@ def main():
                    'rng': 'philox4x32-10 in-kernel', 'l2': 'inputs larger than L2 (population %.0f MiB per buffer)'
                    % (NP_local * D * 8 / 2 ** 20), 'grid': grid, 'block': block, 'smem_bytes': smem,
                    'inf_fraction': inf_frac, 'accept_fraction': acc_frac,
+                   'sustain_s_before_timing': args.sustain, 'burst_ms_per_step': burst_ms / steps,
                    'parallelism': 'candidate-sharded x%d, all-gather best per generation' % world if distributed
                    else 'single GPU'},
         'roofline': roofline,

@@ -160,6 +160,11 @@ int mb2_read_result(mb2_ctx* ctx, mb2_result* out, double* x_host, void* stream)
  * (inf if out of the strict range else cost(x)) + penalty(x).  x_dev [n, dim], out_dev [n]. */
 int mb2_eval_cost(mb2_ctx* ctx, const double* x_dev, int64_t n, double* out_dev, void* stream);
 
+/* self test of the table-driven divide used by the griewangk cost (x / sqrt(i+1) without a divide
+ * instruction): compares n random operands in [-span, span] bit for bit with the IEEE divide and
+ * returns the number of mismatches (expected 0).  Requires mb2_set_cost(GRIEWANGK) first. */
+int mb2_selftest_division(mb2_ctx* ctx, int64_t n, uint64_t seed, double span, int64_t* mismatches);
+
 /* launch geometry of the fused kernel (for bench.py / profiling): CTAs, threads, dynamic smem */
 int mb2_launch_info(mb2_ctx* ctx, int32_t* grid, int32_t* block, int32_t* smem_bytes);
 /* number of kernels this library has launched through the context (bench.py gpu_launches) */

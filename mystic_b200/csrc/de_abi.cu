@@ -74,8 +74,9 @@ struct mb2_ctx {
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
-  CostParams cp = {0, nullptr, 0.0, 0.0};
+  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr};
   double* cheb_x = nullptr;
+  double2* grw_tab = nullptr;
   PenaltyParams pp = {0, nullptr, nullptr, nullptr, nullptr};
   int* pen_type = nullptr;
   double* pen_G = nullptr;
@@ -207,9 +208,10 @@ bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
   const size_t slots = (budget - row) / (3 * row);  // (group, stage) buffers that fit on one SM
   int g = kTmaMaxGroups;
   while (g > 1 && (size_t)g > slots) g >>= 1;
-  // warps per row: every thread should own at least one pair of 16-byte chunks (4 dimensions)
+  // warps per row: about 8 dimensions per thread (B200 sweeps: D=1024 -> 4 warps, D=256 -> 1 warp;
+  // more warps per row only add barrier and per-warp overhead once the CTA is full)
   int gw = 1;
-  while (gw < 8 && g * (gw * 2) * 32 <= kTmaMaxThreads && (gw * 2) * 32 * 4 <= dim) gw <<= 1;
+  while (gw < 8 && g * (gw * 2) * 32 <= kTmaMaxThreads && (gw * 2) * 32 * 8 <= dim) gw <<= 1;
   if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
   int st = 1;
   while (st < kTmaMaxStages && (size_t)g * (st * 2) <= slots) st *= 2;
@@ -384,6 +386,7 @@ int mb2_destroy(mb2_ctx* c) {
   cudaFree(c->lo);
   cudaFree(c->hi);
   cudaFree(c->cheb_x);
+  cudaFree(c->grw_tab);
   cudaFree(c->pen_type);
   cudaFree(c->pen_G);
   cudaFree(c->pen_h);
@@ -490,7 +493,38 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
     c->cp.cheb_tp = tp;
     c->cp.cheb_tm = tm;
   }
+  if (cost == MB2_COST_GRIEWANGK && c->grw_tab == nullptr) {
+    // {sqrt(i+1.0), 1/sqrt(i+1.0)}: glibc sqrt and the host divide are correctly rounded
+    std::vector<double2> tab(c->dim);
+    for (int i = 0; i < c->dim; ++i) {
+      volatile double sq = std::sqrt((double)i + 1.0);
+      volatile double rc = 1.0 / sq;
+      tab[i].x = sq;
+      tab[i].y = rc;
+    }
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaMalloc(&c->grw_tab, sizeof(double2) * c->dim));
+    CUDA_TRY(cudaMemcpy(c->grw_tab, tab.data(), sizeof(double2) * c->dim, cudaMemcpyHostToDevice));
+    c->cp.grw_tab = c->grw_tab;
+  }
   c->cost = cost;
+  return MB2_OK;
+}
+
+int mb2_selftest_division(mb2_ctx* c, int64_t n, uint64_t seed, double span, int64_t* mismatches) {
+  if (c == nullptr || mismatches == nullptr || n < 1) return fail(MB2_EINVAL, "bad argument");
+  if (c->grw_tab == nullptr) return fail(MB2_ESTATE, "set the griewangk cost first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  unsigned long long* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
+  selftest_division_kernel<<<c->sm_count * 8, 256>>>(n, (uint32_t)seed, (uint32_t)(seed >> 32), span, c->grw_tab, c->dim, d);
+  CUDA_TRY(cudaGetLastError());
+  unsigned long long h = 0;
+  CUDA_TRY(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  ++c->launches;
+  *mismatches = (int64_t)h;
   return MB2_OK;
 }
 

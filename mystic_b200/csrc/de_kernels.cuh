@@ -427,6 +427,24 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// self test: div_by_table(c, sqrt(i+1), 1/sqrt(i+1)) against the IEEE divide on n Philox-random
+// operands; counts bit mismatches
+__global__ void selftest_division_kernel(int64_t n, uint32_t k0, uint32_t k1, double span, const double2* tab, int D,
+                                         unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const u32x4 v = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 7u, 9u, k0, k1);
+    const double u = u64_to_unit(((uint64_t)v.x << 32) | v.y);
+    const double c = (2.0 * u - 1.0) * span;
+    const int i = (int)(v.z % (uint32_t)D);
+    const double2 sr = tab[i];
+    const double want = c / sqrt((double)i + 1.0);
+    const double got = div_by_table(c, sr.x, sr.y);
+    if (__double_as_longlong(want) != __double_as_longlong(got)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
 }

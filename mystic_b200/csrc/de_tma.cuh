@@ -77,6 +77,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[kTmaMaxGroups * kTmaMaxStages];
   __shared__ double s_scratch[kTmaMaxGroups * 16];
+  __shared__ int s_nstart[kTmaMaxGroups * kTmaMaxStages];  // crossover start index of the row in each stage
   __shared__ double sh_e[kTmaMaxGroups];
   __shared__ int64_t sh_i[kTmaMaxGroups];
   __shared__ unsigned long long sh_ninf[kTmaMaxGroups], sh_nacc[kTmaMaxGroups];
@@ -106,11 +107,14 @@ __global__ void __launch_bounds__(MAXT, 1)
   const int64_t g0 = (int64_t)blockIdx.x * ngroups + group;
   const int64_t ng = (int64_t)gridDim.x * ngroups;
 
-  // issue the three row loads of candidate c into stage s (group leader only)
+  // issue the three row loads of candidate c into stage s (group leader only).  The draws are made
+  // once, here; the start index travels to the group through shared memory (published by the
+  // release of the mbarrier arrive, acquired by the group's wait on the same barrier).
   auto issue = [&](int64_t c, int s) {
     int64_t r[2];
     int nstart;
     best1_draws(P, c, r, &nstart);
+    s_nstart[group * kTmaMaxStages + s] = nstart;
     unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
     mbar_expect_tx(bars + s, 3u * row_bytes);
     bulk_g2s(buf, P.pop_cur + c * D, row_bytes, bars + s);
@@ -140,16 +144,11 @@ __global__ void __launch_bounds__(MAXT, 1)
     const double2* s_d1 = reinterpret_cast<const double2*>(buf + 2 * row_stride);
     const double2* s_b2 = reinterpret_cast<const double2*>(s_best);
 
-    int nstart;
-    if (P.replay) {
-      nstart = __ldg(P.r_nstart + c);
-    } else {
-      int64_t r[2];
-      best1_draws(P, c, r, &nstart);
-    }
     const uint32_t cand_g = (uint32_t)(P.global_offset + c);
+    const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
 
     mbar_wait(bars + s, parity);
+    const int nstart = s_nstart[group * kTmaMaxStages + s];
 
     // ---- trial vector (strategy.py:77-85), two conflict-free double2 chunks per thread per trip:
     //      chunk pA = base + tig and pB = pA + gthreads.  Crossover words: Philox block q covers
@@ -218,7 +217,6 @@ __global__ void __launch_bounds__(MAXT, 1)
       if (leader) P.cap_energy[c] = E;
     }
 
-    const double e_old = __ldg(P.e_cur + c);
     const bool acc = E < e_old;
     // generic-proxy writes of the trial -> visible to the async proxy; all reads of this stage done
     fence_proxy_async();

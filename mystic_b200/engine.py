@@ -169,6 +169,11 @@ class DeviceEngine(object):
         check(lib.mb2_eval_cost(self._ctx, x.data_ptr(), int(x.shape[0]), out.data_ptr(), self._stream()))
         return out.cpu().numpy()
 
+    def selftest_division(self, n, seed=1, span=400.0):
+        bad = ctypes.c_int64(-1)
+        check(lib.mb2_selftest_division(self._ctx, int(n), int(seed), float(span), ctypes.byref(bad)))
+        return bad.value
+
     def launch_info(self):
         g, b, s = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         check(lib.mb2_launch_info(self._ctx, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))

@@ -284,3 +284,15 @@ def test_full_size_properties_config2():
         runs.append((eng.population_tensor().clone(), [h[0] for h in hist]))
         eng.close()
     assert torch.equal(runs[0][0], runs[1][0]) and runs[0][1] == runs[1][1]   # deterministic
+
+
+def test_table_divide_is_ieee_exact():
+    """griewangk's x / sqrt(i+1) is computed from a {sqrt, reciprocal} table with two Markstein
+    refinements; it must equal the IEEE divide bit for bit"""
+    from mystic_b200 import models
+    from mystic_b200.engine import DeviceEngine
+    eng = DeviceEngine(8, 1024)
+    eng.set_cost(models.griewangk.cost_id, [])
+    for span in (1e-3, 1.0, 400.0, 1e6, 1e150):
+        assert eng.selftest_division(1 << 24, seed=int(span * 7) + 3, span=span) == 0, span
+    eng.close()
