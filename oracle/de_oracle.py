@@ -261,14 +261,17 @@ def _mulhi64(a, b):
     return mid >> np.uint64(32)
 
 
-def philox_donors(seed, generation, cand, NP, D, k):
+def philox_donors(seed, generation, cand, NP, D, k, offset=0):
     """Donor indices [n,k] (distinct, != cand, uniform over ordered k-tuples) and start index.
 
     stream STREAM_DONORS, counter (block, cand, generation, stream); block b supplies the
     64-bit words r_{2b} = x0<<32|x1 and r_{2b+1} = x2<<32|x3.  Donor i uses r_i:
     t = mulhi64(r_i, NP-1-i) is a rank among the not-yet-excluded indices, converted to an index by
     walking the sorted exclusion list {cand, earlier donors}.  nstart = mulhi64(r_k, D).
-    Replaces random.sample(...)/random.randrange(D) (strategy.py:27,42) in Philox mode."""
+    Replaces random.sample(...)/random.randrange(D) (strategy.py:27,42) in Philox mode.
+
+    `cand` are GLOBAL candidate indices (they key the counter); donors are drawn from the shard
+    [offset, offset+NP) and returned as LOCAL row indices, excluding the candidate's own local row."""
     cand = np.asarray(cand, dtype=np.int64)
     n = cand.shape[0]
     k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
@@ -280,7 +283,7 @@ def philox_donors(seed, generation, cand, NP, D, k):
         words.append((x2.astype(np.uint64) << np.uint64(32)) | x3.astype(np.uint64))
     donors = np.zeros((n, k), dtype=np.int64)
     excl = np.full((n, k + 1), np.iinfo(np.int64).max, dtype=np.int64)  # sorted ascending, padded
-    excl[:, 0] = cand
+    excl[:, 0] = cand - int(offset)
     for i in range(k):
         t = _mulhi64(words[i], NP - 1 - i).astype(np.int64)
         idx = t.copy()
@@ -464,7 +467,7 @@ def step(state, strategy, CR, F, cost, penalty_terms=(), replay=None, philox=Non
         mask = crossover_mask_replay(xover, D, nstart, np.asarray(replay['uni']), CR)
     else:
         cand = np.arange(NP, dtype=np.int64) + int(philox.get('offset', 0))
-        donors, nstart = philox_donors(philox['seed'], g, cand, NP, D, k)
+        donors, nstart = philox_donors(philox['seed'], g, cand, NP, D, k, offset=int(philox.get('offset', 0)))
         words = philox_xover_words(philox['seed'], g, cand, D)
         mask = crossover_mask_philox(xover, D, nstart, words, CR)
     mutant = mutate(base, pop, state.bestSolution, donors, F)
