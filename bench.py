@@ -41,9 +41,12 @@ WORKLOADS = {
     'c5': dict(desc='Griewangk 256-D, NP=2097152/GPU, Best1Bin CR=0.9 F=0.8, clamp +-400',
                cost='griewangk', extra=(), dim=256, np=2097152, strategy='Best1Bin', CR=0.9, F=0.8, lo=-400.,
                hi=400., bounds='clamp', penalty=None, k=2),
-    'c3': dict(desc='chebyshev8cost M=4096, 9 coeffs, NP=1048576/GPU, Best1Exp CR=1.0 F=0.9, init +-100 (Horner)',
+    'c3': dict(desc='chebyshev8cost M=4096, 9 coeffs, NP=1048576/GPU, Best1Exp CR=1.0 F=0.9, init +-100 (FP64 DMMA)',
                cost='chebyshev8cost', extra=(4096,), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
-               lo=-100., hi=100., bounds=None, penalty=None, k=2),
+               lo=-100., hi=100., bounds=None, penalty=None, k=2, tensor_cores=True),
+    'c3h': dict(desc='chebyshev8cost M=4096, 9 coeffs, NP=1048576/GPU, Best1Exp CR=1.0 F=0.9, init +-100 (Horner)',
+                cost='chebyshev8cost', extra=(4096,), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
+                lo=-100., hi=100., bounds=None, penalty=None, k=2),
 }
 
 BIN_STRATEGIES = ('Best1Bin',)
@@ -183,7 +186,8 @@ def build_solver(w, NP_global, distributed, seed):
     from mystic_b200 import DifferentialEvolutionSolver2, penalty
     D = w['dim']
     s = DifferentialEvolutionSolver2(D, NP_global, rng='philox', seed=seed, distributed=distributed,
-                                     CrossProbability=w['CR'], ScalingFactor=w['F'], strategy=w['strategy'])
+                                     CrossProbability=w['CR'], ScalingFactor=w['F'], strategy=w['strategy'],
+                                     tensor_cores=bool(w.get('tensor_cores')))
     if w['bounds'] == 'clamp':
         s.SetStrictRanges([w['lo']] * D, [w['hi']] * D, tight=True)
     elif w['bounds'] == 'reject':
@@ -344,7 +348,13 @@ def main():
                 'kernel': 'de_step_kernel (fused generation) + de_finalize_kernel, per generation, per GPU'}
     flops = algorithmic_flops_per_candidate(w)
     if flops:
-        roofline['fp64_tflops_achieved'] = flops * NP_local / step_s / 1e12
+        # the Chebyshev contraction is FP64-pipe bound: DMMA peak measured on this pool's B200 with
+        # tools/fp64_peak.cu (profiles/r1_fp64_peaks_b200.json): 33.02 TFLOP/s (DFMA 34.15, cuBLAS DGEMM 35.4)
+        tf = flops * NP_local / step_s / 1e12
+        roofline = {'bound': 'tensor', 'achieved': tf, 'peak': 33.02, 'unit': 'TFLOP/s', 'frac': tf / 33.02,
+                    'traffic': None, 'peak_source': 'measured DMMA.8x8x4 peak (profiles/r1_fp64_peaks_b200.json)',
+                    'algorithmic_flops_per_candidate': flops, 'hbm_frac': achieved / peaks['hbm_gbs'],
+                    'kernel': 'de_step_cheb_mma_kernel' if w.get('tensor_cores') else 'de_step_kernel (Horner)'}
 
     line = {
         'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': value, 'unit': 'candidate-evals/s',

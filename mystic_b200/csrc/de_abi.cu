@@ -13,6 +13,7 @@
 #include "../../include/mystic_b200.h"
 #include "de_kernels.cuh"
 #include "de_tma.cuh"
+#include "de_cheb_mma.cuh"
 
 using namespace mb2;
 
@@ -74,7 +75,9 @@ struct mb2_ctx {
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
-  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr};
+  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr};
+  double* cheb_vfrag = nullptr;
+  int cheb_ks = 0;
   double* cheb_x = nullptr;
   double2* grw_tab = nullptr;
   PenaltyParams pp = {0, nullptr, nullptr, nullptr, nullptr};
@@ -236,20 +239,31 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
                    (out_rows == nullptr || (reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
   StrategyInfo s = c->sinfo;
   if (mode != MODE_STEP) s = {BASE_RAND1, XOVER_EXP, 3};  // no best/donors needed; any instance
-  StepKernel k = pick_kernel(s, c->cost, vec);
-  if (k == nullptr) return fail(MB2_EINVAL, "no kernel for strategy %d cost %d", c->strategy, c->cost);
+  const bool cheb_mma = (c->cost == MB2_COST_CHEBYSHEV_MMA);
+  StepKernel k = cheb_mma ? nullptr : pick_kernel(s, c->cost, vec);
+  if (k == nullptr && !cheb_mma) return fail(MB2_EINVAL, "no kernel for strategy %d cost %d", c->strategy, c->cost);
+  typedef void (*ChebKernel)(const StepParams, int, int, int);
+  ChebKernel kc = nullptr;
+  if (cheb_mma)
+    kc = c->cheb_ks == 1 ? de_step_cheb_mma_kernel<1> : (c->cheb_ks == 2 ? de_step_cheb_mma_kernel<2> : de_step_cheb_mma_kernel<4>);
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 &&
-      tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
+      !cheb_mma && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
 
   int wpc, smem;
   int occ = 0;
   int rows_per_cta;
-  if (kt != nullptr) {
+  if (kc != nullptr) {
+    wpc = kChebWarps;
+    rows_per_cta = kChebWarps * kChebBatch;
+    smem = (int)(sizeof(double) * (size_t)kChebWarps * (kChebBatch * c->dim + kChebBatch));
+    CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc, wpc * 32, smem));
+  } else if (kt != nullptr) {
     wpc = tg * tw;
     rows_per_cta = tg;
     smem = tsmem;
@@ -309,7 +323,9 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->wpc = wpc;
   c->grid = (int)grid;
   c->smem = smem;
-  if (kt != nullptr)
+  if (kc != nullptr)
+    kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (kt != nullptr)
     kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
   else
     k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
@@ -386,6 +402,7 @@ int mb2_destroy(mb2_ctx* c) {
   cudaFree(c->lo);
   cudaFree(c->hi);
   cudaFree(c->cheb_x);
+  cudaFree(c->cheb_vfrag);
   cudaFree(c->grw_tab);
   cudaFree(c->pen_type);
   cudaFree(c->pen_G);
@@ -459,8 +476,9 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
   if (cost < MB2_COST_ROSEN || cost > MB2_COST_CHEBYSHEV_MMA) return fail(MB2_EINVAL, "unknown cost id %d", cost);
   if (cost == MB2_COST_ZIMMERMANN && c->dim != 2) return fail(MB2_EINVAL, "zimmermann requires dim == 2");
-  if (cost == MB2_COST_CHEBYSHEV_MMA) return fail(MB2_EINVAL, "chebyshev DMMA cost is not available in this build");
-  if (cost == MB2_COST_CHEBYSHEV) {
+  if (cost == MB2_COST_CHEBYSHEV_MMA && c->dim > kChebMaxDim)
+    return fail(MB2_EINVAL, "chebyshev DMMA cost supports at most %d coefficients", kChebMaxDim);
+  if (cost == MB2_COST_CHEBYSHEV || cost == MB2_COST_CHEBYSHEV_MMA) {
     if (!params || nparams < 3) return fail(MB2_EINVAL, "chebyshev params = {M, order, target[order+1]}");
     const int M = (int)params[0], order = (int)params[1];
     if (M < 2 || order < 0 || nparams != order + 3) return fail(MB2_EINVAL, "bad chebyshev params (M=%d order=%d)", M, order);
@@ -492,6 +510,32 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
     c->cp.cheb_x = c->cheb_x;
     c->cp.cheb_tp = tp;
     c->cp.cheb_tm = tm;
+    if (cost == MB2_COST_CHEBYSHEV_MMA) {
+      // Vandermonde fragments in mma.m8n8k4 B-operand order (see de_cheb_mma.cuh)
+      const int n = c->dim - 1;  // order of the trial polynomial
+      const int KS = n <= 4 ? 1 : (n <= 8 ? 2 : 4);
+      const int ntiles = (M + 7) / 8;
+      std::vector<double> vf((size_t)ntiles * KS * 32, 0.0);
+      for (int t = 0; t < ntiles; ++t)
+        for (int s = 0; s < KS; ++s)
+          for (int lane = 0; lane < 32; ++lane) {
+            const int k = 4 * s + (lane & 3), i = 8 * t + (lane >> 2);
+            double v = 0.0;
+            if (k < n && i < M) {
+              volatile double pw = 1.0;
+              for (int e = 0; e < n - k; ++e) pw = pw * xs[i];
+              v = pw;
+            }
+            vf[((size_t)t * KS + s) * 32 + lane] = v;
+          }
+      cudaFree(c->cheb_vfrag);
+      c->cheb_vfrag = nullptr;
+      CUDA_TRY(cudaMalloc(&c->cheb_vfrag, sizeof(double) * vf.size()));
+      CUDA_TRY(cudaMemcpy(c->cheb_vfrag, vf.data(), sizeof(double) * vf.size(), cudaMemcpyHostToDevice));
+      c->cp.cheb_vfrag = c->cheb_vfrag;
+      c->cp.cheb_ntiles = ntiles;
+      c->cheb_ks = KS;
+    }
   }
   if (cost == MB2_COST_GRIEWANGK && c->grw_tab == nullptr) {
     // {sqrt(i+1.0), 1/sqrt(i+1.0)}: glibc sqrt and the host divide are correctly rounded

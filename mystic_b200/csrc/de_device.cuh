@@ -158,6 +158,10 @@ struct CostParams {
   int cheb_M;             // number of points in [-1, 1]
   const double* cheb_x;   // [M] the reference's accumulated abscissae (x=-1; x+=dx)
   double cheb_tp, cheb_tm;  // polyeval(target, +1.2), polyeval(target, -1.2)
+  // DMMA path: Vandermonde fragments vfrag[(tile*KS + s)*32 + lane] = x_i^(n-k), k = 4s + lane%4,
+  // i = 8*tile + lane/4 (0 for k >= n or i >= M), ntiles = ceil(M/8)
+  const double* cheb_vfrag;
+  int cheb_ntiles;
   // griewangk (models/storn.py:135-139): per-dimension {sqrt(i+1), RN(1/sqrt(i+1))}, both
   // correctly rounded on the host, so the kernel needs neither a square root nor a divide
   const double2* grw_tab;

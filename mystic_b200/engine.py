@@ -183,12 +183,12 @@ class DeviceEngine(object):
         return int(lib.mb2_launch_count(self._ctx))
 
 
-def evaluate_rows(cost, X, extra_args=(), bounds=None, penalty=None):
+def evaluate_rows(cost, X, extra_args=(), bounds=None, penalty=None, tensor_cores=False):
     """cost(x) for every row of X [n, D], on the device (mb2_eval_cost)."""
     X = np.ascontiguousarray(X, dtype=np.float64)
     eng = DeviceEngine(X.shape[0], X.shape[1])
     try:
-        eng.set_cost(cost.cost_id, cost.params(tuple(extra_args)))
+        eng.set_cost(cost.device_id(tensor_cores, X.shape[1]), cost.params(tuple(extra_args)))
         if bounds is not None:
             eng.set_bounds(*bounds)
         if penalty is not None:

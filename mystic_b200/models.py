@@ -32,6 +32,14 @@ class DeviceCost(object):
         self.order = order
         self.__doc__ = doc
 
+    def device_id(self, tensor_cores=False, dim=None):
+        """cost id handed to mb2_set_cost.  The Chebyshev costs have a second implementation that
+        runs the coefficient x abscissa contraction on the FP64 tensor cores (DMMA); it is not
+        bit-faithful to the reference's Horner evaluation, so it is opt-in (tensor_cores=True)."""
+        if tensor_cores and self.cost_id == COST_CHEBYSHEV and (dim is None or dim <= 17):
+            return COST_CHEBYSHEV_MMA
+        return self.cost_id
+
     def params(self, extra_args=()):
         """numeric parameter vector handed to mb2_set_cost"""
         if self.cost_id in (COST_CHEBYSHEV, COST_CHEBYSHEV_MMA):
@@ -41,12 +49,12 @@ class DeviceCost(object):
             raise TypeError('%s() takes no ExtraArgs' % self.__name__)
         return []
 
-    def __call__(self, x, *extra_args):
+    def __call__(self, x, *extra_args, **kwds):
         """Evaluate on the device (one row, or a [n, D] batch) through mb2_eval_cost."""
         from .engine import evaluate_rows
         import numpy as np
         arr = np.asarray(x, dtype=np.float64)
-        out = evaluate_rows(self, np.atleast_2d(arr), extra_args)
+        out = evaluate_rows(self, np.atleast_2d(arr), extra_args, tensor_cores=kwds.get('tensor_cores', False))
         return float(out[0]) if arr.ndim == 1 else out
 
     def __repr__(self):

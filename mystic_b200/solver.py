@@ -27,6 +27,8 @@ Engine-specific constructor keywords (not in the reference):
     keep_trials=bool keep every trial vector / energy of the last generation on the device
                      (`trialSolution`, `trialEnergy`)
     distributed=bool shard the population by candidate over torch.distributed ranks, one GPU each
+    tensor_cores=bool evaluate the Chebyshev fitting costs on the FP64 tensor cores (DMMA) instead of the
+                     bit-faithful Horner path (default False)
 """
 import random
 from collections.abc import Callable as _Callable
@@ -91,6 +93,7 @@ class DifferentialEvolutionSolver2(object):
         self._device = kwds.pop('device', None)
         self._keep_trials = bool(kwds.pop('keep_trials', False))
         self._distributed = bool(kwds.pop('distributed', False))
+        self._tensor_cores = bool(kwds.pop('tensor_cores', False))
         engine = kwds.pop('engine', None)
         if engine is not None:
             self._engine_factory = engine
@@ -594,7 +597,7 @@ class DifferentialEvolutionSolver2(object):
         if mode != BOUNDS_NONE and not fresh and self.generations:
             self._reclip_population(lo, hi)
         eng.set_bounds(mode, lo, hi)
-        eng.set_cost(dev.cost_id, dev.params(args))
+        eng.set_cost(dev.device_id(self._tensor_cores, self.nDim), dev.params(args))
         if self._penalty is _no_penalty:
             eng.set_penalty()
         else:

@@ -296,3 +296,60 @@ def test_table_divide_is_ieee_exact():
     for span in (1e-3, 1.0, 400.0, 1e6, 1e150):
         assert eng.selftest_division(1 << 24, seed=int(span * 7) + 3, span=span) == 0, span
     eng.close()
+
+
+@pytest.mark.parametrize('name,extra,D,span', [('chebyshev8cost', (61,), 9, 100.), ('chebyshev8cost', (4096,), 9, 3.),
+                                               ('chebyshev16cost', (333,), 17, 2.), ('chebyshev4cost', (100,), 5, 10.),
+                                               ('chebyshev2cost', (61,), 3, 5.), ('chebyshev6cost', (77,), 7, 5.)])
+def test_chebyshev_dmma_cost_matches_oracle(name, extra, D, span):
+    """FP64 tensor-core (DMMA) evaluation of the Chebyshev cost against the oracle's Horner evaluation
+    on random populations; reports how many abscissae sit within 1e-9 of the |px| = 1 threshold"""
+    from mystic_b200 import models
+    rng = np.random.default_rng(11)
+    X = rng.uniform(-span, span, size=(1000, D))
+    X[0] = models.CHEBYSHEV_TARGETS[D - 1]   # the optimum itself: px equioscillates at +-1
+    got = getattr(models, name)(X, *extra, tensor_cores=True)
+    want = orc.make_cost(name, extra)(X)
+    xs = orc.chebyshev_points(extra[0])
+    px = np.stack([orc._polyeval(X, x) for x in xs], axis=1)
+    near = int((np.abs(np.abs(px[1:]) - 1.0) < 1e-9).sum())
+    print('%s M=%d: %d of %d points within 1e-9 of the threshold (random rows)' % (name, extra[0], near, px[1:].size))
+    np.testing.assert_allclose(got[1:], want[1:], rtol=1e-12, atol=0)
+    assert abs(got[0] - want[0]) <= 4.0 * extra[0]   # at the optimum every point may flip by (1-(-1))^2 = 4
+
+
+def test_chebyshev_dmma_trajectory_matches_oracle():
+    """whole generations through de_step_cheb_mma_kernel (Philox draws, all crossover kinds)"""
+    from mystic_b200 import models
+    from mystic_b200.engine import DeviceEngine
+    for strat, CR, F, M, NP, bounds in (('Best1Exp', 1.0, 0.9, 128, 200, None), ('Best1Bin', 0.9, 0.8, 61, 130, (-50., 50.)),
+                                        ('Rand2Exp', 0.8, 0.7, 100, 77, None), ('RandToBest1Bin', 0.9, 0.8, 64, 64, None)):
+        D, seed = 9, 0xCEB + NP
+        lo, hi = np.full(D, -100.), np.full(D, 100.)
+        eng = DeviceEngine(NP, D, keep_trials=True)
+        eng.set_cost(models.COST_CHEBYSHEV_MMA, models.chebyshev8cost.params((M,)))
+        mode = orc.BOUNDS_NONE
+        if bounds:
+            mode = orc.BOUNDS_CLAMP
+            eng.set_bounds(mode, np.full(D, bounds[0]), np.full(D, bounds[1]))
+        eng.set_strategy(orc.STRATEGIES[strat][0], F, CR)
+        eng.set_rng_philox(seed)
+        eng.init_population(seed, lo, hi)
+        st = orc.DEState(orc.philox_init_population(seed, NP, lo, hi), None if not bounds else np.full(D, bounds[0]),
+                         None if not bounds else np.full(D, bounds[1]), mode)
+        cost = orc.make_cost('chebyshev8cost', (M,))
+        for g in range(6):
+            if g == 0:
+                eng.eval_initial()
+                orc.step0(st, cost)
+            else:
+                eng.step()
+                orc.step(st, strat, CR, F, cost, philox=dict(seed=seed, offset=0))
+            best_e, best_idx, n_inf, n_acc, gen, best_x = eng.read_result()
+            trial, trial_e = eng.trials()
+            G.assert_bits_equal(trial, st.trialSolution, '%s gen %d trial' % (strat, g))
+            np.testing.assert_allclose(trial_e, st.trialEnergy, rtol=1e-12)
+            G.assert_bits_equal(eng.population(), st.population, '%s gen %d population' % (strat, g))
+            G.assert_bits_equal(best_x, st.bestSolution, '%s gen %d best' % (strat, g))
+            assert n_acc == int(st.accepted.sum())
+        eng.close()
