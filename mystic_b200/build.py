@@ -14,7 +14,7 @@ LIBDIR = os.path.join(HERE, '_lib')
 LIBPATH = os.path.join(LIBDIR, 'libmystic_b200.so')
 
 SOURCES = ['de_abi.cu']
-HEADERS = ['philox.cuh', 'de_device.cuh', 'de_kernels.cuh', 'de_tma.cuh', os.path.join('..', '..', 'include', 'mystic_b200.h')]
+HEADERS = ['philox.cuh', 'de_device.cuh', 'de_kernels.cuh', 'de_tma.cuh', 'de_cheb_mma.cuh', 'de_small.cuh', os.path.join('..', '..', 'include', 'mystic_b200.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',

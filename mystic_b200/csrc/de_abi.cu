@@ -14,6 +14,7 @@
 #include "de_kernels.cuh"
 #include "de_tma.cuh"
 #include "de_cheb_mma.cuh"
+#include "de_small.cuh"
 
 using namespace mb2;
 
@@ -246,12 +247,26 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   ChebKernel kc = nullptr;
   if (cheb_mma)
     kc = c->cheb_ks == 1 ? de_step_cheb_mma_kernel<1> : (c->cheb_ks == 2 ? de_step_cheb_mma_kernel<2> : de_step_cheb_mma_kernel<4>);
+  // short rows: one thread per candidate (all modes, so energies of a context share one summation order)
+  ChebKernel ks = nullptr;
+  int small_max = env_int("MB2_SMALL_MAXD", kSmallMaxDim);
+  if (small_max > kSmallMaxDim) small_max = kSmallMaxDim;
+  if (!cheb_mma && c->dim <= small_max) {
+    switch (c->cost) {
+      case MB2_COST_ROSEN: ks = de_step_small_kernel<COST_ROSEN>; break;
+      case MB2_COST_CORANA: ks = de_step_small_kernel<COST_CORANA>; break;
+      case MB2_COST_GRIEWANGK: ks = de_step_small_kernel<COST_GRIEWANGK>; break;
+      case MB2_COST_ZIMMERMANN: ks = de_step_small_kernel<COST_ZIMMERMANN>; break;
+      case MB2_COST_CHEBYSHEV: ks = de_step_small_kernel<COST_CHEBYSHEV>; break;
+    }
+  }
+  s = c->sinfo;  // the thread-per-candidate kernels take the strategy at run time in every mode
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 &&
-      !cheb_mma && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
+      !cheb_mma && ks == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
 
   int wpc, smem;
@@ -263,6 +278,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     smem = (int)(sizeof(double) * (size_t)kChebWarps * (kChebBatch * c->dim + kChebBatch));
     CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc, wpc * 32, smem));
+  } else if (ks != nullptr) {
+    wpc = kSmallWarps;
+    rows_per_cta = kSmallWarps * 32;
+    smem = (int)(sizeof(double) * (size_t)kSmallWarps * 32 * (c->dim | 1));
+    CUDA_TRY(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, wpc * 32, smem));
   } else if (kt != nullptr) {
     wpc = tg * tw;
     rows_per_cta = tg;
@@ -325,6 +346,8 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->smem = smem;
   if (kc != nullptr)
     kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (ks != nullptr)
+    ks<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (kt != nullptr)
     kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
   else

@@ -172,11 +172,13 @@ struct CostParams {
 // instead of the ~28 of the generic divide.  Falls back to the IEEE divide for non-finite or
 // tiny/huge operands where the residuals could over/underflow.
 __device__ __forceinline__ double div_by_table(double c, double s, double r) {
-  const double a = fabs(c);
-  if (!(a > 1e-280 && a < 1e280)) return c / s;
   const double q0 = __dmul_rn(c, r);
   const double q1 = __fma_rn(__fma_rn(-q0, s, c), r, q0);
-  return __fma_rn(__fma_rn(-q1, s, c), r, q1);
+  const double q2 = __fma_rn(__fma_rn(-q1, s, c), r, q1);
+  // |c| near the overflow threshold (residuals overflow -> NaN), infinities and NaN take the IEEE
+  // divide; s >= 1, so the quotient itself never overflows for finite c
+  if (!(fabs(c) < 1e300)) return c / s;
+  return q2;
 }
 
 enum : int { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4 };
@@ -253,15 +255,28 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
       sa[m] = 0.0;
       pa[m] = 1.0;
     }
-    for (int i0 = g.tig; i0 < D; i0 += 256) {
+    if ((D & 255) == 0) {  // whole blocks of 256 virtual threads: no per-element guard
+      for (int i0 = g.tig; i0 < D; i0 += 256) {
 #pragma unroll
-      for (int m = 0; m < NA; ++m) {
-        const int i = i0 + m * NT;
-        if (i < D) {
+        for (int m = 0; m < NA; ++m) {
+          const int i = i0 + m * NT;
           const double c = xs[i];
           sa[m] = dadd(sa[m], dmul(c, c));
           const double2 t = __ldg(cp.grw_tab + i);  // {sqrt(i+1), 1/sqrt(i+1)}
           pa[m] = dmul(pa[m], cos(div_by_table(c, t.x, t.y)));
+        }
+      }
+    } else {
+      for (int i0 = g.tig; i0 < D; i0 += 256) {
+#pragma unroll
+        for (int m = 0; m < NA; ++m) {
+          const int i = i0 + m * NT;
+          if (i < D) {
+            const double c = xs[i];
+            sa[m] = dadd(sa[m], dmul(c, c));
+            const double2 t = __ldg(cp.grw_tab + i);
+            pa[m] = dmul(pa[m], cos(div_by_table(c, t.x, t.y)));
+          }
         }
       }
     }

@@ -1,0 +1,414 @@
+// Thread-per-candidate generation kernel for short rows (D <= 128).
+//
+// With a warp (or several) per row, a 64-dimensional candidate (512 B) costs ~800 warp
+// instructions of mostly per-row overhead; here a warp owns a batch of 32 consecutive candidates:
+//   A  the 32 parent rows (one contiguous 32*8*D-byte block) are loaded cooperatively, coalesced,
+//      into a padded shared-memory tile (odd row stride: conflict-free column access);
+//   B  every lane turns its own row into the trial vector in place: draws (replayed or Philox),
+//      crossover window / mask, mutation from the donors' global rows (only the crossed
+//      dimensions are read), bounds;
+//   C  every lane evaluates cost and penalty of its row SEQUENTIALLY, in the reference's own
+//      summation order (rosen: numpy's pairwise sum; griewangk, chebyshev, penalties: left to
+//      right), so energies are bit-identical to the reference except for libm differences;
+//   D  greedy selection; rejected rows get their crossed dimensions back from the parent;
+//   E  the 32 next-generation rows leave cooperatively, coalesced.
+// The kernel also serves generation 0 and mb2_eval_cost for these row lengths, so energies within
+// one context always come from the same code.
+#pragma once
+#include "de_kernels.cuh"
+
+namespace mb2 {
+
+constexpr int kSmallMaxDim = 128;
+constexpr int kSmallWarps = 4;
+
+// numpy.sum of n <= 128 doubles (pairwise_sum_DOUBLE: 8 running sums, then the tail)
+template <typename F>
+__device__ __forceinline__ double np_sum_le128(int n, F term) {
+  if (n < 8) {
+    double res = 0.0;
+    for (int i = 0; i < n; ++i) res = dadd(res, term(i));
+    return res;
+  }
+  double r[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r[j] = term(j);
+  int i = 8;
+  for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = dadd(r[j], term(i + j));
+  }
+  double res = dadd(dadd(dadd(r[0], r[1]), dadd(r[2], r[3])), dadd(dadd(r[4], r[5]), dadd(r[6], r[7])));
+  for (; i < n; ++i) res = dadd(res, term(i));
+  return res;
+}
+
+// cost of one row held by one thread, reference summation order
+template <int COST>
+__device__ __forceinline__ double thread_cost(const double* x, int D, const CostParams& cp) {
+  if (COST == COST_ROSEN) {
+    // dejong.py:98-101, numpy.sum order
+    if (D < 2) return 0.0;
+    return np_sum_le128(D - 1, [&](int i) {
+      const double a = x[i], b = x[i + 1];
+      const double t = dsub(b, dmul(a, a));
+      const double u = dsub(1.0, a);
+      return dadd(dmul(100.0, dmul(t, t)), dmul(u, u));
+    });
+  } else if (COST == COST_CORANA) {
+    const double d[4] = {1., 1000., 10., 100.};
+    double v[4] = {0., 0., 0., 0.};
+    if (D >= 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = x[j];
+    } else {
+      if (D >= 1) v[0] = x[0];
+      if (D >= 2) v[2] = x[1];
+      if (D >= 3) v[3] = x[2];
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double xj = v[j];
+      const double sg = (xj > 0.0) ? 1.0 : ((xj < 0.0) ? -1.0 : 0.0);
+      const double zj = dmul(dmul(floor(dadd(fabs(xj / 0.2), 0.49999)), sg), 0.2);
+      double term;
+      if (fabs(dsub(xj, zj)) < 0.05) {
+        const double sz = (zj > 0.0) ? 1.0 : ((zj < 0.0) ? -1.0 : 0.0);
+        const double w = dsub(zj, dmul(0.05, sz));
+        term = dmul(dmul(0.15, dmul(w, w)), d[j]);
+      } else {
+        term = dmul(dmul(d[j], xj), xj);
+      }
+      r = dadd(r, term);
+    }
+    return r;
+  } else if (COST == COST_GRIEWANGK) {
+    // storn.py:135-139, left to right
+    double s = 0.0, p = 1.0;
+    for (int i = 0; i < D; ++i) s = dadd(s, dmul(x[i], x[i]));
+    for (int i = 0; i < D; ++i) {
+      const double2 t = __ldg(cp.grw_tab + i);
+      p = dmul(p, cos(div_by_table(x[i], t.x, t.y)));
+    }
+    return dadd(dsub(s / 4000.0, p), 1.0);
+  } else if (COST == COST_ZIMMERMANN) {
+    const double x0 = x[0], x1 = (D > 1) ? x[1] : 0.0;
+    const double f8 = dsub(dsub(9.0, x0), x1);
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    if (x0 < 0.0) c0 = dmul(-100.0, x0);
+    if (x1 < 0.0) c1 = dmul(-100.0, x1);
+    const double a = dsub(x0, 3.0), b = dsub(x1, 2.0);
+    const double xx = dadd(dmul(a, a), dmul(b, b));
+    if (xx > 16.0) c2 = dmul(100.0, dsub(xx, 16.0));
+    const double pr = dmul(x0, x1);
+    if (pr > 14.0) c3 = dmul(100.0, dsub(pr, 14.0));
+    double m = f8;
+    if (c0 > m) m = c0;
+    if (c1 > m) m = c1;
+    if (c2 > m) m = c2;
+    if (c3 > m) m = c3;
+    return m;
+  } else {
+    // _model_helper.py:16-33, sequential over the abscissae
+    double result = 0.0;
+    const int M = cp.cheb_M;
+    for (int i = 0; i < M; ++i) {
+      const double px = horner(x, D, __ldg(cp.cheb_x + i));
+      if (px < -1.0 || px > 1.0) {
+        const double u = dsub(1.0, px);
+        result = dadd(result, dmul(u, u));
+      }
+    }
+    double px = dsub(horner(x, D, 1.2), cp.cheb_tp);
+    if (px < 0.0) result = dadd(result, dmul(px, px));
+    px = dsub(horner(x, D, -1.2), cp.cheb_tm);
+    if (px < 0.0) result = dadd(result, dmul(px, px));
+    return result;
+  }
+}
+
+__device__ __forceinline__ double thread_penalty(const double* x, int D, const PenaltyParams& pp) {
+  double pen = 0.0;
+  for (int t = 0; t < pp.n; ++t) {
+    const double* g = pp.G + (int64_t)t * D;
+    double acc = 0.0;
+    for (int j = 0; j < D; ++j) acc = dadd(acc, dmul(__ldg(g + j), x[j]));
+    const double pf = dsub(acc, __ldg(pp.h + t));
+    const double k = __ldg(pp.kscale + t);
+    const int ty = __ldg(pp.ptype + t);
+    const double mpos = (pf > 0.0) ? pf : 0.0;
+    double v;
+    if (ty == 0) v = dmul(k, dmul(pf, pf));
+    else if (ty == 1) v = dmul(k, fabs(pf));
+    else if (ty == 2) v = dmul(2.0 * k, dmul(mpos, mpos));
+    else v = dmul(2.0 * k, fabs(mpos));
+    pen = dadd(v, pen);
+  }
+  return pen;
+}
+
+template <int COST>
+__global__ void __launch_bounds__(kSmallWarps * 32)
+    de_step_small_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double sh_e[kSmallWarps];
+  __shared__ int64_t sh_i[kSmallWarps];
+  __shared__ unsigned long long sh_ninf[kSmallWarps], sh_nacc[kSmallWarps];
+
+  const int D = P.dim;
+  const int Dp = D | 1;  // odd row stride: lanes reading column i of 32 rows hit distinct banks
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  double* tile = smem + (size_t)warp * 32 * Dp;
+  double* row = tile + lane * Dp;
+
+  double w_best_e = CUDART_INF;
+  int64_t w_best_idx = INT64_MAX;
+  unsigned long long w_ninf = 0, w_nacc = 0;
+  const bool uni_b = P.bounds_uniform != 0;
+
+  const int64_t nbatch = (P.np + 31) / 32;
+  const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
+  const int64_t nw = (int64_t)gridDim.x * wpc;
+  for (int64_t b = gw; b < nbatch; b += nw) {
+    const int64_t c0 = b * 32;
+    const int nrows = (int)((P.np - c0 < 32) ? (P.np - c0) : 32);
+    const int64_t c = c0 + lane;
+    const bool live = lane < nrows;
+
+    // ---- A: coalesced load of the batch's parent rows (contiguous in memory)
+    {
+      const double* __restrict__ src = P.pop_cur + c0 * D;
+      const int total = nrows * D;
+      int r = 0, col = lane;
+      while (col >= D) {
+        col -= D;
+        ++r;
+      }
+      for (int idx = lane; idx < total; idx += 32) {
+        tile[r * Dp + col] = ld_stream1(src + idx);
+        col += 32;
+        while (col >= D) {
+          col -= D;
+          ++r;
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- B: trial vector in place
+    bool oob = false, clamp_touched = false;
+    int nstart = 0, L = 0;
+    if (live) {
+      if (P.mode == MODE_STEP) {
+        int64_t r[5] = {0, 0, 0, 0, 0};
+        const uint32_t cand_g = (uint32_t)(P.global_offset + c);
+        if (P.replay) {
+          for (int j = 0; j < ndonors; ++j) r[j] = __ldg(P.r_donors + c * 5 + j);
+          nstart = __ldg(P.r_nstart + c);
+        } else {
+          switch (ndonors) {
+            case 2: draw_donors<2>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
+            case 3: draw_donors<3>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
+            case 4: draw_donors<4>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
+            default: draw_donors<5>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
+          }
+        }
+        const double* u = P.r_uni + c * (int64_t)(D + 1);
+        const double* __restrict__ q0 = P.pop_cur + r[0] * D;
+        const double* __restrict__ q1 = P.pop_cur + r[1] * D;
+        const double* __restrict__ q2 = P.pop_cur + r[2] * D;
+        const double* __restrict__ q3 = P.pop_cur + r[3] * D;
+        const double* __restrict__ q4 = P.pop_cur + r[4] * D;
+        auto mutate_dim = [&](int i) {
+          double p[5];
+          p[0] = ld_stream1(q0 + i);
+          p[1] = ld_stream1(q1 + i);
+          p[2] = ndonors > 2 ? ld_stream1(q2 + i) : 0.0;
+          p[3] = ndonors > 3 ? ld_stream1(q3 + i) : 0.0;
+          p[4] = ndonors > 4 ? ld_stream1(q4 + i) : 0.0;
+          const double bst = __ldg(P.best_x + i);
+          const double x = row[i];
+          double v;
+          switch (base) {
+            case BASE_BEST1: v = mutant<BASE_BEST1>(x, bst, p, P.F); break;
+            case BASE_RAND1: v = mutant<BASE_RAND1>(x, bst, p, P.F); break;
+            case BASE_RANDTOBEST1: v = mutant<BASE_RANDTOBEST1>(x, bst, p, P.F); break;
+            case BASE_BEST2: v = mutant<BASE_BEST2>(x, bst, p, P.F); break;
+            default: v = mutant<BASE_RAND2>(x, bst, p, P.F); break;
+          }
+          row[i] = v;
+        };
+        if (xover == XOVER_BIN) {
+          // strategy.py:77-85
+          u32x4 w = {0, 0, 0, 0};
+          for (int i = 0; i < D; ++i) {
+            bool hit;
+            if (P.replay) {
+              hit = __ldg(u + i) < P.CR;
+            } else {
+              if ((i & 3) == 0) w = philox4x32_10((uint32_t)(i >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+              const uint32_t word = (i & 3) == 0 ? w.x : ((i & 3) == 1 ? w.y : ((i & 3) == 2 ? w.z : w.w));
+              hit = (uint64_t)word < P.thr;
+            }
+            if (hit || i == nstart) mutate_dim(i);
+          }
+          L = D;  // every dimension may have changed
+        } else {
+          // strategy.py:48-56: L leading successes, capped at D
+          u32x4 w = {0, 0, 0, 0};
+          while (L < D) {
+            bool ok;
+            if (P.replay) {
+              ok = __ldg(u + L) < P.CR;
+            } else {
+              if ((L & 3) == 0) w = philox4x32_10((uint32_t)(L >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+              const uint32_t word = (L & 3) == 0 ? w.x : ((L & 3) == 1 ? w.y : ((L & 3) == 2 ? w.z : w.w));
+              ok = (uint64_t)word < P.thr;
+            }
+            if (!ok) break;
+            ++L;
+          }
+          int i = nstart;
+          for (int j = 0; j < L; ++j) {
+            mutate_dim(i);
+            if (++i == D) i = 0;
+          }
+        }
+        if (P.bounds_mode != BOUNDS_NONE) {
+          for (int i = 0; i < D; ++i) {
+            const double l = uni_b ? P.lo_s : __ldg(P.lo + i);
+            const double h = uni_b ? P.hi_s : __ldg(P.hi + i);
+            double x = row[i];
+            if (P.bounds_mode == BOUNDS_CLAMP) {
+              const double x_in = x;
+              x = (x > l) ? x : l;  // python max(lo, x); min(hi, x)
+              x = (x < h) ? x : h;
+              clamp_touched |= __double_as_longlong(x) != __double_as_longlong(x_in);
+              row[i] = x;
+            } else {
+              oob |= (x < l) || (x > h);
+            }
+          }
+        }
+      } else if (P.bounds_mode != BOUNDS_NONE) {
+        for (int i = 0; i < D; ++i) {
+          const double l = uni_b ? P.lo_s : __ldg(P.lo + i);
+          const double h = uni_b ? P.hi_s : __ldg(P.hi + i);
+          double x = row[i];
+          if (P.mode == MODE_GEN0) {
+            x = fmin(fmax(x, l), h);  // numpy clip (differential_evolution.py:516-520)
+            row[i] = x;
+          }
+          oob |= (x < l) || (x > h);
+        }
+      }
+    }
+
+    // ---- C: energy = (inf if out of range else cost) + penalty, sequential per thread
+    double E = CUDART_INF;
+    bool acc = false;
+    if (live) {
+      if (!oob) E = thread_cost<COST>(row, D, P.cost);
+      E = dadd(E, thread_penalty(row, D, P.pen));
+      if (P.cap_trial != nullptr && P.mode != MODE_EVAL) {
+        for (int i = 0; i < D; ++i) P.cap_trial[c * D + i] = row[i];
+        P.cap_energy[c] = E;
+      }
+      if (P.mode == MODE_EVAL) {
+        P.e_next[c] = E;
+      } else {
+        // ---- D: selection (differential_evolution.py:603-613)
+        const double e_old = (P.mode == MODE_GEN0) ? CUDART_INF : __ldg(P.e_cur + c);
+        acc = E < e_old;
+        P.e_next[c] = acc ? E : e_old;
+        if (acc) {
+          ++w_nacc;
+          if (E < w_best_e) {
+            w_best_e = E;
+            w_best_idx = c;
+          }
+        }
+        if (isinf(E)) ++w_ninf;
+        if (!acc && P.mode == MODE_STEP) {
+          // rejected: the crossed dimensions get the parent's values back; if the clamp changed
+          // anything (normally only crossed dimensions: the population is inside the bounds since
+          // generation 0) the whole row is restored
+          const double* __restrict__ prow = P.pop_cur + c * D;
+          if (clamp_touched || L == D) {
+            for (int i = 0; i < D; ++i) row[i] = ld_stream1(prow + i);
+          } else {
+            int i = nstart;
+            for (int j = 0; j < L; ++j) {
+              row[i] = ld_stream1(prow + i);
+              if (++i == D) i = 0;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- E: coalesced store of the batch's next-generation rows
+    if (P.mode != MODE_EVAL) {
+      double* __restrict__ dst = P.pop_next + c0 * D;
+      const int total = nrows * D;
+      int r = 0, col = lane;
+      while (col >= D) {
+        col -= D;
+        ++r;
+      }
+      for (int idx = lane; idx < total; idx += 32) {
+        dst[idx] = tile[r * Dp + col];
+        col += 32;
+        while (col >= D) {
+          col -= D;
+          ++r;
+        }
+      }
+    }
+    __syncwarp();  // the tile is reused by the next batch
+  }
+
+  if (P.mode == MODE_EVAL) return;
+
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oe = __shfl_xor_sync(0xffffffffu, w_best_e, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, w_best_idx, o);
+    if (oe < w_best_e || (oe == w_best_e && oi < w_best_idx)) {
+      w_best_e = oe;
+      w_best_idx = oi;
+    }
+    w_ninf += __shfl_xor_sync(0xffffffffu, w_ninf, o);
+    w_nacc += __shfl_xor_sync(0xffffffffu, w_nacc, o);
+  }
+  if (lane == 0) {
+    sh_e[warp] = w_best_e;
+    sh_i[warp] = w_best_idx;
+    sh_ninf[warp] = w_ninf;
+    sh_nacc[warp] = w_nacc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double be = sh_e[0];
+    int64_t bi = sh_i[0];
+    unsigned long long ni = sh_ninf[0], na = sh_nacc[0];
+    for (int w = 1; w < wpc; ++w) {
+      if (sh_e[w] < be || (sh_e[w] == be && sh_i[w] < bi)) {
+        be = sh_e[w];
+        bi = sh_i[w];
+      }
+      ni += sh_ninf[w];
+      na += sh_nacc[w];
+    }
+    P.part_e[blockIdx.x] = be;
+    P.part_idx[blockIdx.x] = bi;
+    P.part_ninf[blockIdx.x] = ni;
+    P.part_nacc[blockIdx.x] = na;
+  }
+}
+
+}  // namespace mb2

@@ -13,6 +13,8 @@
 // Semantics are those of de_step_kernel<BASE_BEST1, XOVER_BIN, COST> (de_kernels.cuh); the same
 // device functions produce the numbers, so both kernels agree bit for bit.
 #pragma once
+#include <type_traits>
+
 #include "de_kernels.cuh"
 
 namespace mb2 {
@@ -155,55 +157,61 @@ __global__ void __launch_bounds__(MAXT, 1)
     //      dims 4q..4q+3, i.e. chunks 2q and 2q+1, so the thread pair (2m, 2m+1) shares blocks qA and
     //      qB; the even thread computes qA, the odd thread qB, and they swap halves by shuffle.
     bool oob = false;
-#pragma unroll 2
-    for (int base = 0; base < npairs; base += 2 * gthreads) {
-      const int pA = base + tig, pB = base + gthreads + tig;
-      bool cx[4];  // crossover decisions for dims 2pA, 2pA+1, 2pB, 2pB+1
-      if (P.replay) {
-        const double* u = P.r_uni + c * (int64_t)(D + 1);
-        cx[0] = (pA < npairs) && ((2 * pA == nstart) || (__ldg(u + 2 * pA) < P.CR));
-        cx[1] = (pA < npairs) && ((2 * pA + 1 == nstart) || (__ldg(u + 2 * pA + 1) < P.CR));
-        cx[2] = (pB < npairs) && ((2 * pB == nstart) || (__ldg(u + 2 * pB) < P.CR));
-        cx[3] = (pB < npairs) && ((2 * pB + 1 == nstart) || (__ldg(u + 2 * pB + 1) < P.CR));
-      } else {
-        const int q = ((tig & 1) ? pB : pA) >> 1;  // even thread: qA, odd thread: qB
-        const u32x4 w = philox4x32_10((uint32_t)q, cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-        // even thread keeps (x,y) of qA for pA and needs (x,y) of qB from its odd neighbour;
-        // odd thread keeps (z,w) of qB for pB and needs (z,w) of qA from its even neighbour.
-        const uint32_t send0 = (tig & 1) ? w.x : w.z;
-        const uint32_t send1 = (tig & 1) ? w.y : w.w;
-        const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1);
-        const uint32_t got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-        const uint32_t a0 = (tig & 1) ? got0 : w.x, a1 = (tig & 1) ? got1 : w.y;  // words for chunk pA
-        const uint32_t b0 = (tig & 1) ? w.z : got0, b1 = (tig & 1) ? w.w : got1;  // words for chunk pB
-        cx[0] = (pA < npairs) && ((2 * pA == nstart) || ((uint64_t)a0 < P.thr));
-        cx[1] = (pA < npairs) && ((2 * pA + 1 == nstart) || ((uint64_t)a1 < P.thr));
-        cx[2] = (pB < npairs) && ((2 * pB == nstart) || ((uint64_t)b0 < P.thr));
-        cx[3] = (pB < npairs) && ((2 * pB + 1 == nstart) || ((uint64_t)b1 < P.thr));
-      }
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int p = h ? pB : pA;
-        if (p < npairs) {
-          double2 x = s_par[p];
-          const double2 a = s_d0[p], b = s_d1[p], bs = s_b2[p];
-          if (cx[2 * h]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
-          if (cx[2 * h + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
-          if (P.bounds_mode != BOUNDS_NONE) {
-            const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p + 1);
-            const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p + 1);
-            if (P.bounds_mode == BOUNDS_CLAMP) {
-              x.x = (x.x > l0) ? x.x : l0;
-              x.x = (x.x < h0) ? x.x : h0;
-              x.y = (x.y > l1) ? x.y : l1;
-              x.y = (x.y < h1) ? x.y : h1;
-            } else {
-              oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);  // nothing is out of range after a clamp
-            }
-          }
-          s_d0[p] = x;
+    auto trip = [&](int base, auto guard) {
+      constexpr bool GUARD = decltype(guard)::value;
+        const int pA = base + tig, pB = base + gthreads + tig;
+        bool cx[4];  // crossover decisions for dims 2pA, 2pA+1, 2pB, 2pB+1
+        if (P.replay) {
+          const double* u = P.r_uni + c * (int64_t)(D + 1);
+          cx[0] = (!GUARD || pA < npairs) && ((2 * pA == nstart) || (__ldg(u + 2 * pA) < P.CR));
+          cx[1] = (!GUARD || pA < npairs) && ((2 * pA + 1 == nstart) || (__ldg(u + 2 * pA + 1) < P.CR));
+          cx[2] = (!GUARD || pB < npairs) && ((2 * pB == nstart) || (__ldg(u + 2 * pB) < P.CR));
+          cx[3] = (!GUARD || pB < npairs) && ((2 * pB + 1 == nstart) || (__ldg(u + 2 * pB + 1) < P.CR));
+        } else {
+          const int q = ((tig & 1) ? pB : pA) >> 1;  // even thread: qA, odd thread: qB
+          const u32x4 w = philox4x32_10((uint32_t)q, cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+          // even thread keeps (x,y) of qA for pA and needs (x,y) of qB from its odd neighbour;
+          // odd thread keeps (z,w) of qB for pB and needs (z,w) of qA from its even neighbour.
+          const uint32_t send0 = (tig & 1) ? w.x : w.z;
+          const uint32_t send1 = (tig & 1) ? w.y : w.w;
+          const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1);
+          const uint32_t got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
+          const uint32_t a0 = (tig & 1) ? got0 : w.x, a1 = (tig & 1) ? got1 : w.y;  // words for chunk pA
+          const uint32_t b0 = (tig & 1) ? w.z : got0, b1 = (tig & 1) ? w.w : got1;  // words for chunk pB
+          cx[0] = (!GUARD || pA < npairs) && ((2 * pA == nstart) || ((uint64_t)a0 < P.thr));
+          cx[1] = (!GUARD || pA < npairs) && ((2 * pA + 1 == nstart) || ((uint64_t)a1 < P.thr));
+          cx[2] = (!GUARD || pB < npairs) && ((2 * pB == nstart) || ((uint64_t)b0 < P.thr));
+          cx[3] = (!GUARD || pB < npairs) && ((2 * pB + 1 == nstart) || ((uint64_t)b1 < P.thr));
         }
-      }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = h ? pB : pA;
+          if (!GUARD || p < npairs) {
+            double2 x = s_par[p];
+            const double2 a = s_d0[p], b = s_d1[p], bs = s_b2[p];
+            if (cx[2 * h]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
+            if (cx[2 * h + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
+            if (P.bounds_mode != BOUNDS_NONE) {
+              const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p + 1);
+              const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p + 1);
+              if (P.bounds_mode == BOUNDS_CLAMP) {
+                x.x = (x.x > l0) ? x.x : l0;
+                x.x = (x.x < h0) ? x.x : h0;
+                x.y = (x.y > l1) ? x.y : l1;
+                x.y = (x.y < h1) ? x.y : h1;
+              } else {
+                oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);  // nothing is out of range after a clamp
+              }
+            }
+            s_d0[p] = x;
+          }
+        }
+    };
+    if (npairs % (2 * gthreads) == 0) {  // whole trips only: no per-chunk guards
+#pragma unroll 2
+      for (int base = 0; base < npairs; base += 2 * gthreads) trip(base, std::false_type());
+    } else {
+      for (int base = 0; base < npairs; base += 2 * gthreads) trip(base, std::true_type());
     }
     oob = group_any(grp, oob);  // also the barrier that publishes the trial vector to the group
 

@@ -49,8 +49,20 @@ def configure(eng, meta):
     eng.set_strategy(sid, meta['F_eff'], meta['CR_eff'])
 
 
+@pytest.fixture(params=['thread_per_row', 'warp_per_row'])
+def kernel_path(request, monkeypatch):
+    """rows of <= 128 dimensions normally run in the thread-per-candidate kernel (de_small.cuh);
+    MB2_SMALL_MAXD=0 sends them through the warp/group-per-row kernels (de_kernels.cuh, de_tma.cuh)
+    instead, so the recordings exercise every kernel family"""
+    if request.param == 'warp_per_row':
+        monkeypatch.setenv('MB2_SMALL_MAXD', '0')
+    else:
+        monkeypatch.delenv('MB2_SMALL_MAXD', raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize('name', G.names())
-def test_engine_replay_matches_reference_recording(name):
+def test_engine_replay_matches_reference_recording(name, kernel_path):
     """free-running: recorded initial population + recorded draws in; every generation's trial
     vectors / populations / best solution bit-exact, energies <= 1e-12, evaluation counts exact"""
     from mystic_b200.engine import DeviceEngine
@@ -145,7 +157,7 @@ PHILOX_CASES = [
 
 
 @pytest.mark.parametrize('case', PHILOX_CASES, ids=lambda c: '%s-%s-D%d' % (c[2], c[3], c[0]))
-def test_philox_mode_matches_oracle_philox(case):
+def test_philox_mode_matches_oracle_philox(case, kernel_path):
     """production RNG: device-side population init, donors and crossover masks follow the same
     Philox protocol as the oracle, so whole trajectories are comparable bit for bit"""
     from mystic_b200 import models, penalty
@@ -221,7 +233,7 @@ def test_device_cost_callable_known_answers():
     close(models.chebyshev8cost([100, -50, 3, 7, -20, 1, 0.5, -2, 1], 4096), 2014464.4595239898)
 
 
-def test_costs_random_batches_match_oracle():
+def test_costs_random_batches_match_oracle(kernel_path):
     """every device cost on random batches, several row lengths (vector and scalar load paths)"""
     from mystic_b200 import models
     rng = np.random.default_rng(7)
