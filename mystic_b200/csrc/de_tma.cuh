@@ -57,18 +57,19 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-constexpr int kTmaMaxGroups = 16;  // groups per CTA (named barriers 1..15 serve groups of more than one warp)
+constexpr int kTmaMaxGroups = 32;  // groups per CTA (named barriers 1..15 serve groups of more than one warp)
 constexpr int kTmaMaxStages = 4;
 constexpr int kTmaMaxThreads = 1024;
 
-// donors + start index of candidate c (replayed or Philox), uniform across the group
-__device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int64_t (&r)[2], int* nstart) {
+// donors + start index of candidate c (replayed or Philox); collective over the calling warp
+// (the two Philox blocks are computed by two lanes in parallel)
+__device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int lane, int64_t (&r)[2], int* nstart) {
   if (P.replay) {
     r[0] = __ldg(P.r_donors + c * 5 + 0);
     r[1] = __ldg(P.r_donors + c * 5 + 1);
     *nstart = __ldg(P.r_nstart + c);
   } else {
-    draw_donors<2>(P.key0, P.key1, P.generation, (uint32_t)(P.global_offset + c), c, P.np, P.dim, r, nstart);
+    draw_donors_warp<2>(P.key0, P.key1, P.generation, (uint32_t)(P.global_offset + c), c, P.np, P.dim, lane, r, nstart);
   }
 }
 
@@ -112,19 +113,22 @@ __global__ void __launch_bounds__(MAXT, 1)
   // issue the three row loads of candidate c into stage s (group leader only).  The draws are made
   // once, here; the start index travels to the group through shared memory (published by the
   // release of the mbarrier arrive, acquired by the group's wait on the same barrier).
+  // called by the whole leader WARP of the group (tig < 32): collective draws, lane 0 issues
   auto issue = [&](int64_t c, int s) {
     int64_t r[2];
     int nstart;
-    best1_draws(P, c, r, &nstart);
-    s_nstart[group * kTmaMaxStages + s] = nstart;
-    unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
-    mbar_expect_tx(bars + s, 3u * row_bytes);
-    bulk_g2s(buf, P.pop_cur + c * D, row_bytes, bars + s);
-    bulk_g2s(buf + row_stride, P.pop_cur + r[0] * D, row_bytes, bars + s);
-    bulk_g2s(buf + 2 * row_stride, P.pop_cur + r[1] * D, row_bytes, bars + s);
+    best1_draws(P, c, lane, r, &nstart);
+    if (leader) {
+      s_nstart[group * kTmaMaxStages + s] = nstart;
+      unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
+      mbar_expect_tx(bars + s, 3u * row_bytes);
+      bulk_g2s(buf, P.pop_cur + c * D, row_bytes, bars + s);
+      bulk_g2s(buf + row_stride, P.pop_cur + r[0] * D, row_bytes, bars + s);
+      bulk_g2s(buf + 2 * row_stride, P.pop_cur + r[1] * D, row_bytes, bars + s);
+    }
   };
 
-  if (leader) {
+  if (tig < 32) {
     for (int s = 0; s < stages; ++s) {
       const int64_t c = g0 + (int64_t)s * ng;
       if (c < P.np) issue(c, s);
@@ -237,13 +241,16 @@ __global__ void __launch_bounds__(MAXT, 1)
       }
     }
     if (isinf(E)) ++g_ninf;
-    if (leader) {
-      bulk_s2g(P.pop_next + c * D, acc ? (const void*)s_d0 : (const void*)s_par, row_bytes);
-      bulk_commit();
-      P.e_next[c] = acc ? E : e_old;
-      // refill this stage with the row it serves next, once the store has finished reading it
+    if (tig < 32) {
+      if (leader) {
+        bulk_s2g(P.pop_next + c * D, acc ? (const void*)s_d0 : (const void*)s_par, row_bytes);
+        bulk_commit();
+        P.e_next[c] = acc ? E : e_old;
+        bulk_wait_read0();  // the store has finished reading the stage
+      }
+      __syncwarp();
+      // refill this stage with the row it serves next
       const int64_t cn = c + (int64_t)stages * ng;
-      bulk_wait_read0();
       if (cn < P.np) issue(cn, s);
     }
     if (++s == stages) {

@@ -104,6 +104,46 @@ MB2_HD void draw_donors(uint32_t k0, uint32_t k1, uint32_t generation, uint32_t 
   *nstart = (int)mulhi64(r[K], (uint64_t)dim);
 }
 
+#if defined(__CUDACC__)
+// Warp-collective variant of draw_donors (same results): lane b computes Philox block b, the
+// 64-bit words are gathered by shuffle, then every lane resolves ranks to indices redundantly.
+// All 32 lanes of the warp must call it.
+template <int K>
+__device__ __forceinline__ void draw_donors_warp(uint32_t k0, uint32_t k1, uint32_t generation, uint32_t cand_global,
+                                                 int64_t cand_local, int64_t np_local, int dim, int lane,
+                                                 int64_t* donors, int* nstart) {
+  const u32x4 v = philox4x32_10((uint32_t)lane, cand_global, generation, STREAM_DONORS, k0, k1);
+  const uint64_t even = ((uint64_t)v.x << 32) | v.y, odd = ((uint64_t)v.z << 32) | v.w;
+  uint64_t r[6];
+#pragma unroll
+  for (int b = 0; b < (K + 2) / 2; ++b) {
+    r[2 * b] = __shfl_sync(0xffffffffu, even, b);
+    r[2 * b + 1] = __shfl_sync(0xffffffffu, odd, b);
+  }
+  int64_t ex[K + 1];
+  ex[0] = cand_local;
+#pragma unroll
+  for (int i = 1; i <= K; ++i) ex[i] = INT64_MAX;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    int64_t idx = (int64_t)mulhi64(r[i], (uint64_t)(np_local - 1 - i));
+#pragma unroll
+    for (int e = 0; e <= i; ++e) idx += (idx >= ex[e]) ? 1 : 0;
+    donors[i] = idx;
+    int64_t carry = idx;
+#pragma unroll
+    for (int e = 0; e <= i + 1; ++e) {
+      const int64_t cur = ex[e];
+      if (carry < cur) {
+        ex[e] = carry;
+        carry = cur;
+      }
+    }
+  }
+  *nstart = (int)mulhi64(r[K], (uint64_t)dim);
+}
+#endif
+
 MB2_HD uint64_t crossover_threshold(double cr) {
   if (!(cr > 0.0)) return 0ull;
   if (cr >= 1.0) return 4294967296ull;
