@@ -199,8 +199,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
     __syncwarp();
 
     // ---- B: trial vector in place
-    bool oob = false, clamp_touched = false;
+    bool oob = false, binomial = false;
     int nstart = 0, L = 0;
+    double undo[kSmallMaxDim];  // parent values of the crossed dimensions (exponential crossover)
     if (live) {
       if (P.mode == MODE_STEP) {
         int64_t r[5] = {0, 0, 0, 0, 0};
@@ -255,7 +256,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
             }
             if (hit || i == nstart) mutate_dim(i);
           }
-          L = D;  // every dimension may have changed
+          binomial = true;  // every dimension may have changed: a rejected row is re-read
         } else {
           // strategy.py:48-56: L leading successes, capped at D
           u32x4 w = {0, 0, 0, 0};
@@ -271,22 +272,69 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
             if (!ok) break;
             ++L;
           }
-          int i = nstart;
-          for (int j = 0; j < L; ++j) {
-            mutate_dim(i);
-            if (++i == D) i = 0;
+          // window dims i_j = (nstart + j) mod D, four at a time: all donor loads of a chunk are
+          // issued before any is used (the scattered 8-byte loads are the latency of this kernel).
+          // Only crossed dimensions can leave the bounds (parents are inside them since generation
+          // 0), so the clamp / range test runs on the window only.  The parent's values go to an
+          // undo log that restores the row if the trial is rejected.
+          for (int j0 = 0; j0 < L; j0 += 4) {
+            int idx[4];
+            double pv[4][5];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              int i = nstart + j0 + t;
+              if (i >= D) i -= D;
+              if (i >= D) i -= D;
+              idx[t] = i;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (j0 + t < L) {
+                pv[t][0] = ld_stream1(q0 + idx[t]);
+                pv[t][1] = ld_stream1(q1 + idx[t]);
+                pv[t][2] = ndonors > 2 ? ld_stream1(q2 + idx[t]) : 0.0;
+                pv[t][3] = ndonors > 3 ? ld_stream1(q3 + idx[t]) : 0.0;
+                pv[t][4] = ndonors > 4 ? ld_stream1(q4 + idx[t]) : 0.0;
+              }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              if (j0 + t < L) {
+                const int i = idx[t];
+                const double x = row[i];
+                undo[j0 + t] = x;
+                const double bst = __ldg(P.best_x + i);
+                double v;
+                switch (base) {
+                  case BASE_BEST1: v = mutant<BASE_BEST1>(x, bst, pv[t], P.F); break;
+                  case BASE_RAND1: v = mutant<BASE_RAND1>(x, bst, pv[t], P.F); break;
+                  case BASE_RANDTOBEST1: v = mutant<BASE_RANDTOBEST1>(x, bst, pv[t], P.F); break;
+                  case BASE_BEST2: v = mutant<BASE_BEST2>(x, bst, pv[t], P.F); break;
+                  default: v = mutant<BASE_RAND2>(x, bst, pv[t], P.F); break;
+                }
+                if (P.bounds_mode != BOUNDS_NONE) {
+                  const double l = uni_b ? P.lo_s : __ldg(P.lo + i);
+                  const double h = uni_b ? P.hi_s : __ldg(P.hi + i);
+                  if (P.bounds_mode == BOUNDS_CLAMP) {
+                    v = (v > l) ? v : l;  // python max(lo, x); min(hi, x)
+                    v = (v < h) ? v : h;
+                  } else {
+                    oob |= (v < l) || (v > h);
+                  }
+                }
+                row[i] = v;
+              }
+            }
           }
         }
-        if (P.bounds_mode != BOUNDS_NONE) {
+        if (xover == XOVER_BIN && P.bounds_mode != BOUNDS_NONE) {
           for (int i = 0; i < D; ++i) {
             const double l = uni_b ? P.lo_s : __ldg(P.lo + i);
             const double h = uni_b ? P.hi_s : __ldg(P.hi + i);
             double x = row[i];
             if (P.bounds_mode == BOUNDS_CLAMP) {
-              const double x_in = x;
               x = (x > l) ? x : l;  // python max(lo, x); min(hi, x)
               x = (x < h) ? x : h;
-              clamp_touched |= __double_as_longlong(x) != __double_as_longlong(x_in);
               row[i] = x;
             } else {
               oob |= (x < l) || (x > h);
@@ -333,16 +381,14 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
         }
         if (isinf(E)) ++w_ninf;
         if (!acc && P.mode == MODE_STEP) {
-          // rejected: the crossed dimensions get the parent's values back; if the clamp changed
-          // anything (normally only crossed dimensions: the population is inside the bounds since
-          // generation 0) the whole row is restored
-          const double* __restrict__ prow = P.pop_cur + c * D;
-          if (clamp_touched || L == D) {
+          // rejected: the crossed dimensions get the parent's values back
+          if (binomial) {
+            const double* __restrict__ prow = P.pop_cur + c * D;
             for (int i = 0; i < D; ++i) row[i] = ld_stream1(prow + i);
           } else {
             int i = nstart;
             for (int j = 0; j < L; ++j) {
-              row[i] = ld_stream1(prow + i);
+              row[i] = undo[j];
               if (++i == D) i = 0;
             }
           }
