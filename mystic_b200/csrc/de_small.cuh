@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
   int64_t w_best_idx = INT64_MAX;
   unsigned long long w_ninf = 0, w_nacc = 0;
   const bool uni_b = P.bounds_uniform != 0;
+  const unsigned inv_d = (unsigned)((0x100000000ull + (unsigned)D - 1) / (unsigned)D);  // ceil(2^32 / D)
 
   const int64_t nbatch = (P.np + 31) / 32;
   const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
@@ -178,21 +179,25 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
     const int64_t c = c0 + lane;
     const bool live = lane < nrows;
 
-    // ---- A: coalesced load of the batch's parent rows (contiguous in memory)
+    // ---- A: coalesced load of the batch's parent rows (contiguous in memory), eight loads in
+    //      flight per lane; element idx of the block lives at tile[idx / D][idx % D]
     {
       const double* __restrict__ src = P.pop_cur + c0 * D;
       const int total = nrows * D;
-      int r = 0, col = lane;
-      while (col >= D) {
-        col -= D;
-        ++r;
-      }
-      for (int idx = lane; idx < total; idx += 32) {
-        tile[r * Dp + col] = ld_stream1(src + idx);
-        col += 32;
-        while (col >= D) {
-          col -= D;
-          ++r;
+      for (int base = lane; base < total; base += 256) {
+        double v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = base + 32 * k;
+          v[k] = (idx < total) ? ld_stream1(src + idx) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int idx = base + 32 * k;
+          if (idx < total) {
+            const int r = (int)__umulhi((unsigned)idx, inv_d);  // idx / D (idx < 4096, D <= 128)
+            tile[r * Dp + (idx - r * D)] = v[k];
+          }
         }
       }
     }
@@ -401,18 +406,9 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
     if (P.mode != MODE_EVAL) {
       double* __restrict__ dst = P.pop_next + c0 * D;
       const int total = nrows * D;
-      int r = 0, col = lane;
-      while (col >= D) {
-        col -= D;
-        ++r;
-      }
       for (int idx = lane; idx < total; idx += 32) {
-        dst[idx] = tile[r * Dp + col];
-        col += 32;
-        while (col >= D) {
-          col -= D;
-          ++r;
-        }
+        const int r = (int)__umulhi((unsigned)idx, inv_d);
+        dst[idx] = tile[r * Dp + (idx - r * D)];
       }
     }
     __syncwarp();  // the tile is reused by the next batch
