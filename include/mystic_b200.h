@@ -137,6 +137,12 @@ int mb2_upload_population(mb2_ctx* ctx, const double* pop_host, void* stream);
 /* optional capture of every trial vector / trial energy of the next steps (NULL disables) */
 int mb2_set_capture(mb2_ctx* ctx, double* trial_dev, double* trial_energy_dev);
 
+/* Resume a saved solver (abstract_solver.py:975-1027 SaveSolver / solvers.py:90-125 LoadSolver):
+ * after mb2_upload_population of the saved population, install its energies, the best member
+ * and the generation counter without re-evaluating anything.  Synchronous. */
+int mb2_restore_state(mb2_ctx* ctx, const double* energy_host, double best_energy, int64_t best_index,
+                      const double* best_x_host, int64_t generation);
+
 /* generation 0: differential_evolution.py:516-520 (clip into the strict range), :559-567,
  * :575-582 with strategy=None, :589, :603-613 */
 int mb2_eval_initial(mb2_ctx* ctx, void* stream);

@@ -14,7 +14,7 @@ EXPORTS = [
     'mb2_set_strategy', 'mb2_set_bounds', 'mb2_set_cost', 'mb2_set_penalty', 'mb2_set_rng_philox',
     'mb2_set_rng_replay', 'mb2_init_population', 'mb2_upload_population', 'mb2_set_capture',
     'mb2_eval_initial', 'mb2_step', 'mb2_pack_best', 'mb2_merge_best', 'mb2_read_result', 'mb2_eval_cost',
-    'mb2_launch_info', 'mb2_launch_count', 'mb2_selftest_division',
+    'mb2_launch_info', 'mb2_launch_count', 'mb2_selftest_division', 'mb2_restore_state',
 ]
 
 
@@ -60,6 +60,7 @@ def _load():
         'mb2_launch_info': (ctypes.c_int, [vp, c_int32_p, c_int32_p, c_int32_p]),
         'mb2_launch_count': (i64, [vp]),
         'mb2_selftest_division': (ctypes.c_int, [vp, i64, u64, dbl, c_int64_p]),
+        'mb2_restore_state': (ctypes.c_int, [vp, c_double_p, dbl, i64, c_double_p, i64]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it

@@ -691,6 +691,19 @@ int mb2_upload_population(mb2_ctx* c, const double* pop_host, void* stream) {
   return MB2_OK;
 }
 
+int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy, int64_t best_index,
+                      const double* best_x_host, int64_t generation) {
+  if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
+  if (!energy_host || !best_x_host || generation < 0) return fail(MB2_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  CUDA_TRY(cudaMemcpy(c->en[c->cur], energy_host, sizeof(double) * c->np, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMemcpy(c->best_x, best_x_host, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
+  DeviceState st = {best_energy, best_index, 0, 0, generation};
+  CUDA_TRY(cudaMemcpy(c->st, &st, sizeof(st), cudaMemcpyHostToDevice));
+  c->generation = generation;
+  return MB2_OK;
+}
+
 int mb2_eval_initial(mb2_ctx* c, void* stream) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   CUDA_TRY(cudaSetDevice(c->device));

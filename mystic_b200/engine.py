@@ -118,6 +118,11 @@ class DeviceEngine(object):
             raise ValueError('population shape %r != %r' % (pop.shape, (self.np_local, self.dim)))
         check(lib.mb2_upload_population(self._ctx, pop.ctypes.data_as(ctypes.c_void_p), self._stream()))
 
+    def restore_state(self, energies, best_energy, best_index, best_x, generation):
+        e = np.ascontiguousarray(energies, dtype=np.float64)
+        x = np.ascontiguousarray(best_x, dtype=np.float64)
+        check(lib.mb2_restore_state(self._ctx, _dptr(e), float(best_energy), int(best_index), _dptr(x), int(generation)))
+
     def _current(self):
         p, e = ctypes.c_void_p(), ctypes.c_void_p()
         check(lib.mb2_current(self._ctx, ctypes.byref(p), ctypes.byref(e)))

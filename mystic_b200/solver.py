@@ -62,6 +62,17 @@ def _default_termination(inst, *args, **kwds):
     return ''
 
 
+def _pickler():
+    """dill when it is installed (what the reference uses, abstract_solver.py:983): it can also
+    serialise mystic's closure-based termination objects; plain pickle otherwise"""
+    try:
+        import dill
+        return dill
+    except ImportError:
+        import pickle
+        return pickle
+
+
 class _DeviceObjective(object):
     """What `_cost[0]` is in the reference: the decorated objective
     (inf outside the strict range, else cost) + penalty -- evaluated on the device."""
@@ -152,6 +163,7 @@ class DifferentialEvolutionSolver2(object):
         self._replay_source = None
         self._device_cost = None
         self._last = None  # (n_inf, n_accepted, best_index) of the last generation
+        self._resume = None  # device state to reinstall after LoadSolver / unpickling
         self._world = 1
         self._rank = 0
         self._np_local = NP
@@ -592,6 +604,11 @@ class DifferentialEvolutionSolver2(object):
                     self._engine.population_tensor()[0, :] = self._engine.population_tensor().new_tensor(x0)
             else:
                 self._engine.upload_population(self._host_pop)
+            if self._resume is not None:
+                # a solver loaded from a restart file: energies, best member and generation counter
+                # are installed as saved, nothing is re-evaluated
+                self._engine.restore_state(**self._resume)
+                self._resume = None
         eng = self._engine
         mode, lo, hi = self._effective_bounds()
         if mode != BOUNDS_NONE and not fresh and self.generations:
@@ -827,15 +844,27 @@ class DifferentialEvolutionSolver2(object):
         state['_engine'] = None
         state['_live'] = False
         if eng is not None:
-            state['_host_pop_shard'] = eng.population()
-            state['_host_energy_shard'] = eng.energies()
+            # device buffers -> host arrays; the engine is rebuilt lazily by the next Step()
+            state['_host_pop'] = eng.population()
+            state['_device_init'] = None
+            if len(self._stepmon):
+                state['_resume'] = dict(energies=eng.energies(), best_energy=float(self.bestEnergy),
+                                        best_index=(self._last[2] if self._last else -1),
+                                        best_x=np.array(self.bestSolution, dtype=np.float64),
+                                        generation=len(self._stepmon) - 1)
+        state['_engine_factory'] = None if '_engine_factory' not in self.__dict__ else self.__dict__['_engine_factory']
         state['_replay_source'] = None
         cost = state.get('_cost', (None, None, None))
         state['_cost'] = (None, cost[1], cost[2])
         return state
 
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        if self.__dict__.get('_engine_factory') is None:
+            self.__dict__.pop('_engine_factory', None)
+
     def SaveSolver(self, filename=None, **kwds):
-        import pickle
+        pickle = _pickler()
         if filename is None:
             if self._state is None:
                 import os
@@ -858,3 +887,11 @@ class DifferentialEvolutionSolver2(object):
 
 
 B200DifferentialEvolutionSolver2 = DifferentialEvolutionSolver2
+
+
+def LoadSolver(filename=None, **kwds):
+    """mystic/solvers.py:90-125: load a solver saved with SaveSolver / SetSaveFrequency"""
+    with open(filename, 'rb') as f:
+        solver = _pickler().load(f)
+    solver.__dict__.update(kwds)
+    return solver

@@ -15,130 +15,170 @@ inf = float('inf')
 EARLYEXIT = 0
 
 
-def _condition(name, kwds, test):
-    doc = '%s with %s' % (name, kwds)
+class _Condition(object):
+    """A termination condition: `cond(solver, info=False)`.  A class (not a closure) so that solvers
+    holding one can be pickled by SaveSolver without dill."""
 
-    def cond(inst, info=False):
-        met = test(inst)
+    def __init__(self, name, kwds):
+        self.name = name
+        self.kwds = dict(kwds)
+        self.__doc__ = '%s with %s' % (name, kwds)
+        self.__name__ = '_' + name
+
+    def __call__(self, inst, info=False):
+        met = _TESTS[self.name](inst, **self.kwds)
         if info:
-            return doc if met else ''
+            return self.__doc__ if met else ''
         return bool(met)
-    cond.__doc__ = doc
-    cond.__name__ = '_' + name
-    return cond
-
-
-def VTR(tolerance=0.005, target=0.0):
-    """abs(cost[-1] - target) <= tolerance   (mystic/termination.py:181-196)"""
-    def test(inst):
-        hist = inst.energy_history
-        return bool(len(hist)) and abs(hist[-1] - target) <= tolerance
-    return _condition('VTR', {'tolerance': tolerance, 'target': target}, test)
 
 
 def _lookback(generations):
     return 0 if generations is None else int(generations)
 
 
+def _vtr(inst, tolerance, target):
+    hist = inst.energy_history
+    return bool(len(hist)) and abs(hist[-1] - target) <= tolerance
+
+
+def _cog(inst, tolerance, generations):
+    hist = inst.energy_history
+    g = _lookback(generations)
+    if not len(hist) or len(hist) <= g:
+        return False
+    return (hist[-g] - hist[-1]) <= tolerance or hist[-g] == hist[-1]
+
+
+def _ncog(inst, tolerance, generations):
+    hist = inst.energy_history
+    g = _lookback(generations)
+    if not len(hist) or len(hist) <= g:
+        return False
+    if hist[-g] == hist[-1]:
+        return True
+    return 2.0 * (hist[-g] - hist[-1]) <= tolerance * (abs(hist[-g]) + abs(hist[-1])) + 1e-20
+
+
+def _vtrcog(inst, ftol, gtol, generations, target):
+    hist = inst.energy_history
+    if not len(hist):
+        return False
+    g = _lookback(generations)
+    if len(hist) > g and ((hist[-g] - hist[-1]) <= gtol or hist[-g] == hist[-1]):
+        return True
+    return abs(hist[-1] - target) <= ftol
+
+
+def _nct(inst, fval, tolerance, generations):
+    hist = inst.energy_history
+    if not len(hist):
+        return False
+    g = _lookback(generations)
+    if g and fval is None:
+        return len(hist) > g and ((hist[-g] - hist[-1]) <= 0 or hist[-g] == hist[-1])
+    if not g and fval is None:
+        return True
+    return abs(hist[-1] - fval) <= abs(tolerance * fval)
+
+
+def _crt(inst, xtol, ftol):
+    sim = np.array(inst.population)
+    fsim = np.array(inst.popEnergy)
+    if len(fsim) < 2:
+        return False
+    with np.errstate(invalid='ignore'):
+        return bool(np.max(np.abs(sim[1:] - sim[0])) <= xtol and np.max(np.abs(fsim[0] - fsim[1:])) <= ftol)
+
+
+def _spread(inst, tolerance):
+    sim = np.array(inst.population)
+    return bool(np.all(np.abs(sim - sim[0]) <= np.abs(tolerance * sim[0])))
+
+
+def _limits(inst, generations, evaluations):
+    maxiter = inf if generations is None else generations
+    maxfun = inf if evaluations is None else evaluations
+    return inst._fcalls[0] >= maxfun or inst.generations >= maxiter
+
+
+def _interrupt(inst):
+    return bool(inst._EARLYEXIT)
+
+
+_TESTS = {'VTR': _vtr, 'ChangeOverGeneration': _cog, 'NormalizedChangeOverGeneration': _ncog,
+          'VTRChangeOverGeneration': _vtrcog, 'NormalizedCostTarget': _nct, 'CandidateRelativeTolerance': _crt,
+          'PopulationSpread': _spread, 'EvaluationLimits': _limits, 'SolverInterrupt': _interrupt}
+
+
+def VTR(tolerance=0.005, target=0.0):
+    """abs(cost[-1] - target) <= tolerance   (mystic/termination.py:181-196)"""
+    return _Condition('VTR', {'tolerance': tolerance, 'target': target})
+
+
 def ChangeOverGeneration(tolerance=1e-6, generations=30):
     """cost[-g] - cost[-1] <= tolerance   (mystic/termination.py:198-217)"""
-    def test(inst):
-        hist = inst.energy_history
-        g = _lookback(generations)
-        if not len(hist) or len(hist) <= g:
-            return False
-        return (hist[-g] - hist[-1]) <= tolerance or hist[-g] == hist[-1]
-    return _condition('ChangeOverGeneration', {'tolerance': tolerance, 'generations': generations}, test)
+    return _Condition('ChangeOverGeneration', {'tolerance': tolerance, 'generations': generations})
 
 
 def NormalizedChangeOverGeneration(tolerance=1e-4, generations=10):
     """2*(cost[-g]-cost[-1]) <= tolerance*(|cost[-g]|+|cost[-1]|) + 1e-20   (termination.py:219-240)"""
-    def test(inst):
-        hist = inst.energy_history
-        g = _lookback(generations)
-        if not len(hist) or len(hist) <= g:
-            return False
-        if hist[-g] == hist[-1]:
-            return True
-        return 2.0 * (hist[-g] - hist[-1]) <= tolerance * (abs(hist[-g]) + abs(hist[-1])) + 1e-20
-    return _condition('NormalizedChangeOverGeneration', {'tolerance': tolerance, 'generations': generations}, test)
+    return _Condition('NormalizedChangeOverGeneration', {'tolerance': tolerance, 'generations': generations})
 
 
 def VTRChangeOverGeneration(ftol=0.005, gtol=1e-6, generations=30, target=0.0):
     """cost[-g] - cost[-1] <= gtol or abs(cost[-1] - target) <= ftol   (termination.py:320-342)"""
-    def test(inst):
-        hist = inst.energy_history
-        if not len(hist):
-            return False
-        g = _lookback(generations)
-        if len(hist) > g and ((hist[-g] - hist[-1]) <= gtol or hist[-g] == hist[-1]):
-            return True
-        return abs(hist[-1] - target) <= ftol
-    return _condition('VTRChangeOverGeneration',
-                      {'ftol': ftol, 'gtol': gtol, 'generations': generations, 'target': target}, test)
+    return _Condition('VTRChangeOverGeneration',
+                      {'ftol': ftol, 'gtol': gtol, 'generations': generations, 'target': target})
 
 
 def NormalizedCostTarget(fval=None, tolerance=1e-6, generations=30):
     """abs(cost[-1]-fval) <= abs(tolerance*fval), or no improvement over g iterations (termination.py:290-318)"""
-    def test(inst):
-        hist = inst.energy_history
-        if not len(hist):
-            return False
-        g = _lookback(generations)
-        if g and fval is None:
-            return len(hist) > g and ((hist[-g] - hist[-1]) <= 0 or hist[-g] == hist[-1])
-        if not g and fval is None:
-            return True
-        return abs(hist[-1] - fval) <= abs(tolerance * fval)
-    return _condition('NormalizedCostTarget', {'fval': fval, 'tolerance': tolerance, 'generations': generations}, test)
+    return _Condition('NormalizedCostTarget', {'fval': fval, 'tolerance': tolerance, 'generations': generations})
 
 
 def CandidateRelativeTolerance(xtol=1e-4, ftol=1e-4):
     """abs(xi-x0) <= xtol & abs(fi-f0) <= ftol; reads the whole population (termination.py:242-267)"""
-    def test(inst):
-        sim = np.array(inst.population)
-        fsim = np.array(inst.popEnergy)
-        if len(fsim) < 2:
-            return False
-        with np.errstate(invalid='ignore'):
-            return bool(np.max(np.abs(sim[1:] - sim[0])) <= xtol and np.max(np.abs(fsim[0] - fsim[1:])) <= ftol)
-    return _condition('CandidateRelativeTolerance', {'xtol': xtol, 'ftol': ftol}, test)
+    return _Condition('CandidateRelativeTolerance', {'xtol': xtol, 'ftol': ftol})
 
 
 def PopulationSpread(tolerance=1e-6):
     """abs(params - params[0]) <= abs(tolerance*params[0]); reads the whole population (termination.py:344-361)"""
-    def test(inst):
-        sim = np.array(inst.population)
-        return bool(np.all(np.abs(sim - sim[0]) <= np.abs(tolerance * sim[0])))
-    return _condition('PopulationSpread', {'tolerance': tolerance}, test)
+    return _Condition('PopulationSpread', {'tolerance': tolerance})
 
 
 def EvaluationLimits(generations=None, evaluations=None):
     """iterations >= generations or fcalls >= evaluations   (termination.py:386-408)"""
-    maxiter = inf if generations is None else generations
-    maxfun = inf if evaluations is None else evaluations
+    return _Condition('EvaluationLimits', {'generations': generations, 'evaluations': evaluations})
 
-    def test(inst):
-        return inst._fcalls[0] >= maxfun or inst.generations >= maxiter
-    return _condition('EvaluationLimits', {'generations': generations, 'evaluations': evaluations}, test)
+
+class _TimeLimits(_Condition):
+    def __init__(self, seconds, system):
+        _Condition.__init__(self, 'TimeLimits', {'seconds': seconds, 'system': system})
+        self._delta = inf if seconds is None else getattr(seconds, 'total_seconds', lambda: abs(seconds))()
+        self.reset()
+
+    def _timer(self):
+        system = self.kwds['system']
+        return _time.time() if system is None else (_time.perf_counter() if system else _time.process_time())
+
+    def reset(self):
+        self._start = self._timer()
+
+    def __call__(self, inst, info=False):
+        met = (self._timer() - self._start) >= self._delta
+        if info:
+            return self.__doc__ if met else ''
+        return bool(met)
 
 
 def TimeLimits(seconds=86400, system=None):
     """elapsed time >= seconds   (termination.py:410-437)"""
-    timer = _time.time if system is None else (_time.perf_counter if system else _time.process_time)
-    start = [timer()]
-    delta = inf if seconds is None else getattr(seconds, 'total_seconds', lambda: abs(seconds))()
-
-    def test(inst):
-        return (timer() - start[0]) >= delta
-    cond = _condition('TimeLimits', {'seconds': seconds, 'system': system}, test)
-    cond.reset = lambda: start.__setitem__(0, timer())
-    return cond
+    return _TimeLimits(seconds, system)
 
 
 def SolverInterrupt():
     """_EARLYEXIT == True   (termination.py:439-451)"""
-    return _condition('SolverInterrupt', {}, lambda inst: bool(inst._EARLYEXIT))
+    return _Condition('SolverInterrupt', {})
 
 
 class When(tuple):

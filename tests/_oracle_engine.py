@@ -68,6 +68,15 @@ class OracleEngine(object):
         self._pop = np.array(pop, dtype=np.float64)
         self.state = None
 
+    def restore_state(self, energies, best_energy, best_index, best_x, generation):
+        mode, lo, hi = self.bounds
+        self.state = orc.DEState(self._pop, lo, hi, mode)
+        self.state.popEnergy = np.array(energies, dtype=np.float64)
+        self.state.bestEnergy = float(best_energy)
+        self.state.bestSolution = np.array(best_x, dtype=np.float64)
+        self.state.generation = int(generation)
+        self.best_idx = int(best_index)
+
     def population_tensor(self):
         arr = self._pop if self.state is None else self.state.population
         return torch.from_numpy(arr)

@@ -365,3 +365,30 @@ def test_chebyshev_dmma_trajectory_matches_oracle():
             G.assert_bits_equal(best_x, st.bestSolution, '%s gen %d best' % (strat, g))
             assert n_acc == int(st.accepted.sum())
         eng.close()
+
+
+def test_save_and_load_solver_on_device(tmp_path):
+    """restart files (abstract_solver.py:975-1018): device state -> host arrays -> device state"""
+    from mystic_b200 import DifferentialEvolutionSolver2, LoadSolver, models, termination
+
+    def make():
+        s = DifferentialEvolutionSolver2(256, 300, rng='philox', seed=91, strategy='Best1Bin')
+        s.SetRandomInitialPoints([-400.] * 256, [400.] * 256)
+        s.SetStrictRanges([-400.] * 256, [400.] * 256, tight=True)
+        s.SetTermination(termination.VTR(-1.0))
+        s.SetEvaluationLimits(generations=10 ** 6)
+        return s
+    a = make()
+    a.Step(models.griewangk)
+    for _ in range(4):
+        a.Step()
+    path = str(tmp_path / 'restart.pkl')
+    a.SaveSolver(path)
+    b = LoadSolver(path)
+    for _ in range(3):
+        a.Step()
+        b.Step(models.griewangk)
+    assert list(a.energy_history) == list(b.energy_history)
+    assert np.array_equal(a.population, b.population)
+    assert np.array_equal(a.popEnergy, b.popEnergy)
+    assert a.evaluations == b.evaluations and a.generations == b.generations == 7

@@ -190,3 +190,33 @@ def test_generation_monitor_prepend_and_null():
     assert len(s._stepmon) == 2
     s.SetGenerationMonitor(VerboseMonitor(1000), new=True)
     assert len(s._stepmon) == 0
+
+
+def test_save_and_load_solver_resumes_identically(tmp_path):
+    """SetSaveFrequency / SaveSolver / LoadSolver (abstract_solver.py:975-1018, solvers.py:90-125):
+    a solver reloaded from its restart file continues exactly like the one that kept running"""
+    from mystic_b200 import LoadSolver
+
+    def make():
+        s = DifferentialEvolutionSolver2(4, 20, rng='philox', seed=77, engine=OracleEngine, strategy='Best1Exp')
+        s.SetRandomInitialPoints([-2.] * 4, [2.] * 4)
+        s.SetStrictRanges([-2.] * 4, [2.] * 4)
+        s.SetTermination(termination.VTR(-1.0))
+        s.SetEvaluationLimits(generations=10 ** 6)
+        return s
+    a = make()
+    a.Step(models.rosen)
+    for _ in range(5):
+        a.Step()
+    path = str(tmp_path / 'restart.pkl')
+    a.SaveSolver(path)
+    b = LoadSolver(path)
+    b._engine_factory = OracleEngine
+    assert b.generations == a.generations and b.evaluations == a.evaluations
+    for _ in range(4):
+        a.Step()
+        b.Step(models.rosen)
+    assert list(a.energy_history) == list(b.energy_history)
+    G.assert_bits_equal(a.population, b.population, 'population after resume')
+    G.assert_bits_equal(np.array(a.bestSolution), np.array(b.bestSolution), 'bestSolution after resume')
+    assert a.evaluations == b.evaluations

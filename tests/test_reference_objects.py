@@ -1,0 +1,93 @@
+"""Drop-in claim: UNMODIFIED mystic objects (termination conditions, monitors, strategy functions,
+model functions, penalty decorators) are accepted by the B200 solver.  Runs only where the
+reference is importable (the build container: /root/reference + the klepto shim); the generation
+step is supplied by the test-only OracleEngine, the same code path runs on the GPU in
+tests/test_gpu_parity.py with mystic_b200's own twins of these objects."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if not os.path.isdir('/root/reference/mystic'):
+    pytest.skip('reference not available here', allow_module_level=True)
+sys.path.insert(0, os.path.join(REPO, 'oracle', '_shim'))
+sys.path.insert(1, '/root/reference')
+
+import mystic.models  # noqa: E402
+import mystic.monitors  # noqa: E402
+import mystic.penalty  # noqa: E402
+import mystic.strategy  # noqa: E402
+import mystic.termination  # noqa: E402
+
+from mystic_b200 import DifferentialEvolutionSolver2, penalty  # noqa: E402
+from tests import _golden as G  # noqa: E402
+from tests._oracle_engine import OracleEngine  # noqa: E402
+
+
+def test_reference_objects_drive_the_solver_to_the_reference_result():
+    """BASELINE config 1 with mystic's own rosen / Best1Exp / VTR / Monitor objects"""
+    meta, z = G.load('c1_rosen3_best1exp')
+    random.seed(123)
+    s = DifferentialEvolutionSolver2(3, 40, rng='reference', engine=OracleEngine)
+    s.SetRandomInitialPoints([0.] * 3, [2.] * 3)
+    s.SetEvaluationLimits(generations=99999)
+    mon = mystic.monitors.Monitor()
+    s.SetGenerationMonitor(mon)
+    s.Solve(mystic.models.rosen, mystic.termination.VTR(1e-4), strategy=mystic.strategy.Best1Exp,
+            CrossProbability=0.5, ScalingFactor=0.6)
+    assert s.generations == 39 and s.evaluations == 1600
+    assert s.bestEnergy == 7.710567500336223e-05
+    assert len(mon) == 40 and mon.y[-1] == s.bestEnergy
+    assert s.Terminated(info=True).startswith('VTR with')
+
+
+def test_reference_compound_termination_and_verbose_monitor(capsys):
+    T = mystic.termination
+    random.seed(5)
+    s = DifferentialEvolutionSolver2(4, 24, rng='reference', engine=OracleEngine)
+    s.SetRandomInitialPoints([-2.] * 4, [2.] * 4)
+    s.SetStrictRanges([-2.] * 4, [2.] * 4)
+    s.SetGenerationMonitor(mystic.monitors.VerboseMonitor(5))
+    s.SetEvaluationLimits(generations=40)
+    s.Solve(mystic.models.rosen, T.Or(T.VTR(1e-8), T.ChangeOverGeneration(1e-12, 500), T.NormalizedChangeOverGeneration(1e-12, 500)),
+            strategy=mystic.strategy.Rand1Bin)
+    out = capsys.readouterr().out
+    assert 'Generation 0 has' in out and 'Generation 5 has' in out
+    assert s.generations == 40
+    assert s.Terminated(info=True).startswith('EvaluationLimits with')
+    for cond in (T.CandidateRelativeTolerance(), T.PopulationSpread(), T.EvaluationLimits(10, 10), T.VTRChangeOverGeneration()):
+        assert isinstance(cond(s), (bool, np.bool_))
+        assert isinstance(cond(s, info=True), str)
+
+
+def test_reference_penalty_decorator_with_linear_condition():
+    """mystic.penalty.quadratic_inequality over a mystic_b200.penalty.linear condition"""
+    @mystic.penalty.quadratic_inequality(penalty.linear([1.] * 8, 100.), k=100, h=5)
+    def pen(x):
+        return 0.0
+    meta, z = G.load('corana8_rand1exp_pen')
+    random.seed(meta['seed'])
+    s = DifferentialEvolutionSolver2(8, 32, rng='replay', engine=OracleEngine, CrossProbability=meta['CR'],
+                                     ScalingFactor=meta['F'])
+    s.SetPopulation(z['pop0'])
+    s.SetStrictRanges(meta['bounds'][0], meta['bounds'][1], tight=True)
+    s.SetPenalty(pen)
+    s.SetReplayDraws((z['donors'][g], z['nstart'][g], z['uni'][g]) for g in range(z['donors'].shape[0]))
+    s.SetEvaluationLimits(generations=meta['maxgen'])
+    s.Solve(mystic.models.corana, mystic.termination.VTR(-1.0), strategy=mystic.strategy.Rand1Exp)
+    G.assert_bits_equal(np.array(s.energy_history), z['energy_history'], 'energy history')
+    G.assert_bits_equal(s.population, z['pop'][-1], 'population')
+
+
+def test_host_callables_are_rejected():
+    s = DifferentialEvolutionSolver2(3, 8, engine=OracleEngine)
+    with pytest.raises(TypeError):
+        s.SetObjective(mystic.models.sphere)          # a mystic model without a device twin
+    with pytest.raises(TypeError):
+        @mystic.penalty.quadratic_inequality(lambda x: sum(x) - 1.0)
+        def pen(x):
+            return 0.0
+        s.SetPenalty(pen)                             # python condition: not device-expressible
