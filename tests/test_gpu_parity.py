@@ -392,3 +392,68 @@ def test_save_and_load_solver_on_device(tmp_path):
     assert np.array_equal(a.population, b.population)
     assert np.array_equal(a.popEnergy, b.popEnergy)
     assert a.evaluations == b.evaluations and a.generations == b.generations == 7
+
+
+FULL_SIZE = {
+    # BASELINE.json configs 3-5 at full (per-GPU) size: (dim, NP, strategy, cost, extra, tensor cores, CR, F, span, bounds mode, penalty)
+    'c3_chebyshev_dmma': (9, 1 << 20, 'Best1Exp', 'chebyshev8cost', (4096,), True, 1.0, 0.9, 100., orc.BOUNDS_NONE, None),
+    'c4_corana_penalty': (64, 1 << 20, 'Rand1Exp', 'corana', (), False, 0.9, 0.8, 1000., orc.BOUNDS_CLAMP,
+                          dict(G=1.0, h=100., k=100, hpow=5)),
+    'c5_griewangk': (256, 1 << 21, 'Best1Bin', 'griewangk', (), False, 0.9, 0.8, 400., orc.BOUNDS_CLAMP, None),
+}
+
+
+@pytest.mark.parametrize('name', sorted(FULL_SIZE))
+def test_full_size_properties(name):
+    """size-independent properties at the full BASELINE sizes: greedy selection never worsens a
+    member, bestEnergy = min(popEnergy) at the lowest index, bounds respected, stored energies are
+    the cost of the stored rows (re-evaluation is idempotent), a sample agrees with the oracle,
+    accepted-count bookkeeping, determinism of a second run"""
+    import torch
+    from mystic_b200 import models, penalty
+    from mystic_b200.engine import DeviceEngine
+    D, NP, strat, cost, extra, tc, CR, F, span, mode, pen = FULL_SIZE[name]
+    lo, hi = np.full(D, -span), np.full(D, span)
+    c = getattr(models, cost)
+    terms = ()
+    finals = []
+    for rep in range(2):
+        eng = DeviceEngine(NP, D)
+        eng.set_cost(c.device_id(tc, D), c.params(extra))
+        if mode != orc.BOUNDS_NONE:
+            eng.set_bounds(mode, lo, hi)
+        if pen:
+            @penalty.quadratic_inequality(penalty.linear([pen['G']] * D, pen['h']), k=pen['k'], h=pen['hpow'])
+            def p(x):
+                return 0.0
+            eng.set_penalty(*p.device_terms(D))
+            terms = [dict(ptype='quadratic_inequality', G=[pen['G']] * D, h=pen['h'], k=pen['k'], hpow=pen['hpow'])]
+        eng.set_strategy(orc.STRATEGIES[strat][0], F, CR)
+        eng.set_rng_philox(0xBA5E)
+        eng.init_population(0xBA5E, lo, hi)
+        eng.eval_initial()
+        prev = eng.read_result()
+        e_prev = eng.energy_tensor().clone()
+        for g in range(3):
+            eng.step()
+            r = eng.read_result()
+            e_now = eng.energy_tensor()
+            assert bool((e_now <= e_prev).all())
+            assert int((e_now < e_prev).sum()) == r[3]
+            assert r[0] == float(e_now.min()) and r[0] <= prev[0]
+            if r[0] < prev[0]:
+                assert r[1] == int(torch.argmin(e_now))
+            prev, e_prev = r, e_now.clone()
+        pop = eng.population_tensor()
+        if mode != orc.BOUNDS_NONE:
+            assert bool((pop >= -span).all()) and bool((pop <= span).all())
+        sample = torch.arange(0, NP, 4099, device=pop.device)
+        rows = pop[sample].cpu().numpy()
+        re = eng.eval_cost(rows)
+        assert np.array_equal(re, e_now[sample].cpu().numpy())
+        st = orc.DEState(rows[:24], lo if mode else None, hi if mode else None, mode)
+        want = orc.evaluate(rows[:24], orc.make_cost(cost, extra), st, terms)
+        energy_close(re[:24], want, rows[:24], cost, name + ' oracle sample')
+        finals.append((pop.clone(), prev[0]))
+        eng.close()
+    assert torch.equal(finals[0][0], finals[1][0]) and finals[0][1] == finals[1][1]
