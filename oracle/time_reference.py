@@ -49,6 +49,16 @@ def run(name, dim, NP, cost, strategy, CR, F, lo, hi, tight, gens, penalty=None,
 
 def main():
     rows = []
+    global run
+    _run = run
+
+    def run(*a, **k):
+        try:
+            return _run(*a, **k)
+        except Exception as e:   # e.g. RecursionError: 2*D nested symbolic clamp functions at D=1024
+            out = dict(problem=a[0], dim=a[1], NP=a[2], error='%s: %s' % (type(e).__name__, str(e)[:80]))
+            print(json.dumps(out), flush=True)
+            return out
     rows.append(run('C2 rosen 1024-D Best1Bin clamp', 1024, 1024, 'rosen', 'Best1Bin', 0.9, 0.8, -5., 5., True, 2))
     rows.append(run('C2 rosen 1024-D Best1Bin reject', 1024, 1024, 'rosen', 'Best1Bin', 0.9, 0.8, -5., 5., False, 3))
     rows.append(run('C2 rosen 1024-D Best1Bin reject', 1024, 4096, 'rosen', 'Best1Bin', 0.9, 0.8, -5., 5., False, 2))

@@ -153,6 +153,13 @@ PHILOX_CASES = [
     (5, 20, 'Best2Bin', 'rosen', (), None, None, 0.0, 0.8, 5),
     (1024, 96, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
     (256, 80, 'Best1Bin', 'griewangk', (), (-400., 400., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
+    # TMA group widths 2 and 8, a single group per CTA, rows that are not whole trips
+    (512, 40, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_REJECT), None, 0.5, 0.8, 3),
+    (2048, 20, 'Best1Bin', 'griewangk', (), (-400., 400., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
+    (4096, 12, 'Best1Bin', 'rosen', (), None, None, 0.9, 0.8, 3),
+    (1000, 30, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
+    (129, 30, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
+    (6001, 8, 'Rand2Exp', 'griewangk', (), None, None, 0.999, 0.8, 2),
 ]
 
 
