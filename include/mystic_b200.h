@@ -98,6 +98,14 @@ const char* mb2_last_error(void);
 int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset,
                mb2_ctx** out);
 int mb2_destroy(mb2_ctx* ctx);
+/* Same, but the context's small device buffers (state, best member, bounds, per-CTA partials, cost
+ * tables) and its pinned host staging are carved out of caller-owned workspaces (e.g. tensors from
+ * a caching allocator) instead of cudaMalloc / cudaMallocHost, which cost milliseconds each next to
+ * gigabytes of live allocations.  mb2_workspace_bytes gives sufficient sizes for the common costs;
+ * anything that does not fit falls back to cudaMalloc.  The workspaces must outlive the context. */
+int64_t mb2_workspace_bytes(int32_t dim, int64_t* host_bytes);
+int mb2_create_ws(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset,
+                  void* dev_workspace, int64_t dev_bytes, void* host_workspace, int64_t host_bytes, mb2_ctx** out);
 
 /* Double-buffered population and energies (the reference keeps `population` and
  * `trialSolution`, abstract_map_solver.py:113-114).  pop_a is the current generation. */

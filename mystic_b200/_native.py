@@ -14,7 +14,7 @@ EXPORTS = [
     'mb2_set_strategy', 'mb2_set_bounds', 'mb2_set_cost', 'mb2_set_penalty', 'mb2_set_rng_philox',
     'mb2_set_rng_replay', 'mb2_init_population', 'mb2_upload_population', 'mb2_set_capture',
     'mb2_eval_initial', 'mb2_step', 'mb2_pack_best', 'mb2_merge_best', 'mb2_read_result', 'mb2_eval_cost',
-    'mb2_launch_info', 'mb2_launch_count', 'mb2_selftest_division', 'mb2_restore_state',
+    'mb2_launch_info', 'mb2_launch_count', 'mb2_selftest_division', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
 ]
 
 
@@ -40,6 +40,8 @@ def _load():
         'mb2_last_error': (ctypes.c_char_p, []),
         'mb2_create': (ctypes.c_int, [ctypes.c_int, i64, i32, i64, i64, ctypes.POINTER(vp)]),
         'mb2_destroy': (ctypes.c_int, [vp]),
+        'mb2_workspace_bytes': (i64, [i32, c_int64_p]),
+        'mb2_create_ws': (ctypes.c_int, [ctypes.c_int, i64, i32, i64, i64, vp, i64, vp, i64, ctypes.POINTER(vp)]),
         'mb2_bind_buffers': (ctypes.c_int, [vp, vp, vp, vp, vp]),
         'mb2_current': (ctypes.c_int, [vp, ctypes.POINTER(vp), ctypes.POINTER(vp)]),
         'mb2_set_strategy': (ctypes.c_int, [vp, ctypes.c_int, dbl, dbl]),

@@ -106,9 +106,44 @@ struct mb2_ctx {
   int64_t launches = 0;
   // launch geometry of the fused kernel
   int wpc = 8, grid = 0, smem = 0;
+  // small device / pinned-host buffers come out of a caller-provided workspace when there is one
+  // (torch's caching allocators make that free; cudaMalloc / cudaMallocHost cost milliseconds
+  // each next to gigabytes of live allocations) and from cudaMalloc otherwise
+  char* ws_dev = nullptr;
+  size_t ws_dev_cap = 0, ws_dev_off = 0;
+  char* ws_host = nullptr;
+  size_t ws_host_cap = 0, ws_host_off = 0;
+  std::vector<void*> owned_dev, owned_host;
+  size_t cap_cheb_x = 0, cap_vfrag = 0, cap_pen = 0;
+  double* init_lo = nullptr;
+  double* init_hi = nullptr;
 };
 
 namespace {
+
+int dev_alloc(mb2_ctx* c, size_t bytes, void** out) {
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (c->ws_dev != nullptr && c->ws_dev_off + need <= c->ws_dev_cap) {
+    *out = c->ws_dev + c->ws_dev_off;
+    c->ws_dev_off += need;
+    return MB2_OK;
+  }
+  CUDA_TRY(cudaMalloc(out, need));
+  c->owned_dev.push_back(*out);
+  return MB2_OK;
+}
+
+int host_alloc(mb2_ctx* c, size_t bytes, void** out) {
+  const size_t need = (bytes + 63) & ~(size_t)63;
+  if (c->ws_host != nullptr && c->ws_host_off + need <= c->ws_host_cap) {
+    *out = c->ws_host + c->ws_host_off;
+    c->ws_host_off += need;
+    return MB2_OK;
+  }
+  CUDA_TRY(cudaMallocHost(out, need));
+  c->owned_host.push_back(*out);
+  return MB2_OK;
+}
 
 typedef void (*StepKernel)(const StepParams);
 
@@ -153,20 +188,18 @@ void geometry(int dim_pad, int* wpc, int* smem) {
 
 int ensure_parts(mb2_ctx* c, int n) {
   if (n <= c->parts_cap) return MB2_OK;
-  cudaFree(c->part_e);
-  cudaFree(c->part_idx);
-  cudaFree(c->part_ninf);
-  cudaFree(c->part_nacc);
-  c->part_e = nullptr;
-  c->part_idx = nullptr;
-  c->part_ninf = nullptr;
-  c->part_nacc = nullptr;
-  c->parts_cap = 0;
-  CUDA_TRY(cudaMalloc(&c->part_e, sizeof(double) * n));
-  CUDA_TRY(cudaMalloc(&c->part_idx, sizeof(int64_t) * n));
-  CUDA_TRY(cudaMalloc(&c->part_ninf, sizeof(unsigned long long) * n));
-  CUDA_TRY(cudaMalloc(&c->part_nacc, sizeof(unsigned long long) * n));
-  c->parts_cap = n;
+  int cap = c->sm_count * 32;  // at most 32 resident CTAs per SM: persistent grids never exceed this
+  if (cap < n) cap = n;
+  void* p = nullptr;
+  if (int rc = dev_alloc(c, sizeof(double) * cap, &p)) return rc;
+  c->part_e = (double*)p;
+  if (int rc = dev_alloc(c, sizeof(int64_t) * cap, &p)) return rc;
+  c->part_idx = (int64_t*)p;
+  if (int rc = dev_alloc(c, sizeof(unsigned long long) * cap, &p)) return rc;
+  c->part_ninf = (unsigned long long*)p;
+  if (int rc = dev_alloc(c, sizeof(unsigned long long) * cap, &p)) return rc;
+  c->part_nacc = (unsigned long long*)p;
+  c->parts_cap = cap;
   return MB2_OK;
 }
 
@@ -374,7 +407,14 @@ int mb2_abi_version(void) { return MB2_ABI_VERSION; }
 
 const char* mb2_last_error(void) { return g_err; }
 
-int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset, mb2_ctx** out) {
+int64_t mb2_workspace_bytes(int32_t dim, int64_t* host_bytes) {
+  if (host_bytes) *host_bytes = 4096 + (int64_t)sizeof(double) * dim;
+  // state, best, bounds (x4 rows), partials for 148*32 CTAs, tables for the common costs
+  return 262144 + 64 * (int64_t)dim;
+}
+
+int mb2_create_ws(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset,
+                  void* dev_workspace, int64_t dev_bytes, void* host_workspace, int64_t host_bytes, mb2_ctx** out) {
   if (out == nullptr) return fail(MB2_EINVAL, "out is NULL");
   *out = nullptr;
   if (np_local < 1 || dim < 1 || np_global < np_local || global_offset < 0 || global_offset + np_local > np_global)
@@ -390,53 +430,58 @@ int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int
   c->offset = global_offset;
   c->dim = dim;
   c->dim_pad = (dim + 3) & ~3;
-  cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (dev_workspace != nullptr && dev_bytes > 0) {
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(dev_workspace) + 255) & ~(uintptr_t)255;
+    c->ws_dev = reinterpret_cast<char*>(a);
+    c->ws_dev_cap = (size_t)dev_bytes - (size_t)(a - reinterpret_cast<uintptr_t>(dev_workspace));
+  }
+  if (host_workspace != nullptr && host_bytes > 0) {
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(host_workspace) + 63) & ~(uintptr_t)63;
+    c->ws_host = reinterpret_cast<char*>(a);
+    c->ws_host_cap = (size_t)host_bytes - (size_t)(a - reinterpret_cast<uintptr_t>(host_workspace));
+  }
+  // (cudaGetDeviceProperties costs milliseconds; one attribute is all that is needed)
+  int sms = 0;
+  cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
   if (e != cudaSuccess) {
     delete c;
-    return fail(MB2_ECUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return fail(MB2_ECUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
   }
-  c->sm_count = prop.multiProcessorCount;
-  bool ok = cudaMalloc(&c->best_x, sizeof(double) * dim) == cudaSuccess &&
-            cudaMalloc(&c->st, sizeof(DeviceState)) == cudaSuccess &&
-            cudaMalloc(&c->lo, sizeof(double) * dim) == cudaSuccess &&
-            cudaMalloc(&c->hi, sizeof(double) * dim) == cudaSuccess &&
-            cudaMallocHost(&c->h_st, sizeof(DeviceState)) == cudaSuccess &&
-            cudaMallocHost(&c->h_best_x, sizeof(double) * dim) == cudaSuccess;
-  if (ok) {
+  c->sm_count = sms;
+  void* p = nullptr;
+  int rc = MB2_OK;
+  if (!rc) rc = dev_alloc(c, sizeof(double) * dim, &p), c->best_x = (double*)p;
+  if (!rc) rc = dev_alloc(c, sizeof(DeviceState), &p), c->st = (DeviceState*)p;
+  if (!rc) rc = dev_alloc(c, sizeof(double) * dim, &p), c->lo = (double*)p;
+  if (!rc) rc = dev_alloc(c, sizeof(double) * dim, &p), c->hi = (double*)p;
+  if (!rc) rc = dev_alloc(c, sizeof(double) * dim, &p), c->init_lo = (double*)p;
+  if (!rc) rc = dev_alloc(c, sizeof(double) * dim, &p), c->init_hi = (double*)p;
+  if (!rc) rc = host_alloc(c, sizeof(DeviceState), &p), c->h_st = (DeviceState*)p;
+  if (!rc) rc = host_alloc(c, sizeof(double) * dim, &p), c->h_best_x = (double*)p;
+  if (!rc) rc = ensure_parts(c, 1);
+  if (!rc) {
     DeviceState init = {INFINITY, -1, 0, 0, -1};
-    ok = cudaMemcpy(c->st, &init, sizeof(init), cudaMemcpyHostToDevice) == cudaSuccess &&
-         cudaMemset(c->best_x, 0, sizeof(double) * dim) == cudaSuccess;
+    if (cudaMemcpy(c->st, &init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess ||
+        cudaMemset(c->best_x, 0, sizeof(double) * dim) != cudaSuccess)
+      rc = fail(MB2_ECUDA, "context initialisation failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
-  if (!ok) {
-    const char* msg = cudaGetErrorString(cudaGetLastError());
+  if (rc) {
     mb2_destroy(c);
-    return fail(MB2_ECUDA, "context allocation failed: %s", msg);
+    return rc;
   }
   *out = c;
   return MB2_OK;
 }
 
+int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset, mb2_ctx** out) {
+  return mb2_create_ws(device, np_local, dim, np_global, global_offset, nullptr, 0, nullptr, 0, out);
+}
+
 int mb2_destroy(mb2_ctx* c) {
   if (c == nullptr) return MB2_OK;
   cudaSetDevice(c->device);
-  cudaFree(c->best_x);
-  cudaFree(c->st);
-  cudaFree(c->lo);
-  cudaFree(c->hi);
-  cudaFree(c->cheb_x);
-  cudaFree(c->cheb_vfrag);
-  cudaFree(c->grw_tab);
-  cudaFree(c->pen_type);
-  cudaFree(c->pen_G);
-  cudaFree(c->pen_h);
-  cudaFree(c->pen_k);
-  cudaFree(c->part_e);
-  cudaFree(c->part_idx);
-  cudaFree(c->part_ninf);
-  cudaFree(c->part_nacc);
-  cudaFreeHost(c->h_st);
-  cudaFreeHost(c->h_best_x);
+  for (void* p : c->owned_dev) cudaFree(p);
+  for (void* p : c->owned_host) cudaFreeHost(p);
   delete c;
   return MB2_OK;
 }
@@ -525,9 +570,12 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
       if (sgn) tm = val; else tp = val;
     }
     CUDA_TRY(cudaSetDevice(c->device));
-    cudaFree(c->cheb_x);
-    c->cheb_x = nullptr;
-    CUDA_TRY(cudaMalloc(&c->cheb_x, sizeof(double) * M));
+    if (c->cap_cheb_x < sizeof(double) * M) {
+      void* p = nullptr;
+      if (int rc = dev_alloc(c, sizeof(double) * M, &p)) return rc;
+      c->cheb_x = (double*)p;
+      c->cap_cheb_x = sizeof(double) * M;
+    }
     CUDA_TRY(cudaMemcpy(c->cheb_x, xs.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
     c->cp.cheb_M = M;
     c->cp.cheb_x = c->cheb_x;
@@ -551,9 +599,12 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
             }
             vf[((size_t)t * KS + s) * 32 + lane] = v;
           }
-      cudaFree(c->cheb_vfrag);
-      c->cheb_vfrag = nullptr;
-      CUDA_TRY(cudaMalloc(&c->cheb_vfrag, sizeof(double) * vf.size()));
+      if (c->cap_vfrag < sizeof(double) * vf.size()) {
+        void* p = nullptr;
+        if (int rc = dev_alloc(c, sizeof(double) * vf.size(), &p)) return rc;
+        c->cheb_vfrag = (double*)p;
+        c->cap_vfrag = sizeof(double) * vf.size();
+      }
       CUDA_TRY(cudaMemcpy(c->cheb_vfrag, vf.data(), sizeof(double) * vf.size(), cudaMemcpyHostToDevice));
       c->cp.cheb_vfrag = c->cheb_vfrag;
       c->cp.cheb_ntiles = ntiles;
@@ -570,7 +621,9 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
       tab[i].y = rc;
     }
     CUDA_TRY(cudaSetDevice(c->device));
-    CUDA_TRY(cudaMalloc(&c->grw_tab, sizeof(double2) * c->dim));
+    void* p = nullptr;
+    if (int rc = dev_alloc(c, sizeof(double2) * c->dim, &p)) return rc;
+    c->grw_tab = (double2*)p;
     CUDA_TRY(cudaMemcpy(c->grw_tab, tab.data(), sizeof(double2) * c->dim, cudaMemcpyHostToDevice));
     c->cp.grw_tab = c->grw_tab;
   }
@@ -582,14 +635,12 @@ int mb2_selftest_division(mb2_ctx* c, int64_t n, uint64_t seed, double span, int
   if (c == nullptr || mismatches == nullptr || n < 1) return fail(MB2_EINVAL, "bad argument");
   if (c->grw_tab == nullptr) return fail(MB2_ESTATE, "set the griewangk cost first");
   CUDA_TRY(cudaSetDevice(c->device));
-  unsigned long long* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, sizeof(unsigned long long)));
+  unsigned long long* d = c->part_ninf;  // scratch: not in use between generations
   CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
   selftest_division_kernel<<<c->sm_count * 8, 256>>>(n, (uint32_t)seed, (uint32_t)(seed >> 32), span, c->grw_tab, c->dim, d);
   CUDA_TRY(cudaGetLastError());
   unsigned long long h = 0;
   CUDA_TRY(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
-  cudaFree(d);
   ++c->launches;
   *mismatches = (int64_t)h;
   return MB2_OK;
@@ -600,23 +651,21 @@ int mb2_set_penalty(mb2_ctx* c, int32_t nterms, const int32_t* ptype, const doub
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
   if (nterms < 0) return fail(MB2_EINVAL, "nterms < 0");
   CUDA_TRY(cudaSetDevice(c->device));
-  cudaFree(c->pen_type);
-  cudaFree(c->pen_G);
-  cudaFree(c->pen_h);
-  cudaFree(c->pen_k);
-  c->pen_type = nullptr;
-  c->pen_G = nullptr;
-  c->pen_h = nullptr;
-  c->pen_k = nullptr;
   c->pp = {0, nullptr, nullptr, nullptr, nullptr};
   if (nterms == 0) return MB2_OK;
   if (!ptype || !G || !h || !kscale) return fail(MB2_EINVAL, "penalty arrays are NULL");
   for (int i = 0; i < nterms; ++i)
     if (ptype[i] < 0 || ptype[i] > 3) return fail(MB2_EINVAL, "unknown penalty type %d", ptype[i]);
-  CUDA_TRY(cudaMalloc(&c->pen_type, sizeof(int) * nterms));
-  CUDA_TRY(cudaMalloc(&c->pen_G, sizeof(double) * nterms * c->dim));
-  CUDA_TRY(cudaMalloc(&c->pen_h, sizeof(double) * nterms));
-  CUDA_TRY(cudaMalloc(&c->pen_k, sizeof(double) * nterms));
+  const size_t pen_bytes = ((sizeof(int) * nterms + 255) & ~(size_t)255) + sizeof(double) * nterms * (c->dim + 2);
+  if (c->cap_pen < pen_bytes) {
+    void* p = nullptr;
+    if (int rc = dev_alloc(c, pen_bytes, &p)) return rc;
+    c->pen_type = (int*)p;
+    c->cap_pen = pen_bytes;
+  }
+  c->pen_G = reinterpret_cast<double*>(reinterpret_cast<char*>(c->pen_type) + ((sizeof(int) * nterms + 255) & ~(size_t)255));
+  c->pen_h = c->pen_G + (size_t)nterms * c->dim;
+  c->pen_k = c->pen_h + nterms;
   CUDA_TRY(cudaMemcpy(c->pen_type, ptype, sizeof(int) * nterms, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->pen_G, G, sizeof(double) * nterms * c->dim, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->pen_h, h, sizeof(double) * nterms, cudaMemcpyHostToDevice));
@@ -655,9 +704,7 @@ int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const doubl
   if (!lo || !hi) return fail(MB2_EINVAL, "init bounds are NULL");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
-  double *dlo = nullptr, *dhi = nullptr;
-  CUDA_TRY(cudaMalloc(&dlo, sizeof(double) * c->dim));
-  CUDA_TRY(cudaMalloc(&dhi, sizeof(double) * c->dim));
+  double *dlo = c->init_lo, *dhi = c->init_hi;
   CUDA_TRY(cudaMemcpyAsync(dlo, lo, sizeof(double) * c->dim, cudaMemcpyHostToDevice, s));
   CUDA_TRY(cudaMemcpyAsync(dhi, hi, sizeof(double) * c->dim, cudaMemcpyHostToDevice, s));
   const int64_t total = c->np * ((c->dim + 1) / 2);
@@ -668,9 +715,7 @@ int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const doubl
                                                            dhi, (uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32));
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
-  CUDA_TRY(cudaStreamSynchronize(s));  // lo/hi are pageable host buffers and dlo/dhi are freed here
-  cudaFree(dlo);
-  cudaFree(dhi);
+  CUDA_TRY(cudaStreamSynchronize(s));  // lo/hi are pageable host buffers
   c->generation = -1;
   return MB2_OK;
 }

@@ -35,9 +35,15 @@ class DeviceEngine(object):
         f64 = dict(dtype=torch.float64, device=self.device)
         self._pop = [torch.empty((self.np_local, self.dim), **f64) for _ in range(2)]
         self._en = [torch.full((self.np_local,), float('inf'), **f64) for _ in range(2)]
+        # the context's small buffers live in workspaces owned by torch's caching allocators
+        hb = ctypes.c_int64(0)
+        db = int(lib.mb2_workspace_bytes(self.dim, ctypes.byref(hb)))
+        self._ws_dev = torch.empty((db,), dtype=torch.uint8, device=self.device)
+        self._ws_host = torch.empty((hb.value,), dtype=torch.uint8, pin_memory=True)
         self._ctx = ctypes.c_void_p()
-        check(lib.mb2_create(self.device.index, self.np_local, self.dim, self.np_global, self.offset,
-                             ctypes.byref(self._ctx)))
+        check(lib.mb2_create_ws(self.device.index, self.np_local, self.dim, self.np_global, self.offset,
+                                self._ws_dev.data_ptr(), db, self._ws_host.data_ptr(), hb.value,
+                                ctypes.byref(self._ctx)))
         check(lib.mb2_bind_buffers(self._ctx, self._pop[0].data_ptr(), self._pop[1].data_ptr(),
                                    self._en[0].data_ptr(), self._en[1].data_ptr()))
         self._trial = self._trial_e = None
