@@ -314,15 +314,19 @@ def main():
         t0 = time.perf_counter()
         s2.SetPopulation(hp, local=True)         # this rank's rows; pinned, uploaded as is
         s2.Step(cost, ExtraArgs=extra)           # H2D upload + generation 0
+        t1 = time.perf_counter()
         for _ in range(steps):
             s2.Step()                            # K generations, result read back every step
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if os.environ.get('MB2_BENCH_DEBUG'):
+            print('e2e: upload + generation 0 %.2f ms, %d steps %.2f ms' % ((t1 - t0) * 1e3, steps, (t0 + dt - t1) * 1e3),
+                  file=sys.stderr)
         del s2
         return dt
 
     e2e_run()                                    # warm-up: device allocations come from torch's cache afterwards
-    e2e_s = e2e_run()
+    e2e_s = min(e2e_run(), e2e_run())            # best of two (host-side jitter: PCIe, page faults)
     t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
