@@ -311,14 +311,15 @@ def main():
         s2 = build_solver(w, NP_global, distributed, seed)
         s2.SetTermination(never)
         barrier()
+        s2.SetEvaluationLimits(generations=steps, evaluations=10 ** 18)
         t0 = time.perf_counter()
         s2.SetPopulation(hp, local=True)         # this rank's rows; pinned, uploaded as is
         s2.Step(cost, ExtraArgs=extra)           # H2D upload + generation 0
         t1 = time.perf_counter()
-        for _ in range(steps):
-            s2.Step()                            # K generations, result read back every step
-        torch.cuda.synchronize()
+        s2.Solve()                               # the user's call: K generations until the generation limit;
+        torch.cuda.synchronize()                 # every generation's (bestEnergy, counters, bestSolution) reaches the host
         dt = time.perf_counter() - t0
+        assert s2.generations == steps, (s2.generations, steps)
         if os.environ.get('MB2_BENCH_DEBUG'):
             print('e2e: upload + generation 0 %.2f ms, %d steps %.2f ms' % ((t1 - t0) * 1e3, steps, (t0 + dt - t1) * 1e3),
                   file=sys.stderr)
@@ -374,8 +375,9 @@ def main():
         'roofline': roofline,
         'e2e': {'value': NP_global * steps / e2e_s, 'unit': 'candidate-evals/s',
                 'h2d_bytes_per_step': h2d_per_step, 'd2h_bytes_per_step': d2h_per_step,
-                'what': 'pinned host population -> H2D -> generation 0 -> %d x solver.Step() (best read back to the '
-                        'host, termination + monitor every step); only the %d generations are counted' % (steps, steps)},
+                'what': 'pinned host population -> H2D -> generation 0 -> solver.Solve() for %d generations (every '
+                        'generation\'s best energy, counters and bestSolution read back to the host, termination + '
+                        'monitor per generation); only the %d generations are counted' % (steps, steps)},
         'gpu_launches': int(launches),
         'clocks': clocks,
     }

@@ -158,6 +158,35 @@ int mb2_eval_initial(mb2_ctx* ctx, void* stream);
  * penalty, selection and generation best (:603-613) in ONE fused kernel + a 1-CTA argmin */
 int mb2_step(mb2_ctx* ctx, void* stream);
 
+/* Device-resident multi-generation stepping.  `Solve` in the reference returns to the host after
+ * every generation to evaluate the termination condition (abstract_solver.py:1134-1148); the
+ * conditions that only read the energy history and the counters are evaluated here by the argmin
+ * epilogue instead, so a batch of generations runs without a host round trip and stops exactly
+ * where the reference would.  kinds: 0 none, 1 VTR (termination.py:181-196), 2 ChangeOverGeneration
+ * (:198-217), 3 NormalizedChangeOverGeneration (:219-240), 4 VTRChangeOverGeneration (:320-342),
+ * 5 EvaluationLimits (:386-408); max_* are the solver's own limits (abstract_solver.py:703-711),
+ * negative = none. */
+typedef struct mb2_termination {
+  int32_t kind;
+  int32_t lookback;          /* the condition's `generations` argument */
+  double tolerance;          /* VTR tolerance / COG, NCOG tolerance / VTRCOG ftol */
+  double target;
+  double gtol;               /* VTRCOG only */
+  int64_t term_generations;  /* EvaluationLimits condition */
+  int64_t term_evaluations;
+  int64_t max_generations;   /* solver._maxiter */
+  int64_t max_evaluations;   /* solver._maxfun */
+  int64_t generations;       /* solver.generations so far */
+  int64_t evaluations;       /* solver.evaluations so far */
+} mb2_termination;
+/* install the condition and seed the device-side energy history (solver.energy_history) */
+int mb2_set_termination(mb2_ctx* ctx, const mb2_termination* t, const double* history_host, int64_t history_len);
+/* enqueue up to max_steps generations; each appends [best_energy, best_index, n_inf, n_accepted,
+ * bestSolution[dim]] to log_dev [max_steps, dim+4]; generations after the stop are no-ops */
+int mb2_run(mb2_ctx* ctx, int32_t max_steps, double* log_dev, void* stream);
+/* synchronise; number of generations actually executed and whether a condition stopped the batch */
+int mb2_run_result(mb2_ctx* ctx, int32_t* executed, int32_t* stopped, void* stream);
+
 /* multi-GPU best exchange (Best and RandToBest strategies read the global best,
  * strategy.py:52,83,137,164,247,274): pack this shard's [best_energy, best_index(global),
  * n_inf, n_accepted, bestSolution[dim]] (dim+4 doubles) for an all-gather, then merge the

@@ -15,6 +15,7 @@ EXPORTS = [
     'mb2_set_rng_replay', 'mb2_init_population', 'mb2_upload_population', 'mb2_set_capture',
     'mb2_eval_initial', 'mb2_step', 'mb2_pack_best', 'mb2_merge_best', 'mb2_read_result', 'mb2_eval_cost',
     'mb2_launch_info', 'mb2_launch_count', 'mb2_selftest_division', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
+    'mb2_set_termination', 'mb2_run', 'mb2_run_result',
 ]
 
 
@@ -22,6 +23,14 @@ class Result(ctypes.Structure):
     """struct mb2_result"""
     _fields_ = [('best_energy', ctypes.c_double), ('best_index', ctypes.c_int64), ('n_inf', ctypes.c_int64),
                 ('n_accepted', ctypes.c_int64), ('generation', ctypes.c_int64)]
+
+
+class Termination(ctypes.Structure):
+    """struct mb2_termination"""
+    _fields_ = [('kind', ctypes.c_int32), ('lookback', ctypes.c_int32), ('tolerance', ctypes.c_double),
+                ('target', ctypes.c_double), ('gtol', ctypes.c_double), ('term_generations', ctypes.c_int64),
+                ('term_evaluations', ctypes.c_int64), ('max_generations', ctypes.c_int64),
+                ('max_evaluations', ctypes.c_int64), ('generations', ctypes.c_int64), ('evaluations', ctypes.c_int64)]
 
 
 class NativeError(RuntimeError):
@@ -63,6 +72,9 @@ def _load():
         'mb2_launch_count': (i64, [vp]),
         'mb2_selftest_division': (ctypes.c_int, [vp, i64, u64, dbl, c_int64_p]),
         'mb2_restore_state': (ctypes.c_int, [vp, c_double_p, dbl, i64, c_double_p, i64]),
+        'mb2_set_termination': (ctypes.c_int, [vp, ctypes.POINTER(Termination), c_double_p, i64]),
+        'mb2_run': (ctypes.c_int, [vp, i32, vp, vp]),
+        'mb2_run_result': (ctypes.c_int, [vp, c_int32_p, c_int32_p, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it

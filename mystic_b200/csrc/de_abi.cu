@@ -4,6 +4,7 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -117,6 +118,13 @@ struct mb2_ctx {
   size_t cap_cheb_x = 0, cap_vfrag = 0, cap_pen = 0;
   double* init_lo = nullptr;
   double* init_hi = nullptr;
+  // batch mode (mb2_run): device-resident termination state, its host description and mirror
+  RunState* run = nullptr;
+  RunState* h_run = nullptr;  // pinned
+  int run_active = 0;         // launches carry the stop flag / run state
+  int run_cur0 = 0;
+  int64_t run_gen0 = 0;
+  int run_enqueued = 0;
 };
 
 namespace {
@@ -373,6 +381,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   P.part_nacc = c->part_nacc;
   P.cap_trial = c->cap_trial;
   P.cap_energy = c->cap_energy;
+  P.stop = (c->run_active && mode == MODE_STEP) ? &c->run->stop : nullptr;
 
   c->wpc = wpc;
   c->grid = (int)grid;
@@ -393,7 +402,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
 int launch_finalize(mb2_ctx* c, int gen0, cudaStream_t stream) {
   de_finalize_kernel<<<1, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
                                             c->pop[c->cur ^ 1], c->dim, c->offset, gen0, c->generation + 1,
-                                            c->best_x, c->st);
+                                            c->best_x, c->st, (c->run_active && !gen0) ? c->run : nullptr);
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
   return MB2_OK;
@@ -773,6 +782,90 @@ int mb2_step(mb2_ctx* c, void* stream) {
   c->cur ^= 1;
   c->generation += 1;
   c->replay = 0;  // recorded draws are consumed by exactly one generation
+  return MB2_OK;
+}
+
+int mb2_set_termination(mb2_ctx* c, const mb2_termination* t, const double* history_host, int64_t history_len) {
+  if (c == nullptr || t == nullptr) return fail(MB2_EINVAL, "NULL argument");
+  if (t->kind < TERM_NONE || t->kind > TERM_LIMITS) return fail(MB2_EINVAL, "unknown termination kind %d", t->kind);
+  if (t->lookback < 0 || t->lookback >= kHistMax) return fail(MB2_EINVAL, "lookback must be in [0, %d)", kHistMax);
+  if (history_len < 0 || (history_len > 0 && history_host == nullptr)) return fail(MB2_EINVAL, "bad history");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (c->run == nullptr) {
+    void* p = nullptr;
+    if (int rc = dev_alloc(c, sizeof(RunState), &p)) return rc;
+    c->run = (RunState*)p;
+    if (int rc = host_alloc(c, sizeof(RunState), &p)) return rc;
+    c->h_run = (RunState*)p;
+  }
+  RunState* r = c->h_run;
+  memset(r, 0, sizeof(RunState));
+  r->kind = t->kind;
+  r->lookback = t->lookback;
+  r->tol = t->tolerance;
+  r->target = t->target;
+  r->gtol = t->gtol;
+  r->term_generations = t->term_generations;
+  r->term_evaluations = t->term_evaluations;
+  r->max_generations = t->max_generations;
+  r->max_evaluations = t->max_evaluations;
+  r->generations = t->generations;
+  r->evaluations = t->evaluations;
+  r->np_eval = c->np_global;
+  r->hist_count = history_len;
+  if (history_len > 0) {
+    r->hist0 = history_host[0];
+    const int64_t first = history_len > kHistMax ? history_len - kHistMax : 0;
+    for (int64_t i = first; i < history_len; ++i) r->hist[i % kHistMax] = history_host[i];
+  }
+  CUDA_TRY(cudaMemcpy(c->run, r, sizeof(RunState), cudaMemcpyHostToDevice));
+  return MB2_OK;
+}
+
+int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
+  if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
+  if (c->run == nullptr) return fail(MB2_ESTATE, "mb2_set_termination must run before mb2_run");
+  if (c->generation < 0) return fail(MB2_ESTATE, "mb2_eval_initial must run before mb2_run");
+  if (max_steps < 1 || log_dev == nullptr) return fail(MB2_EINVAL, "bad argument");
+  if (c->replay) return fail(MB2_EINVAL, "batch stepping needs the Philox generator (replayed draws are per generation)");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // arm the log for this batch (stream ordered: the previous batch has been read back by mb2_run_result)
+  struct { long long count, cap; double* log; } arm = {0, max_steps, log_dev};
+  CUDA_TRY(cudaMemcpyAsync(&c->run->log_count, &arm, sizeof(arm), cudaMemcpyHostToDevice, s));
+  c->run_active = 1;
+  c->run_cur0 = c->cur;
+  c->run_gen0 = c->generation;
+  c->run_enqueued = max_steps;
+  int rc = MB2_OK;
+  for (int k = 0; k < max_steps && rc == MB2_OK; ++k) {
+    rc = launch_step(c, MODE_STEP, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s);
+    if (rc == MB2_OK) rc = launch_finalize(c, 0, s);
+    if (rc == MB2_OK) {
+      c->cur ^= 1;
+      c->generation += 1;
+    }
+  }
+  c->run_active = 0;
+  return rc;
+}
+
+int mb2_run_result(mb2_ctx* c, int32_t* executed, int32_t* stopped, void* stream) {
+  if (c == nullptr || c->run == nullptr || executed == nullptr || stopped == nullptr) return fail(MB2_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(c->h_run, c->run, offsetof(RunState, hist0), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const int done = (int)c->h_run->log_count;
+  *executed = done;
+  *stopped = (c->h_run->stop == 1) ? 1 : 0;
+  // generations after the stop were no-ops: put the double buffer and the counter where the device is
+  c->cur = c->run_cur0 ^ (done & 1);
+  c->generation = c->run_gen0 + done;
+  if (c->h_run->stop == 2) {  // log full without a termination: clear the flag for the next batch
+    int zero = 0;
+    CUDA_TRY(cudaMemcpy(&c->run->stop, &zero, sizeof(int), cudaMemcpyHostToDevice));
+  }
   return MB2_OK;
 }
 

@@ -34,6 +34,7 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 template <int KS>  // k-steps of 4 coefficients: 1 (order <= 4), 2 (order <= 8), 4 (order <= 16)
 __global__ void __launch_bounds__(kChebWarps * 32)
     de_step_cheb_mma_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
+  if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(16) double smem[];
   __shared__ double sh_e[kChebWarps];
   __shared__ int64_t sh_i[kChebWarps];

@@ -19,7 +19,33 @@ enum : int { BOUNDS_NONE = 0, BOUNDS_REJECT = 1, BOUNDS_CLAMP = 2 };
 
 constexpr int kWarpsPerCtaMax = 8;
 
+// Device-resident multi-generation stepping: the termination conditions that
+// only read the energy history and the counters (mystic/termination.py:181-240, 320-342, 386-408,
+// and the solver's own limits, abstract_solver.py:703-711) are evaluated by the finalize kernel;
+// once one is met `stop` is raised and every later launch of the batch returns immediately.
+constexpr int kHistMax = 1024;
+enum : int { TERM_NONE = 0, TERM_VTR = 1, TERM_COG = 2, TERM_NCOG = 3, TERM_VTRCOG = 4, TERM_LIMITS = 5 };
+
+struct RunState {
+  int stop;
+  int kind;
+  int lookback;  // "generations" argument of the condition
+  int pad_;
+  double tol, target, gtol;
+  long long term_generations, term_evaluations;  // EvaluationLimits condition (<0: none)
+  long long max_generations, max_evaluations;    // solver._maxiter / _maxfun (<0: none)
+  long long generations;                         // solver.generations
+  long long evaluations;                         // solver._fcalls[0]
+  long long np_eval;                             // evaluations per generation before skipping inf
+  long long hist_count;                          // len(energy_history)
+  long long log_count, log_cap;
+  double* log;                                   // [log_cap, D+4]: best_e, best_idx, n_inf, n_acc, x[D]
+  double hist0;                                  // energy_history[0] (python hist[-0])
+  double hist[kHistMax];                         // ring of the last energies
+};
+
 struct StepParams {
+  const int* stop;  // non-null in batch mode: return at once when *stop != 0
   // population (double buffered) and energies
   const double* pop_cur;
   double* pop_next;
@@ -113,6 +139,7 @@ __device__ __forceinline__ int exp_length_philox(uint32_t k0, uint32_t k1, uint3
 template <int BASE, int XOVER, int COST, bool VEC>
 __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
     de_step_kernel(const __grid_constant__ StepParams P) {
+  if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(16) double smem[];
   constexpr int K = NumDonors<BASE>::value;
   constexpr bool kNeedsBest = (BASE == BASE_BEST1 || BASE == BASE_RANDTOBEST1 || BASE == BASE_BEST2);
@@ -345,7 +372,9 @@ __global__ void __launch_bounds__(256)
                        const unsigned long long* __restrict__ part_ninf,
                        const unsigned long long* __restrict__ part_nacc, int nparts,
                        const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
-                       int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st) {
+                       int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
+                       RunState* __restrict__ rs) {
+  if (rs != nullptr && rs->stop) return;  // batch mode: this generation was not run
   __shared__ double sh_e[256];
   __shared__ int64_t sh_i[256];
   __shared__ unsigned long long sh_a[256], sh_b[256];
@@ -404,6 +433,59 @@ __global__ void __launch_bounds__(256)
   if (w != -1) {
     const double* src = pop_next + (w == -2 ? 0 : w) * D;
     for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = src[i];
+  }
+  if (rs == nullptr) return;
+  __syncthreads();
+  // ---- batch mode: log the generation, then the host part of Step(): counters and termination
+  const long long slot = rs->log_count;
+  if (slot < rs->log_cap) {
+    double* rec = rs->log + slot * (D + 4);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) rec[4 + i] = best_x[i];
+    if (threadIdx.x == 0) {
+      rec[0] = st->best_e;
+      rec[1] = (double)st->best_idx;
+      rec[2] = (double)st->n_inf;
+      rec[3] = (double)st->n_acc;
+    }
+  }
+  if (threadIdx.x == 0) {
+    rs->log_count = slot + 1;
+    rs->evaluations += rs->np_eval - st->n_inf;        // differential_evolution.py:601
+    rs->generations += 1;
+    const double e = st->best_e;                        // stepmon(bestSolution, bestEnergy) (:617)
+    if (rs->hist_count == 0) rs->hist0 = e;
+    rs->hist[rs->hist_count % kHistMax] = e;
+    rs->hist_count += 1;
+    const long long lg = rs->hist_count;
+    const int g = rs->lookback;
+    // python hist[-g]: g == 0 addresses hist[0]
+    const double hg = (g == 0) ? rs->hist0 : rs->hist[(lg - g + (long long)kHistMax * 4) % kHistMax];
+    const double h1 = e;
+    bool met = false;
+    switch (rs->kind) {
+      case TERM_VTR:  // termination.py:181-196
+        met = fabs(h1 - rs->target) <= rs->tol;
+        break;
+      case TERM_COG:  // termination.py:198-217
+        met = (lg > g) && ((hg - h1) <= rs->tol || hg == h1);
+        break;
+      case TERM_NCOG:  // termination.py:219-240
+        met = (lg > g) && (hg == h1 || 2.0 * (hg - h1) <= rs->tol * (fabs(hg) + fabs(h1)) + 1e-20);
+        break;
+      case TERM_VTRCOG:  // termination.py:320-342
+        met = ((lg > g) && ((hg - h1) <= rs->gtol || hg == h1)) || (fabs(h1 - rs->target) <= rs->tol);
+        break;
+      case TERM_LIMITS:  // termination.py:386-408
+        met = (rs->term_evaluations >= 0 && rs->evaluations >= rs->term_evaluations) ||
+              (rs->term_generations >= 0 && rs->generations >= rs->term_generations);
+        break;
+      default:
+        break;
+    }
+    // the solver's own limits (abstract_solver.py:703-711)
+    if (rs->max_evaluations >= 0 && rs->evaluations >= rs->max_evaluations) met = true;
+    if (rs->max_generations >= 0 && rs->generations >= rs->max_generations) met = true;
+    if (met || rs->log_count >= rs->log_cap) rs->stop = met ? 1 : 2;  // 2: log full (cannot happen: one batch = log_cap launches)
   }
 }
 

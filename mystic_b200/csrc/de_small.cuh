@@ -151,6 +151,7 @@ __device__ __forceinline__ double thread_penalty(const double* x, int D, const P
 template <int COST>
 __global__ void __launch_bounds__(kSmallWarps * 32)
     de_step_small_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
+  if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(16) double smem[];
   __shared__ double sh_e[kSmallWarps];
   __shared__ int64_t sh_i[kSmallWarps];

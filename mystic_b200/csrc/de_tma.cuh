@@ -77,6 +77,7 @@ __device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int 
 template <int COST, int GW, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
     de_step_best1bin_tma_kernel(const __grid_constant__ StepParams P, int stages) {
+  if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[kTmaMaxGroups * kTmaMaxStages];
   __shared__ double s_scratch[kTmaMaxGroups * 16];

@@ -52,6 +52,7 @@ class DeviceEngine(object):
             self._trial_e = torch.full((self.np_local,), float('inf'), **f64)
             check(lib.mb2_set_capture(self._ctx, self._trial.data_ptr(), self._trial_e.data_ptr()))
         self._replay = None  # keeps the uploaded draw tensors alive until consumed
+        self._log = self._log_host = None  # batch-mode generation log
         self._record = torch.empty((self.dim + 4,), **f64)
         self._xbuf = np.empty(self.dim, dtype=np.float64)
 
@@ -158,6 +159,36 @@ class DeviceEngine(object):
 
     def step(self):
         check(lib.mb2_step(self._ctx, self._stream()))
+
+    # ---- device-resident multi-generation stepping -----------------------------------------
+    def run(self, max_steps, term, history, generations, evaluations, max_generations, max_evaluations):
+        """Enqueue up to max_steps generations with the termination test on the device; returns
+        (records [executed, dim+4], stopped).  `term` = dict(kind, lookback, tolerance, target, gtol,
+        term_generations, term_evaluations) as produced by mystic_b200.termination.device_descriptor."""
+        t = _native.Termination()
+        t.kind, t.lookback = int(term['kind']), int(term.get('lookback', 0))
+        t.tolerance, t.target, t.gtol = float(term.get('tolerance', 0.0)), float(term.get('target', 0.0)), float(term.get('gtol', 0.0))
+        t.term_generations = int(term.get('term_generations', -1))
+        t.term_evaluations = int(term.get('term_evaluations', -1))
+        t.max_generations = -1 if max_generations is None else int(max_generations)
+        t.max_evaluations = -1 if max_evaluations is None else int(max_evaluations)
+        t.generations, t.evaluations = int(generations), int(evaluations)
+        tail = np.ascontiguousarray(history[-1024:] if len(history) > 1024 else history, dtype=np.float64)
+        if len(history) > 1024:
+            # the device ring is indexed by absolute position: hand over the full length with the tail
+            full = np.empty(len(history), dtype=np.float64)
+            full[:] = history
+            tail = full
+        check(lib.mb2_set_termination(self._ctx, ctypes.byref(t), _dptr(tail) if tail.size else None, int(tail.size)))
+        if self._log is None or self._log.shape[0] < max_steps:
+            self._log = torch.empty((max_steps, self.dim + 4), dtype=torch.float64, device=self.device)
+            self._log_host = torch.empty((max_steps, self.dim + 4), dtype=torch.float64, pin_memory=True)
+        check(lib.mb2_run(self._ctx, int(max_steps), self._log.data_ptr(), self._stream()))
+        done, stopped = ctypes.c_int32(0), ctypes.c_int32(0)
+        check(lib.mb2_run_result(self._ctx, ctypes.byref(done), ctypes.byref(stopped), self._stream()))
+        n = done.value
+        self._log_host[:n].copy_(self._log[:n])
+        return self._log_host[:n].numpy().copy(), bool(stopped.value)
 
     def pack_best(self):
         check(lib.mb2_pack_best(self._ctx, self._record.data_ptr(), self._stream()))

@@ -815,11 +815,59 @@ class DifferentialEvolutionSolver2(object):
         return msg
 
     def _Solve(self, cost, ExtraArgs, **settings):
-        """abstract_solver.py:1151-1180 (collapse machinery is out of scope)"""
+        """abstract_solver.py:1151-1180 (collapse machinery is out of scope).  When nothing needs the
+        host between generations (no callback, no restart files, device-side RNG, a termination the
+        device can evaluate) generations run in batches with the termination test inside the
+        argmin epilogue; the monitor and the counters are then replayed from the batch log, and the
+        solver stops exactly where step-by-step execution would."""
         stop = False
         while not stop:
-            stop = self.Step(**settings)
+            desc = self._batch_descriptor(settings)
+            if desc is None:
+                stop = self.Step(**settings)
+            else:
+                stop = self._run_batch(desc, settings)
         return
+
+    _batch_generations = 64
+
+    def _batch_descriptor(self, settings):
+        if not self._batch_generations or not len(self._stepmon) or not self._live:
+            return None                       # generation 0 and (re)decoration go through Step()
+        if self._rng != 'philox' or self._distributed or self._saveiter or self._EARLYEXIT:
+            return None
+        if settings.get('callback') is not None or settings.get('disp'):
+            return None
+        if not hasattr(self._engine, 'run'):
+            return None
+        return _termination.device_descriptor(self._termination)
+
+    def _run_batch(self, desc, settings):
+        """Step() for up to `_batch_generations` generations without a host round trip."""
+        msg = self.Terminated(info=True) or None          # Step() checks before stepping (:1134)
+        if msg is None:
+            step_settings = self._process_inputs(settings)
+            (sid, k, _), name = _strategy.strategy_id(step_settings['strategy'])
+            if self._np_local < k + 1:
+                raise ValueError('Sample larger than population or is negative')
+            self._engine.set_strategy(sid, self.scale, self.probability)
+            self._SetEvaluationLimits()
+            records, _stopped = self._engine.run(self._batch_generations, desc, list(self.energy_history),
+                                                 self.generations, self._fcalls[0], self._maxiter, self._maxfun)
+            D = self.nDim
+            for rec in records:
+                self._fcalls[0] += self.nPop - int(rec[2])
+                self._last = (int(rec[2]), int(rec[3]), int(rec[1]))
+                self.bestEnergy = float(rec[0])
+                self.bestSolution = rec[4:4 + D].copy()
+                self._stepmon(self.bestSolution[:], self.bestEnergy, self.id)
+            if self.Terminated():
+                self.Finalize()
+            msg = self.Terminated(info=True) or None
+            if msg:
+                self._stepmon.info('STOP("%s")' % msg)
+                self._save_state(force=True)
+        return msg
 
     def Solve(self, cost=None, termination=None, ExtraArgs=None, **kwds):
         """differential_evolution.py:695-721 -> abstract_solver.py:1182-1229"""

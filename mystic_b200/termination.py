@@ -264,3 +264,41 @@ def state(condition):
         elif ' with ' in doc:
             out[doc] = eval(doc.split(' with ', 1)[1], {'inf': inf, 'nan': float('nan')})
     return out
+
+
+_DEVICE_KINDS = {'VTR': 1, 'ChangeOverGeneration': 2, 'NormalizedChangeOverGeneration': 3,
+                 'VTRChangeOverGeneration': 4, 'EvaluationLimits': 5}
+
+
+def device_descriptor(condition):
+    """Describe a condition for the device-side check of the batched generation loop
+    (mb2_set_termination), or None when it cannot run there (compound conditions, conditions that
+    read the population, time limits, user callables).  Works for these factories and for the
+    unmodified mystic.termination ones alike: both carry "<Name> with {kwds}" in __doc__."""
+    if isinstance(condition, tuple):
+        return None
+    doc = getattr(condition, '__doc__', None)
+    if not doc or ' with ' not in doc:
+        return None
+    name, kw = doc.split(' with ', 1)
+    if name not in _DEVICE_KINDS:
+        return None
+    try:
+        kw = eval(kw, {'inf': inf, 'nan': float('nan')})
+    except Exception:
+        return None
+    d = dict(kind=_DEVICE_KINDS[name], lookback=0, tolerance=0.0, target=0.0, gtol=0.0,
+             term_generations=-1, term_evaluations=-1)
+    if name == 'VTR':
+        d.update(tolerance=kw['tolerance'], target=kw['target'])
+    elif name in ('ChangeOverGeneration', 'NormalizedChangeOverGeneration'):
+        d.update(tolerance=kw['tolerance'], lookback=_lookback(kw['generations']))
+    elif name == 'VTRChangeOverGeneration':
+        d.update(tolerance=kw['ftol'], gtol=kw['gtol'], target=kw['target'], lookback=_lookback(kw['generations']))
+    else:
+        g, e = kw['generations'], kw['evaluations']
+        d.update(term_generations=-1 if g is None or g == inf else int(g),
+                 term_evaluations=-1 if e is None or e == inf else int(e))
+    if not (0 <= d['lookback'] < 1024):
+        return None
+    return d

@@ -116,6 +116,45 @@ class OracleEngine(object):
                      philox=dict(seed=self.seed, offset=self.offset))
         self._after()
 
+    def run(self, max_steps, term, history, generations, evaluations, max_generations, max_evaluations):
+        """CPU twin of DeviceEngine.run: same termination rules as de_finalize_kernel"""
+        hist = list(history)
+        gens, evals = int(generations), int(evaluations)
+        recs = []
+        stopped = False
+        g = int(term.get('lookback', 0))
+        for _ in range(max_steps):
+            self.step()
+            st = self.state
+            recs.append(np.concatenate([[st.bestEnergy, float(self.best_idx), float(self.n_inf), float(self.n_acc)],
+                                        st.bestSolution]))
+            evals += self.np_global - self.n_inf
+            gens += 1
+            hist.append(st.bestEnergy)
+            lg, h1 = len(hist), hist[-1]
+            hg = (hist[-g] if g else hist[0]) if lg > g else h1
+            kind = term['kind']
+            met = False
+            if kind == 1:
+                met = abs(h1 - term['target']) <= term['tolerance']
+            elif kind == 2:
+                met = lg > g and ((hg - h1) <= term['tolerance'] or hg == h1)
+            elif kind == 3:
+                met = lg > g and (hg == h1 or 2.0 * (hg - h1) <= term['tolerance'] * (abs(hg) + abs(h1)) + 1e-20)
+            elif kind == 4:
+                met = (lg > g and ((hg - h1) <= term['gtol'] or hg == h1)) or abs(h1 - term['target']) <= term['tolerance']
+            elif kind == 5:
+                met = (term['term_evaluations'] >= 0 and evals >= term['term_evaluations']) or \
+                      (term['term_generations'] >= 0 and gens >= term['term_generations'])
+            if max_evaluations is not None and evals >= max_evaluations:
+                met = True
+            if max_generations is not None and gens >= max_generations:
+                met = True
+            if met:
+                stopped = True
+                break
+        return np.array(recs).reshape(len(recs), self.dim + 4), stopped
+
     def pack_best(self):
         st = self.state
         rec = np.concatenate([[st.bestEnergy, float(self.best_idx), float(self.n_inf), float(self.n_acc)],

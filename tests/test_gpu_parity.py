@@ -464,3 +464,28 @@ def test_full_size_properties(name):
         finals.append((pop.clone(), prev[0]))
         eng.close()
     assert torch.equal(finals[0][0], finals[1][0]) and finals[0][1] == finals[1][1]
+
+
+@pytest.mark.parametrize('term', [('VTR', 1e-2), ('ChangeOverGeneration', 1e-3, 5), ('VTRChangeOverGeneration', 1e-3, 1e-4, 6),
+                                  ('NormalizedChangeOverGeneration', 1e-2, 4), ('EvaluationLimits', 37, None)])
+@pytest.mark.parametrize('shape', [(3, 20, 'Best1Exp', 'rosen'), (256, 64, 'Best1Bin', 'griewangk')])
+def test_batched_solve_on_device_stops_exactly_like_step_by_step(term, shape):
+    """device-side termination test (de_finalize_kernel, batch mode) against step-by-step Solve()"""
+    from mystic_b200 import DifferentialEvolutionSolver2, models, termination
+    D, NP, strat, cost = shape
+
+    def make(batch):
+        s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=4242, strategy=strat)
+        s._batch_generations = batch
+        s.SetRandomInitialPoints([0.] * D, [2.] * D)
+        s.SetEvaluationLimits(generations=150, evaluations=150 * NP)
+        s.Solve(getattr(models, cost), getattr(termination, term[0])(*term[1:]))
+        return s
+    a, b, c = make(0), make(7), make(64)
+    for s in (b, c):
+        assert s.generations == a.generations and s.evaluations == a.evaluations
+        assert list(s.energy_history) == list(a.energy_history)
+        assert s.Terminated(info=True) == a.Terminated(info=True)
+        assert np.array_equal(s.population, a.population)
+        assert np.array_equal(s.popEnergy, a.popEnergy)
+        assert [list(x) for x in s.solution_history] == [list(x) for x in a.solution_history]

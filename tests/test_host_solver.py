@@ -220,3 +220,26 @@ def test_save_and_load_solver_resumes_identically(tmp_path):
     G.assert_bits_equal(a.population, b.population, 'population after resume')
     G.assert_bits_equal(np.array(a.bestSolution), np.array(b.bestSolution), 'bestSolution after resume')
     assert a.evaluations == b.evaluations
+
+
+@pytest.mark.parametrize('term', [('VTR', 1e-2), ('ChangeOverGeneration', 1e-3, 5), ('NormalizedChangeOverGeneration', 1e-2, 4),
+                                  ('VTRChangeOverGeneration', 1e-3, 1e-4, 6), ('EvaluationLimits', 37, None),
+                                  ('EvaluationLimits', None, 900), ('ChangeOverGeneration', 1e-30, 0)])
+def test_batched_solve_stops_exactly_like_step_by_step(term):
+    """Solve() with the device-side termination test (batches of generations) against the
+    same solve executed one Step() at a time: same stop generation, message, histories, counters"""
+    def make(batch):
+        s = DifferentialEvolutionSolver2(3, 20, rng='philox', seed=4242, engine=OracleEngine, strategy='Best1Exp')
+        s._batch_generations = batch
+        s.SetRandomInitialPoints([0.] * 3, [2.] * 3)
+        s.SetEvaluationLimits(generations=150, evaluations=2500)
+        s.Solve(models.rosen, getattr(termination, term[0])(*term[1:]))
+        return s
+    a, b, c = make(0), make(7), make(64)
+    for s in (b, c):
+        assert s.generations == a.generations and s.evaluations == a.evaluations
+        assert list(s.energy_history) == list(a.energy_history)
+        assert s.Terminated(info=True) == a.Terminated(info=True)
+        G.assert_bits_equal(s.population, a.population, 'population')
+        assert s._stepmon._info == a._stepmon._info
+        assert [list(x) for x in s.solution_history] == [list(x) for x in a.solution_history]
