@@ -15,6 +15,7 @@ N > 1 shards by candidate, one rank per GPU, weak scaling (NP per GPU fixed), pe
 all-gather of the shard bests over NCCL.
 """
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -324,6 +325,7 @@ def main():
             print('e2e: upload + generation 0 %.2f ms, %d steps %.2f ms' % ((t1 - t0) * 1e3, steps, (t0 + dt - t1) * 1e3),
                   file=sys.stderr)
         del s2
+        gc.collect()
         return dt
 
     e2e_run()                                    # warm-up: device allocations come from torch's cache afterwards

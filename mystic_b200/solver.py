@@ -31,6 +31,7 @@ Engine-specific constructor keywords (not in the reference):
                      bit-faithful Horner path (default False)
 """
 import random
+import weakref
 from collections.abc import Callable as _Callable
 
 import numpy as np
@@ -78,11 +79,13 @@ class _DeviceObjective(object):
     (inf outside the strict range, else cost) + penalty -- evaluated on the device."""
 
     def __init__(self, solver):
-        self._solver = solver
+        # weak: the solver holds this object in `_cost`; a strong reference back would make a cycle
+        # and keep gigabytes of device buffers alive until the garbage collector runs
+        self._solver = weakref.ref(solver)
 
     def __call__(self, x):
         x = np.asarray(x, dtype=np.float64)
-        out = self._solver._engine.eval_cost(np.atleast_2d(x))
+        out = self._solver()._engine.eval_cost(np.atleast_2d(x))
         return float(out[0]) if x.ndim == 1 else out
 
 
