@@ -1,8 +1,10 @@
 """Build the CUDA shared library in-tree (mystic_b200/_lib/libmystic_b200.so) for sm_100a.
 
-nvcc cross-compiles without a GPU.  The library is the product: there is no CPU fallback,
-`mystic_b200._native` raises if it is missing.
+nvcc cross-compiles without a GPU.  The kernel instantiations are spread over several
+translation units that compile in parallel.  The library is the product: there is no CPU
+fallback, `mystic_b200._native` raises if it is missing.
 """
+import concurrent.futures
 import os
 import shutil
 import subprocess
@@ -11,17 +13,18 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIBDIR = os.path.join(HERE, '_lib')
+OBJDIR = os.path.join(LIBDIR, 'obj')
 LIBPATH = os.path.join(LIBDIR, 'libmystic_b200.so')
 
-SOURCES = ['de_abi.cu']
-HEADERS = ['philox.cuh', 'de_device.cuh', 'de_kernels.cuh', 'de_tma.cuh', 'de_cheb_mma.cuh', 'de_small.cuh', os.path.join('..', '..', 'include', 'mystic_b200.h')]
+SOURCES = ['de_abi.cu', 'inst_ldg_exp.cu', 'inst_ldg_bin.cu', 'inst_tma_512.cu', 'inst_tma_1024.cu', 'inst_small.cu']
+HEADERS = ['philox.cuh', 'de_device.cuh', 'de_kernels.cuh', 'de_misc.cuh', 'de_tma.cuh', 'de_cheb_mma.cuh', 'de_small.cuh',
+           os.path.join('..', '..', 'include', 'mystic_b200.h')]
 
 NVCC_FLAGS = [
     '-gencode', 'arch=compute_100a,code=sm_100a',
     '-lineinfo', '-O3', '-std=c++17',
     # host code computes reference-order constants (chebyshev abscissae): no FMA contraction
     '-Xcompiler', '-fPIC,-ffp-contract=off',
-    '-shared',
 ]
 
 
@@ -32,33 +35,49 @@ def _nvcc():
     return exe
 
 
+def _deps():
+    return [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
+
+
 def _stale():
     if not os.path.exists(LIBPATH):
         return True
     t = os.path.getmtime(LIBPATH)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.normpath(os.path.join(CSRC, h)) for h in HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
+
+
+def _compile(args):
+    src, obj, verbose = args
+    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+    return src, proc.returncode, proc.stdout
 
 
 def build(force=False, verbose=False):
     """Compile if the library is missing or older than its sources; return its path."""
     if not force and not _stale():
         return LIBPATH
-    os.makedirs(LIBDIR, exist_ok=True)
-    tmp = LIBPATH + '.tmp.%d' % os.getpid()
-    cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ['-o', tmp]
-    if verbose:
-        cmd.insert(1, '-Xptxas')
-        cmd.insert(2, '-v')
-        print(' '.join(cmd), file=sys.stderr)
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
-    if proc.returncode != 0:
-        if os.path.exists(tmp):
-            os.remove(tmp)
-        raise RuntimeError('nvcc failed:\n' + proc.stdout)
-    os.replace(tmp, LIBPATH)
-    if verbose:
-        print(proc.stdout, file=sys.stderr)
+    os.makedirs(OBJDIR, exist_ok=True)
+    jobs = [(os.path.join(CSRC, s), os.path.join(OBJDIR, s[:-3] + '.%d.o' % os.getpid()), verbose) for s in SOURCES]
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+        results = list(pool.map(_compile, jobs))
+    objs = [j[1] for j in jobs]
+    try:
+        for src, rc, out in results:
+            if verbose:
+                print(out, file=sys.stderr)
+            if rc != 0:
+                raise RuntimeError('nvcc failed on %s:\n%s' % (src, out))
+        tmp = LIBPATH + '.tmp.%d' % os.getpid()
+        link = subprocess.run([_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a'] + objs + ['-o', tmp],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
+        if link.returncode != 0:
+            raise RuntimeError('link failed:\n' + link.stdout)
+        os.replace(tmp, LIBPATH)
+    finally:
+        for o in objs:
+            if os.path.exists(o):
+                os.remove(o)
     return LIBPATH
 
 

@@ -13,6 +13,7 @@
 
 #include "../../include/mystic_b200.h"
 #include "de_kernels.cuh"
+#include "de_misc.cuh"
 #include "de_tma.cuh"
 #include "de_cheb_mma.cuh"
 #include "de_small.cuh"
@@ -153,35 +154,22 @@ int host_alloc(mb2_ctx* c, size_t bytes, void** out) {
   return MB2_OK;
 }
 
+// kernel instantiations live in their own translation units (inst_*.cu) so that they compile in
+// parallel; these getters return the host stubs
 typedef void (*StepKernel)(const StepParams);
-
-template <int BASE, int XOVER, int COST>
-StepKernel pick_vec(bool vec) {
-  return vec ? (StepKernel)de_step_kernel<BASE, XOVER, COST, true> : (StepKernel)de_step_kernel<BASE, XOVER, COST, false>;
-}
-
-template <int BASE, int XOVER>
-StepKernel pick_cost(int cost, bool vec) {
-  switch (cost) {
-    case MB2_COST_ROSEN: return pick_vec<BASE, XOVER, COST_ROSEN>(vec);
-    case MB2_COST_CORANA: return pick_vec<BASE, XOVER, COST_CORANA>(vec);
-    case MB2_COST_GRIEWANGK: return pick_vec<BASE, XOVER, COST_GRIEWANGK>(vec);
-    case MB2_COST_ZIMMERMANN: return pick_vec<BASE, XOVER, COST_ZIMMERMANN>(vec);
-    case MB2_COST_CHEBYSHEV: return pick_vec<BASE, XOVER, COST_CHEBYSHEV>(vec);
-  }
-  return nullptr;
-}
+typedef void (*TmaKernel)(const StepParams, int);
+typedef void (*ThreadRowKernel)(const StepParams, int, int, int);
+}  // namespace
+namespace mb2 {
+StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
+TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
+ThreadRowKernel get_small_kernel(int cost);
+ThreadRowKernel get_cheb_mma_kernel(int ksteps);
+}  // namespace mb2
+namespace {
 
 StepKernel pick_kernel(const StrategyInfo& s, int cost, bool vec) {
-  if (s.xover == XOVER_BIN) return pick_cost<BASE_BEST1, XOVER_BIN>(cost, vec);
-  switch (s.base) {
-    case BASE_BEST1: return pick_cost<BASE_BEST1, XOVER_EXP>(cost, vec);
-    case BASE_RAND1: return pick_cost<BASE_RAND1, XOVER_EXP>(cost, vec);
-    case BASE_RANDTOBEST1: return pick_cost<BASE_RANDTOBEST1, XOVER_EXP>(cost, vec);
-    case BASE_BEST2: return pick_cost<BASE_BEST2, XOVER_EXP>(cost, vec);
-    case BASE_RAND2: return pick_cost<BASE_RAND2, XOVER_EXP>(cost, vec);
-  }
-  return nullptr;
+  return get_ldg_kernel(s.xover == XOVER_BIN ? BASE_BEST1 : s.base, s.xover, cost, vec);
 }
 
 // warps per CTA and dynamic shared memory for a row length
@@ -211,31 +199,7 @@ int ensure_parts(mb2_ctx* c, int n) {
   return MB2_OK;
 }
 
-typedef void (*TmaKernel)(const StepParams, int);
-
-template <int GW, int MAXT>
-TmaKernel pick_tma_cost(int cost) {
-  switch (cost) {
-    case MB2_COST_ROSEN: return de_step_best1bin_tma_kernel<COST_ROSEN, GW, MAXT>;
-    case MB2_COST_CORANA: return de_step_best1bin_tma_kernel<COST_CORANA, GW, MAXT>;
-    case MB2_COST_GRIEWANGK: return de_step_best1bin_tma_kernel<COST_GRIEWANGK, GW, MAXT>;
-    case MB2_COST_ZIMMERMANN: return de_step_best1bin_tma_kernel<COST_ZIMMERMANN, GW, MAXT>;
-    case MB2_COST_CHEBYSHEV: return de_step_best1bin_tma_kernel<COST_CHEBYSHEV, GW, MAXT>;
-  }
-  return nullptr;
-}
-
-// threads <= 512 use the 128-register build, larger CTAs the 64-register build
-TmaKernel pick_tma_kernel(int cost, int gwarps, int threads) {
-  const bool big = threads > 512;
-  switch (gwarps) {
-    case 1: return big ? pick_tma_cost<1, 1024>(cost) : pick_tma_cost<1, 512>(cost);
-    case 2: return big ? pick_tma_cost<2, 1024>(cost) : pick_tma_cost<2, 512>(cost);
-    case 4: return big ? pick_tma_cost<4, 1024>(cost) : pick_tma_cost<4, 512>(cost);
-    case 8: return big ? pick_tma_cost<8, 1024>(cost) : pick_tma_cost<8, 512>(cost);
-  }
-  return nullptr;
-}
+TmaKernel pick_tma_kernel(int cost, int gwarps, int threads) { return get_tma_kernel(cost, gwarps, threads); }
 
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
@@ -284,23 +248,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   const bool cheb_mma = (c->cost == MB2_COST_CHEBYSHEV_MMA);
   StepKernel k = cheb_mma ? nullptr : pick_kernel(s, c->cost, vec);
   if (k == nullptr && !cheb_mma) return fail(MB2_EINVAL, "no kernel for strategy %d cost %d", c->strategy, c->cost);
-  typedef void (*ChebKernel)(const StepParams, int, int, int);
-  ChebKernel kc = nullptr;
-  if (cheb_mma)
-    kc = c->cheb_ks == 1 ? de_step_cheb_mma_kernel<1> : (c->cheb_ks == 2 ? de_step_cheb_mma_kernel<2> : de_step_cheb_mma_kernel<4>);
+  ThreadRowKernel kc = cheb_mma ? get_cheb_mma_kernel(c->cheb_ks) : nullptr;
   // short rows: one thread per candidate (all modes, so energies of a context share one summation order)
-  ChebKernel ks = nullptr;
+  ThreadRowKernel ks = nullptr;
   int small_max = env_int("MB2_SMALL_MAXD", kSmallMaxDim);
   if (small_max > kSmallMaxDim) small_max = kSmallMaxDim;
-  if (!cheb_mma && c->dim <= small_max) {
-    switch (c->cost) {
-      case MB2_COST_ROSEN: ks = de_step_small_kernel<COST_ROSEN>; break;
-      case MB2_COST_CORANA: ks = de_step_small_kernel<COST_CORANA>; break;
-      case MB2_COST_GRIEWANGK: ks = de_step_small_kernel<COST_GRIEWANGK>; break;
-      case MB2_COST_ZIMMERMANN: ks = de_step_small_kernel<COST_ZIMMERMANN>; break;
-      case MB2_COST_CHEBYSHEV: ks = de_step_small_kernel<COST_CHEBYSHEV>; break;
-    }
-  }
+  if (!cheb_mma && c->dim <= small_max) ks = get_small_kernel(c->cost);
   s = c->sinfo;  // the thread-per-candidate kernels take the strategy at run time in every mode
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples

@@ -1,0 +1,222 @@
+// The non-templated kernels of the engine: argmin epilogue (K3) with the device-side termination
+// test, population initialisation (K0), multi-GPU best exchange records, self tests.  Included by
+// exactly one translation unit (de_abi.cu).
+#pragma once
+#include "de_kernels.cuh"
+
+namespace mb2 {
+
+// K3: reduce the per-CTA partials, update bestEnergy/bestSolution if the generation best beats
+// the previous best (strict '<', :610), publish counters.  One CTA.
+__global__ void __launch_bounds__(256)
+    de_finalize_kernel(const double* __restrict__ part_e, const int64_t* __restrict__ part_idx,
+                       const unsigned long long* __restrict__ part_ninf,
+                       const unsigned long long* __restrict__ part_nacc, int nparts,
+                       const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
+                       int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
+                       RunState* __restrict__ rs) {
+  if (rs != nullptr && rs->stop) return;  // batch mode: this generation was not run
+  __shared__ double sh_e[256];
+  __shared__ int64_t sh_i[256];
+  __shared__ unsigned long long sh_a[256], sh_b[256];
+  __shared__ int64_t sh_winner;
+  double be = CUDART_INF;
+  int64_t bi = INT64_MAX;
+  unsigned long long ni = 0, na = 0;
+  for (int k = threadIdx.x; k < nparts; k += blockDim.x) {
+    const double e = part_e[k];
+    const int64_t i = part_idx[k];
+    if (e < be || (e == be && i < bi)) {
+      be = e;
+      bi = i;
+    }
+    ni += part_ninf[k];
+    na += part_nacc[k];
+  }
+  sh_e[threadIdx.x] = be;
+  sh_i[threadIdx.x] = bi;
+  sh_a[threadIdx.x] = ni;
+  sh_b[threadIdx.x] = na;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) {
+      const double e = sh_e[threadIdx.x + s];
+      const int64_t i = sh_i[threadIdx.x + s];
+      if (e < sh_e[threadIdx.x] || (e == sh_e[threadIdx.x] && i < sh_i[threadIdx.x])) {
+        sh_e[threadIdx.x] = e;
+        sh_i[threadIdx.x] = i;
+      }
+      sh_a[threadIdx.x] += sh_a[threadIdx.x + s];
+      sh_b[threadIdx.x] += sh_b[threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const double prev = gen0 ? CUDART_INF : st->best_e;
+    int64_t winner = -1;
+    if (sh_i[0] != INT64_MAX && sh_e[0] < prev) {
+      winner = sh_i[0];
+      st->best_e = sh_e[0];
+      st->best_idx = global_offset + winner;
+    } else if (gen0) {
+      // nothing finite yet: bestSolution stays population[0], bestEnergy = popEnergy[0] = inf (:559-567)
+      st->best_e = CUDART_INF;
+      st->best_idx = -1;
+      winner = -2;  // copy row 0
+    }
+    st->n_inf = (int64_t)sh_a[0];
+    st->n_acc = (int64_t)sh_b[0];
+    st->generation = generation;
+    sh_winner = winner;
+  }
+  __syncthreads();
+  const int64_t w = sh_winner;
+  if (w != -1) {
+    const double* src = pop_next + (w == -2 ? 0 : w) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = src[i];
+  }
+  if (rs == nullptr) return;
+  __syncthreads();
+  // ---- batch mode: log the generation, then the host part of Step(): counters and termination
+  const long long slot = rs->log_count;
+  if (slot < rs->log_cap) {
+    double* rec = rs->log + slot * (D + 4);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) rec[4 + i] = best_x[i];
+    if (threadIdx.x == 0) {
+      rec[0] = st->best_e;
+      rec[1] = (double)st->best_idx;
+      rec[2] = (double)st->n_inf;
+      rec[3] = (double)st->n_acc;
+    }
+  }
+  if (threadIdx.x == 0) {
+    rs->log_count = slot + 1;
+    rs->evaluations += rs->np_eval - st->n_inf;        // differential_evolution.py:601
+    rs->generations += 1;
+    const double e = st->best_e;                        // stepmon(bestSolution, bestEnergy) (:617)
+    if (rs->hist_count == 0) rs->hist0 = e;
+    rs->hist[rs->hist_count % kHistMax] = e;
+    rs->hist_count += 1;
+    const long long lg = rs->hist_count;
+    const int g = rs->lookback;
+    // python hist[-g]: g == 0 addresses hist[0]
+    const double hg = (g == 0) ? rs->hist0 : rs->hist[(lg - g + (long long)kHistMax * 4) % kHistMax];
+    const double h1 = e;
+    bool met = false;
+    switch (rs->kind) {
+      case TERM_VTR:  // termination.py:181-196
+        met = fabs(h1 - rs->target) <= rs->tol;
+        break;
+      case TERM_COG:  // termination.py:198-217
+        met = (lg > g) && ((hg - h1) <= rs->tol || hg == h1);
+        break;
+      case TERM_NCOG:  // termination.py:219-240
+        met = (lg > g) && (hg == h1 || 2.0 * (hg - h1) <= rs->tol * (fabs(hg) + fabs(h1)) + 1e-20);
+        break;
+      case TERM_VTRCOG:  // termination.py:320-342
+        met = ((lg > g) && ((hg - h1) <= rs->gtol || hg == h1)) || (fabs(h1 - rs->target) <= rs->tol);
+        break;
+      case TERM_LIMITS:  // termination.py:386-408
+        met = (rs->term_evaluations >= 0 && rs->evaluations >= rs->term_evaluations) ||
+              (rs->term_generations >= 0 && rs->generations >= rs->term_generations);
+        break;
+      default:
+        break;
+    }
+    // the solver's own limits (abstract_solver.py:703-711)
+    if (rs->max_evaluations >= 0 && rs->evaluations >= rs->max_evaluations) met = true;
+    if (rs->max_generations >= 0 && rs->generations >= rs->max_generations) met = true;
+    if (met || rs->log_count >= rs->log_cap) rs->stop = met ? 1 : 2;  // 2: log full (cannot happen: one batch = log_cap launches)
+  }
+}
+
+// K0: device-side SetRandomInitialPoints (abstract_solver.py:532-534): pop[c][j] = lo + (hi-lo)*u
+__global__ void __launch_bounds__(256)
+    de_init_population_kernel(double* __restrict__ pop, double* __restrict__ energy, int64_t np, int D,
+                              int64_t global_offset, const double* __restrict__ lo, const double* __restrict__ hi,
+                              uint32_t k0, uint32_t k1) {
+  const int64_t nblk = (D + 1) / 2;  // philox blocks per row (2 doubles each)
+  const int64_t total = np * nblk;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t c = t / nblk;
+    const int b = (int)(t - c * nblk);
+    const u32x4 v = philox4x32_10((uint32_t)b, (uint32_t)(global_offset + c), 0u, STREAM_INIT, k0, k1);
+    const int j = 2 * b;
+    const double u0 = u64_to_unit(((uint64_t)v.x << 32) | v.y);
+    const double u1 = u64_to_unit(((uint64_t)v.z << 32) | v.w);
+    pop[c * D + j] = dadd(lo[j], dmul(dsub(hi[j], lo[j]), u0));
+    if (j + 1 < D) pop[c * D + j + 1] = dadd(lo[j + 1], dmul(dsub(hi[j + 1], lo[j + 1]), u1));
+    if (b == 0) energy[c] = CUDART_INF;
+  }
+}
+
+// self test: div_by_table(c, sqrt(i+1), 1/sqrt(i+1)) against the IEEE divide on n Philox-random
+// operands; counts bit mismatches
+__global__ void selftest_division_kernel(int64_t n, uint32_t k0, uint32_t k1, double span, const double2* tab, int D,
+                                         unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const u32x4 v = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 7u, 9u, k0, k1);
+    const double u = u64_to_unit(((uint64_t)v.x << 32) | v.y);
+    const double c = (2.0 * u - 1.0) * span;
+    const int i = (int)(v.z % (uint32_t)D);
+    const double2 sr = tab[i];
+    const double want = c / sqrt((double)i + 1.0);
+    const double got = div_by_table(c, sr.x, sr.y);
+    if (__double_as_longlong(want) != __double_as_longlong(got)) ++bad;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+__global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
+}
+
+// multi-GPU best exchange records: [best_e, best_idx(global), n_inf, n_acc, x[D]]
+__global__ void pack_best_kernel(const DeviceState* __restrict__ st, const double* __restrict__ best_x, int D,
+                                 double* __restrict__ rec) {
+  if (threadIdx.x == 0) {
+    rec[0] = st->best_e;
+    rec[1] = (double)st->best_idx;
+    rec[2] = (double)st->n_inf;
+    rec[3] = (double)st->n_acc;
+  }
+  for (int i = threadIdx.x; i < D; i += blockDim.x) rec[4 + i] = best_x[i];
+}
+
+__global__ void merge_best_kernel(const double* __restrict__ recs, int world, int D, double* __restrict__ best_x,
+                                  DeviceState* __restrict__ st) {
+  __shared__ int sh_w;
+  if (threadIdx.x == 0) {
+    int w = -1;
+    double be = CUDART_INF;
+    double bi = 0.0;
+    double ninf = 0.0, nacc = 0.0;
+    for (int r = 0; r < world; ++r) {
+      const double* rec = recs + (int64_t)r * (D + 4);
+      ninf += rec[2];
+      nacc += rec[3];
+      if (rec[1] < 0.0) continue;  // shard has no best yet
+      if (w < 0 || rec[0] < be || (rec[0] == be && rec[1] < bi)) {
+        w = r;
+        be = rec[0];
+        bi = rec[1];
+      }
+    }
+    if (w >= 0) {
+      st->best_e = be;
+      st->best_idx = (int64_t)bi;
+    }
+    st->n_inf = (int64_t)ninf;
+    st->n_acc = (int64_t)nacc;
+    sh_w = w;
+  }
+  __syncthreads();
+  const int w = sh_w;
+  if (w >= 0) {
+    const double* rec = recs + (int64_t)w * (D + 4);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = rec[4 + i];
+  }
+}
+
+}  // namespace mb2
