@@ -17,6 +17,7 @@
 #include "de_tma.cuh"
 #include "de_cheb_mma.cuh"
 #include "de_small.cuh"
+#include "de_subwarp.cuh"
 
 using namespace mb2;
 
@@ -165,6 +166,7 @@ StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
 ThreadRowKernel get_small_kernel(int cost);
 ThreadRowKernel get_cheb_mma_kernel(int ksteps);
+ThreadRowKernel get_subwarp_kernel(int cost, int lanes_per_row, bool vec);
 }  // namespace mb2
 namespace {
 
@@ -253,14 +255,22 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   ThreadRowKernel ks = nullptr;
   int small_max = env_int("MB2_SMALL_MAXD", kSmallMaxDim);
   if (small_max > kSmallMaxDim) small_max = kSmallMaxDim;
-  if (!cheb_mma && c->dim <= small_max) ks = get_small_kernel(c->cost);
+  // MB2_SMALL_KERNEL: 1 = several rows per warp (default), 2 = one thread per row, 0 = neither
+  const int small_kind = env_int("MB2_SMALL_KERNEL", 1);
+  ThreadRowKernel kw = nullptr;
+  int lpr = 4;
+  while (lpr < 32 && lpr * 8 < c->dim) lpr <<= 1;  // about 8 dimensions per lane
+  if (!cheb_mma && c->dim <= small_max) {
+    if (small_kind == 2) ks = get_small_kernel(c->cost);
+    else if (small_kind == 1) kw = get_subwarp_kernel(c->cost, lpr, vec);
+  }
   s = c->sinfo;  // the thread-per-candidate kernels take the strategy at run time in every mode
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 &&
-      !cheb_mma && ks == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
+      !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
 
   int wpc, smem;
@@ -272,6 +282,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     smem = (int)(sizeof(double) * (size_t)kChebWarps * (kChebBatch * c->dim + kChebBatch));
     CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc, wpc * 32, smem));
+  } else if (kw != nullptr) {
+    wpc = kSubWarps;
+    rows_per_cta = kSubWarps * (32 / lpr);
+    smem = (int)(sizeof(double) * (size_t)(1 + kSubWarps * (32 / lpr)) * c->dim_pad);
+    CUDA_TRY(cudaFuncSetAttribute(kw, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kw, wpc * 32, smem));
   } else if (ks != nullptr) {
     wpc = kSmallWarps;
     rows_per_cta = kSmallWarps * 32;
@@ -341,6 +357,8 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->smem = smem;
   if (kc != nullptr)
     kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (kw != nullptr)
+    kw<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (ks != nullptr)
     ks<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (kt != nullptr)

@@ -1,0 +1,399 @@
+// Several candidate rows per warp, for short rows (D <= 128).
+//
+// With one warp per row, a 64-dimensional row (512 B) costs ~1000 warp instructions, most of
+// them per-row overhead (draws, reductions, selection) executed by lanes that have no data.
+// Here a group of LPR lanes (4, 8, 16 or 32) owns a row and a warp processes 32/LPR rows at
+// once, so that overhead is shared by SIMT: the same instructions serve 2-8 rows.  Loads stay
+// 16-byte vectors on the contiguous row segments.
+//
+// The kernel serves every mode (step, generation 0, mb2_eval_cost) for its row lengths, so the
+// energies of a context always come from one summation order: lane `sub` of a group accumulates
+// elements sub, sub+LPR, ... in order and the group combines the lanes by a xor tree.
+#pragma once
+#include "de_kernels.cuh"
+
+namespace mb2 {
+
+constexpr int kSubMaxDim = 128;
+constexpr int kSubWarps = 8;
+
+template <int LPR, bool PROD>
+__device__ __forceinline__ double seg_reduce(double v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    const double w = __shfl_xor_sync(0xffffffffu, v, o);
+    v = PROD ? dmul(v, w) : dadd(v, w);
+  }
+  return v;
+}
+
+template <int COST, int LPR>
+__device__ __forceinline__ double seg_cost(const double* xs, int D, int sub, const CostParams& cp) {
+  if (COST == COST_ROSEN) {
+    double acc = 0.0;
+    for (int i = sub; i < D - 1; i += LPR) {
+      const double a = xs[i], b = xs[i + 1];
+      const double t = dsub(b, dmul(a, a));
+      const double u = dsub(1.0, a);
+      acc = dadd(acc, dadd(dmul(100.0, dmul(t, t)), dmul(u, u)));
+    }
+    return seg_reduce<LPR, false>(acc);
+  } else if (COST == COST_CORANA) {
+    const double d[4] = {1., 1000., 10., 100.};
+    double x[4] = {0., 0., 0., 0.};
+    if (D >= 4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) x[j] = xs[j];
+    } else {
+      if (D >= 1) x[0] = xs[0];
+      if (D >= 2) x[2] = xs[1];
+      if (D >= 3) x[3] = xs[2];
+    }
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const double xj = x[j];
+      const double sg = (xj > 0.0) ? 1.0 : ((xj < 0.0) ? -1.0 : 0.0);
+      const double zj = dmul(dmul(floor(dadd(fabs(xj / 0.2), 0.49999)), sg), 0.2);
+      double term;
+      if (fabs(dsub(xj, zj)) < 0.05) {
+        const double sz = (zj > 0.0) ? 1.0 : ((zj < 0.0) ? -1.0 : 0.0);
+        const double w = dsub(zj, dmul(0.05, sz));
+        term = dmul(dmul(0.15, dmul(w, w)), d[j]);
+      } else {
+        term = dmul(dmul(d[j], xj), xj);
+      }
+      r = dadd(r, term);
+    }
+    return r;
+  } else if (COST == COST_GRIEWANGK) {
+    double s = 0.0, p = 1.0;
+    for (int i = sub; i < D; i += LPR) {
+      const double c = xs[i];
+      s = dadd(s, dmul(c, c));
+      const double2 t = __ldg(cp.grw_tab + i);
+      p = dmul(p, cos(div_by_table(c, t.x, t.y)));
+    }
+    s = seg_reduce<LPR, false>(s);
+    p = seg_reduce<LPR, true>(p);
+    return dadd(dsub(s / 4000.0, p), 1.0);
+  } else if (COST == COST_ZIMMERMANN) {
+    const double x0 = xs[0], x1 = (D > 1) ? xs[1] : 0.0;
+    const double f8 = dsub(dsub(9.0, x0), x1);
+    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+    if (x0 < 0.0) c0 = dmul(-100.0, x0);
+    if (x1 < 0.0) c1 = dmul(-100.0, x1);
+    const double a = dsub(x0, 3.0), b = dsub(x1, 2.0);
+    const double xx = dadd(dmul(a, a), dmul(b, b));
+    if (xx > 16.0) c2 = dmul(100.0, dsub(xx, 16.0));
+    const double pr = dmul(x0, x1);
+    if (pr > 14.0) c3 = dmul(100.0, dsub(pr, 14.0));
+    double m = f8;
+    if (c0 > m) m = c0;
+    if (c1 > m) m = c1;
+    if (c2 > m) m = c2;
+    if (c3 > m) m = c3;
+    return m;
+  } else {
+    double acc = 0.0;
+    const int M = cp.cheb_M;
+    for (int i = sub; i < M; i += LPR) {
+      const double px = horner(xs, D, __ldg(cp.cheb_x + i));
+      if (px < -1.0 || px > 1.0) {
+        const double u = dsub(1.0, px);
+        acc = dadd(acc, dmul(u, u));
+      }
+    }
+    double r = seg_reduce<LPR, false>(acc);
+    double px = dsub(horner(xs, D, 1.2), cp.cheb_tp);
+    if (px < 0.0) r = dadd(r, dmul(px, px));
+    px = dsub(horner(xs, D, -1.2), cp.cheb_tm);
+    if (px < 0.0) r = dadd(r, dmul(px, px));
+    return r;
+  }
+}
+
+template <int LPR>
+__device__ __forceinline__ double seg_penalty(const double* xs, int D, int sub, const PenaltyParams& pp) {
+  double total = 0.0;
+  for (int t = 0; t < pp.n; ++t) {
+    const double* g = pp.G + (int64_t)t * D;
+    double acc = 0.0;
+    for (int i = sub; i < D; i += LPR) acc = dadd(acc, dmul(__ldg(g + i), xs[i]));
+    const double pf = dsub(seg_reduce<LPR, false>(acc), __ldg(pp.h + t));
+    const double k = __ldg(pp.kscale + t);
+    const int ty = __ldg(pp.ptype + t);
+    const double m = (pf > 0.0) ? pf : 0.0;
+    double v;
+    if (ty == 0) v = dmul(k, dmul(pf, pf));
+    else if (ty == 1) v = dmul(k, fabs(pf));
+    else if (ty == 2) v = dmul(2.0 * k, dmul(m, m));
+    else v = dmul(2.0 * k, fabs(m));
+    total = dadd(v, total);
+  }
+  return total;
+}
+
+template <int COST, int LPR, bool VEC>
+__global__ void __launch_bounds__(kSubWarps * 32)
+    de_step_subwarp_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
+  if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double sh_e[kSubWarps];
+  __shared__ int64_t sh_i[kSubWarps];
+  __shared__ unsigned long long sh_ninf[kSubWarps], sh_nacc[kSubWarps];
+  constexpr int RPW = 32 / LPR;  // rows per warp
+
+  const int D = P.dim;
+  const int Dp = P.dim_pad;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpc = blockDim.x >> 5;
+  const int grp = lane / LPR;
+  const int sub = lane % LPR;
+  const bool uni_b = P.bounds_uniform != 0;
+  const bool needs_best = (base == BASE_BEST1 || base == BASE_RANDTOBEST1 || base == BASE_BEST2);
+  double* s_best = smem;                                                  // [Dp]
+  double* s_trial = smem + Dp + ((size_t)warp * RPW + grp) * Dp;          // [Dp] per row
+
+  if (P.mode == MODE_STEP && needs_best) {
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
+  }
+  __syncthreads();
+
+  double w_best_e = CUDART_INF;
+  int64_t w_best_idx = INT64_MAX;
+  unsigned long long w_ninf = 0, w_nacc = 0;
+
+  const int64_t nchunks = (P.np + RPW - 1) / RPW;
+  const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
+  const int64_t nw = (int64_t)gridDim.x * wpc;
+  for (int64_t ch = gw; ch < nchunks; ch += nw) {
+    const int64_t c = ch * RPW + grp;
+    const bool live = c < P.np;
+    const int64_t cc = live ? c : (P.np - 1);  // idle groups shadow the last row and discard the result
+    const double* __restrict__ prow = P.pop_cur + cc * D;
+    bool oob = false;
+
+    if (P.mode == MODE_STEP) {
+      int64_t r[5] = {0, 0, 0, 0, 0};
+      int nstart;
+      const uint32_t cand_g = (uint32_t)(P.global_offset + cc);
+      if (P.replay) {
+        for (int j = 0; j < ndonors; ++j) r[j] = __ldg(P.r_donors + cc * 5 + j);
+        nstart = __ldg(P.r_nstart + cc);
+      } else {
+        switch (ndonors) {
+          case 2: draw_donors<2>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
+          case 3: draw_donors<3>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
+          case 4: draw_donors<4>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
+          default: draw_donors<5>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
+        }
+      }
+      // exponential crossover length (strategy.py:48-56): every lane of the group scans the same
+      // words sequentially (D <= 128: at most 32 Philox blocks, on average 1/(1-CR) words)
+      int L = 0;
+      if (xover == XOVER_EXP) {
+        const double* u = P.r_uni + cc * (int64_t)(D + 1);
+        u32x4 w = {0, 0, 0, 0};
+        while (L < D) {
+          bool ok;
+          if (P.replay) {
+            ok = __ldg(u + L) < P.CR;
+          } else {
+            if ((L & 3) == 0) w = philox4x32_10((uint32_t)(L >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+            const uint32_t word = (L & 3) == 0 ? w.x : ((L & 3) == 1 ? w.y : ((L & 3) == 2 ? w.z : w.w));
+            ok = (uint64_t)word < P.thr;
+          }
+          if (!ok) break;
+          ++L;
+        }
+      }
+      const double* __restrict__ d0 = P.pop_cur + r[0] * D;
+      const double* __restrict__ d1 = P.pop_cur + r[1] * D;
+      const double* __restrict__ d2 = P.pop_cur + r[2] * D;
+      const double* __restrict__ d3 = P.pop_cur + r[3] * D;
+      const double* __restrict__ d4 = P.pop_cur + r[4] * D;
+
+      for (int i0 = sub * 4; i0 < D; i0 += LPR * 4) {
+        double x[4];
+        load4<VEC>(prow, i0, D, x);
+        bool cross[4];
+        if (xover == XOVER_BIN) {
+          if (P.replay) {
+            const double* u = P.r_uni + cc * (int64_t)(D + 1) + i0;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) cross[e] = (i0 + e < D) && ((i0 + e == nstart) || (__ldg(u + e) < P.CR));
+          } else {
+            const u32x4 w = philox4x32_10((uint32_t)(i0 >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+            cross[0] = (i0 == nstart) || ((uint64_t)w.x < P.thr);
+            cross[1] = (i0 + 1 < D) && ((i0 + 1 == nstart) || ((uint64_t)w.y < P.thr));
+            cross[2] = (i0 + 2 < D) && ((i0 + 2 == nstart) || ((uint64_t)w.z < P.thr));
+            cross[3] = (i0 + 3 < D) && ((i0 + 3 == nstart) || ((uint64_t)w.w < P.thr));
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            int rel = i0 + e - nstart;
+            if (rel < 0) rel += D;
+            cross[e] = (i0 + e < D) && (rel < L);
+          }
+        }
+        if (cross[0] | cross[1] | cross[2] | cross[3]) {
+          double q[5][4];
+          load4<VEC>(d0, i0, D, q[0]);
+          load4<VEC>(d1, i0, D, q[1]);
+          if (ndonors > 2) load4<VEC>(d2, i0, D, q[2]);
+          if (ndonors > 3) load4<VEC>(d3, i0, D, q[3]);
+          if (ndonors > 4) load4<VEC>(d4, i0, D, q[4]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (cross[e]) {
+              double p[5];
+#pragma unroll
+              for (int j = 0; j < 5; ++j) p[j] = (j < ndonors) ? q[j][e] : 0.0;
+              const double b = needs_best ? s_best[i0 + e] : 0.0;
+              switch (base) {
+                case BASE_BEST1: x[e] = mutant<BASE_BEST1>(x[e], b, p, P.F); break;
+                case BASE_RAND1: x[e] = mutant<BASE_RAND1>(x[e], b, p, P.F); break;
+                case BASE_RANDTOBEST1: x[e] = mutant<BASE_RANDTOBEST1>(x[e], b, p, P.F); break;
+                case BASE_BEST2: x[e] = mutant<BASE_BEST2>(x[e], b, p, P.F); break;
+                default: x[e] = mutant<BASE_RAND2>(x[e], b, p, P.F); break;
+              }
+            }
+          }
+        }
+        if (P.bounds_mode != BOUNDS_NONE) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (i0 + e < D) {
+              const double l = uni_b ? P.lo_s : __ldg(P.lo + i0 + e);
+              const double h = uni_b ? P.hi_s : __ldg(P.hi + i0 + e);
+              if (P.bounds_mode == BOUNDS_CLAMP) {
+                x[e] = (x[e] > l) ? x[e] : l;  // python max(lo, x)
+                x[e] = (x[e] < h) ? x[e] : h;  // python min(hi, x)
+              } else {
+                oob |= (x[e] < l) || (x[e] > h);
+              }
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_trial[i0 + e] = x[e];
+      }
+    } else {
+      for (int i0 = sub * 4; i0 < D; i0 += LPR * 4) {
+        double x[4];
+        load4<VEC>(prow, i0, D, x);
+        if (P.bounds_mode != BOUNDS_NONE) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (i0 + e < D) {
+              const double l = uni_b ? P.lo_s : __ldg(P.lo + i0 + e);
+              const double h = uni_b ? P.hi_s : __ldg(P.hi + i0 + e);
+              if (P.mode == MODE_GEN0) x[e] = fmin(fmax(x[e], l), h);
+              oob |= (x[e] < l) || (x[e] > h);
+            }
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s_trial[i0 + e] = x[e];
+      }
+    }
+    // any lane of the group out of range?  (segmented OR over the LPR lanes)
+    {
+      const unsigned m = __ballot_sync(0xffffffffu, oob);
+      const unsigned seg = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (grp * LPR));
+      oob = (m & seg) != 0;
+    }
+    __syncwarp();
+
+    double E = CUDART_INF;
+    {
+      // every group evaluates (idle groups on a shadow row): the shuffles inside need all lanes
+      const double cost = seg_cost<COST, LPR>(s_trial, D, sub, P.cost);
+      if (!oob) E = cost;
+      E = dadd(E, seg_penalty<LPR>(s_trial, D, sub, P.pen));
+    }
+
+    if (live && P.cap_trial != nullptr && P.mode != MODE_EVAL) {
+      for (int i = sub; i < D; i += LPR) P.cap_trial[c * D + i] = s_trial[i];
+      if (sub == 0) P.cap_energy[c] = E;
+    }
+
+    if (P.mode == MODE_EVAL) {
+      if (live && sub == 0) P.e_next[c] = E;
+    } else if (live) {
+      const double e_old = (P.mode == MODE_GEN0) ? CUDART_INF : __ldg(P.e_cur + c);
+      const bool acc = E < e_old;
+      double* __restrict__ nrow = P.pop_next + c * D;
+      if (acc || P.mode == MODE_GEN0) {
+        for (int i0 = sub * 4; i0 < D; i0 += LPR * 4) {
+          double x[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) x[e] = s_trial[i0 + e];
+          store4<VEC>(nrow, i0, D, x);
+        }
+      } else {
+        for (int i0 = sub * 4; i0 < D; i0 += LPR * 4) {
+          double x[4];
+          load4<VEC>(prow, i0, D, x);
+          store4<VEC>(nrow, i0, D, x);
+        }
+      }
+      if (sub == 0) {
+        P.e_next[c] = acc ? E : e_old;
+        if (acc) {
+          ++w_nacc;
+          if (E < w_best_e || (E == w_best_e && c < w_best_idx)) {
+            w_best_e = E;
+            w_best_idx = c;
+          }
+        }
+        if (isinf(E)) ++w_ninf;
+      }
+    }
+    __syncwarp();  // s_trial is reused by the next chunk
+  }
+
+  if (P.mode == MODE_EVAL) return;
+
+  // warp argmin over the group leaders (other lanes carry +inf / 0)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double oe = __shfl_xor_sync(0xffffffffu, w_best_e, o);
+    const int64_t oi = __shfl_xor_sync(0xffffffffu, w_best_idx, o);
+    if (oe < w_best_e || (oe == w_best_e && oi < w_best_idx)) {
+      w_best_e = oe;
+      w_best_idx = oi;
+    }
+    w_ninf += __shfl_xor_sync(0xffffffffu, w_ninf, o);
+    w_nacc += __shfl_xor_sync(0xffffffffu, w_nacc, o);
+  }
+  if (lane == 0) {
+    sh_e[warp] = w_best_e;
+    sh_i[warp] = w_best_idx;
+    sh_ninf[warp] = w_ninf;
+    sh_nacc[warp] = w_nacc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double be = sh_e[0];
+    int64_t bi = sh_i[0];
+    unsigned long long ni = sh_ninf[0], na = sh_nacc[0];
+    for (int w = 1; w < wpc; ++w) {
+      if (sh_e[w] < be || (sh_e[w] == be && sh_i[w] < bi)) {
+        be = sh_e[w];
+        bi = sh_i[w];
+      }
+      ni += sh_ninf[w];
+      na += sh_nacc[w];
+    }
+    P.part_e[blockIdx.x] = be;
+    P.part_idx[blockIdx.x] = bi;
+    P.part_ninf[blockIdx.x] = ni;
+    P.part_nacc[blockIdx.x] = na;
+  }
+}
+
+}  // namespace mb2

@@ -49,15 +49,13 @@ def configure(eng, meta):
     eng.set_strategy(sid, meta['F_eff'], meta['CR_eff'])
 
 
-@pytest.fixture(params=['thread_per_row', 'warp_per_row'])
+@pytest.fixture(params=['rows_per_warp', 'thread_per_row', 'warp_per_row'])
 def kernel_path(request, monkeypatch):
-    """rows of <= 128 dimensions normally run in the thread-per-candidate kernel (de_small.cuh);
-    MB2_SMALL_MAXD=0 sends them through the warp/group-per-row kernels (de_kernels.cuh, de_tma.cuh)
-    instead, so the recordings exercise every kernel family"""
-    if request.param == 'warp_per_row':
-        monkeypatch.setenv('MB2_SMALL_MAXD', '0')
-    else:
-        monkeypatch.delenv('MB2_SMALL_MAXD', raising=False)
+    """rows of <= 128 dimensions normally run several to a warp (de_subwarp.cuh);
+    MB2_SMALL_KERNEL=2 selects the thread-per-candidate kernel (de_small.cuh) and 0 sends them through
+    the warp/group-per-row kernels (de_kernels.cuh, de_tma.cuh), so the recordings exercise every
+    kernel family"""
+    monkeypatch.setenv('MB2_SMALL_KERNEL', {'rows_per_warp': '1', 'thread_per_row': '2', 'warp_per_row': '0'}[request.param])
     return request.param
 
 
