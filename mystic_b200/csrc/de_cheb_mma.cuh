@@ -105,20 +105,7 @@ __global__ void __launch_bounds__(kChebWarps * 32)
             if (hit || i == nstart) cmask |= 1u << i;
           }
         } else {
-          int L = 0;
-          u32x4 w = {0, 0, 0, 0};
-          while (L < D) {
-            bool ok;
-            if (P.replay) {
-              ok = __ldg(u + L) < P.CR;
-            } else {
-              if ((L & 3) == 0) w = philox4x32_10((uint32_t)(L >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-              const uint32_t word = (L & 3) == 0 ? w.x : ((L & 3) == 1 ? w.y : ((L & 3) == 2 ? w.z : w.w));
-              ok = (uint64_t)word < P.thr;
-            }
-            if (!ok) break;
-            ++L;
-          }
+          const int L = exp_length_thread(P, cand_g, c, D);
           for (int j = 0; j < L; ++j) {
             int i = nstart + j;
             if (i >= D) i -= D;

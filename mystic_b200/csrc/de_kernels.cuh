@@ -111,6 +111,26 @@ __device__ __forceinline__ int exp_length_replay(const double* __restrict__ uni,
   return D;
 }
 
+// Same length computed by ONE thread for its own candidate (thread- and group-per-row kernels):
+// a whole Philox block (4 words) per iteration, no per-word branches.
+__device__ __forceinline__ int exp_length_thread(const StepParams& P, uint32_t cand, int64_t c, int D) {
+  int L = 0;
+  if (P.replay) {
+    const double* u = P.r_uni + c * (int64_t)(D + 1);
+    while (L < D && (__ldg(u + L) < P.CR)) ++L;  // NaN (not drawn) -> stop
+    return L;
+  }
+  for (int b = 0; L < D; ++b) {
+    const u32x4 w = philox4x32_10((uint32_t)b, cand, P.generation, STREAM_XOVER, P.key0, P.key1);
+    const unsigned ok = ((uint64_t)w.x < P.thr ? 1u : 0u) | ((uint64_t)w.y < P.thr ? 2u : 0u) |
+                        ((uint64_t)w.z < P.thr ? 4u : 0u) | ((uint64_t)w.w < P.thr ? 8u : 0u);
+    const int run = __ffs(~ok) - 1;  // leading successes in this block (4 when ok == 0xF)
+    L += run;
+    if (run < 4) break;
+  }
+  return L < D ? L : D;
+}
+
 __device__ __forceinline__ int exp_length_philox(uint32_t k0, uint32_t k1, uint32_t gen, uint32_t cand, int D,
                                                  uint64_t thr, int lane) {
   for (int base = 0; base < D; base += 128) {

@@ -265,19 +265,7 @@ __global__ void __launch_bounds__(kSmallWarps * 32)
           binomial = true;  // every dimension may have changed: a rejected row is re-read
         } else {
           // strategy.py:48-56: L leading successes, capped at D
-          u32x4 w = {0, 0, 0, 0};
-          while (L < D) {
-            bool ok;
-            if (P.replay) {
-              ok = __ldg(u + L) < P.CR;
-            } else {
-              if ((L & 3) == 0) w = philox4x32_10((uint32_t)(L >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-              const uint32_t word = (L & 3) == 0 ? w.x : ((L & 3) == 1 ? w.y : ((L & 3) == 2 ? w.z : w.w));
-              ok = (uint64_t)word < P.thr;
-            }
-            if (!ok) break;
-            ++L;
-          }
+          L = exp_length_thread(P, cand_g, c, D);
           // window dims i_j = (nstart + j) mod D, four at a time: all donor loads of a chunk are
           // issued before any is used (the scattered 8-byte loads are the latency of this kernel).
           // Only crossed dimensions can leave the bounds (parents are inside them since generation

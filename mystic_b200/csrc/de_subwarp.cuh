@@ -191,24 +191,8 @@ __global__ void __launch_bounds__(kSubWarps * 32)
         }
       }
       // exponential crossover length (strategy.py:48-56): every lane of the group scans the same
-      // words sequentially (D <= 128: at most 32 Philox blocks, on average 1/(1-CR) words)
-      int L = 0;
-      if (xover == XOVER_EXP) {
-        const double* u = P.r_uni + cc * (int64_t)(D + 1);
-        u32x4 w = {0, 0, 0, 0};
-        while (L < D) {
-          bool ok;
-          if (P.replay) {
-            ok = __ldg(u + L) < P.CR;
-          } else {
-            if ((L & 3) == 0) w = philox4x32_10((uint32_t)(L >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-            const uint32_t word = (L & 3) == 0 ? w.x : ((L & 3) == 1 ? w.y : ((L & 3) == 2 ? w.z : w.w));
-            ok = (uint64_t)word < P.thr;
-          }
-          if (!ok) break;
-          ++L;
-        }
-      }
+      // Philox blocks (D <= 128: at most 32, on average 1/(4(1-CR)))
+      const int L = (xover == XOVER_EXP) ? exp_length_thread(P, cand_g, cc, D) : 0;
       const double* __restrict__ d0 = P.pop_cur + r[0] * D;
       const double* __restrict__ d1 = P.pop_cur + r[1] * D;
       const double* __restrict__ d2 = P.pop_cur + r[2] * D;
