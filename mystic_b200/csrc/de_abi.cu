@@ -18,6 +18,7 @@
 #include "de_cheb_mma.cuh"
 #include "de_small.cuh"
 #include "de_subwarp.cuh"
+#include "de_rows.cuh"
 
 using namespace mb2;
 
@@ -75,6 +76,9 @@ struct mb2_ctx {
   double F = 0.8, CR = 0.9;
   int bounds_mode = BOUNDS_NONE;
   int bounds_uniform = 0;
+  // every row of the current population lies inside [lo, hi]: generation 0 clipped it with these
+  // bounds and nothing has replaced rows or bounds since (lets kernels skip re-checking parents)
+  int rows_in_range = 0;
   double lo_s = 0.0, hi_s = 0.0;
   double* lo = nullptr;
   double* hi = nullptr;
@@ -167,6 +171,9 @@ TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
 ThreadRowKernel get_small_kernel(int cost);
 ThreadRowKernel get_cheb_mma_kernel(int ksteps);
 ThreadRowKernel get_subwarp_kernel(int cost, int lanes_per_row, bool vec);
+ThreadRowKernel get_rows_kernel_rosen(int lanes_per_row, int ndonors);
+ThreadRowKernel get_rows_kernel_corana(int lanes_per_row, int ndonors);
+ThreadRowKernel get_rows_kernel_griewangk(int lanes_per_row, int ndonors);
 }  // namespace mb2
 namespace {
 
@@ -255,16 +262,24 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   ThreadRowKernel ks = nullptr;
   int small_max = env_int("MB2_SMALL_MAXD", kSmallMaxDim);
   if (small_max > kSmallMaxDim) small_max = kSmallMaxDim;
-  // MB2_SMALL_KERNEL: 1 = several rows per warp (default), 2 = one thread per row, 0 = neither
-  const int small_kind = env_int("MB2_SMALL_KERNEL", 1);
-  ThreadRowKernel kw = nullptr;
+  // MB2_SMALL_KERNEL: 3 = K2d rows kernel where it applies, else as 1 (default); 1 = several rows
+  // per warp (generic); 2 = one thread per row; 0 = none of them
+  const int small_kind = env_int("MB2_SMALL_KERNEL", 3);
+  ThreadRowKernel kw = nullptr, kr = nullptr;
   int lpr = 4;
   while (lpr < 32 && lpr * 8 < c->dim) lpr <<= 1;  // about 8 dimensions per lane
+  s = c->sinfo;  // the short-row kernels take the strategy at run time in every mode
   if (!cheb_mma && c->dim <= small_max) {
-    if (small_kind == 2) ks = get_small_kernel(c->cost);
-    else if (small_kind == 1) kw = get_subwarp_kernel(c->cost, lpr, vec);
+    if (small_kind == 3 && c->dim % 4 == 0 && c->dim >= kRowsMinDim && c->dim <= kRowsMaxDim && vec) {
+      lpr = (c->dim <= 64) ? 4 : 8;  // 16 dimensions per lane
+      if (c->cost == MB2_COST_ROSEN) kr = get_rows_kernel_rosen(lpr, s.k);
+      else if (c->cost == MB2_COST_CORANA) kr = get_rows_kernel_corana(lpr, s.k);
+      else if (c->cost == MB2_COST_GRIEWANGK) kr = get_rows_kernel_griewangk(lpr, s.k);
+    }
+    if (kr != nullptr) kw = kr;
+    else if (small_kind == 2) ks = get_small_kernel(c->cost);
+    else if (small_kind == 1 || small_kind == 3) kw = get_subwarp_kernel(c->cost, lpr, vec);
   }
-  s = c->sinfo;  // the thread-per-candidate kernels take the strategy at run time in every mode
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
@@ -282,6 +297,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     smem = (int)(sizeof(double) * (size_t)kChebWarps * (kChebBatch * c->dim + kChebBatch));
     CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc, wpc * 32, smem));
+  } else if (kr != nullptr) {
+    wpc = kRowsWarps;
+    rows_per_cta = kRowsWarps * (32 / lpr);
+    smem = (int)(sizeof(double) * ((size_t)c->dim + (size_t)kRowsWarps * 2 * (32 / lpr) * (c->dim + 2)));
+    CUDA_TRY(cudaFuncSetAttribute(kr, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kr, wpc * 32, smem));
   } else if (kw != nullptr) {
     wpc = kSubWarps;
     rows_per_cta = kSubWarps * (32 / lpr);
@@ -330,6 +351,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   P.mode = mode;
   P.bounds_mode = c->bounds_mode;
   P.bounds_uniform = c->bounds_uniform;
+  P.rows_in_range = (mode == MODE_STEP && in_rows == c->pop[c->cur]) ? c->rows_in_range : 0;
   P.lo_s = c->lo_s;
   P.hi_s = c->hi_s;
   P.F = c->F;
@@ -476,6 +498,7 @@ int mb2_bind_buffers(mb2_ctx* c, double* pop_a, double* pop_b, double* e_a, doub
   c->en[1] = e_b;
   c->cur = 0;
   c->generation = -1;
+  c->rows_in_range = 0;
   return MB2_OK;
 }
 
@@ -517,6 +540,7 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
     c->hi_s = hi[0];
   }
   c->bounds_mode = mode;
+  c->rows_in_range = 0;
   return MB2_OK;
 }
 
@@ -697,6 +721,7 @@ int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const doubl
   ++c->launches;
   CUDA_TRY(cudaStreamSynchronize(s));  // lo/hi are pageable host buffers
   c->generation = -1;
+  c->rows_in_range = 0;
   return MB2_OK;
 }
 
@@ -713,6 +738,7 @@ int mb2_upload_population(mb2_ctx* c, const double* pop_host, void* stream) {
   ++c->launches;
   CUDA_TRY(cudaStreamSynchronize(s));
   c->generation = -1;
+  c->rows_in_range = 0;
   return MB2_OK;
 }
 
@@ -726,6 +752,7 @@ int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy,
   DeviceState st = {best_energy, best_index, 0, 0, generation};
   CUDA_TRY(cudaMemcpy(c->st, &st, sizeof(st), cudaMemcpyHostToDevice));
   c->generation = generation;
+  c->rows_in_range = 0;  // the caller installed rows this context has not checked
   return MB2_OK;
 }
 
@@ -739,6 +766,7 @@ int mb2_eval_initial(mb2_ctx* c, void* stream) {
   if (int rc = launch_finalize(c, 1, s)) return rc;
   c->cur ^= 1;
   c->generation = 0;
+  c->rows_in_range = (c->bounds_mode != BOUNDS_NONE) ? 1 : 0;  // MODE_GEN0 clipped every row
   return MB2_OK;
 }
 

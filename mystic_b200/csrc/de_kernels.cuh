@@ -61,6 +61,7 @@ struct StepParams {
   int mode;     // MODE_*
   int bounds_mode;
   int bounds_uniform;  // 1: every dimension has the same [lo_s, hi_s] (no per-dimension loads)
+  int rows_in_range;   // 1: every row of pop_cur is known to lie inside [lo, hi] (generation 0 clipped it)
   double lo_s, hi_s;
   double F, CR;
   // RNG

@@ -104,6 +104,34 @@ MB2_HD void draw_donors(uint32_t k0, uint32_t k1, uint32_t generation, uint32_t 
   *nstart = (int)mulhi64(r[K], (uint64_t)dim);
 }
 
+// Ranks -> indices: donor i is the rank-th index among those not yet excluded ({candidate,
+// earlier donors}); r[0..K-1] are the donor words, r[K] the word of the start index.
+template <int K>
+MB2_HD void resolve_donors(const uint64_t* r, int64_t cand_local, int64_t np_local, int dim, int64_t* donors,
+                           int* nstart) {
+  int64_t ex[K + 1];  // sorted exclusion list, padded with +inf
+  ex[0] = cand_local;
+#pragma unroll
+  for (int i = 1; i <= K; ++i) ex[i] = INT64_MAX;
+#pragma unroll
+  for (int i = 0; i < K; ++i) {
+    int64_t idx = (int64_t)mulhi64(r[i], (uint64_t)(np_local - 1 - i));
+#pragma unroll
+    for (int e = 0; e <= i; ++e) idx += (idx >= ex[e]) ? 1 : 0;
+    donors[i] = idx;
+    int64_t carry = idx;
+#pragma unroll
+    for (int e = 0; e <= i + 1; ++e) {
+      const int64_t cur = ex[e];
+      if (carry < cur) {
+        ex[e] = carry;
+        carry = cur;
+      }
+    }
+  }
+  *nstart = (int)mulhi64(r[K], (uint64_t)dim);
+}
+
 #if defined(__CUDACC__)
 // Warp-collective variant of draw_donors (same results): lane b computes Philox block b, the
 // 64-bit words are gathered by shuffle, then every lane resolves ranks to indices redundantly.

@@ -49,13 +49,15 @@ def configure(eng, meta):
     eng.set_strategy(sid, meta['F_eff'], meta['CR_eff'])
 
 
-@pytest.fixture(params=['rows_per_warp', 'thread_per_row', 'warp_per_row'])
+@pytest.fixture(params=['rows_tiled', 'rows_per_warp', 'thread_per_row', 'warp_per_row'])
 def kernel_path(request, monkeypatch):
-    """rows of <= 128 dimensions normally run several to a warp (de_subwarp.cuh);
-    MB2_SMALL_KERNEL=2 selects the thread-per-candidate kernel (de_small.cuh) and 0 sends them through
+    """rows of <= 128 dimensions normally run several to a warp: de_rows.cuh (MB2_SMALL_KERNEL=3, the
+    default) where it applies (rosen / corana / griewangk, 16 <= D <= 128, D % 4 == 0), de_subwarp.cuh
+    (1) otherwise; 2 selects the thread-per-candidate kernel (de_small.cuh) and 0 sends them through
     the warp/group-per-row kernels (de_kernels.cuh, de_tma.cuh), so the recordings exercise every
     kernel family"""
-    monkeypatch.setenv('MB2_SMALL_KERNEL', {'rows_per_warp': '1', 'thread_per_row': '2', 'warp_per_row': '0'}[request.param])
+    monkeypatch.setenv('MB2_SMALL_KERNEL', {'rows_tiled': '3', 'rows_per_warp': '1', 'thread_per_row': '2',
+                                            'warp_per_row': '0'}[request.param])
     return request.param
 
 
@@ -158,6 +160,17 @@ PHILOX_CASES = [
     (1000, 30, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
     (129, 30, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 3),
     (6001, 8, 'Rand2Exp', 'griewangk', (), None, None, 0.999, 0.8, 2),
+    # short rows, several to a warp (de_rows.cuh): both group widths, every donor count, windows that
+    # wrap / cover the whole row / are empty, NP that leaves idle groups in the last warp
+    (32, 50, 'Best1Bin', 'rosen', (), (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 6),
+    (128, 41, 'Rand2Exp', 'griewangk', (), (-400., 400., orc.BOUNDS_REJECT), None, 0.97, 0.8, 5),
+    (100, 30, 'Best2Exp', 'rosen', (), None, None, 0.98, 0.7, 5),
+    (64, 37, 'RandToBest1Exp', 'griewangk', (), (-400., 400., orc.BOUNDS_CLAMP), None, 1.0, 0.8, 4),
+    (48, 33, 'Best1Exp', 'corana', (), (-1000., 1000., orc.BOUNDS_REJECT),
+     [dict(ptype='quadratic_inequality', G=[1.] * 48, h=100., k=100, hpow=5),
+      dict(ptype='linear_equality', G=[0.5] * 48, h=3., k=10, hpow=2)], 0.9, 0.8, 6),
+    (16, 19, 'Rand1Exp', 'rosen', (), (-2., 2., orc.BOUNDS_CLAMP), None, 0.0, 0.8, 3),
+    (128, 64, 'Best1Bin', 'corana', (), (-1000., 1000., orc.BOUNDS_CLAMP), None, 0.3, 0.9, 4),
 ]
 
 
@@ -242,9 +255,9 @@ def test_costs_random_batches_match_oracle(kernel_path):
     """every device cost on random batches, several row lengths (vector and scalar load paths)"""
     from mystic_b200 import models
     rng = np.random.default_rng(7)
-    for name, dims, span, extra in (('rosen', (2, 3, 8, 31, 64, 257, 1024), 3., ()),
-                                    ('corana', (1, 2, 3, 4, 9, 64), 1000., ()),
-                                    ('griewangk', (1, 5, 10, 63, 256), 400., ()),
+    for name, dims, span, extra in (('rosen', (2, 3, 8, 16, 31, 64, 100, 128, 257, 1024), 3., ()),
+                                    ('corana', (1, 2, 3, 4, 9, 16, 64, 128), 1000., ()),
+                                    ('griewangk', (1, 5, 10, 20, 63, 64, 128, 256), 400., ()),
                                     ('zimmermann', (2,), 8., ()),
                                     ('chebyshev8cost', (9,), 100., (61,)),
                                     ('chebyshev8cost', (9,), 3., (4096,)),
