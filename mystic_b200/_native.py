@@ -5,6 +5,9 @@ import os
 
 from .build import LIBPATH
 
+# a tuning variant built with `python -m mystic_b200.build --out PATH -D...` (still this CUDA library)
+LIBPATH = os.environ.get('MB2_LIBRARY') or LIBPATH
+
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int32_p = ctypes.POINTER(ctypes.c_int32)
 c_int64_p = ctypes.POINTER(ctypes.c_int64)

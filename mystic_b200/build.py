@@ -48,39 +48,46 @@ def _stale():
 
 
 def _compile(args):
-    src, obj, verbose = args
-    cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
+    src, obj, verbose, extra = args
+    cmd = [_nvcc()] + NVCC_FLAGS + list(extra) + (['-Xptxas', '-v'] if verbose else []) + ['-c', src, '-o', obj]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
     return src, proc.returncode, proc.stdout
 
 
-def build(force=False, verbose=False):
-    """Compile if the library is missing or older than its sources; return its path."""
-    if not force and not _stale():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compile if the library is missing or older than its sources; return its path.
+    `extra_flags` / `out` build a tuning variant (e.g. -DMB2_ROWS_CPT=1) next to the product library;
+    MB2_LIBRARY=<path> makes mystic_b200._native load it."""
+    if out is None and not force and not _stale():
         return LIBPATH
     os.makedirs(OBJDIR, exist_ok=True)
-    jobs = [(os.path.join(CSRC, s), os.path.join(OBJDIR, s[:-3] + '.%d.o' % os.getpid()), verbose) for s in SOURCES]
+    tag = '%d.%s' % (os.getpid(), os.path.basename(out) if out else 'lib')
+    jobs = [(os.path.join(CSRC, s), os.path.join(OBJDIR, s[:-3] + '.%s.o' % tag), verbose, tuple(extra_flags)) for s in SOURCES]
     with concurrent.futures.ThreadPoolExecutor(max_workers=len(jobs)) as pool:
         results = list(pool.map(_compile, jobs))
     objs = [j[1] for j in jobs]
     try:
-        for src, rc, out in results:
+        for src, rc, log in results:
             if verbose:
-                print(out, file=sys.stderr)
+                print(log, file=sys.stderr)
             if rc != 0:
-                raise RuntimeError('nvcc failed on %s:\n%s' % (src, out))
-        tmp = LIBPATH + '.tmp.%d' % os.getpid()
+                raise RuntimeError('nvcc failed on %s:\n%s' % (src, log))
+        target = out or LIBPATH
+        tmp = target + '.tmp.%d' % os.getpid()
         link = subprocess.run([_nvcc(), '-shared', '-gencode', 'arch=compute_100a,code=sm_100a'] + objs + ['-o', tmp],
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True)
         if link.returncode != 0:
             raise RuntimeError('link failed:\n' + link.stdout)
-        os.replace(tmp, LIBPATH)
+        os.replace(tmp, target)
     finally:
         for o in objs:
             if os.path.exists(o):
                 os.remove(o)
-    return LIBPATH
+    return out or LIBPATH
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    # python -m mystic_b200.build [--force] [-v] [--out PATH -DNAME=VALUE ...]
+    argv = sys.argv[1:]
+    out = argv[argv.index('--out') + 1] if '--out' in argv else None
+    print(build(force='--force' in argv, verbose='-v' in argv, extra_flags=[a for a in argv if a.startswith('-D')], out=out))

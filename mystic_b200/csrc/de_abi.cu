@@ -270,7 +270,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   while (lpr < 32 && lpr * 8 < c->dim) lpr <<= 1;  // about 8 dimensions per lane
   s = c->sinfo;  // the short-row kernels take the strategy at run time in every mode
   if (!cheb_mma && c->dim <= small_max) {
-    if (small_kind == 3 && c->dim % 4 == 0 && c->dim >= kRowsMinDim && c->dim <= kRowsMaxDim && vec) {
+    if (small_kind == 3 && c->dim % 4 == 0 && c->dim >= kRowsMinDim && c->dim <= kRowsMaxDim && vec && np <= 0x7fffffff) {
       lpr = (c->dim <= 64) ? 4 : 8;  // 16 dimensions per lane
       if (c->cost == MB2_COST_ROSEN) kr = get_rows_kernel_rosen(lpr, s.k);
       else if (c->cost == MB2_COST_CORANA) kr = get_rows_kernel_corana(lpr, s.k);

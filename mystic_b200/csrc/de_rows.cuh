@@ -5,21 +5,22 @@
 // A group of LPR lanes (4 for D <= 64, 8 for D <= 128) owns a row; a warp works on 32/LPR rows
 // at once, so every per-row step (draws, window bookkeeping, selection) is one SIMT instruction
 // stream for 4-8 rows.  Per chunk of rows:
-//   1. the parent rows are read with 16-byte streaming loads (lane `sub` owns the 4-element
-//      chunks q = sub, sub+LPR, ...) and written to two shared-memory tiles of the warp: the
-//      parent tile (kept for rejected trials) and the trial tile;
-//   2. the draws of a row are spread over the lanes of its group: ONE Philox4x32-10 evaluation
-//      per lane yields the donor blocks (lanes 0..NB-1) and the first crossover blocks (other
-//      lanes) at once; the exponential crossover length is found by ballot over the group and
-//      further rounds of LPR blocks are only computed while some row of the warp needs them
+//   1. the parent rows go global -> shared with 16-byte cp.async copies (consecutive lanes of a
+//      group copy consecutive 16-byte pieces, so every 32-byte sector is requested once) into the
+//      warp's tile; no registers are held while they are in flight;
+//   2. meanwhile the draws of a row are spread over the lanes of its group: ONE Philox4x32-10
+//      evaluation per lane yields the donor blocks (lanes 0..NB-1) and the first crossover blocks
+//      (other lanes) at once; the exponential crossover length is found by ballot over the group
+//      and further rounds of LPR blocks are only computed while some row of the warp needs them
 //      (same counters and words as philox.cuh / oracle/de_oracle.py: results are identical);
-//   3. only the chunks inside the crossover window are visited: lane `sub` of the group takes the
-//      window's chunks sub, sub+LPR, ...; donor segments are 16-byte vector loads along D; the
-//      mutated and clamped chunk goes back to the trial tile;
-//   4. cost and penalty read the trial tile: lane `sub` accumulates its own elements in order and
-//      the group combines the LPR partial sums by a xor tree (corana: lane j evaluates term j and
-//      the four terms are summed in the reference's order);
-//   5. selection picks the tile (trial or parent) that is streamed to the next generation.
+//   3. only the 4-element chunks inside the crossover window are visited: lane `sub` of the group
+//      takes the window's chunks sub, sub+LPR, ...; donor segments are 16-byte vector loads along
+//      D; the trial is built IN PLACE in the tile and the original chunk goes to an undo tile;
+//   4. cost and penalty read the tile: lane `sub` accumulates the chunks q = sub, sub+LPR, ... in
+//      order and the group combines the LPR partial sums by a xor tree (corana: lane j evaluates
+//      term j and the four terms are summed in the reference's order);
+//   5. selection streams the tile to the next generation; a rejected trial takes the window's
+//      chunks from the undo tile instead.
 // The kernel serves every mode (step, generation 0, mb2_eval_cost) for its row lengths, so all
 // energies of a context come from one summation order.
 //
@@ -30,6 +31,12 @@
 
 namespace mb2 {
 
+#ifndef MB2_ROWS_MINBLOCKS
+#define MB2_ROWS_MINBLOCKS 2
+#endif
+#ifndef MB2_ROWS_CPT
+#define MB2_ROWS_CPT 1
+#endif
 constexpr int kRowsWarps = 8;
 constexpr int kRowsTrips = 4;     // 4-element chunks per lane: D <= 16 * LPR
 constexpr int kRowsMinDim = 16;
@@ -167,8 +174,205 @@ __device__ __forceinline__ int first_failure(const u32x4& w, uint64_t thr) {
   return first;
 }
 
+// the draws of one candidate (strategy.py:27,42,48-56)
+template <int K>
+struct RowDraws {
+  int r[K];      // donor rows (the kernel is only used for shards of < 2^31 rows)
+  int nstart;    // first mutated dimension
+  int L;         // exponential crossover length
+};
+
+// Warp-collective: every lane of the warp calls it for the row of its group.
+template <int LPR, int K>
+__device__ __forceinline__ void rows_draw(const StepParams& P, int xover, int64_t cc, int sub, int gbase, RowDraws<K>& d) {
+  constexpr unsigned LMASK = (1u << LPR) - 1u;
+  constexpr int NB = (K + 2) / 2;  // Philox blocks of the donor stream (K donors + start index)
+  const int D = P.dim;
+  const uint32_t cand_g = (uint32_t)(P.global_offset + cc);
+  d.nstart = 0;
+  d.L = 0;
+  if (P.replay) {
+#pragma unroll
+    for (int j = 0; j < K; ++j) d.r[j] = __ldg(P.r_donors + cc * 5 + j);
+    d.nstart = __ldg(P.r_nstart + cc);
+    if (xover == XOVER_EXP) d.L = exp_length_thread(P, cand_g, cc, D);
+    return;
+  }
+  const bool donor_lane = sub < NB;
+  u32x4 v = philox4x32_10((uint32_t)(donor_lane ? sub : sub - NB), cand_g, P.generation,
+                          donor_lane ? STREAM_DONORS : STREAM_XOVER, P.key0, P.key1);
+  const uint64_t even = ((uint64_t)v.x << 32) | v.y, odd = ((uint64_t)v.z << 32) | v.w;
+  uint64_t rw[2 * NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    rw[2 * b] = __shfl_sync(0xffffffffu, even, gbase + b);
+    rw[2 * b + 1] = __shfl_sync(0xffffffffu, odd, gbase + b);
+  }
+  int64_t r64[K];
+  resolve_donors<K>(rw, cc, P.np, D, r64, &d.nstart);
+#pragma unroll
+  for (int j = 0; j < K; ++j) d.r[j] = (int)r64[j];
+  if (xover == XOVER_EXP) {
+    // L = number of leading successes, at most D
+    int first = donor_lane ? 4 : first_failure(v, P.thr);
+    int done = LPR - NB;  // crossover blocks examined so far
+    int L = 0;
+    bool resolved = false;
+    {
+      const unsigned seg = (__ballot_sync(0xffffffffu, first < 4) >> gbase) & LMASK;
+      const int src = seg ? (__ffs(seg) - 1) : sub;
+      const int f = __shfl_sync(0xffffffffu, first, gbase + src);
+      if (seg) {
+        L = 4 * (src - NB) + f;
+        resolved = true;
+      }
+    }
+    while (__any_sync(0xffffffffu, !resolved && 4 * done < D)) {
+      v = philox4x32_10((uint32_t)(done + sub), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+      first = first_failure(v, P.thr);
+      const unsigned seg = (__ballot_sync(0xffffffffu, first < 4) >> gbase) & LMASK;
+      const int src = seg ? (__ffs(seg) - 1) : sub;
+      const int f = __shfl_sync(0xffffffffu, first, gbase + src);
+      if (!resolved && seg) {
+        L = 4 * (done + src) + f;
+        resolved = true;
+      }
+      done += LPR;
+    }
+    if (!resolved || L > D) L = D;
+    d.L = L;
+  }
+}
+
+// the K donor segments of one 4-element chunk
+template <int K>
+struct DonorChunk {
+  double2 v[K][2];
+};
+
+template <int K>
+__device__ __forceinline__ void rows_load_donors(const double* __restrict__ pop, const RowDraws<K>& d, int D, int i0,
+                                                 DonorChunk<K>& dc) {
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    const double* dr = pop + (int64_t)d.r[j] * D + i0;
+    dc.v[j][0] = ld_stream2(dr);
+    dc.v[j][1] = ld_stream2(dr + 2);
+  }
+}
+
+// mutate the crossed elements of chunk q of the trial tile, apply the bounds to them
+template <int K>
+__device__ __forceinline__ bool rows_mutate_chunk(const StepParams& P, int base, int xover, const RowDraws<K>& d, int64_t cc,
+                                                  int q, const DonorChunk<K>& dc, const double* s_best, double* t_trial, double* t_undo) {
+  const int D = P.dim;
+  const int i0 = q << 2;
+  bool cross[4];
+  if (xover == XOVER_BIN) {
+    // strategy.py:79-85: i == n or random() < CR, one draw per dimension
+    if (P.replay) {
+      const double* u = P.r_uni + cc * (int64_t)(D + 1) + i0;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) cross[e] = (i0 + e == d.nstart) || (__ldg(u + e) < P.CR);
+    } else {
+      const u32x4 wv = philox4x32_10((uint32_t)q, (uint32_t)(P.global_offset + cc), P.generation, STREAM_XOVER, P.key0, P.key1);
+      cross[0] = (i0 == d.nstart) || ((uint64_t)wv.x < P.thr);
+      cross[1] = (i0 + 1 == d.nstart) || ((uint64_t)wv.y < P.thr);
+      cross[2] = (i0 + 2 == d.nstart) || ((uint64_t)wv.z < P.thr);
+      cross[3] = (i0 + 3 == d.nstart) || ((uint64_t)wv.w < P.thr);
+    }
+  } else {
+    int rel = i0 - d.nstart;
+    if (rel < 0) rel += D;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int re = rel + e;
+      if (re >= D) re -= D;
+      cross[e] = re < d.L;
+    }
+  }
+  const double2 xa = *reinterpret_cast<const double2*>(t_trial + i0);
+  const double2 xb = *reinterpret_cast<const double2*>(t_trial + i0 + 2);
+  const double x[4] = {xa.x, xa.y, xb.x, xb.y};
+  *reinterpret_cast<double2*>(t_undo + i0) = xa;  // the parent's chunk, for a rejected trial
+  *reinterpret_cast<double2*>(t_undo + i0 + 2) = xb;
+  double bst[4] = {0.0, 0.0, 0.0, 0.0};
+  if (K != 3 && K != 5) {  // Best1, RandToBest1, Best2 read bestSolution
+    const double2 ba = *reinterpret_cast<const double2*>(s_best + i0);
+    const double2 bb = *reinterpret_cast<const double2*>(s_best + i0 + 2);
+    bst[0] = ba.x;
+    bst[1] = ba.y;
+    bst[2] = bb.x;
+    bst[3] = bb.y;
+  }
+  double y[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    double pe[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int j = 0; j < K; ++j) pe[j] = (e == 0) ? dc.v[j][0].x : ((e == 1) ? dc.v[j][0].y : ((e == 2) ? dc.v[j][1].x : dc.v[j][1].y));
+    if (K == 2) {
+      y[e] = (base == BASE_BEST1) ? mutant<BASE_BEST1>(x[e], bst[e], pe, P.F) : mutant<BASE_RANDTOBEST1>(x[e], bst[e], pe, P.F);
+    } else if (K == 3) {
+      y[e] = mutant<BASE_RAND1>(x[e], bst[e], pe, P.F);
+    } else if (K == 4) {
+      y[e] = mutant<BASE_BEST2>(x[e], bst[e], pe, P.F);
+    } else {
+      y[e] = mutant<BASE_RAND2>(x[e], bst[e], pe, P.F);
+    }
+  }
+  bool oob = false;
+  if (P.bounds_mode != BOUNDS_NONE) {
+    double l[4], h[4];
+    if (P.bounds_uniform) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        l[e] = P.lo_s;
+        h[e] = P.hi_s;
+      }
+    } else {
+      const double2 la = __ldg(reinterpret_cast<const double2*>(P.lo + i0)), lb = __ldg(reinterpret_cast<const double2*>(P.lo + i0 + 2));
+      const double2 ha = __ldg(reinterpret_cast<const double2*>(P.hi + i0)), hb = __ldg(reinterpret_cast<const double2*>(P.hi + i0 + 2));
+      l[0] = la.x, l[1] = la.y, l[2] = lb.x, l[3] = lb.y;
+      h[0] = ha.x, h[1] = ha.y, h[2] = hb.x, h[3] = hb.y;
+    }
+    if (P.bounds_mode == BOUNDS_CLAMP) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        y[e] = (y[e] > l[e]) ? y[e] : l[e];  // python max(lo, x)
+        y[e] = (y[e] < h[e]) ? y[e] : h[e];  // python min(hi, x)
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oob |= cross[e] && ((y[e] < l[e]) || (y[e] > h[e]));
+    }
+  }
+  *reinterpret_cast<double2*>(t_trial + i0) = make_double2(cross[0] ? y[0] : x[0], cross[1] ? y[1] : x[1]);
+  *reinterpret_cast<double2*>(t_trial + i0 + 2) = make_double2(cross[2] ? y[2] : x[2], cross[3] ? y[3] : x[3]);
+  return oob;
+}
+
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// a parent row global -> shared without passing through registers: lane `sub` copies the
+// 16-byte pieces sub, sub+LPR, ...
+template <int LPR>
+__device__ __forceinline__ void rows_fetch_parent(const double* __restrict__ prow, int D, int sub, double* tile) {
+#pragma unroll
+  for (int t = 0; t < 2 * kRowsTrips; ++t) {
+    const int i = 2 * (t * LPR + sub);
+    if (i < D) cp_async16(tile + i, prow + i);
+  }
+  cp_async_commit();
+}
+
 template <int COST, int LPR, int K>
-__global__ void __launch_bounds__(kRowsWarps * 32)
+__global__ void __launch_bounds__(kRowsWarps * 32, MB2_ROWS_MINBLOCKS)
     de_step_rows_kernel(const __grid_constant__ StepParams P, int base, int xover, int /*ndonors*/) {
   if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(16) double smem[];
@@ -177,8 +381,8 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
   __shared__ unsigned long long sh_ninf[kRowsWarps], sh_nacc[kRowsWarps];
   constexpr int RPW = 32 / LPR;  // rows per warp
   constexpr unsigned LMASK = (1u << LPR) - 1u;
-  constexpr int NB = (K + 2) / 2;  // Philox blocks of the donor stream (K donors + start index)
-  static_assert(LPR >= 4 && LPR <= 16 && NB < LPR, "group too narrow for the draws");
+  constexpr int CPT = (K <= 3) ? MB2_ROWS_CPT : 1;  // window chunks per lane whose donor loads are issued together
+  static_assert(LPR >= 4 && LPR <= 16 && (K + 2) / 2 < LPR, "group too narrow for the draws");
 
   const int D = P.dim;
   const int NQ = D >> 2;
@@ -190,12 +394,15 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
   const int sub = lane % LPR;
   const int gbase = grp * LPR;
   const bool uni_b = P.bounds_uniform != 0;
+  const bool step = P.mode == MODE_STEP;
   const bool needs_best = (base == BASE_BEST1 || base == BASE_RANDTOBEST1 || base == BASE_BEST2);
-  double* s_best = smem;                                                         // [D]
-  double* t_trial = smem + D + (size_t)warp * (2 * RPW * TS) + (size_t)grp * TS;  // this row's trial tile
-  double* t_parent = t_trial + RPW * TS;
+  // the untouched elements of a trial need no bounds handling when generation 0 clipped the rows
+  const bool check_own = P.bounds_mode != BOUNDS_NONE && !(step && P.rows_in_range);
+  double* s_best = smem;                                                        // [D]
+  double* t_row = smem + D + (size_t)warp * (2 * RPW * TS) + (size_t)grp * TS;  // this row: parent, then trial in place
+  double* t_undo = t_row + RPW * TS;                                             // parent chunks the trial replaced
 
-  if (P.mode == MODE_STEP && needs_best) {
+  if (step && needs_best) {
     for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
   }
   __syncthreads();
@@ -211,91 +418,55 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
     const int64_t c = ch * RPW + grp;
     const bool live = c < P.np;
     const int64_t cc = live ? c : (P.np - 1);  // idle groups shadow the last row and discard the result
-    const double* __restrict__ prow = P.pop_cur + cc * D;
 
-    // ---- 1. parent row: issue the loads first, they are consumed after the draws
-    double2 p[kRowsTrips][2];
-#pragma unroll
-    for (int t = 0; t < kRowsTrips; ++t) {
-      const int q = t * LPR + sub;
-      if (q < NQ) {
-        p[t][0] = ld_stream2(prow + 4 * q);
-        p[t][1] = ld_stream2(prow + 4 * q + 2);
-      } else {
-        p[t][0] = make_double2(0.0, 0.0);
-        p[t][1] = make_double2(0.0, 0.0);
-      }
-    }
+    // ---- 1. parent row -> tile (asynchronous), 2. draws
+    rows_fetch_parent<LPR>(P.pop_cur + cc * D, D, sub, t_row);
     double e_old = CUDART_INF;
-    if (P.mode == MODE_STEP) e_old = __ldg(P.e_cur + cc);
-
-    // ---- 2. draws
-    int64_t r[K];
-    int nstart = 0, L = 0;
-    const uint32_t cand_g = (uint32_t)(P.global_offset + cc);
-    if (P.mode == MODE_STEP) {
-      if (P.replay) {
-#pragma unroll
-        for (int j = 0; j < K; ++j) r[j] = __ldg(P.r_donors + cc * 5 + j);
-        nstart = __ldg(P.r_nstart + cc);
-        if (xover == XOVER_EXP) L = exp_length_thread(P, cand_g, cc, D);
-      } else {
-        const bool donor_lane = sub < NB;
-        u32x4 v = philox4x32_10((uint32_t)(donor_lane ? sub : sub - NB), cand_g, P.generation,
-                                donor_lane ? STREAM_DONORS : STREAM_XOVER, P.key0, P.key1);
-        const uint64_t even = ((uint64_t)v.x << 32) | v.y, odd = ((uint64_t)v.z << 32) | v.w;
-        uint64_t rw[2 * NB];
-#pragma unroll
-        for (int b = 0; b < NB; ++b) {
-          rw[2 * b] = __shfl_sync(0xffffffffu, even, gbase + b);
-          rw[2 * b + 1] = __shfl_sync(0xffffffffu, odd, gbase + b);
-        }
-        resolve_donors<K>(rw, cc, P.np, D, r, &nstart);
-        if (xover == XOVER_EXP) {
-          // strategy.py:48-56: L = number of leading successes, at most D
-          int first = donor_lane ? 4 : first_failure(v, P.thr);
-          int done = LPR - NB;  // crossover blocks examined so far
-          bool resolved = false;
-          {
-            const unsigned seg = (__ballot_sync(0xffffffffu, first < 4) >> gbase) & LMASK;
-            const int src = seg ? (__ffs(seg) - 1) : sub;
-            const int f = __shfl_sync(0xffffffffu, first, gbase + src);
-            if (seg) {
-              L = 4 * (src - NB) + f;
-              resolved = true;
-            }
-          }
-          while (__any_sync(0xffffffffu, !resolved && 4 * done < D)) {
-            v = philox4x32_10((uint32_t)(done + sub), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-            first = first_failure(v, P.thr);
-            const unsigned seg = (__ballot_sync(0xffffffffu, first < 4) >> gbase) & LMASK;
-            const int src = seg ? (__ffs(seg) - 1) : sub;
-            const int f = __shfl_sync(0xffffffffu, first, gbase + src);
-            if (!resolved && seg) {
-              L = 4 * (done + src) + f;
-              resolved = true;
-            }
-            done += LPR;
-          }
-          if (!resolved || L > D) L = D;
-        }
+    RowDraws<K> dr;
+    int q0 = 0, nq = 0;
+    if (step) {
+      e_old = __ldg(P.e_cur + cc);
+      rows_draw<LPR, K>(P, xover, cc, sub, gbase, dr);
+      nq = NQ;
+      if (xover == XOVER_EXP) {
+        q0 = dr.nstart >> 2;
+        nq = (dr.L > 0) ? (((dr.nstart + dr.L - 1) >> 2) - q0 + 1) : 0;
+        if (nq > NQ) nq = NQ;  // a full-length window that starts inside a chunk: each chunk once
       }
     }
 
-    // ---- own chunks -> tiles (generation 0: clipped into the strict range first)
-    bool oob = false;
+    // ---- 3. crossover window: chunks q0 .. q0+nq-1 (mod NQ); the donor loads of the lane's first
+    // CPT chunks are issued before the parent row is waited for
+    DonorChunk<K> dc[CPT];
+    int qs[CPT];
+    if (step) {
 #pragma unroll
-    for (int t = 0; t < kRowsTrips; ++t) {
-      const int q = t * LPR + sub;
-      if (q < NQ) {
-        double x[4] = {p[t][0].x, p[t][0].y, p[t][1].x, p[t][1].y};
-        if (P.mode == MODE_STEP) {
-          *reinterpret_cast<double2*>(t_parent + 4 * q) = p[t][0];
-          *reinterpret_cast<double2*>(t_parent + 4 * q + 2) = p[t][1];
-        }
-        // a parent row is inside the range once generation 0 has clipped it (rows_in_range);
-        // otherwise the untouched elements of the trial are treated like the reference treats them
-        if (P.bounds_mode != BOUNDS_NONE && !(P.mode == MODE_STEP && P.rows_in_range)) {
+      for (int u = 0; u < CPT; ++u) {
+        int q = q0 + sub + u * LPR;
+        if (q >= NQ) q -= NQ;
+        qs[u] = q;
+        if (sub + u * LPR < nq) rows_load_donors<K>(P.pop_cur, dr, D, q << 2, dc[u]);
+      }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+
+    bool oob = false;
+    if (check_own) {
+      // generation 0: clip into the strict range (differential_evolution.py:516-520); evaluation:
+      // range test; a step whose parents were not clipped by this context: the whole trial is
+      // clamped / tested like the reference does, and the raw parent is kept in the undo tile
+#pragma unroll
+      for (int t = 0; t < kRowsTrips; ++t) {
+        const int q = t * LPR + sub;
+        if (q < NQ) {
+          const double2 pa = *reinterpret_cast<const double2*>(t_row + 4 * q);
+          const double2 pb = *reinterpret_cast<const double2*>(t_row + 4 * q + 2);
+          double x[4] = {pa.x, pa.y, pb.x, pb.y};
+          if (step) {
+            *reinterpret_cast<double2*>(t_undo + 4 * q) = pa;
+            *reinterpret_cast<double2*>(t_undo + 4 * q + 2) = pb;
+          }
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const double l = uni_b ? P.lo_s : __ldg(P.lo + 4 * q + e);
@@ -303,111 +474,31 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
             if (P.mode == MODE_GEN0) {
               x[e] = fmin(fmax(x[e], l), h);
               oob |= (x[e] < l) || (x[e] > h);
-            } else if (P.mode == MODE_STEP && P.bounds_mode == BOUNDS_CLAMP) {
+            } else if (step && P.bounds_mode == BOUNDS_CLAMP) {
               x[e] = (x[e] > l) ? x[e] : l;  // python max(lo, x)
               x[e] = (x[e] < h) ? x[e] : h;  // python min(hi, x)
             } else {
               oob |= (x[e] < l) || (x[e] > h);
             }
           }
+          *reinterpret_cast<double2*>(t_row + 4 * q) = make_double2(x[0], x[1]);
+          *reinterpret_cast<double2*>(t_row + 4 * q + 2) = make_double2(x[2], x[3]);
         }
-        *reinterpret_cast<double2*>(t_trial + 4 * q) = make_double2(x[0], x[1]);
-        *reinterpret_cast<double2*>(t_trial + 4 * q + 2) = make_double2(x[2], x[3]);
       }
+      __syncwarp();
     }
-    __syncwarp();
 
-    // ---- 3. crossover window: chunks q0 .. q0+nq-1 (mod NQ) of the trial tile
-    if (P.mode == MODE_STEP) {
-      int q0 = 0, nq = NQ;
-      if (xover == XOVER_EXP) {
-        q0 = nstart >> 2;
-        nq = (L > 0) ? (((nstart + L - 1) >> 2) - q0 + 1) : 0;
-        if (nq > NQ) nq = NQ;  // a full-length window that starts inside a chunk: each chunk once
+    if (step) {
+#pragma unroll
+      for (int u = 0; u < CPT; ++u) {
+        if (sub + u * LPR < nq) oob |= rows_mutate_chunk<K>(P, base, xover, dr, cc, qs[u], dc[u], s_best, t_row, t_undo);
       }
-      const double* __restrict__ d0 = P.pop_cur + r[0] * D;
-      const double* __restrict__ d1 = P.pop_cur + r[1] * D;
-      const double* __restrict__ d2 = P.pop_cur + r[K > 2 ? 2 : 0] * D;
-      const double* __restrict__ d3 = P.pop_cur + r[K > 3 ? 3 : 0] * D;
-      const double* __restrict__ d4 = P.pop_cur + r[K > 4 ? 4 : 0] * D;
-      for (int w = sub; w < nq; w += LPR) {
+      for (int w = sub + CPT * LPR; w < nq; w += LPR) {  // long windows: the remaining chunks
         int q = q0 + w;
         if (q >= NQ) q -= NQ;
-        const int i0 = q << 2;
-        bool cross[4];
-        if (xover == XOVER_BIN) {
-          // strategy.py:79-85: i == n or random() < CR, one draw per dimension
-          if (P.replay) {
-            const double* u = P.r_uni + cc * (int64_t)(D + 1) + i0;
-#pragma unroll
-            for (int e = 0; e < 4; ++e) cross[e] = (i0 + e == nstart) || (__ldg(u + e) < P.CR);
-          } else {
-            const u32x4 wv = philox4x32_10((uint32_t)q, cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-            cross[0] = (i0 == nstart) || ((uint64_t)wv.x < P.thr);
-            cross[1] = (i0 + 1 == nstart) || ((uint64_t)wv.y < P.thr);
-            cross[2] = (i0 + 2 == nstart) || ((uint64_t)wv.z < P.thr);
-            cross[3] = (i0 + 3 == nstart) || ((uint64_t)wv.w < P.thr);
-          }
-        } else {
-          int rel = i0 - nstart;
-          if (rel < 0) rel += D;
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            int re = rel + e;
-            if (re >= D) re -= D;
-            cross[e] = re < L;
-          }
-        }
-        if (cross[0] | cross[1] | cross[2] | cross[3]) {
-          double dn[5][4];
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            if (j < K) {
-              const double* dr = (j == 0) ? d0 : ((j == 1) ? d1 : ((j == 2) ? d2 : ((j == 3) ? d3 : d4)));
-              const double2 a = ld_stream2(dr + i0), b = ld_stream2(dr + i0 + 2);
-              dn[j][0] = a.x;
-              dn[j][1] = a.y;
-              dn[j][2] = b.x;
-              dn[j][3] = b.y;
-            } else {
-#pragma unroll
-              for (int e = 0; e < 4; ++e) dn[j][e] = 0.0;
-            }
-          }
-          const double2 xa = *reinterpret_cast<const double2*>(t_trial + i0);
-          const double2 xb = *reinterpret_cast<const double2*>(t_trial + i0 + 2);
-          double x[4] = {xa.x, xa.y, xb.x, xb.y};
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (cross[e]) {
-              const double pe[5] = {dn[0][e], dn[1][e], dn[2][e], dn[3][e], dn[4][e]};
-              const double b = needs_best ? s_best[i0 + e] : 0.0;
-              double y;
-              if (K == 2) {
-                y = (base == BASE_BEST1) ? mutant<BASE_BEST1>(x[e], b, pe, P.F) : mutant<BASE_RANDTOBEST1>(x[e], b, pe, P.F);
-              } else if (K == 3) {
-                y = mutant<BASE_RAND1>(x[e], b, pe, P.F);
-              } else if (K == 4) {
-                y = mutant<BASE_BEST2>(x[e], b, pe, P.F);
-              } else {
-                y = mutant<BASE_RAND2>(x[e], b, pe, P.F);
-              }
-              if (P.bounds_mode != BOUNDS_NONE) {
-                const double l = uni_b ? P.lo_s : __ldg(P.lo + i0 + e);
-                const double h = uni_b ? P.hi_s : __ldg(P.hi + i0 + e);
-                if (P.bounds_mode == BOUNDS_CLAMP) {
-                  y = (y > l) ? y : l;
-                  y = (y < h) ? y : h;
-                } else {
-                  oob |= (y < l) || (y > h);
-                }
-              }
-              x[e] = y;
-            }
-          }
-          *reinterpret_cast<double2*>(t_trial + i0) = make_double2(x[0], x[1]);
-          *reinterpret_cast<double2*>(t_trial + i0 + 2) = make_double2(x[2], x[3]);
-        }
+        DonorChunk<K> dx;
+        rows_load_donors<K>(P.pop_cur, dr, D, q << 2, dx);
+        oob |= rows_mutate_chunk<K>(P, base, xover, dr, cc, q, dx, s_best, t_row, t_undo);
       }
     }
     // any lane of the group out of range?
@@ -418,13 +509,13 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
     // shadow row because the shuffles inside need every lane
     double E = CUDART_INF;
     {
-      const double cost = rows_cost<COST, LPR>(t_trial, NQ, sub, gbase, P.cost);
+      const double cost = rows_cost<COST, LPR>(t_row, NQ, sub, gbase, P.cost);
       if (!oob) E = cost;
-      E = dadd(E, rows_penalty<LPR>(t_trial, D, NQ, sub, P.pen));
+      E = dadd(E, rows_penalty<LPR>(t_row, D, NQ, sub, P.pen));
     }
 
     if (live && P.cap_trial != nullptr && P.mode != MODE_EVAL) {
-      for (int i = sub; i < D; i += LPR) P.cap_trial[c * D + i] = t_trial[i];
+      for (int i = sub; i < D; i += LPR) P.cap_trial[c * D + i] = t_row[i];
       if (sub == 0) P.cap_energy[c] = E;
     }
 
@@ -433,16 +524,18 @@ __global__ void __launch_bounds__(kRowsWarps * 32)
       if (live && sub == 0) P.e_next[c] = E;
     } else if (live) {
       const bool acc = E < e_old;
-      const double* src = (acc || P.mode == MODE_GEN0) ? t_trial : t_parent;
+      const bool keep = acc || P.mode == MODE_GEN0;
       double* __restrict__ nrow = P.pop_next + c * D;
 #pragma unroll
-      for (int t = 0; t < kRowsTrips; ++t) {
-        const int q = t * LPR + sub;
-        if (q < NQ) {
-          const double2 a = *reinterpret_cast<const double2*>(src + 4 * q);
-          const double2 b = *reinterpret_cast<const double2*>(src + 4 * q + 2);
-          st_stream2(nrow + 4 * q, a.x, a.y);
-          st_stream2(nrow + 4 * q + 2, b.x, b.y);
+      for (int t = 0; t < 2 * kRowsTrips; ++t) {
+        const int i = 2 * (t * LPR + sub);  // 16-byte piece of chunk i/4
+        if (i < D) {
+          int rq = (i >> 2) - q0;
+          if (rq < 0) rq += NQ;
+          // a rejected trial: chunks the window (or the clamp of the whole row) replaced come from the undo tile
+          const bool undo = !keep && (check_own || rq < nq);
+          const double2 a = *reinterpret_cast<const double2*>((undo ? t_undo : t_row) + i);
+          st_stream2(nrow + i, a.x, a.y);
         }
       }
       if (sub == 0) {
