@@ -208,6 +208,11 @@ int mb2_eval_cost(mb2_ctx* ctx, const double* x_dev, int64_t n, double* out_dev,
  * returns the number of mismatches (expected 0).  Requires mb2_set_cost(GRIEWANGK) first. */
 int mb2_selftest_division(mb2_ctx* ctx, int64_t n, uint64_t seed, double span, int64_t* mismatches);
 
+/* Self-test of the griewangk cosine (cos_bounded in csrc/de_device.cuh, which replaces math.cos of
+ * mystic/models/storn.py:139 on the device): max |cos_bounded(a) - cos(a)| over n arguments drawn
+ * uniformly from [-span, span], span <= 1e5.  Synchronises. */
+int mb2_selftest_cosine(mb2_ctx* ctx, int64_t n, uint64_t seed, double span, double* max_abs_err);
+
 /* launch geometry of the fused kernel (for bench.py / profiling): CTAs, threads, dynamic smem */
 int mb2_launch_info(mb2_ctx* ctx, int32_t* grid, int32_t* block, int32_t* smem_bytes);
 /* number of kernels this library has launched through the context (bench.py gpu_launches) */

@@ -83,7 +83,8 @@ struct mb2_ctx {
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
-  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr};
+  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0};
+  double bounds_absmax = 0.0;  // max(|lo_i|, |hi_i|) of the strict range
   double* cheb_vfrag = nullptr;
   int cheb_ks = 0;
   double* cheb_x = nullptr;
@@ -365,6 +366,9 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   P.r_nstart = c->r_nstart;
   P.r_uni = c->r_uni;
   P.cost = c->cp;
+  // rows inside a finite strict range (generation 0 clips, trials are clamped or rejected; the
+  // energy of an out-of-range row is inf whatever its cost evaluates to): guard-free griewangk factors
+  P.cost.grw_bounded = (c->bounds_mode != BOUNDS_NONE && c->bounds_absmax <= kCosFastMax) ? 1 : 0;
   P.pen = c->pp;
   P.part_e = c->part_e;
   P.part_idx = c->part_idx;
@@ -536,6 +540,9 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
     bool uni = true;
     for (int i = 1; i < c->dim; ++i) uni = uni && lo[i] == lo[0] && hi[i] == hi[0];
     c->bounds_uniform = uni ? 1 : 0;
+    double am = 0.0;
+    for (int i = 0; i < c->dim; ++i) am = fmax(am, fmax(fabs(lo[i]), fabs(hi[i])));
+    c->bounds_absmax = am;
     c->lo_s = lo[0];
     c->hi_s = hi[0];
   }
@@ -647,6 +654,21 @@ int mb2_selftest_division(mb2_ctx* c, int64_t n, uint64_t seed, double span, int
   CUDA_TRY(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
   ++c->launches;
   *mismatches = (int64_t)h;
+  return MB2_OK;
+}
+
+int mb2_selftest_cosine(mb2_ctx* c, int64_t n, uint64_t seed, double span, double* max_abs_err) {
+  if (c == nullptr || max_abs_err == nullptr || n < 1 || !(span <= kCosFastMax)) return fail(MB2_EINVAL, "bad argument");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (int rc = ensure_parts(c, 1)) return rc;
+  unsigned long long* d = c->part_ninf;  // scratch: not in use between generations
+  CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
+  selftest_cosine_kernel<<<c->sm_count * 8, 256>>>(n, (uint32_t)seed, (uint32_t)(seed >> 32), span, d);
+  CUDA_TRY(cudaGetLastError());
+  unsigned long long h = 0;
+  CUDA_TRY(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  ++c->launches;
+  memcpy(max_abs_err, &h, sizeof(h));
   return MB2_OK;
 }
 

@@ -165,6 +165,7 @@ struct CostParams {
   // griewangk (models/storn.py:135-139): per-dimension {sqrt(i+1), RN(1/sqrt(i+1))}, both
   // correctly rounded on the host, so the kernel needs neither a square root nor a divide
   const double2* grw_tab;
+  int grw_bounded;  // 1: the strict range keeps every |x_i| <= kCosFastMax (guard-free factors)
 };
 
 // c / s with r = RN(1/s): two Markstein refinement steps on top of c*r give the correctly
@@ -179,6 +180,48 @@ __device__ __forceinline__ double div_by_table(double c, double s, double r) {
   // divide; s >= 1, so the quotient itself never overflows for finite c
   if (!(fabs(c) < 1e300)) return c / s;
   return q2;
+}
+
+// cos(a) for |a| <= kCosFastMax, built for the griewangk product (models/storn.py:139): reduce by
+// multiples of pi with a two-part Cody-Waite step (exact first FMA), then ONE even polynomial on
+// [-pi/2, pi/2] (Remez fit of cos(sqrt(u)), degree 9 in u = t^2, truncation 6e-21) and the sign
+// from the parity of the multiple.  ABSOLUTE error <= 1.6e-16 (checked against mpmath), which is
+// what a factor of the product needs: a factor near zero carries its error into the product
+// scaled by the other factors (<= 1).  16 instructions instead of ~50 for the general cos with
+// its sin/cos kernel selection; no branches.
+constexpr double kCosFastMax = 1.0e5;
+__device__ __forceinline__ double cos_bounded(double a) {
+  const double kMagic = 6755399441055744.0;  // 1.5 * 2^52: the sum's low mantissa bits hold rint(a/pi)
+  const double big = __fma_rn(a, 0.31830988618379069, kMagic);
+  const int q = __double2loint(big);
+  const double j = __dsub_rn(big, kMagic);
+  double t = __fma_rn(-j, 3.1415926535897931, a);
+  t = __fma_rn(-j, 1.2246467991473532e-16, t);
+  const double u = __dmul_rn(t, t);
+  double p = -1.51196479263702045e-16;
+  p = __fma_rn(p, u, 4.77687040278621769e-14);
+  p = __fma_rn(p, u, -1.14706700869031000e-11);
+  p = __fma_rn(p, u, 2.08767556647971772e-09);
+  p = __fma_rn(p, u, -2.75573192096311045e-07);
+  p = __fma_rn(p, u, 2.48015873014924644e-05);
+  p = __fma_rn(p, u, -1.38888888888885295e-03);
+  p = __fma_rn(p, u, 4.16666666666666574e-02);
+  p = __fma_rn(p, u, -5.00000000000000000e-01);
+  p = __fma_rn(p, u, 1.0);
+  return __hiloint2double(__double2hiint(p) ^ (q << 31), __double2loint(p));
+}
+
+// One factor of the griewangk product: cos(c / sqrt(i+1)) with {s, r} = {sqrt(i+1), RN(1/sqrt(i+1))}.
+// `bounded`: |c| <= kCosFastMax is guaranteed by the strict range, so the guards are dropped (a
+// tiny |c| whose residuals underflow still gives a quotient that is tiny, and cos of it is 1).
+__device__ __forceinline__ double grw_factor(double c, double s, double r, bool bounded) {
+  if (bounded) {
+    const double q0 = __dmul_rn(c, r);
+    const double q1 = __fma_rn(__fma_rn(-q0, s, c), r, q0);
+    return cos_bounded(__fma_rn(__fma_rn(-q1, s, c), r, q1));
+  }
+  const double q = div_by_table(c, s, r);
+  return (fabs(q) <= kCosFastMax) ? cos_bounded(q) : cos(q);
 }
 
 enum : int { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4 };
@@ -255,7 +298,7 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
       sa[m] = 0.0;
       pa[m] = 1.0;
     }
-    if ((D & 255) == 0) {  // whole blocks of 256 virtual threads: no per-element guard
+    if ((D & 255) == 0 && cp.grw_bounded) {  // whole blocks of 256 virtual threads, bounded arguments: no guards
       for (int i0 = g.tig; i0 < D; i0 += 256) {
 #pragma unroll
         for (int m = 0; m < NA; ++m) {
@@ -263,7 +306,7 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
           const double c = xs[i];
           sa[m] = dadd(sa[m], dmul(c, c));
           const double2 t = __ldg(cp.grw_tab + i);  // {sqrt(i+1), 1/sqrt(i+1)}
-          pa[m] = dmul(pa[m], cos(div_by_table(c, t.x, t.y)));
+          pa[m] = dmul(pa[m], grw_factor(c, t.x, t.y, true));
         }
       }
     } else {
@@ -275,7 +318,7 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
             const double c = xs[i];
             sa[m] = dadd(sa[m], dmul(c, c));
             const double2 t = __ldg(cp.grw_tab + i);
-            pa[m] = dmul(pa[m], cos(div_by_table(c, t.x, t.y)));
+            pa[m] = dmul(pa[m], grw_factor(c, t.x, t.y, cp.grw_bounded != 0));
           }
         }
       }

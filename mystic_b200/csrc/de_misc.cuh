@@ -168,6 +168,20 @@ __global__ void selftest_division_kernel(int64_t n, uint32_t k0, uint32_t k1, do
   if (bad) atomicAdd(mismatches, bad);
 }
 
+// max |cos_bounded(a) - cos(a)| over n arguments uniform in [-span, span] (bits of the maximum,
+// positive doubles order like their bit patterns)
+__global__ void selftest_cosine_kernel(int64_t n, uint32_t k0, uint32_t k1, double span, unsigned long long* max_bits) {
+  double worst = 0.0;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const u32x4 v = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), 11u, 13u, k0, k1);
+    const double u = u64_to_unit(((uint64_t)v.x << 32) | v.y);
+    const double a = (2.0 * u - 1.0) * span;
+    const double e = fabs(cos_bounded(a) - cos(a));
+    if (!(e <= worst)) worst = e;  // NaN sticks
+  }
+  atomicMax(max_bits, (unsigned long long)__double_as_longlong(worst));
+}
+
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
 }

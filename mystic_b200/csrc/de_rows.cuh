@@ -120,7 +120,7 @@ __device__ __forceinline__ double rows_cost(const double* xs, int NQ, int sub, i
         for (int e = 0; e < 4; ++e) {
           s = dadd(s, dmul(x[e], x[e]));
           const double2 tb = __ldg(cp.grw_tab + 4 * q + e);
-          p = dmul(p, cos(div_by_table(x[e], tb.x, tb.y)));
+          p = dmul(p, grw_factor(x[e], tb.x, tb.y, cp.grw_bounded != 0));
         }
       }
     }

@@ -89,7 +89,7 @@ __device__ __forceinline__ double thread_cost(const double* x, int D, const Cost
     for (int i = 0; i < D; ++i) s = dadd(s, dmul(x[i], x[i]));
     for (int i = 0; i < D; ++i) {
       const double2 t = __ldg(cp.grw_tab + i);
-      p = dmul(p, cos(div_by_table(x[i], t.x, t.y)));
+      p = dmul(p, grw_factor(x[i], t.x, t.y, cp.grw_bounded != 0));
     }
     return dadd(dsub(s / 4000.0, p), 1.0);
   } else if (COST == COST_ZIMMERMANN) {

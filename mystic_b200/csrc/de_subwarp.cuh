@@ -72,7 +72,7 @@ __device__ __forceinline__ double seg_cost(const double* xs, int D, int sub, con
       const double c = xs[i];
       s = dadd(s, dmul(c, c));
       const double2 t = __ldg(cp.grw_tab + i);
-      p = dmul(p, cos(div_by_table(c, t.x, t.y)));
+      p = dmul(p, grw_factor(c, t.x, t.y, cp.grw_bounded != 0));
     }
     s = seg_reduce<LPR, false>(s);
     p = seg_reduce<LPR, true>(p);

@@ -216,6 +216,11 @@ class DeviceEngine(object):
         check(lib.mb2_selftest_division(self._ctx, int(n), int(seed), float(span), ctypes.byref(bad)))
         return bad.value
 
+    def selftest_cosine(self, n, seed=1, span=400.0):
+        worst = ctypes.c_double(-1.0)
+        check(lib.mb2_selftest_cosine(self._ctx, int(n), int(seed), float(span), ctypes.byref(worst)))
+        return worst.value
+
     def launch_info(self):
         g, b, s = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
         check(lib.mb2_launch_info(self._ctx, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
