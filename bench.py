@@ -214,8 +214,14 @@ def main():
     ap.add_argument('--np', type=int, default=0, help='override rows per GPU (testing)')
     ap.add_argument('--ref-np', type=int, default=4096, help='rows of the bounded CPU sample')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='multi-GPU best exchange: stores into peer memory fused into the epilogue kernel, or an NCCL all-gather')
     ap.add_argument('--sustain', type=float, default=0.7, help='seconds of un-timed load before the timed region')
     args = ap.parse_args()
+    os.environ['MB2_EXCHANGE'] = args.exchange
+    if os.environ.get('MB2_BENCH_DEBUG'):
+        import faulthandler
+        faulthandler.dump_traceback_later(90, exit=True)   # a hung run prints where it hangs
     w = dict(WORKLOADS[args.workload])
     if args.np:
         w['np'] = args.np
@@ -372,7 +378,8 @@ def main():
                    % (NP_local * D * 8 / 2 ** 20), 'grid': grid, 'block': block, 'smem_bytes': smem,
                    'inf_fraction': inf_frac, 'accept_fraction': acc_frac,
                    'sustain_s_before_timing': args.sustain, 'burst_ms_per_step': burst_ms / steps,
-                   'parallelism': 'candidate-sharded x%d, all-gather best per generation' % world if distributed
+                   'parallelism': ('candidate-sharded x%d, ' % world) + ('best exchange by peer-memory stores (NVLink) fused into the argmin epilogue'
+                                                                          if args.exchange == 'peer' else 'NCCL all-gather of the bests per generation') if distributed
                    else 'single GPU'},
         'roofline': roofline,
         'e2e': {'value': NP_global * steps / e2e_s, 'unit': 'candidate-evals/s',

@@ -195,6 +195,27 @@ int mb2_run_result(mb2_ctx* ctx, int32_t* executed, int32_t* stopped, void* stre
 int mb2_pack_best(mb2_ctx* ctx, double* record_dev, void* stream);
 int mb2_merge_best(mb2_ctx* ctx, const double* records_dev, int32_t world, void* stream);
 
+/* The same exchange WITHOUT a collective library call: fused into the argmin epilogue of
+ * mb2_eval_initial / mb2_step as stores into peer memory over NVLink.
+ *   mb2_exchange_open     allocates this rank's mailbox and returns its CUDA IPC handle
+ *                         (handle_bytes >= 64);
+ *   mb2_exchange_connect  takes the handles of all ranks ([world][handle_bytes], exchanged by the
+ *                         caller, e.g. torch.distributed.all_gather_object) and maps the peers'
+ *                         mailboxes; from then on every mb2_eval_initial / mb2_step of this context
+ *                         ends with the exchange, and every rank must make the same sequence of calls;
+ *   mb2_exchange_connected  1 when mb2_exchange_open adopted the mailbox and peer mappings an
+ *                         earlier, destroyed context of this process left behind (same device, world,
+ *                         rank and dim): the handle round trip is not needed IF EVERY rank adopted
+ *                         (the caller checks that with one small reduction); otherwise
+ *   mb2_exchange_reset    drops what was adopted, and mb2_exchange_open then starts afresh;
+ *   mb2_exchange_best     runs the exchange alone (after mb2_restore_state).
+ * A peer that does not deliver within 5 s makes the next mb2_read_result fail. One node, <= 16 ranks. */
+int mb2_exchange_open(mb2_ctx* ctx, int32_t world, int32_t rank, void* handle_out, int32_t handle_bytes);
+int mb2_exchange_connect(mb2_ctx* ctx, const void* handles, int32_t handle_bytes);
+int mb2_exchange_connected(mb2_ctx* ctx);
+int mb2_exchange_reset(mb2_ctx* ctx);
+int mb2_exchange_best(mb2_ctx* ctx, void* stream);
+
 /* synchronises `stream`, then returns the generation result and bestSolution (dim doubles;
  * x_host may be NULL) */
 int mb2_read_result(mb2_ctx* ctx, mb2_result* out, double* x_host, void* stream);

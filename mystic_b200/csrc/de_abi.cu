@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -132,9 +133,32 @@ struct mb2_ctx {
   int run_cur0 = 0;
   int64_t run_gen0 = 0;
   int run_enqueued = 0;
+  // peer-memory best exchange (sharded population): this rank's mailbox, the peers' mailboxes as
+  // mapped here, the epoch of the last exchange
+  ExchangeParams xp = {};
+  double* mailbox = nullptr;
+  size_t mailbox_bytes = 0;
+  void* peer_maps[kMaxWorld] = {};
+  int xchg_connected = 0;
+  int xchg_no_adopt = 0;  // after mb2_exchange_reset: open a fresh mailbox
+  int* h_xerr = nullptr;  // pinned
 };
 
 namespace {
+
+// Mailboxes of destroyed contexts are parked here with their peer mappings: the next context of
+// this process with the same (device, world, rank, slot size) adopts them instead of repeating
+// cudaMalloc + the IPC handle round trip + cudaIpcOpenMemHandle per peer (milliseconds).  Every
+// rank runs the same sequence of solvers, so all ranks adopt or none does.
+struct ParkedChannel {
+  int device;
+  ExchangeParams xp;
+  double* mailbox;
+  size_t bytes;
+  void* peer_maps[kMaxWorld];
+};
+std::mutex g_park_mutex;
+std::vector<ParkedChannel> g_parked;
 
 int dev_alloc(mb2_ctx* c, size_t bytes, void** out) {
   const size_t need = (bytes + 255) & ~(size_t)255;
@@ -396,10 +420,21 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   return MB2_OK;
 }
 
+ExchangeParams next_exchange(mb2_ctx* c) {
+  ExchangeParams X = c->xp;
+  if (c->xchg_connected) {
+    X.epoch = ++c->xp.epoch;
+  } else {
+    X.world = 1;
+  }
+  return X;
+}
+
 int launch_finalize(mb2_ctx* c, int gen0, cudaStream_t stream) {
   de_finalize_kernel<<<1, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
                                             c->pop[c->cur ^ 1], c->dim, c->offset, gen0, c->generation + 1,
-                                            c->best_x, c->st, (c->run_active && !gen0) ? c->run : nullptr);
+                                            c->best_x, c->st, (c->run_active && !gen0) ? c->run : nullptr,
+                                            next_exchange(c));
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
   return MB2_OK;
@@ -486,6 +521,24 @@ int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int
 int mb2_destroy(mb2_ctx* c) {
   if (c == nullptr) return MB2_OK;
   cudaSetDevice(c->device);
+  if (c->mailbox != nullptr) {
+    int err = 1;
+    if (c->xchg_connected && cudaDeviceSynchronize() == cudaSuccess &&
+        cudaMemcpy(&err, c->xp.error, sizeof(int), cudaMemcpyDeviceToHost) == cudaSuccess && err == 0) {
+      ParkedChannel pc;
+      pc.device = c->device;
+      pc.xp = c->xp;
+      pc.mailbox = c->mailbox;
+      pc.bytes = c->mailbox_bytes;
+      memcpy(pc.peer_maps, c->peer_maps, sizeof(pc.peer_maps));
+      std::lock_guard<std::mutex> lock(g_park_mutex);
+      g_parked.push_back(pc);
+    } else {
+      for (int r = 0; r < kMaxWorld; ++r)
+        if (c->peer_maps[r] != nullptr) cudaIpcCloseMemHandle(c->peer_maps[r]);
+      cudaFree(c->mailbox);
+    }
+  }
   for (void* p : c->owned_dev) cudaFree(p);
   for (void* p : c->owned_host) cudaFreeHost(p);
   delete c;
@@ -908,13 +961,116 @@ int mb2_merge_best(mb2_ctx* c, const double* records, int32_t world, void* strea
   return MB2_OK;
 }
 
+int mb2_exchange_open(mb2_ctx* c, int32_t world, int32_t rank, void* handle_out, int32_t handle_bytes) {
+  if (c == nullptr || handle_out == nullptr) return fail(MB2_EINVAL, "NULL argument");
+  if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world)
+    return fail(MB2_EINVAL, "world %d / rank %d out of range (2..%d ranks)", world, rank, kMaxWorld);
+  if (handle_bytes < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail(MB2_EINVAL, "handle buffer too small");
+  if (c->mailbox != nullptr) return fail(MB2_ESTATE, "exchange already opened");
+  CUDA_TRY(cudaSetDevice(c->device));
+  const int stride = (c->dim + 4 + 1) & ~1;  // 16-byte slots
+  memset(handle_out, 0, (size_t)handle_bytes);
+  {
+    void* p = nullptr;
+    if (int rc = host_alloc(c, sizeof(int), &p)) return rc;
+    c->h_xerr = (int*)p;
+    *c->h_xerr = 0;
+  }
+  if (!c->xchg_no_adopt) {
+    // a parked channel of an earlier context of this process?
+    std::lock_guard<std::mutex> lock(g_park_mutex);
+    for (size_t k = 0; k < g_parked.size(); ++k) {
+      const ParkedChannel& pc = g_parked[k];
+      if (pc.device == c->device && pc.xp.world == world && pc.xp.rank == rank && pc.xp.stride == stride) {
+        c->xp = pc.xp;  // the epoch counter carries on
+        c->mailbox = pc.mailbox;
+        c->mailbox_bytes = pc.bytes;
+        memcpy(c->peer_maps, pc.peer_maps, sizeof(c->peer_maps));
+        c->xchg_connected = 1;
+        g_parked.erase(g_parked.begin() + (long)k);
+        return MB2_OK;
+      }
+    }
+  }
+  const size_t bytes = sizeof(double) * 2 * (size_t)world * stride + sizeof(unsigned long long) * 2 * (size_t)world + sizeof(int) * 4;
+  // its own allocation: an IPC handle names a whole cudaMalloc block
+  CUDA_TRY(cudaMalloc((void**)&c->mailbox, bytes));
+  CUDA_TRY(cudaMemset(c->mailbox, 0, bytes));  // flags 0: epochs start at 1
+  c->mailbox_bytes = bytes;
+  cudaIpcMemHandle_t h;
+  CUDA_TRY(cudaIpcGetMemHandle(&h, c->mailbox));
+  memcpy(handle_out, &h, sizeof(h));
+  c->xp = {};
+  c->xp.world = world;
+  c->xp.rank = rank;
+  c->xp.stride = stride;
+  c->xp.epoch = 0;
+  c->xp.timeout_ns = 5000000000ull;
+  c->xp.box[rank] = c->mailbox;
+  c->xp.error = reinterpret_cast<int*>(reinterpret_cast<char*>(c->mailbox) + bytes - sizeof(int) * 4);
+  CUDA_TRY(cudaDeviceSynchronize());
+  return MB2_OK;
+}
+
+int mb2_exchange_connected(mb2_ctx* c) { return (c != nullptr && c->xchg_connected) ? 1 : 0; }
+
+int mb2_exchange_reset(mb2_ctx* c) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (c->mailbox != nullptr) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int r = 0; r < kMaxWorld; ++r) {
+      if (c->peer_maps[r] != nullptr) cudaIpcCloseMemHandle(c->peer_maps[r]);
+      c->peer_maps[r] = nullptr;
+    }
+    cudaFree(c->mailbox);
+    c->mailbox = nullptr;
+  }
+  c->xp = {};
+  c->xchg_connected = 0;
+  c->xchg_no_adopt = 1;
+  return MB2_OK;
+}
+
+int mb2_exchange_connect(mb2_ctx* c, const void* handles, int32_t handle_bytes) {
+  if (c == nullptr || handles == nullptr) return fail(MB2_EINVAL, "NULL argument");
+  if (c->mailbox == nullptr) return fail(MB2_ESTATE, "mb2_exchange_open first");
+  if (c->xchg_connected) return MB2_OK;
+  if (handle_bytes < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail(MB2_EINVAL, "handle stride too small");
+  CUDA_TRY(cudaSetDevice(c->device));
+  for (int r = 0; r < c->xp.world; ++r) {
+    if (r == c->xp.rank) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + (size_t)r * handle_bytes, sizeof(h));
+    void* p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_maps[r] = p;
+    c->xp.box[r] = static_cast<double*>(p);
+  }
+  c->xchg_connected = 1;
+  return MB2_OK;
+}
+
+int mb2_exchange_best(mb2_ctx* c, void* stream) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (!c->xchg_connected) return fail(MB2_ESTATE, "mb2_exchange_connect first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  exchange_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c->dim, c->best_x, c->st, next_exchange(c));
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
+}
+
 int mb2_read_result(mb2_ctx* c, mb2_result* out, double* x_host, void* stream) {
   if (c == nullptr || out == nullptr) return fail(MB2_EINVAL, "NULL argument");
   CUDA_TRY(cudaSetDevice(c->device));
   cudaStream_t s = (cudaStream_t)stream;
+  if (c->xchg_connected) CUDA_TRY(cudaMemcpyAsync(c->h_xerr, c->xp.error, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, s));
   if (x_host) CUDA_TRY(cudaMemcpyAsync(c->h_best_x, c->best_x, sizeof(double) * c->dim, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
+  if (c->xchg_connected && *c->h_xerr != 0)
+    return fail(MB2_ECUDA, "best exchange: a peer did not deliver its record within %.1f s", c->xp.timeout_ns * 1e-9);
   out->best_energy = c->h_st->best_e;
   out->best_index = c->h_st->best_idx;
   out->n_inf = c->h_st->n_inf;

@@ -6,15 +6,108 @@
 
 namespace mb2 {
 
+// ---- multi-GPU best exchange over peer memory (NVLink), fused into the argmin epilogue -----------
+// Every rank owns a mailbox [2 parities][world slots][stride doubles] + flags [2][world]; the
+// mailboxes of all ranks are mapped into every rank's address space (CUDA IPC).  After its local
+// argmin a rank stores its record [best_e, best_idx(global), n_inf, n_acc, x[D]] into slot `rank`
+// of EVERY mailbox (remote stores), fences, raises the slot's flag to the exchange epoch, waits
+// until the `world` flags of its own mailbox carry the epoch and merges the records it received:
+// lowest energy wins, ties to the lowest global index (differential_evolution.py:611 strict '<'
+// in ascending candidate order).  Parities alternate per exchange, so a rank that is one exchange
+// ahead never overwrites a record a slower rank is still reading.
+constexpr int kMaxWorld = 16;
+struct ExchangeParams {
+  int world, rank;
+  int stride;                     // doubles per slot (>= D + 4)
+  int pad_;
+  unsigned long long epoch;       // of this exchange, > 0, the same on every rank
+  unsigned long long timeout_ns;  // give up waiting for a peer after this long
+  double* box[kMaxWorld];         // box[r]: rank r's mailbox as mapped here
+  int* error;                     // raised on a timeout
+};
+
+__device__ __forceinline__ unsigned long long* exchange_flags(double* box, int world, int stride) {
+  return reinterpret_cast<unsigned long long*>(box + (size_t)2 * world * stride);
+}
+
+__device__ __forceinline__ void exchange_best(const ExchangeParams& X, int D, double* __restrict__ best_x,
+                                              DeviceState* __restrict__ st) {
+  __shared__ int sh_w;
+  const int par = (int)(X.epoch & 1ull);
+  // ---- my record into slot `rank` of every mailbox
+  for (int r = 0; r < X.world; ++r) {
+    double* rec = X.box[r] + ((size_t)par * X.world + X.rank) * X.stride;
+    if (threadIdx.x == 0) {
+      rec[0] = st->best_e;
+      rec[1] = (double)st->best_idx;
+      rec[2] = (double)st->n_inf;
+      rec[3] = (double)st->n_acc;
+    }
+    for (int i = threadIdx.x; i < D; i += blockDim.x) rec[4 + i] = best_x[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < X.world) {
+    unsigned long long* f = exchange_flags(X.box[threadIdx.x], X.world, X.stride) + (size_t)par * X.world + X.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(X.epoch) : "memory");
+    // ---- wait for the record of rank threadIdx.x in my own mailbox
+    const unsigned long long* mine = exchange_flags(X.box[X.rank], X.world, X.stride) + (size_t)par * X.world + threadIdx.x;
+    unsigned long long t0 = 0, now = 0, v = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+      if (v == X.epoch) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (now - t0 > X.timeout_ns) {
+        atomicExch(X.error, 1);
+        break;
+      }
+      __nanosleep(64);
+    }
+  }
+  __syncthreads();
+  // ---- merge
+  const double* recs = X.box[X.rank] + (size_t)par * X.world * X.stride;
+  if (threadIdx.x == 0) {
+    int w = -1;
+    double be = CUDART_INF, bi = 0.0, ninf = 0.0, nacc = 0.0;
+    for (int r = 0; r < X.world; ++r) {
+      const volatile double* rec = recs + (size_t)r * X.stride;
+      ninf += rec[2];
+      nacc += rec[3];
+      if (rec[1] < 0.0) continue;  // shard has no best yet
+      if (w < 0 || rec[0] < be || (rec[0] == be && rec[1] < bi)) {
+        w = r;
+        be = rec[0];
+        bi = rec[1];
+      }
+    }
+    if (w >= 0) {
+      st->best_e = be;
+      st->best_idx = (int64_t)bi;
+    }
+    st->n_inf = (int64_t)ninf;
+    st->n_acc = (int64_t)nacc;
+    sh_w = w;
+  }
+  __syncthreads();
+  const int w = sh_w;
+  if (w >= 0 && w != X.rank) {
+    const volatile double* rec = recs + (size_t)w * X.stride;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = rec[4 + i];
+  }
+}
+
 // K3: reduce the per-CTA partials, update bestEnergy/bestSolution if the generation best beats
-// the previous best (strict '<', :610), publish counters.  One CTA.
+// the previous best (strict '<', :610), publish counters; with X.world > 1 the shards' bests are
+// exchanged over peer memory in the same kernel.  One CTA.
 __global__ void __launch_bounds__(256)
     de_finalize_kernel(const double* __restrict__ part_e, const int64_t* __restrict__ part_idx,
                        const unsigned long long* __restrict__ part_ninf,
                        const unsigned long long* __restrict__ part_nacc, int nparts,
                        const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
                        int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
-                       RunState* __restrict__ rs) {
+                       RunState* __restrict__ rs, const __grid_constant__ ExchangeParams X) {
   if (rs != nullptr && rs->stop) return;  // batch mode: this generation was not run
   __shared__ double sh_e[256];
   __shared__ int64_t sh_i[256];
@@ -74,6 +167,10 @@ __global__ void __launch_bounds__(256)
   if (w != -1) {
     const double* src = pop_next + (w == -2 ? 0 : w) * D;
     for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = src[i];
+  }
+  if (X.world > 1) {  // sharded population: install the global best on every shard
+    __syncthreads();
+    exchange_best(X, D, best_x, st);
   }
   if (rs == nullptr) return;
   __syncthreads();
@@ -196,6 +293,12 @@ __global__ void pack_best_kernel(const DeviceState* __restrict__ st, const doubl
     rec[3] = (double)st->n_acc;
   }
   for (int i = threadIdx.x; i < D; i += blockDim.x) rec[4 + i] = best_x[i];
+}
+
+// exchange alone (after a restored state, or whenever the host asks for it)
+__global__ void __launch_bounds__(256)
+    exchange_best_kernel(int D, double* __restrict__ best_x, DeviceState* __restrict__ st, const __grid_constant__ ExchangeParams X) {
+  exchange_best(X, D, best_x, st);
 }
 
 __global__ void merge_best_kernel(const double* __restrict__ recs, int world, int D, double* __restrict__ best_x,

@@ -52,6 +52,7 @@ class DeviceEngine(object):
             self._trial_e = torch.full((self.np_local,), float('inf'), **f64)
             check(lib.mb2_set_capture(self._ctx, self._trial.data_ptr(), self._trial_e.data_ptr()))
         self._replay = None  # keeps the uploaded draw tensors alive until consumed
+        self.peer_exchange = False  # True: eval_initial()/step() end with the exchange of the shards' bests
         self._log = self._log_host = None  # batch-mode generation log
         self._record = torch.empty((self.dim + 4,), **f64)
         self._xbuf = np.empty(self.dim, dtype=np.float64)
@@ -189,6 +190,30 @@ class DeviceEngine(object):
         n = done.value
         self._log_host[:n].copy_(self._log[:n])
         return self._log_host[:n].numpy().copy(), bool(stopped.value)
+
+    # ---- sharded populations: best exchange ------------------------------------------------
+    def connect_peers(self, world, rank, all_gather_object, all_agree):
+        """fuse the exchange of the shards' bests into the argmin epilogue (stores into peer memory
+        over NVLink, include/mystic_b200.h mb2_exchange_*).  torch.distributed plumbing comes from the
+        caller: `all_gather_object(obj) -> list` moves the 64-byte CUDA IPC handles between the
+        ranks, `all_agree(flag) -> bool` is a logical AND over the ranks."""
+        buf = ctypes.create_string_buffer(64)
+        check(lib.mb2_exchange_open(self._ctx, int(world), int(rank), buf, 64))
+        # mailbox and peer mappings of an earlier engine of this process adopted -- on every rank?
+        if all_agree(bool(lib.mb2_exchange_connected(self._ctx))):
+            self.peer_exchange = True
+            return
+        if lib.mb2_exchange_connected(self._ctx):
+            check(lib.mb2_exchange_reset(self._ctx))
+            check(lib.mb2_exchange_open(self._ctx, int(world), int(rank), buf, 64))
+        handles = all_gather_object(buf.raw)
+        if len(handles) != world:
+            raise RuntimeError('expected %d handles, got %d' % (world, len(handles)))
+        check(lib.mb2_exchange_connect(self._ctx, b''.join(handles), 64))
+        self.peer_exchange = True
+
+    def exchange_best(self):
+        check(lib.mb2_exchange_best(self._ctx, self._stream()))
 
     def pack_best(self):
         check(lib.mb2_pack_best(self._ctx, self._record.data_ptr(), self._stream()))

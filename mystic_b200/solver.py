@@ -30,6 +30,7 @@ Engine-specific constructor keywords (not in the reference):
     tensor_cores=bool evaluate the Chebyshev fitting costs on the FP64 tensor cores (DMMA) instead of the
                      bit-faithful Horner path (default False)
 """
+import os
 import random
 import weakref
 from collections.abc import Callable as _Callable
@@ -607,6 +608,25 @@ class DifferentialEvolutionSolver2(object):
                     self._engine.population_tensor()[0, :] = self._engine.population_tensor().new_tensor(x0)
             else:
                 self._engine.upload_population(self._host_pop)
+            if self._distributed and self._world > 1 and hasattr(self._engine, 'connect_peers') \
+                    and os.environ.get('MB2_EXCHANGE', 'peer') != 'nccl':
+                # the shards' bests travel as stores into peer memory (NVLink), fused into the argmin
+                # epilogue of every generation; MB2_EXCHANGE=nccl keeps the all-gather of _exchange_best
+                import torch.distributed as dist
+
+                import torch
+
+                def gather(obj):
+                    out = [None] * self._world
+                    dist.all_gather_object(out, obj)
+                    return out
+
+                def agree(flag):
+                    dev = self._engine.device if dist.get_backend() == 'nccl' else 'cpu'
+                    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=dev)
+                    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                    return bool(t.item())
+                self._engine.connect_peers(self._world, self._rank, gather, agree)
             if self._resume is not None:
                 # a solver loaded from a restart file: energies, best member and generation counter
                 # are installed as saved, nothing is re-evaluated
@@ -747,6 +767,8 @@ class DifferentialEvolutionSolver2(object):
     def _exchange_best(self):
         """distributed: all-gather the shards' (energy, global index, counters, bestSolution) records
         and let every shard install the global best (lowest energy, ties to the lowest index)."""
+        if getattr(self._engine, 'peer_exchange', False):
+            return  # already done by the generation's own epilogue kernel (engine.connect_peers)
         import torch
         import torch.distributed as dist
         rec = self._engine.pack_best()

@@ -53,14 +53,24 @@ def main():
     rank = int(os.environ['RANK'])
     world = int(os.environ['WORLD_SIZE'])
     local = int(os.environ.get('LOCAL_RANK', rank))
+    # MB2_DIST_ONE_GPU=1: every rank on cuda:0 with a gloo group (NCCL refuses two ranks on one
+    # device) -- lets a single-GPU box exercise the peer-memory exchange between processes
+    one_gpu = os.environ.get('MB2_DIST_ONE_GPU') == '1'
+    if one_gpu:
+        local = 0
     torch.cuda.set_device(local)
-    dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    if one_gpu:
+        dist.init_process_group('gloo')
+    else:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
     ok = True
     for (strategy, cost, D, NP, mode, lo, hi) in [('Best1Bin', 'rosen', 64, 1000, orc.BOUNDS_CLAMP, -5., 5.),
                                                   ('RandToBest1Exp', 'griewangk', 30, 301, orc.BOUNDS_REJECT, -400., 400.),
                                                   ('Rand1Exp', 'rosen', 9, 77, orc.BOUNDS_CLAMP, -2., 2.)]:
         seed, gens = 0xD15C0 + D, 6
         s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=seed, distributed=True, strategy=strategy)
+        if os.environ.get('MB2_EXCHANGE', 'peer') == 'peer':
+            assert hasattr(s, '_engine')
         s.SetRandomInitialPoints([lo] * D, [hi] * D)
         s.SetStrictRanges([lo] * D, [hi] * D, tight=(mode == orc.BOUNDS_CLAMP))
         s.SetTermination(termination.VTR(-1.0))
@@ -71,13 +81,15 @@ def main():
         cid = getattr(models, cost).cost_id
         engs, hist = emulate(world, NP, D, seed, strategy, cid, (mode, np.full(D, lo), np.full(D, hi)), gens)
         mine = engs[rank]
+        if os.environ.get('MB2_EXCHANGE', 'peer') == 'peer':
+            assert s._engine.peer_exchange, 'the peer-memory exchange is not in use'
         same_pop = np.array_equal(s.population, mine.population())
         same_best = np.array_equal(np.array(s.bestSolution), mine.state.bestSolution)
         e_ok = np.allclose(np.array(s.energy_history), np.array(hist), rtol=1e-12, atol=0)
         print('rank %d %s/%s D=%d NP=%d: population %s, bestSolution %s, energy history %s, evaluations %d'
               % (rank, strategy, cost, D, NP, same_pop, same_best, e_ok, s.evaluations), flush=True)
         ok = ok and same_pop and same_best and e_ok
-    t = torch.tensor([1 if ok else 0], device='cuda')
+    t = torch.tensor([1 if ok else 0], device='cpu' if one_gpu else 'cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()
     if int(t.item()) != 1:
