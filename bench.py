@@ -52,6 +52,15 @@ WORKLOADS = {
 
 BIN_STRATEGIES = ('Best1Bin',)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of the fused generation kernel, per launch at the
+# workload's full per-GPU size, from one `ncu --set full` capture each (summaries under profiles/)
+NCU_TRAFFIC = {
+    'c2': (1.444437e9 + 0.511764e9, 'profiles/r1_c2_tma_kernel_ncu_full_summary.csv'),
+    'c3': (0.254003e9 + 0.033973e9, 'profiles/r1_c3_kernel_ncu_full_summary.csv'),
+    'c4': (1.071825e9 + 0.497635e9, 'profiles/r1_c4_rows_kernel_ncu_full_summary.csv'),
+    'c5': (12.791188e9 + 4.326547e9, 'profiles/r1_c5_kernel_ncu_full_summary.csv'),
+}
+
 
 def algorithmic_bytes_per_candidate(w):
     """population double buffered; parent + k donor rows read, new row written,
@@ -359,13 +368,17 @@ def main():
                 'frac_burst': bpc * NP_local / (burst_ms * 1e-3 / steps) / 1e9 / peaks['hbm_gbs'],
                 'algorithmic_bytes_per_candidate': bpc,
                 'kernel': 'de_step_kernel (fused generation) + de_finalize_kernel, per generation, per GPU'}
+    if args.workload in NCU_TRAFFIC and NP_local == WORKLOADS[args.workload]['np']:
+        roofline['traffic'], roofline['traffic_source'] = NCU_TRAFFIC[args.workload]
+        roofline['algorithmic_bytes_per_launch'] = bpc * NP_local
     flops = algorithmic_flops_per_candidate(w)
     if flops:
         # the Chebyshev contraction is FP64-pipe bound: DMMA peak measured on this pool's B200 with
         # tools/fp64_peak.cu (profiles/r1_fp64_peaks_b200.json): 33.02 TFLOP/s (DFMA 34.15, cuBLAS DGEMM 35.4)
         tf = flops * NP_local / step_s / 1e12
         roofline = {'bound': 'tensor', 'achieved': tf, 'peak': 33.02, 'unit': 'TFLOP/s', 'frac': tf / 33.02,
-                    'traffic': None, 'peak_source': 'measured DMMA.8x8x4 peak (profiles/r1_fp64_peaks_b200.json)',
+                    'traffic': roofline.get('traffic'), 'traffic_source': roofline.get('traffic_source'),
+                    'peak_source': 'measured DMMA.8x8x4 peak (profiles/r1_fp64_peaks_b200.json)',
                     'algorithmic_flops_per_candidate': flops, 'hbm_frac': achieved / peaks['hbm_gbs'],
                     'kernel': 'de_step_cheb_mma_kernel' if w.get('tensor_cores') else 'de_step_kernel (Horner)'}
 

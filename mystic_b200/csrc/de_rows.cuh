@@ -37,7 +37,10 @@ namespace mb2 {
 #ifndef MB2_ROWS_CPT
 #define MB2_ROWS_CPT 1
 #endif
-constexpr int kRowsWarps = 8;
+#ifndef MB2_ROWS_WARPS
+#define MB2_ROWS_WARPS 8
+#endif
+constexpr int kRowsWarps = MB2_ROWS_WARPS;
 constexpr int kRowsTrips = 4;     // 4-element chunks per lane: D <= 16 * LPR
 constexpr int kRowsMinDim = 16;
 constexpr int kRowsMaxDim = 128;
