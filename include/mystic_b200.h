@@ -58,7 +58,12 @@ enum mb2_cost {
   MB2_COST_GRIEWANGK = 2,  /* models/storn.py:120-139 */
   MB2_COST_ZIMMERMANN = 3, /* models/storn.py:161-191 */
   MB2_COST_CHEBYSHEV = 4,  /* models/_model_helper.py:16-33, Horner (math/poly.py:37-39), bit-faithful px */
-  MB2_COST_CHEBYSHEV_MMA = 5 /* same cost, [NP x D]*[D x M] contraction on FP64 tensor cores (DMMA) */
+  MB2_COST_CHEBYSHEV_MMA = 5, /* same cost, [NP x D]*[D x M] contraction on FP64 tensor cores (DMMA) */
+  /* data-fit residual costs of forward_model.py:204-260 (CostFactory.getCostFunction with the default
+   * L2 metric): sum(((F(params)(x_i) - obs_i)/sigma)^2) over M evaluation points */
+  MB2_COST_POLYFIT = 6,     /* F = models/poly.py:36-54 (numpy.poly1d), dim = number of coefficients <= 32 */
+  MB2_COST_POLYFIT_MMA = 7, /* same cost, the coefficient x point contraction on DMMA (dim <= 17) */
+  MB2_COST_LORENTZIAN = 8   /* F = models/lorentzian.py:32-37, dim = 7 */
 };
 
 /* SetStrictRanges modes (abstract_solver.py:334-448, tools.py:404-430) */
@@ -118,7 +123,8 @@ int mb2_current(mb2_ctx* ctx, double** pop_dev, double** energy_dev);
 int mb2_set_strategy(mb2_ctx* ctx, int strategy, double scale, double cross);
 /* abstract_solver.py:334-405 SetStrictRanges; lo/hi have `dim` entries (ignored for NONE) */
 int mb2_set_bounds(mb2_ctx* ctx, int mode, const double* lo_host, const double* hi_host);
-/* cost(x, *ExtraArgs): params for CHEBYSHEV* = {M, order, target coeffs[order+1]} */
+/* cost(x, *ExtraArgs): params for CHEBYSHEV* = {M, order, target coeffs[order+1]};
+ * for POLYFIT* / LORENTZIAN = {M, sigma, evalpts[M], observations[M]} */
 int mb2_set_cost(mb2_ctx* ctx, int cost, const double* params_host, int32_t nparams);
 /* stacked penalty decorators, term 0 innermost (penalty.py:80-98 `dec`); G is [nterms, dim],
  * kscale[i] = k*h**n (the decorator's current multiplier before the inequality factor 2) */

@@ -84,7 +84,9 @@ struct mb2_ctx {
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
-  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0};
+  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0, nullptr, 1.0};
+  double* fit_obs = nullptr;
+  size_t cap_fit_obs = 0;
   double bounds_absmax = 0.0;  // max(|lo_i|, |hi_i|) of the strict range
   double* cheb_vfrag = nullptr;
   int cheb_ks = 0;
@@ -194,7 +196,10 @@ namespace mb2 {
 StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
 ThreadRowKernel get_small_kernel(int cost);
-ThreadRowKernel get_cheb_mma_kernel(int ksteps);
+ThreadRowKernel get_cheb_mma_kernel(int ksteps, bool resid);
+StepKernel get_datafit_ldg_kernel(int base, int xover, int cost);
+ThreadRowKernel get_datafit_small_kernel(int cost);
+ThreadRowKernel get_datafit_subwarp_kernel(int cost);
 ThreadRowKernel get_subwarp_kernel(int cost, int lanes_per_row, bool vec);
 ThreadRowKernel get_rows_kernel_rosen(int lanes_per_row, int ndonors);
 ThreadRowKernel get_rows_kernel_corana(int lanes_per_row, int ndonors);
@@ -202,7 +207,10 @@ ThreadRowKernel get_rows_kernel_griewangk(int lanes_per_row, int ndonors);
 }  // namespace mb2
 namespace {
 
+bool is_datafit(int cost) { return cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN; }
+
 StepKernel pick_kernel(const StrategyInfo& s, int cost, bool vec) {
+  if (is_datafit(cost)) return get_datafit_ldg_kernel(s.base, s.xover, cost);
   return get_ldg_kernel(s.xover == XOVER_BIN ? BASE_BEST1 : s.base, s.xover, cost, vec);
 }
 
@@ -279,10 +287,11 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
                    (out_rows == nullptr || (reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
   StrategyInfo s = c->sinfo;
   if (mode != MODE_STEP) s = {BASE_RAND1, XOVER_EXP, 3};  // no best/donors needed; any instance
-  const bool cheb_mma = (c->cost == MB2_COST_CHEBYSHEV_MMA);
+  const bool cheb_mma = (c->cost == MB2_COST_CHEBYSHEV_MMA || c->cost == MB2_COST_POLYFIT_MMA);
+  const bool datafit = is_datafit(c->cost);
   StepKernel k = cheb_mma ? nullptr : pick_kernel(s, c->cost, vec);
   if (k == nullptr && !cheb_mma) return fail(MB2_EINVAL, "no kernel for strategy %d cost %d", c->strategy, c->cost);
-  ThreadRowKernel kc = cheb_mma ? get_cheb_mma_kernel(c->cheb_ks) : nullptr;
+  ThreadRowKernel kc = cheb_mma ? get_cheb_mma_kernel(c->cheb_ks, c->cost == MB2_COST_POLYFIT_MMA) : nullptr;
   // short rows: one thread per candidate (all modes, so energies of a context share one summation order)
   ThreadRowKernel ks = nullptr;
   int small_max = env_int("MB2_SMALL_MAXD", kSmallMaxDim);
@@ -302,14 +311,14 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
       else if (c->cost == MB2_COST_GRIEWANGK) kr = get_rows_kernel_griewangk(lpr, s.k);
     }
     if (kr != nullptr) kw = kr;
-    else if (small_kind == 2) ks = get_small_kernel(c->cost);
-    else if (small_kind == 1 || small_kind == 3) kw = get_subwarp_kernel(c->cost, lpr, vec);
+    else if (small_kind == 2) ks = datafit ? get_datafit_small_kernel(c->cost) : get_small_kernel(c->cost);
+    else if (small_kind == 1 || small_kind == 3) kw = datafit ? get_datafit_subwarp_kernel(c->cost) : get_subwarp_kernel(c->cost, lpr, vec);
   }
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
-  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 &&
+  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 && !datafit &&
       !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
 
@@ -606,10 +615,75 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
 
 int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
-  if (cost < MB2_COST_ROSEN || cost > MB2_COST_CHEBYSHEV_MMA) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (cost < MB2_COST_ROSEN || cost > MB2_COST_LORENTZIAN) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (cost == MB2_COST_LORENTZIAN && c->dim != 7) return fail(MB2_EINVAL, "lorentzian has 7 parameters (a1,a2,a3,A0,E0,G0,n)");
+  if ((cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN) && c->dim > 32)
+    return fail(MB2_EINVAL, "data-fit costs support at most 32 model parameters");
+  if (cost == MB2_COST_POLYFIT_MMA && c->dim > kChebMaxDim)
+    return fail(MB2_EINVAL, "polynomial-fit DMMA cost supports at most %d coefficients", kChebMaxDim);
   if (cost == MB2_COST_ZIMMERMANN && c->dim != 2) return fail(MB2_EINVAL, "zimmermann requires dim == 2");
   if (cost == MB2_COST_CHEBYSHEV_MMA && c->dim > kChebMaxDim)
     return fail(MB2_EINVAL, "chebyshev DMMA cost supports at most %d coefficients", kChebMaxDim);
+  // evaluation points -> device; Vandermonde fragments of the DMMA variants (see de_cheb_mma.cuh)
+  auto upload_points = [&](const std::vector<double>& xs, bool mma) -> int {
+    const int M = (int)xs.size();
+    CUDA_TRY(cudaSetDevice(c->device));
+    if (c->cap_cheb_x < sizeof(double) * M) {
+      void* p = nullptr;
+      if (int rc = dev_alloc(c, sizeof(double) * M, &p)) return rc;
+      c->cheb_x = (double*)p;
+      c->cap_cheb_x = sizeof(double) * M;
+    }
+    CUDA_TRY(cudaMemcpy(c->cheb_x, xs.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
+    c->cp.cheb_M = M;
+    c->cp.cheb_x = c->cheb_x;
+    if (!mma) return MB2_OK;
+    const int n = c->dim - 1;  // order of the trial polynomial
+    const int KS = n <= 4 ? 1 : (n <= 8 ? 2 : 4);
+    const int ntiles = (M + 7) / 8;
+    std::vector<double> vf((size_t)ntiles * KS * 32, 0.0);
+    for (int t = 0; t < ntiles; ++t)
+      for (int s = 0; s < KS; ++s)
+        for (int lane = 0; lane < 32; ++lane) {
+          const int k = 4 * s + (lane & 3), i = 8 * t + (lane >> 2);
+          double v = 0.0;
+          if (k < n && i < M) {
+            volatile double pw = 1.0;
+            for (int e = 0; e < n - k; ++e) pw = pw * xs[i];
+            v = pw;
+          }
+          vf[((size_t)t * KS + s) * 32 + lane] = v;
+        }
+    if (c->cap_vfrag < sizeof(double) * vf.size()) {
+      void* p = nullptr;
+      if (int rc = dev_alloc(c, sizeof(double) * vf.size(), &p)) return rc;
+      c->cheb_vfrag = (double*)p;
+      c->cap_vfrag = sizeof(double) * vf.size();
+    }
+    CUDA_TRY(cudaMemcpy(c->cheb_vfrag, vf.data(), sizeof(double) * vf.size(), cudaMemcpyHostToDevice));
+    c->cp.cheb_vfrag = c->cheb_vfrag;
+    c->cp.cheb_ntiles = ntiles;
+    c->cheb_ks = KS;
+    return MB2_OK;
+  };
+  if (cost == MB2_COST_POLYFIT || cost == MB2_COST_POLYFIT_MMA || cost == MB2_COST_LORENTZIAN) {
+    if (!params || nparams < 4) return fail(MB2_EINVAL, "data-fit params = {M, sigma, evalpts[M], observations[M]}");
+    const int M = (int)params[0];
+    const double sigma = params[1];
+    if (M < 1 || nparams != 2 + 2 * M) return fail(MB2_EINVAL, "bad data-fit params (M=%d, %d values)", M, nparams);
+    if (!(sigma != 0.0)) return fail(MB2_EINVAL, "sigma must not be zero");
+    std::vector<double> xs(params + 2, params + 2 + M);
+    if (int rc = upload_points(xs, cost == MB2_COST_POLYFIT_MMA)) return rc;
+    if (c->cap_fit_obs < sizeof(double) * M) {
+      void* p = nullptr;
+      if (int rc = dev_alloc(c, sizeof(double) * M, &p)) return rc;
+      c->fit_obs = (double*)p;
+      c->cap_fit_obs = sizeof(double) * M;
+    }
+    CUDA_TRY(cudaMemcpy(c->fit_obs, params + 2 + M, sizeof(double) * M, cudaMemcpyHostToDevice));
+    c->cp.fit_obs = c->fit_obs;
+    c->cp.fit_sigma = sigma;
+  }
   if (cost == MB2_COST_CHEBYSHEV || cost == MB2_COST_CHEBYSHEV_MMA) {
     if (!params || nparams < 3) return fail(MB2_EINVAL, "chebyshev params = {M, order, target[order+1]}");
     const int M = (int)params[0], order = (int)params[1];
@@ -633,47 +707,9 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
       }
       if (sgn) tm = val; else tp = val;
     }
-    CUDA_TRY(cudaSetDevice(c->device));
-    if (c->cap_cheb_x < sizeof(double) * M) {
-      void* p = nullptr;
-      if (int rc = dev_alloc(c, sizeof(double) * M, &p)) return rc;
-      c->cheb_x = (double*)p;
-      c->cap_cheb_x = sizeof(double) * M;
-    }
-    CUDA_TRY(cudaMemcpy(c->cheb_x, xs.data(), sizeof(double) * M, cudaMemcpyHostToDevice));
-    c->cp.cheb_M = M;
-    c->cp.cheb_x = c->cheb_x;
+    if (int rc = upload_points(xs, cost == MB2_COST_CHEBYSHEV_MMA)) return rc;
     c->cp.cheb_tp = tp;
     c->cp.cheb_tm = tm;
-    if (cost == MB2_COST_CHEBYSHEV_MMA) {
-      // Vandermonde fragments in mma.m8n8k4 B-operand order (see de_cheb_mma.cuh)
-      const int n = c->dim - 1;  // order of the trial polynomial
-      const int KS = n <= 4 ? 1 : (n <= 8 ? 2 : 4);
-      const int ntiles = (M + 7) / 8;
-      std::vector<double> vf((size_t)ntiles * KS * 32, 0.0);
-      for (int t = 0; t < ntiles; ++t)
-        for (int s = 0; s < KS; ++s)
-          for (int lane = 0; lane < 32; ++lane) {
-            const int k = 4 * s + (lane & 3), i = 8 * t + (lane >> 2);
-            double v = 0.0;
-            if (k < n && i < M) {
-              volatile double pw = 1.0;
-              for (int e = 0; e < n - k; ++e) pw = pw * xs[i];
-              v = pw;
-            }
-            vf[((size_t)t * KS + s) * 32 + lane] = v;
-          }
-      if (c->cap_vfrag < sizeof(double) * vf.size()) {
-        void* p = nullptr;
-        if (int rc = dev_alloc(c, sizeof(double) * vf.size(), &p)) return rc;
-        c->cheb_vfrag = (double*)p;
-        c->cap_vfrag = sizeof(double) * vf.size();
-      }
-      CUDA_TRY(cudaMemcpy(c->cheb_vfrag, vf.data(), sizeof(double) * vf.size(), cudaMemcpyHostToDevice));
-      c->cp.cheb_vfrag = c->cheb_vfrag;
-      c->cp.cheb_ntiles = ntiles;
-      c->cheb_ks = KS;
-    }
   }
   if (cost == MB2_COST_GRIEWANGK && c->grw_tab == nullptr) {
     // {sqrt(i+1.0), 1/sqrt(i+1.0)}: glibc sqrt and the host divide are correctly rounded

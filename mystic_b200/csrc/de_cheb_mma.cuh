@@ -31,7 +31,10 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                : "d"(a), "d"(b));
 }
 
-template <int KS>  // k-steps of 4 coefficients: 1 (order <= 4), 2 (order <= 8), 4 (order <= 16)
+// RESID: the epilogue is the squared residual of a polynomial least-squares data fit
+// (MB2_COST_POLYFIT_MMA: sum(((p(x_i) - obs_i)/sigma)^2), forward_model.py:241-258 with
+// models/poly.py:36-54) instead of the Chebyshev threshold terms; no end-point terms then.
+template <int KS, bool RESID = false>  // k-steps of 4 coefficients: 1 (order <= 4), 2 (order <= 8), 4 (order <= 16)
 __global__ void __launch_bounds__(kChebWarps * 32)
     de_step_cheb_mma_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
   if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
@@ -196,12 +199,23 @@ __global__ void __launch_bounds__(kChebWarps * 32)
       }
       const int i0 = t * 8 + 2 * acol;
       const bool v0 = i0 < M, v1 = i0 + 1 < M;
+      if (RESID) {
+        const double o0 = v0 ? __ldg(P.cost.fit_obs + i0) : 0.0, o1 = v1 ? __ldg(P.cost.fit_obs + i0 + 1) : 0.0;
+        const double is = 1.0 / P.cost.fit_sigma;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        // _model_helper.py:23-24: if px<-1 or px>1: result += (1-px)**2   (NaN compares false)
-        const double t0 = 1.0 - c0v[r], t1 = 1.0 - c1v[r];
-        if (v0 && fabs(c0v[r]) > 1.0) sum[r] = fma(t0, t0, sum[r]);
-        if (v1 && fabs(c1v[r]) > 1.0) sum[r] = fma(t1, t1, sum[r]);
+        for (int r = 0; r < 8; ++r) {
+          const double t0 = (c0v[r] - o0) * is, t1 = (c1v[r] - o1) * is;
+          if (v0) sum[r] = fma(t0, t0, sum[r]);
+          if (v1) sum[r] = fma(t1, t1, sum[r]);
+        }
+      } else {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          // _model_helper.py:23-24: if px<-1 or px>1: result += (1-px)**2   (NaN compares false)
+          const double t0 = 1.0 - c0v[r], t1 = 1.0 - c1v[r];
+          if (v0 && fabs(c0v[r]) > 1.0) sum[r] = fma(t0, t0, sum[r]);
+          if (v1 && fabs(c1v[r]) > 1.0) sum[r] = fma(t1, t1, sum[r]);
+        }
       }
     }
 #pragma unroll
@@ -223,16 +237,18 @@ __global__ void __launch_bounds__(kChebWarps * 32)
       double E = CUDART_INF;
       if (!(oobmask & (1u << h))) {
         E = s_sum[cl];
-        // _model_helper.py:27-31: px = p_trial(+-1.2) - p_target(+-1.2); if px<0: result += px*px
-        double vp = 0.0, vm = 0.0;
-        for (int j = 0; j < D; ++j) {
-          vp = fma(vp, 1.2, row[j]);
-          vm = fma(vm, -1.2, row[j]);
+        if (!RESID) {
+          // _model_helper.py:27-31: px = p_trial(+-1.2) - p_target(+-1.2); if px<0: result += px*px
+          double vp = 0.0, vm = 0.0;
+          for (int j = 0; j < D; ++j) {
+            vp = fma(vp, 1.2, row[j]);
+            vm = fma(vm, -1.2, row[j]);
+          }
+          double px = vp - P.cost.cheb_tp;
+          if (px < 0.0) E = fma(px, px, E);
+          px = vm - P.cost.cheb_tm;
+          if (px < 0.0) E = fma(px, px, E);
         }
-        double px = vp - P.cost.cheb_tp;
-        if (px < 0.0) E = fma(px, px, E);
-        px = vm - P.cost.cheb_tm;
-        if (px < 0.0) E = fma(px, px, E);
       }
       // penalty: t_{n-1} + (... + (t_0 + 0.0)), linear conditions, sequential dot (penalty.py)
       double pen = 0.0;

@@ -166,6 +166,10 @@ struct CostParams {
   // correctly rounded on the host, so the kernel needs neither a square root nor a divide
   const double2* grw_tab;
   int grw_bounded;  // 1: the strict range keeps every |x_i| <= kCosFastMax (guard-free factors)
+  // data-fit residual costs (forward_model.py:204-260): metric sum(((F(params)(x_i) - obs_i)/sigma)^2)
+  // over the cheb_M evaluation points cheb_x[] (the DMMA variant reads cheb_vfrag as well)
+  const double* fit_obs;  // [M] observations
+  double fit_sigma;
 };
 
 // c / s with r = RN(1/s): two Markstein refinement steps on top of c*r give the correctly
@@ -224,13 +228,47 @@ __device__ __forceinline__ double grw_factor(double c, double s, double r, bool 
   return (fabs(q) <= kCosFastMax) ? cos_bounded(q) : cos(q);
 }
 
-enum : int { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4 };
+enum : int {
+  COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4,
+  COST_POLYFIT = 6, COST_LORENTZIAN = 8  // numbered like mb2_cost (5 and 7 are the DMMA variants)
+};
 
 // Horner exactly as mystic/math/poly.py:37-39: val = 0*x; for c in coeffs: val = c + val*x
 __device__ __forceinline__ double horner(const double* __restrict__ c, int n, double x) {
   double val = dmul(0.0, x);
   for (int j = 0; j < n; ++j) val = dadd(c[j], dmul(val, x));
   return val;
+}
+
+// One squared residual of a data-fit cost (forward_model.py:241-258: x = F(params)(evalpts);
+// x = x - observations, or (x - observations)/sigma; metric sum(x*x)), elementwise in numpy's order.
+// polynomial model (models/poly.py:36-54): numpy.poly1d(coeffs)(x) is numpy.polyval's
+// `y = zeros_like(x); for pv in p: y = y*x + pv` (leading zero coefficients change nothing)
+__device__ __forceinline__ double polyfit_term(const double* __restrict__ c, int n, double x, double obs, double sigma) {
+  double y = 0.0;
+  for (int j = 0; j < n; ++j) y = dadd(dmul(y, x), c[j]);
+  double r = dsub(y, obs);
+  if (sigma != 1.0) r = __ddiv_rn(r, sigma);  // AbstractModel's default sigma = 1.0 divides exactly
+  return dmul(r, r);
+}
+// lorentzian peak (models/lorentzian.py:32-37), coeffs = (a1,a2,a3,A0,E0,G0,n):
+//   (a1 + a2*x + a3*x*x + A0*(G0/(2*pi))/((x-E0)*(x-E0) + (G0/2)*(G0/2)))/n
+__device__ __forceinline__ double lorentz_term(const double* __restrict__ p, double x, double obs, double sigma) {
+  const double a1 = p[0], a2 = p[1], a3 = p[2], A0 = p[3], E0 = p[4], G0 = p[5], nn = p[6];
+  const double k = dmul(A0, __ddiv_rn(G0, 6.283185307179586));  // 2*pi in binary64
+  const double hg = __ddiv_rn(G0, 2.0);
+  const double d = dsub(x, E0);
+  const double den = dadd(dmul(d, d), dmul(hg, hg));
+  const double s = dadd(dadd(a1, dmul(a2, x)), dmul(dmul(a3, x), x));
+  const double v = __ddiv_rn(dadd(s, __ddiv_rn(k, den)), nn);
+  double r = dsub(v, obs);
+  if (sigma != 1.0) r = __ddiv_rn(r, sigma);
+  return dmul(r, r);
+}
+template <int COST>
+__device__ __forceinline__ double fit_term(const double* __restrict__ xs, int D, const CostParams& cp, int i) {
+  const double x = __ldg(cp.cheb_x + i), obs = __ldg(cp.fit_obs + i);
+  return (COST == COST_POLYFIT) ? polyfit_term(xs, D, x, obs, cp.fit_sigma) : lorentz_term(xs, x, obs, cp.fit_sigma);
 }
 
 // Group-cooperative cost of one row `xs` (shared memory, D entries).  Every thread of the group
@@ -344,6 +382,19 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
     if (c2 > m) m = c2;
     if (c3 > m) m = c3;
     return m;
+  } else if (COST == COST_POLYFIT || COST == COST_LORENTZIAN) {
+    double acc[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) acc[m] = 0.0;
+    const int M = cp.cheb_M;
+    for (int i0 = g.tig; i0 < M; i0 += 256) {
+#pragma unroll
+      for (int m = 0; m < NA; ++m) {
+        const int i = i0 + m * NT;
+        if (i < M) acc[m] = dadd(acc[m], fit_term<COST>(xs, D, cp, i));
+      }
+    }
+    return group_reduce<false, GW>(g, acc, 0);
   } else {  // COST_CHEBYSHEV
     // _model_helper.py:16-33
     double acc[NA];

@@ -109,6 +109,11 @@ __device__ __forceinline__ double thread_cost(const double* x, int D, const Cost
     if (c2 > m) m = c2;
     if (c3 > m) m = c3;
     return m;
+  } else if (COST == COST_POLYFIT || COST == COST_LORENTZIAN) {
+    double result = 0.0;
+    const int M = cp.cheb_M;
+    for (int i = 0; i < M; ++i) result = dadd(result, fit_term<COST>(x, D, cp, i));
+    return result;
   } else {
     // _model_helper.py:16-33, sequential over the abscissae
     double result = 0.0;

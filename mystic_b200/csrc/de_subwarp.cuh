@@ -94,6 +94,11 @@ __device__ __forceinline__ double seg_cost(const double* xs, int D, int sub, con
     if (c2 > m) m = c2;
     if (c3 > m) m = c3;
     return m;
+  } else if (COST == COST_POLYFIT || COST == COST_LORENTZIAN) {
+    double acc = 0.0;
+    const int M = cp.cheb_M;
+    for (int i = sub; i < M; i += LPR) acc = dadd(acc, fit_term<COST>(xs, D, cp, i));
+    return seg_reduce<LPR, false>(acc);
   } else {
     double acc = 0.0;
     const int M = cp.cheb_M;

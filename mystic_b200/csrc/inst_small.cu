@@ -24,7 +24,10 @@ ThreadRowKernel get_small_kernel(int cost) {
   return nullptr;
 }
 
-ThreadRowKernel get_cheb_mma_kernel(int ksteps) {
+ThreadRowKernel get_cheb_mma_kernel(int ksteps, bool resid) {
+  if (resid)
+    return ksteps == 1 ? de_step_cheb_mma_kernel<1, true>
+                       : (ksteps == 2 ? de_step_cheb_mma_kernel<2, true> : de_step_cheb_mma_kernel<4, true>);
   return ksteps == 1 ? de_step_cheb_mma_kernel<1> : (ksteps == 2 ? de_step_cheb_mma_kernel<2> : de_step_cheb_mma_kernel<4>);
 }
 }  // namespace mb2

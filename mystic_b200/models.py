@@ -5,6 +5,10 @@
     griewangk   mystic/models/storn.py:120-139
     zimmermann  mystic/models/storn.py:161-191
     chebyshev{2,4,6,8,16}cost   mystic/models/poly.py:124-149, mystic/models/_model_helper.py:10-33
+    poly.CostFactory / poly.CostFactory2, lorentzian.CostFactory / lorentzian.CostFactory2
+                data-fit residual costs, mystic/models/abstract_model.py:146-161 ->
+                mystic/forward_model.py:204-260 with mystic/models/poly.py:36-54 and
+                mystic/models/lorentzian.py:32-37
 
 A descriptor names a cost function compiled into the fused kernel.  `resolve()` also recognises
 the unmodified reference callables (mystic.models.rosen is `Rosenbrock().function`, etc.) so
@@ -13,6 +17,7 @@ with TypeError: the engine has no CPU path.
 """
 
 COST_ROSEN, COST_CORANA, COST_GRIEWANGK, COST_ZIMMERMANN, COST_CHEBYSHEV, COST_CHEBYSHEV_MMA = range(6)
+COST_POLYFIT, COST_POLYFIT_MMA, COST_LORENTZIAN = 6, 7, 8
 
 CHEBYSHEV_TARGETS = {  # mystic/models/_model_helper.py:10-14
     2: [2., 0., -1.],
@@ -60,6 +65,80 @@ class DeviceCost(object):
     def __repr__(self):
         return '<mystic_b200 device cost %s>' % self.__name__
 
+
+class DataFitCost(DeviceCost):
+    """sum(((F(params)(x_i) - obs_i)/sigma)**2) over the evaluation points: what
+    mystic.forward_model.CostFactory.getCostFunction builds for ONE model with the default L2
+    metric (forward_model.py:204-260).  F is the polynomial (numpy.poly1d) or the lorentzian model."""
+
+    def __init__(self, name, cost_id, pts, observations, nparams, sigma=1.0):
+        import numpy as np
+        DeviceCost.__init__(self, name, cost_id, doc=self.__doc__)
+        self.pts = np.ascontiguousarray(pts, dtype=np.float64).ravel()
+        self.observations = np.ascontiguousarray(observations, dtype=np.float64).ravel()
+        if self.pts.shape != self.observations.shape or self.pts.size < 1:
+            raise ValueError('evaluation points and observations must be two equally long, non-empty vectors')
+        self.nparams = int(nparams)
+        self.sigma = 1.0 if sigma is None else float(sigma)   # getCostFunction(sigma=None) does not divide
+        if self.sigma == 0.0:
+            raise ZeroDivisionError('sigma')
+
+    def device_id(self, tensor_cores=False, dim=None):
+        """the polynomial fit has a second implementation on the FP64 tensor cores (the coefficient x
+        point contraction as DMMA); like the Chebyshev one it is not bit-faithful to the Horner order
+        of numpy.polyval, so it is opt-in (tensor_cores=True)."""
+        if tensor_cores and self.cost_id == COST_POLYFIT and (dim is None or dim <= 17):
+            return COST_POLYFIT_MMA
+        return self.cost_id
+
+    def params(self, extra_args=()):
+        if extra_args:
+            raise TypeError('%s() takes no ExtraArgs' % self.__name__)
+        return [float(self.pts.size), self.sigma] + self.pts.tolist() + self.observations.tolist()
+
+
+class _FitModel(object):
+    """mystic.models.poly / mystic.models.lorentzian as far as the DE path needs them
+    (abstract_model.py:103-161): evaluate, ForwardFactory, CostFactory, CostFactory2."""
+
+    def __init__(self, name, cost_id, nparams=None):
+        self.__name__ = name
+        self._cost_id = cost_id
+        self._nparams = nparams
+
+    def evaluate(self, coeffs, x):
+        """the forward model on the host, in the reference's operation order (used to make observations)"""
+        import numpy as np
+        x = np.asarray(x, dtype=np.float64)
+        if self._cost_id == COST_POLYFIT:
+            val = 0 * x                      # mystic/math/poly.py:37-39
+            for c in coeffs:
+                val = c + val * x
+            return val
+        a1, a2, a3, A0, E0, G0, n = [float(c) for c in coeffs]   # models/lorentzian.py:32-37
+        return (a1 + a2*x + a3*x*x + A0 * ( G0/(2*np.pi) )/( (x-E0)*(x-E0)+(G0/2)*(G0/2) ))/n
+
+    def ForwardFactory(self, coeffs):
+        coeffs = list(coeffs)
+        return lambda evalpts: self.evaluate(coeffs, evalpts)
+
+    def _check(self, nparams):
+        if self._nparams is not None and int(nparams) != self._nparams:
+            raise ValueError('%s has %d parameters' % (self.__name__, self._nparams))
+
+    def CostFactory(self, target, pts):
+        """cost function from a list of target coefficients and evaluation points (abstract_model.py:146-153)"""
+        self._check(len(target))
+        return DataFitCost(self.__name__ + '.cost', self._cost_id, pts, self.evaluate(target, pts), len(target))
+
+    def CostFactory2(self, pts, datapts, nparams):
+        """cost function from data points and evaluation points (abstract_model.py:155-161)"""
+        self._check(nparams)
+        return DataFitCost(self.__name__ + '.cost', self._cost_id, pts, datapts, nparams)
+
+
+poly = _FitModel('poly', COST_POLYFIT)
+lorentzian = _FitModel('lorentz', COST_LORENTZIAN, 7)
 
 rosen = DeviceCost('rosen', COST_ROSEN, doc="Rosenbrock's saddle, sum(100*(x[1:]-x[:-1]**2)**2 + (1-x[:-1])**2)")
 corana = DeviceCost('corana', COST_CORANA, doc="Corana's parabola (first four coordinates)")

@@ -19,7 +19,9 @@ class Config(ctypes.Structure):
                 ('F', ctypes.c_double), ('CR', ctypes.c_double), ('bounds_mode', ctypes.c_int32),
                 ('cost', ctypes.c_int32), ('lo', _dp), ('hi', _dp), ('cheb_M', ctypes.c_int32),
                 ('cheb_order', ctypes.c_int32), ('cheb_target', _dp), ('n_pen', ctypes.c_int32),
-                ('pad_', ctypes.c_int32), ('pen_type', _ip), ('pen_G', _dp), ('pen_h', _dp), ('pen_k', _dp)]
+                ('pad_', ctypes.c_int32), ('pen_type', _ip), ('pen_G', _dp), ('pen_h', _dp), ('pen_k', _dp),
+                ('fit_M', ctypes.c_int32), ('pad2_', ctypes.c_int32), ('fit_pts', _dp), ('fit_obs', _dp),
+                ('fit_sigma', ctypes.c_double)]
 
 
 _lib = None
@@ -83,8 +85,16 @@ class COracle(object):
             self._lo = np.ascontiguousarray(lo, dtype=np.float64)
             self._hi = np.ascontiguousarray(hi, dtype=np.float64)
             cfg.lo, cfg.hi = _d(self._lo), _d(self._hi)
+        cfg.fit_sigma = 1.0
         if cost in self.COSTS:
             cfg.cost = self.COSTS[cost]
+        elif cost in ('polyfit', 'lorentzian'):   # extra = (pts, observations[, sigma])
+            cfg.cost = 6 if cost == 'polyfit' else 8
+            self._fit_pts = np.ascontiguousarray(extra[0], dtype=np.float64)
+            self._fit_obs = np.ascontiguousarray(extra[1], dtype=np.float64)
+            cfg.fit_M = int(self._fit_pts.size)
+            cfg.fit_pts, cfg.fit_obs = _d(self._fit_pts), _d(self._fit_obs)
+            cfg.fit_sigma = float(extra[2]) if len(extra) > 2 else 1.0
         else:
             order = int(cost[len('chebyshev'):-len('cost')])
             cfg.cost = 4

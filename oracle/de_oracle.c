@@ -23,7 +23,8 @@
 enum { BASE_BEST1 = 0, BASE_RAND1 = 1, BASE_RANDTOBEST1 = 2, BASE_BEST2 = 3, BASE_RAND2 = 4 };
 enum { XOVER_EXP = 0, XOVER_BIN = 1 };
 enum { BOUNDS_NONE = 0, BOUNDS_REJECT = 1, BOUNDS_CLAMP = 2 };
-enum { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4 };
+enum { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4,
+       COST_POLYFIT = 6, COST_LORENTZIAN = 8 };
 
 typedef struct {
   int32_t dim;
@@ -45,6 +46,12 @@ typedef struct {
   const double* pen_G;
   const double* pen_h;
   const double* pen_k; /* k*h**n */
+  /* data-fit residual costs (forward_model.py:204-260): M points, observations, sigma */
+  int32_t fit_M;
+  int32_t pad2_;
+  const double* fit_pts;
+  const double* fit_obs;
+  double fit_sigma;
 } orc_config;
 
 /* strategy id -> base, crossover, donors (strategy.py:34-311; only Best1Bin is binomial) */
@@ -142,6 +149,27 @@ static double cost_rosen(const double* x, int D, double* scratch) {
     scratch[i] = 100.0 * (t * t) + u * u;
   }
   return np_pairwise_sum(scratch, D - 1);
+}
+
+/* forward_model.py:241-258 with models/poly.py:36-54 (numpy.polyval order) or
+ * models/lorentzian.py:32-37; x = (F - obs)/sigma; numpy.sum(x*x).  scratch: fit_M doubles */
+static double cost_datafit(const double* c, int D, const orc_config* cfg, double* scratch) {
+  const int M = cfg->fit_M;
+  for (int i = 0; i < M; ++i) {
+    const double x = cfg->fit_pts[i];
+    double y;
+    if (cfg->cost == COST_POLYFIT) {
+      y = 0.0;
+      for (int j = 0; j < D; ++j) y = y * x + c[j];
+    } else {
+      const double a1 = c[0], a2 = c[1], a3 = c[2], A0 = c[3], E0 = c[4], G0 = c[5], n = c[6];
+      const double pi = 3.141592653589793;
+      y = (a1 + a2 * x + a3 * x * x + A0 * (G0 / (2 * pi)) / ((x - E0) * (x - E0) + (G0 / 2) * (G0 / 2))) / n;
+    }
+    const double d = (y - cfg->fit_obs[i]) / cfg->fit_sigma;
+    scratch[i] = d * d;
+  }
+  return np_pairwise_sum(scratch, M);
 }
 
 static double sign_(double v) { return (v > 0.0) ? 1.0 : ((v < 0.0) ? -1.0 : 0.0); }
@@ -250,6 +278,8 @@ static double energy_of(const double* x, const orc_config* cfg, double* scratch)
       case COST_CORANA: raw = cost_corana(x, D); break;
       case COST_GRIEWANGK: raw = cost_griewangk(x, D); break;
       case COST_ZIMMERMANN: raw = cost_zimmermann(x); break;
+      case COST_POLYFIT:
+      case COST_LORENTZIAN: raw = cost_datafit(x, D, cfg, scratch); break;
       default: raw = cost_chebyshev(x, D, cfg); break;
     }
   }
@@ -298,7 +328,7 @@ int orc_step0(const orc_config* cfg, const double* pop_cur, double* pop_next, do
   const int64_t np = cfg->np;
 #pragma omp parallel
   {
-    double* scratch = (double*)malloc(sizeof(double) * (D + 1));
+    double* scratch = (double*)malloc(sizeof(double) * ((D > cfg->fit_M ? D : cfg->fit_M) + 1));
 #pragma omp for schedule(static)
     for (int64_t c = 0; c < np; ++c) {
       double* row = pop_next + c * D;
@@ -339,7 +369,7 @@ int orc_step(const orc_config* cfg, const double* pop_cur, double* pop_next, con
 #pragma omp parallel
   {
     double* t = (double*)malloc(sizeof(double) * (D + 1));
-    double* scratch = (double*)malloc(sizeof(double) * (D + 1));
+    double* scratch = (double*)malloc(sizeof(double) * ((D > cfg->fit_M ? D : cfg->fit_M) + 1));
     unsigned char* mask = (unsigned char*)malloc(D);
 #pragma omp for schedule(static)
     for (int64_t c = 0; c < np; ++c) {

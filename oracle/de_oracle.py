@@ -169,8 +169,53 @@ def cost_chebyshev(x, order=8, M=61):
     return result
 
 
+def cost_polyfit(x, pts, obs, sigma=1.0):
+    """mystic/forward_model.py:241-258 with the polynomial model of mystic/models/poly.py:36-54:
+    F(params) = numpy.poly1d(params) whose evaluation is numpy.polyval's
+    `y = zeros_like(x); for pv in p: y = y*x + pv`; x = (y - observations)/sigma; metric
+    numpy.sum(x*x) (abstract_model.py: sigma = 1.0, metric L2)."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    pts = np.asarray(pts, dtype=np.float64)
+    obs = np.asarray(obs, dtype=np.float64)
+    out = np.empty(x.shape[0])
+    for r in range(x.shape[0]):
+        y = np.zeros_like(pts)
+        for pv in x[r]:
+            y = y * pts + pv
+        d = (y - obs) / sigma
+        out[r] = np.sum(d * d)
+    return out
+
+
+def cost_lorentzian(x, pts, obs, sigma=1.0):
+    """the same residual cost with the lorentzian peak of mystic/models/lorentzian.py:32-37,
+    coeffs = (a1,a2,a3,A0,E0,G0,n), evaluated in the reference's own expression order."""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    pts = np.asarray(pts, dtype=np.float64)
+    obs = np.asarray(obs, dtype=np.float64)
+    pi = np.pi
+    out = np.empty(x.shape[0])
+    for r in range(x.shape[0]):
+        a1, a2, a3, A0, E0, G0, n = [float(v) for v in x[r]]
+        X = pts
+        with np.errstate(all='ignore'):
+            try:
+                y = (a1 + a2*X + a3*X*X + A0 * ( G0/(2*pi) )/( (X-E0)*(X-E0)+(G0/2)*(G0/2) ))/n
+            except ZeroDivisionError:   # n == 0.0 as a python float; cannot happen inside a strict range n > 0
+                y = np.full_like(X, np.nan)
+            d = (y - obs) / sigma
+            out[r] = np.sum(d * d)
+    return out
+
+
 def make_cost(name, extra_args=()):
-    """name -> f(X[NP,D]) -> [NP]; names as exported by mystic.models / mystic.models.poly."""
+    """name -> f(X[NP,D]) -> [NP]; names as exported by mystic.models / mystic.models.poly.
+    Data-fit costs: name 'polyfit' / 'lorentzian' with extra_args = (pts, observations[, sigma])."""
+    if name in ('polyfit', 'lorentzian'):
+        pts, obs = extra_args[0], extra_args[1]
+        sigma = float(extra_args[2]) if len(extra_args) > 2 else 1.0
+        f = cost_polyfit if name == 'polyfit' else cost_lorentzian
+        return lambda X: f(X, pts, obs, sigma)
     if name == 'rosen':
         return cost_rosen
     if name == 'corana':

@@ -72,6 +72,28 @@ class RecordingMap(object):
         return out
 
 
+def _fit_points(spec):
+    """('arange', lo, hi, step) | ('linspace', lo, hi, M) | explicit list -> float64 array"""
+    if isinstance(spec, (list, tuple)) and spec and spec[0] == 'arange':
+        return np.arange(spec[1], spec[2], spec[3], dtype=np.float64)
+    if isinstance(spec, (list, tuple)) and spec and spec[0] == 'linspace':
+        return np.linspace(spec[1], spec[2], int(spec[3]))
+    return np.asarray(spec, dtype=np.float64)
+
+
+def _fit_cost(case):
+    """data-fit residual costs built by the REFERENCE's own factories:
+    mystic.models.poly.CostFactory(target, pts) / mystic.models.lorentzian.CostFactory(target, pts)
+    (abstract_model.py:146-153 -> forward_model.py:204-260).  Returns (cost, pts, observations)."""
+    import mystic.models as mm
+    model = mm.poly if case['cost'] == 'polyfit' else mm.lorentzian
+    pts = _fit_points(case['fit']['pts'])
+    target = [float(v) for v in case['fit']['target']]
+    cost = model.CostFactory(target, pts)
+    obs = np.asarray(model.evaluate(target, pts), dtype=np.float64)
+    return cost, pts, obs
+
+
 def _cost(name):
     import importlib
     import mystic.models as mm
@@ -156,11 +178,15 @@ def record(case):
             import mystic.termination as mt
             term = mt.VTR(-1.0)  # never satisfied for the non-negative costs used here
         extra = tuple(case['ExtraArgs']) if case.get('ExtraArgs') else None
+        fit = None
+        if case['cost'] in ('polyfit', 'lorentzian'):
+            fit = _fit_cost(case)
+        the_cost = fit[0] if fit else _cost(case['cost'])
         if via == 'ctor':
-            solver.Solve(_cost(case['cost']), term, ExtraArgs=extra, strategy=strategy,
+            solver.Solve(the_cost, term, ExtraArgs=extra, strategy=strategy,
                          callback=callback)
         else:
-            solver.Solve(_cost(case['cost']), term, ExtraArgs=extra, strategy=strategy,
+            solver.Solve(the_cost, term, ExtraArgs=extra, strategy=strategy,
                          CrossProbability=case['CR'], ScalingFactor=case['F'],
                          callback=callback)
     finally:
@@ -199,6 +225,8 @@ def record(case):
         'energy_history': np.array(solver.energy_history, dtype=np.float64),
         'donors': donors, 'nstart': nstart, 'nuni': nuni, 'uni': uni, 'mt_state': mt_state,
     }
+    if fit:
+        out['fit_pts'], out['fit_obs'] = fit[1], fit[2]
     return out
 
 
@@ -302,6 +330,19 @@ def cases():
                                             bounds=([-1000.] * 64, [1000.] * 64, True),
                                             penalty=[dict(ptype='quadratic_inequality', G=[1.] * 64, h=100., k=100, hpow=5)],
                                             maxgen=4)
+    # data-fit residual costs: the reference's own CostFactory closures
+    cs['fit_poly3_rand1exp'] = dict(dim=3, NP=20, strategy='Rand1Exp', cost='polyfit', CR=0.5, F=0.5, seed=301,
+                                    init=('random', [-100.] * 3, [100.] * 3), bounds=([-100.] * 3, [100.] * 3, False),
+                                    fit=dict(target=[1., 2., 1.], pts=('arange', -50., 51., 1.)), maxgen=12)
+    cs['fit_poly9_best1bin'] = dict(dim=9, NP=36, strategy='Best1Bin', cost='polyfit', CR=0.9, F=0.8, seed=302,
+                                    init=('random', [-200.] * 9, [200.] * 9),
+                                    fit=dict(target=[128., 0., -256., 0., 160., 0., -32., 0., 1.], pts=('linspace', -1., 1., 200)),
+                                    maxgen=8)
+    cs['fit_lorentzian_rand1exp'] = dict(dim=7, NP=28, strategy='Rand1Exp', cost='lorentzian', CR=0.9, F=0.8, seed=303,
+                                         init=('random', [0.5, 30., -15., 10., 0., 0.05, 100.], [2., 60., -5., 50., 2., 1., 200.]),
+                                         bounds=([0.5, 30., -15., 10., 0., 0.05, 100.], [2., 60., -5., 50., 2., 1., 200.], True),
+                                         fit=dict(target=[1., 45., -10., 20., 1., 0.1, 120.], pts=('arange', 0.05, 3.0, 0.1)),
+                                         maxgen=10)
     return cs
 
 

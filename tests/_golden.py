@@ -19,6 +19,27 @@ def load(name):
     return meta, z
 
 
+FIT_COSTS = ('polyfit', 'lorentzian')
+
+
+def extra_of(meta, z):
+    """ExtraArgs of the recorded run for orc.make_cost / c_port.COracle: data-fit costs carry their
+    evaluation points and observations in the recording"""
+    if meta['cost'] in FIT_COSTS:
+        return (z['fit_pts'], z['fit_obs'], 1.0)
+    return tuple(meta.get('ExtraArgs') or ())
+
+
+def device_cost_of(meta, z):
+    """the mystic_b200.models object of the recorded run"""
+    from mystic_b200 import models
+    if meta['cost'] == 'polyfit':
+        return models.poly.CostFactory2(z['fit_pts'], z['fit_obs'], meta['dim'])
+    if meta['cost'] == 'lorentzian':
+        return models.lorentzian.CostFactory2(z['fit_pts'], z['fit_obs'], meta['dim'])
+    return getattr(models, meta['cost'])
+
+
 def bounds_of(meta):
     b = meta.get('bounds')
     if b is None:

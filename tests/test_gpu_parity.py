@@ -33,11 +33,11 @@ def energy_close(dev, ref, x=None, cost=None, what=''):
         raise AssertionError('%s: energy mismatch at %d: %r vs %r' % (what, i, dev[i], ref[i]))
 
 
-def configure(eng, meta):
+def configure(eng, meta, z=None):
     from mystic_b200 import models, penalty
     lo, hi, mode = G.bounds_of(meta)
     eng.set_bounds(mode, lo, hi)
-    cost = getattr(models, meta['cost'])
+    cost = G.device_cost_of(meta, z)
     eng.set_cost(cost.cost_id, cost.params(tuple(meta.get('ExtraArgs') or ())))
     if meta.get('penalty'):
         def pen(x):
@@ -69,7 +69,7 @@ def test_engine_replay_matches_reference_recording(name, kernel_path):
     meta, z = G.load(name)
     NP, D = z['pop0'].shape
     eng = DeviceEngine(NP, D, keep_trials=True)
-    configure(eng, meta)
+    configure(eng, meta, z)
     eng.upload_population(z['pop0'])
     evals = 0
     for g in range(meta['generations'] + 1):
@@ -117,7 +117,7 @@ def test_solver_reference_rng_reproduces_seeded_reference_run(name):
     else:
         s.SetInitialPoints(list(meta['init'][1]), meta['init'][2])
     G.restore_mt_state(z)
-    solve(s, meta)
+    solve(s, meta, z)
     assert s.generations == meta['generations']
     assert s.evaluations == meta['evaluations']
     assert str(s.Terminated(info=True)) == meta['stop']
@@ -171,7 +171,22 @@ PHILOX_CASES = [
       dict(ptype='linear_equality', G=[0.5] * 48, h=3., k=10, hpow=2)], 0.9, 0.8, 6),
     (16, 19, 'Rand1Exp', 'rosen', (), (-2., 2., orc.BOUNDS_CLAMP), None, 0.0, 0.8, 3),
     (128, 64, 'Best1Bin', 'corana', (), (-1000., 1000., orc.BOUNDS_CLAMP), None, 0.3, 0.9, 4),
+    # data-fit residual costs: extra = (evaluation points, observations)
+    (5, 40, 'Best1Exp', 'polyfit', (np.linspace(-2., 2., 77), np.cos(np.linspace(-2., 2., 77))), (-3., 3., orc.BOUNDS_CLAMP),
+     None, 0.9, 0.8, 6),
+    (9, 30, 'Best1Bin', 'polyfit', (np.linspace(-1., 1., 300), np.linspace(-1., 1., 300) ** 8), None, None, 0.9, 0.7, 5),
+    (7, 33, 'Rand1Exp', 'lorentzian', (np.arange(0.05, 3.0, 0.1), 1.0 / (1.0 + np.arange(0.05, 3.0, 0.1) ** 2)),
+     (0.1, 3., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 6),
 ]
+
+
+def _device_cost(cost, extra, dim):
+    from mystic_b200 import models
+    if cost == 'polyfit':
+        return models.poly.CostFactory2(extra[0], extra[1], dim), ()
+    if cost == 'lorentzian':
+        return models.lorentzian.CostFactory2(extra[0], extra[1], dim), ()
+    return getattr(models, cost), extra
 
 
 @pytest.mark.parametrize('case', PHILOX_CASES, ids=lambda c: '%s-%s-D%d' % (c[2], c[3], c[0]))
@@ -190,8 +205,8 @@ def test_philox_mode_matches_oracle_philox(case, kernel_path):
     ihi = np.full(dim, 3.0) if bounds is None else hi * 1.25
 
     eng = DeviceEngine(NP, dim, keep_trials=True)
-    c = getattr(models, cost)
-    eng.set_cost(c.cost_id, c.params(extra))
+    c, dev_extra = _device_cost(cost, extra, dim)
+    eng.set_cost(c.cost_id, c.params(dev_extra))
     eng.set_bounds(mode, lo, hi)
     terms = pen or ()
     if pen:
@@ -267,6 +282,68 @@ def test_costs_random_batches_match_oracle(kernel_path):
             got = getattr(models, name)(X, *extra)
             want = orc.make_cost(name, extra)(X)
             energy_close(got, want, X, name, '%s D=%d' % (name, D))
+
+
+def test_datafit_costs_random_batches_match_oracle(kernel_path):
+    """forward_model.CostFactory costs (polynomial least squares, lorentzian) on random parameter
+    batches: Horner / elementwise paths <= 1e-12 of the oracle (numpy in the reference's order), with
+    and without sigma; the DMMA contraction of the polynomial fit on the same batches"""
+    from mystic_b200 import models
+    rng = np.random.default_rng(11)
+    pts = np.linspace(-1., 1., 333)
+    for n, span in ((3, 100.), (9, 200.), (17, 5.)):
+        target = rng.uniform(-span, span, size=n)
+        cost = models.poly.CostFactory(target, pts)
+        X = rng.uniform(-span, span, size=(97, n))
+        want = orc.cost_polyfit(X, pts, cost.observations)
+        energy_close(cost(X), want, what='polyfit n=%d' % n)
+        energy_close(cost(X, tensor_cores=True), want, what='polyfit DMMA n=%d' % n)
+        scaled = models.DataFitCost('poly.cost', models.COST_POLYFIT, pts, cost.observations, n, sigma=2.5)
+        energy_close(scaled(X), orc.cost_polyfit(X, pts, cost.observations, 2.5), what='polyfit sigma n=%d' % n)
+        energy_close(scaled(X, tensor_cores=True), orc.cost_polyfit(X, pts, cost.observations, 2.5), what='polyfit DMMA sigma')
+    assert models.poly.CostFactory([1., 2., 1.], np.arange(-50., 51.))([1., 2., 1.]) == 0.0
+    lo = np.array([0.5, 30., -15., 10., 0., 0.05, 100.])
+    hi = np.array([2., 60., -5., 50., 2., 1., 200.])
+    bins = np.arange(0.05, 3.0, 0.1)
+    lcost = models.lorentzian.CostFactory([1., 45., -10., 20., 1., 0.1, 120.], bins)
+    X = lo + (hi - lo) * rng.uniform(size=(97, 7))
+    energy_close(lcost(X), orc.cost_lorentzian(X, bins, lcost.observations), what='lorentzian')
+    assert lcost([1., 45., -10., 20., 1., 0.1, 120.]) == 0.0
+
+
+def test_polyfit_dmma_trajectory_matches_oracle():
+    """the tensor-core polynomial fit inside the fused generation kernel: trial vectors / selections
+    bit-exact against the oracle on a random population, energies <= 1e-12"""
+    from mystic_b200 import models
+    from mystic_b200.engine import DeviceEngine
+    D, NP, M = 9, 200, 513
+    pts = np.linspace(-1., 1., M)
+    obs = np.polyval([128., 0., -256., 0., 160., 0., -32., 0., 1.], pts) + 0.25 * np.sin(7 * pts)
+    cost = models.poly.CostFactory2(pts, obs, D)
+    seed = 0xF17
+    eng = DeviceEngine(NP, D, keep_trials=True)
+    eng.set_cost(cost.device_id(True, D), cost.params())
+    eng.set_bounds(orc.BOUNDS_NONE)
+    eng.set_strategy(orc.STRATEGIES['Best1Exp'][0], 0.9, 1.0)
+    eng.set_rng_philox(seed)
+    ilo, ihi = np.full(D, -100.), np.full(D, 100.)
+    eng.init_population(seed, ilo, ihi)
+    st = orc.DEState(orc.philox_init_population(seed, NP, ilo, ihi), None, None, orc.BOUNDS_NONE)
+    ocost = orc.make_cost('polyfit', (pts, obs))
+    for g in range(5):
+        if g == 0:
+            eng.eval_initial()
+            orc.step0(st, ocost, ())
+        else:
+            eng.step()
+            orc.step(st, 'Best1Exp', 1.0, 0.9, ocost, (), philox=dict(seed=seed, offset=0))
+        best_e, best_idx, n_inf, n_acc, gen, best_x = eng.read_result()
+        trial, trial_e = eng.trials()
+        G.assert_bits_equal(trial, st.trialSolution, 'gen %d trial' % g)
+        energy_close(trial_e, st.trialEnergy, what='gen %d trialE' % g)
+        G.assert_bits_equal(eng.population(), st.population, 'gen %d population' % g)
+        G.assert_bits_equal(best_x, st.bestSolution, 'gen %d bestX' % g)
+    eng.close()
 
 
 def test_full_size_properties_config2():

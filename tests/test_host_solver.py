@@ -37,14 +37,14 @@ def make_solver(meta, z, rng, engine=OracleEngine, **extra):
     return s
 
 
-def solve(s, meta):
+def solve(s, meta, z=None):
     term = getattr(termination, meta['termination'][0])(*meta['termination'][1:]) if meta.get('termination') \
         else termination.VTR(-1.0)
     extra = tuple(meta['ExtraArgs']) if meta.get('ExtraArgs') else None
     kw = dict(strategy=getattr(strategy, meta['strategy']))
     if meta['via'] == 'solve':
         kw.update(CrossProbability=meta['CR'], ScalingFactor=meta['F'])
-    s.Solve(getattr(models, meta['cost']), term, ExtraArgs=extra, **kw)
+    s.Solve(G.device_cost_of(meta, z), term, ExtraArgs=extra, **kw)
 
 
 def replay_draws(z):
@@ -75,7 +75,7 @@ def test_solve_replay_matches_reference(name):
     s = make_solver(meta, z, 'replay')
     s.SetPopulation(z['pop0'])
     s.SetReplayDraws(replay_draws(z))
-    solve(s, meta)
+    solve(s, meta, z)
     check_against_reference(s, meta, z, exact_energy=(meta['cost'] != 'griewangk'))
 
 
@@ -94,7 +94,7 @@ def test_solve_reference_rng_reproduces_seeded_reference_run(name):
         s.SetInitialPoints(list(meta['init'][1]), meta['init'][2])
     G.assert_bits_equal(s.population, z['pop0'], 'initial population')
     G.restore_mt_state(z)
-    solve(s, meta)
+    solve(s, meta, z)
     check_against_reference(s, meta, z, exact_energy=(meta['cost'] != 'griewangk'))
 
 

@@ -13,7 +13,7 @@ def test_c_oracle_reproduces_reference(name):
     meta, z = G.load(name)
     lo, hi, mode = G.bounds_of(meta)
     o = c_port.COracle(z['pop0'], meta['strategy'], meta['CR_eff'], meta['F_eff'], meta['cost'],
-                       tuple(meta.get('ExtraArgs') or ()), lo, hi, mode, meta.get('penalty') or ())
+                       G.extra_of(meta, z), lo, hi, mode, meta.get('penalty') or ())
     for g in range(meta['generations'] + 1):
         if g == 0:
             o.step0()

@@ -15,7 +15,7 @@ from tests import _golden as G
 def test_oracle_reproduces_reference(name):
     meta, z = G.load(name)
     lo, hi, mode = G.bounds_of(meta)
-    cost = orc.make_cost(meta['cost'], tuple(meta.get('ExtraArgs') or ()))
+    cost = orc.make_cost(meta['cost'], G.extra_of(meta, z))
     pen = meta.get('penalty') or ()
     st = orc.DEState(z['pop0'], lo, hi, mode)
     orc.step0(st, cost, pen)
