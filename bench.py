@@ -48,9 +48,35 @@ WORKLOADS = {
     'c3h': dict(desc='chebyshev8cost M=4096, 9 coeffs, NP=1048576/GPU, Best1Exp CR=1.0 F=0.9, init +-100 (Horner)',
                 cost='chebyshev8cost', extra=(4096,), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
                 lo=-100., hi=100., bounds=None, penalty=None, k=2),
+    # data-fit residual costs of forward_model.CostFactory (extra = points/observations, made in main)
+    'f2': dict(desc='polynomial least-squares fit (poly.CostFactory2), 9 coeffs x 4096 points, NP=1048576/GPU, Best1Exp CR=1.0 '
+                    'F=0.9, init +-100 (FP64 DMMA)',
+               cost='polyfit', extra=(), fit=dict(M=4096), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
+               lo=-100., hi=100., bounds=None, penalty=None, k=2, tensor_cores=True),
+    'f2h': dict(desc='polynomial least-squares fit (poly.CostFactory2), 9 coeffs x 4096 points, NP=1048576/GPU, Best1Exp '
+                     'CR=1.0 F=0.9, init +-100 (Horner, numpy.polyval order)',
+                cost='polyfit', extra=(), fit=dict(M=4096), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
+                lo=-100., hi=100., bounds=None, penalty=None, k=2),
 }
 
 BIN_STRATEGIES = ('Best1Bin',)
+
+
+def fit_data(w):
+    """synthetic data of a data-fit workload: Chebyshev-8 values on [-1, 1] plus a smooth perturbation"""
+    M = w['fit']['M']
+    pts = np.linspace(-1.0, 1.0, M)
+    obs = np.polyval([128., 0., -256., 0., 160., 0., -32., 0., 1.], pts) + 0.25 * np.sin(7.0 * pts)
+    return pts, obs
+
+
+def device_cost(w):
+    """-> (mystic_b200.models cost object, ExtraArgs)"""
+    from mystic_b200 import models
+    if w['cost'] == 'polyfit':
+        pts, obs = w['extra'][0], w['extra'][1]
+        return models.poly.CostFactory2(pts, obs, w['dim']), None
+    return getattr(models, w['cost']), (tuple(w['extra']) or None)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the fused generation kernel, per launch at the
 # workload's full per-GPU size, from one `ncu --set full` capture each (summaries under profiles/)
@@ -75,6 +101,9 @@ def algorithmic_bytes_per_candidate(w):
 def algorithmic_flops_per_candidate(w):
     if w['cost'].startswith('chebyshev'):
         return 2.0 * w['dim'] * (w['extra'][0] + 2)
+    if w['cost'] == 'polyfit':
+        M = w['fit']['M']
+        return (2.0 * w['dim'] + 3.0) * M   # Horner mul+add per coefficient, residual, square, accumulate
     return None
 
 
@@ -232,6 +261,8 @@ def main():
         import faulthandler
         faulthandler.dump_traceback_later(90, exit=True)   # a hung run prints where it hangs
     w = dict(WORKLOADS[args.workload])
+    if w.get('fit'):
+        w['extra'] = fit_data(w)
     if args.np:
         w['np'] = args.np
 
@@ -258,8 +289,7 @@ def main():
     NP_global = NP_local * world
     D = w['dim']
     seed = 0x5EED
-    cost = getattr(models, w['cost'])
-    extra = tuple(w['extra']) or None
+    cost, extra = device_cost(w)
     never = termination.VTR(-1.0)
 
     def barrier():
@@ -380,7 +410,8 @@ def main():
                     'traffic': roofline.get('traffic'), 'traffic_source': roofline.get('traffic_source'),
                     'peak_source': 'measured DMMA.8x8x4 peak (profiles/r1_fp64_peaks_b200.json)',
                     'algorithmic_flops_per_candidate': flops, 'hbm_frac': achieved / peaks['hbm_gbs'],
-                    'kernel': 'de_step_cheb_mma_kernel' if w.get('tensor_cores') else 'de_step_kernel (Horner)'}
+                    'kernel': ('de_step_cheb_mma_kernel' + ('<KS, RESID>' if w['cost'] == 'polyfit' else ''))
+                    if w.get('tensor_cores') else 'de_step_kernel (Horner)'}
 
     line = {
         'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': value, 'unit': 'candidate-evals/s',

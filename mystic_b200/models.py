@@ -155,6 +155,37 @@ _BY_NAME = dict((c.__name__, c) for c in (rosen, corana, griewangk, zimmermann, 
 _BY_REFERENCE_CLASS = {'Rosenbrock': rosen, 'Corana': corana, 'Griewangk': griewangk, 'Zimmermann': zimmermann}
 
 
+def _resolve_reference_costfactory(cost):
+    """The closure mystic.forward_model.CostFactory.getCostFunction returns (forward_model.py:241-258),
+    e.g. from mystic.models.poly.CostFactory(target, pts): recognised when it holds exactly ONE model
+    whose ForwardFactory belongs to mystic.models.poly.Polynomial or mystic.models.lorentzian.Lorentzian,
+    no input checker / output filter, and the default L2 metric."""
+    import numpy as np
+    code = getattr(cost, '__code__', None)
+    if code is None or getattr(cost, '__module__', '') != 'mystic.forward_model' or not cost.__closure__:
+        return None
+    cells = dict(zip(code.co_freevars, (c.cell_contents for c in cost.__closure__)))
+    if not all(k in cells for k in ('self', 'evalpts', 'observations', 'sigma', 'metric')):
+        return None
+    cf = cells['self']
+    fac, nin = getattr(cf, '_forwardFactories', None), getattr(cf, '_inputs', None)
+    if not fac or len(fac) != 1:
+        raise TypeError('the B200 engine evaluates CostFactory costs with exactly one forward model')
+    owner = getattr(fac[0], '__self__', None)
+    kind = {'Polynomial': COST_POLYFIT, 'Lorentzian': COST_LORENTZIAN}.get(type(owner).__name__)
+    if kind is None or not type(owner).__module__.startswith('mystic.models'):
+        raise TypeError('only the poly and lorentzian forward models of mystic.models exist on the device')
+    from_null = lambda f: type(f).__name__ in ('NullChecker', 'function') and f(np.ones(1), np.ones(1)) is None  # noqa: E731
+    ident = lambda f: np.array_equal(f(np.array([1.5, -2.0])), np.array([1.5, -2.0]))  # noqa: E731
+    if not from_null(cf._inputCheckers[0]) or not ident(cf._outputFilters[0]):
+        raise TypeError('input checkers / output filters of a CostFactory cannot run on the device')
+    probe = np.array([1.0, -2.0, 0.5])
+    if float(cells['metric'](probe)) != 5.25:
+        raise TypeError('only the default L2 metric, sum(x*x), exists on the device')
+    name = 'poly.cost' if kind == COST_POLYFIT else 'lorentz.cost'
+    return DataFitCost(name, kind, cells['evalpts'], cells['observations'], nin[0], cells['sigma'])
+
+
 def resolve(cost):
     """DeviceCost | reference callable | name -> DeviceCost, else TypeError."""
     if isinstance(cost, DeviceCost):
@@ -170,6 +201,9 @@ def resolve(cost):
             if kls == 'Rosenbrock' and getattr(owner, 'axis', None) is not None:
                 raise TypeError('Rosenbrock(axis=...) is not supported on the device')
             return _BY_REFERENCE_CLASS[kls]
+    fit = _resolve_reference_costfactory(cost)
+    if fit is not None:
+        return fit
     name = getattr(cost, '__name__', None)
     if mod.startswith('mystic.models') and name in _BY_NAME:
         return _BY_NAME[name]  # mystic.models.poly.chebyshev8cost etc.

@@ -91,3 +91,37 @@ def test_host_callables_are_rejected():
         def pen(x):
             return 0.0
         s.SetPenalty(pen)                             # python condition: not device-expressible
+
+
+def test_reference_costfactory_closures_are_recognised():
+    """mystic.models.poly.CostFactory(target, pts) / lorentzian.CostFactory2(...) return closures of
+    mystic.forward_model.CostFactory.getCostFunction; resolve() turns them into the device's data-fit
+    costs with the same points, observations and sigma, and the reference-seeded run reproduces the
+    recording made with that very closure"""
+    from mystic_b200 import models
+    pts = np.arange(-50., 51., 1.)
+    ref_cost = mystic.models.poly.CostFactory([1., 2., 1.], pts)
+    dev = models.resolve(ref_cost)
+    assert dev.cost_id == models.COST_POLYFIT and dev.nparams == 3 and dev.sigma == 1.0
+    assert np.array_equal(dev.pts, pts) and np.array_equal(dev.observations, mystic.models.poly.evaluate([1., 2., 1.], pts))
+    bins = np.arange(0.05, 3.0, 0.1)
+    lor = models.resolve(mystic.models.lorentzian.CostFactory2(bins, np.ones_like(bins), 7))
+    assert lor.cost_id == models.COST_LORENTZIAN and lor.nparams == 7
+    # other metrics cannot run on the device
+    from mystic.forward_model import CostFactory
+    cf = CostFactory()
+    cf.addModel(mystic.models.poly.ForwardFactory, 3, 'poly')
+    with pytest.raises(TypeError):
+        models.resolve(cf.getCostFunction(pts, pts, metric=lambda x: np.sum(np.abs(x))))
+    # end to end against the recording: the reference closure handed to the B200 solver
+    meta, z = G.load('fit_poly3_rand1exp')
+    random.seed(meta['seed'])
+    s = DifferentialEvolutionSolver2(3, 20, rng='reference', engine=OracleEngine, CrossProbability=0.5, ScalingFactor=0.5)
+    s.SetRandomInitialPoints([-100.] * 3, [100.] * 3)
+    s.SetStrictRanges([-100.] * 3, [100.] * 3)
+    s.SetEvaluationLimits(generations=meta['maxgen'])
+    G.restore_mt_state(z)
+    s.Solve(ref_cost, mystic.termination.VTR(-1.0), strategy=mystic.strategy.Rand1Exp)
+    assert s.generations == meta['generations'] and s.evaluations == meta['evaluations']
+    G.assert_bits_equal(np.array(s.bestSolution), z['bestX'][-1], 'bestSolution')
+    G.assert_bits_equal(np.array(s.energy_history), z['energy_history'], 'energy_history')
