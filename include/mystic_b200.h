@@ -63,7 +63,12 @@ enum mb2_cost {
    * L2 metric): sum(((F(params)(x_i) - obs_i)/sigma)^2) over M evaluation points */
   MB2_COST_POLYFIT = 6,     /* F = models/poly.py:36-54 (numpy.poly1d), dim = number of coefficients <= 32 */
   MB2_COST_POLYFIT_MMA = 7, /* same cost, the coefficient x point contraction on DMMA (dim <= 17) */
-  MB2_COST_LORENTZIAN = 8   /* F = models/lorentzian.py:32-37, dim = 7 */
+  MB2_COST_LORENTZIAN = 8,  /* F = models/lorentzian.py:32-37, dim = 7 */
+  /* separable test functions (any dim) */
+  MB2_COST_SPHERE = 9,      /* models/dejong.py:54-66   */
+  MB2_COST_RASTRIGIN = 10,  /* models/pohlheim.py:123-132 */
+  MB2_COST_SCHWEFEL = 11,   /* models/pohlheim.py:60-71 */
+  MB2_COST_ACKLEY = 12      /* models/pohlheim.py:186-204 */
 };
 
 /* SetStrictRanges modes (abstract_solver.py:334-448, tools.py:404-430) */

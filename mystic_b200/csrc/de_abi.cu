@@ -84,7 +84,7 @@ struct mb2_ctx {
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
-  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0, nullptr, 1.0};
+  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0, nullptr, 1.0, 0};
   double* fit_obs = nullptr;
   size_t cap_fit_obs = 0;
   double bounds_absmax = 0.0;  // max(|lo_i|, |hi_i|) of the strict range
@@ -198,6 +198,9 @@ TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
 ThreadRowKernel get_small_kernel(int cost);
 ThreadRowKernel get_cheb_mma_kernel(int ksteps, bool resid);
 StepKernel get_datafit_ldg_kernel(int base, int xover, int cost);
+StepKernel get_separable_ldg_kernel(int base, int xover, bool vec);
+ThreadRowKernel get_separable_small_kernel();
+ThreadRowKernel get_separable_subwarp_kernel(int lanes_per_row, bool vec);
 ThreadRowKernel get_datafit_small_kernel(int cost);
 ThreadRowKernel get_datafit_subwarp_kernel(int cost);
 ThreadRowKernel get_subwarp_kernel(int cost, int lanes_per_row, bool vec);
@@ -209,8 +212,11 @@ namespace {
 
 bool is_datafit(int cost) { return cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN; }
 
+bool is_separable(int cost) { return cost >= MB2_COST_SPHERE && cost <= MB2_COST_ACKLEY; }
+
 StepKernel pick_kernel(const StrategyInfo& s, int cost, bool vec) {
   if (is_datafit(cost)) return get_datafit_ldg_kernel(s.base, s.xover, cost);
+  if (is_separable(cost)) return get_separable_ldg_kernel(s.base, s.xover, vec);
   return get_ldg_kernel(s.xover == XOVER_BIN ? BASE_BEST1 : s.base, s.xover, cost, vec);
 }
 
@@ -289,6 +295,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   if (mode != MODE_STEP) s = {BASE_RAND1, XOVER_EXP, 3};  // no best/donors needed; any instance
   const bool cheb_mma = (c->cost == MB2_COST_CHEBYSHEV_MMA || c->cost == MB2_COST_POLYFIT_MMA);
   const bool datafit = is_datafit(c->cost);
+  const bool separable = is_separable(c->cost);
   StepKernel k = cheb_mma ? nullptr : pick_kernel(s, c->cost, vec);
   if (k == nullptr && !cheb_mma) return fail(MB2_EINVAL, "no kernel for strategy %d cost %d", c->strategy, c->cost);
   ThreadRowKernel kc = cheb_mma ? get_cheb_mma_kernel(c->cheb_ks, c->cost == MB2_COST_POLYFIT_MMA) : nullptr;
@@ -311,14 +318,17 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
       else if (c->cost == MB2_COST_GRIEWANGK) kr = get_rows_kernel_griewangk(lpr, s.k);
     }
     if (kr != nullptr) kw = kr;
-    else if (small_kind == 2) ks = datafit ? get_datafit_small_kernel(c->cost) : get_small_kernel(c->cost);
-    else if (small_kind == 1 || small_kind == 3) kw = datafit ? get_datafit_subwarp_kernel(c->cost) : get_subwarp_kernel(c->cost, lpr, vec);
+    else if (small_kind == 2)
+      ks = datafit ? get_datafit_small_kernel(c->cost) : (separable ? get_separable_small_kernel() : get_small_kernel(c->cost));
+    else if (small_kind == 1 || small_kind == 3)
+      kw = datafit ? get_datafit_subwarp_kernel(c->cost)
+                   : (separable ? get_separable_subwarp_kernel(lpr, vec) : get_subwarp_kernel(c->cost, lpr, vec));
   }
 
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
-  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 && !datafit &&
+  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 && !datafit && !separable &&
       !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
 
@@ -615,7 +625,8 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
 
 int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
-  if (cost < MB2_COST_ROSEN || cost > MB2_COST_LORENTZIAN) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (cost < MB2_COST_ROSEN || cost > MB2_COST_ACKLEY) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (cost >= MB2_COST_SPHERE) c->cp.sep_kind = cost - MB2_COST_SPHERE;
   if (cost == MB2_COST_LORENTZIAN && c->dim != 7) return fail(MB2_EINVAL, "lorentzian has 7 parameters (a1,a2,a3,A0,E0,G0,n)");
   if ((cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN) && c->dim > 32)
     return fail(MB2_EINVAL, "data-fit costs support at most 32 model parameters");

@@ -170,6 +170,7 @@ struct CostParams {
   // over the cheb_M evaluation points cheb_x[] (the DMMA variant reads cheb_vfrag as well)
   const double* fit_obs;  // [M] observations
   double fit_sigma;
+  int sep_kind;  // COST_SEPARABLE: which of the SEP_* functions
 };
 
 // c / s with r = RN(1/s): two Markstein refinement steps on top of c*r give the correctly
@@ -230,8 +231,39 @@ __device__ __forceinline__ double grw_factor(double c, double s, double r, bool 
 
 enum : int {
   COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4,
-  COST_POLYFIT = 6, COST_LORENTZIAN = 8  // numbered like mb2_cost (5 and 7 are the DMMA variants)
+  COST_POLYFIT = 6, COST_LORENTZIAN = 8,  // numbered like mb2_cost (5 and 7 are the DMMA variants)
+  COST_SEPARABLE = 9                      // mb2_cost 9..12: one kernel body, cp.sep_kind selects the function
 };
+
+// Separable test functions: two running sums over the coordinates and a closing formula.
+//   sphere     dejong.py:63-66     f = sum(c*c)
+//   rastrigin  pohlheim.py:132     10.*N + sum(c*c - 10.*cos(2*pi*c))
+//   schwefel   pohlheim.py:71      sum(-c * sin(sqrt(abs(c))))
+//   ackley     pohlheim.py:199-204 -20*exp(-0.2*sqrt(sum(c*c)/N)) + (-exp(sum(cos(2*pi*c))/N) + 20 + exp(1))
+// Terms follow the reference's operation order; sin/cos/exp are CUDA's (<= 2 ulp from glibc's).
+enum : int { SEP_SPHERE = 0, SEP_RASTRIGIN = 1, SEP_SCHWEFEL = 2, SEP_ACKLEY = 3 };
+__device__ __forceinline__ void sep_accumulate(int kind, double c, double& s1, double& s2) {
+  const double two_pi = 6.283185307179586;  // 2*pi in binary64
+  if (kind == SEP_SPHERE) {
+    s1 = dadd(s1, dmul(c, c));
+  } else if (kind == SEP_RASTRIGIN) {
+    s1 = dadd(s1, dsub(dmul(c, c), dmul(10.0, cos(dmul(two_pi, c)))));
+  } else if (kind == SEP_SCHWEFEL) {
+    s1 = dadd(s1, dmul(-c, sin(sqrt(fabs(c)))));
+  } else {
+    s1 = dadd(s1, dmul(c, c));
+    s2 = dadd(s2, cos(dmul(two_pi, c)));
+  }
+}
+__device__ __forceinline__ double sep_finish(int kind, double s1, double s2, int n) {
+  if (kind == SEP_RASTRIGIN) return dadd(dmul(10.0, (double)n), s1);
+  if (kind == SEP_ACKLEY) {
+    const double f0 = dmul(-20.0, exp(dmul(-0.2, sqrt(s1 / (double)n))));
+    const double f1 = dadd(dadd(-exp(s2 / (double)n), 20.0), 2.718281828459045);  // math.exp(1)
+    return dadd(f0, f1);
+  }
+  return s1;
+}
 
 // Horner exactly as mystic/math/poly.py:37-39: val = 0*x; for c in coeffs: val = c + val*x
 __device__ __forceinline__ double horner(const double* __restrict__ c, int n, double x) {
@@ -382,6 +414,24 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
     if (c2 > m) m = c2;
     if (c3 > m) m = c3;
     return m;
+  } else if (COST == COST_SEPARABLE) {
+    double sa[NA], sb[NA];
+#pragma unroll
+    for (int m = 0; m < NA; ++m) {
+      sa[m] = 0.0;
+      sb[m] = 0.0;
+    }
+    const int kind = cp.sep_kind;
+    for (int i0 = g.tig; i0 < D; i0 += 256) {
+#pragma unroll
+      for (int m = 0; m < NA; ++m) {
+        const int i = i0 + m * NT;
+        if (i < D) sep_accumulate(kind, xs[i], sa[m], sb[m]);
+      }
+    }
+    const double s1 = group_reduce<false, GW>(g, sa, 0);
+    const double s2 = (kind == SEP_ACKLEY) ? group_reduce<false, GW>(g, sb, 1) : 0.0;
+    return sep_finish(kind, s1, s2, D);
   } else if (COST == COST_POLYFIT || COST == COST_LORENTZIAN) {
     double acc[NA];
 #pragma unroll

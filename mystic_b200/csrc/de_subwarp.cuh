@@ -94,6 +94,12 @@ __device__ __forceinline__ double seg_cost(const double* xs, int D, int sub, con
     if (c2 > m) m = c2;
     if (c3 > m) m = c3;
     return m;
+  } else if (COST == COST_SEPARABLE) {
+    double s1 = 0.0, s2 = 0.0;
+    for (int i = sub; i < D; i += LPR) sep_accumulate(cp.sep_kind, xs[i], s1, s2);
+    s1 = seg_reduce<LPR, false>(s1);
+    s2 = seg_reduce<LPR, false>(s2);
+    return sep_finish(cp.sep_kind, s1, s2, D);
   } else if (COST == COST_POLYFIT || COST == COST_LORENTZIAN) {
     double acc = 0.0;
     const int M = cp.cheb_M;

@@ -24,7 +24,8 @@ enum { BASE_BEST1 = 0, BASE_RAND1 = 1, BASE_RANDTOBEST1 = 2, BASE_BEST2 = 3, BAS
 enum { XOVER_EXP = 0, XOVER_BIN = 1 };
 enum { BOUNDS_NONE = 0, BOUNDS_REJECT = 1, BOUNDS_CLAMP = 2 };
 enum { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4,
-       COST_POLYFIT = 6, COST_LORENTZIAN = 8 };
+       COST_POLYFIT = 6, COST_LORENTZIAN = 8, COST_SPHERE = 9, COST_RASTRIGIN = 10, COST_SCHWEFEL = 11,
+       COST_ACKLEY = 12 };
 
 typedef struct {
   int32_t dim;
@@ -204,6 +205,27 @@ static double cost_griewangk(const double* c, int D) {
   return s / 4000. - p + 1;
 }
 
+/* dejong.py:63-66, pohlheim.py:71,132,199-204 (plain left-to-right sums) */
+static double cost_separable(const double* c, int D, int cost) {
+  const double pi = 3.141592653589793;
+  double s1 = 0.0, s2 = 0.0;
+  for (int i = 0; i < D; ++i) {
+    switch (cost) {
+      case COST_SPHERE: s1 += c[i] * c[i]; break;
+      case COST_RASTRIGIN: s1 += c[i] * c[i] - 10. * cos(2 * pi * c[i]); break;
+      case COST_SCHWEFEL: s1 += -c[i] * sin(sqrt(fabs(c[i]))); break;
+      default: s1 += c[i] * c[i]; s2 += cos(2 * pi * c[i]); break;
+    }
+  }
+  if (cost == COST_RASTRIGIN) return 10. * D + s1;
+  if (cost == COST_ACKLEY) {
+    const double f0 = -20. * exp(-0.2 * sqrt(s1 / D));
+    const double f1 = -exp(s2 / D) + 20. + exp(1.0);
+    return f0 + f1;
+  }
+  return s1;
+}
+
 static double cost_zimmermann(const double* c) {
   /* storn.py:182-191 */
   double x0 = c[0], x1 = c[1];
@@ -280,6 +302,10 @@ static double energy_of(const double* x, const orc_config* cfg, double* scratch)
       case COST_ZIMMERMANN: raw = cost_zimmermann(x); break;
       case COST_POLYFIT:
       case COST_LORENTZIAN: raw = cost_datafit(x, D, cfg, scratch); break;
+      case COST_SPHERE:
+      case COST_RASTRIGIN:
+      case COST_SCHWEFEL:
+      case COST_ACKLEY: raw = cost_separable(x, D, cfg->cost); break;
       default: raw = cost_chebyshev(x, D, cfg); break;
     }
   }

@@ -59,6 +59,9 @@ def cost_rosen(x):
 
 _pow = np.frompyfunc(math.pow, 2, 1)
 _cos = np.frompyfunc(math.cos, 1, 1)
+_sin = np.frompyfunc(math.sin, 1, 1)
+_exp = np.frompyfunc(math.exp, 1, 1)
+_sqrt = np.frompyfunc(math.sqrt, 1, 1)
 
 
 def cost_corana(x):
@@ -169,6 +172,56 @@ def cost_chebyshev(x, order=8, M=61):
     return result
 
 
+def _f(a):
+    return np.asarray(a, dtype=np.float64)
+
+
+def cost_sphere(x):
+    """mystic/models/dejong.py:63-66: f = 0.; for c in coeffs: f += c*c"""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    f = np.zeros(x.shape[0])
+    for i in range(x.shape[1]):
+        f = f + x[:, i] * x[:, i]
+    return f
+
+
+def cost_rastrigin(x):
+    """mystic/models/pohlheim.py:132: 10.*len(coeffs) + sum(c*c - 10.*cos(2*pi*c) for c in coeffs)
+    (plain left-to-right sum, see cost_griewangk's note on CPython 3.12's compensated sum())"""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    s = np.zeros(x.shape[0])
+    for i in range(x.shape[1]):
+        c = x[:, i]
+        s = s + (c * c - 10. * _f(_cos(2 * math.pi * c)))
+    return 10. * x.shape[1] + s
+
+
+def cost_schwefel(x):
+    """mystic/models/pohlheim.py:71: sum(-c * sin(sqrt(abs(c))) for c in coeffs)"""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    s = np.zeros(x.shape[0])
+    for i in range(x.shape[1]):
+        c = x[:, i]
+        s = s + (-c) * _f(_sin(_f(_sqrt(np.abs(c)))))
+    return s
+
+
+def cost_ackley(x):
+    """mystic/models/pohlheim.py:199-204"""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    n = x.shape[1]
+    a, b, d = 20., 0.2, 2 * math.pi
+    s1 = np.zeros(x.shape[0])
+    s2 = np.zeros(x.shape[0])
+    for i in range(n):
+        c = x[:, i]
+        s1 = s1 + c * c
+        s2 = s2 + _f(_cos(d * c))
+    f0 = -a * _f(_exp(-b * _f(_sqrt(s1 / n))))
+    f1 = -_f(_exp(s2 / n)) + a + math.exp(1)
+    return f0 + f1
+
+
 def cost_polyfit(x, pts, obs, sigma=1.0):
     """mystic/forward_model.py:241-258 with the polynomial model of mystic/models/poly.py:36-54:
     F(params) = numpy.poly1d(params) whose evaluation is numpy.polyval's
@@ -224,6 +277,8 @@ def make_cost(name, extra_args=()):
         return cost_griewangk
     if name == 'zimmermann':
         return cost_zimmermann
+    if name in ('sphere', 'rastrigin', 'schwefel', 'ackley'):
+        return {'sphere': cost_sphere, 'rastrigin': cost_rastrigin, 'schwefel': cost_schwefel, 'ackley': cost_ackley}[name]
     if name.startswith('chebyshev') and name.endswith('cost'):
         order = int(name[len('chebyshev'):-len('cost')])
         M = int(extra_args[0]) if extra_args else 61

@@ -330,6 +330,17 @@ def cases():
                                             bounds=([-1000.] * 64, [1000.] * 64, True),
                                             penalty=[dict(ptype='quadratic_inequality', G=[1.] * 64, h=100., k=100, hpow=5)],
                                             maxgen=4)
+    # separable test functions of mystic.models
+    cs['sep_sphere_best1exp'] = dict(dim=12, NP=30, strategy='Best1Exp', cost='sphere', CR=0.9, F=0.8, seed=401,
+                                     init=('random', [-5.] * 12, [5.] * 12), maxgen=10)
+    cs['sep_rastrigin_rand1bin'] = dict(dim=10, NP=40, strategy='Rand1Bin', cost='rastrigin', CR=0.9, F=0.8, seed=402,
+                                        init=('random', [-5.12] * 10, [5.12] * 10),
+                                        bounds=([-5.12] * 10, [5.12] * 10, True), maxgen=10)
+    cs['sep_schwefel_randtobest'] = dict(dim=8, NP=32, strategy='RandToBest1Exp', cost='schwefel', CR=0.9, F=0.8, seed=403,
+                                         init=('random', [-500.] * 8, [500.] * 8),
+                                         bounds=([-500.] * 8, [500.] * 8, False), maxgen=10)
+    cs['sep_ackley_best2exp'] = dict(dim=16, NP=36, strategy='Best2Exp', cost='ackley', CR=0.9, F=0.6, seed=404,
+                                     init=('random', [-10.] * 16, [10.] * 16), maxgen=8)
     # data-fit residual costs: the reference's own CostFactory closures
     cs['fit_poly3_rand1exp'] = dict(dim=3, NP=20, strategy='Rand1Exp', cost='polyfit', CR=0.5, F=0.5, seed=301,
                                     init=('random', [-100.] * 3, [100.] * 3), bounds=([-100.] * 3, [100.] * 3, False),

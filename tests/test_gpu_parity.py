@@ -27,6 +27,13 @@ def energy_close(dev, ref, x=None, cost=None, what=''):
     if cost == 'griewangk' and x is not None:
         xx = np.atleast_2d(x)
         scale = np.maximum(scale, (xx * xx).sum(axis=1) / 4000. + 2.0)
+    elif cost in ('rastrigin', 'schwefel', 'ackley') and x is not None:
+        # sums of transcendental terms that cancel (CUDA's sin/cos/exp differ from glibc's by <= 2 ulp):
+        # the tolerance is relative to the magnitude of the terms, not of the (possibly small) total
+        xx = np.atleast_2d(x)
+        mag = {'rastrigin': (xx * xx).sum(axis=1) + 20.0 * xx.shape[1], 'schwefel': np.abs(xx).sum(axis=1),
+               'ackley': np.full(xx.shape[0], 45.0)}[cost]
+        scale = np.maximum(scale, mag)
     ok = both_inf | (np.abs(dev - ref) <= RTOL * scale)
     if not ok.all():
         i = int(np.argmax(~ok))
@@ -171,6 +178,11 @@ PHILOX_CASES = [
       dict(ptype='linear_equality', G=[0.5] * 48, h=3., k=10, hpow=2)], 0.9, 0.8, 6),
     (16, 19, 'Rand1Exp', 'rosen', (), (-2., 2., orc.BOUNDS_CLAMP), None, 0.0, 0.8, 3),
     (128, 64, 'Best1Bin', 'corana', (), (-1000., 1000., orc.BOUNDS_CLAMP), None, 0.3, 0.9, 4),
+    # separable test functions (one kernel body, function picked at run time)
+    (24, 40, 'Best1Bin', 'rastrigin', (), (-5.12, 5.12, orc.BOUNDS_CLAMP), None, 0.9, 0.8, 6),
+    (200, 36, 'Best1Bin', 'ackley', (), (-30., 30., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 4),
+    (10, 33, 'Rand2Exp', 'schwefel', (), (-500., 500., orc.BOUNDS_REJECT), None, 0.9, 0.8, 6),
+    (300, 30, 'Best2Exp', 'sphere', (), None, None, 0.95, 0.8, 4),
     # data-fit residual costs: extra = (evaluation points, observations)
     (5, 40, 'Best1Exp', 'polyfit', (np.linspace(-2., 2., 77), np.cos(np.linspace(-2., 2., 77))), (-3., 3., orc.BOUNDS_CLAMP),
      None, 0.9, 0.8, 6),
@@ -274,6 +286,10 @@ def test_costs_random_batches_match_oracle(kernel_path):
                                     ('corana', (1, 2, 3, 4, 9, 16, 64, 128), 1000., ()),
                                     ('griewangk', (1, 5, 10, 20, 63, 64, 128, 256), 400., ()),
                                     ('zimmermann', (2,), 8., ()),
+                                    ('sphere', (1, 7, 64, 300), 5., ()),
+                                    ('rastrigin', (2, 10, 64, 257), 5.12, ()),
+                                    ('schwefel', (3, 20, 128), 500., ()),
+                                    ('ackley', (2, 16, 100, 1024), 30., ()),
                                     ('chebyshev8cost', (9,), 100., (61,)),
                                     ('chebyshev8cost', (9,), 3., (4096,)),
                                     ('chebyshev16cost', (17,), 2., (333,))):

@@ -76,7 +76,7 @@ def test_solve_replay_matches_reference(name):
     s.SetPopulation(z['pop0'])
     s.SetReplayDraws(replay_draws(z))
     solve(s, meta, z)
-    check_against_reference(s, meta, z, exact_energy=(meta['cost'] != 'griewangk'))
+    check_against_reference(s, meta, z, exact_energy=(meta['cost'] not in G.COMPENSATED_SUM_COSTS))
 
 
 @pytest.mark.parametrize('name', G.names())
@@ -95,7 +95,7 @@ def test_solve_reference_rng_reproduces_seeded_reference_run(name):
     G.assert_bits_equal(s.population, z['pop0'], 'initial population')
     G.restore_mt_state(z)
     solve(s, meta, z)
-    check_against_reference(s, meta, z, exact_energy=(meta['cost'] != 'griewangk'))
+    check_against_reference(s, meta, z, exact_energy=(meta['cost'] not in G.COMPENSATED_SUM_COSTS))
 
 
 def test_baseline_config1_golden_values():

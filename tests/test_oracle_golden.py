@@ -26,7 +26,7 @@ def test_oracle_reproduces_reference(name):
             orc.step(st, meta['strategy'], meta['CR_eff'], meta['F_eff'], cost, pen, replay=replay)
         G.assert_bits_equal(st.trialSolution, z['trial'][g], '%s gen %d trial' % (name, g))
         G.assert_bits_equal(st.population, z['pop'][g], '%s gen %d pop' % (name, g))
-        if meta['cost'] == 'griewangk':
+        if meta['cost'] in G.COMPENSATED_SUM_COSTS:
             # builtin sum() of the recording interpreter (3.12) is compensated for runs of
             # exact floats; see oracle/de_oracle.py:cost_griewangk
             for a, b in ((st.trialEnergy, z['trialE'][g]), (st.popEnergy, z['popE'][g]),
