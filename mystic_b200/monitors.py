@@ -123,22 +123,127 @@ class Monitor(object):
         return self[i]
 
 
+def _is_seq(v):
+    return isinstance(v, (list, tuple)) or type(v).__name__ == 'ndarray'
+
+
+def _unscaled(self, k_applied):
+    """the last y as it is reported: the stored value has the monitor's k applied (monitors.py:355-357)"""
+    y = self._y[-1]
+    if k_applied or self.k is None:
+        return y
+    return [v / self.k for v in y] if isinstance(y, list) else y / self.k
+
+
+def _interval(v):
+    return float('inf') if (not v or v != v) else v
+
+
+def _screen_report(self, x, y, id, best, k, yint, xint):
+    """the lines VerboseMonitor / VerboseLoggingMonitor print (monitors.py:391-420, 534-563)"""
+    step = len(self) - 1
+    tag = '' if id is None else '[id: %s] ' % (id,)
+    if yint != float('inf') and int(step % yint) == 0:
+        v = _unscaled(self, k)
+        who = ''
+        if _is_seq(y) and not self._all:
+            who, v = ' best', v[best]
+        print('%sGeneration %s has%s %s: %s' % (tag, step, who, self.label, v))
+    if xint != float('inf') and int(step % xint) == 0:
+        if not _is_seq(x):
+            who, text = '', ' %s' % (self._x[-1],)
+        elif self._all:
+            who, text = '', '\n %s' % (self._x[-1],)
+        else:
+            who, text = ' best', '\n %s' % (self._x[-1][best],)
+        print('%sGeneration %s has%s fit parameters:%s' % (tag, step, who, text))
+    sys.stdout.flush()
+
+
 class VerboseMonitor(Monitor):
     """prints y every `interval` calls, x every `xinterval` (monitors.py:373-428)"""
 
     def __init__(self, interval=10, xinterval=float('inf'), all=True, **kwds):
         super(VerboseMonitor, self).__init__(**kwds)
-        self._yinterval = interval
-        self._xinterval = xinterval
+        self._yinterval = _interval(interval)
+        self._xinterval = _interval(xinterval)
         self._all = all
 
-    def __call__(self, x, y, id=None, **kwds):
-        super(VerboseMonitor, self).__call__(x, y, id, **kwds)
-        step = len(self) - 1
-        who = '' if id is None else ' id(%s)' % id
-        if self._yinterval is not float('inf') and int(step % self._yinterval) == 0:
-            print('Generation %d has %s: %s%s' % (step, self.label, self._y[-1], who))
-            sys.stdout.flush()
-        if self._xinterval != float('inf') and int(step % self._xinterval) == 0:
-            print('Generation %d has fit parameters:\n %s%s' % (step, self._x[-1], who))
-            sys.stdout.flush()
+    def info(self, message):
+        super(VerboseMonitor, self).info(message)
+        print('%s' % message)
+
+    def __call__(self, x, y, id=None, best=0, k=False, **kwds):
+        super(VerboseMonitor, self).__call__(x, y, id)
+        _screen_report(self, x, y, id, best, k, self._yinterval, self._xinterval)
+
+
+class LoggingMonitor(Monitor):
+    """writes `  (step[, id])     y   x` lines to a file every `interval` calls, with the reference's
+    header and layout (monitors.py:431-514), so log readers written for mystic keep working"""
+
+    def __init__(self, interval=1, filename='log.txt', new=False, all=True, info=None, **kwds):
+        import datetime
+        import os
+        super(LoggingMonitor, self).__init__(**kwds)
+        self._filename = filename
+        self._yinterval = self._xinterval = _interval(interval)
+        head = new or not os.path.exists(filename) or 'label' in kwds
+        with open(filename, 'w' if new else 'a') as f:
+            if info or head:
+                f.write('# %s\n' % datetime.datetime.now().ctime())
+                if info:
+                    f.write('# %s\n' % (info,))
+                if head:
+                    f.write('# ___#___  __%s__  __params__\n' % self.label)
+        self._all = all
+
+    def info(self, message):
+        super(LoggingMonitor, self).info(message)
+        with open(self._filename, 'a') as f:
+            f.write('# %s\n' % (message,))
+
+    def __call__(self, x, y, id=None, best=0, k=False, **kwds):
+        super(LoggingMonitor, self).__call__(x, y, id)
+        if self._yinterval == float('inf') or int((len(self) - 1) % self._yinterval) != 0:
+            return
+        v = _unscaled(self, k)
+        if _is_seq(y) and not self._all:
+            v = v[best]
+        xs = self._x[-1]
+        if _is_seq(x) and not self._all:
+            xs = xs[best]
+        text = '%s' % (xs,) if _is_seq(xs) else '[%s]' % (xs,)
+        step = (len(self) - 1,) if id is None else (len(self) - 1, id)
+        with open(self._filename, 'a') as f:
+            f.write('  %s     %s   %s\n' % (step, v, text))
+
+    def __reduce__(self):
+        state = dict(_x=self._x, _y=self._y, _id=self._id, _info=self._info, k=self.k, label=self.label)
+        return (self.__class__, (self._yinterval, self._filename, False, self._all, None), state)
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+
+
+class VerboseLoggingMonitor(LoggingMonitor):
+    """LoggingMonitor that also prints like VerboseMonitor (monitors.py:516-585)"""
+
+    def __init__(self, interval=1, yinterval=10, xinterval=float('inf'), filename='log.txt', new=False, all=True,
+                 info=None, **kwds):
+        super(VerboseLoggingMonitor, self).__init__(interval, filename, new, all, info, **kwds)
+        self._vyinterval = _interval(yinterval)
+        self._vxinterval = _interval(xinterval)
+
+    def info(self, message):
+        super(VerboseLoggingMonitor, self).info(message)
+        print('%s' % message)
+
+    def __call__(self, x, y, id=None, best=0, k=False, **kwds):
+        super(VerboseLoggingMonitor, self).__call__(x, y, id, best, k)
+        _screen_report(self, x, y, id, best, k, self._vyinterval, self._vxinterval)
+
+    def __reduce__(self):
+        state = dict(_x=self._x, _y=self._y, _id=self._id, _info=self._info, k=self.k, label=self.label)
+        return (self.__class__, (self._yinterval, self._vyinterval, self._vxinterval, self._filename, False, self._all, None),
+                state)

@@ -243,3 +243,36 @@ def test_batched_solve_stops_exactly_like_step_by_step(term):
         G.assert_bits_equal(s.population, a.population, 'population')
         assert s._stepmon._info == a._stepmon._info
         assert [list(x) for x in s.solution_history] == [list(x) for x in a.solution_history]
+
+
+def test_logging_monitors_write_the_reference_layout(tmp_path, capsys):
+    """LoggingMonitor / VerboseLoggingMonitor / VerboseMonitor: header, line layout and screen text of
+    mystic/monitors.py:373-585 (checked against literal expectations here, against the reference's
+    own classes in tests/test_reference_objects.py)"""
+    import pickle
+    from mystic_b200.monitors import LoggingMonitor, VerboseLoggingMonitor, VerboseMonitor
+    log = tmp_path / 'log.txt'
+    m = LoggingMonitor(2, str(log), new=True, info='run A')
+    for i in range(5):
+        m([1.0 * i, 2.0], 0.5 * i, id=(7 if i == 4 else None))
+    m.info('done')
+    lines = log.read_text().splitlines()
+    assert lines[0].startswith('# ') and lines[1] == '# run A' and lines[2] == '# ___#___  __ChiSquare__  __params__'
+    assert lines[3:] == ['  (0,)     0.0   [0.0, 2.0]', '  (2,)     1.0   [2.0, 2.0]', '  (4, 7)     2.0   [4.0, 2.0]', '# done']
+    assert len(m) == 5 and m.y == [0.0, 0.5, 1.0, 1.5, 2.0]
+    m2 = pickle.loads(pickle.dumps(m))                    # restart files carry the monitor
+    assert m2.y == m.y and m2._filename == str(log)
+    capsys.readouterr()
+    v = VerboseMonitor(2, 4)
+    for i in range(5):
+        v([1.0 * i], 0.25 * i, id=(3 if i == 2 else None))
+    out = capsys.readouterr().out.splitlines()
+    assert out == ['Generation 0 has ChiSquare: 0.0', 'Generation 0 has fit parameters:', ' [0.0]',
+                   '[id: 3] Generation 2 has ChiSquare: 0.5', 'Generation 4 has ChiSquare: 1.0',
+                   'Generation 4 has fit parameters:', ' [4.0]']
+    vl = VerboseLoggingMonitor(1, 2, filename=str(tmp_path / 'v.txt'), new=True, label='cost')
+    for i in range(3):
+        vl([0.5], 1.0 + i)
+    assert capsys.readouterr().out.splitlines() == ['Generation 0 has cost: 1.0', 'Generation 2 has cost: 3.0']
+    assert (tmp_path / 'v.txt').read_text().splitlines()[1:] == ['# ___#___  __cost__  __params__', '  (0,)     1.0   [0.5]',
+                                                                '  (1,)     2.0   [0.5]', '  (2,)     3.0   [0.5]']

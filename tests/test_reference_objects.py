@@ -128,3 +128,25 @@ def test_reference_costfactory_closures_are_recognised():
     assert s.generations == meta['generations'] and s.evaluations == meta['evaluations']
     G.assert_bits_equal(np.array(s.bestSolution), z['bestX'][-1], 'bestSolution')
     G.assert_bits_equal(np.array(s.energy_history), z['energy_history'], 'energy_history')
+
+
+def test_monitor_twins_print_and_log_like_the_reference(tmp_path, capsys):
+    """mystic_b200.monitors.{VerboseMonitor, LoggingMonitor, VerboseLoggingMonitor} against the
+    reference's classes on the same call sequence: same screen text, same log file (but its date line)"""
+    from mystic_b200 import monitors as ours
+    calls = [([0.5 * i, -1.0], 2.0 - 0.25 * i, (9 if i == 3 else None)) for i in range(7)]
+
+    def drive(mod, tag):
+        capsys.readouterr()
+        v = mod.VerboseMonitor(3, 2)
+        lg = mod.LoggingMonitor(2, str(tmp_path / (tag + '_l.txt')), new=True, info='hello')
+        vl = mod.VerboseLoggingMonitor(1, 3, 6, str(tmp_path / (tag + '_v.txt')), new=True, label='energy')
+        for x, y, i in calls:
+            for m in (v, lg, vl):
+                m(x, y, id=i)
+        lg.info('bye')
+        screen = capsys.readouterr().out
+        files = [(tmp_path / (tag + s)).read_text().splitlines()[1:] for s in ('_l.txt', '_v.txt')]
+        return screen, files, (v.y, lg.y, vl.x)
+
+    assert drive(ours, 'ours') == drive(mystic.monitors, 'ref')
