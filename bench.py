@@ -152,6 +152,36 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Run this process on the CPUs of the NUMA node the GPU hangs off, so the pinned host buffers of
+    the end-to-end leg are first touched (and DMA-read) locally: with 8 ranks uploading at once a
+    remote node halves the aggregate H2D rate.  Returns the node, or None when it cannot be found."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        if all(hasattr(pr, a) for a in ('pci_domain_id', 'pci_bus_id', 'pci_device_id')):
+            bdf = '%04x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        else:
+            out = subprocess.run(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i', str(device_index)],
+                                 stdout=subprocess.PIPE, universal_newlines=True, timeout=20).stdout.strip()
+            dom, rest = out.split(':', 1)
+            bdf = (dom[-4:] + ':' + rest).lower()
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(REPO, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -348,7 +378,8 @@ def main():
 
     # ---- end to end: host population (pinned) -> H2D -> generation 0 -> K x Step() with the result
     #      of every step read back to the host
-    host_pop = torch.empty((NP_local, D), dtype=torch.float64).pin_memory()
+    numa_node = bind_to_gpu_numa_node(local_rank)
+    host_pop = torch.empty((NP_local, D), dtype=torch.float64, pin_memory=True)
     rng = np.random.default_rng(seed + rank)
     hp = host_pop.numpy()
     chunk = max(1, (1 << 24) // D)
@@ -423,6 +454,7 @@ def main():
                    % (NP_local * D * 8 / 2 ** 20), 'grid': grid, 'block': block, 'smem_bytes': smem,
                    'inf_fraction': inf_frac, 'accept_fraction': acc_frac,
                    'sustain_s_before_timing': args.sustain, 'burst_ms_per_step': burst_ms / steps,
+                   'e2e_host_numa_node': numa_node,
                    'parallelism': ('candidate-sharded x%d, ' % world) + ('best exchange by peer-memory stores (NVLink) fused into the argmin epilogue'
                                                                           if args.exchange == 'peer' else 'NCCL all-gather of the bests per generation') if distributed
                    else 'single GPU'},

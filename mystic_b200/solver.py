@@ -859,8 +859,10 @@ class DifferentialEvolutionSolver2(object):
     def _batch_descriptor(self, settings):
         if not self._batch_generations or not len(self._stepmon) or not self._live:
             return None                       # generation 0 and (re)decoration go through Step()
-        if self._rng != 'philox' or self._distributed or self._saveiter or self._EARLYEXIT:
+        if self._rng != 'philox' or self._saveiter or self._EARLYEXIT:
             return None
+        if self._distributed and self._world > 1 and not getattr(self._engine, 'peer_exchange', False):
+            return None                       # the all-gather exchange is a host call per generation
         if settings.get('callback') is not None or settings.get('disp'):
             return None
         if not hasattr(self._engine, 'run'):

@@ -89,6 +89,22 @@ def main():
         print('rank %d %s/%s D=%d NP=%d: population %s, bestSolution %s, energy history %s, evaluations %d'
               % (rank, strategy, cost, D, NP, same_pop, same_best, e_ok, s.evaluations), flush=True)
         ok = ok and same_pop and same_best and e_ok
+    # Solve(): with the peer exchange inside the epilogue kernel, sharded runs take the device-resident
+    # multi-generation loop too (termination test on the merged best, the same on every rank); it must
+    # stop at the same generation, with the same history, as stepping generation by generation
+    runs = []
+    for batch in (64, 0):
+        D, NP = 12, 500
+        s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=0xBA7C4, distributed=True, strategy='Best1Exp')
+        s._batch_generations = batch
+        s.SetRandomInitialPoints([-3.] * D, [3.] * D)
+        s.SetStrictRanges([-3.] * D, [3.] * D, tight=True)
+        s.SetEvaluationLimits(generations=400)
+        s.Solve(models.rosen, termination.ChangeOverGeneration(1e-2, 7))
+        runs.append((s.generations, s.evaluations, list(s.energy_history), list(s.bestSolution), str(s.Terminated(info=True))))
+    same = runs[0] == runs[1] and 7 < runs[0][0] < 400
+    print('rank %d batched Solve == stepwise Solve: %s (%d generations, %s)' % (rank, same, runs[0][0], runs[0][4]), flush=True)
+    ok = ok and same
     t = torch.tensor([1 if ok else 0], device='cpu' if one_gpu else 'cuda')
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     dist.destroy_process_group()

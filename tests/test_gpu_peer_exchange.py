@@ -21,3 +21,4 @@ def test_peer_exchange_between_two_processes_on_one_gpu():
                           timeout=240)
     assert proc.returncode == 0, proc.stdout[-3000:]
     assert 'multi-gpu parity ok (world 2)' in proc.stdout, proc.stdout[-3000:]
+    assert proc.stdout.count('batched Solve == stepwise Solve: True') == 2, proc.stdout[-3000:]
