@@ -1,3 +1,8 @@
+#!/bin/bash
+# One-GPU evidence run (under gpurun): default bench line + reference arm, the ncu launch list of the
+# bench command, `ncu --set full` captures of the top kernels, the other workloads, smoke().
+# Everything lands in gpurun_out/; tools/summarize_ncu.py and tools/ncu_lines.py turn the reports
+# into the summaries tracked under profiles/.
 set -x
 python bench.py > gpurun_out/r1_bench_default.json 2> gpurun_out/r1_bench_default.err
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r1_bench_reference.json 2> gpurun_out/r1_bench_reference.err
@@ -9,6 +14,6 @@ done
 for w in c3; do
   ncu --set full --clock-control none --import-source on -k regex:de_step_cheb_mma --launch-skip 3 -c 1 -f -o gpurun_out/prof_${w}_r1b python bench.py --workload $w --no-cpu-baseline --steps 2 --warmup 3 > gpurun_out/ncu_${w}_r1b.log 2>&1
 done
-for w in c3 c4 c5; do python bench.py --workload $w --no-cpu-baseline > gpurun_out/r1_bench_${w}.json 2> gpurun_out/r1_bench_${w}.err; done
+for w in c3 c4 c5 f2; do python bench.py --workload $w --no-cpu-baseline > gpurun_out/r1_bench_${w}.json 2> gpurun_out/r1_bench_${w}.err; done
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_r1b.log 2>&1; tail -2 gpurun_out/smoke_r1b.log
 tail -c 600 gpurun_out/r1_bench_default.json; tail -c 400 gpurun_out/r1_bench_reference.json

@@ -1,3 +1,6 @@
+#!/bin/bash
+# Multi-GPU evidence run (under `gpurun --gpus N`): parity of every shard with the oracle's emulation
+# (tests/dist_gpu_check.py) and the weak-scaling bench lines for C2 and C5.   usage: run_multigpu.sh N
 N=${1:-8}
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
 echo "== dist check exchange=peer"; timeout 200 $TR tests/dist_gpu_check.py 2>&1 | grep -v "^W1\|^\*\*\*\|OMP_NUM" | tail -4 | tee gpurun_out/dist_check_${N}_peer.log
