@@ -970,3 +970,68 @@ def LoadSolver(filename=None, **kwds):
         solver = _pickler().load(f)
     solver.__dict__.update(kwds)
     return solver
+
+
+def diffev2(cost, x0, npop=4, args=(), bounds=None, ftol=5e-3, gtol=None, maxiter=None, maxfun=None, cross=0.9,
+            scale=0.8, full_output=0, disp=1, retall=0, callback=None, **kwds):
+    """The one-call interface of mystic.differential_evolution.diffev2 (differential_evolution.py:721-933,
+    scipy.optimize.fmin style) on the B200 engine.  Same keywords (handler, id, strategy, itermon,
+    evalmon, constraints, penalty, tightrange, cliprange) and the same return value
+    `xopt | (xopt, fopt, iter, funcalls, warnflag[, allvecs])`; `map` is accepted and ignored (the
+    whole population is evaluated by one kernel).  Engine options pass through: rng, seed, device,
+    distributed, tensor_cores, engine.
+
+    Like the reference it draws the initial population from `bounds` when bounds are given and from
+    around `x0` otherwise, and hands `cross` / `scale` to Solve() (where the reference's own quirk
+    lets the constructor defaults win, differential_evolution.py:676-692)."""
+    import numpy as _np
+    strategy = kwds['strategy'] if 'strategy' in kwds else _strategy.Best1Bin
+    stepmon = kwds['itermon'] if 'itermon' in kwds else _monitors.Monitor()
+    evalmon = kwds['evalmon'] if 'evalmon' in kwds else _monitors.Monitor()
+    if gtol:   # a number of generations: ChangeOverGeneration, else the default VTRChangeOverGeneration
+        termination = _termination.ChangeOverGeneration(ftol, gtol)
+    else:
+        termination = _termination.VTRChangeOverGeneration(ftol)
+    engine_opts = dict((k, kwds[k]) for k in ('rng', 'seed', 'device', 'distributed', 'tensor_cores', 'engine', 'keep_trials')
+                       if k in kwds)
+    solver = DifferentialEvolutionSolver2(len(x0), npop, **engine_opts)
+    solver.SetEvaluationLimits(maxiter, maxfun)
+    solver.SetEvaluationMonitor(evalmon)
+    solver.SetGenerationMonitor(stepmon)
+    if 'id' in kwds:
+        solver.id = int(kwds['id'])
+    if 'penalty' in kwds:
+        solver.SetPenalty(kwds['penalty'])
+    if 'constraints' in kwds:
+        solver.SetConstraints(kwds['constraints'])
+    if bounds is not None:
+        minb, maxb = [list(v) for v in _np.asarray(bounds, dtype=float).T]
+        solver.SetStrictRanges(minb, maxb, tight=kwds.get('tightrange'), clip=kwds.get('cliprange'))
+        solver.SetRandomInitialPoints(minb, maxb)
+    else:
+        solver.SetInitialPoints(x0)
+    if kwds.get('handler'):
+        solver.enable_signal_handler()
+    solver.Solve(cost, termination=termination, strategy=strategy, CrossProbability=cross, ScalingFactor=scale,
+                 ExtraArgs=args, callback=callback)
+    x = solver.bestSolution
+    fval = solver.bestEnergy
+    warnflag = 0
+    fcalls, iterations = solver.evaluations, solver.generations
+    if fcalls >= solver._maxfun:
+        warnflag = 1
+        if disp:
+            print('Warning: Maximum number of function evaluations has been exceeded.')
+    elif iterations >= solver._maxiter:
+        warnflag = 2
+        if disp:
+            print('Warning: Maximum number of iterations has been exceeded')
+    elif disp:
+        print('Optimization terminated successfully.')
+        print('         Current function value: %s' % fval)
+        print('         Iterations: %d' % iterations)
+        print('         Function evaluations: %d' % fcalls)
+    if full_output:
+        out = (x, fval, iterations, fcalls, warnflag)
+        return out + (stepmon.x,) if retall else out
+    return (x, stepmon.x) if retall else x

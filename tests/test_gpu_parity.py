@@ -605,3 +605,16 @@ def test_batched_solve_on_device_stops_exactly_like_step_by_step(term, shape):
         assert np.array_equal(s.population, a.population)
         assert np.array_equal(s.popEnergy, a.popEnergy)
         assert [list(x) for x in s.solution_history] == [list(x) for x in a.solution_history]
+
+
+def test_diffev2_one_call_interface_on_device():
+    """mystic_b200.diffev2 (differential_evolution.py:721-933 interface) on the GPU: converges on the
+    3-D Rosenbrock problem, is deterministic for a seed, and honours maxiter with warnflag 2"""
+    from mystic_b200 import diffev2, models
+    bounds = [(-3., 3.)] * 3
+    a = diffev2(models.rosen, [0.] * 3, npop=60, bounds=bounds, ftol=1e-8, gtol=30, seed=11, full_output=1, disp=0)
+    b = diffev2(models.rosen, [0.] * 3, npop=60, bounds=bounds, ftol=1e-8, gtol=30, seed=11, full_output=1, disp=0)
+    assert list(a[0]) == list(b[0]) and a[1:] == b[1:]
+    assert a[1] < 1e-6 and np.allclose(a[0], 1.0, atol=1e-2) and a[4] == 0
+    c = diffev2(models.rosen, [0.] * 3, npop=60, bounds=bounds, ftol=1e-30, maxiter=9, seed=11, full_output=1, retall=1, disp=0)
+    assert c[2] == 9 and c[4] == 2 and len(c[5]) == 10

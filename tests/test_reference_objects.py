@@ -150,3 +150,31 @@ def test_monitor_twins_print_and_log_like_the_reference(tmp_path, capsys):
         return screen, files, (v.y, lg.y, vl.x)
 
     assert drive(ours, 'ours') == drive(mystic.monitors, 'ref')
+
+
+def test_diffev2_one_call_interface_matches_the_reference(capsys):
+    """mystic_b200.diffev2 against mystic.differential_evolution.diffev2 under the same seed
+    (rng='reference', generation step by the test-only OracleEngine): same xopt, fopt, iterations,
+    function calls, warnflag, allvecs and the same convergence messages"""
+    import mystic.differential_evolution as mde
+    from mystic_b200 import diffev2, models
+    bounds = [(-3., 3.)] * 3
+    for kw in (dict(ftol=1e-3), dict(ftol=1e-6, gtol=12), dict(ftol=1e-9, maxiter=7), dict(ftol=1e-9, maxfun=150)):
+        random.seed(77)
+        capsys.readouterr()
+        want = mde.diffev2(mystic.models.rosen, [0.] * 3, npop=20, bounds=bounds, full_output=1, retall=1, disp=1, **kw)
+        want_out = capsys.readouterr().out
+        random.seed(77)
+        got = diffev2(models.rosen, [0.] * 3, npop=20, bounds=bounds, full_output=1, retall=1, disp=1,
+                      rng='reference', engine=OracleEngine, **kw)
+        got_out = capsys.readouterr().out
+        assert list(got[0]) == list(want[0]) and got[1:5] == want[1:5], (kw, got[1:5], want[1:5])
+        assert [list(v) for v in got[5]] == [list(v) for v in want[5]]
+        assert got_out == want_out
+    # no bounds: the population starts around x0 (SetInitialPoints)
+    random.seed(5)
+    want = mde.diffev2(mystic.models.rosen, [0.8, 1.2, 0.7], npop=16, ftol=1e-2, full_output=1, disp=0)
+    random.seed(5)
+    got = diffev2(mystic.models.rosen, [0.8, 1.2, 0.7], npop=16, ftol=1e-2, full_output=1, disp=0, rng='reference',
+                  engine=OracleEngine)
+    assert list(got[0]) == list(want[0]) and got[1:] == want[1:]
