@@ -23,6 +23,9 @@
 
 namespace mb2 {
 
+#ifndef MB2_CHEB_MINBLOCKS
+#define MB2_CHEB_MINBLOCKS 2
+#endif
 constexpr int kChebMaxDim = 17;    // order <= 16
 constexpr int kChebBatch = 64;     // candidates per warp batch (8 row tiles x 8)
 constexpr int kChebWarps = 8;
@@ -38,16 +41,24 @@ __device__ __forceinline__ void dmma884_init(double& d0, double& d1, double a, d
                : "=d"(d0), "=d"(d1)
                : "d"(a), "d"(b), "d"(c0), "d"(c1));
 }
-// q = 1 - px: is px outside [-1, 1] (q < 0 or q > 2; false for NaN like the reference's
-// `px<-1 or px>1`)?  (Deciding this on the bit pattern instead, to keep the compares off the FP64
-// pipe the MMAs run on, was measured slower: 2.05 G instead of 1.59 G instructions per generation.)
-__device__ __forceinline__ bool outside_unit(double q) { return q < 0.0 || q > 2.0; }
+// q = 1 - px: is px outside [-1, 1], i.e. q < 0 or q > 2?  Decided on the bit pattern, because the
+// FP64 pipe the compares would run on is the one the MMAs need (ncu: 48 % of the stall samples were
+// math-pipe throttle with two DSETPs per point): as unsigned, the high word of a negative double
+// is >= 0x80000000 and that of a double above 2.0 is >= 0x40000000 (2.0 itself is 0x40000000:0).
+// Infinities count as outside, like in the reference; a NaN would too, which the reference's
+// `px<-1 or px>1` does not do -- rows whose coefficients are large enough for p(x) to overflow into
+// a NaN are therefore evaluated by the Horner fallback of phase 3 (kChebSafeCoeff).
+__device__ __forceinline__ bool outside_unit(double q) {
+  const unsigned hi = (unsigned)__double2hiint(q);
+  return hi > 0x40000000u || (hi == 0x40000000u && __double2loint(q) != 0);
+}
+constexpr double kChebSafeCoeff = 1e150;  // |coefficients| below this cannot overflow a degree <= 16 polynomial on |x| <= 1.2
 
 // RESID: the epilogue is the squared residual of a polynomial least-squares data fit
 // (MB2_COST_POLYFIT_MMA: sum(((p(x_i) - obs_i)/sigma)^2), forward_model.py:241-258 with
 // models/poly.py:36-54) instead of the Chebyshev threshold terms; no end-point terms then.
 template <int KS, bool RESID = false>  // k-steps of 4 coefficients: 1 (order <= 4), 2 (order <= 8), 4 (order <= 16)
-__global__ void __launch_bounds__(kChebWarps * 32)
+__global__ void __launch_bounds__(kChebWarps * 32, MB2_CHEB_MINBLOCKS)
     de_step_cheb_mma_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
   if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(16) double smem[];
@@ -75,6 +86,7 @@ __global__ void __launch_bounds__(kChebWarps * 32)
   for (int64_t b = gw; b < nbatch; b += nw) {
     const int64_t c0 = b * kChebBatch;
     unsigned oobmask = 0;  // bit h: this lane's candidate h is out of range
+    unsigned bigmask = 0;  // bit h: a coefficient so large (or not finite) that p(x) may overflow: Horner fallback
 
     // ---------------- phase 1: trial vectors, one thread per candidate (two per lane)
 #pragma unroll 1
@@ -167,6 +179,11 @@ __global__ void __launch_bounds__(kChebWarps * 32)
         }
       }
       if (oob) oobmask |= 1u << h;
+      if (!RESID) {
+        bool big = false;
+        for (int i = 0; i < D; ++i) big |= !(fabs(row[i]) < kChebSafeCoeff);
+        if (big) bigmask |= 1u << h;
+      }
     }
     __syncwarp();
 
@@ -264,6 +281,17 @@ __global__ void __launch_bounds__(kChebWarps * 32)
       double E = CUDART_INF;
       if (!(oobmask & (1u << h))) {
         E = s_sum[cl];
+        if (!RESID && (bigmask & (1u << h))) {
+          // the reference's own loop (_model_helper.py:18-25), NaN-safe comparisons
+          E = 0.0;
+          for (int i = 0; i < P.cost.cheb_M; ++i) {
+            const double px = horner(row, D, __ldg(P.cost.cheb_x + i));
+            if (px < -1.0 || px > 1.0) {
+              const double u = dsub(1.0, px);
+              E = dadd(E, dmul(u, u));
+            }
+          }
+        }
         if (!RESID) {
           // _model_helper.py:27-31: px = p_trial(+-1.2) - p_target(+-1.2); if px<0: result += px*px
           double vp = 0.0, vm = 0.0;
