@@ -618,3 +618,22 @@ def test_diffev2_one_call_interface_on_device():
     assert a[1] < 1e-6 and np.allclose(a[0], 1.0, atol=1e-2) and a[4] == 0
     c = diffev2(models.rosen, [0.] * 3, npop=60, bounds=bounds, ftol=1e-30, maxiter=9, seed=11, full_output=1, retall=1, disp=0)
     assert c[2] == 9 and c[4] == 2 and len(c[5]) == 10
+
+
+def test_chebyshev_dmma_huge_coefficients_take_the_horner_fallback():
+    """rows whose coefficients could overflow p(x) are evaluated by the reference's own loop inside the
+    DMMA kernel (NaN-safe comparisons): same inf / NaN pattern and values as the oracle"""
+    from mystic_b200 import models
+    rng = np.random.default_rng(3)
+    X = rng.uniform(-100., 100., size=(128, 9))
+    X[5, 2] = 1e200
+    X[17, 0] = -1e308
+    X[17, 1] = 1e308
+    X[40, 8] = 3e151
+    X[77, 4] = np.inf
+    got = models.chebyshev8cost(X, 257, tensor_cores=True)
+    with np.errstate(all='ignore'):
+        want = orc.make_cost('chebyshev8cost', (257,))(X)
+    assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
+    fin = np.isfinite(want)
+    assert fin.sum() >= 124 and np.allclose(got[fin], want[fin], rtol=1e-12, atol=0)
