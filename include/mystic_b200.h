@@ -68,7 +68,10 @@ enum mb2_cost {
   MB2_COST_SPHERE = 9,      /* models/dejong.py:54-66   */
   MB2_COST_RASTRIGIN = 10,  /* models/pohlheim.py:123-132 */
   MB2_COST_SCHWEFEL = 11,   /* models/pohlheim.py:60-71 */
-  MB2_COST_ACKLEY = 12      /* models/pohlheim.py:186-204 */
+  MB2_COST_ACKLEY = 12,     /* models/pohlheim.py:186-204 */
+  MB2_COST_STEP = 13,       /* models/dejong.py:166-192 */
+  MB2_COST_MICHAL = 14,     /* models/pohlheim.py:226-240 */
+  MB2_COST_POWERS = 15      /* models/pohlheim.py:153-163 */
 };
 
 /* SetStrictRanges modes (abstract_solver.py:334-448, tools.py:404-430) */

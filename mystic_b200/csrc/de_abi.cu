@@ -212,7 +212,7 @@ namespace {
 
 bool is_datafit(int cost) { return cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN; }
 
-bool is_separable(int cost) { return cost >= MB2_COST_SPHERE && cost <= MB2_COST_ACKLEY; }
+bool is_separable(int cost) { return cost >= MB2_COST_SPHERE && cost <= MB2_COST_POWERS; }
 
 StepKernel pick_kernel(const StrategyInfo& s, int cost, bool vec) {
   if (is_datafit(cost)) return get_datafit_ldg_kernel(s.base, s.xover, cost);
@@ -625,7 +625,7 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
 
 int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
-  if (cost < MB2_COST_ROSEN || cost > MB2_COST_ACKLEY) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (cost < MB2_COST_ROSEN || cost > MB2_COST_POWERS) return fail(MB2_EINVAL, "unknown cost id %d", cost);
   if (cost >= MB2_COST_SPHERE) c->cp.sep_kind = cost - MB2_COST_SPHERE;
   if (cost == MB2_COST_LORENTZIAN && c->dim != 7) return fail(MB2_EINVAL, "lorentzian has 7 parameters (a1,a2,a3,A0,E0,G0,n)");
   if ((cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN) && c->dim > 32)

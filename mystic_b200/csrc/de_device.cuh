@@ -241,10 +241,25 @@ enum : int {
 //   schwefel   pohlheim.py:71      sum(-c * sin(sqrt(abs(c))))
 //   ackley     pohlheim.py:199-204 -20*exp(-0.2*sqrt(sum(c*c)/N)) + (-exp(sum(cos(2*pi*c))/N) + 20 + exp(1))
 // Terms follow the reference's operation order; sin/cos/exp are CUDA's (<= 2 ulp from glibc's).
-enum : int { SEP_SPHERE = 0, SEP_RASTRIGIN = 1, SEP_SCHWEFEL = 2, SEP_ACKLEY = 3 };
-__device__ __forceinline__ void sep_accumulate(int kind, double c, double& s1, double& s2) {
+//   step       dejong.py:184-192   30. + sum(floor(c) | 30*(c - 5.12) | 30*(5.12 - c))
+//   michal     pohlheim.py:237-240 -sum(sin(c_i) * sin((i+1)*c_i**2/pi)**20)
+//   powers     pohlheim.py:162-163 sum(abs(c_i)**(i+2))
+enum : int { SEP_SPHERE = 0, SEP_RASTRIGIN = 1, SEP_SCHWEFEL = 2, SEP_ACKLEY = 3, SEP_STEP = 4, SEP_MICHAL = 5, SEP_POWERS = 6 };
+__device__ __forceinline__ void sep_accumulate(int kind, double c, int i, double& s1, double& s2) {
   const double two_pi = 6.283185307179586;  // 2*pi in binary64
-  if (kind == SEP_SPHERE) {
+  if (kind == SEP_STEP) {
+    double t;
+    if (fabs(c) <= 5.12) t = floor(c);
+    else if (c > 5.12) t = dmul(30.0, dsub(c, 5.12));
+    else t = dmul(30.0, dsub(5.12, c));  // also where a NaN lands, like the reference's else branch
+    s1 = dadd(s1, t);
+  } else if (kind == SEP_MICHAL) {
+    const double w = sin(__ddiv_rn(dmul((double)(i + 1), dmul(c, c)), 3.141592653589793));
+    const double w2 = dmul(w, w), w4 = dmul(w2, w2), w8 = dmul(w4, w4), w16 = dmul(w8, w8);
+    s1 = dadd(s1, dmul(sin(c), dmul(w16, w4)));  // w**20 by squaring: <= 3 ulp from pow()
+  } else if (kind == SEP_POWERS) {
+    s1 = dadd(s1, pow(fabs(c), (double)(i + 2)));
+  } else if (kind == SEP_SPHERE) {
     s1 = dadd(s1, dmul(c, c));
   } else if (kind == SEP_RASTRIGIN) {
     s1 = dadd(s1, dsub(dmul(c, c), dmul(10.0, cos(dmul(two_pi, c)))));
@@ -257,6 +272,8 @@ __device__ __forceinline__ void sep_accumulate(int kind, double c, double& s1, d
 }
 __device__ __forceinline__ double sep_finish(int kind, double s1, double s2, int n) {
   if (kind == SEP_RASTRIGIN) return dadd(dmul(10.0, (double)n), s1);
+  if (kind == SEP_STEP) return dadd(30.0, s1);
+  if (kind == SEP_MICHAL) return -s1;
   if (kind == SEP_ACKLEY) {
     const double f0 = dmul(-20.0, exp(dmul(-0.2, sqrt(s1 / (double)n))));
     const double f1 = dadd(dadd(-exp(s2 / (double)n), 20.0), 2.718281828459045);  // math.exp(1)
@@ -426,7 +443,7 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
 #pragma unroll
       for (int m = 0; m < NA; ++m) {
         const int i = i0 + m * NT;
-        if (i < D) sep_accumulate(kind, xs[i], sa[m], sb[m]);
+        if (i < D) sep_accumulate(kind, xs[i], i, sa[m], sb[m]);
       }
     }
     const double s1 = group_reduce<false, GW>(g, sa, 0);

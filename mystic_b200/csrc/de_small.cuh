@@ -111,7 +111,7 @@ __device__ __forceinline__ double thread_cost(const double* x, int D, const Cost
     return m;
   } else if (COST == COST_SEPARABLE) {
     double s1 = 0.0, s2 = 0.0;
-    for (int i = 0; i < D; ++i) sep_accumulate(cp.sep_kind, x[i], s1, s2);
+    for (int i = 0; i < D; ++i) sep_accumulate(cp.sep_kind, x[i], i, s1, s2);
     return sep_finish(cp.sep_kind, s1, s2, D);
   } else if (COST == COST_POLYFIT || COST == COST_LORENTZIAN) {
     double result = 0.0;

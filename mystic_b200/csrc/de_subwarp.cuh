@@ -96,7 +96,7 @@ __device__ __forceinline__ double seg_cost(const double* xs, int D, int sub, con
     return m;
   } else if (COST == COST_SEPARABLE) {
     double s1 = 0.0, s2 = 0.0;
-    for (int i = sub; i < D; i += LPR) sep_accumulate(cp.sep_kind, xs[i], s1, s2);
+    for (int i = sub; i < D; i += LPR) sep_accumulate(cp.sep_kind, xs[i], i, s1, s2);
     s1 = seg_reduce<LPR, false>(s1);
     s2 = seg_reduce<LPR, false>(s2);
     return sep_finish(cp.sep_kind, s1, s2, D);

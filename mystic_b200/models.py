@@ -4,8 +4,8 @@
     corana      mystic/models/storn.py:57-96
     griewangk   mystic/models/storn.py:120-139
     zimmermann  mystic/models/storn.py:161-191
-    sphere      mystic/models/dejong.py:54-66
-    rastrigin, schwefel, ackley   mystic/models/pohlheim.py:60-71, 123-132, 186-204
+    sphere, step   mystic/models/dejong.py:54-66, 166-192
+    rastrigin, schwefel, ackley, michal, powers   mystic/models/pohlheim.py:60-71, 123-132, 186-204, 226-240, 153-163
     chebyshev{2,4,6,8,16}cost   mystic/models/poly.py:124-149, mystic/models/_model_helper.py:10-33
     poly.CostFactory / poly.CostFactory2, lorentzian.CostFactory / lorentzian.CostFactory2
                 data-fit residual costs, mystic/models/abstract_model.py:146-161 ->
@@ -20,7 +20,7 @@ with TypeError: the engine has no CPU path.
 
 COST_ROSEN, COST_CORANA, COST_GRIEWANGK, COST_ZIMMERMANN, COST_CHEBYSHEV, COST_CHEBYSHEV_MMA = range(6)
 COST_POLYFIT, COST_POLYFIT_MMA, COST_LORENTZIAN = 6, 7, 8
-COST_SPHERE, COST_RASTRIGIN, COST_SCHWEFEL, COST_ACKLEY = 9, 10, 11, 12
+COST_SPHERE, COST_RASTRIGIN, COST_SCHWEFEL, COST_ACKLEY, COST_STEP, COST_MICHAL, COST_POWERS = 9, 10, 11, 12, 13, 14, 15
 
 CHEBYSHEV_TARGETS = {  # mystic/models/_model_helper.py:10-14
     2: [2., 0., -1.],
@@ -151,16 +151,20 @@ sphere = DeviceCost('sphere', COST_SPHERE, doc='De Jong sphere, sum(x_i^2)')
 rastrigin = DeviceCost('rastrigin', COST_RASTRIGIN, doc="Rastrigin's function, 10 N + sum(x_i^2 - 10 cos(2 pi x_i))")
 schwefel = DeviceCost('schwefel', COST_SCHWEFEL, doc="Schwefel's function, sum(-x_i sin(sqrt(|x_i|)))")
 ackley = DeviceCost('ackley', COST_ACKLEY, doc="Ackley's path function")
+step = DeviceCost('step', COST_STEP, doc="De Jong's step function")
+michal = DeviceCost('michal', COST_MICHAL, doc="Michalewicz's function")
+powers = DeviceCost('powers', COST_POWERS, doc="Pohlheim's sum of different powers")
 chebyshev2cost = DeviceCost('chebyshev2cost', COST_CHEBYSHEV, 2, 'order-2 Chebyshev fitting cost')
 chebyshev4cost = DeviceCost('chebyshev4cost', COST_CHEBYSHEV, 4, 'order-4 Chebyshev fitting cost')
 chebyshev6cost = DeviceCost('chebyshev6cost', COST_CHEBYSHEV, 6, 'order-6 Chebyshev fitting cost')
 chebyshev8cost = DeviceCost('chebyshev8cost', COST_CHEBYSHEV, 8, 'order-8 Chebyshev fitting cost')
 chebyshev16cost = DeviceCost('chebyshev16cost', COST_CHEBYSHEV, 16, 'order-16 Chebyshev fitting cost')
 
-_BY_NAME = dict((c.__name__, c) for c in (rosen, corana, griewangk, zimmermann, sphere, rastrigin, schwefel, ackley, chebyshev2cost, chebyshev4cost,
+_BY_NAME = dict((c.__name__, c) for c in (rosen, corana, griewangk, zimmermann, sphere, rastrigin, schwefel, ackley, step, michal, powers, chebyshev2cost, chebyshev4cost,
                                           chebyshev6cost, chebyshev8cost, chebyshev16cost))
 _BY_REFERENCE_CLASS = {'Rosenbrock': rosen, 'Corana': corana, 'Griewangk': griewangk, 'Zimmermann': zimmermann,
-                       'Sphere': sphere, 'Rastrigin': rastrigin, 'Schwefel': schwefel, 'Ackley': ackley}
+                       'Sphere': sphere, 'Rastrigin': rastrigin, 'Schwefel': schwefel, 'Ackley': ackley,
+                       'Step': step, 'Michalewicz': michal, 'DifferentPowers': powers}
 
 
 def _resolve_reference_costfactory(cost):
@@ -218,5 +222,5 @@ def resolve(cost):
     raise TypeError(
         "cost %r is not a device cost function: the B200 engine evaluates the cost inside the fused "
         "CUDA kernel and has no CPU path. Use mystic_b200.models.{rosen,corana,griewangk,zimmermann,"
-        "sphere,rastrigin,schwefel,ackley,chebyshevNcost,poly.CostFactory,lorentzian.CostFactory} or the "
+        "sphere,rastrigin,schwefel,ackley,step,michal,powers,chebyshevNcost,poly.CostFactory,lorentzian.CostFactory} or the "
         "corresponding mystic.models objects." % (cost,))

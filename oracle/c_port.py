@@ -56,7 +56,7 @@ def _d(a):
 class COracle(object):
     """Same state machine as oracle.de_oracle.DEState + step0/step, in C with OpenMP."""
 
-    COSTS = {'rosen': 0, 'corana': 1, 'griewangk': 2, 'zimmermann': 3, 'sphere': 9, 'rastrigin': 10, 'schwefel': 11, 'ackley': 12}
+    COSTS = {'rosen': 0, 'corana': 1, 'griewangk': 2, 'zimmermann': 3, 'sphere': 9, 'rastrigin': 10, 'schwefel': 11, 'ackley': 12, 'step': 13, 'michal': 14, 'powers': 15}
 
     def __init__(self, population, strategy, CR, F, cost, extra=(), lo=None, hi=None, bounds_mode=0, penalty=()):
         from oracle import de_oracle as orc

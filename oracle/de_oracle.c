@@ -25,7 +25,7 @@ enum { XOVER_EXP = 0, XOVER_BIN = 1 };
 enum { BOUNDS_NONE = 0, BOUNDS_REJECT = 1, BOUNDS_CLAMP = 2 };
 enum { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4,
        COST_POLYFIT = 6, COST_LORENTZIAN = 8, COST_SPHERE = 9, COST_RASTRIGIN = 10, COST_SCHWEFEL = 11,
-       COST_ACKLEY = 12 };
+       COST_ACKLEY = 12, COST_STEP = 13, COST_MICHAL = 14, COST_POWERS = 15 };
 
 typedef struct {
   int32_t dim;
@@ -208,16 +208,24 @@ static double cost_griewangk(const double* c, int D) {
 /* dejong.py:63-66, pohlheim.py:71,132,199-204 (plain left-to-right sums) */
 static double cost_separable(const double* c, int D, int cost) {
   const double pi = 3.141592653589793;
-  double s1 = 0.0, s2 = 0.0;
+  double s1 = (cost == COST_STEP) ? 30. : 0.0, s2 = 0.0;
   for (int i = 0; i < D; ++i) {
     switch (cost) {
       case COST_SPHERE: s1 += c[i] * c[i]; break;
       case COST_RASTRIGIN: s1 += c[i] * c[i] - 10. * cos(2 * pi * c[i]); break;
       case COST_SCHWEFEL: s1 += -c[i] * sin(sqrt(fabs(c[i]))); break;
+      case COST_STEP:
+        if (fabs(c[i]) <= 5.12) s1 += floor(c[i]);
+        else if (c[i] > 5.12) s1 += 30 * (c[i] - 5.12);
+        else s1 += 30 * (5.12 - c[i]);
+        break;
+      case COST_MICHAL: s1 += sin(c[i]) * pow(sin((i + 1) * pow(c[i], 2) / pi), 20); break;
+      case COST_POWERS: s1 += pow(fabs(c[i]), i + 2); break;
       default: s1 += c[i] * c[i]; s2 += cos(2 * pi * c[i]); break;
     }
   }
   if (cost == COST_RASTRIGIN) return 10. * D + s1;
+  if (cost == COST_MICHAL) return -s1;
   if (cost == COST_ACKLEY) {
     const double f0 = -20. * exp(-0.2 * sqrt(s1 / D));
     const double f1 = -exp(s2 / D) + 20. + exp(1.0);
@@ -305,7 +313,10 @@ static double energy_of(const double* x, const orc_config* cfg, double* scratch)
       case COST_SPHERE:
       case COST_RASTRIGIN:
       case COST_SCHWEFEL:
-      case COST_ACKLEY: raw = cost_separable(x, D, cfg->cost); break;
+      case COST_ACKLEY:
+      case COST_STEP:
+      case COST_MICHAL:
+      case COST_POWERS: raw = cost_separable(x, D, cfg->cost); break;
       default: raw = cost_chebyshev(x, D, cfg); break;
     }
   }

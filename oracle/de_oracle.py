@@ -222,6 +222,40 @@ def cost_ackley(x):
     return f0 + f1
 
 
+def cost_step(x):
+    """mystic/models/dejong.py:184-192"""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    f = np.full(x.shape[0], 30.)
+    for i in range(x.shape[1]):
+        c = x[:, i]
+        with np.errstate(invalid='ignore'):
+            t = np.where(np.abs(c) <= 5.12, np.floor(c), np.where(c > 5.12, 30 * (c - 5.12), 30 * (5.12 - c)))
+        f = f + t
+    return f
+
+
+def cost_michal(x):
+    """mystic/models/pohlheim.py:237-240 (plain left-to-right sum)"""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    s = np.zeros(x.shape[0])
+    _pow = np.frompyfunc(lambda a, b: a ** b, 2, 1)
+    for i in range(x.shape[1]):
+        c = x[:, i]
+        w = _f(_sin(_f((i + 1) * _f(_pow(c, 2)) / math.pi)))
+        s = s + _f(_sin(c)) * _f(_pow(w, 20))
+    return -s
+
+
+def cost_powers(x):
+    """mystic/models/pohlheim.py:162-163"""
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    s = np.zeros(x.shape[0])
+    _pow = np.frompyfunc(lambda a, b: a ** b, 2, 1)
+    for i in range(x.shape[1]):
+        s = s + _f(_pow(np.abs(x[:, i]).astype(object), i + 2))
+    return s
+
+
 def cost_polyfit(x, pts, obs, sigma=1.0):
     """mystic/forward_model.py:241-258 with the polynomial model of mystic/models/poly.py:36-54:
     F(params) = numpy.poly1d(params) whose evaluation is numpy.polyval's
@@ -277,8 +311,9 @@ def make_cost(name, extra_args=()):
         return cost_griewangk
     if name == 'zimmermann':
         return cost_zimmermann
-    if name in ('sphere', 'rastrigin', 'schwefel', 'ackley'):
-        return {'sphere': cost_sphere, 'rastrigin': cost_rastrigin, 'schwefel': cost_schwefel, 'ackley': cost_ackley}[name]
+    if name in ('sphere', 'rastrigin', 'schwefel', 'ackley', 'step', 'michal', 'powers'):
+        return {'sphere': cost_sphere, 'rastrigin': cost_rastrigin, 'schwefel': cost_schwefel, 'ackley': cost_ackley,
+                'step': cost_step, 'michal': cost_michal, 'powers': cost_powers}[name]
     if name.startswith('chebyshev') and name.endswith('cost'):
         order = int(name[len('chebyshev'):-len('cost')])
         M = int(extra_args[0]) if extra_args else 61

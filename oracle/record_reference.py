@@ -341,6 +341,12 @@ def cases():
                                          bounds=([-500.] * 8, [500.] * 8, False), maxgen=10)
     cs['sep_ackley_best2exp'] = dict(dim=16, NP=36, strategy='Best2Exp', cost='ackley', CR=0.9, F=0.6, seed=404,
                                      init=('random', [-10.] * 16, [10.] * 16), maxgen=8)
+    cs['sep_step_best1bin'] = dict(dim=9, NP=30, strategy='Best1Bin', cost='step', CR=0.9, F=0.8, seed=405,
+                                   init=('random', [-7.] * 9, [7.] * 9), maxgen=8)
+    cs['sep_michal_rand2exp'] = dict(dim=6, NP=30, strategy='Rand2Exp', cost='michal', CR=0.9, F=0.7, seed=406,
+                                     init=('random', [0.] * 6, [3.14] * 6), bounds=([0.] * 6, [3.14] * 6, True), maxgen=8)
+    cs['sep_powers_best1exp'] = dict(dim=7, NP=28, strategy='Best1Exp', cost='powers', CR=0.9, F=0.8, seed=407,
+                                     init=('random', [-1.5] * 7, [1.5] * 7), maxgen=8)
     # data-fit residual costs: the reference's own CostFactory closures
     cs['fit_poly3_rand1exp'] = dict(dim=3, NP=20, strategy='Rand1Exp', cost='polyfit', CR=0.5, F=0.5, seed=301,
                                     init=('random', [-100.] * 3, [100.] * 3), bounds=([-100.] * 3, [100.] * 3, False),

@@ -27,12 +27,12 @@ def energy_close(dev, ref, x=None, cost=None, what=''):
     if cost == 'griewangk' and x is not None:
         xx = np.atleast_2d(x)
         scale = np.maximum(scale, (xx * xx).sum(axis=1) / 4000. + 2.0)
-    elif cost in ('rastrigin', 'schwefel', 'ackley') and x is not None:
+    elif cost in ('rastrigin', 'schwefel', 'ackley', 'michal') and x is not None:
         # sums of transcendental terms that cancel (CUDA's sin/cos/exp differ from glibc's by <= 2 ulp):
         # the tolerance is relative to the magnitude of the terms, not of the (possibly small) total
         xx = np.atleast_2d(x)
         mag = {'rastrigin': (xx * xx).sum(axis=1) + 20.0 * xx.shape[1], 'schwefel': np.abs(xx).sum(axis=1),
-               'ackley': np.full(xx.shape[0], 45.0)}[cost]
+               'ackley': np.full(xx.shape[0], 45.0), 'michal': np.full(xx.shape[0], float(xx.shape[1]))}[cost]
         scale = np.maximum(scale, mag)
     ok = both_inf | (np.abs(dev - ref) <= RTOL * scale)
     if not ok.all():
@@ -183,6 +183,9 @@ PHILOX_CASES = [
     (200, 36, 'Best1Bin', 'ackley', (), (-30., 30., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 4),
     (10, 33, 'Rand2Exp', 'schwefel', (), (-500., 500., orc.BOUNDS_REJECT), None, 0.9, 0.8, 6),
     (300, 30, 'Best2Exp', 'sphere', (), None, None, 0.95, 0.8, 4),
+    (40, 36, 'Rand1Exp', 'step', (), (-7., 7., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5),
+    (12, 30, 'Best1Bin', 'michal', (), (0., 3.14, orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5),
+    (9, 28, 'RandToBest1Exp', 'powers', (), (-1.5, 1.5, orc.BOUNDS_REJECT), None, 0.9, 0.8, 5),
     # data-fit residual costs: extra = (evaluation points, observations)
     (5, 40, 'Best1Exp', 'polyfit', (np.linspace(-2., 2., 77), np.cos(np.linspace(-2., 2., 77))), (-3., 3., orc.BOUNDS_CLAMP),
      None, 0.9, 0.8, 6),
@@ -290,6 +293,9 @@ def test_costs_random_batches_match_oracle(kernel_path):
                                     ('rastrigin', (2, 10, 64, 257), 5.12, ()),
                                     ('schwefel', (3, 20, 128), 500., ()),
                                     ('ackley', (2, 16, 100, 1024), 30., ()),
+                                    ('step', (1, 9, 64, 200), 8., ()),
+                                    ('michal', (2, 10, 64), 3.14, ()),
+                                    ('powers', (1, 7, 20), 1.5, ()),
                                     ('chebyshev8cost', (9,), 100., (61,)),
                                     ('chebyshev8cost', (9,), 3., (4096,)),
                                     ('chebyshev16cost', (17,), 2., (333,))):
