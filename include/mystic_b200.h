@@ -230,6 +230,17 @@ int mb2_exchange_connected(mb2_ctx* ctx);
 int mb2_exchange_reset(mb2_ctx* ctx);
 int mb2_exchange_best(mb2_ctx* ctx, void* stream);
 
+/* Batch of independent solvers in one launch (the ensemble path: mystic/abstract_ensemble_solver.py
+ * launches N nested solvers through `map`; here N small DE2 populations advance together).
+ * The `np_local` rows of the context are n_islands populations of np_local / n_islands members laid
+ * side by side; every island draws its donors among its own members (its rows key the Philox
+ * counters), follows its own best member and reports its own result: island i behaves exactly like
+ * shard i of a sharded population without the best exchange.  Rows of at most 128 dimensions;
+ * mb2_eval_initial / mb2_step advance all islands, mb2_read_islands returns n_islands results and
+ * best members ([n_islands, dim], may be NULL).  Call before mb2_eval_initial. */
+int mb2_set_islands(mb2_ctx* ctx, int32_t n_islands);
+int mb2_read_islands(mb2_ctx* ctx, mb2_result* out, double* x_host, void* stream);
+
 /* synchronises `stream`, then returns the generation result and bestSolution (dim doubles;
  * x_host may be NULL) */
 int mb2_read_result(mb2_ctx* ctx, mb2_result* out, double* x_host, void* stream);

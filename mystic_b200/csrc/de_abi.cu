@@ -141,6 +141,13 @@ struct mb2_ctx {
   double* mailbox = nullptr;
   size_t mailbox_bytes = 0;
   void* peer_maps[kMaxWorld] = {};
+  // batch of independent solvers (mb2_set_islands): n_islands populations of np / n_islands rows
+  // side by side in the buffers, each with its own best member and DeviceState
+  int n_islands = 1;
+  DeviceState* st_isl = nullptr;
+  double* best_x_isl = nullptr;
+  DeviceState* h_st_isl = nullptr;  // pinned
+  double* h_best_isl = nullptr;     // pinned
   int xchg_connected = 0;
   int xchg_no_adopt = 0;  // after mb2_exchange_reset: open a fresh mailbox
   int* h_xerr = nullptr;  // pinned
@@ -201,6 +208,9 @@ StepKernel get_datafit_ldg_kernel(int base, int xover, int cost);
 StepKernel get_separable_ldg_kernel(int base, int xover, bool vec);
 ThreadRowKernel get_separable_small_kernel();
 ThreadRowKernel get_separable_subwarp_kernel(int lanes_per_row, bool vec);
+ThreadRowKernel get_subwarp_islands_kernel(int cost, int lanes_per_row, bool vec);
+ThreadRowKernel get_datafit_subwarp_islands_kernel(int cost);
+ThreadRowKernel get_separable_subwarp_islands_kernel(int lanes_per_row, bool vec);
 ThreadRowKernel get_datafit_small_kernel(int cost);
 ThreadRowKernel get_datafit_subwarp_kernel(int cost);
 ThreadRowKernel get_subwarp_kernel(int cost, int lanes_per_row, bool vec);
@@ -286,9 +296,52 @@ bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
   return true;
 }
 
+int ensure_parts(mb2_ctx* c, int n);
+void fill_params(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out, int64_t np,
+                 StepParams* out);
+
+// batch of independent solvers: generation 0 / one generation of every island in ONE launch
+// (grid.y = island) of the rows-per-warp kernel with run-time strategy (rows of <= 128 dimensions)
+int launch_step_islands(mb2_ctx* c, int mode, cudaStream_t stream) {
+  const int64_t inp = c->np / c->n_islands;
+  if (c->dim > kSubMaxDim) return fail(MB2_EINVAL, "batched solvers support rows of at most %d dimensions", kSubMaxDim);
+  if (c->cost == MB2_COST_CHEBYSHEV_MMA || c->cost == MB2_COST_POLYFIT_MMA)
+    return fail(MB2_EINVAL, "batched solvers use the Horner / elementwise cost variants");
+  const double* in_rows = c->pop[c->cur];
+  double* out_rows = c->pop[c->cur ^ 1];
+  const bool vec = (c->dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(in_rows) & 15) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
+  int lpr = 4;
+  while (lpr < 32 && lpr * 8 < c->dim) lpr <<= 1;
+  ThreadRowKernel k = is_datafit(c->cost) ? get_datafit_subwarp_islands_kernel(c->cost)
+                                          : (is_separable(c->cost) ? get_separable_subwarp_islands_kernel(lpr, vec)
+                                                                   : get_subwarp_islands_kernel(c->cost, lpr, vec));
+  if (k == nullptr) return fail(MB2_EINVAL, "no batched kernel for cost %d", c->cost);
+  const int rows_per_cta = kSubWarps * (32 / lpr);
+  const int smem = (int)(sizeof(double) * (size_t)(1 + kSubWarps * (32 / lpr)) * c->dim_pad);
+  CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  int64_t gx = (inp + rows_per_cta - 1) / rows_per_cta;
+  if (gx > 64) gx = 64;  // the CTAs of an island stride over its rows
+  if (int rc = ensure_parts(c, (int)(gx * c->n_islands))) return rc;
+  StepParams P;
+  fill_params(c, mode, in_rows, out_rows, c->en[c->cur], c->en[c->cur ^ 1], inp, &P);
+  P.best_x = c->best_x_isl;
+  P.rows_in_range = 0;
+  P.stop = nullptr;
+  c->wpc = kSubWarps;
+  c->grid = (int)gx;
+  c->smem = smem;
+  const StrategyInfo s = c->sinfo;
+  k<<<dim3((unsigned)gx, (unsigned)c->n_islands), kSubWarps * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
+}
+
 // configure + launch the fused kernel in `mode` over `np` rows
 int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out,
                 int64_t np, cudaStream_t stream) {
+  if (c->n_islands > 1 && mode != MODE_EVAL) return launch_step_islands(c, mode, stream);
   const bool vec = (c->dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(in_rows) & 15) == 0) &&
                    (out_rows == nullptr || (reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
   StrategyInfo s = c->sinfo;
@@ -380,6 +433,38 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   if (int rc = ensure_parts(c, (int)grid)) return rc;
 
   StepParams P;
+  fill_params(c, mode, in_rows, out_rows, e_in, e_out, np, &P);
+  c->wpc = wpc;
+  c->grid = (int)grid;
+  c->smem = smem;
+  if (kc != nullptr)
+    kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (kw != nullptr)
+    kw<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (ks != nullptr)
+    ks<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (kt != nullptr)
+    kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
+  else
+    k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
+}
+
+ExchangeParams next_exchange(mb2_ctx* c) {
+  ExchangeParams X = c->xp;
+  if (c->xchg_connected) {
+    X.epoch = ++c->xp.epoch;
+  } else {
+    X.world = 1;
+  }
+  return X;
+}
+
+void fill_params(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out, int64_t np,
+                 StepParams* out) {
+  StepParams P;
   memset(&P, 0, sizeof(P));
   P.pop_cur = in_rows;
   P.pop_next = out_rows;
@@ -421,35 +506,18 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   P.cap_energy = c->cap_energy;
   P.stop = (c->run_active && mode == MODE_STEP) ? &c->run->stop : nullptr;
 
-  c->wpc = wpc;
-  c->grid = (int)grid;
-  c->smem = smem;
-  if (kc != nullptr)
-    kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
-  else if (kw != nullptr)
-    kw<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
-  else if (ks != nullptr)
-    ks<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
-  else if (kt != nullptr)
-    kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
-  else
-    k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
-  CUDA_TRY(cudaGetLastError());
-  ++c->launches;
-  return MB2_OK;
-}
-
-ExchangeParams next_exchange(mb2_ctx* c) {
-  ExchangeParams X = c->xp;
-  if (c->xchg_connected) {
-    X.epoch = ++c->xp.epoch;
-  } else {
-    X.world = 1;
-  }
-  return X;
+  *out = P;
 }
 
 int launch_finalize(mb2_ctx* c, int gen0, cudaStream_t stream) {
+  if (c->n_islands > 1) {
+    de_finalize_islands_kernel<<<(unsigned)c->n_islands, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
+                                                                           c->pop[c->cur ^ 1], c->np / c->n_islands, c->dim, c->offset, gen0,
+                                                                           c->generation + 1, c->best_x_isl, c->st_isl);
+    CUDA_TRY(cudaGetLastError());
+    ++c->launches;
+    return MB2_OK;
+  }
   de_finalize_kernel<<<1, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
                                             c->pop[c->cur ^ 1], c->dim, c->offset, gen0, c->generation + 1,
                                             c->best_x, c->st, (c->run_active && !gen0) ? c->run : nullptr,
@@ -868,6 +936,7 @@ int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy,
                       const double* best_x_host, int64_t generation) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   if (!energy_host || !best_x_host || generation < 0) return fail(MB2_EINVAL, "bad argument");
+  if (c->n_islands > 1) return fail(MB2_EINVAL, "restart files of batched solvers are not supported");
   CUDA_TRY(cudaSetDevice(c->device));
   CUDA_TRY(cudaMemcpy(c->en[c->cur], energy_host, sizeof(double) * c->np, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->best_x, best_x_host, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
@@ -946,6 +1015,7 @@ int mb2_set_termination(mb2_ctx* c, const mb2_termination* t, const double* hist
 int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   if (c->run == nullptr) return fail(MB2_ESTATE, "mb2_set_termination must run before mb2_run");
+  if (c->n_islands > 1) return fail(MB2_EINVAL, "batched solvers are stepped with mb2_step (their termination lives on the host)");
   if (c->generation < 0) return fail(MB2_ESTATE, "mb2_eval_initial must run before mb2_run");
   if (max_steps < 1 || log_dev == nullptr) return fail(MB2_EINVAL, "bad argument");
   if (c->replay) return fail(MB2_EINVAL, "batch stepping needs the Philox generator (replayed draws are per generation)");
@@ -1008,12 +1078,63 @@ int mb2_merge_best(mb2_ctx* c, const double* records, int32_t world, void* strea
   return MB2_OK;
 }
 
+int mb2_set_islands(mb2_ctx* c, int32_t n_islands) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (n_islands < 1 || c->np % n_islands != 0)
+    return fail(MB2_EINVAL, "%lld rows do not split into %d equal populations", (long long)c->np, n_islands);
+  if (c->xchg_connected) return fail(MB2_ESTATE, "batched solvers and sharded populations do not combine");
+  if (c->generation >= 0) return fail(MB2_ESTATE, "mb2_set_islands must come before mb2_eval_initial");
+  const int64_t inp = c->np / n_islands;
+  if (n_islands > 1 && inp < c->sinfo.k + 1)
+    return fail(MB2_EINVAL, "each population needs at least %d members for this strategy", c->sinfo.k + 1);
+  CUDA_TRY(cudaSetDevice(c->device));
+  if (n_islands > 1 && (c->st_isl == nullptr || n_islands > c->n_islands)) {
+    void* p = nullptr;
+    if (int rc = dev_alloc(c, sizeof(DeviceState) * n_islands, &p)) return rc;
+    c->st_isl = (DeviceState*)p;
+    if (int rc = dev_alloc(c, sizeof(double) * (size_t)n_islands * c->dim, &p)) return rc;
+    c->best_x_isl = (double*)p;
+    if (int rc = host_alloc(c, sizeof(DeviceState) * n_islands, &p)) return rc;
+    c->h_st_isl = (DeviceState*)p;
+    if (int rc = host_alloc(c, sizeof(double) * (size_t)n_islands * c->dim, &p)) return rc;
+    c->h_best_isl = (double*)p;
+  }
+  if (n_islands > 1) {
+    std::vector<DeviceState> init((size_t)n_islands, DeviceState{INFINITY, -1, 0, 0, -1});
+    CUDA_TRY(cudaMemcpy(c->st_isl, init.data(), sizeof(DeviceState) * n_islands, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemset(c->best_x_isl, 0, sizeof(double) * (size_t)n_islands * c->dim));
+  }
+  c->n_islands = n_islands;
+  return MB2_OK;
+}
+
+int mb2_read_islands(mb2_ctx* c, mb2_result* out, double* x_host, void* stream) {
+  if (c == nullptr || out == nullptr) return fail(MB2_EINVAL, "NULL argument");
+  if (c->n_islands < 2) return fail(MB2_ESTATE, "mb2_set_islands first");
+  CUDA_TRY(cudaSetDevice(c->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)c->n_islands;
+  CUDA_TRY(cudaMemcpyAsync(c->h_st_isl, c->st_isl, sizeof(DeviceState) * n, cudaMemcpyDeviceToHost, s));
+  if (x_host) CUDA_TRY(cudaMemcpyAsync(c->h_best_isl, c->best_x_isl, sizeof(double) * n * c->dim, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (size_t i = 0; i < n; ++i) {
+    out[i].best_energy = c->h_st_isl[i].best_e;
+    out[i].best_index = c->h_st_isl[i].best_idx;
+    out[i].n_inf = c->h_st_isl[i].n_inf;
+    out[i].n_accepted = c->h_st_isl[i].n_acc;
+    out[i].generation = c->h_st_isl[i].generation;
+  }
+  if (x_host) memcpy(x_host, c->h_best_isl, sizeof(double) * n * c->dim);
+  return MB2_OK;
+}
+
 int mb2_exchange_open(mb2_ctx* c, int32_t world, int32_t rank, void* handle_out, int32_t handle_bytes) {
   if (c == nullptr || handle_out == nullptr) return fail(MB2_EINVAL, "NULL argument");
   if (world < 2 || world > kMaxWorld || rank < 0 || rank >= world)
     return fail(MB2_EINVAL, "world %d / rank %d out of range (2..%d ranks)", world, rank, kMaxWorld);
   if (handle_bytes < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail(MB2_EINVAL, "handle buffer too small");
   if (c->mailbox != nullptr) return fail(MB2_ESTATE, "exchange already opened");
+  if (c->n_islands > 1) return fail(MB2_ESTATE, "batched solvers and sharded populations do not combine");
   CUDA_TRY(cudaSetDevice(c->device));
   const int stride = (c->dim + 4 + 1) & ~1;  // 16-byte slots
   memset(handle_out, 0, (size_t)handle_bytes);

@@ -101,13 +101,12 @@ __device__ __forceinline__ void exchange_best(const ExchangeParams& X, int D, do
 // K3: reduce the per-CTA partials, update bestEnergy/bestSolution if the generation best beats
 // the previous best (strict '<', :610), publish counters; with X.world > 1 the shards' bests are
 // exchanged over peer memory in the same kernel.  One CTA.
-__global__ void __launch_bounds__(256)
-    de_finalize_kernel(const double* __restrict__ part_e, const int64_t* __restrict__ part_idx,
-                       const unsigned long long* __restrict__ part_ninf,
-                       const unsigned long long* __restrict__ part_nacc, int nparts,
-                       const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
-                       int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
-                       RunState* __restrict__ rs, const __grid_constant__ ExchangeParams X) {
+__device__ __forceinline__ void finalize_body(const double* __restrict__ part_e, const int64_t* __restrict__ part_idx,
+                                              const unsigned long long* __restrict__ part_ninf,
+                                              const unsigned long long* __restrict__ part_nacc, int nparts,
+                                              const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
+                                              int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
+                                              RunState* __restrict__ rs, const ExchangeParams& X) {
   if (rs != nullptr && rs->stop) return;  // batch mode: this generation was not run
   __shared__ double sh_e[256];
   __shared__ int64_t sh_i[256];
@@ -225,6 +224,32 @@ __global__ void __launch_bounds__(256)
     if (rs->max_generations >= 0 && rs->generations >= rs->max_generations) met = true;
     if (met || rs->log_count >= rs->log_cap) rs->stop = met ? 1 : 2;  // 2: log full (cannot happen: one batch = log_cap launches)
   }
+}
+
+__global__ void __launch_bounds__(256)
+    de_finalize_kernel(const double* __restrict__ part_e, const int64_t* __restrict__ part_idx,
+                       const unsigned long long* __restrict__ part_ninf,
+                       const unsigned long long* __restrict__ part_nacc, int nparts,
+                       const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
+                       int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
+                       RunState* __restrict__ rs, const __grid_constant__ ExchangeParams X) {
+  finalize_body(part_e, part_idx, part_ninf, part_nacc, nparts, pop_next, D, global_offset, gen0, generation, best_x, st, rs, X);
+}
+
+// Batch of independent solvers: one CTA per island (blockIdx.x), each with its own partials
+// [isl*nparts, (isl+1)*nparts), rows, best member and DeviceState.
+__global__ void __launch_bounds__(256)
+    de_finalize_islands_kernel(const double* __restrict__ part_e, const int64_t* __restrict__ part_idx,
+                               const unsigned long long* __restrict__ part_ninf,
+                               const unsigned long long* __restrict__ part_nacc, int nparts,
+                               const double* __restrict__ pop_next, int64_t island_np, int D, int64_t global_offset,
+                               int gen0, int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st) {
+  const int64_t isl = blockIdx.x;
+  ExchangeParams none;
+  none.world = 1;
+  finalize_body(part_e + isl * nparts, part_idx + isl * nparts, part_ninf + isl * nparts, part_nacc + isl * nparts, nparts,
+                pop_next + isl * island_np * D, D, global_offset + isl * island_np, gen0, generation, best_x + isl * D,
+                st + isl, nullptr, none);
 }
 
 // K0: device-side SetRandomInitialPoints (abstract_solver.py:532-534): pop[c][j] = lo + (hi-lo)*u

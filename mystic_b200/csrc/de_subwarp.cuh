@@ -145,9 +145,10 @@ __device__ __forceinline__ double seg_penalty(const double* xs, int D, int sub, 
   return total;
 }
 
+// The kernel body; `P` is the launch's parameter block (de_step_subwarp_kernel) or a per-island copy
+// of it (de_step_subwarp_islands_kernel); `part` indexes this CTA's partials.
 template <int COST, int LPR, bool VEC>
-__global__ void __launch_bounds__(kSubWarps * 32)
-    de_step_subwarp_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
+__device__ __forceinline__ void subwarp_body(const StepParams& P, int base, int xover, int ndonors, int part) {
   if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(16) double smem[];
   __shared__ double sh_e[kSubWarps];
@@ -384,11 +385,46 @@ __global__ void __launch_bounds__(kSubWarps * 32)
       ni += sh_ninf[w];
       na += sh_nacc[w];
     }
-    P.part_e[blockIdx.x] = be;
-    P.part_idx[blockIdx.x] = bi;
-    P.part_ninf[blockIdx.x] = ni;
-    P.part_nacc[blockIdx.x] = na;
+    P.part_e[part] = be;
+    P.part_idx[part] = bi;
+    P.part_ninf[part] = ni;
+    P.part_nacc[part] = na;
   }
+}
+
+template <int COST, int LPR, bool VEC>
+__global__ void __launch_bounds__(kSubWarps * 32)
+    de_step_subwarp_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
+  subwarp_body<COST, LPR, VEC>(P, base, xover, ndonors, (int)blockIdx.x);
+}
+
+// Batch of independent solvers: blockIdx.y is the island.  P describes ONE island
+// (np rows, first island's pointers); island y works on rows [y*np, (y+1)*np) of the buffers, draws
+// its donors among them, follows its own best member best_x[y*dim..] and reports into its own
+// partials -- exactly what a shard of a sharded population does (global_offset keys the Philox
+// counters, so every island has its own draws).
+template <int COST, int LPR, bool VEC>
+__global__ void __launch_bounds__(kSubWarps * 32)
+    de_step_subwarp_islands_kernel(const __grid_constant__ StepParams P, int base, int xover, int ndonors) {
+  StepParams Q = P;
+  const int64_t isl = blockIdx.y;
+  const int64_t row0 = isl * P.np;
+  Q.pop_cur += row0 * P.dim;
+  if (Q.pop_next != nullptr) Q.pop_next += row0 * P.dim;
+  if (Q.e_cur != nullptr) Q.e_cur += row0;
+  Q.e_next += row0;
+  Q.best_x += isl * P.dim;
+  Q.global_offset += row0;
+  if (Q.r_donors != nullptr) {
+    Q.r_donors += row0 * 5;
+    Q.r_nstart += row0;
+    Q.r_uni += row0 * (int64_t)(P.dim + 1);
+  }
+  if (Q.cap_trial != nullptr) {
+    Q.cap_trial += row0 * P.dim;
+    Q.cap_energy += row0;
+  }
+  subwarp_body<COST, LPR, VEC>(Q, base, xover, ndonors, (int)(isl * gridDim.x + blockIdx.x));
 }
 
 }  // namespace mb2

@@ -38,4 +38,10 @@ ThreadRowKernel get_datafit_subwarp_kernel(int cost) {  // 4 lanes per row (dim 
              ? (ThreadRowKernel)de_step_subwarp_kernel<COST_POLYFIT, 4, false>
              : (cost == MB2_COST_LORENTZIAN ? (ThreadRowKernel)de_step_subwarp_kernel<COST_LORENTZIAN, 4, false> : nullptr);
 }
+
+ThreadRowKernel get_datafit_subwarp_islands_kernel(int cost) {
+  return cost == MB2_COST_POLYFIT
+             ? (ThreadRowKernel)de_step_subwarp_islands_kernel<COST_POLYFIT, 4, false>
+             : (cost == MB2_COST_LORENTZIAN ? (ThreadRowKernel)de_step_subwarp_islands_kernel<COST_LORENTZIAN, 4, false> : nullptr);
+}
 }  // namespace mb2

@@ -42,4 +42,20 @@ ThreadRowKernel get_separable_subwarp_kernel(int lanes_per_row, bool vec) {
   }
   return nullptr;
 }
+
+template <int LPR>
+static ThreadRowKernel sep_isl(bool vec) {
+  return vec ? (ThreadRowKernel)de_step_subwarp_islands_kernel<COST_SEPARABLE, LPR, true>
+             : (ThreadRowKernel)de_step_subwarp_islands_kernel<COST_SEPARABLE, LPR, false>;
+}
+
+ThreadRowKernel get_separable_subwarp_islands_kernel(int lanes_per_row, bool vec) {
+  switch (lanes_per_row) {
+    case 4: return sep_isl<4>(vec);
+    case 8: return sep_isl<8>(vec);
+    case 16: return sep_isl<16>(vec);
+    case 32: return sep_isl<32>(vec);
+  }
+  return nullptr;
+}
 }  // namespace mb2

@@ -52,6 +52,7 @@ class DeviceEngine(object):
             self._trial_e = torch.full((self.np_local,), float('inf'), **f64)
             check(lib.mb2_set_capture(self._ctx, self._trial.data_ptr(), self._trial_e.data_ptr()))
         self._replay = None  # keeps the uploaded draw tensors alive until consumed
+        self.n_islands = 1
         self.peer_exchange = False  # True: eval_initial()/step() end with the exchange of the shards' bests
         self._log = self._log_host = None  # batch-mode generation log
         self._record = torch.empty((self.dim + 4,), **f64)
@@ -190,6 +191,23 @@ class DeviceEngine(object):
         n = done.value
         self._log_host[:n].copy_(self._log[:n])
         return self._log_host[:n].numpy().copy(), bool(stopped.value)
+
+    # ---- batch of independent solvers -------------------------------------------------------
+    def set_islands(self, n_islands):
+        """the rows become n_islands independent populations advanced by the same launches"""
+        check(lib.mb2_set_islands(self._ctx, int(n_islands)))
+        self.n_islands = int(n_islands)
+
+    def read_islands(self):
+        """-> (best_energy[n], best_index[n], n_inf[n], n_accepted[n], generation, bestSolution[n, dim]); synchronises"""
+        n = self.n_islands
+        res = (_native.Result * n)()
+        x = np.empty((n, self.dim), dtype=np.float64)
+        check(lib.mb2_read_islands(self._ctx, ctypes.cast(res, ctypes.c_void_p), _dptr(x), self._stream()))
+        self._replay = None
+        return (np.array([r.best_energy for r in res]), np.array([r.best_index for r in res], dtype=np.int64),
+                np.array([r.n_inf for r in res], dtype=np.int64), np.array([r.n_accepted for r in res], dtype=np.int64),
+                int(res[0].generation), x)
 
     # ---- sharded populations: best exchange ------------------------------------------------
     def connect_peers(self, world, rank, all_gather_object, all_agree):

@@ -1,0 +1,102 @@
+"""Batch of independent solvers in one launch (mb2_set_islands): island i of a batched
+engine must be, bit for bit, what a stand-alone engine computes for shard i of the same rows
+(same Philox counters: they are keyed by the global row index; donors among the shard's own rows)."""
+import numpy as np
+import pytest
+
+from oracle import de_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+CASES = [
+    # dim, rows per island, islands, strategy, cost, bounds (lo, hi, mode)
+    (8, 24, 5, 'Best1Exp', 'rosen', None),
+    (64, 40, 7, 'Best1Bin', 'griewangk', (-400., 400., orc.BOUNDS_CLAMP)),
+    (12, 30, 4, 'RandToBest1Exp', 'rastrigin', (-5.12, 5.12, orc.BOUNDS_REJECT)),
+    (7, 28, 3, 'Rand1Exp', 'lorentzian', (0.05, 200., orc.BOUNDS_CLAMP)),
+    (2, 9, 16, 'Best2Exp', 'zimmermann', (0., 5., orc.BOUNDS_REJECT)),
+    (100, 33, 2, 'Rand2Exp', 'sphere', None),
+]
+
+
+def _cost(name, dim):
+    from mystic_b200 import models
+    if name == 'lorentzian':
+        bins = np.arange(0.05, 3.0, 0.1)
+        return models.lorentzian.CostFactory([1., 45., -10., 20., 1., 0.1, 120.], bins)
+    return getattr(models, name)
+
+
+def _configure(eng, cost, strat, bounds, dim, seed):
+    eng.set_cost(cost.cost_id, cost.params(()))
+    if bounds is None:
+        eng.set_bounds(orc.BOUNDS_NONE)
+    else:
+        eng.set_bounds(bounds[2], np.full(dim, bounds[0]), np.full(dim, bounds[1]))
+    eng.set_strategy(orc.STRATEGIES[strat][0], 0.8, 0.9)
+    eng.set_rng_philox(seed)
+
+
+@pytest.mark.parametrize('case', CASES, ids=lambda c: '%s-%s-D%d-x%d' % (c[3], c[4], c[0], c[2]))
+def test_islands_equal_independent_shards(case, monkeypatch):
+    from mystic_b200.engine import DeviceEngine
+    monkeypatch.setenv('MB2_SMALL_KERNEL', '1')   # the stand-alone shards run the same kernel family: identical energies
+    dim, inp, S, strat, cname, bounds = case
+    total, seed = inp * S, 0x151A + dim
+    cost = _cost(cname, dim)
+    ilo = np.full(dim, -3.0 if bounds is None else bounds[0] * 1.2 if bounds[0] < 0 else bounds[0])
+    ihi = np.full(dim, 3.0 if bounds is None else bounds[1] * 1.2)
+    big = DeviceEngine(total, dim, keep_trials=True)
+    _configure(big, cost, strat, bounds, dim, seed)
+    big.set_islands(S)
+    big.init_population(seed, ilo, ihi)
+    shards = []
+    for i in range(S):
+        e = DeviceEngine(inp, dim, total, i * inp, keep_trials=True)
+        _configure(e, cost, strat, bounds, dim, seed)
+        e.init_population(seed, ilo, ihi)
+        shards.append(e)
+    for g in range(6):
+        if g == 0:
+            big.eval_initial()
+            [e.eval_initial() for e in shards]
+        else:
+            big.step()
+            [e.step() for e in shards]
+        be, bi, ninf, nacc, gen, bx = big.read_islands()
+        pop, en = big.population(), big.energies()
+        trial, trial_e = big.trials()
+        assert gen == g
+        for i, e in enumerate(shards):
+            r = e.read_result()
+            sl = slice(i * inp, (i + 1) * inp)
+            tag = 'generation %d island %d' % (g, i)
+            assert np.array_equal(pop[sl], e.population()), tag
+            assert np.array_equal(en[sl], e.energies()), tag
+            assert np.array_equal(trial[sl], e.trials()[0]) and np.array_equal(trial_e[sl], e.trials()[1], equal_nan=True), tag
+            assert (be[i], bi[i], ninf[i], nacc[i]) == (r[0], r[1], r[2], r[3]), (tag, be[i], bi[i], r[:4])
+            assert np.array_equal(bx[i], r[5]), tag
+    big.close()
+    [e.close() for e in shards]
+
+
+def test_islands_reject_what_they_cannot_do():
+    from mystic_b200 import models
+    from mystic_b200._native import NativeError
+    from mystic_b200.engine import DeviceEngine
+    eng = DeviceEngine(30, 4)
+    eng.set_cost(models.rosen.cost_id, [])
+    eng.set_strategy(orc.STRATEGIES['Rand2Exp'][0], 0.8, 0.9)
+    with pytest.raises(NativeError):
+        eng.set_islands(7)            # 30 rows do not split into 7 populations
+    with pytest.raises(NativeError):
+        eng.set_islands(6)            # 5 members cannot supply 5 distinct donors besides the candidate
+    eng.set_islands(3)
+    eng.close()
+    wide = DeviceEngine(40, 200)
+    wide.set_cost(models.rosen.cost_id, [])
+    wide.set_islands(2)
+    wide.init_population(1, np.full(200, -1.), np.full(200, 1.))
+    with pytest.raises(NativeError):
+        wide.eval_initial()           # rows of more than 128 dimensions
+    wide.close()
