@@ -82,14 +82,43 @@ class OracleEngine(object):
         self.state.generation = int(generation)
         self.best_idx = int(best_index)
 
+    # ---- batch of independent solvers: island i is shard i of the rows, without a best exchange
+    def set_islands(self, n):
+        n = int(n)
+        if n < 1 or self.np_local % n:
+            raise ValueError('%d rows do not split into %d equal populations' % (self.np_local, n))
+        self.n_islands = n
+        self._isl = None
+
+    def _islands(self):
+        if getattr(self, '_isl', None) is None:
+            inp = self.np_local // self.n_islands
+            self._isl = []
+            for i in range(self.n_islands):
+                e = OracleEngine(inp, self.dim, self.np_global, self.offset + i * inp)
+                e.cost, e.pen, e.bounds, e.seed = self.cost, self.pen, self.bounds, self.seed
+                e._pop = self._pop[i * inp:(i + 1) * inp].copy()
+                self._isl.append(e)
+        return self._isl
+
+    def read_islands(self):
+        rs = [e.read_result() for e in self._islands()]
+        return (np.array([r[0] for r in rs]), np.array([r[1] for r in rs], dtype=np.int64),
+                np.array([r[2] for r in rs], dtype=np.int64), np.array([r[3] for r in rs], dtype=np.int64),
+                int(rs[0][4]), np.array([r[5] for r in rs]))
+
     def population_tensor(self):
         arr = self._pop if self.state is None else self.state.population
         return torch.from_numpy(arr)
 
     def population(self):
+        if getattr(self, 'n_islands', 1) > 1 and getattr(self, '_isl', None):
+            return np.concatenate([e.population() for e in self._isl])
         return (self._pop if self.state is None else self.state.population).copy()
 
     def energies(self):
+        if getattr(self, 'n_islands', 1) > 1 and getattr(self, '_isl', None):
+            return np.concatenate([e.energies() for e in self._isl])
         return np.full(self.np_local, np.inf) if self.state is None else self.state.popEnergy.copy()
 
     def trials(self):
@@ -104,6 +133,11 @@ class OracleEngine(object):
         self.launches += 2
 
     def eval_initial(self):
+        if getattr(self, 'n_islands', 1) > 1:
+            for e in self._islands():
+                e.eval_initial()
+            self.launches += 2
+            return
         mode, lo, hi = self.bounds
         self.state = orc.DEState(self._pop, lo, hi, mode)
         self.best_idx = -1
@@ -111,6 +145,12 @@ class OracleEngine(object):
         self._after()
 
     def step(self):
+        if getattr(self, 'n_islands', 1) > 1:
+            for e in self._islands():
+                e.strategy, e.F, e.CR = self.strategy, self.F, self.CR
+                e.step()
+            self.launches += 2
+            return
         st = self.state
         st.bestIndex = -1
         if self.replay is not None:

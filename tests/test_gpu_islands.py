@@ -100,3 +100,30 @@ def test_islands_reject_what_they_cannot_do():
     with pytest.raises(NativeError):
         wide.eval_initial()           # rows of more than 128 dimensions
     wide.close()
+
+
+def test_buckshot_on_device_equals_the_oracle_ensemble():
+    """mystic_b200.ensemble.BuckshotSolver with its nested DE2 runs on the device against the same
+    class over the test-only oracle engine: same members, same stop generations, best members bit-exact"""
+    import random
+    from mystic_b200 import DifferentialEvolutionSolver2, models, termination
+    from mystic_b200.ensemble import BuckshotSolver
+    from tests._oracle_engine import OracleEngine
+    runs = []
+    for engine in (None, OracleEngine):
+        random.seed(21)
+        s = BuckshotSolver(4, 12, engine=engine, seed=99)
+        s.SetNestedSolver(DifferentialEvolutionSolver2(4, 24, strategy='Best1Exp'))
+        s.SetStrictRanges([-2.] * 4, [2.] * 4)
+        s.SetEvaluationLimits(generations=80)
+        s.Solve(models.rosen, termination.VTR(1e-4))
+        runs.append(s)
+    dev, ref = runs
+    assert dev._all_iters == ref._all_iters and dev._all_evals == ref._all_evals
+    assert len(set(dev._all_iters)) > 1
+    for a, b in zip(dev._all_bestSolution, ref._all_bestSolution):
+        assert np.array_equal(a, b)
+    assert np.allclose(dev._all_bestEnergy, ref._all_bestEnergy, rtol=1e-12, atol=0)
+    assert np.array_equal(dev.bestSolution, ref.bestSolution) and dev.Terminated(info=True) == ref.Terminated(info=True)
+    # the energy fill of the upload, then ONE fused launch + one epilogue per generation for all members together
+    assert dev._engine.launch_count() == 1 + 2 * (max(dev._all_iters) + 1)
