@@ -48,6 +48,9 @@ WORKLOADS = {
     'c3h': dict(desc='chebyshev8cost M=4096, 9 coeffs, NP=1048576/GPU, Best1Exp CR=1.0 F=0.9, init +-100 (Horner)',
                 cost='chebyshev8cost', extra=(4096,), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
                 lo=-100., hi=100., bounds=None, penalty=None, k=2),
+    'x2': dict(desc='Rosenbrock 1024-D, NP=65536/GPU, Rand1Exp CR=0.9 F=0.8, SetStrictRanges(+-5, tight=True) (exponential crossover, long rows)',
+               cost='rosen', extra=(), dim=1024, np=65536, strategy='Rand1Exp', CR=0.9, F=0.8, lo=-5., hi=5.,
+               bounds='clamp', penalty=None, k=3),
     # data-fit residual costs of forward_model.CostFactory (extra = points/observations, made in main)
     'f2': dict(desc='polynomial least-squares fit (poly.CostFactory2), 9 coeffs x 4096 points, NP=1048576/GPU, Best1Exp CR=1.0 '
                     'F=0.9, init +-100 (FP64 DMMA)',

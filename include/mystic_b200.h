@@ -263,6 +263,20 @@ int mb2_selftest_cosine(mb2_ctx* ctx, int64_t n, uint64_t seed, double span, dou
 int mb2_launch_info(mb2_ctx* ctx, int32_t* grid, int32_t* block, int32_t* smem_bytes);
 /* number of kernels this library has launched through the context (bench.py gpu_launches) */
 int64_t mb2_launch_count(mb2_ctx* ctx);
+/* which kernel family the last fused launch (generation 0, step or evaluation) used: the tests assert
+ * that a case runs on the kernel it is meant to cover */
+enum mb2_kernel_family_id {
+  MB2_KERNEL_NONE = 0,
+  MB2_KERNEL_WARP_PER_ROW = 1,   /* de_kernels.cuh: plain loads, one warp per row */
+  MB2_KERNEL_TMA_BIN = 2,        /* de_tma.cuh: Best1Bin, whole rows staged by cp.async.bulk */
+  MB2_KERNEL_TMA_EXP = 3,        /* de_tma_exp.cuh: exponential crossover, parent row + donor windows staged */
+  MB2_KERNEL_ROWS = 4,           /* de_rows.cuh: 16..128-dimensional rows, tiles of rows per warp */
+  MB2_KERNEL_ROWS_PER_WARP = 5,  /* de_subwarp.cuh */
+  MB2_KERNEL_THREAD_PER_ROW = 6, /* de_small.cuh */
+  MB2_KERNEL_DMMA = 7,           /* de_cheb_mma.cuh: FP64 tensor-core contraction */
+  MB2_KERNEL_ISLANDS = 8         /* batch of solvers, grid.y = island */
+};
+int mb2_kernel_family(mb2_ctx* ctx);
 
 #ifdef __cplusplus
 }

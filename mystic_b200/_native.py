@@ -17,7 +17,7 @@ EXPORTS = [
     'mb2_set_strategy', 'mb2_set_bounds', 'mb2_set_cost', 'mb2_set_penalty', 'mb2_set_rng_philox',
     'mb2_set_rng_replay', 'mb2_init_population', 'mb2_upload_population', 'mb2_set_capture',
     'mb2_eval_initial', 'mb2_step', 'mb2_pack_best', 'mb2_merge_best', 'mb2_read_result', 'mb2_eval_cost',
-    'mb2_launch_info', 'mb2_launch_count', 'mb2_selftest_division', 'mb2_selftest_cosine', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
+    'mb2_launch_info', 'mb2_launch_count', 'mb2_kernel_family', 'mb2_selftest_division', 'mb2_selftest_cosine', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
     'mb2_set_termination', 'mb2_run', 'mb2_run_result', 'mb2_set_islands', 'mb2_read_islands', 'mb2_exchange_open', 'mb2_exchange_connect', 'mb2_exchange_connected', 'mb2_exchange_reset', 'mb2_exchange_best',
 ]
 
@@ -73,6 +73,7 @@ def _load():
         'mb2_eval_cost': (ctypes.c_int, [vp, vp, i64, vp, vp]),
         'mb2_launch_info': (ctypes.c_int, [vp, c_int32_p, c_int32_p, c_int32_p]),
         'mb2_launch_count': (i64, [vp]),
+        'mb2_kernel_family': (ctypes.c_int, [vp]),
         'mb2_selftest_division': (ctypes.c_int, [vp, i64, u64, dbl, c_int64_p]),
         'mb2_set_islands': (ctypes.c_int, [vp, i32]),
         'mb2_read_islands': (ctypes.c_int, [vp, ctypes.c_void_p, c_double_p, vp]),

@@ -117,6 +117,7 @@ struct mb2_ctx {
   int64_t launches = 0;
   // launch geometry of the fused kernel
   int wpc = 8, grid = 0, smem = 0;
+  int family = MB2_KERNEL_NONE;  // kernel family of the last fused launch
   // small device / pinned-host buffers come out of a caller-provided workspace when there is one
   // (torch's caching allocators make that free; cudaMalloc / cudaMallocHost cost milliseconds
   // each next to gigabytes of live allocations) and from cudaMalloc otherwise
@@ -198,10 +199,12 @@ int host_alloc(mb2_ctx* c, size_t bytes, void** out) {
 typedef void (*StepKernel)(const StepParams);
 typedef void (*TmaKernel)(const StepParams, int);
 typedef void (*ThreadRowKernel)(const StepParams, int, int, int);
+typedef void (*ExpTmaKernel)(const StepParams, int, int, int, int);
 }  // namespace
 namespace mb2 {
 StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
+ExpTmaKernel get_exp_tma_kernel(int cost, int gwarps);
 ThreadRowKernel get_small_kernel(int cost);
 ThreadRowKernel get_cheb_mma_kernel(int ksteps, bool resid);
 StepKernel get_datafit_ldg_kernel(int base, int xover, int cost);
@@ -296,6 +299,53 @@ bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
   return true;
 }
 
+// Ring geometry of K2e (exponential crossover, de_tma_exp.cuh).  A stage holds the parent row, an
+// undo buffer and k donor-segment buffers of `cap` elements each; cap covers the crossover window
+// (plus alignment slack) with probability >= 0.999: P(L > n) = CR^n.  In-flight bytes per SM are what
+// matter (a stage carries one row), so the ring is as deep as the shared memory allows.
+bool exp_tma_geometry(int dim, int k, double CR, int* groups, int* gwarps, int* stages, int* cap, int* smem) {
+  const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
+  const size_t budget = 220 * 1024;
+  int want = dim;
+  if (CR < 1.0) {
+    const double n = (CR > 0.0) ? std::ceil(std::log(1e-3) / std::log(CR)) : 1.0;
+    if (n + 3.0 < (double)dim) want = (int)n + 3;
+  }
+  want = (want + 1) & ~1;
+  if (want < 8) want = 8;
+  if (want > dim) want = dim;
+  const int ec = env_int("MB2_XTMA_CAP", 0);
+  if (ec >= 2 && ec <= dim) want = ec & ~1;
+  size_t stage = (row + (size_t)(k + 1) * want * 8 + 128 + 127) & ~(size_t)127;
+  if (row + 2 * stage > budget) {  // whole-row donor buffers do not fit twice: short windows only
+    want = 64 < dim ? 64 : dim;
+    stage = (row + (size_t)(k + 1) * want * 8 + 128 + 127) & ~(size_t)127;
+    if (row + 2 * stage > budget) return false;
+  }
+  const size_t slots = (budget - row) / stage;  // (group, stage) buffers that fit on one SM
+  int gw = 1;
+  while (gw < 8 && (gw * 2) * 32 * 8 <= dim) gw <<= 1;  // about 8 dimensions per thread
+  int g = kTmaMaxThreads / (gw * 32);
+  if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
+  if (g > kTmaMaxGroups) g = kTmaMaxGroups;
+  if ((size_t)g > slots) g = (int)slots;
+  int st = (int)(slots / g);
+  if (st > kTmaMaxStages) st = kTmaMaxStages;
+  const int eg = env_int("MB2_XTMA_GROUPS", 0), ew = env_int("MB2_XTMA_GWARPS", 0), es = env_int("MB2_XTMA_STAGES", 0);
+  if (eg >= 1 && eg <= kTmaMaxGroups && (ew == 1 || (ew == 2 || ew == 4 || ew == 8) && eg <= 15) && es >= 1 &&
+      es <= kTmaMaxStages && (size_t)eg * es <= slots && eg * ew * 32 <= kTmaMaxThreads) {
+    g = eg;
+    gw = ew;
+    st = es;
+  }
+  *groups = g;
+  *gwarps = gw;
+  *stages = st;
+  *cap = want;
+  *smem = (int)(row + (size_t)g * st * stage);
+  return true;
+}
+
 int ensure_parts(mb2_ctx* c, int n);
 void fill_params(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out, int64_t np,
                  StepParams* out);
@@ -331,6 +381,7 @@ int launch_step_islands(mb2_ctx* c, int mode, cudaStream_t stream) {
   c->wpc = kSubWarps;
   c->grid = (int)gx;
   c->smem = smem;
+  c->family = MB2_KERNEL_ISLANDS;
   const StrategyInfo s = c->sinfo;
   k<<<dim3((unsigned)gx, (unsigned)c->n_islands), kSubWarps * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   CUDA_TRY(cudaGetLastError());
@@ -384,6 +435,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 && !datafit && !separable &&
       !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
+  // the other strategies read a short window of the donors: K2e keeps long rows in a TMA ring
+  ExpTmaKernel kx = nullptr;
+  int xcap = 0;
+  if (mode == MODE_STEP && s.xover == XOVER_EXP && vec && env_int("MB2_TMA_EXP", 1) != 0 && !datafit && !cheb_mma &&
+      ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, &tg, &tw, &ts, &xcap, &tsmem))
+    kx = get_exp_tma_kernel(c->cost, tw);
 
   int wpc, smem;
   int occ = 0;
@@ -418,6 +475,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     smem = tsmem;
     CUDA_TRY(cudaFuncSetAttribute(kt, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kt, wpc * 32, smem));
+  } else if (kx != nullptr) {
+    wpc = tg * tw;
+    rows_per_cta = tg;
+    smem = tsmem;
+    CUDA_TRY(cudaFuncSetAttribute(kx, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kx, wpc * 32, smem));
   } else {
     geometry(c->dim_pad, &wpc, &smem);
     rows_per_cta = wpc;
@@ -437,6 +500,8 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->wpc = wpc;
   c->grid = (int)grid;
   c->smem = smem;
+  c->family = kc ? MB2_KERNEL_DMMA : kr ? MB2_KERNEL_ROWS : kw ? MB2_KERNEL_ROWS_PER_WARP : ks ? MB2_KERNEL_THREAD_PER_ROW
+              : kt ? MB2_KERNEL_TMA_BIN : kx ? MB2_KERNEL_TMA_EXP : MB2_KERNEL_WARP_PER_ROW;
   if (kc != nullptr)
     kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (kw != nullptr)
@@ -445,6 +510,8 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     ks<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (kt != nullptr)
     kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
+  else if (kx != nullptr)
+    kx<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts, xcap, s.base, s.k);
   else
     k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());
@@ -1271,5 +1338,7 @@ int mb2_launch_info(mb2_ctx* c, int32_t* grid, int32_t* block, int32_t* smem) {
 }
 
 int64_t mb2_launch_count(mb2_ctx* c) { return c ? c->launches : 0; }
+
+int mb2_kernel_family(mb2_ctx* c) { return c ? c->family : MB2_KERNEL_NONE; }
 
 }  // extern "C"

@@ -1,0 +1,325 @@
+// K2e: exponential-crossover generation kernel for long rows, TMA bulk staging.
+//
+// Nine of the reference's ten strategies run the exponential loop (mystic/strategy.py:48-56): a
+// trial differs from its parent only inside a window of L consecutive (wrapping) dimensions that
+// starts at `nstart`, E[L] = CR(1-CR^D)/(1-CR) (9 at CR = 0.9).  Per candidate the kernel therefore
+// moves the parent row in, the selected row out, and k short donor segments:
+//   * a GROUP of GW warps owns one candidate at a time and a private ring of `stages` buffers;
+//   * the group's leader warp makes the draws (donors, start index, window length; same Philox
+//     counters as every other kernel) and issues `cp.async.bulk` copies onto the stage's mbarrier:
+//     the parent row (8*D bytes) and, per donor, the 16-byte aligned segment(s) covering the
+//     window (two when it wraps), compacted into a `cap`-element buffer;
+//   * the trial is built IN PLACE in the parent buffer; the parent's window values go to an undo
+//     buffer, so a rejected trial (the common case) is restored by rewriting L elements;
+//   * cost / penalty read the row from shared memory with the canonical reduction of
+//     de_device.cuh, and the selected row leaves with one bulk shared->global copy.
+// Windows longer than `cap` (probability < 1e-3 by the host's choice of cap) read their donor
+// elements with plain loads and restore a rejected trial from the parent row in global memory.
+//
+// Semantics are those of de_step_kernel<BASE, XOVER_EXP, COST> (de_kernels.cuh); the same device
+// functions produce the numbers, so both kernels agree bit for bit.
+#pragma once
+#include "de_tma.cuh"
+
+namespace mb2 {
+
+struct ExpStageMeta {  // written by the leader before the mbarrier arrive, read by the group after the wait
+  int nstart, L, fits, a1, n1;
+  int pad_[3];
+  long long r[5];
+};
+static_assert(sizeof(ExpStageMeta) <= 128, "stage meta must fit its 128-byte slot");
+
+__device__ __forceinline__ double mutant_rt(int base, double t, double b, const double (&p)[5], double F) {
+  switch (base) {
+    case BASE_BEST1: return mutant<BASE_BEST1>(t, b, p, F);
+    case BASE_RAND1: return mutant<BASE_RAND1>(t, b, p, F);
+    case BASE_RANDTOBEST1: return mutant<BASE_RANDTOBEST1>(t, b, p, F);
+    case BASE_BEST2: return mutant<BASE_BEST2>(t, b, p, F);
+    default: return mutant<BASE_RAND2>(t, b, p, F);
+  }
+}
+
+// donors + start index for a run-time donor count; collective over the calling warp, same
+// results as draw_donors<K>
+__device__ __forceinline__ void draw_donors_warp_rt(const StepParams& P, int kdon, int64_t c, int lane, int64_t (&r)[5],
+                                                    int* nstart) {
+  if (P.replay) {
+#pragma unroll
+    for (int j = 0; j < 5; ++j) r[j] = (j < kdon) ? (int64_t)__ldg(P.r_donors + c * 5 + j) : 0;
+    *nstart = __ldg(P.r_nstart + c);
+    return;
+  }
+  const u32x4 v = philox4x32_10((uint32_t)lane, (uint32_t)(P.global_offset + c), P.generation, STREAM_DONORS, P.key0, P.key1);
+  const uint64_t even = ((uint64_t)v.x << 32) | v.y, odd = ((uint64_t)v.z << 32) | v.w;
+  uint64_t w[6];
+#pragma unroll
+  for (int b = 0; b < 3; ++b) {
+    w[2 * b] = __shfl_sync(0xffffffffu, even, b);
+    w[2 * b + 1] = __shfl_sync(0xffffffffu, odd, b);
+  }
+#pragma unroll
+  for (int j = 0; j < 5; ++j) r[j] = 0;
+  switch (kdon) {
+    case 2: resolve_donors<2>(w, c, P.np, P.dim, r, nstart); break;
+    case 3: resolve_donors<3>(w, c, P.np, P.dim, r, nstart); break;
+    case 4: resolve_donors<4>(w, c, P.np, P.dim, r, nstart); break;
+    default: resolve_donors<5>(w, c, P.np, P.dim, r, nstart); break;
+  }
+}
+
+// requires: dim even (rows are 16-byte multiples), cap even, MODE_STEP.  blockDim = groups * GW * 32 <= MAXT.
+template <int COST, int GW, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1)
+    de_step_exp_tma_kernel(const __grid_constant__ StepParams P, int stages, int cap, int base, int kdon) {
+  if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[kTmaMaxGroups * kTmaMaxStages];
+  __shared__ double s_scratch[kTmaMaxGroups * 16];
+  __shared__ double sh_e[kTmaMaxGroups];
+  __shared__ int64_t sh_i[kTmaMaxGroups];
+  __shared__ unsigned long long sh_ninf[kTmaMaxGroups], sh_nacc[kTmaMaxGroups];
+
+  const int D = P.dim;
+  const unsigned row_bytes = (unsigned)D * 8u;
+  const size_t row_stride = ((size_t)row_bytes + 127) & ~(size_t)127;  // keep every buffer 128-B aligned
+  const size_t seg_stride = (size_t)cap * 8u;                           // one donor's (or the undo) buffer
+  const size_t stage_stride = (row_stride + (size_t)(kdon + 1) * seg_stride + 128 + 127) & ~(size_t)127;
+  constexpr int gthreads = GW * 32;
+  const int group = threadIdx.x / gthreads;
+  const int ngroups = blockDim.x / gthreads;
+  const int tig = threadIdx.x - group * gthreads;
+  const int lane = threadIdx.x & 31;
+  const bool leader = (tig == 0);
+  const Group<GW> grp = {tig, tig >> 5, lane, 1 + group, s_scratch + group * 16};
+  const bool needs_best = (base == BASE_BEST1 || base == BASE_RANDTOBEST1 || base == BASE_BEST2);
+
+  double* s_best = reinterpret_cast<double*>(smem_raw);
+  unsigned char* s_ring = smem_raw + row_stride + (size_t)group * stages * stage_stride;
+  uint64_t* bars = s_bar + group * kTmaMaxStages;
+
+  if (needs_best)
+    for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
+  if (leader) {
+    for (int s = 0; s < stages; ++s) mbar_init(bars + s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int64_t g0 = (int64_t)blockIdx.x * ngroups + group;
+  const int64_t ng = (int64_t)gridDim.x * ngroups;
+
+  // stage layout: [row][undo cap][donor 0 cap]...[donor k-1 cap][meta]
+  auto stage_row = [&](int s) { return reinterpret_cast<double*>(s_ring + (size_t)s * stage_stride); };
+  auto stage_undo = [&](int s) { return reinterpret_cast<double*>(s_ring + (size_t)s * stage_stride + row_stride); };
+  auto stage_don = [&](int s, int j) {
+    return reinterpret_cast<double*>(s_ring + (size_t)s * stage_stride + row_stride + (size_t)(1 + j) * seg_stride);
+  };
+  auto stage_meta = [&](int s) {
+    return reinterpret_cast<ExpStageMeta*>(s_ring + (size_t)s * stage_stride + row_stride + (size_t)(kdon + 1) * seg_stride);
+  };
+
+  // Draws of candidate c and its loads into stage s.  Called by the whole leader WARP of the group
+  // (tig < 32): the draws are collective, lane 0 loads the parent row, lanes 1..k / 9..8+k the first /
+  // wrapped segment of donor lane-1 / lane-9.
+  auto issue = [&](int64_t c, int s) {
+    int64_t r[5];
+    int nstart;
+    draw_donors_warp_rt(P, kdon, c, lane, r, &nstart);
+    const int L = P.replay ? exp_length_replay(P.r_uni + c * (int64_t)(D + 1), D, P.CR, lane)
+                           : exp_length_philox(P.key0, P.key1, P.generation, (uint32_t)(P.global_offset + c), D, P.thr, lane);
+    // 16-byte aligned cover of the window [nstart, nstart+L) mod D: [a1, a1+n1) and, wrapped, [0, n2)
+    int a1 = nstart & ~1;
+    const int end = nstart + L;
+    int n1 = (end < D ? ((end + 1) & ~1) : D) - a1;
+    int n2 = (end > D) ? ((end - D + 1) & ~1) : 0;
+    if (L >= D) {  // the whole row
+      a1 = 0;
+      n1 = D;
+      n2 = 0;
+    }
+    const bool fits = (L > 0) && (n1 + n2 <= cap);
+    uint64_t* bar = bars + s;
+    if (leader) {
+      ExpStageMeta* m = stage_meta(s);
+      m->nstart = nstart;
+      m->L = L;
+      m->fits = fits ? 1 : 0;
+      m->a1 = a1;
+      m->n1 = n1;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) m->r[j] = r[j];
+      mbar_expect_tx(bar, row_bytes + (fits ? (unsigned)(kdon * (n1 + n2)) * 8u : 0u));
+      bulk_g2s(stage_row(s), P.pop_cur + c * D, row_bytes, bar);
+    }
+    __syncwarp();
+    if (fits) {
+      const int j1 = lane - 1, j2 = lane - 9;
+      if (j1 >= 0 && j1 < kdon) {
+        const int64_t rj = (j1 == 0) ? r[0] : (j1 == 1) ? r[1] : (j1 == 2) ? r[2] : (j1 == 3) ? r[3] : r[4];
+        bulk_g2s(stage_don(s, j1), P.pop_cur + rj * D + a1, (unsigned)n1 * 8u, bar);
+      }
+      if (n2 > 0 && j2 >= 0 && j2 < kdon) {
+        const int64_t rj = (j2 == 0) ? r[0] : (j2 == 1) ? r[1] : (j2 == 2) ? r[2] : (j2 == 3) ? r[3] : r[4];
+        bulk_g2s(stage_don(s, j2) + n1, P.pop_cur + rj * D, (unsigned)n2 * 8u, bar);
+      }
+    }
+  };
+
+  if (tig < 32) {
+    for (int s = 0; s < stages; ++s) {
+      const int64_t c = g0 + (int64_t)s * ng;
+      if (c < P.np) issue(c, s);
+    }
+  }
+
+  double g_best_e = CUDART_INF;
+  int64_t g_best_idx = INT64_MAX;
+  unsigned long long g_ninf = 0, g_nacc = 0;
+  const bool uni_b = P.bounds_uniform != 0;
+  // rows of this generation are known to lie inside the strict range: only the window can leave it
+  const bool window_only = (P.bounds_mode == BOUNDS_NONE) || (P.rows_in_range != 0);
+
+  int s = 0;
+  unsigned parity = 0;
+  for (int64_t c = g0; c < P.np; c += ng) {
+    double* s_row = stage_row(s);
+    double* s_undo = stage_undo(s);
+    const ExpStageMeta* meta = stage_meta(s);
+    const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
+
+    mbar_wait(bars + s, parity);
+    const int nstart = meta->nstart, L = meta->L, a1 = meta->a1, n1 = meta->n1;
+    const bool fits = meta->fits != 0;
+
+    // ---- trial vector in place (strategy.py:48-56): window element w is dimension (nstart + w) mod D
+    bool oob = false;
+    for (int w = tig; w < L; w += gthreads) {
+      int i = nstart + w;
+      if (i >= D) i -= D;
+      const double t = s_row[i];
+      double p[5] = {0., 0., 0., 0., 0.};
+      if (fits) {
+        const int off = (i >= a1) ? (i - a1) : (n1 + i);
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (j < kdon) p[j] = stage_don(s, j)[off];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (j < kdon) p[j] = __ldg(P.pop_cur + meta->r[j] * D + i);
+      }
+      double x = mutant_rt(base, t, needs_best ? s_best[i] : 0.0, p, P.F);
+      if (window_only && P.bounds_mode != BOUNDS_NONE) {
+        const double l = uni_b ? P.lo_s : __ldg(P.lo + i);
+        const double h = uni_b ? P.hi_s : __ldg(P.hi + i);
+        if (P.bounds_mode == BOUNDS_CLAMP) {
+          x = (x > l) ? x : l;  // python max(lo, x)
+          x = (x < h) ? x : h;  // python min(hi, x)
+        } else {
+          oob |= (x < l) || (x > h);
+        }
+      }
+      if (fits) s_undo[w] = t;
+      s_row[i] = x;
+    }
+    if (!window_only) {
+      // rows this context has not checked against the range: the reference clamps / tests every
+      // element of the trial, untouched ones included
+      group_sync(grp);
+      for (int i = tig; i < D; i += gthreads) {
+        double x = s_row[i];
+        const double l = uni_b ? P.lo_s : __ldg(P.lo + i);
+        const double h = uni_b ? P.hi_s : __ldg(P.hi + i);
+        if (P.bounds_mode == BOUNDS_CLAMP) {
+          x = (x > l) ? x : l;
+          x = (x < h) ? x : h;
+          s_row[i] = x;
+        } else {
+          oob |= (x < l) || (x > h);
+        }
+      }
+    }
+    oob = group_any(grp, oob);  // also the barrier that publishes the trial vector to the group
+
+    double E = CUDART_INF;
+    if (!oob) E = group_cost<COST, GW>(grp, s_row, D, P.cost);
+    E = dadd(E, group_penalty(grp, s_row, D, P.pen));
+
+    if (P.cap_trial != nullptr) {
+      for (int i = tig; i < D; i += gthreads) P.cap_trial[c * D + i] = s_row[i];
+      if (leader) P.cap_energy[c] = E;
+    }
+
+    const bool acc = E < e_old;
+    if (!acc) {
+      // every thread has read the trial (costs without a group reduction and the capture end
+      // without a barrier) before a rejected one is undone
+      if (COST == COST_CORANA || COST == COST_ZIMMERMANN || P.cap_trial != nullptr) group_sync(grp);
+      // ---- rejected: put the parent back (:603-609 keeps the old row)
+      if (!window_only && P.bounds_mode == BOUNDS_CLAMP) {
+        for (int i = tig; i < D; i += gthreads) s_row[i] = __ldg(P.pop_cur + c * D + i);
+      } else {
+        for (int w = tig; w < L; w += gthreads) {
+          int i = nstart + w;
+          if (i >= D) i -= D;
+          s_row[i] = fits ? s_undo[w] : __ldg(P.pop_cur + c * D + i);
+        }
+      }
+    }
+    // generic-proxy writes of the row -> visible to the async proxy; all reads of this stage done
+    fence_proxy_async();
+    group_sync(grp);
+    if (acc) {
+      ++g_nacc;
+      if (E < g_best_e) {
+        g_best_e = E;
+        g_best_idx = c;
+      }
+    }
+    if (isinf(E)) ++g_ninf;
+    if (tig < 32) {
+      if (leader) {
+        bulk_s2g(P.pop_next + c * D, s_row, row_bytes);
+        bulk_commit();
+        P.e_next[c] = acc ? E : e_old;
+        bulk_wait_read0();  // the store has finished reading the stage
+      }
+      __syncwarp();
+      // refill this stage with the row it serves next
+      const int64_t cn = c + (int64_t)stages * ng;
+      if (cn < P.np) issue(cn, s);
+    }
+    if (++s == stages) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  if (leader) {
+    bulk_wait_all0();
+    sh_e[group] = g_best_e;
+    sh_i[group] = g_best_idx;
+    sh_ninf[group] = g_ninf;
+    sh_nacc[group] = g_nacc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double be = sh_e[0];
+    int64_t bi = sh_i[0];
+    unsigned long long ni = sh_ninf[0], na = sh_nacc[0];
+    for (int w = 1; w < ngroups; ++w) {
+      if (sh_e[w] < be || (sh_e[w] == be && sh_i[w] < bi)) {
+        be = sh_e[w];
+        bi = sh_i[w];
+      }
+      ni += sh_ninf[w];
+      na += sh_nacc[w];
+    }
+    P.part_e[blockIdx.x] = be;
+    P.part_idx[blockIdx.x] = bi;
+    P.part_ninf[blockIdx.x] = ni;
+    P.part_nacc[blockIdx.x] = na;
+  }
+}
+
+}  // namespace mb2

@@ -269,6 +269,12 @@ class DeviceEngine(object):
         check(lib.mb2_launch_info(self._ctx, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
         return g.value, b.value, s.value
 
+    KERNEL_FAMILIES = ('none', 'warp_per_row', 'tma_bin', 'tma_exp', 'rows', 'rows_per_warp', 'thread_per_row', 'dmma', 'islands')
+
+    def kernel_family(self):
+        """kernel family of the last fused launch (mb2_kernel_family)"""
+        return self.KERNEL_FAMILIES[int(lib.mb2_kernel_family(self._ctx))]
+
     def launch_count(self):
         return int(lib.mb2_launch_count(self._ctx))
 
