@@ -323,12 +323,14 @@ bool exp_tma_geometry(int dim, int k, double CR, int* groups, int* gwarps, int* 
     if (row + 2 * stage > budget) return false;
   }
   const size_t slots = (budget - row) / stage;  // (group, stage) buffers that fit on one SM
-  int gw = 1;
-  while (gw < 8 && (gw * 2) * 32 * 8 <= dim) gw <<= 1;  // about 8 dimensions per thread
-  int g = kTmaMaxThreads / (gw * 32);
-  if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
+  // B200 sweep at D=1024 (profiles/README.md): rows in flight matter most -- 15 groups x 2 warps x 1 stage
+  // 0.210 ms, 8 groups x 4 warps x 2 stages 0.301 ms.  As many groups as fit, then >= 16 dimensions per thread.
+  int g = (int)slots;
   if (g > kTmaMaxGroups) g = kTmaMaxGroups;
-  if ((size_t)g > slots) g = (int)slots;
+  int gw = 1;
+  while (gw < 8 && (gw * 2) * 32 * 16 <= dim && (g > 15 ? 15 : g) * (gw * 2) * 32 <= kTmaMaxThreads) gw <<= 1;
+  if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
+  if (g * gw * 32 > kTmaMaxThreads) g = kTmaMaxThreads / (gw * 32);
   int st = (int)(slots / g);
   if (st > kTmaMaxStages) st = kTmaMaxStages;
   const int eg = env_int("MB2_XTMA_GROUPS", 0), ew = env_int("MB2_XTMA_GWARPS", 0), es = env_int("MB2_XTMA_STAGES", 0);
@@ -432,7 +434,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
-  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 && !datafit && !separable &&
+  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 && !datafit &&
       !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
   // the other strategies read a short window of the donors: K2e keeps long rows in a TMA ring

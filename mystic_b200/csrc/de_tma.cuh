@@ -43,6 +43,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity), "r"(MB2_TMA_WAIT_HINT_NS)
       : "memory");
 }
+// A group's wait for its stage: with MB2_TMA_LEADER_WAIT the group's first warp alone polls the
+// mbarrier and the other warps block on the group's named barrier (bar.sync does not issue while it
+// waits; a try_wait loop does).  The barrier orders the leader's acquire before the others' reads.
+#ifndef MB2_TMA_LEADER_WAIT
+#define MB2_TMA_LEADER_WAIT 1
+#endif
+template <int GW>
+__device__ __forceinline__ void group_wait_stage(const Group<GW>& g, uint64_t* bar, unsigned parity) {
+  if (GW == 1 || !MB2_TMA_LEADER_WAIT) {
+    mbar_wait(bar, parity);
+  } else {
+    if (g.wig == 0) mbar_wait(bar, parity);
+    group_sync(g);
+  }
+}
 // global -> shared bulk copy, completion counted in bytes on `bar` (size multiple of 16, 16-B aligned)
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     const uint32_t cand_g = (uint32_t)(P.global_offset + c);
     const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
 
-    mbar_wait(bars + s, parity);
+    group_wait_stage(grp, bars + s, parity);
     const int nstart = s_nstart[group * kTmaMaxStages + s];
 
     // ---- trial vector (strategy.py:77-85), two conflict-free double2 chunks per thread per trip:

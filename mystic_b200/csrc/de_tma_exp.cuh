@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     const ExpStageMeta* meta = stage_meta(s);
     const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
 
-    mbar_wait(bars + s, parity);
+    group_wait_stage(grp, bars + s, parity);
     const int nstart = meta->nstart, L = meta->L, a1 = meta->a1, n1 = meta->n1;
     const bool fits = meta->fits != 0;
 

@@ -7,6 +7,7 @@ typedef void (*TmaKernel)(const StepParams, int);
 
 template <int GW>
 static TmaKernel tma_cost(int cost) {
+  if (cost >= MB2_COST_SPHERE && cost <= MB2_COST_POWERS) return de_step_best1bin_tma_kernel<COST_SEPARABLE, GW, 1024>;
   switch (cost) {
     case MB2_COST_ROSEN: return de_step_best1bin_tma_kernel<COST_ROSEN, GW, 1024>;
     case MB2_COST_CORANA: return de_step_best1bin_tma_kernel<COST_CORANA, GW, 1024>;
