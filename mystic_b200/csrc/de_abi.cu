@@ -20,6 +20,7 @@
 #include "de_small.cuh"
 #include "de_subwarp.cuh"
 #include "de_rows.cuh"
+#include "de_rows_bulk.cuh"
 
 using namespace mb2;
 
@@ -220,6 +221,9 @@ ThreadRowKernel get_subwarp_kernel(int cost, int lanes_per_row, bool vec);
 ThreadRowKernel get_rows_kernel_rosen(int lanes_per_row, int ndonors);
 ThreadRowKernel get_rows_kernel_corana(int lanes_per_row, int ndonors);
 ThreadRowKernel get_rows_kernel_griewangk(int lanes_per_row, int ndonors);
+ThreadRowKernel get_rows_bulk_kernel_rosen(int lanes_per_row, int ndonors);
+ThreadRowKernel get_rows_bulk_kernel_corana(int lanes_per_row, int ndonors);
+ThreadRowKernel get_rows_bulk_kernel_griewangk(int lanes_per_row, int ndonors);
 }  // namespace mb2
 namespace {
 
@@ -348,6 +352,39 @@ bool exp_tma_geometry(int dim, int k, double CR, int* groups, int* gwarps, int* 
   return true;
 }
 
+// Geometry of K2f (de_rows_bulk.cuh): warps per CTA (one CTA per SM), stages per warp, slots (4-element
+// chunks) of a stage's donor pools = what shared memory is left after the row tiles.  False when the
+// pools would be too small to hold typical windows.
+bool rows_bulk_geometry(int dim, int lpr, int k, int* warps, int* stages, int* pool, int* smem) {
+  const int rpw = 32 / lpr;
+  const size_t best = (((size_t)dim * 8) + 127) & ~(size_t)127;
+  const size_t rows = (size_t)rpw * (dim + 2) * 8, meta = (size_t)rpw * sizeof(BulkRowMeta);
+  const size_t budget = 220 * 1024 - best;
+  // B200 sweep at C4 (profiles/README.md): the step is bound by the warps' own dependent chains, so the
+  // number of resident warps decides (8 warps 0.53 ms, 12: 0.40, 16: 0.35-0.37, 20: 0.34, 24: 0.32); a
+  // second stage per warp does not pay for the pool space it takes.
+  int w = env_int("MB2_RB_WARPS", kBulkRowsMaxWarps), st = env_int("MB2_RB_STAGES", 1);
+  if (w < 1 || w > kBulkRowsMaxWarps) w = kBulkRowsMaxWarps;
+  if (st < 1 || st > kBulkRowsMaxStages) st = 1;
+  const size_t avail = (budget / w) & ~(size_t)127;
+  const size_t fixed = (size_t)st * (rows + meta + 128) + 128;
+  if (avail <= fixed) return false;
+  int slots = (int)((avail - fixed) / (32 * (size_t)(1 + st * k)));
+  const int all = rpw * (dim >> 2);  // every chunk of every row
+  if (slots > all) slots = all;
+  const int es = env_int("MB2_RB_POOL", 0);
+  if (es >= 1 && es < slots) slots = es;
+  if (slots < 2 * rpw && es == 0) return false;
+  const size_t pool_b = (size_t)slots * 32;
+  const size_t stage_b = (rows + (size_t)k * pool_b + meta + 127) & ~(size_t)127;
+  const size_t warp_b = ((pool_b + 127) & ~(size_t)127) + (size_t)st * stage_b;
+  *warps = w;
+  *stages = st;
+  *pool = slots;
+  *smem = (int)(best + (size_t)w * warp_b);
+  return true;
+}
+
 int ensure_parts(mb2_ctx* c, int n);
 void fill_params(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out, int64_t np,
                  StepParams* out);
@@ -412,7 +449,8 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   // MB2_SMALL_KERNEL: 3 = K2d rows kernel where it applies, else as 1 (default); 1 = several rows
   // per warp (generic); 2 = one thread per row; 0 = none of them
   const int small_kind = env_int("MB2_SMALL_KERNEL", 3);
-  ThreadRowKernel kw = nullptr, kr = nullptr;
+  ThreadRowKernel kw = nullptr, kr = nullptr, kb = nullptr;
+  int bw = 0, bst = 0, bpool = 0, bsmem = 0;
   int lpr = 4;
   while (lpr < 32 && lpr * 8 < c->dim) lpr <<= 1;  // about 8 dimensions per lane
   s = c->sinfo;  // the short-row kernels take the strategy at run time in every mode
@@ -422,6 +460,15 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
       if (c->cost == MB2_COST_ROSEN) kr = get_rows_kernel_rosen(lpr, s.k);
       else if (c->cost == MB2_COST_CORANA) kr = get_rows_kernel_corana(lpr, s.k);
       else if (c->cost == MB2_COST_GRIEWANGK) kr = get_rows_kernel_griewangk(lpr, s.k);
+    }
+    // exponential crossover over rows known to lie in the strict range: K2f moves the same tiles with the
+    // bulk-copy engine, a stage ahead of the arithmetic
+    if (kr != nullptr && mode == MODE_STEP && s.xover == XOVER_EXP && env_int("MB2_ROWS_BULK", 1) != 0 &&
+        (c->bounds_mode == BOUNDS_NONE || (in_rows == c->pop[c->cur] && c->rows_in_range)) &&
+        rows_bulk_geometry(c->dim, lpr, s.k, &bw, &bst, &bpool, &bsmem)) {
+      if (c->cost == MB2_COST_ROSEN) kb = get_rows_bulk_kernel_rosen(lpr, s.k);
+      else if (c->cost == MB2_COST_CORANA) kb = get_rows_bulk_kernel_corana(lpr, s.k);
+      else if (c->cost == MB2_COST_GRIEWANGK) kb = get_rows_bulk_kernel_griewangk(lpr, s.k);
     }
     if (kr != nullptr) kw = kr;
     else if (small_kind == 2)
@@ -453,6 +500,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     smem = (int)(sizeof(double) * (size_t)kChebWarps * (kChebBatch * c->dim + kChebBatch));
     CUDA_TRY(cudaFuncSetAttribute(kc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kc, wpc * 32, smem));
+  } else if (kb != nullptr) {
+    wpc = bw;
+    rows_per_cta = bw * (32 / lpr);
+    smem = bsmem;
+    CUDA_TRY(cudaFuncSetAttribute(kb, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb, wpc * 32, smem));
   } else if (kr != nullptr) {
     wpc = kRowsWarps;
     rows_per_cta = kRowsWarps * (32 / lpr);
@@ -502,10 +555,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->wpc = wpc;
   c->grid = (int)grid;
   c->smem = smem;
-  c->family = kc ? MB2_KERNEL_DMMA : kr ? MB2_KERNEL_ROWS : kw ? MB2_KERNEL_ROWS_PER_WARP : ks ? MB2_KERNEL_THREAD_PER_ROW
+  c->family = kc ? MB2_KERNEL_DMMA : kb ? MB2_KERNEL_ROWS_BULK : kr ? MB2_KERNEL_ROWS : kw ? MB2_KERNEL_ROWS_PER_WARP : ks ? MB2_KERNEL_THREAD_PER_ROW
               : kt ? MB2_KERNEL_TMA_BIN : kx ? MB2_KERNEL_TMA_EXP : MB2_KERNEL_WARP_PER_ROW;
   if (kc != nullptr)
     kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (kb != nullptr)
+    kb<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, bst, bpool);
   else if (kw != nullptr)
     kw<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (ks != nullptr)

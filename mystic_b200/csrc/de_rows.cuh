@@ -264,10 +264,11 @@ __device__ __forceinline__ void rows_load_donors(const double* __restrict__ pop,
   }
 }
 
-// mutate the crossed elements of chunk q of the trial tile, apply the bounds to them
+// mutate the crossed elements of chunk q of the trial tile, apply the bounds to them; the parent's
+// chunk goes to the 4 doubles at `undo_chunk` (nullptr: the caller restores a rejected trial itself)
 template <int K>
 __device__ __forceinline__ bool rows_mutate_chunk(const StepParams& P, int base, int xover, const RowDraws<K>& d, int64_t cc,
-                                                  int q, const DonorChunk<K>& dc, const double* s_best, double* t_trial, double* t_undo) {
+                                                  int q, const DonorChunk<K>& dc, const double* s_best, double* t_trial, double* undo_chunk) {
   const int D = P.dim;
   const int i0 = q << 2;
   bool cross[4];
@@ -297,8 +298,10 @@ __device__ __forceinline__ bool rows_mutate_chunk(const StepParams& P, int base,
   const double2 xa = *reinterpret_cast<const double2*>(t_trial + i0);
   const double2 xb = *reinterpret_cast<const double2*>(t_trial + i0 + 2);
   const double x[4] = {xa.x, xa.y, xb.x, xb.y};
-  *reinterpret_cast<double2*>(t_undo + i0) = xa;  // the parent's chunk, for a rejected trial
-  *reinterpret_cast<double2*>(t_undo + i0 + 2) = xb;
+  if (undo_chunk != nullptr) {  // the parent's chunk, for a rejected trial
+    *reinterpret_cast<double2*>(undo_chunk) = xa;
+    *reinterpret_cast<double2*>(undo_chunk + 2) = xb;
+  }
   double bst[4] = {0.0, 0.0, 0.0, 0.0};
   if (K != 3 && K != 5) {  // Best1, RandToBest1, Best2 read bestSolution
     const double2 ba = *reinterpret_cast<const double2*>(s_best + i0);
@@ -494,14 +497,14 @@ __global__ void __launch_bounds__(kRowsWarps * 32, MB2_ROWS_MINBLOCKS)
     if (step) {
 #pragma unroll
       for (int u = 0; u < CPT; ++u) {
-        if (sub + u * LPR < nq) oob |= rows_mutate_chunk<K>(P, base, xover, dr, cc, qs[u], dc[u], s_best, t_row, t_undo);
+        if (sub + u * LPR < nq) oob |= rows_mutate_chunk<K>(P, base, xover, dr, cc, qs[u], dc[u], s_best, t_row, t_undo + (qs[u] << 2));
       }
       for (int w = sub + CPT * LPR; w < nq; w += LPR) {  // long windows: the remaining chunks
         int q = q0 + w;
         if (q >= NQ) q -= NQ;
         DonorChunk<K> dx;
         rows_load_donors<K>(P.pop_cur, dr, D, q << 2, dx);
-        oob |= rows_mutate_chunk<K>(P, base, xover, dr, cc, q, dx, s_best, t_row, t_undo);
+        oob |= rows_mutate_chunk<K>(P, base, xover, dr, cc, q, dx, s_best, t_row, t_undo + (q << 2));
       }
     }
     // any lane of the group out of range?

@@ -70,6 +70,126 @@ __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ 
   }
 }
 
+
+// ---- the same pattern through the bulk-copy engine (cp.async.bulk, SASS UBLKCP): a warp owns `ST` stages
+// of 8 rows; one warp instruction issues the 8 parent copies (lanes 0..7) and the 8*K donor-segment copies
+// (lanes 8..8+8K-1) of a stage onto its mbarrier, the rows leave with 8 bulk stores.  No registers are held
+// while the data flies and the next stage is requested before this one is touched.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 1000000;\n@!p bra WAIT_LOOP;\n}\n" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+template <int K, int ST, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) bulk_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t np, int D,
+                                                          int seg, uint32_t salt) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[WARPS * ST];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned rowb = (unsigned)D * 8u, segb = (unsigned)seg * 32u;
+  const size_t stage_bytes = 8 * (size_t)rowb + 8 * (size_t)K * segb;
+  unsigned char* my = smem + (size_t)warp * ST * stage_bytes;
+  uint64_t* bar = bars + warp * ST;
+  if (lane == 0)
+    for (int s = 0; s < ST; ++s) mbar_init(bar + s, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+  const int NQ = D >> 2;
+  auto issue = [&](int64_t ch, int s) {
+    unsigned char* st = my + (size_t)s * stage_bytes;
+    if (lane == 0) mbar_expect_tx(bar + s, (unsigned)stage_bytes);
+    __syncwarp();
+    if (lane < 8) {
+      bulk_g2s(st + lane * rowb, in + (ch * 8 + lane) * D, rowb, bar + s);
+    } else if (lane < 8 + 8 * K) {
+      const int row = (lane - 8) & 7, j = (lane - 8) >> 3;
+      const int64_t c = ch * 8 + row;
+      const uint32_t h = mix((uint32_t)c * 0x9E3779B9u + salt);
+      int q0 = (int)(h % (uint32_t)NQ);
+      if (q0 + seg > NQ) q0 = NQ - seg;  // no wrap in the probe
+      const int64_t r = (int64_t)(mix(h + 0x51ED270Bu * (j + 1)) % (uint32_t)np);
+      bulk_g2s(st + 8 * rowb + (size_t)(j * 8 + row) * segb, in + r * D + 4 * q0, segb, bar + s);
+    }
+  };
+  int64_t nch = np / 8;
+  for (int s = 0; s < ST; ++s)
+    if (gw + s * nw < nch) issue(gw + s * nw, s);
+  int s = 0;
+  unsigned parity = 0;
+  for (int64_t ch = gw; ch < nch; ch += nw) {
+    unsigned char* st = my + (size_t)s * stage_bytes;
+    mbar_wait(bar + s, parity);
+    // touch: add the first donor element of each segment to the first element of its row
+    if (K > 0 && lane < 8) {
+      double a = 0.0;
+      for (int j = 0; j < K; ++j) a += *reinterpret_cast<double*>(st + 8 * rowb + (size_t)(j * 8 + lane) * segb);
+      *reinterpret_cast<double*>(st + lane * rowb) += a;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane < 8) {
+      bulk_s2g(out + (ch * 8 + lane) * D, st + lane * rowb, rowb);
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    __syncwarp();
+    if (ch + (int64_t)ST * nw < nch) issue(ch + (int64_t)ST * nw, s);
+    if (++s == ST) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  if (lane < 8) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+template <int K, int ST, int WARPS>
+static void run_bulk(const double* in, double* out, int64_t np, int D, int seg) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const size_t smem = (size_t)WARPS * ST * (8 * (size_t)D * 8 + 8 * (size_t)K * seg * 32);
+  cudaFuncSetAttribute(bulk_kernel<K, ST, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bulk_kernel<K, ST, WARPS>, WARPS * 32, smem);
+  if (occ < 1) {
+    printf("{\"bulk\": true, \"error\": \"does not fit\", \"smem\": %zu}\n", smem);
+    return;
+  }
+  const int grid = 148 * occ;
+  float best = 1e30f;
+  for (int rep = 0; rep < 12; ++rep) {
+    cudaEventRecord(e0);
+    bulk_kernel<K, ST, WARPS><<<grid, WARPS * 32, smem>>>(in, out, np, D, seg, 17u * rep + 1u);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  const double bytes = (double)np * (16.0 * D + (double)K * seg * 32.0);
+  printf("{\"bulk\": true, \"donors\": %d, \"chunks_per_donor\": %d, \"stages\": %d, \"warps\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"requested_GB\": %.4f, \"GBps\": %.1f}\n",
+         K, seg, ST, WARPS, occ, best, bytes / 1e9, bytes / 1e6 / best);
+}
+
 template <int K>
 static void run(const double* in, double* out, int64_t np, int D, int seg, int ctas_per_sm) {
   cudaEvent_t e0, e1;
@@ -107,6 +227,16 @@ int main(int argc, char** argv) {
     run<2>(a, b, np, D, 4, occ);
     run<5>(a, b, np, D, 4, occ);
   }
+  run_bulk<0, 2, 8>(a, b, np, D, 0);
+  run_bulk<0, 4, 8>(a, b, np, D, 0);
+  run_bulk<0, 2, 16>(a, b, np, D, 0);
+  run_bulk<3, 1, 8>(a, b, np, D, 3);
+  run_bulk<3, 2, 8>(a, b, np, D, 3);
+  run_bulk<3, 3, 8>(a, b, np, D, 3);
+  run_bulk<3, 2, 4>(a, b, np, D, 3);
+  run_bulk<3, 2, 16>(a, b, np, D, 3);
+  run_bulk<3, 4, 4>(a, b, np, D, 3);
+  run_bulk<2, 2, 8>(a, b, np, D, 4);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) {
     printf("error: %s\n", cudaGetErrorString(e));
