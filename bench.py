@@ -85,9 +85,10 @@ def device_cost(w):
 # workload's full per-GPU size, from one `ncu --set full` capture each (summaries under profiles/)
 NCU_TRAFFIC = {
     'c2': (1.444322e9 + 0.513861e9, 'profiles/r1_c2_tma_kernel_ncu_full_summary.csv'),
+    'x2': (0.567731e9 + 0.493002e9, 'profiles/r1_x2_exp_tma_kernel_ncu_full_summary.csv'),
     'c3': (0.265026e9 + 0.037010e9, 'profiles/r1_c3_kernel_ncu_full_summary.csv'),
     'f2': (0.258753e9 + 0.034031e9, 'profiles/r1_f2_polyfit_dmma_ncu_full_summary.csv'),
-    'c4': (1.071825e9 + 0.497635e9, 'profiles/r1_c4_rows_kernel_ncu_full_summary.csv'),
+    'c4': (1.026244e9 + 0.512175e9, 'profiles/r1_c4_rows_bulk_kernel_ncu_full_summary.csv'),
     'c5': (12.791601e9 + 4.323565e9, 'profiles/r1_c5_kernel_ncu_full_summary.csv'),
 }
 
