@@ -358,7 +358,7 @@ bool exp_tma_geometry(int dim, int k, double CR, int* groups, int* gwarps, int* 
 bool rows_bulk_geometry(int dim, int lpr, int k, int* warps, int* stages, int* pool, int* smem) {
   const int rpw = 32 / lpr;
   const size_t best = (((size_t)dim * 8) + 127) & ~(size_t)127;
-  const size_t rows = (size_t)rpw * (dim + 2) * 8, meta = (size_t)rpw * sizeof(BulkRowMeta);
+  const size_t rows = (size_t)rpw * dim * 8, meta = (size_t)rpw * sizeof(BulkRowMeta);
   const size_t budget = 220 * 1024 - best;
   // B200 sweep at C4 (profiles/README.md): the step is bound by the warps' own dependent chains, so the
   // number of resident warps decides (8 warps 0.53 ms, 12: 0.40, 16: 0.35-0.37, 20: 0.34, 24: 0.32); a

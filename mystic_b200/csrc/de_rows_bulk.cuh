@@ -52,7 +52,10 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
 
   const int D = P.dim;
   const int NQ = D >> 2;
-  const int TS = D + 2;  // tile row stride (de_rows.cuh)
+  // The tile is unpadded (K2d pads its rows by 16 bytes against bank conflicts): the rows of a stage are
+  // contiguous in global memory, so ONE copy brings all parents in and ONE takes the next generation out
+  // (a copy request costs ~8 instructions of an elect loop; two-way conflicts on the 16-byte tile reads cost less)
+  const int TS = D;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpc = blockDim.x >> 5;
@@ -90,11 +93,14 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
   auto issue = [&](int64_t ch, unsigned char* st, uint64_t* bar) {
     const int64_t c = ch * RPW + grp;
     const int64_t cc = (c < P.np) ? c : (P.np - 1);  // idle groups shadow the last row
+    const int64_t left = P.np - ch * RPW;
+    const unsigned nlive = left < RPW ? (unsigned)left : (unsigned)RPW;
     RowDraws<K> dr;
     rows_draw<LPR, K>(P, XOVER_EXP, cc, sub, gbase, dr);
     const int q0 = dr.nstart >> 2;
     int nq = (dr.L > 0) ? (((dr.nstart + dr.L - 1) >> 2) - q0 + 1) : 0;
     if (nq > NQ) nq = NQ;  // a full-length window that starts inside a chunk: each chunk once
+    if (c >= P.np) nq = 0;   // idle groups mutate nothing (their tile rows hold stale data, results are discarded)
     // slots of the row in the pools: exclusive prefix sum of nq over the rows of the warp
     int incl = (sub == 0) ? nq : 0;
 #pragma unroll
@@ -105,7 +111,6 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
     int off = __shfl_sync(0xffffffffu, incl, gbase) - nq;
     const bool fits = (nq > 0) && (off + nq <= wq_cap);
     if (!fits) off = -1;
-    double* t_row = reinterpret_cast<double*>(st) + (size_t)grp * TS;
     if (sub == 0) {
       BulkRowMeta* m = reinterpret_cast<BulkRowMeta*>(st + rows_bytes + (size_t)K * pool_bytes) + grp;
       m->nstart = dr.nstart;
@@ -115,11 +120,12 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
       m->off = off;
 #pragma unroll
       for (int j = 0; j < K; ++j) m->r[j] = dr.r[j];
-      mbar_expect_tx(bar, row_bytes + (fits ? (unsigned)(K * nq) * 32u : 0u));
+      mbar_expect_tx(bar, (lane == 0 ? nlive * row_bytes : 0u) + (fits ? (unsigned)(K * nq) * 32u : 0u));
     }
     __syncwarp();
-    // one copy instruction serves the whole warp: lane 0 of a group requests the parent row, lane 1 + j the
-    // window's cover of donor j (a second instruction for the wrapped parts; further rounds when K > LPR - 1)
+    // one copy instruction serves the whole warp: lane 0 requests the stage's parent rows, lane 1 + j of a
+    // row's group the window's cover of donor j (a second instruction for the wrapped parts; further rounds
+    // when K > LPR - 1)
     const int n1 = (q0 + nq <= NQ) ? nq : (NQ - q0);  // chunks before the wrap
 #pragma unroll
     for (int jb = 0; jb < K; jb += LPR - 1) {
@@ -129,9 +135,10 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
 #pragma unroll
       for (int t = 0; t < K; ++t)
         if (t == j) rj = dr.r[t];
-      const double* src = (sub == 0) ? (P.pop_cur + cc * D) : (P.pop_cur + (int64_t)rj * D + 4 * q0);
-      double* dst = (sub == 0) ? t_row : (reinterpret_cast<double*>(st + rows_bytes + (size_t)(donor ? j : 0) * pool_bytes) + 4 * (donor ? off : 0));
-      const unsigned bytes = (sub == 0) ? (jb == 0 ? row_bytes : 0u) : (donor ? (unsigned)n1 * 32u : 0u);
+      const double* src = (lane == 0) ? (P.pop_cur + ch * RPW * D) : (P.pop_cur + (int64_t)rj * D + 4 * q0);
+      double* dst = (lane == 0) ? reinterpret_cast<double*>(st)
+                                : (reinterpret_cast<double*>(st + rows_bytes + (size_t)(donor ? j : 0) * pool_bytes) + 4 * (donor ? off : 0));
+      const unsigned bytes = (lane == 0) ? (jb == 0 ? nlive * row_bytes : 0u) : (donor ? (unsigned)n1 * 32u : 0u);
       if (bytes) bulk_g2s(dst, src, bytes, bar);
       if (__any_sync(0xffffffffu, donor && n1 < nq)) {
         if (donor && n1 < nq) bulk_g2s(dst + 4 * n1, P.pop_cur + (int64_t)rj * D, (unsigned)(nq - n1) * 32u, bar);
@@ -225,9 +232,16 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
     }
     fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk store; reads of the stage done
     __syncwarp();
-    if (sub == 0 && live) {
-      bulk_s2g(P.pop_next + c * D, t_row, row_bytes);
+    const bool whole = (ch + 1) * RPW <= P.np;  // every row of the stage is live: one store for all of them
+    if (lane == 0 && whole) {
+      bulk_s2g(P.pop_next + ch * RPW * D, st, RPW * row_bytes);
       bulk_commit();
+    }
+    if (sub == 0 && live) {
+      if (!whole) {
+        bulk_s2g(P.pop_next + c * D, t_row, row_bytes);
+        bulk_commit();
+      }
       P.e_next[c] = acc ? E : e_old;
       if (acc) {
         ++w_nacc;
