@@ -66,7 +66,11 @@ def main():
     ok = True
     for (strategy, cost, D, NP, mode, lo, hi) in [('Best1Bin', 'rosen', 64, 1000, orc.BOUNDS_CLAMP, -5., 5.),
                                                   ('RandToBest1Exp', 'griewangk', 30, 301, orc.BOUNDS_REJECT, -400., 400.),
-                                                  ('Rand1Exp', 'rosen', 9, 77, orc.BOUNDS_CLAMP, -2., 2.)]:
+                                                  ('Rand1Exp', 'rosen', 9, 77, orc.BOUNDS_CLAMP, -2., 2.),
+                                                  # sharded runs of the bulk-copy kernels: short rows (de_rows_bulk.cuh) and
+                                                  # long rows with the exchanged best member (de_tma_exp.cuh)
+                                                  ('Rand1Exp', 'corana', 64, 2003, orc.BOUNDS_CLAMP, -1000., 1000.),
+                                                  ('Best1Exp', 'rosen', 200, 303, orc.BOUNDS_CLAMP, -5., 5.)]:
         seed, gens = 0xD15C0 + D, 6
         s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=seed, distributed=True, strategy=strategy)
         if os.environ.get('MB2_EXCHANGE', 'peer') == 'peer':
