@@ -221,9 +221,10 @@ ThreadRowKernel get_subwarp_kernel(int cost, int lanes_per_row, bool vec);
 ThreadRowKernel get_rows_kernel_rosen(int lanes_per_row, int ndonors);
 ThreadRowKernel get_rows_kernel_corana(int lanes_per_row, int ndonors);
 ThreadRowKernel get_rows_kernel_griewangk(int lanes_per_row, int ndonors);
-ThreadRowKernel get_rows_bulk_kernel_rosen(int lanes_per_row, int ndonors);
-ThreadRowKernel get_rows_bulk_kernel_corana(int lanes_per_row, int ndonors);
-ThreadRowKernel get_rows_bulk_kernel_griewangk(int lanes_per_row, int ndonors);
+typedef void (*BulkRowsKernel)(const StepParams, int, const BulkRowsLayout);
+BulkRowsKernel get_rows_bulk_kernel_rosen(int lanes_per_row, int ndonors);
+BulkRowsKernel get_rows_bulk_kernel_corana(int lanes_per_row, int ndonors);
+BulkRowsKernel get_rows_bulk_kernel_griewangk(int lanes_per_row, int ndonors);
 }  // namespace mb2
 namespace {
 
@@ -355,7 +356,7 @@ bool exp_tma_geometry(int dim, int k, double CR, int* groups, int* gwarps, int* 
 // Geometry of K2f (de_rows_bulk.cuh): warps per CTA (one CTA per SM), stages per warp, slots (4-element
 // chunks) of a stage's donor pools = what shared memory is left after the row tiles.  False when the
 // pools would be too small to hold typical windows.
-bool rows_bulk_geometry(int dim, int lpr, int k, int* warps, int* stages, int* pool, int* smem) {
+bool rows_bulk_geometry(int dim, int lpr, int k, int* warps, BulkRowsLayout* L, int* smem) {
   const int rpw = 32 / lpr;
   const size_t best = (((size_t)dim * 8) + 127) & ~(size_t)127;
   const size_t rows = (size_t)rpw * dim * 8, meta = (size_t)rpw * sizeof(BulkRowMeta);
@@ -376,12 +377,17 @@ bool rows_bulk_geometry(int dim, int lpr, int k, int* warps, int* stages, int* p
   if (es >= 1 && es < slots) slots = es;
   if (slots < 2 * rpw && es == 0) return false;
   const size_t pool_b = (size_t)slots * 32;
-  const size_t stage_b = (rows + (size_t)k * pool_b + meta + 127) & ~(size_t)127;
-  const size_t warp_b = ((pool_b + 127) & ~(size_t)127) + (size_t)st * stage_b;
+  L->stages = st;
+  L->slots = slots;
+  L->best_bytes = (unsigned)best;
+  L->rows_bytes = (unsigned)rows;
+  L->pool_bytes = (unsigned)pool_b;
+  L->meta_off = (unsigned)(rows + (size_t)k * pool_b);
+  L->stage_bytes = (unsigned)((rows + (size_t)k * pool_b + meta + 127) & ~(size_t)127);
+  L->undo_bytes = (unsigned)((pool_b + 127) & ~(size_t)127);
+  L->warp_bytes = L->undo_bytes + (unsigned)st * L->stage_bytes;
   *warps = w;
-  *stages = st;
-  *pool = slots;
-  *smem = (int)(best + (size_t)w * warp_b);
+  *smem = (int)(best + (size_t)w * L->warp_bytes);
   return true;
 }
 
@@ -449,8 +455,10 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   // MB2_SMALL_KERNEL: 3 = K2d rows kernel where it applies, else as 1 (default); 1 = several rows
   // per warp (generic); 2 = one thread per row; 0 = none of them
   const int small_kind = env_int("MB2_SMALL_KERNEL", 3);
-  ThreadRowKernel kw = nullptr, kr = nullptr, kb = nullptr;
-  int bw = 0, bst = 0, bpool = 0, bsmem = 0;
+  ThreadRowKernel kw = nullptr, kr = nullptr;
+  BulkRowsKernel kb = nullptr;
+  BulkRowsLayout blay = {};
+  int bw = 0, bsmem = 0;
   int lpr = 4;
   while (lpr < 32 && lpr * 8 < c->dim) lpr <<= 1;  // about 8 dimensions per lane
   s = c->sinfo;  // the short-row kernels take the strategy at run time in every mode
@@ -465,7 +473,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     // bulk-copy engine, a stage ahead of the arithmetic
     if (kr != nullptr && mode == MODE_STEP && s.xover == XOVER_EXP && env_int("MB2_ROWS_BULK", 1) != 0 &&
         (c->bounds_mode == BOUNDS_NONE || (in_rows == c->pop[c->cur] && c->rows_in_range)) &&
-        rows_bulk_geometry(c->dim, lpr, s.k, &bw, &bst, &bpool, &bsmem)) {
+        rows_bulk_geometry(c->dim, lpr, s.k, &bw, &blay, &bsmem)) {
       if (c->cost == MB2_COST_ROSEN) kb = get_rows_bulk_kernel_rosen(lpr, s.k);
       else if (c->cost == MB2_COST_CORANA) kb = get_rows_bulk_kernel_corana(lpr, s.k);
       else if (c->cost == MB2_COST_GRIEWANGK) kb = get_rows_bulk_kernel_griewangk(lpr, s.k);
@@ -560,7 +568,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   if (kc != nullptr)
     kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (kb != nullptr)
-    kb<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, bst, bpool);
+    kb<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, blay);
   else if (kw != nullptr)
     kw<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (ks != nullptr)

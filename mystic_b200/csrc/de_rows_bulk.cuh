@@ -37,9 +37,24 @@ struct BulkRowMeta {  // one per row of a stage, written at issue time
 };
 static_assert(sizeof(BulkRowMeta) == 48, "meta slot");
 
+// shared-memory layout, computed once on the host (de_abi.cu: rows_bulk_geometry) so that the kernel reads
+// it from the constant bank instead of re-deriving it with 64-bit arithmetic inside the loop:
+// best member | per warp: undo pool, then per stage: rows, K donor pools, meta
+struct BulkRowsLayout {
+  int stages;            // stages per warp
+  int slots;             // 4-element chunks per pool
+  unsigned best_bytes;   // bestSolution [D], rounded to 128
+  unsigned rows_bytes;   // the stage's rows
+  unsigned pool_bytes;   // one pool (slots * 32)
+  unsigned meta_off;     // rows_bytes + K * pool_bytes
+  unsigned stage_bytes;  // rounded to 128
+  unsigned undo_bytes;   // the warp's undo pool, rounded to 128
+  unsigned warp_bytes;   // undo_bytes + stages * stage_bytes
+};
+
 template <int COST, int LPR, int K>
 __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
-    de_step_rows_bulk_kernel(const __grid_constant__ StepParams P, int base, int stages, int wq_cap) {
+    de_step_rows_bulk_kernel(const __grid_constant__ StepParams P, int base, const __grid_constant__ BulkRowsLayout G) {
   if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_bar[kBulkRowsMaxWarps * kBulkRowsMaxStages];
@@ -65,16 +80,11 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
   const bool needs_best = (base == BASE_BEST1 || base == BASE_RANDTOBEST1 || base == BASE_BEST2);
   const unsigned row_bytes = (unsigned)D * 8u;
 
-  // shared memory: best member | per warp: undo pool, then per stage: rows, donor pools, meta
-  const size_t best_bytes = ((size_t)D * 8 + 127) & ~(size_t)127;
-  const size_t rows_bytes = (size_t)RPW * TS * 8;
-  const size_t pool_bytes = (size_t)wq_cap * 32;
-  const size_t stage_bytes = (rows_bytes + (size_t)K * pool_bytes + RPW * sizeof(BulkRowMeta) + 127) & ~(size_t)127;
-  const size_t warp_bytes = ((pool_bytes + 127) & ~(size_t)127) + (size_t)stages * stage_bytes;
+  const int stages = G.stages, wq_cap = G.slots;
   double* s_best = reinterpret_cast<double*>(smem_raw);
-  unsigned char* w_base = smem_raw + best_bytes + (size_t)warp * warp_bytes;
+  unsigned char* w_base = smem_raw + G.best_bytes + warp * G.warp_bytes;
   double* s_undo = reinterpret_cast<double*>(w_base);
-  unsigned char* s_stages = w_base + ((pool_bytes + 127) & ~(size_t)127);
+  unsigned char* s_stages = w_base + G.undo_bytes;
   uint64_t* bars = s_bar + warp * kBulkRowsMaxStages;
 
   if (needs_best)
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
     const bool fits = (nq > 0) && (off + nq <= wq_cap);
     if (!fits) off = -1;
     if (sub == 0) {
-      BulkRowMeta* m = reinterpret_cast<BulkRowMeta*>(st + rows_bytes + (size_t)K * pool_bytes) + grp;
+      BulkRowMeta* m = reinterpret_cast<BulkRowMeta*>(st + G.meta_off) + grp;
       m->nstart = dr.nstart;
       m->L = dr.L;
       m->q0 = q0;
@@ -137,7 +147,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
         if (t == j) rj = dr.r[t];
       const double* src = (lane == 0) ? (P.pop_cur + ch * RPW * D) : (P.pop_cur + (int64_t)rj * D + 4 * q0);
       double* dst = (lane == 0) ? reinterpret_cast<double*>(st)
-                                : (reinterpret_cast<double*>(st + rows_bytes + (size_t)(donor ? j : 0) * pool_bytes) + 4 * (donor ? off : 0));
+                                : (reinterpret_cast<double*>(st + G.rows_bytes + (unsigned)(donor ? j : 0) * G.pool_bytes) + 4 * (donor ? off : 0));
       const unsigned bytes = (lane == 0) ? (jb == 0 ? nlive * row_bytes : 0u) : (donor ? (unsigned)n1 * 32u : 0u);
       if (bytes) bulk_g2s(dst, src, bytes, bar);
       if (__any_sync(0xffffffffu, donor && n1 < nq)) {
@@ -148,7 +158,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
 
   for (int s = 0; s < stages; ++s) {
     const int64_t ch = gw + (int64_t)s * nw;
-    if (ch < nchunks) issue(ch, s_stages + (size_t)s * stage_bytes, bars + s);
+    if (ch < nchunks) issue(ch, s_stages + (unsigned)s * G.stage_bytes, bars + s);
   }
 
   double w_best_e = CUDART_INF;
@@ -158,7 +168,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
   int s = 0;
   unsigned parity = 0;
   for (int64_t ch = gw; ch < nchunks; ch += nw) {
-    unsigned char* st = s_stages + (size_t)s * stage_bytes;
+    unsigned char* st = s_stages + (unsigned)s * G.stage_bytes;
     const int64_t c = ch * RPW + grp;
     const bool live = c < P.np;
     const int64_t cc = live ? c : (P.np - 1);
@@ -166,7 +176,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
     const double e_old = __ldg(P.e_cur + cc);  // in flight while the warp waits for its stage
 
     mbar_wait(bars + s, parity);
-    const BulkRowMeta* m = reinterpret_cast<const BulkRowMeta*>(st + rows_bytes + (size_t)K * pool_bytes) + grp;
+    const BulkRowMeta* m = reinterpret_cast<const BulkRowMeta*>(st + G.meta_off) + grp;
     RowDraws<K> dr;
     dr.nstart = m->nstart;
     dr.L = m->L;
@@ -186,7 +196,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
       if (fits) {
 #pragma unroll
         for (int j = 0; j < K; ++j) {
-          const double* dp = reinterpret_cast<const double*>(st + rows_bytes + (size_t)j * pool_bytes) + 4 * (off + w);
+          const double* dp = reinterpret_cast<const double*>(st + G.rows_bytes + (unsigned)j * G.pool_bytes) + 4 * (off + w);
           dc.v[j][0] = *reinterpret_cast<const double2*>(dp);
           dc.v[j][1] = *reinterpret_cast<const double2*>(dp + 2);
         }
