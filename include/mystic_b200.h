@@ -71,7 +71,19 @@ enum mb2_cost {
   MB2_COST_ACKLEY = 12,     /* models/pohlheim.py:186-204 */
   MB2_COST_STEP = 13,       /* models/dejong.py:166-192 */
   MB2_COST_MICHAL = 14,     /* models/pohlheim.py:226-240 */
-  MB2_COST_POWERS = 15      /* models/pohlheim.py:153-163 */
+  MB2_COST_POWERS = 15,     /* models/pohlheim.py:153-163 */
+  /* closed-form functions of two variables (dim must be 2) ... */
+  MB2_COST_BRANINS = 16,    /* models/pohlheim.py:261-282 */
+  MB2_COST_EASOM = 17,      /* models/pohlheim.py:303-313 */
+  MB2_COST_GOLDSTEIN = 18,  /* models/pohlheim.py:336-355 */
+  MB2_COST_PEAKS = 19,      /* models/nag.py:48-59 */
+  MB2_COST_VENKAT91 = 20,   /* models/venkataraman.py:38-52 */
+  MB2_COST_FOSC3D = 21,     /* models/wolfram.py:44-64 */
+  MB2_COST_NMIN51 = 22,     /* models/wolfram.py:87-103 */
+  MB2_COST_SHEKEL = 23,     /* models/dejong.py:252-278 */
+  /* ... and of any number of variables, evaluated coordinate by coordinate in the reference's order */
+  MB2_COST_ELLIPSOID = 24,  /* models/pohlheim.py:92-102 */
+  MB2_COST_PAVIANI = 25     /* models/schittkowski.py:46-71 */
 };
 
 /* SetStrictRanges modes (abstract_solver.py:334-448, tools.py:404-430) */

@@ -85,7 +85,7 @@ struct mb2_ctx {
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
-  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0, nullptr, 1.0, 0};
+  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0, nullptr, 1.0, 0, 0, {0.0, 0.0, 0.0}};
   double* fit_obs = nullptr;
   size_t cap_fit_obs = 0;
   double bounds_absmax = 0.0;  // max(|lo_i|, |hi_i|) of the strict range
@@ -825,14 +825,26 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
 
 int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
-  if (cost < MB2_COST_ROSEN || cost > MB2_COST_POWERS) return fail(MB2_EINVAL, "unknown cost id %d", cost);
-  if (cost >= MB2_COST_SPHERE) c->cp.sep_kind = cost - MB2_COST_SPHERE;
+  if (cost < MB2_COST_ROSEN || cost > MB2_COST_PAVIANI) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (is_separable(cost)) c->cp.sep_kind = cost - MB2_COST_SPHERE;
+  // closed-form functions one thread evaluates (fixed_cost, de_device.cuh) run on the zimmermann instantiations
+  c->cp.fixed_kind = FIX_ZIMMERMANN;
+  if (cost >= MB2_COST_BRANINS) {
+    if (cost <= MB2_COST_SHEKEL && c->dim != 2) return fail(MB2_EINVAL, "cost %d is a function of two variables", cost);
+    c->cp.fixed_kind = FIX_BRANINS + (cost - MB2_COST_BRANINS);
+    const double pi = 3.141592653589793;  // math.pi
+    c->cp.fixed_c[0] = 5.1 / (4 * pow(pi, 2));  // pohlheim.py:279, as Python evaluates it
+    c->cp.fixed_c[1] = 5. / pi;
+    c->cp.fixed_c[2] = 1. / (8 * pi);
+    cost = MB2_COST_ZIMMERMANN;
+  }
   if (cost == MB2_COST_LORENTZIAN && c->dim != 7) return fail(MB2_EINVAL, "lorentzian has 7 parameters (a1,a2,a3,A0,E0,G0,n)");
   if ((cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN) && c->dim > 32)
     return fail(MB2_EINVAL, "data-fit costs support at most 32 model parameters");
   if (cost == MB2_COST_POLYFIT_MMA && c->dim > kChebMaxDim)
     return fail(MB2_EINVAL, "polynomial-fit DMMA cost supports at most %d coefficients", kChebMaxDim);
-  if (cost == MB2_COST_ZIMMERMANN && c->dim != 2) return fail(MB2_EINVAL, "zimmermann requires dim == 2");
+  if (cost == MB2_COST_ZIMMERMANN && c->cp.fixed_kind == FIX_ZIMMERMANN && c->dim != 2)
+    return fail(MB2_EINVAL, "zimmermann requires dim == 2");
   if (cost == MB2_COST_CHEBYSHEV_MMA && c->dim > kChebMaxDim)
     return fail(MB2_EINVAL, "chebyshev DMMA cost supports at most %d coefficients", kChebMaxDim);
   // evaluation points -> device; Vandermonde fragments of the DMMA variants (see de_cheb_mma.cuh)

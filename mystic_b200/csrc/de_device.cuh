@@ -171,6 +171,9 @@ struct CostParams {
   const double* fit_obs;  // [M] observations
   double fit_sigma;
   int sep_kind;  // COST_SEPARABLE: which of the SEP_* functions
+  // COST_ZIMMERMANN stands for the family of closed-form functions one thread evaluates (fixed_cost)
+  int fixed_kind;      // FIX_*
+  double fixed_c[3];   // branins: b = 5.1/(4*pi**2), c = 5./pi, f = 1./(8*pi), computed on the host like Python does
 };
 
 // c / s with r = RN(1/s): two Markstein refinement steps on top of c*r give the correctly
@@ -320,6 +323,122 @@ __device__ __forceinline__ double fit_term(const double* __restrict__ xs, int D,
   return (COST == COST_POLYFIT) ? polyfit_term(xs, D, x, obs, cp.fit_sigma) : lorentz_term(xs, x, obs, cp.fit_sigma);
 }
 
+// Closed-form test functions evaluated by ONE thread in the reference's operation order (Python floats:
+// `**` is libm pow, here x*x for squares, CUDA's pow / sin / cos / exp / log otherwise: <= 2 ulp from glibc's).
+//   zimmermann storn.py:182-191      branins   pohlheim.py:278-282   easom    pohlheim.py:312-313
+//   goldstein  pohlheim.py:352-355   peaks     nag.py:55-59          venkat91 venkataraman.py:50-52
+//   fosc3d     wolfram.py:60-64      nmin51    wolfram.py:101-103    shekel   dejong.py:266-278
+//   ellipsoid  pohlheim.py:101-102 (any D)     paviani   schittkowski.py:64-71 (any D)
+enum : int { FIX_ZIMMERMANN = 0, FIX_BRANINS = 1, FIX_EASOM = 2, FIX_GOLDSTEIN = 3, FIX_PEAKS = 4, FIX_VENKAT91 = 5,
+             FIX_FOSC3D = 6, FIX_NMIN51 = 7, FIX_SHEKEL = 8, FIX_ELLIPSOID = 9, FIX_PAVIANI = 10 };
+
+static __device__ __noinline__ double fixed_cost(int kind, const double* x, int D, const CostParams& cp) {
+  const double kPi = 3.141592653589793;
+  if (kind == FIX_ELLIPSOID) {
+    double pre = 0.0, acc = 0.0;  // sum(sum(coeffs[0:i+1])**2 for i in range(N))
+    for (int i = 0; i < D; ++i) {
+      pre = dadd(pre, x[i]);
+      acc = dadd(acc, dmul(pre, pre));
+    }
+    return acc;
+  }
+  if (kind == FIX_PAVIANI) {
+    double s = 0.0, p = x[0];
+    for (int i = 0; i < D; ++i) {
+      const double v = x[i];
+      if (v >= 10.0 || v <= 2.0) {
+        s = CUDART_INF;
+        break;
+      }
+      const double a = log(dsub(v, 2.0)), b = log(dsub(10.0, v));
+      s = dadd(s, dadd(dmul(a, a), dmul(b, b)));
+    }
+    for (int i = 1; i < D; ++i) p = dmul(p, x[i]);
+    return dsub(s, pow(p, 0.2));
+  }
+  const double x0 = x[0], x1 = (D > 1) ? x[1] : 0.0;
+  switch (kind) {
+    case FIX_BRANINS: {
+      const double b = cp.fixed_c[0], c = cp.fixed_c[1], f = cp.fixed_c[2];
+      const double t = dsub(dadd(dsub(x1, dmul(b, dmul(x0, x0))), dmul(c, x0)), 6.0);
+      const double f0 = dmul(1.0, dmul(t, t));
+      const double f1 = dadd(dmul(dmul(10.0, dsub(1.0, f)), cos(x0)), 10.0);
+      return dadd(f0, f1);
+    }
+    case FIX_EASOM: {
+      const double a = dsub(x0, kPi), b = dsub(x1, kPi);
+      return dmul(dmul(-cos(x0), cos(x1)), exp(-dadd(dmul(a, a), dmul(b, b))));
+    }
+    case FIX_GOLDSTEIN: {
+      const double s0 = dmul(x0, x0), s1 = dmul(x1, x1);
+      double f0 = dsub(19.0, dmul(14.0, x0));
+      f0 = dadd(f0, dmul(3.0, s0));
+      f0 = dsub(f0, dmul(14.0, x1));
+      f0 = dadd(f0, dmul(dmul(6.0, x0), x1));
+      f0 = dadd(f0, dmul(3.0, s1));
+      double f1 = dsub(18.0, dmul(32.0, x0));
+      f1 = dadd(f1, dmul(12.0, s0));
+      f1 = dadd(f1, dmul(48.0, x1));
+      f1 = dsub(f1, dmul(dmul(36.0, x0), x1));
+      f1 = dadd(f1, dmul(27.0, s1));
+      const double u = dadd(dadd(x0, x1), 1.0), v = dsub(dmul(2.0, x0), dmul(3.0, x1));
+      return dmul(dadd(1.0, dmul(dmul(u, u), f0)), dadd(30.0, dmul(dmul(v, v), f1)));
+    }
+    case FIX_PEAKS: {
+      const double xx = dmul(x0, x0), yy = dmul(x1, x1);
+      const double y1 = dadd(x1, 1.0), xm = dsub(1.0, x0), xp = dadd(x0, 1.0);
+      const double t1 = dmul(dmul(3.0, dmul(xm, xm)), exp(dsub(-xx, dmul(y1, y1))));
+      const double in2 = dsub(dsub(dmul(x0, 1. / 5.), pow(x0, 3.0)), pow(x1, 5.0));
+      const double t2 = dmul(dmul(10.0, in2), exp(dsub(-xx, yy)));
+      const double t3 = dmul(1. / 3., exp(dsub(-dmul(xp, xp), yy)));
+      return dsub(dsub(t1, t2), t3);
+    }
+    case FIX_VENKAT91: {
+      const double a = dsub(x0, 4.0), b = dsub(x1, 4.0);
+      const double R = sqrt(dadd(dadd(dmul(a, a), dmul(b, b)), 0.1));
+      return dmul(-20.0, sin(R)) / R;
+    }
+    case FIX_FOSC3D: {
+      const double func = dadd(dmul(-4.0, exp(dsub(dmul(-x0, x0), dmul(x1, x1)))), dmul(sin(dmul(6.0, x0)), sin(dmul(5.0, x1))));
+      const double pen = (x1 < 0.0) ? dmul(dmul(100.0, x1), x1) : 0.0;
+      return dadd(func, pen);
+    }
+    case FIX_NMIN51: {
+      double r = dadd(exp(sin(dmul(50.0, x0))), sin(dmul(60.0, exp(x1))));
+      r = dadd(r, sin(dmul(70.0, sin(x0))));
+      r = dadd(r, sin(sin(dmul(80.0, x1))));
+      r = dsub(r, sin(dmul(10.0, dadd(x0, x1))));
+      return dadd(r, dmul(1. / 4., dadd(dmul(x0, x0), dmul(x1, x1))));
+    }
+    case FIX_SHEKEL: {
+      double r = 0.0;
+      for (int i = 0; i < 25; ++i) {
+        const double a1 = -32.0 + 16.0 * (i % 5), a2 = -32.0 + 16.0 * (i / 5);
+        const double z = dadd(dadd(dmul(1.0, (double)i), pow(dsub(x0, a1), 6.0)), pow(dsub(x1, a2), 6.0));
+        r = dadd(r, (z != 0.0) ? 1.0 / z : CUDART_INF);
+      }
+      return 1.0 / dadd(0.002, r);
+    }
+    default: {  // FIX_ZIMMERMANN (D == 2)
+      const double f8 = dsub(dsub(9.0, x0), x1);
+      double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
+      if (x0 < 0.0) c0 = dmul(-100.0, x0);
+      if (x1 < 0.0) c1 = dmul(-100.0, x1);
+      const double a = dsub(x0, 3.0), b = dsub(x1, 2.0);
+      const double xx = dadd(dmul(a, a), dmul(b, b));
+      if (xx > 16.0) c2 = dmul(100.0, dsub(xx, 16.0));
+      const double pr = dmul(x0, x1);
+      if (pr > 14.0) c3 = dmul(100.0, dsub(pr, 14.0));
+      double m = f8;  // python max(f8,c0,c1,c2,c3): replace only when strictly greater
+      if (c0 > m) m = c0;
+      if (c1 > m) m = c1;
+      if (c2 > m) m = c2;
+      if (c3 > m) m = c3;
+      return m;
+    }
+  }
+}
+
 // Group-cooperative cost of one row `xs` (shared memory, D entries).  Every thread of the group
 // returns the same value.  Per-element terms follow the reference's operation order without
 // FMA, so each term is bit-identical to the reference; only the summation tree differs
@@ -414,23 +533,7 @@ __device__ __forceinline__ double group_cost(const Group<GW>& g, const double* x
     const double p = group_reduce<true, GW>(g, pa, 1);
     return dadd(dsub(s / 4000.0, p), 1.0);
   } else if (COST == COST_ZIMMERMANN) {
-    // storn.py:182-191 (D == 2)
-    const double x0 = xs[0], x1 = (D > 1) ? xs[1] : 0.0;
-    const double f8 = dsub(dsub(9.0, x0), x1);
-    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-    if (x0 < 0.0) c0 = dmul(-100.0, x0);
-    if (x1 < 0.0) c1 = dmul(-100.0, x1);
-    const double a = dsub(x0, 3.0), b = dsub(x1, 2.0);
-    const double xx = dadd(dmul(a, a), dmul(b, b));
-    if (xx > 16.0) c2 = dmul(100.0, dsub(xx, 16.0));
-    const double pr = dmul(x0, x1);
-    if (pr > 14.0) c3 = dmul(100.0, dsub(pr, 14.0));
-    double m = f8;  // python max(f8,c0,c1,c2,c3): replace only when strictly greater
-    if (c0 > m) m = c0;
-    if (c1 > m) m = c1;
-    if (c2 > m) m = c2;
-    if (c3 > m) m = c3;
-    return m;
+    return fixed_cost(cp.fixed_kind, xs, D, cp);  // every thread evaluates the row
   } else if (COST == COST_SEPARABLE) {
     double sa[NA], sb[NA];
 #pragma unroll

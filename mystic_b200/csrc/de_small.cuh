@@ -93,22 +93,7 @@ __device__ __forceinline__ double thread_cost(const double* x, int D, const Cost
     }
     return dadd(dsub(s / 4000.0, p), 1.0);
   } else if (COST == COST_ZIMMERMANN) {
-    const double x0 = x[0], x1 = (D > 1) ? x[1] : 0.0;
-    const double f8 = dsub(dsub(9.0, x0), x1);
-    double c0 = 0.0, c1 = 0.0, c2 = 0.0, c3 = 0.0;
-    if (x0 < 0.0) c0 = dmul(-100.0, x0);
-    if (x1 < 0.0) c1 = dmul(-100.0, x1);
-    const double a = dsub(x0, 3.0), b = dsub(x1, 2.0);
-    const double xx = dadd(dmul(a, a), dmul(b, b));
-    if (xx > 16.0) c2 = dmul(100.0, dsub(xx, 16.0));
-    const double pr = dmul(x0, x1);
-    if (pr > 14.0) c3 = dmul(100.0, dsub(pr, 14.0));
-    double m = f8;
-    if (c0 > m) m = c0;
-    if (c1 > m) m = c1;
-    if (c2 > m) m = c2;
-    if (c3 > m) m = c3;
-    return m;
+    return fixed_cost(cp.fixed_kind, x, D, cp);
   } else if (COST == COST_SEPARABLE) {
     double s1 = 0.0, s2 = 0.0;
     for (int i = 0; i < D; ++i) sep_accumulate(cp.sep_kind, x[i], i, s1, s2);

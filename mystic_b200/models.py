@@ -6,6 +6,9 @@
     zimmermann  mystic/models/storn.py:161-191
     sphere, step   mystic/models/dejong.py:54-66, 166-192
     rastrigin, schwefel, ackley, michal, powers   mystic/models/pohlheim.py:60-71, 123-132, 186-204, 226-240, 153-163
+    branins, easom, goldstein, ellipsoid   mystic/models/pohlheim.py:261-282, 303-313, 336-355, 92-102
+    peaks, venkat91, fosc3d, nmin51, shekel, paviani   mystic/models/nag.py:48-59, venkataraman.py:38-52,
+                wolfram.py:44-64, 87-103, dejong.py:252-278, schittkowski.py:46-71
     chebyshev{2,4,6,8,16}cost   mystic/models/poly.py:124-149, mystic/models/_model_helper.py:10-33
     poly.CostFactory / poly.CostFactory2, lorentzian.CostFactory / lorentzian.CostFactory2
                 data-fit residual costs, mystic/models/abstract_model.py:146-161 ->
@@ -21,6 +24,8 @@ with TypeError: the engine has no CPU path.
 COST_ROSEN, COST_CORANA, COST_GRIEWANGK, COST_ZIMMERMANN, COST_CHEBYSHEV, COST_CHEBYSHEV_MMA = range(6)
 COST_POLYFIT, COST_POLYFIT_MMA, COST_LORENTZIAN = 6, 7, 8
 COST_SPHERE, COST_RASTRIGIN, COST_SCHWEFEL, COST_ACKLEY, COST_STEP, COST_MICHAL, COST_POWERS = 9, 10, 11, 12, 13, 14, 15
+(COST_BRANINS, COST_EASOM, COST_GOLDSTEIN, COST_PEAKS, COST_VENKAT91, COST_FOSC3D, COST_NMIN51, COST_SHEKEL, COST_ELLIPSOID,
+ COST_PAVIANI) = range(16, 26)
 
 CHEBYSHEV_TARGETS = {  # mystic/models/_model_helper.py:10-14
     2: [2., 0., -1.],
@@ -154,17 +159,30 @@ ackley = DeviceCost('ackley', COST_ACKLEY, doc="Ackley's path function")
 step = DeviceCost('step', COST_STEP, doc="De Jong's step function")
 michal = DeviceCost('michal', COST_MICHAL, doc="Michalewicz's function")
 powers = DeviceCost('powers', COST_POWERS, doc="Pohlheim's sum of different powers")
+branins = DeviceCost('branins', COST_BRANINS, doc="Branins's rcos function (2-D)")
+easom = DeviceCost('easom', COST_EASOM, doc="Easom's function (2-D)")
+goldstein = DeviceCost('goldstein', COST_GOLDSTEIN, doc="Goldstein-Price's function (2-D)")
+peaks = DeviceCost('peaks', COST_PEAKS, doc="NAG's peaks function (2-D)")
+venkat91 = DeviceCost('venkat91', COST_VENKAT91, doc="Venkataraman's sinc function (2-D)")
+fosc3d = DeviceCost('fosc3d', COST_FOSC3D, doc="Wolfram's fOsc3D function (2-D)")
+nmin51 = DeviceCost('nmin51', COST_NMIN51, doc="Wolfram's NMinimize test function 51 (2-D)")
+shekel = DeviceCost('shekel', COST_SHEKEL, doc="Shekel's foxholes (2-D)")
+ellipsoid = DeviceCost('ellipsoid', COST_ELLIPSOID, doc="Pohlheim's rotated hyper-ellipsoid, sum of squared prefix sums")
+paviani = DeviceCost('paviani', COST_PAVIANI, doc="Paviani's function (x_i in (2, 10))")
 chebyshev2cost = DeviceCost('chebyshev2cost', COST_CHEBYSHEV, 2, 'order-2 Chebyshev fitting cost')
 chebyshev4cost = DeviceCost('chebyshev4cost', COST_CHEBYSHEV, 4, 'order-4 Chebyshev fitting cost')
 chebyshev6cost = DeviceCost('chebyshev6cost', COST_CHEBYSHEV, 6, 'order-6 Chebyshev fitting cost')
 chebyshev8cost = DeviceCost('chebyshev8cost', COST_CHEBYSHEV, 8, 'order-8 Chebyshev fitting cost')
 chebyshev16cost = DeviceCost('chebyshev16cost', COST_CHEBYSHEV, 16, 'order-16 Chebyshev fitting cost')
 
-_BY_NAME = dict((c.__name__, c) for c in (rosen, corana, griewangk, zimmermann, sphere, rastrigin, schwefel, ackley, step, michal, powers, chebyshev2cost, chebyshev4cost,
+_BY_NAME = dict((c.__name__, c) for c in (rosen, corana, griewangk, zimmermann, sphere, rastrigin, schwefel, ackley, step, michal, powers, branins, easom,
+                                          goldstein, peaks, venkat91, fosc3d, nmin51, shekel, ellipsoid, paviani, chebyshev2cost, chebyshev4cost,
                                           chebyshev6cost, chebyshev8cost, chebyshev16cost))
 _BY_REFERENCE_CLASS = {'Rosenbrock': rosen, 'Corana': corana, 'Griewangk': griewangk, 'Zimmermann': zimmermann,
                        'Sphere': sphere, 'Rastrigin': rastrigin, 'Schwefel': schwefel, 'Ackley': ackley,
-                       'Step': step, 'Michalewicz': michal, 'DifferentPowers': powers}
+                       'Step': step, 'Michalewicz': michal, 'DifferentPowers': powers, 'Branins': branins, 'Easom': easom,
+                       'GoldsteinPrice': goldstein, 'Peaks': peaks, 'Sinc': venkat91, 'fOsc3D': fosc3d, 'NMinimize51': nmin51,
+                       'Shekel': shekel, 'HyperEllipsoid': ellipsoid, 'Paviani': paviani}
 
 
 def _resolve_reference_costfactory(cost):
@@ -222,5 +240,5 @@ def resolve(cost):
     raise TypeError(
         "cost %r is not a device cost function: the B200 engine evaluates the cost inside the fused "
         "CUDA kernel and has no CPU path. Use mystic_b200.models.{rosen,corana,griewangk,zimmermann,"
-        "sphere,rastrigin,schwefel,ackley,step,michal,powers,chebyshevNcost,poly.CostFactory,lorentzian.CostFactory} or the "
+        "sphere,rastrigin,schwefel,ackley,step,michal,powers,branins,easom,goldstein,peaks,venkat91,fosc3d,nmin51,shekel,ellipsoid,paviani,chebyshevNcost,poly.CostFactory,lorentzian.CostFactory} or the "
         "corresponding mystic.models objects." % (cost,))

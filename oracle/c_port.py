@@ -56,7 +56,9 @@ def _d(a):
 class COracle(object):
     """Same state machine as oracle.de_oracle.DEState + step0/step, in C with OpenMP."""
 
-    COSTS = {'rosen': 0, 'corana': 1, 'griewangk': 2, 'zimmermann': 3, 'sphere': 9, 'rastrigin': 10, 'schwefel': 11, 'ackley': 12, 'step': 13, 'michal': 14, 'powers': 15}
+    COSTS = {'rosen': 0, 'corana': 1, 'griewangk': 2, 'zimmermann': 3, 'sphere': 9, 'rastrigin': 10, 'schwefel': 11, 'ackley': 12, 'step': 13, 'michal': 14, 'powers': 15,
+             'branins': 16, 'easom': 17, 'goldstein': 18, 'peaks': 19, 'venkat91': 20, 'fosc3d': 21, 'nmin51': 22, 'shekel': 23,
+             'ellipsoid': 24, 'paviani': 25}
 
     def __init__(self, population, strategy, CR, F, cost, extra=(), lo=None, hi=None, bounds_mode=0, penalty=()):
         from oracle import de_oracle as orc

@@ -25,7 +25,9 @@ enum { XOVER_EXP = 0, XOVER_BIN = 1 };
 enum { BOUNDS_NONE = 0, BOUNDS_REJECT = 1, BOUNDS_CLAMP = 2 };
 enum { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3, COST_CHEBYSHEV = 4,
        COST_POLYFIT = 6, COST_LORENTZIAN = 8, COST_SPHERE = 9, COST_RASTRIGIN = 10, COST_SCHWEFEL = 11,
-       COST_ACKLEY = 12, COST_STEP = 13, COST_MICHAL = 14, COST_POWERS = 15 };
+       COST_ACKLEY = 12, COST_STEP = 13, COST_MICHAL = 14, COST_POWERS = 15,
+       COST_BRANINS = 16, COST_EASOM = 17, COST_GOLDSTEIN = 18, COST_PEAKS = 19, COST_VENKAT91 = 20, COST_FOSC3D = 21,
+       COST_NMIN51 = 22, COST_SHEKEL = 23, COST_ELLIPSOID = 24, COST_PAVIANI = 25 };
 
 typedef struct {
   int32_t dim;
@@ -234,6 +236,73 @@ static double cost_separable(const double* c, int D, int cost) {
   return s1;
 }
 
+/* closed-form functions of a few variables: the reference's expressions on doubles (`**` is libm pow):
+ * pohlheim.py:278-282, 312-313, 352-355, 101-102; nag.py:55-59; venkataraman.py:50-52; wolfram.py:60-64,
+ * 101-103; dejong.py:266-278; schittkowski.py:64-71.  ellipsoid: plain sums (the reference's builtin sum()
+ * is compensated since CPython 3.12, see oracle/de_oracle.py) */
+static double cost_fixed(const double* c, int D, int cost) {
+  const double pi = 3.141592653589793;
+  if (cost == COST_ELLIPSOID) {
+    double pre = 0.0, acc = 0.0;
+    for (int i = 0; i < D; ++i) {
+      pre += c[i];
+      acc += pow(pre, 2);
+    }
+    return acc;
+  }
+  if (cost == COST_PAVIANI) {
+    double s = 0.0, p = c[0];
+    for (int i = 0; i < D; ++i) {
+      if (c[i] >= 10. || c[i] <= 2.) {
+        s = INFINITY;
+        break;
+      }
+      s += pow(log(c[i] - 2.), 2) + pow(log(10. - c[i]), 2);
+    }
+    for (int i = 1; i < D; ++i) p = p * c[i];
+    return s - pow(p, .2);
+  }
+  const double x = c[0], y = c[1];
+  switch (cost) {
+    case COST_BRANINS: {
+      const double a = 1., b = 5.1 / (4 * pow(pi, 2)), cc = 5. / pi, d = 6., e = 10., f = 1. / (8 * pi);
+      const double f0 = a * pow(y - b * pow(x, 2) + cc * x - d, 2);
+      const double f1 = e * (1 - f) * cos(x) + e;
+      return f0 + f1;
+    }
+    case COST_EASOM: return -cos(x) * cos(y) * exp(-(pow(x - pi, 2) + pow(y - pi, 2)));
+    case COST_GOLDSTEIN: {
+      const double f0 = 19 - 14 * x + 3 * pow(x, 2) - 14 * y + 6 * x * y + 3 * pow(y, 2);
+      const double f1 = 18 - 32 * x + 12 * pow(x, 2) + 48 * y - 36 * x * y + 27 * pow(y, 2);
+      return (1 + pow(x + y + 1, 2) * f0) * (30 + pow(2 * x - 3 * y, 2) * f1);
+    }
+    case COST_PEAKS:
+      return 3. * pow(1. - x, 2) * exp(-pow(x, 2) - pow(y + 1., 2)) -
+             10. * (x * (1. / 5.) - pow(x, 3) - pow(y, 5)) * exp(-pow(x, 2) - pow(y, 2)) -
+             1. / 3. * exp(-pow(x + 1., 2) - pow(y, 2));
+    case COST_VENKAT91: {
+      const double R = pow(pow(x - 4., 2) + pow(y - 4., 2) + 0.1, .5);
+      return -20. * sin(R) / R;
+    }
+    case COST_FOSC3D: {
+      const double func = -4. * exp(-x * x - y * y) + sin(6. * x) * sin(5. * y);
+      return (y < 0) ? func + 100. * y * y : func + 0;
+    }
+    case COST_NMIN51:
+      return exp(sin(50. * x)) + sin(60. * exp(y)) + sin(70. * sin(x)) + sin(sin(80. * y)) - sin(10. * (x + y)) +
+             1. / 4. * (pow(x, 2) + pow(y, 2));
+    default: {  /* COST_SHEKEL */
+      const double A[5] = {-32., -16., 0., 16., 32.};
+      double r = 0.0;
+      for (int i = 0; i < 25; ++i) {
+        const double z = 1.0 * i + pow(x - A[i % 5], 6) + pow(y - A[i / 5], 6);
+        r += (z != 0) ? 1.0 / z : INFINITY;
+      }
+      return 1.0 / (0.002 + r);
+    }
+  }
+}
+
 static double cost_zimmermann(const double* c) {
   /* storn.py:182-191 */
   double x0 = c[0], x1 = c[1];
@@ -317,6 +386,8 @@ static double energy_of(const double* x, const orc_config* cfg, double* scratch)
       case COST_STEP:
       case COST_MICHAL:
       case COST_POWERS: raw = cost_separable(x, D, cfg->cost); break;
+      case COST_BRANINS: case COST_EASOM: case COST_GOLDSTEIN: case COST_PEAKS: case COST_VENKAT91: case COST_FOSC3D:
+      case COST_NMIN51: case COST_SHEKEL: case COST_ELLIPSOID: case COST_PAVIANI: raw = cost_fixed(x, D, cfg->cost); break;
       default: raw = cost_chebyshev(x, D, cfg); break;
     }
   }

@@ -256,6 +256,116 @@ def cost_powers(x):
     return s
 
 
+
+# ---- closed-form functions of a few variables: the reference's own expressions on Python floats, row by row
+def _rowwise(f):
+    def cost(x):
+        x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+        return np.array([f([float(v) for v in row]) for row in x], dtype=np.float64)
+    return cost
+
+
+def _branins(coeffs):
+    """mystic/models/pohlheim.py:278-282"""
+    pi, cos = math.pi, math.cos
+    x1, x2 = coeffs
+    a = 1.; b = 5.1/(4*pi**2); c = 5./pi; d = 6.; e = 10.; f = 1./(8*pi)
+    f0 = a * (x2 - b * x1**2 + c * x1 - d)**2
+    f1 = e * (1 - f) * cos(x1) + e
+    return f0 + f1
+
+
+def _easom(coeffs):
+    """mystic/models/pohlheim.py:312-313"""
+    pi, cos, exp = math.pi, math.cos, math.exp
+    x0, x1 = coeffs
+    return -cos(x0) * cos(x1) * exp(-((x0-pi)**2+(x1-pi)**2))
+
+
+def _goldstein(coeffs):
+    """mystic/models/pohlheim.py:352-355"""
+    x0, x1 = coeffs
+    f0 = 19 - 14*x0 + 3*x0**2 - 14*x1 + 6*x0*x1 + 3*x1**2
+    f1 = 18 - 32*x0 + 12*x0**2 + 48*x1 - 36*x0*x1 + 27*x1**2
+    return (1 + (x0 + x1 + 1)**2 * f0) * (30 + (2*x0 - 3*x1)**2 * f1)
+
+
+def _peaks(coeffs):
+    """mystic/models/nag.py:55-59"""
+    exp = math.exp
+    x, y = coeffs
+    result = 3.*(1. - x)**2*exp(-x**2 - (y + 1.)**2) - \
+            10.*(x*(1./5.) - x**3 - y**5)*exp(-x**2 - y**2) - \
+            1./3.*exp(-(x + 1.)**2 - y**2)
+    return result
+
+
+def _venkat91(coeffs):
+    """mystic/models/venkataraman.py:50-52"""
+    x, y = coeffs
+    R = ((x-4.)**2 + (y-4.)**2 + 0.1)**.5
+    return -20. * math.sin(R)/R
+
+
+def _fosc3d(coeffs):
+    """mystic/models/wolfram.py:60-64"""
+    exp, sin = math.exp, math.sin
+    x, y = coeffs
+    func = -4. * exp(-x*x - y*y) + sin(6. * x) * sin(5. * y)
+    penalty = 0
+    if y < 0: penalty = 100.*y*y
+    return func + penalty
+
+
+def _nmin51(coeffs):
+    """mystic/models/wolfram.py:101-103"""
+    exp, sin = math.exp, math.sin
+    x, y = coeffs
+    return exp(sin(50.*x)) + sin(60.*exp(y)) + sin(70.*sin(x)) + \
+           sin(sin(80.*y)) - sin(10.*(x + y)) + 1./4.*(x**2 + y**2)
+
+
+def _shekel(coeffs):
+    """mystic/models/dejong.py:266-278"""
+    A = [-32., -16., 0., 16., 32.]
+    a1 = A * 5
+    a2 = [c for c in A for _ in range(5)]
+    x, y = coeffs
+    r = 0.0
+    for i in range(25):
+        z = 1.0*i + pow(x-a1[i], 6) + pow(y-a2[i], 6)
+        if z: r += 1.0/z
+        else: r += math.inf
+    return 1.0/(0.002 + r)
+
+
+def _ellipsoid(coeffs):
+    """mystic/models/pohlheim.py:101-102 (the builtin sum(): compensated since CPython 3.12)"""
+    ncoeffs = range(len(coeffs))
+    return sum(sum(coeffs[0:i+1])**2 for i in ncoeffs)
+
+
+def _paviani(coeffs):
+    """mystic/models/schittkowski.py:64-71"""
+    from functools import reduce
+    s = 0.
+    for x in coeffs:
+        if x >= 10. or x <= 2.:
+            s = math.inf
+            break
+        s += math.log(x-2.)**2 + math.log(10.-x)**2
+    p = reduce(lambda x, y: x*y, coeffs)**(.2)
+    return s - p
+
+
+FIXED_COSTS = {'branins': _branins, 'easom': _easom, 'goldstein': _goldstein, 'peaks': _peaks, 'venkat91': _venkat91,
+               'fosc3d': _fosc3d, 'nmin51': _nmin51, 'shekel': _shekel, 'ellipsoid': _ellipsoid, 'paviani': _paviani}
+# magnitude of the terms the functions combine: the scale energies are compared on (their transcendental
+# terms differ by <= 2 ulp between libm and CUDA, and they cancel)
+FIXED_COST_SCALE = {'branins': 10., 'easom': 1e-3, 'goldstein': 1., 'peaks': 10., 'venkat91': 20., 'fosc3d': 4., 'nmin51': 6.,
+                    'shekel': 1e-3, 'ellipsoid': 0., 'paviani': 10.}
+
+
 def cost_polyfit(x, pts, obs, sigma=1.0):
     """mystic/forward_model.py:241-258 with the polynomial model of mystic/models/poly.py:36-54:
     F(params) = numpy.poly1d(params) whose evaluation is numpy.polyval's
@@ -314,6 +424,8 @@ def make_cost(name, extra_args=()):
     if name in ('sphere', 'rastrigin', 'schwefel', 'ackley', 'step', 'michal', 'powers'):
         return {'sphere': cost_sphere, 'rastrigin': cost_rastrigin, 'schwefel': cost_schwefel, 'ackley': cost_ackley,
                 'step': cost_step, 'michal': cost_michal, 'powers': cost_powers}[name]
+    if name in FIXED_COSTS:
+        return _rowwise(FIXED_COSTS[name])
     if name.startswith('chebyshev') and name.endswith('cost'):
         order = int(name[len('chebyshev'):-len('cost')])
         M = int(extra_args[0]) if extra_args else 61

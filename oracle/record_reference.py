@@ -347,6 +347,28 @@ def cases():
                                      init=('random', [0.] * 6, [3.14] * 6), bounds=([0.] * 6, [3.14] * 6, True), maxgen=8)
     cs['sep_powers_best1exp'] = dict(dim=7, NP=28, strategy='Best1Exp', cost='powers', CR=0.9, F=0.8, seed=407,
                                      init=('random', [-1.5] * 7, [1.5] * 7), maxgen=8)
+    # closed-form functions of mystic.models evaluated by one thread on the device
+    cs['fix_branins_best1exp'] = dict(dim=2, NP=24, strategy='Best1Exp', cost='branins', CR=0.9, F=0.8, seed=501,
+                                      init=('random', [-5., 0.], [10., 15.]), bounds=([-5., 0.], [10., 15.], True), maxgen=10)
+    cs['fix_easom_rand1bin'] = dict(dim=2, NP=24, strategy='Rand1Bin', cost='easom', CR=0.9, F=0.8, seed=502,
+                                    init=('random', [0.] * 2, [6.] * 2), maxgen=10)
+    cs['fix_goldstein_best1bin'] = dict(dim=2, NP=20, strategy='Best1Bin', cost='goldstein', CR=0.9, F=0.8, seed=503,
+                                        init=('random', [-2.] * 2, [2.] * 2), bounds=([-2.] * 2, [2.] * 2, False), maxgen=10)
+    cs['fix_peaks_rand2exp'] = dict(dim=2, NP=24, strategy='Rand2Exp', cost='peaks', CR=0.9, F=0.7, seed=504,
+                                    init=('random', [-3.] * 2, [3.] * 2), maxgen=10)
+    cs['fix_venkat91_randtobest'] = dict(dim=2, NP=24, strategy='RandToBest1Exp', cost='venkat91', CR=0.9, F=0.8, seed=505,
+                                         init=('random', [-10.] * 2, [10.] * 2), bounds=([-10.] * 2, [10.] * 2, True), maxgen=10)
+    cs['fix_fosc3d_best2exp'] = dict(dim=2, NP=24, strategy='Best2Exp', cost='fosc3d', CR=0.9, F=0.6, seed=506,
+                                     init=('random', [-5.] * 2, [5.] * 2), maxgen=10)
+    cs['fix_nmin51_best1exp'] = dict(dim=2, NP=24, strategy='Best1Exp', cost='nmin51', CR=0.9, F=0.8, seed=507,
+                                     init=('random', [-1.] * 2, [1.] * 2), bounds=([-1.] * 2, [1.] * 2, True), maxgen=10)
+    cs['fix_shekel_rand1exp'] = dict(dim=2, NP=24, strategy='Rand1Exp', cost='shekel', CR=0.9, F=0.8, seed=508,
+                                     init=('random', [-50.] * 2, [50.] * 2), bounds=([-50.] * 2, [50.] * 2, False), maxgen=10)
+    cs['fix_ellipsoid_best1bin'] = dict(dim=12, NP=30, strategy='Best1Bin', cost='ellipsoid', CR=0.9, F=0.8, seed=509,
+                                        init=('random', [-65.] * 12, [65.] * 12), maxgen=8)
+    cs['fix_paviani_rand1exp'] = dict(dim=10, NP=30, strategy='Rand1Exp', cost='paviani', CR=0.9, F=0.8, seed=510,
+                                      init=('random', [2.001] * 10, [9.999] * 10), bounds=([2.001] * 10, [9.999] * 10, True),
+                                      maxgen=8)
     # data-fit residual costs: the reference's own CostFactory closures
     cs['fit_poly3_rand1exp'] = dict(dim=3, NP=20, strategy='Rand1Exp', cost='polyfit', CR=0.5, F=0.5, seed=301,
                                     init=('random', [-100.] * 3, [100.] * 3), bounds=([-100.] * 3, [100.] * 3, False),

@@ -22,7 +22,7 @@ def load(name):
 FIT_COSTS = ('polyfit', 'lorentzian')
 # costs the reference sums with the builtin sum(): CPython 3.12 compensates runs of exact floats
 # (oracle/de_oracle.py:cost_griewangk), so their ENERGIES are compared to 1e-14, everything else bit for bit
-COMPENSATED_SUM_COSTS = ('griewangk', 'rastrigin', 'schwefel', 'ackley', 'michal', 'powers')
+COMPENSATED_SUM_COSTS = ('griewangk', 'rastrigin', 'schwefel', 'ackley', 'michal', 'powers', 'ellipsoid')
 
 
 def extra_of(meta, z):

@@ -12,7 +12,8 @@ from oracle import de_oracle as orc
 
 _STRATEGY_BY_ID = dict((v[0], k) for k, v in orc.STRATEGIES.items())
 _COST_NAMES = {0: 'rosen', 1: 'corana', 2: 'griewangk', 3: 'zimmermann', 9: 'sphere', 10: 'rastrigin', 11: 'schwefel',
-               12: 'ackley', 13: 'step', 14: 'michal', 15: 'powers'}   # 4/5: chebyshev (Horner / DMMA)
+               12: 'ackley', 13: 'step', 14: 'michal', 15: 'powers', 16: 'branins', 17: 'easom', 18: 'goldstein', 19: 'peaks',
+               20: 'venkat91', 21: 'fosc3d', 22: 'nmin51', 23: 'shekel', 24: 'ellipsoid', 25: 'paviani'}   # 4/5: chebyshev (Horner / DMMA)
 _PTYPE_BY_ID = dict((v, k) for k, v in orc.PTYPES.items())
 
 

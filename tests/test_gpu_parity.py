@@ -34,6 +34,8 @@ def energy_close(dev, ref, x=None, cost=None, what=''):
         mag = {'rastrigin': (xx * xx).sum(axis=1) + 20.0 * xx.shape[1], 'schwefel': np.abs(xx).sum(axis=1),
                'ackley': np.full(xx.shape[0], 45.0), 'michal': np.full(xx.shape[0], float(xx.shape[1]))}[cost]
         scale = np.maximum(scale, mag)
+    elif cost in orc.FIXED_COST_SCALE:
+        scale = np.maximum(scale, orc.FIXED_COST_SCALE[cost])
     ok = both_inf | (np.abs(dev - ref) <= RTOL * scale)
     if not ok.all():
         i = int(np.argmax(~ok))
@@ -186,6 +188,13 @@ PHILOX_CASES = [
     (40, 36, 'Rand1Exp', 'step', (), (-7., 7., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5),
     (12, 30, 'Best1Bin', 'michal', (), (0., 3.14, orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5),
     (9, 28, 'RandToBest1Exp', 'powers', (), (-1.5, 1.5, orc.BOUNDS_REJECT), None, 0.9, 0.8, 5),
+    # closed-form functions one thread evaluates (fixed_cost)
+    (2, 40, 'Best1Bin', 'branins', (), (-5., 15., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 6),
+    (2, 33, 'Rand1Exp', 'peaks', (), None, None, 0.9, 0.8, 6),
+    (2, 36, 'Best2Exp', 'shekel', (), (-50., 50., orc.BOUNDS_REJECT), None, 0.9, 0.8, 5),
+    (20, 40, 'RandToBest1Exp', 'ellipsoid', (), (-65., 65., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5),
+    (10, 36, 'Rand1Exp', 'paviani', (), (2.5, 9.5, orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5),
+    (130, 30, 'Best1Bin', 'ellipsoid', (), None, None, 0.9, 0.8, 3),
     # data-fit residual costs: extra = (evaluation points, observations)
     (5, 40, 'Best1Exp', 'polyfit', (np.linspace(-2., 2., 77), np.cos(np.linspace(-2., 2., 77))), (-3., 3., orc.BOUNDS_CLAMP),
      None, 0.9, 0.8, 6),
@@ -275,6 +284,13 @@ def test_device_cost_callable_known_answers():
     assert models.zimmermann([7., 2.]) == 0.0
     assert models.zimmermann([1., 1.]) == 7.0
     assert models.zimmermann([-1., 6.]) == 1600.0
+    # minima quoted by the reference's docstrings (pohlheim.py:276, 311, 350; dejong.py:264)
+    assert abs(models.branins([np.pi, 2.275]) - 0.397887) < 1e-6
+    assert abs(models.easom([np.pi, np.pi]) + 1.0) < 1e-15
+    assert models.goldstein([0., -1.]) == 3.0
+    assert models.ellipsoid([1., 2., 3.]) == 1. + 9. + 36.
+    assert models.shekel([-32., -32.]) == 0.0
+    assert models.paviani([1., 5.]) == np.inf
     assert models.chebyshev8cost(models.CHEBYSHEV_TARGETS[8]) == 0.0
     close(models.chebyshev8cost([1.] * 9), 7823.744334789609)
     close(models.chebyshev8cost([1.] * 9, 4096), 22615.651073208195)
@@ -296,11 +312,15 @@ def test_costs_random_batches_match_oracle(kernel_path):
                                     ('step', (1, 9, 64, 200), 8., ()),
                                     ('michal', (2, 10, 64), 3.14, ()),
                                     ('powers', (1, 7, 20), 1.5, ()),
+                                    ('branins', (2,), 10., ()), ('easom', (2,), 6., ()), ('goldstein', (2,), 2., ()),
+                                    ('peaks', (2,), 3., ()), ('venkat91', (2,), 10., ()), ('fosc3d', (2,), 3., ()),
+                                    ('nmin51', (2,), 1., ()), ('shekel', (2,), 50., ()), ('ellipsoid', (1, 5, 33, 200), 65., ()),
+                                    ('paviani', (1, 10, 40), None, ()),
                                     ('chebyshev8cost', (9,), 100., (61,)),
                                     ('chebyshev8cost', (9,), 3., (4096,)),
                                     ('chebyshev16cost', (17,), 2., (333,))):
         for D in dims:
-            X = rng.uniform(-span, span, size=(97, D))
+            X = rng.uniform(-span, span, size=(97, D)) if span else rng.uniform(1.5, 10.5, size=(97, D))
             got = getattr(models, name)(X, *extra)
             want = orc.make_cost(name, extra)(X)
             energy_close(got, want, X, name, '%s D=%d' % (name, D))

@@ -85,9 +85,10 @@ def test_reference_penalty_decorator_with_linear_condition():
 def test_host_callables_are_rejected():
     s = DifferentialEvolutionSolver2(3, 8, engine=OracleEngine)
     with pytest.raises(TypeError):
-        s.SetObjective(mystic.models.easom)           # a mystic model without a device twin
+        s.SetObjective(mystic.models.wavy1)           # a mystic model without a device twin (vector-valued)
     from mystic_b200 import models
-    for name in ('sphere', 'rastrigin', 'schwefel', 'ackley', 'step', 'michal', 'powers', 'rosen', 'corana', 'griewangk', 'zimmermann'):
+    for name in ('sphere', 'rastrigin', 'schwefel', 'ackley', 'step', 'michal', 'powers', 'rosen', 'corana', 'griewangk', 'zimmermann',
+                 'branins', 'easom', 'goldstein', 'peaks', 'venkat91', 'fosc3d', 'nmin51', 'shekel', 'ellipsoid', 'paviani'):
         assert models.resolve(getattr(mystic.models, name)) is getattr(models, name)
     with pytest.raises(TypeError):
         @mystic.penalty.quadratic_inequality(lambda x: sum(x) - 1.0)
