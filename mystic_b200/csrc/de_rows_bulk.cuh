@@ -105,6 +105,11 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
     const int64_t cc = (c < P.np) ? c : (P.np - 1);  // idle groups shadow the last row
     const int64_t left = P.np - ch * RPW;
     const unsigned nlive = left < RPW ? (unsigned)left : (unsigned)RPW;
+    // the parent rows do not depend on the draws: their copy flies while the draws are made
+    if (lane == 0) {
+      mbar_expect_tx_only(bar, nlive * row_bytes);
+      bulk_g2s(st, P.pop_cur + ch * RPW * D, nlive * row_bytes, bar);
+    }
     RowDraws<K> dr;
     rows_draw<LPR, K>(P, XOVER_EXP, cc, sub, gbase, dr);
     const int q0 = dr.nstart >> 2;
@@ -130,12 +135,11 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
       m->off = off;
 #pragma unroll
       for (int j = 0; j < K; ++j) m->r[j] = dr.r[j];
-      mbar_expect_tx(bar, (lane == 0 ? nlive * row_bytes : 0u) + (fits ? (unsigned)(K * nq) * 32u : 0u));
+      mbar_expect_tx(bar, fits ? (unsigned)(K * nq) * 32u : 0u);  // the arrive of this row: meta is published with it
     }
     __syncwarp();
-    // one copy instruction serves the whole warp: lane 0 requests the stage's parent rows, lane 1 + j of a
-    // row's group the window's cover of donor j (a second instruction for the wrapped parts; further rounds
-    // when K > LPR - 1)
+    // one copy instruction serves the whole warp: lane 1 + j of a row's group requests the window's cover
+    // of donor j (a second instruction for the wrapped parts; further rounds when K > LPR - 1)
     const int n1 = (q0 + nq <= NQ) ? nq : (NQ - q0);  // chunks before the wrap
 #pragma unroll
     for (int jb = 0; jb < K; jb += LPR - 1) {
@@ -145,10 +149,9 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
 #pragma unroll
       for (int t = 0; t < K; ++t)
         if (t == j) rj = dr.r[t];
-      const double* src = (lane == 0) ? (P.pop_cur + ch * RPW * D) : (P.pop_cur + (int64_t)rj * D + 4 * q0);
-      double* dst = (lane == 0) ? reinterpret_cast<double*>(st)
-                                : (reinterpret_cast<double*>(st + G.rows_bytes + (unsigned)(donor ? j : 0) * G.pool_bytes) + 4 * (donor ? off : 0));
-      const unsigned bytes = (lane == 0) ? (jb == 0 ? nlive * row_bytes : 0u) : (donor ? (unsigned)n1 * 32u : 0u);
+      const double* src = P.pop_cur + (int64_t)rj * D + 4 * q0;
+      double* dst = reinterpret_cast<double*>(st + G.rows_bytes + (unsigned)(donor ? j : 0) * G.pool_bytes) + 4 * (donor ? off : 0);
+      const unsigned bytes = donor ? (unsigned)n1 * 32u : 0u;
       if (bytes) bulk_g2s(dst, src, bytes, bar);
       if (__any_sync(0xffffffffu, donor && n1 < nq)) {
         if (donor && n1 < nq) bulk_g2s(dst + 4 * n1, P.pop_cur + (int64_t)rj * D, (unsigned)(nq - n1) * 32u, bar);

@@ -27,6 +27,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// add to the transaction count of the current phase WITHOUT arriving: lets a copy that does not depend on
+// the draws (the parent row) start before the draws are made; the arrive follows with the rest of the bytes
+__device__ __forceinline__ void mbar_expect_tx_only(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 #ifndef MB2_TMA_WAIT_HINT_NS
 #define MB2_TMA_WAIT_HINT_NS 1000000u
 #endif

@@ -123,6 +123,12 @@ __global__ void __launch_bounds__(MAXT, 1)
   // (tig < 32): the draws are collective, lane 0 loads the parent row, lanes 1..k / 9..8+k the first /
   // wrapped segment of donor lane-1 / lane-9.
   auto issue = [&](int64_t c, int s) {
+    uint64_t* bar = bars + s;
+    // the parent row does not depend on the draws: its copy flies while they are made
+    if (leader) {
+      mbar_expect_tx_only(bar, row_bytes);
+      bulk_g2s(stage_row(s), P.pop_cur + c * D, row_bytes, bar);
+    }
     int64_t r[5];
     int nstart;
     draw_donors_warp_rt(P, kdon, c, lane, r, &nstart);
@@ -139,7 +145,6 @@ __global__ void __launch_bounds__(MAXT, 1)
       n2 = 0;
     }
     const bool fits = (L > 0) && (n1 + n2 <= cap);
-    uint64_t* bar = bars + s;
     if (leader) {
       ExpStageMeta* m = stage_meta(s);
       m->nstart = nstart;
@@ -149,8 +154,7 @@ __global__ void __launch_bounds__(MAXT, 1)
       m->n1 = n1;
 #pragma unroll
       for (int j = 0; j < 5; ++j) m->r[j] = r[j];
-      mbar_expect_tx(bar, row_bytes + (fits ? (unsigned)(kdon * (n1 + n2)) * 8u : 0u));
-      bulk_g2s(stage_row(s), P.pop_cur + c * D, row_bytes, bar);
+      mbar_expect_tx(bar, fits ? (unsigned)(kdon * (n1 + n2)) * 8u : 0u);  // the arrive: meta is published with it
     }
     __syncwarp();
     if (fits) {
