@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(MAXT, 1)
 
   const int D = P.dim;
   const unsigned row_bytes = (unsigned)D * 8u;
-  const size_t row_stride = ((size_t)row_bytes + 127) & ~(size_t)127;  // keep every buffer 128-B aligned
+  const unsigned row_stride = (row_bytes + 127u) & ~127u;  // keep every buffer 128-B aligned (32-bit offsets: cheap to rematerialise)
   constexpr int gthreads = GW * 32;
   const int group = threadIdx.x / gthreads;
   const int ngroups = blockDim.x / gthreads;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   const Group<GW> grp = {tig, tig >> 5, lane, 1 + group, s_scratch + group * 16};
 
   double* s_best = reinterpret_cast<double*>(smem_raw);
-  unsigned char* s_ring = smem_raw + row_stride + (size_t)group * stages * 3 * row_stride;
+  unsigned char* s_ring = smem_raw + (row_stride + (unsigned)(group * stages) * 3u * row_stride);
   uint64_t* bars = s_bar + group * kTmaMaxStages;
 
   for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     best1_draws(P, c, lane, r, &nstart);
     if (leader) {
       s_nstart[group * kTmaMaxStages + s] = nstart;
-      unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
+      unsigned char* buf = s_ring + (unsigned)s * 3u * row_stride;
       mbar_expect_tx(bars + s, 3u * row_bytes);
       bulk_g2s(buf, P.pop_cur + c * D, row_bytes, bars + s);
       bulk_g2s(buf + row_stride, P.pop_cur + r[0] * D, row_bytes, bars + s);
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   int s = 0;
   unsigned parity = 0;
   for (int64_t c = g0; c < P.np; c += ng) {
-    unsigned char* buf = s_ring + (size_t)s * 3 * row_stride;
+    unsigned char* buf = s_ring + (unsigned)s * 3u * row_stride;
     const double2* s_par = reinterpret_cast<const double2*>(buf);
     double2* s_d0 = reinterpret_cast<double2*>(buf + row_stride);  // becomes the trial vector
     const double2* s_d1 = reinterpret_cast<const double2*>(buf + 2 * row_stride);

@@ -82,9 +82,9 @@ __global__ void __launch_bounds__(MAXT, 1)
 
   const int D = P.dim;
   const unsigned row_bytes = (unsigned)D * 8u;
-  const size_t row_stride = ((size_t)row_bytes + 127) & ~(size_t)127;  // keep every buffer 128-B aligned
-  const size_t seg_stride = (size_t)cap * 8u;                           // one donor's (or the undo) buffer
-  const size_t stage_stride = (row_stride + (size_t)(kdon + 1) * seg_stride + 128 + 127) & ~(size_t)127;
+  const unsigned row_stride = (row_bytes + 127u) & ~127u;  // keep every buffer 128-B aligned (32-bit offsets: cheap to rematerialise)
+  const unsigned seg_stride = (unsigned)cap * 8u;                        // one donor's (or the undo) buffer
+  const unsigned stage_stride = (row_stride + (unsigned)(kdon + 1) * seg_stride + 128u + 127u) & ~127u;
   constexpr int gthreads = GW * 32;
   const int group = threadIdx.x / gthreads;
   const int ngroups = blockDim.x / gthreads;
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   const bool needs_best = (base == BASE_BEST1 || base == BASE_RANDTOBEST1 || base == BASE_BEST2);
 
   double* s_best = reinterpret_cast<double*>(smem_raw);
-  unsigned char* s_ring = smem_raw + row_stride + (size_t)group * stages * stage_stride;
+  unsigned char* s_ring = smem_raw + (row_stride + (unsigned)(group * stages) * stage_stride);
   uint64_t* bars = s_bar + group * kTmaMaxStages;
 
   if (needs_best)
@@ -110,13 +110,13 @@ __global__ void __launch_bounds__(MAXT, 1)
   const int64_t ng = (int64_t)gridDim.x * ngroups;
 
   // stage layout: [row][undo cap][donor 0 cap]...[donor k-1 cap][meta]
-  auto stage_row = [&](int s) { return reinterpret_cast<double*>(s_ring + (size_t)s * stage_stride); };
-  auto stage_undo = [&](int s) { return reinterpret_cast<double*>(s_ring + (size_t)s * stage_stride + row_stride); };
+  auto stage_row = [&](int s) { return reinterpret_cast<double*>(s_ring + (unsigned)s * stage_stride); };
+  auto stage_undo = [&](int s) { return reinterpret_cast<double*>(s_ring + ((unsigned)s * stage_stride + row_stride)); };
   auto stage_don = [&](int s, int j) {
-    return reinterpret_cast<double*>(s_ring + (size_t)s * stage_stride + row_stride + (size_t)(1 + j) * seg_stride);
+    return reinterpret_cast<double*>(s_ring + ((unsigned)s * stage_stride + row_stride + (unsigned)(1 + j) * seg_stride));
   };
   auto stage_meta = [&](int s) {
-    return reinterpret_cast<ExpStageMeta*>(s_ring + (size_t)s * stage_stride + row_stride + (size_t)(kdon + 1) * seg_stride);
+    return reinterpret_cast<ExpStageMeta*>(s_ring + ((unsigned)s * stage_stride + row_stride + (unsigned)(kdon + 1) * seg_stride));
   };
 
   // Draws of candidate c and its loads into stage s.  Called by the whole leader WARP of the group

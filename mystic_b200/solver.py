@@ -562,6 +562,21 @@ class DifferentialEvolutionSolver2(object):
     def Finalize(self):
         self._live = False
 
+    # ---- collapse (abstract_solver.py:783-892): the collapse conditions of mystic.termination
+    # (CollapseAt, CollapseAs, ...) read the whole solution history on the host and rewrite the
+    # constraints; they are outside the data-parallel path, so a device solver
+    # never reports a collapse -- Solve() of the reference keeps going exactly like that when no
+    # collapse condition is installed
+    def Collapsed(self, disp=False, info=False):
+        return {} if info else False
+
+    def Collapse(self, disp=False):
+        return {}
+
+    def _is_new(self):
+        'determine if solver has been run or not (abstract_solver.py:1255-1257)'
+        return bool(self.evaluations) or bool(self.generations)
+
     def _make_engine(self):
         if self._engine_factory is not None:
             return self._engine_factory(self._np_local, self.nDim, self.nPop, self._offset,

@@ -276,3 +276,25 @@ def test_logging_monitors_write_the_reference_layout(tmp_path, capsys):
     assert capsys.readouterr().out.splitlines() == ['Generation 0 has cost: 1.0', 'Generation 2 has cost: 3.0']
     assert (tmp_path / 'v.txt').read_text().splitlines()[1:] == ['# ___#___  __cost__  __params__', '  (0,)     1.0   [0.5]',
                                                                 '  (1,)     2.0   [0.5]', '  (2,)     3.0   [0.5]']
+
+
+def test_collapse_interface_and_deepcopy():
+    """abstract_solver.py:783-892, 1255-1257: a device solver never collapses (no collapse conditions on the
+    data-parallel path), `_is_new` follows the counters, copy.deepcopy goes through the restart state"""
+    import copy
+    from mystic_b200 import DifferentialEvolutionSolver2, models, termination
+    s = DifferentialEvolutionSolver2(3, 12, rng='philox', seed=3, engine=OracleEngine)
+    s.SetRandomInitialPoints([-2.] * 3, [2.] * 3)
+    s.SetTermination(termination.VTR(1e-9))
+    s.SetEvaluationLimits(generations=5)
+    assert s._is_new() is False and s.Collapsed() is False and s.Collapsed(info=True) == {} and s.Collapse() == {}
+    s.Solve(models.rosen)
+    assert s._is_new() is True and s.generations == 5
+    t = copy.deepcopy(s)
+    assert t.generations == 5 and t.bestEnergy == s.bestEnergy and np.array_equal(t.population, s.population)
+    t.SetEvaluationLimits(generations=8)
+    s.SetEvaluationLimits(generations=8)
+    t.Solve()
+    s.Solve()
+    assert t.generations == s.generations == 8 and t.bestEnergy == s.bestEnergy
+    G.assert_bits_equal(t.population, s.population, 'a copy continues like the original')
