@@ -81,6 +81,8 @@ struct mb2_ctx {
   // every row of the current population lies inside [lo, hi]: generation 0 clipped it with these
   // bounds and nothing has replaced rows or bounds since (lets kernels skip re-checking parents)
   int rows_in_range = 0;
+  int rows_checked = 0;   // the rows have been tested against the current bounds since either last changed
+  int* range_flag = nullptr;
   double lo_s = 0.0, hi_s = 0.0;
   double* lo = nullptr;
   double* hi = nullptr;
@@ -438,6 +440,29 @@ int launch_step_islands(mb2_ctx* c, int mode, cudaStream_t stream) {
 int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, const double* e_in, double* e_out,
                 int64_t np, cudaStream_t stream) {
   if (c->n_islands > 1 && mode != MODE_EVAL) return launch_step_islands(c, mode, stream);
+  // Rows that were installed by the caller (restart files, SetPopulation) or bounds that changed after
+  // generation 0 (SetStrictRanges mid-run): test the population once; when every row lies inside the range
+  // the kernels may treat the untouched elements of a trial as in range, as after a generation-0 clip
+  if (mode == MODE_STEP && c->bounds_mode != BOUNDS_NONE && !c->rows_in_range && !c->rows_checked && in_rows == c->pop[c->cur]) {
+    if (c->range_flag == nullptr) {
+      void* p = nullptr;
+      if (int rc = dev_alloc(c, sizeof(int), &p)) return rc;
+      c->range_flag = (int*)p;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->range_flag, 0, sizeof(int), stream));
+    const int64_t n = np * c->dim;
+    int64_t g = (n + 255) / 256;
+    if (g > (int64_t)c->sm_count * 16) g = (int64_t)c->sm_count * 16;
+    rows_outside_range_kernel<<<(unsigned)g, 256, 0, stream>>>(in_rows, n, c->dim, c->lo, c->hi, c->bounds_uniform, c->lo_s, c->hi_s,
+                                                                c->range_flag);
+    CUDA_TRY(cudaGetLastError());
+    ++c->launches;
+    int outside = 1;
+    CUDA_TRY(cudaMemcpyAsync(&outside, c->range_flag, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    c->rows_checked = 1;
+    c->rows_in_range = outside ? 0 : 1;
+  }
   const bool vec = (c->dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(in_rows) & 15) == 0) &&
                    (out_rows == nullptr || (reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
   StrategyInfo s = c->sinfo;
@@ -775,6 +800,7 @@ int mb2_bind_buffers(mb2_ctx* c, double* pop_a, double* pop_b, double* e_a, doub
   c->cur = 0;
   c->generation = -1;
   c->rows_in_range = 0;
+  c->rows_checked = 0;
   return MB2_OK;
 }
 
@@ -820,6 +846,7 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
   }
   c->bounds_mode = mode;
   c->rows_in_range = 0;
+  c->rows_checked = 0;
   return MB2_OK;
 }
 
@@ -1056,6 +1083,7 @@ int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const doubl
   CUDA_TRY(cudaStreamSynchronize(s));  // lo/hi are pageable host buffers
   c->generation = -1;
   c->rows_in_range = 0;
+  c->rows_checked = 0;
   return MB2_OK;
 }
 
@@ -1073,6 +1101,7 @@ int mb2_upload_population(mb2_ctx* c, const double* pop_host, void* stream) {
   CUDA_TRY(cudaStreamSynchronize(s));
   c->generation = -1;
   c->rows_in_range = 0;
+  c->rows_checked = 0;
   return MB2_OK;
 }
 
@@ -1088,6 +1117,7 @@ int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy,
   CUDA_TRY(cudaMemcpy(c->st, &st, sizeof(st), cudaMemcpyHostToDevice));
   c->generation = generation;
   c->rows_in_range = 0;  // the caller installed rows this context has not checked
+  c->rows_checked = 0;
   return MB2_OK;
 }
 

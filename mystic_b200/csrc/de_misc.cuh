@@ -304,6 +304,19 @@ __global__ void selftest_cosine_kernel(int64_t n, uint32_t k0, uint32_t k1, doub
   atomicMax(max_bits, (unsigned long long)__double_as_longlong(worst));
 }
 
+// does every element of the rows lie inside the strict range?  (*flag |= 1 when one does not; NaN counts as outside)
+__global__ void rows_outside_range_kernel(const double* __restrict__ rows, int64_t n, int D, const double* __restrict__ lo,
+                                          const double* __restrict__ hi, int uniform, double lo_s, double hi_s, int* flag) {
+  bool bad = false;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const double x = rows[t];
+    const int j = (int)(t % D);
+    const double l = uniform ? lo_s : __ldg(lo + j), h = uniform ? hi_s : __ldg(hi + j);
+    bad |= !(x >= l && x <= h);
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
 __global__ void fill_kernel(double* __restrict__ p, int64_t n, double v) {
   for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) p[t] = v;
 }

@@ -124,6 +124,32 @@ def test_rows_not_known_to_be_in_range_keep_the_tiled_kernel(monkeypatch):
     eng.close()
 
 
+@pytest.mark.parametrize('mode', [orc.BOUNDS_CLAMP, orc.BOUNDS_REJECT])
+def test_rows_found_in_range_take_the_bulk_kernel(mode, monkeypatch):
+    """a strict range set after generation 0 (or rows installed by the caller: restart files) that every row
+    already satisfies: the engine tests the population once and then treats it like a clipped one"""
+    for k in ENV:
+        monkeypatch.delenv(k, raising=False)
+    dim, NP, strat, cost, CR, F, seed = 64, 333, 'Rand1Exp', 'rosen', 0.9, 0.8, 77
+    eng, _, _, _ = _engine(dim, NP, strat, cost, None, None, CR, F)
+    eng.set_rng_philox(seed)
+    ilo, ihi = np.full(dim, -3.0), np.full(dim, 3.0)
+    eng.init_population(seed, ilo, ihi)
+    st = orc.DEState(orc.philox_init_population(seed, NP, ilo, ihi))
+    ocost = orc.make_cost(cost, ())
+    eng.eval_initial()
+    orc.step0(st, ocost)
+    lo, hi = np.full(dim, -3.0), np.full(dim, 3.5)      # the initial box: nothing is outside
+    eng.set_bounds(mode, lo, hi)
+    st.lo, st.hi, st.bounds_mode = lo, hi, mode
+    for g in range(1, 4):
+        eng.step()
+        assert eng.kernel_family() == 'rows_bulk'
+        orc.step(st, strat, CR, F, ocost, (), philox=dict(seed=seed, offset=0))
+        _compare(eng, st, cost, 'gen %d' % g)
+    eng.close()
+
+
 @pytest.mark.parametrize('strat,cost,dim,NP,pen', [
     ('Rand1Exp', 'corana', 64, 300001, [dict(ptype='quadratic_inequality', G=[1.] * 64, h=100., k=100, hpow=5)]),
     ('Best1Exp', 'griewangk', 128, 100003, None),
