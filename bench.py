@@ -42,6 +42,11 @@ WORKLOADS = {
     'c5': dict(desc='Griewangk 256-D, NP=2097152/GPU, Best1Bin CR=0.9 F=0.8, clamp +-400',
                cost='griewangk', extra=(), dim=256, np=2097152, strategy='Best1Bin', CR=0.9, F=0.8, lo=-400.,
                hi=400., bounds='clamp', penalty=None, k=2),
+    # BASELINE config 5 at its full size: NP = 16 M rows in total (32 GiB per population buffer), split over the
+    # ranks (strong scaling); the end-to-end leg is skipped (it would pin 32 GiB of host memory per run)
+    'c5s': dict(desc='Griewangk 256-D, NP=16777216 in total (strong scaling), Best1Bin CR=0.9 F=0.8, clamp +-400',
+                cost='griewangk', extra=(), dim=256, np=16777216, strategy='Best1Bin', CR=0.9, F=0.8, lo=-400.,
+                hi=400., bounds='clamp', penalty=None, k=2, strong=True, no_e2e=True),
     'c3': dict(desc='chebyshev8cost M=4096, 9 coeffs, NP=1048576/GPU, Best1Exp CR=1.0 F=0.9, init +-100 (FP64 DMMA)',
                cost='chebyshev8cost', extra=(4096,), dim=9, np=1048576, strategy='Best1Exp', CR=1.0, F=0.9,
                lo=-100., hi=100., bounds=None, penalty=None, k=2, tensor_cores=True),
@@ -320,7 +325,7 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
-    NP_local = w['np']
+    NP_local = w['np'] // world if w.get('strong') else w['np']
     NP_global = NP_local * world
     D = w['dim']
     seed = 0x5EED
@@ -383,12 +388,13 @@ def main():
     # ---- end to end: host population (pinned) -> H2D -> generation 0 -> K x Step() with the result
     #      of every step read back to the host
     numa_node = bind_to_gpu_numa_node(local_rank)
-    host_pop = torch.empty((NP_local, D), dtype=torch.float64, pin_memory=True)
+    host_rows = 1 if w.get('no_e2e') else NP_local
+    host_pop = torch.empty((host_rows, D), dtype=torch.float64, pin_memory=True)
     rng = np.random.default_rng(seed + rank)
     hp = host_pop.numpy()
     chunk = max(1, (1 << 24) // D)
-    for i in range(0, NP_local, chunk):
-        hp[i:i + chunk] = rng.uniform(w['lo'], w['hi'], size=(min(chunk, NP_local - i), D))
+    for i in range(0, host_rows, chunk):
+        hp[i:i + chunk] = rng.uniform(w['lo'], w['hi'], size=(min(chunk, host_rows - i), D))
     def e2e_run():
         s2 = build_solver(w, NP_global, distributed, seed)
         s2.SetTermination(never)
@@ -409,8 +415,11 @@ def main():
         gc.collect()
         return dt
 
-    e2e_run()                                    # warm-up: device allocations come from torch's cache afterwards
-    e2e_s = min(e2e_run(), e2e_run())            # best of two (host-side jitter: PCIe, page faults)
+    if w.get('no_e2e'):
+        e2e_s = float('nan')
+    else:
+        e2e_run()                                # warm-up: device allocations come from torch's cache afterwards
+        e2e_s = min(e2e_run(), e2e_run())        # best of two (host-side jitter: PCIe, page faults)
     t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -452,7 +461,7 @@ def main():
     line = {
         'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': value, 'unit': 'candidate-evals/s',
         'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'scaling': 'strong' if w.get('strong') else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': w['desc'], 'np_per_gpu': NP_local, 'np_total': NP_global, 'dim': D,
                    'rng': 'philox4x32-10 in-kernel', 'l2': 'inputs larger than L2 (population %.0f MiB per buffer)'
                    % (NP_local * D * 8 / 2 ** 20), 'grid': grid, 'block': block, 'smem_bytes': smem,
@@ -471,6 +480,10 @@ def main():
         'gpu_launches': int(launches),
         'clocks': clocks,
     }
+    if w.get('no_e2e'):
+        line['e2e'] = {'value': None, 'unit': 'candidate-evals/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': d2h_per_step,
+                       'what': 'not measured for this workload: the host copy of the population is %.0f GiB per rank'
+                               % (NP_local * D * 8 / 2 ** 30)}
     if world == 1 and not args.no_cpu_baseline:
         v, dt, kind, cores, sample = time_oracle(w, min(w['np'], args.ref_np), 3, 1)
         line['cpu_baseline'] = {'value': v, 'unit': 'candidate-evals/s', 'cores': cores, 'kind': kind, 'sample': sample}
