@@ -663,3 +663,27 @@ def test_chebyshev_dmma_huge_coefficients_take_the_horner_fallback():
     assert np.array_equal(np.isnan(got), np.isnan(want)) and np.array_equal(np.isinf(got), np.isinf(want))
     fin = np.isfinite(want)
     assert fin.sum() >= 124 and np.allclose(got[fin], want[fin], rtol=1e-12, atol=0)
+
+
+def test_abi_rejects_malformed_requests():
+    """error behaviour of the C ABI: negative return code + message, no exception across the boundary, the
+    context stays usable"""
+    from mystic_b200 import models
+    from mystic_b200._native import NativeError
+    from mystic_b200.engine import DeviceEngine
+    eng = DeviceEngine(16, 3)
+    for cost in (models.zimmermann, models.branins, models.shekel):
+        with pytest.raises(NativeError, match='two variables|dim == 2'):
+            eng.set_cost(cost.cost_id, ())
+    with pytest.raises(NativeError, match='unknown cost id'):
+        eng.set_cost(99, ())
+    with pytest.raises(NativeError, match='mb2_eval_initial must run before'):
+        eng.set_cost(models.rosen.cost_id, ())
+        eng.step()
+    eng.set_cost(models.ellipsoid.cost_id, ())       # any number of variables
+    eng.set_rng_philox(1)
+    eng.init_population(1, np.full(3, -1.), np.full(3, 1.))
+    eng.eval_initial()
+    eng.step()
+    assert np.isfinite(eng.read_result()[0])
+    eng.close()

@@ -98,14 +98,14 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, unsigned by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
 }
 
-template <int K, int ST, int WARPS>
+template <int K, int ST, int WARPS, int R = 8>
 __global__ void __launch_bounds__(WARPS * 32) bulk_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t np, int D,
                                                           int seg, uint32_t salt) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t bars[WARPS * ST];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const unsigned rowb = (unsigned)D * 8u, segb = (unsigned)seg * 32u;
-  const size_t stage_bytes = 8 * (size_t)rowb + 8 * (size_t)K * segb;
+  const size_t stage_bytes = R * (size_t)rowb + R * (size_t)K * segb;
   unsigned char* my = smem + (size_t)warp * ST * stage_bytes;
   uint64_t* bar = bars + warp * ST;
   if (lane == 0)
@@ -118,19 +118,19 @@ __global__ void __launch_bounds__(WARPS * 32) bulk_kernel(const double* __restri
     unsigned char* st = my + (size_t)s * stage_bytes;
     if (lane == 0) mbar_expect_tx(bar + s, (unsigned)stage_bytes);
     __syncwarp();
-    if (lane < 8) {
-      bulk_g2s(st + lane * rowb, in + (ch * 8 + lane) * D, rowb, bar + s);
-    } else if (lane < 8 + 8 * K) {
-      const int row = (lane - 8) & 7, j = (lane - 8) >> 3;
-      const int64_t c = ch * 8 + row;
+    if (lane < R) {
+      bulk_g2s(st + lane * rowb, in + (ch * R + lane) * D, rowb, bar + s);
+    } else if (lane < R + R * K) {
+      const int row = (lane - R) % R, j = (lane - R) / R;
+      const int64_t c = ch * R + row;
       const uint32_t h = mix((uint32_t)c * 0x9E3779B9u + salt);
       int q0 = (int)(h % (uint32_t)NQ);
       if (q0 + seg > NQ) q0 = NQ - seg;  // no wrap in the probe
       const int64_t r = (int64_t)(mix(h + 0x51ED270Bu * (j + 1)) % (uint32_t)np);
-      bulk_g2s(st + 8 * rowb + (size_t)(j * 8 + row) * segb, in + r * D + 4 * q0, segb, bar + s);
+      bulk_g2s(st + R * rowb + (size_t)(j * R + row) * segb, in + r * D + 4 * q0, segb, bar + s);
     }
   };
-  int64_t nch = np / 8;
+  int64_t nch = np / R;
   for (int s = 0; s < ST; ++s)
     if (gw + s * nw < nch) issue(gw + s * nw, s);
   int s = 0;
@@ -139,15 +139,15 @@ __global__ void __launch_bounds__(WARPS * 32) bulk_kernel(const double* __restri
     unsigned char* st = my + (size_t)s * stage_bytes;
     mbar_wait(bar + s, parity);
     // touch: add the first donor element of each segment to the first element of its row
-    if (K > 0 && lane < 8) {
+    if (K > 0 && lane < R) {
       double a = 0.0;
-      for (int j = 0; j < K; ++j) a += *reinterpret_cast<double*>(st + 8 * rowb + (size_t)(j * 8 + lane) * segb);
+      for (int j = 0; j < K; ++j) a += *reinterpret_cast<double*>(st + R * rowb + (size_t)(j * R + lane) * segb);
       *reinterpret_cast<double*>(st + lane * rowb) += a;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane < 8) {
-      bulk_s2g(out + (ch * 8 + lane) * D, st + lane * rowb, rowb);
+    if (lane < R) {
+      bulk_s2g(out + (ch * R + lane) * D, st + lane * rowb, rowb);
       asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     }
@@ -158,18 +158,18 @@ __global__ void __launch_bounds__(WARPS * 32) bulk_kernel(const double* __restri
       parity ^= 1u;
     }
   }
-  if (lane < 8) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (lane < R) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int K, int ST, int WARPS>
+template <int K, int ST, int WARPS, int R = 8>
 static void run_bulk(const double* in, double* out, int64_t np, int D, int seg) {
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  const size_t smem = (size_t)WARPS * ST * (8 * (size_t)D * 8 + 8 * (size_t)K * seg * 32);
-  cudaFuncSetAttribute(bulk_kernel<K, ST, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t smem = (size_t)WARPS * ST * (R * (size_t)D * 8 + R * (size_t)K * seg * 32);
+  cudaFuncSetAttribute(bulk_kernel<K, ST, WARPS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int occ = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bulk_kernel<K, ST, WARPS>, WARPS * 32, smem);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bulk_kernel<K, ST, WARPS, R>, WARPS * 32, smem);
   if (occ < 1) {
     printf("{\"bulk\": true, \"error\": \"does not fit\", \"smem\": %zu}\n", smem);
     return;
@@ -178,7 +178,7 @@ static void run_bulk(const double* in, double* out, int64_t np, int D, int seg) 
   float best = 1e30f;
   for (int rep = 0; rep < 12; ++rep) {
     cudaEventRecord(e0);
-    bulk_kernel<K, ST, WARPS><<<grid, WARPS * 32, smem>>>(in, out, np, D, seg, 17u * rep + 1u);
+    bulk_kernel<K, ST, WARPS, R><<<grid, WARPS * 32, smem>>>(in, out, np, D, seg, 17u * rep + 1u);
     cudaEventRecord(e1);
     cudaEventSynchronize(e1);
     float ms;
@@ -186,8 +186,8 @@ static void run_bulk(const double* in, double* out, int64_t np, int D, int seg) 
     if (rep >= 2 && ms < best) best = ms;
   }
   const double bytes = (double)np * (16.0 * D + (double)K * seg * 32.0);
-  printf("{\"bulk\": true, \"donors\": %d, \"chunks_per_donor\": %d, \"stages\": %d, \"warps\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"requested_GB\": %.4f, \"GBps\": %.1f}\n",
-         K, seg, ST, WARPS, occ, best, bytes / 1e9, bytes / 1e6 / best);
+  printf("{\"bulk\": true, \"donors\": %d, \"chunks_per_donor\": %d, \"stages\": %d, \"warps\": %d, \"rows_per_stage\": %d, \"ctas_per_sm\": %d, \"ms\": %.4f, \"requested_GB\": %.4f, \"GBps\": %.1f}\n",
+         K, seg, ST, WARPS, R, occ, best, bytes / 1e9, bytes / 1e6 / best);
 }
 
 template <int K>
@@ -219,6 +219,17 @@ int main(int argc, char** argv) {
   cudaMalloc(&b, sizeof(double) * np * D);
   cudaMemset(a, 0, sizeof(double) * np * D);
   cudaMemset(b, 0, sizeof(double) * np * D);
+  if (D >= 512) {  // long rows (x2: Rosenbrock 1024-D, exponential crossover): one row per stage
+    run_bulk<0, 1, 16, 1>(a, b, np, D, 0);
+    run_bulk<0, 2, 8, 1>(a, b, np, D, 0);
+    run_bulk<3, 1, 16, 1>(a, b, np, D, 3);
+    run_bulk<3, 2, 8, 1>(a, b, np, D, 3);
+    run_bulk<3, 2, 12, 1>(a, b, np, D, 3);
+    run_bulk<3, 1, 24, 1>(a, b, np, D, 3);
+    run_bulk<2, 2, 12, 1>(a, b, np, D, 3);
+    cudaDeviceSynchronize();
+    return 0;
+  }
   for (int occ : {2, 4, 8}) {
     run<0>(a, b, np, D, 0, occ);
     run<3>(a, b, np, D, 1, occ);
