@@ -202,3 +202,27 @@ def test_equals_warp_per_row_kernel_bit_for_bit(strat, cost, dim, NP, monkeypatc
     a, b = out['1'][2], out['0'][2]
     assert a[:5] == b[:5]
     G.assert_bits_equal(a[5], b[5], 'best member')
+
+
+@pytest.mark.parametrize('dim', [130, 384, 1000, 2050, 4096, 8190, 12000, 14000])
+@pytest.mark.parametrize('strat,CR', [('Best1Exp', 0.5), ('Rand1Exp', 1.0), ('Best2Exp', 0.9), ('Rand2Exp', 0.999), ('Best1Bin', 0.9)])
+def test_every_supported_row_length_launches_and_matches(dim, strat, CR, monkeypatch):
+    """the ring geometries are derived from the row length, the donor count and CR (de_abi.cu: tma_geometry,
+    exp_tma_geometry): every combination up to the longest row a CTA can hold must fit the 227 KB of shared
+    memory, launch, and agree with the oracle"""
+    for k in ('MB2_XTMA_CAP', 'MB2_XTMA_GROUPS', 'MB2_XTMA_GWARPS', 'MB2_XTMA_STAGES', 'MB2_TMA_EXP'):
+        monkeypatch.delenv(k, raising=False)
+    NP, cost, F, seed = 24, 'sphere' if dim % 3 else 'rosen', 0.7, 4242 + dim
+    eng, lo, hi, mode = _engine(dim, NP, strat, cost, (-4., 4., orc.BOUNDS_CLAMP), None, CR, F)
+    eng.set_rng_philox(seed)
+    eng.init_population(seed, lo, hi)
+    st = orc.DEState(orc.philox_init_population(seed, NP, lo, hi), lo, hi, mode)
+    ocost = orc.make_cost(cost, ())
+    eng.eval_initial()
+    orc.step0(st, ocost)
+    for g in range(1, 3):
+        eng.step()
+        orc.step(st, strat, CR, F, ocost, (), philox=dict(seed=seed, offset=0))
+        _compare(eng, st, cost, 'D=%d %s gen %d (%s)' % (dim, strat, g, eng.kernel_family()))
+    assert eng.kernel_family() in ('tma_exp', 'tma_bin', 'warp_per_row')
+    eng.close()
