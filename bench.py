@@ -42,6 +42,10 @@ WORKLOADS = {
     'c5': dict(desc='Griewangk 256-D, NP=2097152/GPU, Best1Bin CR=0.9 F=0.8, clamp +-400',
                cost='griewangk', extra=(), dim=256, np=2097152, strategy='Best1Bin', CR=0.9, F=0.8, lo=-400.,
                hi=400., bounds='clamp', penalty=None, k=2),
+    # mystic's default strategy on short rows (not a BASELINE config): whole donor rows, binomial crossover
+    'b4': dict(desc='Rosenbrock 64-D, NP=1048576/GPU, Best1Bin CR=0.9 F=0.8, clamp +-5 (binomial crossover, short rows)',
+               cost='rosen', extra=(), dim=64, np=1048576, strategy='Best1Bin', CR=0.9, F=0.8, lo=-5., hi=5.,
+               bounds='clamp', penalty=None, k=2),
     # BASELINE config 5 at its full size: NP = 16 M rows in total (32 GiB per population buffer), split over the
     # ranks (strong scaling); the end-to-end leg is skipped (it would pin 32 GiB of host memory per run)
     'c5s': dict(desc='Griewangk 256-D, NP=16777216 in total (strong scaling), Best1Bin CR=0.9 F=0.8, clamp +-400',
