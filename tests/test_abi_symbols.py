@@ -47,3 +47,18 @@ def test_no_gpu_means_loud_failure():
     s.SetRandomInitialPoints([-1.] * 3, [1.] * 3)
     with pytest.raises(RuntimeError):
         s.Step(models.rosen)
+
+
+def test_missing_library_fails_loudly():
+    """no CPU fallback: without the CUDA library the package cannot drive a solver (the import of the native
+    layer raises and says how to build it)"""
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MB2_LIBRARY=os.path.join(repo, 'mystic_b200', '_lib', 'no_such_library.so'))
+    code = ('import mystic_b200._native as n\n')
+    proc = subprocess.run([sys.executable, '-c', code], cwd=repo, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                          universal_newlines=True, timeout=120)
+    assert proc.returncode != 0
+    assert 'is missing' in proc.stdout and 'no CPU fallback' in proc.stdout, proc.stdout[-2000:]
