@@ -13,6 +13,7 @@ import numpy as np
 
 inf = float('inf')
 EARLYEXIT = 0
+_type = type
 
 
 class _Condition(object):
@@ -95,6 +96,51 @@ def _spread(inst, tolerance):
     return bool(np.all(np.abs(sim - sim[0]) <= np.abs(tolerance * sim[0])))
 
 
+def _improvement(inst, tolerance):
+    """termination.py:275-285: the largest sum over the parameters of |bestSolution - trial| over the trial
+    population (needs the trial vectors: construct the solver with keep_trials=True)"""
+    best = np.array(inst.bestSolution)
+    trial = np.array(inst.trialSolution)
+    answer = np.add.reduce(abs(best - trial).T)
+    if isinstance(answer, np.ndarray):
+        answer = max(answer)
+    return bool(answer <= tolerance)
+
+
+_EPSILON = float(np.sqrt(np.finfo(float).eps))   # mystic/_scipy060optimize.py:47
+
+
+def _gradnorm(inst, tolerance, norm):
+    """termination.py:369-382: forward-difference gradient of the raw cost at bestSolution
+    (_scipy060optimize.py:611-619: D + 1 cost evaluations per test), Lnorm of math/distance.py:24-39"""
+    grad = getattr(inst, 'gradient', [None])[-1]
+    if grad is None:
+        soln = np.asarray(inst.bestSolution, dtype=np.float64)
+        cost = inst._cost[1]
+        pts = np.vstack([soln] + [soln + _EPSILON * np.eye(len(soln))[k] for k in range(len(soln))])
+        try:
+            f = np.asarray(cost(pts), dtype=np.float64)          # device costs take a batch of rows
+            if f.shape != (len(soln) + 1,):
+                raise TypeError
+        except TypeError:
+            f = np.array([cost(x) for x in pts], dtype=np.float64)
+        grad = (f[1:] - f[0]) / _EPSILON
+    w = np.asarray(grad, dtype=np.float64)
+    if not norm:
+        gnorm = np.sum(w != 0.0, dtype=float)
+    elif norm == inf:
+        gnorm = np.max(np.abs(w))
+    elif norm == -inf:
+        gnorm = np.min(np.abs(w))
+    else:
+        with np.errstate(over='raise', invalid='raise'):
+            try:
+                gnorm = np.sum(np.abs(w ** norm)) ** (1. / norm)
+            except FloatingPointError:
+                gnorm = np.max(np.abs(w))
+    return bool(gnorm <= tolerance)
+
+
 def _limits(inst, generations, evaluations):
     maxiter = inf if generations is None else generations
     maxfun = inf if evaluations is None else evaluations
@@ -107,7 +153,8 @@ def _interrupt(inst):
 
 _TESTS = {'VTR': _vtr, 'ChangeOverGeneration': _cog, 'NormalizedChangeOverGeneration': _ncog,
           'VTRChangeOverGeneration': _vtrcog, 'NormalizedCostTarget': _nct, 'CandidateRelativeTolerance': _crt,
-          'PopulationSpread': _spread, 'EvaluationLimits': _limits, 'SolverInterrupt': _interrupt}
+          'PopulationSpread': _spread, 'EvaluationLimits': _limits, 'SolverInterrupt': _interrupt,
+          'SolutionImprovement': _improvement, 'GradientNormTolerance': _gradnorm}
 
 
 def VTR(tolerance=0.005, target=0.0):
@@ -144,6 +191,16 @@ def CandidateRelativeTolerance(xtol=1e-4, ftol=1e-4):
 def PopulationSpread(tolerance=1e-6):
     """abs(params - params[0]) <= abs(tolerance*params[0]); reads the whole population (termination.py:344-361)"""
     return _Condition('PopulationSpread', {'tolerance': tolerance})
+
+
+def SolutionImprovement(tolerance=1e-5):
+    """sum(abs(last_params - current_params)) <= tolerance; reads the trial population (termination.py:269-288)"""
+    return _Condition('SolutionImprovement', {'tolerance': tolerance})
+
+
+def GradientNormTolerance(tolerance=1e-5, norm=inf):
+    """sum(abs(gradient)**norm)**(1.0/norm) <= tolerance, forward-difference gradient (termination.py:363-384)"""
+    return _Condition('GradientNormTolerance', {'tolerance': tolerance, 'norm': norm})
 
 
 def EvaluationLimits(generations=None, evaluations=None):
@@ -250,6 +307,13 @@ class Or(When):
 
     def __repr__(self):
         return 'Or%s' % str(tuple(f for f in self))
+
+
+def type(condition):
+    """get object that generated the given termination instance (termination.py:29-39)"""
+    if isinstance(condition, _Condition):
+        return globals()[condition.name]
+    return _type(condition)
 
 
 def state(condition):

@@ -687,3 +687,31 @@ def test_abi_rejects_malformed_requests():
     eng.step()
     assert np.isfinite(eng.read_result()[0])
     eng.close()
+
+
+def test_gradient_norm_tolerance_on_device():
+    """termination.py:363-384 with the forward-difference gradient of _scipy060optimize.py:611-619: the D + 1
+    cost evaluations go through the device cost (one batch), the verdict equals the oracle's arithmetic"""
+    from mystic_b200 import DifferentialEvolutionSolver2, models, termination
+    D = 5
+    s = DifferentialEvolutionSolver2(D, 40, rng='philox', seed=21)
+    s.SetRandomInitialPoints([-2.] * D, [2.] * D)
+    s.SetTermination(termination.VTR(-1.0))
+    s.SetEvaluationLimits(generations=10 ** 6)
+    s.Step(models.rosen)
+    for _ in range(5):
+        s.Step()
+    x = np.asarray(s.bestSolution, dtype=np.float64)
+    eps = float(np.sqrt(np.finfo(float).eps))
+    f = orc.cost_rosen(np.vstack([x] + [x + eps * np.eye(D)[k] for k in range(D)]))
+    grad = (f[1:] - f[0]) / eps
+    for norm, gnorm in ((termination.inf, np.max(np.abs(grad))), (2, np.sum(np.abs(grad ** 2)) ** 0.5), (1, np.sum(np.abs(grad)))):
+        assert gnorm > 0
+        assert termination.GradientNormTolerance(gnorm * 1.001, norm)(s) is True
+        assert termination.GradientNormTolerance(gnorm * 0.999, norm)(s) is False
+        assert termination.GradientNormTolerance(gnorm * 1.001, norm)(s, info=True).startswith('GradientNormTolerance with')
+    # as a stop condition of Solve(): a huge tolerance stops after the first generation
+    s2 = DifferentialEvolutionSolver2(D, 40, rng='philox', seed=21)
+    s2.SetRandomInitialPoints([-2.] * D, [2.] * D)
+    s2.Solve(models.rosen, termination.GradientNormTolerance(1e30))
+    assert s2.generations <= 1 and str(s2.Terminated(info=True)).startswith('GradientNormTolerance with')

@@ -179,3 +179,30 @@ def test_diffev2_one_call_interface_matches_the_reference(capsys):
     got = diffev2(mystic.models.rosen, [0.8, 1.2, 0.7], npop=16, ftol=1e-2, full_output=1, disp=0, rng='reference',
                   engine=OracleEngine)
     assert list(got[0]) == list(want[0]) and got[1:] == want[1:]
+
+
+def test_population_reading_terminations_equal_the_reference_ones():
+    """SolutionImprovement / CandidateRelativeTolerance / PopulationSpread (termination.py:242-288, 344-361) read
+    the population and the trial vectors of the solver: the twins of mystic_b200.termination and the
+    unmodified mystic.termination objects must give the same verdict, generation by generation"""
+    from mystic_b200 import termination as T
+    s = DifferentialEvolutionSolver2(4, 20, rng='philox', seed=11, engine=OracleEngine, keep_trials=True)
+    s.SetRandomInitialPoints([-1.] * 4, [1.] * 4)
+    s.SetTermination(T.VTR(-1.0))
+    s.SetEvaluationLimits(generations=10 ** 6)
+    from mystic_b200 import models
+    s.Step(models.sphere)
+    pairs = [(T.SolutionImprovement(t), mystic.termination.SolutionImprovement(t)) for t in (1e-3, 0.5, 2.0, 50.)]
+    pairs += [(T.CandidateRelativeTolerance(x, f), mystic.termination.CandidateRelativeTolerance(x, f))
+              for x, f in ((1e-4, 1e-4), (0.5, 0.5), (3.0, 10.0))]
+    pairs += [(T.PopulationSpread(t), mystic.termination.PopulationSpread(t)) for t in (1e-6, 0.5, 1e3)]
+    verdicts = set()
+    for g in range(60):
+        s.Step()
+        for ours, theirs in pairs:
+            assert ours(s) == theirs(s), (g, ours.__doc__)
+            assert ours(s, info=True) == theirs(s, info=True), (g, ours.__doc__)
+            verdicts.add((ours.__doc__, ours(s)))
+    assert len(verdicts) > len(pairs)          # some conditions changed their verdict along the run
+    assert T.type(pairs[0][0]) is T.SolutionImprovement and T.type(3) is int
+    assert T.state(pairs[0][0]) == {'SolutionImprovement with %s' % {'tolerance': 1e-3}: {'tolerance': 1e-3}}
