@@ -1,23 +1,25 @@
 // K2f: the short-row generation step (K2d's row lengths: D a multiple of 4, 16 <= D <= 128) with every
 // byte moved by the bulk-copy engine, for the exponential-crossover strategies.
 //
-// What bounds K2d (de_rows.cuh) is the per-warp chain draws -> donor loads -> wait -> compute -> store:
-// 37 % of its stall samples wait for donor data, and prefetching in software costs registers or LSU
-// slots it does not have.  `tools/gather_peak.cu` shows the copy engine moves the same pattern (a
-// 512-byte parent row and three ~96-byte donor segments in, a row out) in 0.240-0.245 ms at NP = 1 M
-// with almost no instructions (K2d: 0.341-0.350 ms; the plain-load pattern's own ceiling: 0.26-0.27 ms).
-// So here a warp owns a ring of `stages` buffers of 32/LPR rows:
-//   * issue (one stage ahead): the draws of the stage's rows (rows_draw, de_rows.cuh: the same Philox
-//     blocks as every kernel), the window chunks q0 .. q0+nq-1 (mod D/4) of each row, a slot range in the
-//     stage's donor pool by a prefix sum over the rows, then ONE warp instruction per copy kind: lane 0 of
-//     a row's group requests the parent row, lanes 1.. the window's cover of donor 0, 1, ... (a second
-//     copy when the window wraps), all onto the stage's mbarrier (`cp.async.bulk`, SASS UBLKCP);
+// `tools/gather_peak.cu` shows the copy engine moves the access pattern of BASELINE config 4 (a 512-byte
+// parent row and three ~96-byte donor segments in, a row out) in 0.240-0.245 ms at NP = 1 M with almost no
+// instructions (K2d, de_rows.cuh: 0.341-0.350 ms; the same pattern with plain loads: 0.26-0.27 ms).  Here a
+// warp owns a ring of `stages` buffers (one by default) of 32/LPR rows:
+//   * issue: lane 0 requests the stage's parent rows with ONE copy (they are contiguous in global memory and
+//     the tile is unpadded) before anything else, so they fly while the draws are made (rows_draw,
+//     de_rows.cuh: the same Philox blocks as every kernel); the window chunks q0 .. q0+nq-1 (mod D/4) of
+//     each row get a slot range in the stage's donor pools by a prefix sum over the rows, and one SIMT copy
+//     instruction has lane 1 + j of a row's group request the window's cover of donor j (a second one when
+//     the window wraps), all onto the stage's mbarrier (`cp.async.bulk`, SASS UBLKCP: a uniform-datapath
+//     instruction, so that "one instruction" is an elect loop of ~10 instructions per request);
 //   * compute (when the stage has landed): K2d's window mutation in place, with donor chunks read from
-//     the pool and the parent's chunks saved in an undo pool; K2d's cost / penalty; a rejected trial is
-//     undone in the tile; one bulk shared->global copy per row stores the next generation.
-// Rows whose window does not fit the pool read their donors with plain loads and are restored from
-// global memory when rejected (the pool is sized from what shared memory is left: 40 chunks per stage
+//     the pools and the parent's chunks saved in an undo pool; K2d's cost / penalty; a rejected trial is
+//     undone in the tile; ONE bulk shared->global copy stores the stage's rows.
+// Rows whose window does not fit the pools read their donors with plain loads and are restored from
+// global memory when rejected (the pools are sized from what shared memory is left: 36 chunks per stage
 // at C4, mean demand 25).  Results are bit-identical to K2d's: same draws, same mutation and cost code.
+// B200 (profiles/README.md): the step is bound by the warps' own dependent chains, so 24 resident warps at
+// 80 registers (0.30 ms at C4) beat 12 warps with two stages each (0.40 ms).
 #pragma once
 #include "de_rows.cuh"
 #include "de_tma.cuh"
