@@ -83,7 +83,9 @@ enum mb2_cost {
   MB2_COST_SHEKEL = 23,     /* models/dejong.py:252-278 */
   /* ... and of any number of variables, evaluated coordinate by coordinate in the reference's order */
   MB2_COST_ELLIPSOID = 24,  /* models/pohlheim.py:92-102 */
-  MB2_COST_PAVIANI = 25     /* models/schittkowski.py:46-71 */
+  MB2_COST_PAVIANI = 25,    /* models/schittkowski.py:46-71 */
+  /* data-fit residual cost (like 6 and 8) with F = models/br8.py:27-32, dual exponential decay, dim = 5 */
+  MB2_COST_DECAY = 26
 };
 
 /* SetStrictRanges modes (abstract_solver.py:334-448, tools.py:404-430) */
@@ -144,7 +146,8 @@ int mb2_set_strategy(mb2_ctx* ctx, int strategy, double scale, double cross);
 /* abstract_solver.py:334-405 SetStrictRanges; lo/hi have `dim` entries (ignored for NONE) */
 int mb2_set_bounds(mb2_ctx* ctx, int mode, const double* lo_host, const double* hi_host);
 /* cost(x, *ExtraArgs): params for CHEBYSHEV* = {M, order, target coeffs[order+1]};
- * for POLYFIT* / LORENTZIAN = {M, sigma, evalpts[M], observations[M]} */
+ * for POLYFIT* / LORENTZIAN / DECAY = {M, sigma, evalpts[M], observations[M]}, optionally followed by
+ * sigma[M] (a sigma per point: forward_model.py:255 divides elementwise; the scalar is then ignored) */
 int mb2_set_cost(mb2_ctx* ctx, int cost, const double* params_host, int32_t nparams);
 /* stacked penalty decorators, term 0 innermost (penalty.py:80-98 `dec`); G is [nterms, dim],
  * kscale[i] = k*h**n (the decorator's current multiplier before the inequality factor 2) */

@@ -87,9 +87,11 @@ struct mb2_ctx {
   double* lo = nullptr;
   double* hi = nullptr;
   int cost = MB2_COST_ROSEN;
-  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0, nullptr, 1.0, 0, 0, {0.0, 0.0, 0.0}};
+  CostParams cp = {0, nullptr, 0.0, 0.0, nullptr, 0, nullptr, 0, nullptr, 1.0, 0, 0, nullptr, 0, {0.0, 0.0, 0.0}};
   double* fit_obs = nullptr;
   size_t cap_fit_obs = 0;
+  double* fit_sigma_v = nullptr;
+  size_t cap_fit_sigma_v = 0;
   double bounds_absmax = 0.0;  // max(|lo_i|, |hi_i|) of the strict range
   double* cheb_vfrag = nullptr;
   int cheb_ks = 0;
@@ -852,11 +854,17 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
 
 int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
-  if (cost < MB2_COST_ROSEN || cost > MB2_COST_PAVIANI) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  if (cost < MB2_COST_ROSEN || cost > MB2_COST_DECAY) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  c->cp.fit_kind = FIT_LORENTZIAN;
+  if (cost == MB2_COST_DECAY) {  // a second elementwise forward model on the lorentzian instantiations
+    if (c->dim != 5) return fail(MB2_EINVAL, "the dual exponential decay has 5 parameters (a1,a2,a3,a4,a5)");
+    c->cp.fit_kind = FIT_DECAY;
+    cost = MB2_COST_LORENTZIAN;
+  }
   if (is_separable(cost)) c->cp.sep_kind = cost - MB2_COST_SPHERE;
   // closed-form functions one thread evaluates (fixed_cost, de_device.cuh) run on the zimmermann instantiations
   c->cp.fixed_kind = FIX_ZIMMERMANN;
-  if (cost >= MB2_COST_BRANINS) {
+  if (cost >= MB2_COST_BRANINS && cost <= MB2_COST_PAVIANI) {
     if (cost <= MB2_COST_SHEKEL && c->dim != 2) return fail(MB2_EINVAL, "cost %d is a function of two variables", cost);
     c->cp.fixed_kind = FIX_BRANINS + (cost - MB2_COST_BRANINS);
     const double pi = 3.141592653589793;  // math.pi
@@ -865,7 +873,7 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
     c->cp.fixed_c[2] = 1. / (8 * pi);
     cost = MB2_COST_ZIMMERMANN;
   }
-  if (cost == MB2_COST_LORENTZIAN && c->dim != 7) return fail(MB2_EINVAL, "lorentzian has 7 parameters (a1,a2,a3,A0,E0,G0,n)");
+  if (cost == MB2_COST_LORENTZIAN && c->cp.fit_kind == FIT_LORENTZIAN && c->dim != 7) return fail(MB2_EINVAL, "lorentzian has 7 parameters (a1,a2,a3,A0,E0,G0,n)");
   if ((cost == MB2_COST_POLYFIT || cost == MB2_COST_LORENTZIAN) && c->dim > 32)
     return fail(MB2_EINVAL, "data-fit costs support at most 32 model parameters");
   if (cost == MB2_COST_POLYFIT_MMA && c->dim > kChebMaxDim)
@@ -917,11 +925,27 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
     return MB2_OK;
   };
   if (cost == MB2_COST_POLYFIT || cost == MB2_COST_POLYFIT_MMA || cost == MB2_COST_LORENTZIAN) {
-    if (!params || nparams < 4) return fail(MB2_EINVAL, "data-fit params = {M, sigma, evalpts[M], observations[M]}");
+    if (!params || nparams < 4) return fail(MB2_EINVAL, "data-fit params = {M, sigma, evalpts[M], observations[M][, sigma[M]]}");
     const int M = (int)params[0];
     const double sigma = params[1];
-    if (M < 1 || nparams != 2 + 2 * M) return fail(MB2_EINVAL, "bad data-fit params (M=%d, %d values)", M, nparams);
-    if (!(sigma != 0.0)) return fail(MB2_EINVAL, "sigma must not be zero");
+    const bool per_point = (nparams == 2 + 3 * M);  // (x - observations) / sigma with a sigma per point (models/br8.py:47)
+    if (M < 1 || (nparams != 2 + 2 * M && !per_point)) return fail(MB2_EINVAL, "bad data-fit params (M=%d, %d values)", M, nparams);
+    if (!per_point && !(sigma != 0.0)) return fail(MB2_EINVAL, "sigma must not be zero");
+    if (per_point && cost == MB2_COST_POLYFIT_MMA) return fail(MB2_EINVAL, "the DMMA polynomial fit takes a scalar sigma");
+    c->cp.fit_sigma_v = nullptr;
+    if (per_point) {
+      for (int i = 0; i < M; ++i)
+        if (!(params[2 + 2 * M + i] != 0.0)) return fail(MB2_EINVAL, "sigma[%d] must not be zero", i);
+      CUDA_TRY(cudaSetDevice(c->device));
+      if (c->cap_fit_sigma_v < sizeof(double) * M) {
+        void* p = nullptr;
+        if (int rc = dev_alloc(c, sizeof(double) * M, &p)) return rc;
+        c->fit_sigma_v = (double*)p;
+        c->cap_fit_sigma_v = sizeof(double) * M;
+      }
+      CUDA_TRY(cudaMemcpy(c->fit_sigma_v, params + 2 + 2 * M, sizeof(double) * M, cudaMemcpyHostToDevice));
+      c->cp.fit_sigma_v = c->fit_sigma_v;
+    }
     std::vector<double> xs(params + 2, params + 2 + M);
     if (int rc = upload_points(xs, cost == MB2_COST_POLYFIT_MMA)) return rc;
     if (c->cap_fit_obs < sizeof(double) * M) {
@@ -932,7 +956,7 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
     }
     CUDA_TRY(cudaMemcpy(c->fit_obs, params + 2 + M, sizeof(double) * M, cudaMemcpyHostToDevice));
     c->cp.fit_obs = c->fit_obs;
-    c->cp.fit_sigma = sigma;
+    c->cp.fit_sigma = per_point ? 1.0 : sigma;
   }
   if (cost == MB2_COST_CHEBYSHEV || cost == MB2_COST_CHEBYSHEV_MMA) {
     if (!params || nparams < 3) return fail(MB2_EINVAL, "chebyshev params = {M, order, target[order+1]}");

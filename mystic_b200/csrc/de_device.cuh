@@ -172,6 +172,8 @@ struct CostParams {
   double fit_sigma;
   int sep_kind;  // COST_SEPARABLE: which of the SEP_* functions
   // COST_ZIMMERMANN stands for the family of closed-form functions one thread evaluates (fixed_cost)
+  int fit_kind;               // COST_LORENTZIAN instantiations: 0 = lorentzian, 1 = dual exponential decay (FIT_*)
+  const double* fit_sigma_v;  // [M] per-point sigma (nullptr: the scalar fit_sigma)
   int fixed_kind;      // FIX_*
   double fixed_c[3];   // branins: b = 5.1/(4*pi**2), c = 5./pi, f = 1./(8*pi), computed on the host like Python does
 };
@@ -293,34 +295,41 @@ __device__ __forceinline__ double horner(const double* __restrict__ c, int n, do
 }
 
 // One squared residual of a data-fit cost (forward_model.py:241-258: x = F(params)(evalpts);
-// x = x - observations, or (x - observations)/sigma; metric sum(x*x)), elementwise in numpy's order.
+// x = x - observations, or (x - observations)/sigma with a scalar or per-point sigma; metric sum(x*x)),
+// elementwise in numpy's order.
 // polynomial model (models/poly.py:36-54): numpy.poly1d(coeffs)(x) is numpy.polyval's
 // `y = zeros_like(x); for pv in p: y = y*x + pv` (leading zero coefficients change nothing)
-__device__ __forceinline__ double polyfit_term(const double* __restrict__ c, int n, double x, double obs, double sigma) {
+__device__ __forceinline__ double polyfit_value(const double* __restrict__ c, int n, double x) {
   double y = 0.0;
   for (int j = 0; j < n; ++j) y = dadd(dmul(y, x), c[j]);
-  double r = dsub(y, obs);
-  if (sigma != 1.0) r = __ddiv_rn(r, sigma);  // AbstractModel's default sigma = 1.0 divides exactly
-  return dmul(r, r);
+  return y;
 }
 // lorentzian peak (models/lorentzian.py:32-37), coeffs = (a1,a2,a3,A0,E0,G0,n):
 //   (a1 + a2*x + a3*x*x + A0*(G0/(2*pi))/((x-E0)*(x-E0) + (G0/2)*(G0/2)))/n
-__device__ __forceinline__ double lorentz_term(const double* __restrict__ p, double x, double obs, double sigma) {
+__device__ __forceinline__ double lorentz_value(const double* __restrict__ p, double x) {
   const double a1 = p[0], a2 = p[1], a3 = p[2], A0 = p[3], E0 = p[4], G0 = p[5], nn = p[6];
   const double k = dmul(A0, __ddiv_rn(G0, 6.283185307179586));  // 2*pi in binary64
   const double hg = __ddiv_rn(G0, 2.0);
   const double d = dsub(x, E0);
   const double den = dadd(dmul(d, d), dmul(hg, hg));
   const double s = dadd(dadd(a1, dmul(a2, x)), dmul(dmul(a3, x), x));
-  const double v = __ddiv_rn(dadd(s, __ddiv_rn(k, den)), nn);
-  double r = dsub(v, obs);
-  if (sigma != 1.0) r = __ddiv_rn(r, sigma);
-  return dmul(r, r);
+  return __ddiv_rn(dadd(s, __ddiv_rn(k, den)), nn);
+}
+// dual exponential decay (models/br8.py:27-32), coeffs = (a1,a2,a3,a4,a5): a1 + a2*exp(-t/a4) + a3*exp(-t/a5)
+// (CUDA's exp is within 1 ulp of numpy's)
+enum : int { FIT_LORENTZIAN = 0, FIT_DECAY = 1 };
+__device__ __forceinline__ double decay_value(const double* __restrict__ p, double t) {
+  const double e4 = exp(__ddiv_rn(-t, p[3])), e5 = exp(__ddiv_rn(-t, p[4]));
+  return dadd(dadd(p[0], dmul(p[1], e4)), dmul(p[2], e5));
 }
 template <int COST>
 __device__ __forceinline__ double fit_term(const double* __restrict__ xs, int D, const CostParams& cp, int i) {
   const double x = __ldg(cp.cheb_x + i), obs = __ldg(cp.fit_obs + i);
-  return (COST == COST_POLYFIT) ? polyfit_term(xs, D, x, obs, cp.fit_sigma) : lorentz_term(xs, x, obs, cp.fit_sigma);
+  const double v = (COST == COST_POLYFIT) ? polyfit_value(xs, D, x) : (cp.fit_kind == FIT_DECAY ? decay_value(xs, x) : lorentz_value(xs, x));
+  double r = dsub(v, obs);
+  const double sigma = (cp.fit_sigma_v != nullptr) ? __ldg(cp.fit_sigma_v + i) : cp.fit_sigma;
+  if (sigma != 1.0) r = __ddiv_rn(r, sigma);  // AbstractModel's default sigma = 1.0 divides exactly
+  return dmul(r, r);
 }
 
 // Closed-form test functions evaluated by ONE thread in the reference's operation order (Python floats:

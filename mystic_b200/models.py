@@ -24,6 +24,7 @@ with TypeError: the engine has no CPU path.
 COST_ROSEN, COST_CORANA, COST_GRIEWANGK, COST_ZIMMERMANN, COST_CHEBYSHEV, COST_CHEBYSHEV_MMA = range(6)
 COST_POLYFIT, COST_POLYFIT_MMA, COST_LORENTZIAN = 6, 7, 8
 COST_SPHERE, COST_RASTRIGIN, COST_SCHWEFEL, COST_ACKLEY, COST_STEP, COST_MICHAL, COST_POWERS = 9, 10, 11, 12, 13, 14, 15
+COST_DECAY = 26
 (COST_BRANINS, COST_EASOM, COST_GOLDSTEIN, COST_PEAKS, COST_VENKAT91, COST_FOSC3D, COST_NMIN51, COST_SHEKEL, COST_ELLIPSOID,
  COST_PAVIANI) = range(16, 26)
 
@@ -87,21 +88,31 @@ class DataFitCost(DeviceCost):
         if self.pts.shape != self.observations.shape or self.pts.size < 1:
             raise ValueError('evaluation points and observations must be two equally long, non-empty vectors')
         self.nparams = int(nparams)
-        self.sigma = 1.0 if sigma is None else float(sigma)   # getCostFunction(sigma=None) does not divide
-        if self.sigma == 0.0:
-            raise ZeroDivisionError('sigma')
+        # getCostFunction(sigma=None) does not divide; an array divides point by point (forward_model.py:252-255)
+        if sigma is not None and np.ndim(sigma) > 0:
+            self.sigma = np.ascontiguousarray(sigma, dtype=np.float64).ravel()
+            if self.sigma.shape != self.pts.shape:
+                raise ValueError('sigma must be a scalar or have one entry per evaluation point')
+            if not np.all(self.sigma != 0.0):
+                raise ZeroDivisionError('sigma')
+        else:
+            self.sigma = 1.0 if sigma is None else float(sigma)
+            if self.sigma == 0.0:
+                raise ZeroDivisionError('sigma')
 
     def device_id(self, tensor_cores=False, dim=None):
         """the polynomial fit has a second implementation on the FP64 tensor cores (the coefficient x
         point contraction as DMMA); like the Chebyshev one it is not bit-faithful to the Horner order
         of numpy.polyval, so it is opt-in (tensor_cores=True)."""
-        if tensor_cores and self.cost_id == COST_POLYFIT and (dim is None or dim <= 17):
+        if tensor_cores and self.cost_id == COST_POLYFIT and (dim is None or dim <= 17) and isinstance(self.sigma, float):
             return COST_POLYFIT_MMA
         return self.cost_id
 
     def params(self, extra_args=()):
         if extra_args:
             raise TypeError('%s() takes no ExtraArgs' % self.__name__)
+        if not isinstance(self.sigma, float):
+            return [float(self.pts.size), 1.0] + self.pts.tolist() + self.observations.tolist() + self.sigma.tolist()
         return [float(self.pts.size), self.sigma] + self.pts.tolist() + self.observations.tolist()
 
 
@@ -123,6 +134,9 @@ class _FitModel(object):
             for c in coeffs:
                 val = c + val * x
             return val
+        if self._cost_id == COST_DECAY:
+            a1, a2, a3, a4, a5 = [float(c) for c in coeffs]      # models/br8.py:27-32
+            return a1 + a2*np.exp(-x/a4) + a3*np.exp(-x/a5)
         a1, a2, a3, A0, E0, G0, n = [float(c) for c in coeffs]   # models/lorentzian.py:32-37
         return (a1 + a2*x + a3*x*x + A0 * ( G0/(2*np.pi) )/( (x-E0)*(x-E0)+(G0/2)*(G0/2) ))/n
 
@@ -134,19 +148,26 @@ class _FitModel(object):
         if self._nparams is not None and int(nparams) != self._nparams:
             raise ValueError('%s has %d parameters' % (self.__name__, self._nparams))
 
+    def _sigma(self, datapts):
+        """models/br8.py:47,55: the decay model weighs every residual by sqrt(datapts); the others by 1"""
+        import numpy as np
+        return np.sqrt(np.asarray(datapts, dtype=np.float64)) if self._cost_id == COST_DECAY else 1.0
+
     def CostFactory(self, target, pts):
         """cost function from a list of target coefficients and evaluation points (abstract_model.py:146-153)"""
         self._check(len(target))
-        return DataFitCost(self.__name__ + '.cost', self._cost_id, pts, self.evaluate(target, pts), len(target))
+        datapts = self.evaluate(target, pts)
+        return DataFitCost(self.__name__ + '.cost', self._cost_id, pts, datapts, len(target), self._sigma(datapts))
 
     def CostFactory2(self, pts, datapts, nparams):
         """cost function from data points and evaluation points (abstract_model.py:155-161)"""
         self._check(nparams)
-        return DataFitCost(self.__name__ + '.cost', self._cost_id, pts, datapts, nparams)
+        return DataFitCost(self.__name__ + '.cost', self._cost_id, pts, datapts, nparams, self._sigma(datapts))
 
 
 poly = _FitModel('poly', COST_POLYFIT)
 lorentzian = _FitModel('lorentz', COST_LORENTZIAN, 7)
+decay = _FitModel('decay', COST_DECAY, 5)          # mystic.models.decay (br8.py: Bevington's dual exponential decay)
 
 rosen = DeviceCost('rosen', COST_ROSEN, doc="Rosenbrock's saddle, sum(100*(x[1:]-x[:-1]**2)**2 + (1-x[:-1])**2)")
 corana = DeviceCost('corana', COST_CORANA, doc="Corana's parabola (first four coordinates)")
@@ -202,9 +223,9 @@ def _resolve_reference_costfactory(cost):
     if not fac or len(fac) != 1:
         raise TypeError('the B200 engine evaluates CostFactory costs with exactly one forward model')
     owner = getattr(fac[0], '__self__', None)
-    kind = {'Polynomial': COST_POLYFIT, 'Lorentzian': COST_LORENTZIAN}.get(type(owner).__name__)
+    kind = {'Polynomial': COST_POLYFIT, 'Lorentzian': COST_LORENTZIAN, 'BevingtonDecay': COST_DECAY}.get(type(owner).__name__)
     if kind is None or not type(owner).__module__.startswith('mystic.models'):
-        raise TypeError('only the poly and lorentzian forward models of mystic.models exist on the device')
+        raise TypeError('only the poly, lorentzian and decay forward models of mystic.models exist on the device')
     from_null = lambda f: type(f).__name__ in ('NullChecker', 'function') and f(np.ones(1), np.ones(1)) is None  # noqa: E731
     ident = lambda f: np.array_equal(f(np.array([1.5, -2.0])), np.array([1.5, -2.0]))  # noqa: E731
     if not from_null(cf._inputCheckers[0]) or not ident(cf._outputFilters[0]):
@@ -212,7 +233,7 @@ def _resolve_reference_costfactory(cost):
     probe = np.array([1.0, -2.0, 0.5])
     if float(cells['metric'](probe)) != 5.25:
         raise TypeError('only the default L2 metric, sum(x*x), exists on the device')
-    name = 'poly.cost' if kind == COST_POLYFIT else 'lorentz.cost'
+    name = {COST_POLYFIT: 'poly.cost', COST_LORENTZIAN: 'lorentz.cost', COST_DECAY: 'decay.cost'}[kind]
     return DataFitCost(name, kind, cells['evalpts'], cells['observations'], nin[0], cells['sigma'])
 
 

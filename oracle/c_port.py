@@ -21,7 +21,7 @@ class Config(ctypes.Structure):
                 ('cheb_order', ctypes.c_int32), ('cheb_target', _dp), ('n_pen', ctypes.c_int32),
                 ('pad_', ctypes.c_int32), ('pen_type', _ip), ('pen_G', _dp), ('pen_h', _dp), ('pen_k', _dp),
                 ('fit_M', ctypes.c_int32), ('pad2_', ctypes.c_int32), ('fit_pts', _dp), ('fit_obs', _dp),
-                ('fit_sigma', ctypes.c_double)]
+                ('fit_sigma', ctypes.c_double), ('fit_sigma_v', _dp)]
 
 
 _lib = None
@@ -90,13 +90,18 @@ class COracle(object):
         cfg.fit_sigma = 1.0
         if cost in self.COSTS:
             cfg.cost = self.COSTS[cost]
-        elif cost in ('polyfit', 'lorentzian'):   # extra = (pts, observations[, sigma])
-            cfg.cost = 6 if cost == 'polyfit' else 8
+        elif cost in ('polyfit', 'lorentzian', 'decay'):   # extra = (pts, observations[, sigma]), sigma a scalar or one per point
+            cfg.cost = {'polyfit': 6, 'lorentzian': 8, 'decay': 26}[cost]
             self._fit_pts = np.ascontiguousarray(extra[0], dtype=np.float64)
             self._fit_obs = np.ascontiguousarray(extra[1], dtype=np.float64)
             cfg.fit_M = int(self._fit_pts.size)
             cfg.fit_pts, cfg.fit_obs = _d(self._fit_pts), _d(self._fit_obs)
-            cfg.fit_sigma = float(extra[2]) if len(extra) > 2 else 1.0
+            sg = extra[2] if len(extra) > 2 else 1.0
+            if np.ndim(sg) > 0:
+                self._fit_sigma_v = np.ascontiguousarray(sg, dtype=np.float64)
+                cfg.fit_sigma, cfg.fit_sigma_v = 1.0, _d(self._fit_sigma_v)
+            else:
+                cfg.fit_sigma = float(sg)
         else:
             order = int(cost[len('chebyshev'):-len('cost')])
             cfg.cost = 4

@@ -27,7 +27,7 @@ enum { COST_ROSEN = 0, COST_CORANA = 1, COST_GRIEWANGK = 2, COST_ZIMMERMANN = 3,
        COST_POLYFIT = 6, COST_LORENTZIAN = 8, COST_SPHERE = 9, COST_RASTRIGIN = 10, COST_SCHWEFEL = 11,
        COST_ACKLEY = 12, COST_STEP = 13, COST_MICHAL = 14, COST_POWERS = 15,
        COST_BRANINS = 16, COST_EASOM = 17, COST_GOLDSTEIN = 18, COST_PEAKS = 19, COST_VENKAT91 = 20, COST_FOSC3D = 21,
-       COST_NMIN51 = 22, COST_SHEKEL = 23, COST_ELLIPSOID = 24, COST_PAVIANI = 25 };
+       COST_NMIN51 = 22, COST_SHEKEL = 23, COST_ELLIPSOID = 24, COST_PAVIANI = 25, COST_DECAY = 26 };
 
 typedef struct {
   int32_t dim;
@@ -55,6 +55,7 @@ typedef struct {
   const double* fit_pts;
   const double* fit_obs;
   double fit_sigma;
+  const double* fit_sigma_v; /* per-point sigma (models/br8.py:47), NULL: the scalar */
 } orc_config;
 
 /* strategy id -> base, crossover, donors (strategy.py:34-311; only Best1Bin is binomial) */
@@ -164,12 +165,14 @@ static double cost_datafit(const double* c, int D, const orc_config* cfg, double
     if (cfg->cost == COST_POLYFIT) {
       y = 0.0;
       for (int j = 0; j < D; ++j) y = y * x + c[j];
+    } else if (cfg->cost == COST_DECAY) { /* models/br8.py:27-32 */
+      y = c[0] + c[1] * exp(-x / c[3]) + c[2] * exp(-x / c[4]);
     } else {
       const double a1 = c[0], a2 = c[1], a3 = c[2], A0 = c[3], E0 = c[4], G0 = c[5], n = c[6];
       const double pi = 3.141592653589793;
       y = (a1 + a2 * x + a3 * x * x + A0 * (G0 / (2 * pi)) / ((x - E0) * (x - E0) + (G0 / 2) * (G0 / 2))) / n;
     }
-    const double d = (y - cfg->fit_obs[i]) / cfg->fit_sigma;
+    const double d = (y - cfg->fit_obs[i]) / (cfg->fit_sigma_v ? cfg->fit_sigma_v[i] : cfg->fit_sigma);
     scratch[i] = d * d;
   }
   return np_pairwise_sum(scratch, M);
@@ -378,6 +381,7 @@ static double energy_of(const double* x, const orc_config* cfg, double* scratch)
       case COST_GRIEWANGK: raw = cost_griewangk(x, D); break;
       case COST_ZIMMERMANN: raw = cost_zimmermann(x); break;
       case COST_POLYFIT:
+      case COST_DECAY:
       case COST_LORENTZIAN: raw = cost_datafit(x, D, cfg, scratch); break;
       case COST_SPHERE:
       case COST_RASTRIGIN:

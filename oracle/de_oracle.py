@@ -257,6 +257,26 @@ def cost_powers(x):
 
 
 
+def cost_decay(x, pts, obs, sigma=1.0):
+    """the same residual cost with the dual exponential decay of mystic/models/br8.py:27-32,
+    coeffs = (a1,a2,a3,a4,a5); sigma is sqrt(observations) in the reference's own factories (br8.py:47,55)"""
+    from numpy import exp
+    x = np.atleast_2d(np.asarray(x, dtype=np.float64))
+    t = np.asarray(pts, dtype=np.float64)
+    obs = np.asarray(obs, dtype=np.float64)
+    out = np.empty(x.shape[0])
+    for r in range(x.shape[0]):
+        a1, a2, a3, a4, a5 = [float(v) for v in x[r]]
+        with np.errstate(all='ignore'):
+            try:
+                y = a1 + a2*exp(-t/a4) + a3*exp(-t/a5)
+            except ZeroDivisionError:
+                y = np.full_like(t, np.nan)
+            d = (y - obs) / sigma
+            out[r] = np.sum(d * d)
+    return out
+
+
 # ---- closed-form functions of a few variables: the reference's own expressions on Python floats, row by row
 def _rowwise(f):
     def cost(x):
@@ -408,10 +428,11 @@ def cost_lorentzian(x, pts, obs, sigma=1.0):
 def make_cost(name, extra_args=()):
     """name -> f(X[NP,D]) -> [NP]; names as exported by mystic.models / mystic.models.poly.
     Data-fit costs: name 'polyfit' / 'lorentzian' with extra_args = (pts, observations[, sigma])."""
-    if name in ('polyfit', 'lorentzian'):
+    if name in ('polyfit', 'lorentzian', 'decay'):
         pts, obs = extra_args[0], extra_args[1]
-        sigma = float(extra_args[2]) if len(extra_args) > 2 else 1.0
-        f = cost_polyfit if name == 'polyfit' else cost_lorentzian
+        sigma = extra_args[2] if len(extra_args) > 2 else 1.0
+        sigma = np.asarray(sigma, dtype=np.float64) if np.ndim(sigma) > 0 else float(sigma)
+        f = {'polyfit': cost_polyfit, 'lorentzian': cost_lorentzian, 'decay': cost_decay}[name]
         return lambda X: f(X, pts, obs, sigma)
     if name == 'rosen':
         return cost_rosen

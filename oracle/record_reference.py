@@ -86,6 +86,14 @@ def _fit_cost(case):
     mystic.models.poly.CostFactory(target, pts) / mystic.models.lorentzian.CostFactory(target, pts)
     (abstract_model.py:146-153 -> forward_model.py:204-260).  Returns (cost, pts, observations)."""
     import mystic.models as mm
+    if case['cost'] == 'decay':
+        # mystic.models.br8: Bevington's dual exponential decay; `data` = the book's counts, `cost` the
+        # module's own CostFactory2(data[:,0], data[:,1], 5) with sigma = sqrt(counts) (br8.py:51-56, 92)
+        import importlib
+        br8 = importlib.import_module('mystic.models.br8')
+        pts = np.asarray(br8.data[:, 0], dtype=np.float64)
+        obs = np.asarray(br8.data[:, 1], dtype=np.float64)
+        return br8.decay.CostFactory2(br8.data[:, 0], br8.data[:, 1], 5), pts, obs, np.sqrt(br8.data[:, 1])
     model = mm.poly if case['cost'] == 'polyfit' else mm.lorentzian
     pts = _fit_points(case['fit']['pts'])
     target = [float(v) for v in case['fit']['target']]
@@ -179,7 +187,7 @@ def record(case):
             term = mt.VTR(-1.0)  # never satisfied for the non-negative costs used here
         extra = tuple(case['ExtraArgs']) if case.get('ExtraArgs') else None
         fit = None
-        if case['cost'] in ('polyfit', 'lorentzian'):
+        if case['cost'] in ('polyfit', 'lorentzian', 'decay'):
             fit = _fit_cost(case)
         the_cost = fit[0] if fit else _cost(case['cost'])
         if via == 'ctor':
@@ -227,6 +235,8 @@ def record(case):
     }
     if fit:
         out['fit_pts'], out['fit_obs'] = fit[1], fit[2]
+        if len(fit) > 3:
+            out['fit_sigma'] = fit[3]
     return out
 
 
@@ -382,6 +392,9 @@ def cases():
                                          bounds=([0.5, 30., -15., 10., 0., 0.05, 100.], [2., 60., -5., 50., 2., 1., 200.], True),
                                          fit=dict(target=[1., 45., -10., 20., 1., 0.1, 120.], pts=('arange', 0.05, 3.0, 0.1)),
                                          maxgen=10)
+    cs['fit_decay_best1exp'] = dict(dim=5, NP=30, strategy='Best1Exp', cost='decay', CR=0.9, F=0.8, seed=304,
+                                    init=('random', [0., 100., 100., 10., 100.], [20., 1500., 300., 60., 400.]),
+                                    bounds=([0., 100., 100., 10., 100.], [20., 1500., 300., 60., 400.], True), maxgen=10)
     return cs
 
 

@@ -19,17 +19,21 @@ def load(name):
     return meta, z
 
 
-FIT_COSTS = ('polyfit', 'lorentzian')
+FIT_COSTS = ('polyfit', 'lorentzian', 'decay')
 # costs the reference sums with the builtin sum(): CPython 3.12 compensates runs of exact floats
 # (oracle/de_oracle.py:cost_griewangk), so their ENERGIES are compared to 1e-14, everything else bit for bit
 COMPENSATED_SUM_COSTS = ('griewangk', 'rastrigin', 'schwefel', 'ackley', 'michal', 'powers', 'ellipsoid')
+
+# costs the reference evaluates with numpy's vectorised exp (models/br8.py:32): within 1 ulp of libm's, so the C
+# port's ENERGIES are compared to 1e-14 (the numpy oracle reproduces them bit for bit)
+NUMPY_EXP_COSTS = ('decay',)
 
 
 def extra_of(meta, z):
     """ExtraArgs of the recorded run for orc.make_cost / c_port.COracle: data-fit costs carry their
     evaluation points and observations in the recording"""
     if meta['cost'] in FIT_COSTS:
-        return (z['fit_pts'], z['fit_obs'], 1.0)
+        return (z['fit_pts'], z['fit_obs'], z['fit_sigma'] if 'fit_sigma' in z.files else 1.0)
     return tuple(meta.get('ExtraArgs') or ())
 
 
@@ -40,6 +44,8 @@ def device_cost_of(meta, z):
         return models.poly.CostFactory2(z['fit_pts'], z['fit_obs'], meta['dim'])
     if meta['cost'] == 'lorentzian':
         return models.lorentzian.CostFactory2(z['fit_pts'], z['fit_obs'], meta['dim'])
+    if meta['cost'] == 'decay':
+        return models.decay.CostFactory2(z['fit_pts'], z['fit_obs'], meta['dim'])
     return getattr(models, meta['cost'])
 
 

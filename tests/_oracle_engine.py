@@ -48,10 +48,12 @@ class OracleEngine(object):
     def set_cost(self, cost_id, params=()):
         if cost_id in _COST_NAMES:
             self.cost = orc.make_cost(_COST_NAMES[cost_id])
-        elif cost_id in (6, 7, 8):   # data-fit costs: params = [M, sigma, pts[M], obs[M]]
+        elif cost_id in (6, 7, 8, 26):   # data-fit costs: params = [M, sigma, pts[M], obs[M][, sigma[M]]]
             M, sigma = int(params[0]), float(params[1])
             pts, obs = np.asarray(params[2:2 + M], float), np.asarray(params[2 + M:2 + 2 * M], float)
-            self.cost = orc.make_cost('lorentzian' if cost_id == 8 else 'polyfit', (pts, obs, sigma))
+            if len(params) == 2 + 3 * M:
+                sigma = np.asarray(params[2 + 2 * M:], float)
+            self.cost = orc.make_cost({6: 'polyfit', 7: 'polyfit', 8: 'lorentzian', 26: 'decay'}[cost_id], (pts, obs, sigma))
         else:
             M, order = int(params[0]), int(params[1])
             self.cost = orc.make_cost('chebyshev%dcost' % order, (M,))

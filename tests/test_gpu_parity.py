@@ -351,6 +351,20 @@ def test_datafit_costs_random_batches_match_oracle(kernel_path):
     X = lo + (hi - lo) * rng.uniform(size=(97, 7))
     energy_close(lcost(X), orc.cost_lorentzian(X, bins, lcost.observations), what='lorentzian')
     assert lcost([1., 45., -10., 20., 1., 0.1, 120.]) == 0.0
+    # dual exponential decay (models/br8.py), every residual weighed by its own sigma = sqrt(observation);
+    # a per-point sigma on the polynomial fit too
+    t = np.arange(15., 900., 15.)
+    dcost = models.decay.CostFactory([10., 900., 80., 27., 225.], t)
+    assert isinstance(dcost.sigma, np.ndarray) and dcost([10., 900., 80., 27., 225.]) < 1e-18   # CUDA's exp vs numpy's: <= 1 ulp
+    X = np.array([0., 100., 100., 10., 100.]) + np.array([20., 1400., 200., 50., 300.]) * rng.uniform(size=(97, 5))
+    energy_close(dcost(X), orc.cost_decay(X, t, dcost.observations, dcost.sigma), what='decay')
+    counts = np.round(dcost.observations) + 1.0
+    energy_close(models.decay.CostFactory2(t, counts, 5)(X), orc.cost_decay(X, t, counts, np.sqrt(counts)), what='decay data')
+    sig = rng.uniform(0.5, 3.0, size=pts.size)
+    wcost = models.DataFitCost('poly.cost', models.COST_POLYFIT, pts, np.cos(pts), 4, sigma=sig)
+    X = rng.uniform(-3., 3., size=(97, 4))
+    energy_close(wcost(X), orc.cost_polyfit(X, pts, np.cos(pts), sig), what='polyfit per-point sigma')
+    energy_close(wcost(X, tensor_cores=True), orc.cost_polyfit(X, pts, np.cos(pts), sig), what='polyfit per-point sigma (Horner: no DMMA variant)')
 
 
 def test_polyfit_dmma_trajectory_matches_oracle():

@@ -23,7 +23,7 @@ def test_c_oracle_reproduces_reference(name):
         G.assert_bits_equal(o.trial, z['trial'][g], tag + ' trial')
         G.assert_bits_equal(o.population, z['pop'][g], tag + ' pop')
         G.assert_bits_equal(o.best_x, z['bestX'][g], tag + ' bestX')
-        if meta['cost'] in G.COMPENSATED_SUM_COSTS:
+        if meta['cost'] in G.COMPENSATED_SUM_COSTS or meta['cost'] in G.NUMPY_EXP_COSTS:
             np.testing.assert_allclose(o.trial_e, z['trialE'][g], rtol=1e-14)
             np.testing.assert_allclose(o.popEnergy, z['popE'][g], rtol=1e-14)
         else:

@@ -97,6 +97,11 @@ def test_host_callables_are_rejected():
         s.SetPenalty(pen)                             # python condition: not device-expressible
 
 
+def orc_cost(name, extra):
+    from oracle import de_oracle as orc
+    return orc.make_cost(name, extra)
+
+
 def test_reference_costfactory_closures_are_recognised():
     """mystic.models.poly.CostFactory(target, pts) / lorentzian.CostFactory2(...) return closures of
     mystic.forward_model.CostFactory.getCostFunction; resolve() turns them into the device's data-fit
@@ -111,6 +116,14 @@ def test_reference_costfactory_closures_are_recognised():
     bins = np.arange(0.05, 3.0, 0.1)
     lor = models.resolve(mystic.models.lorentzian.CostFactory2(bins, np.ones_like(bins), 7))
     assert lor.cost_id == models.COST_LORENTZIAN and lor.nparams == 7
+    # mystic.models.br8: the module's own cost (Bevington's counts, sigma = sqrt(counts) per point)
+    import importlib
+    br8 = importlib.import_module('mystic.models.br8')
+    dec = models.resolve(br8.cost)
+    assert dec.cost_id == models.COST_DECAY and dec.nparams == 5
+    assert np.array_equal(dec.sigma, np.sqrt(br8.data[:, 1])) and np.array_equal(dec.observations, br8.data[:, 1])
+    p = [10., 900., 80., 27., 225.]
+    assert orc_cost('decay', (dec.pts, dec.observations, dec.sigma))(np.array([p]))[0] == br8.cost(p)
     # other metrics cannot run on the device
     from mystic.forward_model import CostFactory
     cf = CostFactory()
