@@ -10,10 +10,10 @@
     peaks, venkat91, fosc3d, nmin51, shekel, paviani   mystic/models/nag.py:48-59, venkataraman.py:38-52,
                 wolfram.py:44-64, 87-103, dejong.py:252-278, schittkowski.py:46-71
     chebyshev{2,4,6,8,16}cost   mystic/models/poly.py:124-149, mystic/models/_model_helper.py:10-33
-    poly.CostFactory / poly.CostFactory2, lorentzian.CostFactory / lorentzian.CostFactory2
+    poly.CostFactory / poly.CostFactory2, lorentzian.CostFactory / lorentzian.CostFactory2, decay.CostFactory / decay.CostFactory2
                 data-fit residual costs, mystic/models/abstract_model.py:146-161 ->
-                mystic/forward_model.py:204-260 with mystic/models/poly.py:36-54 and
-                mystic/models/lorentzian.py:32-37
+                mystic/forward_model.py:204-260 with mystic/models/poly.py:36-54,
+                mystic/models/lorentzian.py:32-37 and mystic/models/br8.py:27-56
 
 A descriptor names a cost function compiled into the fused kernel.  `resolve()` also recognises
 the unmodified reference callables (mystic.models.rosen is `Rosenbrock().function`, etc.) so
