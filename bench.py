@@ -42,6 +42,13 @@ WORKLOADS = {
     'c5': dict(desc='Griewangk 256-D, NP=2097152/GPU, Best1Bin CR=0.9 F=0.8, clamp +-400',
                cost='griewangk', extra=(), dim=256, np=2097152, strategy='Best1Bin', CR=0.9, F=0.8, lo=-400.,
                hi=400., bounds='clamp', penalty=None, k=2),
+    # other short-row shapes of the exponential-crossover kernels (K2f / K2d): 8 lanes per row, transcendental cost
+    'g128': dict(desc='Griewangk 128-D, NP=1048576/GPU, Rand1Exp CR=0.9 F=0.8, clamp +-400',
+                 cost='griewangk', extra=(), dim=128, np=1048576, strategy='Rand1Exp', CR=0.9, F=0.8, lo=-400., hi=400.,
+                 bounds='clamp', penalty=None, k=3),
+    'r32': dict(desc='Rosenbrock 32-D, NP=2097152/GPU, Best1Exp CR=0.9 F=0.8, clamp +-5',
+                cost='rosen', extra=(), dim=32, np=2097152, strategy='Best1Exp', CR=0.9, F=0.8, lo=-5., hi=5.,
+                bounds='clamp', penalty=None, k=2),
     # mystic's default strategy on short rows (not a BASELINE config): whole donor rows, binomial crossover
     'b4': dict(desc='Rosenbrock 64-D, NP=1048576/GPU, Best1Bin CR=0.9 F=0.8, clamp +-5 (binomial crossover, short rows)',
                cost='rosen', extra=(), dim=64, np=1048576, strategy='Best1Bin', CR=0.9, F=0.8, lo=-5., hi=5.,
