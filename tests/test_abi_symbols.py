@@ -62,3 +62,26 @@ def test_missing_library_fails_loudly():
                           universal_newlines=True, timeout=120)
     assert proc.returncode != 0
     assert 'is missing' in proc.stdout and 'no CPU fallback' in proc.stdout, proc.stdout[-2000:]
+
+
+def test_python_constants_match_the_header():
+    """the cost ids of mystic_b200.models and the kernel-family names of the engine are the enums of
+    include/mystic_b200.h"""
+    import os
+    import re
+    from mystic_b200 import models
+    from mystic_b200.engine import DeviceEngine
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'include', 'mystic_b200.h')).read()
+    enums = dict((k, int(v)) for k, v in re.findall(r'\b(MB2_[A-Z0-9_]+)\s*=\s*(\d+)', hdr))
+    for name, value in vars(models).items():
+        if name.startswith('COST_') and isinstance(value, int):
+            assert enums['MB2_' + name] == value, name
+    costs = [c for c in vars(models).values() if isinstance(c, models.DeviceCost)]
+    assert len(set(c.__name__ for c in costs)) >= 26
+    fam = dict((k[len('MB2_KERNEL_'):].lower(), v) for k, v in enums.items() if k.startswith('MB2_KERNEL_'))
+    names = DeviceEngine.KERNEL_FAMILIES
+    assert len(names) == len(fam)
+    alias = {'warp_per_row': 'warp_per_row', 'tma_bin': 'tma_bin', 'tma_exp': 'tma_exp', 'rows': 'rows', 'rows_per_warp': 'rows_per_warp',
+             'thread_per_row': 'thread_per_row', 'dmma': 'dmma', 'islands': 'islands', 'rows_bulk': 'rows_bulk', 'none': 'none'}
+    for i, n in enumerate(names):
+        assert fam[alias[n]] == i, n
