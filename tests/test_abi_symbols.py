@@ -85,3 +85,27 @@ def test_python_constants_match_the_header():
              'thread_per_row': 'thread_per_row', 'dmma': 'dmma', 'islands': 'islands', 'rows_bulk': 'rows_bulk', 'none': 'none'}
     for i, n in enumerate(names):
         assert fam[alias[n]] == i, n
+
+
+def _build_c_demo(out):
+    import os
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cuda = os.environ.get('CUDA_HOME', '/usr/local/cuda')
+    cmd = ['gcc', '-std=c99', '-O2', '-Wall', '-Werror', os.path.join(repo, 'examples', 'c_abi_demo.c'), '-I' + os.path.join(repo, 'include'),
+           '-I' + os.path.join(cuda, 'include'), '-L' + os.path.join(repo, 'mystic_b200', '_lib'), '-lmystic_b200',
+           '-L' + os.path.join(cuda, 'lib64'), '-lcudart', '-Wl,-rpath,' + os.path.join(repo, 'mystic_b200', '_lib'), '-o', out]
+    return subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=300)
+
+
+def test_header_is_plain_c_and_the_library_links_from_c(tmp_path):
+    """include/mystic_b200.h compiles as C99 and examples/c_abi_demo.c links against the library with nothing but
+    libcudart: the boundary carries no C++ or torch types"""
+    import shutil
+    if shutil.which('gcc') is None:
+        import pytest
+        pytest.skip('no gcc')
+    from mystic_b200 import build as _build
+    _build.build()
+    proc = _build_c_demo(str(tmp_path / 'c_abi_demo'))
+    assert proc.returncode == 0, proc.stdout[-3000:]

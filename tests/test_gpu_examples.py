@@ -19,3 +19,17 @@ def test_example_runs(script, expect):
                           env=dict(os.environ, PYTHONPATH=REPO + os.pathsep + os.environ.get('PYTHONPATH', '')))
     assert proc.returncode == 0, proc.stdout[-3000:]
     assert expect in proc.stdout, proc.stdout[-3000:]
+
+
+def test_c_abi_demo_runs(tmp_path):
+    """examples/c_abi_demo.c: the solver's generation loop driven from plain C through include/mystic_b200.h"""
+    import shutil
+    if shutil.which('gcc') is None:
+        pytest.skip('no gcc')
+    from tests.test_abi_symbols import _build_c_demo
+    exe = str(tmp_path / 'c_abi_demo')
+    proc = _build_c_demo(exe)
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    run = subprocess.run([exe], cwd=REPO, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True, timeout=120)
+    assert run.returncode == 0, run.stdout[-3000:]
+    assert 'generation 200' in run.stdout and 'expected error: unknown cost id 99' in run.stdout, run.stdout
