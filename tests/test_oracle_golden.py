@@ -60,6 +60,28 @@ def test_model_known_answers():
     assert f('chebyshev8cost')([[1.] * 9])[0] == 7823.744334789609
     assert f('chebyshev8cost', (4096,))([[1.] * 9])[0] == 22615.651073208195
     assert f('chebyshev8cost', (4096,))([[100, -50, 3, 7, -20, 1, 0.5, -2, 1]])[0] == 2014464.4595239898
+    # the other mystic.models functions (values of the unmodified reference in the build container; the first
+    # three, the minima its docstrings quote: pohlheim.py:276, 311, 350)
+    for name, x, want in [
+            ('branins', [3.141592653589793, 2.275], 0.39788735772973816),
+            ('easom', [3.141592653589793, 3.141592653589793], -1.0),
+            ('goldstein', [0.0, -1.0], 3.0),
+            ('peaks', [0.22827892, -1.62553496], -6.551133332835841),
+            ('venkat91', [4.0, 4.0], -19.668329370585823),
+            ('fosc3d', [-0.215018, 0.240356], -4.501069742528923),
+            ('nmin51', [-0.02440313, 0.21061247], -3.306868647458795),
+            ('shekel', [-31.5, -31.9], 0.01562551162942235),
+            ('ellipsoid', [1.0, 2.0, 3.0, -4.0], 50.0),
+            ('paviani', [9.35] * 10, -45.77846739623988),
+            ('sphere', [1.0, 2.0, 3.0], 14.0),
+            ('rastrigin', [0.5, -1.5], 42.5),
+            ('schwefel', [420.9687465, 420.9687465], -837.9657745448675),
+            ('ackley', [0.1, -0.2, 0.3], 2.2544445866053593),
+            ('step', [0.5, -1.5, 6.0], 54.4),
+            ('michal', [2.20289811, 1.57078059], -1.8013033991765086),
+            ('powers', [0.5, -0.5, 2.0], 16.375)]:
+        got = f(name)([x])[0]
+        assert got == want or abs(got - want) <= 1e-14 * abs(want), (name, got, want)
     pen = [dict(ptype='quadratic_inequality', G=[1., 1., 1.], h=1.0, k=100, hpow=5)]
     assert orc.penalty_value([[1., 1., 1.]], pen)[0] == 800.0
     assert orc.penalty_value([[0., 0., 0.]], pen)[0] == 0.0
