@@ -97,16 +97,38 @@ def device_cost(w):
         return models.poly.CostFactory2(pts, obs, w['dim']), None
     return getattr(models, w['cost']), (tuple(w['extra']) or None)
 
-# dram__bytes_read.sum + dram__bytes_write.sum of the fused generation kernel, per launch at the
-# workload's full per-GPU size, from one `ncu --set full` capture each (summaries under profiles/)
-NCU_TRAFFIC = {
-    'c2': (1.444322e9 + 0.513861e9, 'profiles/r1_c2_tma_kernel_ncu_full_summary.csv'),
-    'x2': (0.567731e9 + 0.493002e9, 'profiles/r1_x2_exp_tma_kernel_ncu_full_summary.csv'),
-    'c3': (0.265026e9 + 0.037010e9, 'profiles/r1_c3_kernel_ncu_full_summary.csv'),
-    'f2': (0.258753e9 + 0.034031e9, 'profiles/r1_f2_polyfit_dmma_ncu_full_summary.csv'),
-    'c4': (1.026244e9 + 0.512175e9, 'profiles/r1_c4_rows_bulk_kernel_ncu_full_summary.csv'),
-    'c5': (12.791601e9 + 4.323565e9, 'profiles/r1_c5_kernel_ncu_full_summary.csv'),
+# `ncu --set full` captures of the fused generation kernel at each workload's full per-GPU size
+# (summaries under profiles/, newest first): roofline.traffic = dram__bytes_read.sum +
+# dram__bytes_write.sum of ONE launch, read from the committed summary at run time
+NCU_SUMMARIES = {
+    'c2': ('profiles/r2_c2_tma_kernel_ncu_full_summary.csv', 'profiles/r1_c2_tma_kernel_ncu_full_summary.csv'),
+    'x2': ('profiles/r2_x2_exp_tma_kernel_ncu_full_summary.csv', 'profiles/r1_x2_exp_tma_kernel_ncu_full_summary.csv'),
+    'c3': ('profiles/r2_c3_kernel_ncu_full_summary.csv', 'profiles/r1_c3_kernel_ncu_full_summary.csv'),
+    'f2': ('profiles/r2_f2_polyfit_dmma_ncu_full_summary.csv', 'profiles/r1_f2_polyfit_dmma_ncu_full_summary.csv'),
+    'c4': ('profiles/r2_c4_rows_bulk_kernel_ncu_full_summary.csv', 'profiles/r1_c4_rows_bulk_kernel_ncu_full_summary.csv'),
+    'c5': ('profiles/r2_c5_kernel_ncu_full_summary.csv', 'profiles/r1_c5_kernel_ncu_full_summary.csv'),
 }
+_UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
+
+
+def ncu_traffic(workload):
+    """-> (DRAM bytes read + written by one launch of the fused kernel, summary file) or (None, None)"""
+    import csv
+    for rel in NCU_SUMMARIES.get(workload, ()):
+        path = os.path.join(REPO, rel)
+        if not os.path.exists(path):
+            continue
+        got = {}
+        with open(path) as f:
+            for row in csv.reader(f):
+                if len(row) >= 4 and row[1] in ('dram__bytes_read.sum', 'dram__bytes_write.sum') and row[1] not in got:
+                    try:
+                        got[row[1]] = float(row[3]) * _UNIT.get(row[2], 1.0)
+                    except ValueError:
+                        pass
+        if len(got) == 2:
+            return got['dram__bytes_read.sum'] + got['dram__bytes_write.sum'], rel
+    return None, None
 
 
 def algorithmic_bytes_per_candidate(w):
@@ -213,8 +235,21 @@ def measured_peaks():
 
 
 # ------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port on the host cores, bounded sample
+# CPU baseline / reference arm: the C/OpenMP oracle port on every host core over the arm's whole
+# workload, and the reference's own Python solver (baseline/_ref) beside it.  These legs always run
+# in their own process (`bench.py --impl reference`): the GPU process never maps oracle code.
 # ------------------------------------------------------------------------------------------
+def host_threads():
+    return len(os.sched_getaffinity(0))
+
+
+def workload_config(w, NP_local, NP_global):
+    """the `config` object both arms print (identical for the same command line)"""
+    return {'workload': w['desc'], 'np_per_gpu': NP_local, 'np_total': NP_global, 'dim': w['dim'],
+            'l2': 'inputs larger than L2 (population %.0f MiB per GPU per buffer, no flush needed)'
+                  % (NP_local * w['dim'] * 8 / 2 ** 20)}
+
+
 def oracle_setup(w, NP, seed):
     from oracle import de_oracle as orc
     D = w['dim']
@@ -236,7 +271,7 @@ def time_oracle(w, NP, steps, warmup, seed=0x5EED):
     try:
         from oracle import c_port
         if c_port.available():
-            return c_port.time_workload(w, NP, steps, warmup, seed)
+            return c_port.time_workload(w, NP, steps, warmup, seed, threads=host_threads())
     except ImportError:
         pass
     orc, st, cost, pen = oracle_setup(w, NP, seed)
@@ -250,23 +285,71 @@ def time_oracle(w, NP, steps, warmup, seed=0x5EED):
         NP, w['np'], steps)
 
 
+def reference_python(workload, quick, timeout=600):
+    """the UNMODIFIED reference solver (mystic from baseline/_ref) timed by oracle/reference_python.py"""
+    cmd = [sys.executable, os.path.join(REPO, 'oracle', 'reference_python.py'), '--workload', workload]
+    cmd += (['--np', '1024', '--generations', '2', '--pool-np'] if quick else
+            ['--np', '1024', '4096', '--generations', '2', '--pool-np', '64', '--pool-generations', '1', '--procs',
+             str(min(4, host_threads()))])
+    env = dict(os.environ)
+    env.pop('OMP_NUM_THREADS', None)
+    try:
+        out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, timeout=timeout,
+                             env=env)
+        lines = [ln for ln in out.stdout.splitlines() if ln.startswith('{')]
+        return json.loads(lines[-1]) if lines else {'error': (out.stderr or 'no output')[-300:]}
+    except Exception as e:
+        return {'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
+
+
 def run_reference_arm(args, w):
+    """`--impl reference`: rank 0 alone; the whole workload of the arm (all N shards), every host core"""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
-    NP = min(w['np'], args.ref_np)
+    world = max(1, args.gpus)
+    NP_local = w['np'] // world if w.get('strong') else w['np']
+    NP_global = NP_local * world
+    NP = min(NP_global, args.ref_np) if args.ref_np else NP_global
     steps = max(1, args.steps)
     value, dt, kind, cores, sample = time_oracle(w, NP, steps, max(1, min(args.warmup, 2)))
+    cpu = {'value': value, 'unit': 'candidate-evals/s', 'cores': cores, 'kind': kind, 'sample': sample}
+    if not args.no_reference_python:
+        cpu['reference_python'] = reference_python(args.workload, quick=not args.full_reference_python)
     line = {
         'impl': 'reference', 'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': value,
         'unit': 'candidate-evals/s', 'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup,
-        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64',
-        'data': 'synthetic', 'config': {'workload': w['desc'], 'sample_rows': NP},
-        'cpu_baseline': {'value': value, 'unit': 'candidate-evals/s', 'cores': cores, 'kind': kind, 'sample': sample},
+        'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong' if w.get('strong') else 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic', 'config': workload_config(w, NP_local, NP_global),
+        'details': {'rows_timed': NP, 'host_threads': cores},
+        'cpu_baseline': cpu,
         'e2e': {'value': value, 'unit': 'candidate-evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     print(json.dumps(line))
+
+
+def cpu_baseline_subprocess(workload, steps=3, warmup=1, full_python=True, timeout=900):
+    """our arm's `cpu_baseline`: the reference arm in a child process (so this process maps no oracle code)"""
+    cmd = [sys.executable, os.path.abspath(__file__), '--impl', 'reference', '--workload', workload, '--gpus', '1',
+           '--steps', str(steps), '--warmup', str(warmup)] + (['--full-reference-python'] if full_python else [])
+    env = dict(os.environ)
+    for k in ('OMP_NUM_THREADS', 'RANK', 'LOCAL_RANK', 'WORLD_SIZE'):
+        env.pop(k, None)
+    return subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, universal_newlines=True, env=env), timeout
+
+
+def collect_cpu_baseline(handle):
+    proc, timeout = handle
+    try:
+        out, err = proc.communicate(timeout=timeout)
+        lines = [ln for ln in out.splitlines() if ln.startswith('{')]
+        if lines:
+            return json.loads(lines[-1])['cpu_baseline']
+        return {'value': None, 'error': (err or 'no output')[-300:]}
+    except Exception as e:
+        proc.kill()
+        return {'value': None, 'error': '%s: %s' % (type(e).__name__, str(e)[:200])}
 
 
 # ------------------------------------------------------------------------------------------
@@ -293,95 +376,106 @@ def build_solver(w, NP_global, distributed, seed):
     return s
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
-    ap.add_argument('--np', type=int, default=0, help='override rows per GPU (testing)')
-    ap.add_argument('--ref-np', type=int, default=4096, help='rows of the bounded CPU sample')
-    ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
-                    help='multi-GPU best exchange: stores into peer memory fused into the epilogue kernel, or an NCCL all-gather')
-    ap.add_argument('--sustain', type=float, default=0.7, help='seconds of un-timed load before the timed region')
-    args = ap.parse_args()
-    os.environ['MB2_EXCHANGE'] = args.exchange
-    if os.environ.get('MB2_BENCH_DEBUG'):
-        import faulthandler
-        faulthandler.dump_traceback_later(90, exit=True)   # a hung run prints where it hangs
-    w = dict(WORKLOADS[args.workload])
-    if w.get('fit'):
-        w['extra'] = fit_data(w)
-    if args.np:
-        w['np'] = args.np
+class Rig(object):
+    """process-wide state of our arm: ranks, barrier, peaks"""
 
-    if args.impl == 'reference':
-        run_reference_arm(args, w)
-        return
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.world = int(os.environ.get('WORLD_SIZE', '1'))
+        self.rank = int(os.environ.get('RANK', '0'))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py needs a CUDA device: the engine has no CPU fallback')
+        torch.cuda.set_device(self.local_rank)
+        self.distributed = self.world > 1
+        if self.distributed:
+            dist.init_process_group('nccl', device_id=torch.device('cuda', self.local_rank))
+        self.warmup = max(3, args.warmup)
+        self.steps = max(1, args.steps)
+        self.seed = 0x5EED
+        self.peaks, self.peaks_src = measured_peaks()
+        self.fp64 = None
 
-    import torch
-    import torch.distributed as dist
-    from mystic_b200 import models, termination
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.distributed:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device: the engine has no CPU fallback')
-    torch.cuda.set_device(local_rank)
-    distributed = world > 1
-    if distributed:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    warmup = max(3, args.warmup)
-    steps = max(1, args.steps)
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([x], dtype=self.torch.float64, device='cuda')
+        if self.distributed:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def fp64_peaks(self):
+        """FP64 peaks of this GPU measured in this run: DFMA chain and DMMA.8x8x4 (mb2_probe_fp64_peak, our own
+        probe kernels) and cuBLAS DGEMM 4096^3 through torch.matmul (a library call, off the hot path)"""
+        if self.fp64 is None:
+            from mystic_b200.engine import probe_fp64_peak
+            torch = self.torch
+            dfma, dmma = probe_fp64_peak(self.local_rank)
+            n = 4096
+            a = torch.randn((n, n), dtype=torch.float64, device='cuda')
+            b = torch.randn((n, n), dtype=torch.float64, device='cuda')
+            torch.matmul(a, b)
+            best = float('inf')
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                torch.matmul(a, b)
+                e1.record()
+                torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            del a, b
+            torch.cuda.empty_cache()
+            self.fp64 = {'dfma_tflops': dfma, 'dmma_m8n8k4_tflops': dmma, 'cublas_dgemm_4096_tflops': 2.0 * n ** 3 / (best * 1e-3) / 1e12}
+        return self.fp64
+
+
+def device_leg(rig, name, w):
+    """device-resident throughput of one workload: population generated on the device, K generations timed with
+    CUDA events on the launching stream (burst, then again under sustained load), max over ranks"""
+    torch, dist = rig.torch, rig.dist
+    from mystic_b200 import termination
+    world, distributed, steps = rig.world, rig.distributed, rig.steps
     NP_local = w['np'] // world if w.get('strong') else w['np']
     NP_global = NP_local * world
     D = w['dim']
-    seed = 0x5EED
     cost, extra = device_cost(w)
-    never = termination.VTR(-1.0)
-
-    def barrier():
-        torch.cuda.synchronize()
-        if distributed:
-            dist.barrier()
-            torch.cuda.synchronize()
-
-    # ---- device-resident throughput: population generated on the device, K generations timed
-    s = build_solver(w, NP_global, distributed, seed)
+    s = build_solver(w, NP_global, distributed, rig.seed)
     s.SetRandomInitialPoints([w['lo']] * D, [w['hi']] * D)
-    s.SetTermination(never)
+    s.SetTermination(termination.VTR(-1.0))
     s.Step(cost, ExtraArgs=extra)               # generation 0 (allocates, initialises, evaluates)
-    for _ in range(warmup):
+    for _ in range(rig.warmup):
         s.Step()
     eng = s._engine
     grid, block, smem = eng.launch_info()
+    family = eng.kernel_family()
+
     def timed(nsteps):
-        barrier()
+        rig.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(nsteps):
-            eng.step()                           # K2 + K3 on torch's current stream
+            eng.step()                           # K2 + K3 (+ the fused best exchange) on torch's current stream
             if distributed:
-                s._exchange_best()
+                s._exchange_best()               # no-op with the peer exchange; the all-gather with --exchange nccl
         e1.record()
-        barrier()
-        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device='cuda')
-        if distributed:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        return float(tt.item())
+        rig.barrier()
+        return rig.max_over_ranks(e0.elapsed_time(e1))
 
     burst_ms = timed(steps)                      # cold clocks/power state: a burst figure, reported beside `value`
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    sampler = ClockSampler(rig.local_rank) if rig.rank == 0 else None
     if sampler:
         sampler.start()
-    # un-timed sustain phase (~0.7 s of back-to-back generations): the timed region below is only a
-    # few milliseconds, too short for nvidia-smi to sample, so clocks / throttle reasons are sampled
-    # from here through the end of the timed region, under the same load.
+    # un-timed sustain phase: the timed region below is only milliseconds long, too short for nvidia-smi to
+    # sample, so clocks / throttle reasons are sampled from here through the end of the timed region, under
+    # the same load
     t_sus = time.perf_counter()
-    while time.perf_counter() - t_sus < args.sustain:
+    while time.perf_counter() - t_sus < rig.args.sustain:
         for _ in range(10):
             eng.step()
             if distributed:
@@ -390,116 +484,248 @@ def main():
     launches0 = eng.launch_count()
     dev_ms = timed(steps)                        # the reported value: K generations under sustained load
     launches = eng.launch_count() - launches0
-    inf_frac = s._last[0] / float(NP_global) if s._last else 0.0
-    acc_frac = s._last[1] / float(NP_global) if s._last else 0.0
+    res = s._engine.read_result()
     clocks = sampler.stop() if sampler else None
+    out = dict(name=name, w=w, NP_local=NP_local, NP_global=NP_global, dev_ms=dev_ms, burst_ms=burst_ms, launches=int(launches),
+               clocks=clocks, grid=grid, block=block, smem=smem, family=family,
+               inf_fraction=res[2] / float(NP_local), accept_fraction=res[3] / float(NP_local))
     del s, eng
+    gc.collect()
     torch.cuda.empty_cache()
+    return out
 
-    # ---- end to end: host population (pinned) -> H2D -> generation 0 -> K x Step() with the result
-    #      of every step read back to the host
-    numa_node = bind_to_gpu_numa_node(local_rank)
-    host_rows = 1 if w.get('no_e2e') else NP_local
-    host_pop = torch.empty((host_rows, D), dtype=torch.float64, pin_memory=True)
-    rng = np.random.default_rng(seed + rank)
+
+def roofline_of(rig, leg):
+    w, name, NP_local = leg['w'], leg['name'], leg['NP_local']
+    peaks = rig.peaks
+    bpc = algorithmic_bytes_per_candidate(w)
+    step_s = leg['dev_ms'] * 1e-3 / rig.steps
+    burst_s = leg['burst_ms'] * 1e-3 / rig.steps
+    achieved = bpc * NP_local / step_s / 1e9
+    base = name.rstrip('s') if name == 'c5s' else name
+    traffic, traffic_src = (None, None)
+    if NP_local == WORKLOADS.get(base, {}).get('np'):
+        traffic, traffic_src = ncu_traffic(base)
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'traffic_source': traffic_src,
+                'peak_source': rig.peaks_src, 'frac_burst': bpc * NP_local / burst_s / 1e9 / peaks['hbm_gbs'],
+                'algorithmic_bytes_per_candidate': bpc, 'algorithmic_bytes_per_launch': bpc * NP_local,
+                'kernel': 'fused generation kernel (%s) + de_finalize_kernel, per generation, per GPU' % leg['family']}
+    flops = algorithmic_flops_per_candidate(w)
+    if flops:
+        # the Chebyshev / polynomial contraction is FP64-pipe bound; DMMA and DFMA share that pipe on B200, so the
+        # denominator is the highest FP64 rate measured in this run, whichever way it was reached
+        fp = rig.fp64_peaks()
+        which = max(fp, key=fp.get)
+        tf = flops * NP_local / step_s / 1e12
+        roofline = {'bound': 'tensor', 'achieved': tf, 'peak': fp[which], 'unit': 'TFLOP/s', 'frac': tf / fp[which],
+                    'frac_burst': flops * NP_local / burst_s / 1e12 / fp[which],
+                    'frac_of_dmma_probe': tf / fp['dmma_m8n8k4_tflops'],
+                    'traffic': traffic, 'traffic_source': traffic_src,
+                    'peak_source': 'measured in this run: %s (highest of %s)' % (which, json.dumps({k: round(v, 2) for k, v in fp.items()})),
+                    'algorithmic_flops_per_candidate': flops, 'hbm_frac': achieved / peaks['hbm_gbs'],
+                    'kernel': ('de_step_cheb_mma_kernel' + ('<KS, RESID>' if w['cost'] == 'polyfit' else ''))
+                    if w.get('tensor_cores') else 'de_step_kernel (Horner)'}
+    return roofline
+
+
+def leg_record(rig, leg):
+    """sub-record of one workload for the `also` object"""
+    steps = rig.steps
+    return {'workload': leg['w']['desc'], 'np_per_gpu': leg['NP_local'], 'np_total': leg['NP_global'], 'dim': leg['w']['dim'],
+            'n_gpus': rig.world, 'scaling': 'strong' if leg['w'].get('strong') else 'weak',
+            'value': leg['NP_global'] * steps / (leg['dev_ms'] * 1e-3), 'unit': 'candidate-evals/s',
+            'ms_per_step': leg['dev_ms'] / steps, 'burst_ms_per_step': leg['burst_ms'] / steps, 'steps': steps,
+            'roofline': roofline_of(rig, leg), 'clocks': leg['clocks'], 'gpu_launches': leg['launches'],
+            'kernel_family': leg['family'], 'grid': leg['grid'], 'block': leg['block'], 'smem_bytes': leg['smem'],
+            'inf_fraction': leg['inf_fraction'], 'accept_fraction': leg['accept_fraction']}
+
+
+def e2e_leg(rig, w):
+    """end to end through the public API: pinned host population -> SetPopulation -> Step (H2D + generation 0)
+    -> Solve() for K generations, every generation's result read back -> seconds (max over ranks), breakdown"""
+    torch = rig.torch
+    from mystic_b200 import termination
+    world, steps = rig.world, rig.steps
+    NP_local = w['np'] // world if w.get('strong') else w['np']
+    NP_global = NP_local * world
+    D = w['dim']
+    cost, extra = device_cost(w)
+    numa_node = bind_to_gpu_numa_node(rig.local_rank)
+    host_pop = torch.empty((NP_local, D), dtype=torch.float64, pin_memory=True)
+    rng = np.random.default_rng(rig.seed + rig.rank)
     hp = host_pop.numpy()
     chunk = max(1, (1 << 24) // D)
-    for i in range(0, host_rows, chunk):
-        hp[i:i + chunk] = rng.uniform(w['lo'], w['hi'], size=(min(chunk, host_rows - i), D))
-    def e2e_run():
-        s2 = build_solver(w, NP_global, distributed, seed)
-        s2.SetTermination(never)
-        barrier()
+    for i in range(0, NP_local, chunk):
+        hp[i:i + chunk] = rng.uniform(w['lo'], w['hi'], size=(min(chunk, NP_local - i), D))
+
+    def e2e_run(breakdown):
+        s2 = build_solver(w, NP_global, rig.distributed, rig.seed)
+        s2.SetTermination(termination.VTR(-1.0))
+        rig.barrier()
         s2.SetEvaluationLimits(generations=steps, evaluations=10 ** 18)
         t0 = time.perf_counter()
         s2.SetPopulation(hp, local=True)         # this rank's rows; pinned, uploaded as is
         s2.Step(cost, ExtraArgs=extra)           # H2D upload + generation 0
+        if breakdown:
+            torch.cuda.synchronize()
         t1 = time.perf_counter()
         s2.Solve()                               # the user's call: K generations until the generation limit;
         torch.cuda.synchronize()                 # every generation's (bestEnergy, counters, bestSolution) reaches the host
         dt = time.perf_counter() - t0
         assert s2.generations == steps, (s2.generations, steps)
-        if os.environ.get('MB2_BENCH_DEBUG'):
-            print('e2e: upload + generation 0 %.2f ms, %d steps %.2f ms' % ((t1 - t0) * 1e3, steps, (t0 + dt - t1) * 1e3),
-                  file=sys.stderr)
         del s2
         gc.collect()
-        return dt
+        return dt, (t1 - t0), (t0 + dt - t1)
 
-    if w.get('no_e2e'):
-        e2e_s = float('nan')
-    else:
-        e2e_run()                                # warm-up: device allocations come from torch's cache afterwards
-        e2e_s = min(e2e_run(), e2e_run())        # best of two (host-side jitter: PCIe, page faults)
-    t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
-    if distributed:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    d2h_per_step = 8 * D + 40
-    h2d_per_step = NP_local * D * 8.0 / steps
+    _, up_s, st_s = e2e_run(True)                # warm-up (device allocations come from torch's cache afterwards);
+    e2e_s = min(e2e_run(False)[0], e2e_run(False)[0])   # best of two (host-side jitter: PCIe, page faults)
+    e2e_s = rig.max_over_ranks(e2e_s)
+    del host_pop, hp
     torch.cuda.empty_cache()
+    return dict(seconds=e2e_s, NP_local=NP_local, NP_global=NP_global, numa_node=numa_node,
+                breakdown={'upload_and_generation0_ms': rig.max_over_ranks(up_s) * 1e3,
+                           'solve_%d_generations_ms' % steps: rig.max_over_ranks(st_s) * 1e3,
+                           'note': 'from the warm-up run (with a synchronize between the two parts)'})
+
+
+def shard_parity(rig):
+    """N > 1: one small sharded run of the drop-in solver against the numpy oracle's emulation of all shards
+    (tests/dist_gpu_check.emulate: shard-local donors, best merged by the reference's rule) -> bit-exact?"""
+    torch, dist = rig.torch, rig.dist
+    from mystic_b200 import DifferentialEvolutionSolver2, models, termination
+    from oracle import de_oracle as orc
+    from tests.dist_gpu_check import emulate
+    ok = True
+    for strategy, cost, D, NP, lo, hi in (('Best1Bin', 'rosen', 256, 64 * rig.world + 3, -5., 5.),
+                                          ('Rand1Exp', 'corana', 64, 96 * rig.world + 5, -1000., 1000.)):
+        seed, gens = 0xD15C0 + D, 4
+        s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=seed, distributed=True, strategy=strategy)
+        s.SetRandomInitialPoints([lo] * D, [hi] * D)
+        s.SetStrictRanges([lo] * D, [hi] * D, tight=True)
+        s.SetTermination(termination.VTR(-1.0))
+        s.SetEvaluationLimits(generations=10 ** 6)
+        s.Step(getattr(models, cost))
+        for _ in range(gens):
+            s.Step()
+        engs, hist = emulate(rig.world, NP, D, seed, strategy, getattr(models, cost).cost_id,
+                             (orc.BOUNDS_CLAMP, np.full(D, lo), np.full(D, hi)), gens)
+        mine = engs[rig.rank]
+        ok = ok and np.array_equal(s.population, mine.population()) \
+            and np.array_equal(np.array(s.bestSolution), mine.state.bestSolution) \
+            and np.allclose(np.array(s.energy_history), np.array(hist), rtol=1e-12, atol=0)
+        del s
+    t = torch.tensor([1 if ok else 0], device='cuda')
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t.item()))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--np', type=int, default=0, help='override rows per GPU (testing)')
+    ap.add_argument('--ref-np', type=int, default=0, help='cap on the rows of the CPU leg (0 = the whole workload)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-reference-python', action='store_true', help='CPU leg: skip the reference\'s own Python solver')
+    ap.add_argument('--full-reference-python', action='store_true',
+                    help='CPU leg: also NP=4096 serial and the multiprocess.Pool map (about a minute more)')
+    ap.add_argument('--also', default=None,
+                    help='comma-separated workloads measured after the main one and reported as sub-records of the same '
+                         'line (default with the default workload: c5s at every N; c4 and c3 at N=1); "none" disables')
+    ap.add_argument('--exchange', default='peer', choices=['peer', 'nccl'],
+                    help='multi-GPU best exchange: stores into peer memory fused into the epilogue kernel, or an NCCL all-gather')
+    ap.add_argument('--sustain', type=float, default=0.7, help='seconds of un-timed load before the timed region')
+    args = ap.parse_args()
+    os.environ['MB2_EXCHANGE'] = args.exchange
+    if os.environ.get('MB2_BENCH_DEBUG'):
+        import faulthandler
+        faulthandler.dump_traceback_later(600, exit=True)   # a hung run prints where it hangs
+
+    def workload(name):
+        w = dict(WORKLOADS[name])
+        if w.get('fit'):
+            w['extra'] = fit_data(w)
+        return w
+    w = workload(args.workload)
+    if args.np:
+        w['np'] = args.np
+
+    if args.impl == 'reference':
+        run_reference_arm(args, w)
+        return
+
+    rig = Rig(args)
+    torch, dist = rig.torch, rig.dist
+    world, rank, steps = rig.world, rig.rank, rig.steps
+    if args.also is None:
+        also_names = (['c5s'] + (['c4', 'c3'] if world == 1 else [])) if (args.workload == 'c2' and not args.np) else []
+    else:
+        also_names = [a for a in args.also.split(',') if a and a != 'none']
+
+    leg = device_leg(rig, args.workload, w)
+    e2e = None if w.get('no_e2e') else e2e_leg(rig, w)
+    # the CPU legs run in a child process beside the device-timed `also` legs (they do not touch the GPU, and the
+    # `also` legs are timed on the device); the end-to-end leg above, which is host-timed, ran alone
+    cpu_handle = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_handle = cpu_baseline_subprocess(args.workload, full_python=not args.no_reference_python)
+    also = {}
+    for name in also_names:
+        try:
+            also[name] = leg_record(rig, device_leg(rig, name, workload(name)))
+        except Exception as e:  # one sub-record failing must not cost the line
+            also[name] = {'error': '%s: %s' % (type(e).__name__, str(e)[:300])}
+            gc.collect()
+            torch.cuda.empty_cache()
+    parity = shard_parity(rig) if rig.distributed else None
 
     if rank != 0:
-        if distributed:
+        if rig.distributed:
             dist.destroy_process_group()
         return
 
-    value = NP_global * steps / (dev_ms * 1e-3)
-    peaks, peaks_src = measured_peaks()
-    bpc = algorithmic_bytes_per_candidate(w)
-    step_s = dev_ms * 1e-3 / steps
-    achieved = bpc * NP_local / step_s / 1e9
-    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
-                'frac': achieved / peaks['hbm_gbs'], 'traffic': None, 'peak_source': peaks_src,
-                'frac_burst': bpc * NP_local / (burst_ms * 1e-3 / steps) / 1e9 / peaks['hbm_gbs'],
-                'algorithmic_bytes_per_candidate': bpc,
-                'kernel': 'de_step_kernel (fused generation) + de_finalize_kernel, per generation, per GPU'}
-    if args.workload in NCU_TRAFFIC and NP_local == WORKLOADS[args.workload]['np']:
-        roofline['traffic'], roofline['traffic_source'] = NCU_TRAFFIC[args.workload]
-        roofline['algorithmic_bytes_per_launch'] = bpc * NP_local
-    flops = algorithmic_flops_per_candidate(w)
-    if flops:
-        # the Chebyshev contraction is FP64-pipe bound: DMMA peak measured on this pool's B200 with
-        # tools/fp64_peak.cu (profiles/r1_fp64_peaks_b200.json): 33.02 TFLOP/s (DFMA 34.15, cuBLAS DGEMM 35.4)
-        tf = flops * NP_local / step_s / 1e12
-        roofline = {'bound': 'tensor', 'achieved': tf, 'peak': 33.02, 'unit': 'TFLOP/s', 'frac': tf / 33.02,
-                    'traffic': roofline.get('traffic'), 'traffic_source': roofline.get('traffic_source'),
-                    'peak_source': 'measured DMMA.8x8x4 peak (profiles/r1_fp64_peaks_b200.json)',
-                    'algorithmic_flops_per_candidate': flops, 'hbm_frac': achieved / peaks['hbm_gbs'],
-                    'kernel': ('de_step_cheb_mma_kernel' + ('<KS, RESID>' if w['cost'] == 'polyfit' else ''))
-                    if w.get('tensor_cores') else 'de_step_kernel (Horner)'}
-
+    NP_local, NP_global, D = leg['NP_local'], leg['NP_global'], w['dim']
     line = {
-        'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': value, 'unit': 'candidate-evals/s',
-        'n_gpus': world, 'steps': steps, 'warmup': warmup, 'ms_per_step': dev_ms / steps, 'higher_is_better': True,
+        'metric': 'DE candidate-evals/sec (gen+cost+select)', 'value': NP_global * steps / (leg['dev_ms'] * 1e-3),
+        'unit': 'candidate-evals/s', 'n_gpus': world, 'steps': steps, 'warmup': rig.warmup,
+        'ms_per_step': leg['dev_ms'] / steps, 'higher_is_better': True,
         'scaling': 'strong' if w.get('strong') else 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': w['desc'], 'np_per_gpu': NP_local, 'np_total': NP_global, 'dim': D,
-                   'rng': 'philox4x32-10 in-kernel', 'l2': 'inputs larger than L2 (population %.0f MiB per buffer)'
-                   % (NP_local * D * 8 / 2 ** 20), 'grid': grid, 'block': block, 'smem_bytes': smem,
-                   'inf_fraction': inf_frac, 'accept_fraction': acc_frac,
-                   'sustain_s_before_timing': args.sustain, 'burst_ms_per_step': burst_ms / steps,
-                   'e2e_host_numa_node': numa_node,
-                   'parallelism': ('candidate-sharded x%d, ' % world) + ('best exchange by peer-memory stores (NVLink) fused into the argmin epilogue'
-                                                                          if args.exchange == 'peer' else 'NCCL all-gather of the bests per generation') if distributed
-                   else 'single GPU'},
-        'roofline': roofline,
-        'e2e': {'value': NP_global * steps / e2e_s, 'unit': 'candidate-evals/s',
-                'h2d_bytes_per_step': h2d_per_step, 'd2h_bytes_per_step': d2h_per_step,
-                'what': 'pinned host population -> H2D -> generation 0 -> solver.Solve() for %d generations (every '
-                        'generation\'s best energy, counters and bestSolution read back to the host, termination + '
-                        'monitor per generation); only the %d generations are counted' % (steps, steps)},
-        'gpu_launches': int(launches),
-        'clocks': clocks,
+        'config': workload_config(w, NP_local, NP_global),
+        'details': {'rng': 'philox4x32-10 in-kernel', 'grid': leg['grid'], 'block': leg['block'], 'smem_bytes': leg['smem'],
+                    'kernel_family': leg['family'], 'inf_fraction': leg['inf_fraction'], 'accept_fraction': leg['accept_fraction'],
+                    'sustain_s_before_timing': args.sustain, 'burst_ms_per_step': leg['burst_ms'] / steps,
+                    'e2e_host_numa_node': e2e['numa_node'] if e2e else None,
+                    'parallelism': (('candidate-sharded x%d, ' % world) + (
+                        'best exchange by peer-memory stores (NVLink) fused into the argmin epilogue' if args.exchange == 'peer'
+                        else 'NCCL all-gather of the bests per generation')) if rig.distributed else 'single GPU'},
+        'roofline': roofline_of(rig, leg),
+        'gpu_launches': leg['launches'],
+        'clocks': leg['clocks'],
     }
-    if w.get('no_e2e'):
+    d2h_per_step = 8 * D + 40
+    if e2e:
+        line['e2e'] = {'value': NP_global * steps / e2e['seconds'], 'unit': 'candidate-evals/s',
+                       'h2d_bytes_per_step': NP_local * D * 8.0 / steps, 'd2h_bytes_per_step': d2h_per_step,
+                       'what': 'pinned host population -> H2D -> generation 0 -> solver.Solve() for %d generations (every '
+                               'generation\'s best energy, counters and bestSolution read back to the host, termination + '
+                               'monitor per generation); only the %d generations are counted' % (steps, steps),
+                       'breakdown': e2e['breakdown']}
+    else:
         line['e2e'] = {'value': None, 'unit': 'candidate-evals/s', 'h2d_bytes_per_step': None, 'd2h_bytes_per_step': d2h_per_step,
                        'what': 'not measured for this workload: the host copy of the population is %.0f GiB per rank'
                                % (NP_local * D * 8 / 2 ** 30)}
-    if world == 1 and not args.no_cpu_baseline:
-        v, dt, kind, cores, sample = time_oracle(w, min(w['np'], args.ref_np), 3, 1)
-        line['cpu_baseline'] = {'value': v, 'unit': 'candidate-evals/s', 'cores': cores, 'kind': kind, 'sample': sample}
+    if also:
+        line['also'] = also
+    if parity is not None:
+        line['shard_parity'] = parity
+    if cpu_handle is not None:
+        line['cpu_baseline'] = collect_cpu_baseline(cpu_handle)
     print(json.dumps(line))
-    if distributed:
+    if rig.distributed:
         dist.destroy_process_group()
 
 

@@ -274,6 +274,12 @@ int mb2_selftest_division(mb2_ctx* ctx, int64_t n, uint64_t seed, double span, i
  * uniformly from [-span, span], span <= 1e5.  Synchronises. */
 int mb2_selftest_cosine(mb2_ctx* ctx, int64_t n, uint64_t seed, double span, double* max_abs_err);
 
+/* FP64 peaks of `device`, measured now: a DFMA chain per thread (vector pipe) and mma.sync.m8n8k4.f64
+ * (SASS DMMA.8x8x4), in TFLOP/s.  bench.py divides the Chebyshev / polynomial-fit contraction's
+ * achieved rate (MB2_COST_CHEBYSHEV_MMA, the reference's _model_helper.py:16-33 evaluated for a whole
+ * population) by the DMMA figure instead of a constant.  Synchronises `stream`; no context needed. */
+int mb2_probe_fp64_peak(int device, int32_t iters, double* dfma_tflops, double* dmma_tflops, void* stream);
+
 /* launch geometry of the fused kernel (for bench.py / profiling): CTAs, threads, dynamic smem */
 int mb2_launch_info(mb2_ctx* ctx, int32_t* grid, int32_t* block, int32_t* smem_bytes);
 /* number of kernels this library has launched through the context (bench.py gpu_launches) */

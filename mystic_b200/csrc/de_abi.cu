@@ -43,6 +43,27 @@ int fail(int code, const char* fmt, ...) {
       return fail(MB2_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// Every entry point runs on its context's device and leaves the caller's current device as it found it
+// (PyTorch, or another engine of the process, may be working on a different GPU).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+    else if (err == cudaSuccess) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+#define ENTER_DEVICE(dev)                                                                                  \
+  DeviceGuard _device_guard(dev);                                                                          \
+  if (_device_guard.err != cudaSuccess)                                                                    \
+    return fail(MB2_ECUDA, "cudaSetDevice(%d) failed: %s", (int)(dev), cudaGetErrorString(_device_guard.err))
+
 struct StrategyInfo {
   int base, xover, k;
 };
@@ -708,7 +729,7 @@ int mb2_create_ws(int device, int64_t np_local, int32_t dim, int64_t np_global, 
     return fail(MB2_EINVAL, "bad shape np_local=%lld dim=%d np_global=%lld offset=%lld", (long long)np_local, dim,
                 (long long)np_global, (long long)global_offset);
   if (np_global > 0xffffffffll) return fail(MB2_EINVAL, "np_global exceeds the 32-bit Philox candidate counter");
-  CUDA_TRY(cudaSetDevice(device));
+  ENTER_DEVICE(device);
   mb2_ctx* c = new (std::nothrow) mb2_ctx();
   if (c == nullptr) return fail(MB2_EINVAL, "out of host memory");
   c->device = device;
@@ -766,7 +787,7 @@ int mb2_create(int device, int64_t np_local, int32_t dim, int64_t np_global, int
 
 int mb2_destroy(mb2_ctx* c) {
   if (c == nullptr) return MB2_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard _device_guard(c->device);
   if (c->mailbox != nullptr) {
     int err = 1;
     if (c->xchg_connected && cudaDeviceSynchronize() == cudaSuccess &&
@@ -830,11 +851,12 @@ int mb2_set_strategy(mb2_ctx* c, int strategy, double scale, double cross) {
 int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
   if (mode < BOUNDS_NONE || mode > BOUNDS_CLAMP) return fail(MB2_EINVAL, "unknown bounds mode %d", mode);
+  ENTER_DEVICE(c->device);
+  if (c->generation >= 0) CUDA_TRY(cudaDeviceSynchronize());  // kernels of a non-blocking stream may still read lo / hi
   if (mode != BOUNDS_NONE) {
     if (!lo || !hi) return fail(MB2_EINVAL, "bounds arrays are NULL");
     for (int i = 0; i < c->dim; ++i)
       if (lo[i] > hi[i]) return fail(MB2_EINVAL, "each min[i] must be <= the corresponding max[i]");
-    CUDA_TRY(cudaSetDevice(c->device));
     CUDA_TRY(cudaMemcpy(c->lo, lo, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->hi, hi, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
     bool uni = true;
@@ -855,6 +877,8 @@ int mb2_set_bounds(mb2_ctx* c, int mode, const double* lo, const double* hi) {
 int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
   if (cost < MB2_COST_ROSEN || cost > MB2_COST_DECAY) return fail(MB2_EINVAL, "unknown cost id %d", cost);
+  ENTER_DEVICE(c->device);
+  if (c->generation >= 0) CUDA_TRY(cudaDeviceSynchronize());  // kernels of a non-blocking stream may still read the cost tables
   c->cp.fit_kind = FIT_LORENTZIAN;
   if (cost == MB2_COST_DECAY) {  // a second elementwise forward model on the lorentzian instantiations
     if (c->dim != 5) return fail(MB2_EINVAL, "the dual exponential decay has 5 parameters (a1,a2,a3,a4,a5)");
@@ -885,7 +909,6 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
   // evaluation points -> device; Vandermonde fragments of the DMMA variants (see de_cheb_mma.cuh)
   auto upload_points = [&](const std::vector<double>& xs, bool mma) -> int {
     const int M = (int)xs.size();
-    CUDA_TRY(cudaSetDevice(c->device));
     if (c->cap_cheb_x < sizeof(double) * M) {
       void* p = nullptr;
       if (int rc = dev_alloc(c, sizeof(double) * M, &p)) return rc;
@@ -936,7 +959,6 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
     if (per_point) {
       for (int i = 0; i < M; ++i)
         if (!(params[2 + 2 * M + i] != 0.0)) return fail(MB2_EINVAL, "sigma[%d] must not be zero", i);
-      CUDA_TRY(cudaSetDevice(c->device));
       if (c->cap_fit_sigma_v < sizeof(double) * M) {
         void* p = nullptr;
         if (int rc = dev_alloc(c, sizeof(double) * M, &p)) return rc;
@@ -994,7 +1016,6 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
       tab[i].x = sq;
       tab[i].y = rc;
     }
-    CUDA_TRY(cudaSetDevice(c->device));
     void* p = nullptr;
     if (int rc = dev_alloc(c, sizeof(double2) * c->dim, &p)) return rc;
     c->grw_tab = (double2*)p;
@@ -1008,7 +1029,7 @@ int mb2_set_cost(mb2_ctx* c, int cost, const double* params, int32_t nparams) {
 int mb2_selftest_division(mb2_ctx* c, int64_t n, uint64_t seed, double span, int64_t* mismatches) {
   if (c == nullptr || mismatches == nullptr || n < 1) return fail(MB2_EINVAL, "bad argument");
   if (c->grw_tab == nullptr) return fail(MB2_ESTATE, "set the griewangk cost first");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   unsigned long long* d = c->part_ninf;  // scratch: not in use between generations
   CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
   selftest_division_kernel<<<c->sm_count * 8, 256>>>(n, (uint32_t)seed, (uint32_t)(seed >> 32), span, c->grw_tab, c->dim, d);
@@ -1022,7 +1043,7 @@ int mb2_selftest_division(mb2_ctx* c, int64_t n, uint64_t seed, double span, int
 
 int mb2_selftest_cosine(mb2_ctx* c, int64_t n, uint64_t seed, double span, double* max_abs_err) {
   if (c == nullptr || max_abs_err == nullptr || n < 1 || !(span <= kCosFastMax)) return fail(MB2_EINVAL, "bad argument");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   if (int rc = ensure_parts(c, 1)) return rc;
   unsigned long long* d = c->part_ninf;  // scratch: not in use between generations
   CUDA_TRY(cudaMemset(d, 0, sizeof(unsigned long long)));
@@ -1039,7 +1060,8 @@ int mb2_set_penalty(mb2_ctx* c, int32_t nterms, const int32_t* ptype, const doub
                     const double* kscale) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
   if (nterms < 0) return fail(MB2_EINVAL, "nterms < 0");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
+  if (c->generation >= 0) CUDA_TRY(cudaDeviceSynchronize());  // kernels of a non-blocking stream may still read the terms
   c->pp = {0, nullptr, nullptr, nullptr, nullptr};
   if (nterms == 0) return MB2_OK;
   if (!ptype || !G || !h || !kscale) return fail(MB2_EINVAL, "penalty arrays are NULL");
@@ -1091,7 +1113,7 @@ int mb2_set_capture(mb2_ctx* c, double* trial, double* energy) {
 int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const double* hi, void* stream) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   if (!lo || !hi) return fail(MB2_EINVAL, "init bounds are NULL");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   double *dlo = c->init_lo, *dhi = c->init_hi;
   CUDA_TRY(cudaMemcpyAsync(dlo, lo, sizeof(double) * c->dim, cudaMemcpyHostToDevice, s));
@@ -1114,7 +1136,7 @@ int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const doubl
 int mb2_upload_population(mb2_ctx* c, const double* pop_host, void* stream) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   if (!pop_host) return fail(MB2_EINVAL, "pop_host is NULL");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   CUDA_TRY(cudaMemcpyAsync(c->pop[c->cur], pop_host, sizeof(double) * c->np * c->dim, cudaMemcpyHostToDevice, s));
   int64_t grid = (c->np + 255) / 256;
@@ -1134,7 +1156,7 @@ int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy,
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   if (!energy_host || !best_x_host || generation < 0) return fail(MB2_EINVAL, "bad argument");
   if (c->n_islands > 1) return fail(MB2_EINVAL, "restart files of batched solvers are not supported");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   CUDA_TRY(cudaMemcpy(c->en[c->cur], energy_host, sizeof(double) * c->np, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->best_x, best_x_host, sizeof(double) * c->dim, cudaMemcpyHostToDevice));
   DeviceState st = {best_energy, best_index, 0, 0, generation};
@@ -1147,7 +1169,7 @@ int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy,
 
 int mb2_eval_initial(mb2_ctx* c, void* stream) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   c->generation = -1;
   if (int rc = launch_step(c, MODE_GEN0, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s))
@@ -1162,7 +1184,7 @@ int mb2_eval_initial(mb2_ctx* c, void* stream) {
 int mb2_step(mb2_ctx* c, void* stream) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   if (c->generation < 0) return fail(MB2_ESTATE, "mb2_eval_initial must run before mb2_step");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = launch_step(c, MODE_STEP, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s))
     return rc;
@@ -1178,7 +1200,7 @@ int mb2_set_termination(mb2_ctx* c, const mb2_termination* t, const double* hist
   if (t->kind < TERM_NONE || t->kind > TERM_LIMITS) return fail(MB2_EINVAL, "unknown termination kind %d", t->kind);
   if (t->lookback < 0 || t->lookback >= kHistMax) return fail(MB2_EINVAL, "lookback must be in [0, %d)", kHistMax);
   if (history_len < 0 || (history_len > 0 && history_host == nullptr)) return fail(MB2_EINVAL, "bad history");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   if (c->run == nullptr) {
     void* p = nullptr;
     if (int rc = dev_alloc(c, sizeof(RunState), &p)) return rc;
@@ -1217,7 +1239,7 @@ int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
   if (c->generation < 0) return fail(MB2_ESTATE, "mb2_eval_initial must run before mb2_run");
   if (max_steps < 1 || log_dev == nullptr) return fail(MB2_EINVAL, "bad argument");
   if (c->replay) return fail(MB2_EINVAL, "batch stepping needs the Philox generator (replayed draws are per generation)");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   // arm the log for this batch (stream ordered: the previous batch has been read back by mb2_run_result)
   struct { long long count, cap; double* log; } arm = {0, max_steps, log_dev};
@@ -1241,8 +1263,9 @@ int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
 
 int mb2_run_result(mb2_ctx* c, int32_t* executed, int32_t* stopped, void* stream) {
   if (c == nullptr || c->run == nullptr || executed == nullptr || stopped == nullptr) return fail(MB2_EINVAL, "bad argument");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
+  if (c->xchg_connected) CUDA_TRY(cudaMemcpyAsync(c->h_xerr, c->xp.error, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(c->h_run, c->run, offsetof(RunState, hist0), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   const int done = (int)c->h_run->log_count;
@@ -1251,6 +1274,10 @@ int mb2_run_result(mb2_ctx* c, int32_t* executed, int32_t* stopped, void* stream
   // generations after the stop were no-ops: put the double buffer and the counter where the device is
   c->cur = c->run_cur0 ^ (done & 1);
   c->generation = c->run_gen0 + done;
+  // a sharded batch whose best exchange timed out: the shards' bests (and stop decisions) may differ across ranks
+  if ((c->xchg_connected && *c->h_xerr != 0) || c->h_run->stop == 3)
+    return fail(MB2_ECUDA, "best exchange: a peer did not deliver its record within %.1f s (batch stopped after %d generations)",
+                c->xp.timeout_ns * 1e-9, done);
   if (c->h_run->stop == 2) {  // log full without a termination: clear the flag for the next batch
     int zero = 0;
     CUDA_TRY(cudaMemcpy(&c->run->stop, &zero, sizeof(int), cudaMemcpyHostToDevice));
@@ -1260,7 +1287,7 @@ int mb2_run_result(mb2_ctx* c, int32_t* executed, int32_t* stopped, void* stream
 
 int mb2_pack_best(mb2_ctx* c, double* record, void* stream) {
   if (c == nullptr || record == nullptr) return fail(MB2_EINVAL, "NULL argument");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   pack_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c->st, c->best_x, c->dim, record);
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
@@ -1269,7 +1296,7 @@ int mb2_pack_best(mb2_ctx* c, double* record, void* stream) {
 
 int mb2_merge_best(mb2_ctx* c, const double* records, int32_t world, void* stream) {
   if (c == nullptr || records == nullptr || world < 1) return fail(MB2_EINVAL, "bad argument");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   merge_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(records, world, c->dim, c->best_x, c->st);
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
@@ -1285,7 +1312,7 @@ int mb2_set_islands(mb2_ctx* c, int32_t n_islands) {
   const int64_t inp = c->np / n_islands;
   if (n_islands > 1 && inp < c->sinfo.k + 1)
     return fail(MB2_EINVAL, "each population needs at least %d members for this strategy", c->sinfo.k + 1);
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   if (n_islands > 1 && (c->st_isl == nullptr || n_islands > c->n_islands)) {
     void* p = nullptr;
     if (int rc = dev_alloc(c, sizeof(DeviceState) * n_islands, &p)) return rc;
@@ -1309,7 +1336,7 @@ int mb2_set_islands(mb2_ctx* c, int32_t n_islands) {
 int mb2_read_islands(mb2_ctx* c, mb2_result* out, double* x_host, void* stream) {
   if (c == nullptr || out == nullptr) return fail(MB2_EINVAL, "NULL argument");
   if (c->n_islands < 2) return fail(MB2_ESTATE, "mb2_set_islands first");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   const size_t n = (size_t)c->n_islands;
   CUDA_TRY(cudaMemcpyAsync(c->h_st_isl, c->st_isl, sizeof(DeviceState) * n, cudaMemcpyDeviceToHost, s));
@@ -1333,7 +1360,7 @@ int mb2_exchange_open(mb2_ctx* c, int32_t world, int32_t rank, void* handle_out,
   if (handle_bytes < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail(MB2_EINVAL, "handle buffer too small");
   if (c->mailbox != nullptr) return fail(MB2_ESTATE, "exchange already opened");
   if (c->n_islands > 1) return fail(MB2_ESTATE, "batched solvers and sharded populations do not combine");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   const int stride = (c->dim + 4 + 1) & ~1;  // 16-byte slots
   memset(handle_out, 0, (size_t)handle_bytes);
   {
@@ -1371,7 +1398,10 @@ int mb2_exchange_open(mb2_ctx* c, int32_t world, int32_t rank, void* handle_out,
   c->xp.rank = rank;
   c->xp.stride = stride;
   c->xp.epoch = 0;
-  c->xp.timeout_ns = 5000000000ull;
+  {
+    const int ms = env_int("MB2_EXCHANGE_TIMEOUT_MS", 5000);  // tests shorten it
+    c->xp.timeout_ns = (unsigned long long)(ms > 0 ? ms : 5000) * 1000000ull;
+  }
   c->xp.box[rank] = c->mailbox;
   c->xp.error = reinterpret_cast<int*>(reinterpret_cast<char*>(c->mailbox) + bytes - sizeof(int) * 4);
   CUDA_TRY(cudaDeviceSynchronize());
@@ -1382,7 +1412,7 @@ int mb2_exchange_connected(mb2_ctx* c) { return (c != nullptr && c->xchg_connect
 
 int mb2_exchange_reset(mb2_ctx* c) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   if (c->mailbox != nullptr) {
     CUDA_TRY(cudaDeviceSynchronize());
     for (int r = 0; r < kMaxWorld; ++r) {
@@ -1403,7 +1433,7 @@ int mb2_exchange_connect(mb2_ctx* c, const void* handles, int32_t handle_bytes) 
   if (c->mailbox == nullptr) return fail(MB2_ESTATE, "mb2_exchange_open first");
   if (c->xchg_connected) return MB2_OK;
   if (handle_bytes < (int32_t)sizeof(cudaIpcMemHandle_t)) return fail(MB2_EINVAL, "handle stride too small");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   for (int r = 0; r < c->xp.world; ++r) {
     if (r == c->xp.rank) continue;
     cudaIpcMemHandle_t h;
@@ -1420,7 +1450,7 @@ int mb2_exchange_connect(mb2_ctx* c, const void* handles, int32_t handle_bytes) 
 int mb2_exchange_best(mb2_ctx* c, void* stream) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
   if (!c->xchg_connected) return fail(MB2_ESTATE, "mb2_exchange_connect first");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   exchange_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(c->dim, c->best_x, c->st, next_exchange(c));
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
@@ -1429,7 +1459,7 @@ int mb2_exchange_best(mb2_ctx* c, void* stream) {
 
 int mb2_read_result(mb2_ctx* c, mb2_result* out, double* x_host, void* stream) {
   if (c == nullptr || out == nullptr) return fail(MB2_EINVAL, "NULL argument");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
   if (c->xchg_connected) CUDA_TRY(cudaMemcpyAsync(c->h_xerr, c->xp.error, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, s));
@@ -1448,7 +1478,7 @@ int mb2_read_result(mb2_ctx* c, mb2_result* out, double* x_host, void* stream) {
 
 int mb2_eval_cost(mb2_ctx* c, const double* x, int64_t n, double* out, void* stream) {
   if (c == nullptr || x == nullptr || out == nullptr || n < 1) return fail(MB2_EINVAL, "bad argument");
-  CUDA_TRY(cudaSetDevice(c->device));
+  ENTER_DEVICE(c->device);
   const int64_t saved_gen = c->generation;
   const int saved_grid = c->grid;
   double* cap_t = c->cap_trial;

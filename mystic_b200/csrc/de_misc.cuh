@@ -30,9 +30,13 @@ __device__ __forceinline__ unsigned long long* exchange_flags(double* box, int w
   return reinterpret_cast<unsigned long long*>(box + (size_t)2 * world * stride);
 }
 
-__device__ __forceinline__ void exchange_best(const ExchangeParams& X, int D, double* __restrict__ best_x,
+// Returns false when a peer did not deliver within the timeout: *X.error is raised, the mailbox is NOT merged
+// (its records are stale) and this shard keeps its local best; the host fails the next read of the result.
+__device__ __forceinline__ bool exchange_best(const ExchangeParams& X, int D, double* __restrict__ best_x,
                                               DeviceState* __restrict__ st) {
   __shared__ int sh_w;
+  __shared__ int sh_late;
+  if (threadIdx.x == 0) sh_late = 0;
   const int par = (int)(X.epoch & 1ull);
   // ---- my record into slot `rank` of every mailbox
   for (int r = 0; r < X.world; ++r) {
@@ -60,12 +64,14 @@ __device__ __forceinline__ void exchange_best(const ExchangeParams& X, int D, do
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
       if (now - t0 > X.timeout_ns) {
         atomicExch(X.error, 1);
+        sh_late = 1;
         break;
       }
       __nanosleep(64);
     }
   }
   __syncthreads();
+  if (sh_late || *reinterpret_cast<volatile int*>(X.error) != 0) return false;  // an earlier exchange failed: ranks are out of step
   // ---- merge
   const double* recs = X.box[X.rank] + (size_t)par * X.world * X.stride;
   if (threadIdx.x == 0) {
@@ -96,6 +102,7 @@ __device__ __forceinline__ void exchange_best(const ExchangeParams& X, int D, do
     const volatile double* rec = recs + (size_t)w * X.stride;
     for (int i = threadIdx.x; i < D; i += blockDim.x) best_x[i] = rec[4 + i];
   }
+  return true;
 }
 
 // K3: reduce the per-CTA partials, update bestEnergy/bestSolution if the generation best beats
@@ -169,7 +176,11 @@ __device__ __forceinline__ void finalize_body(const double* __restrict__ part_e,
   }
   if (X.world > 1) {  // sharded population: install the global best on every shard
     __syncthreads();
-    exchange_best(X, D, best_x, st);
+    if (!exchange_best(X, D, best_x, st)) {
+      // batch mode: the remaining launches of the batch become no-ops; mb2_run_result reports the failure
+      if (rs != nullptr && threadIdx.x == 0) rs->stop = 3;
+      return;
+    }
   }
   if (rs == nullptr) return;
   __syncthreads();
@@ -336,7 +347,7 @@ __global__ void pack_best_kernel(const DeviceState* __restrict__ st, const doubl
 // exchange alone (after a restored state, or whenever the host asks for it)
 __global__ void __launch_bounds__(256)
     exchange_best_kernel(int D, double* __restrict__ best_x, DeviceState* __restrict__ st, const __grid_constant__ ExchangeParams X) {
-  exchange_best(X, D, best_x, st);
+  (void)exchange_best(X, D, best_x, st);
 }
 
 __global__ void merge_best_kernel(const double* __restrict__ recs, int world, int D, double* __restrict__ best_x,

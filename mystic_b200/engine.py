@@ -19,6 +19,18 @@ def _dptr(arr):
     return arr.ctypes.data_as(_native.c_double_p)
 
 
+def probe_fp64_peak(device=None, iters=20000):
+    """-> (DFMA TFLOP/s, DMMA m8n8k4 TFLOP/s) of `device`, measured now (mb2_probe_fp64_peak)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError('mystic_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback')
+    if device is None:
+        device = torch.cuda.current_device()
+    dfma, dmma = ctypes.c_double(0.0), ctypes.c_double(0.0)
+    check(lib.mb2_probe_fp64_peak(int(device), int(iters), ctypes.byref(dfma), ctypes.byref(dmma),
+                                  ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)))
+    return dfma.value, dmma.value
+
+
 class DeviceEngine(object):
     """Device-resident state of one shard: rows [offset, offset+np_local) of np_global."""
 

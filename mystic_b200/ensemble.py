@@ -161,11 +161,16 @@ class _EnsembleOfDE(object):
         for s in range(S):
             x0 = starts[s]
             rows = pop[s * NP:(s + 1) * NP]
-            for j in range(D):
-                a, b = x0[j] * (1 - radius), x0[j] * (1 + radius)
-                lo_, hi_ = (a, b) if a <= b else (b, a)
-                for i in range(NP):
-                    rows[i, j] = uniform(lo_, hi_)
+            # abstract_solver.py:499-502: a zero coordinate gets [-radius, +radius] (x0*(1 +- radius) would pin
+            # every member to 0 there and no difference vector could ever leave it), then :532-534
+            # random.uniform(min[j], max[j]) member by member
+            lo_ = x0 * (1 - radius)
+            hi_ = x0 * (1 + radius)
+            lo_[lo_ == 0] = -radius
+            hi_[hi_ == 0] = radius
+            for i in range(NP):
+                for j in range(D):
+                    rows[i, j] = uniform(lo_[j], hi_[j])
             rows[0] = x0
         eng = self._engine = self._make_engine(S * NP)
         mode = BOUNDS_NONE
@@ -185,7 +190,8 @@ class _EnsembleOfDE(object):
             self._seed = random.getrandbits(64)
         eng.set_rng_philox(self._seed)
         eng.upload_population(pop)
-        eng.set_islands(S)
+        if S > 1:
+            eng.set_islands(S)     # S == 1 (e.g. LatticeSolver(dim >= 4) with the default nbins): one plain population
 
         self._members = [_Member(self, s) for s in range(S)]
         active = list(range(S))
@@ -196,7 +202,11 @@ class _EnsembleOfDE(object):
                 eng.eval_initial()
             else:
                 eng.step()
-            be, bi, ninf, nacc, gen, bx = eng.read_islands()
+            if S > 1:
+                be, bi, ninf, nacc, gen, bx = eng.read_islands()
+            else:
+                r = eng.read_result()
+                be, bi, ninf, nacc, gen, bx = [r[0]], [r[1]], [r[2]], [r[3]], [r[4]], np.asarray(r[5]).reshape(1, D)
             still = []
             for s in active:
                 m = self._members[s]

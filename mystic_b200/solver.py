@@ -588,6 +588,13 @@ class DifferentialEvolutionSolver2(object):
     def _philox_seed(self):
         if self._seed is None:
             self._seed = random.getrandbits(64)
+            if self._distributed and self._world > 1:
+                # one key for all shards: the draws depend on the global candidate index only, whatever each
+                # rank's private stdlib generator holds (rank 0's draw wins)
+                import torch.distributed as dist
+                box = [self._seed]
+                dist.broadcast_object_list(box, src=0)
+                self._seed = int(box[0])
         return self._seed
 
     def _effective_bounds(self):
@@ -673,6 +680,10 @@ class DifferentialEvolutionSolver2(object):
         pop = pop_t.cpu().numpy()
         en = self._engine.energies()
         indx = int(np.argmin(en)) if len(en) else 0
+        if self._distributed and self._world > 1:
+            # the best member is the GLOBAL one of the last exchange; it lives in one shard only
+            gbest = self._last[2] if self._last else -1
+            indx = gbest - self._offset if self._offset <= gbest < self._offset + pop.shape[0] else -1
         for i in range(pop.shape[0]):
             clipped = pop[i].clip(lo, hi)
             if i == indx:

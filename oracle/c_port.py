@@ -60,7 +60,7 @@ class COracle(object):
              'branins': 16, 'easom': 17, 'goldstein': 18, 'peaks': 19, 'venkat91': 20, 'fosc3d': 21, 'nmin51': 22, 'shekel': 23,
              'ellipsoid': 24, 'paviani': 25}
 
-    def __init__(self, population, strategy, CR, F, cost, extra=(), lo=None, hi=None, bounds_mode=0, penalty=()):
+    def __init__(self, population, strategy, CR, F, cost, extra=(), lo=None, hi=None, bounds_mode=0, penalty=(), trials=True):
         from oracle import de_oracle as orc
         self.lib = load()
         self.pop = [np.ascontiguousarray(population, dtype=np.float64), None]
@@ -71,7 +71,7 @@ class COracle(object):
         self.best_x = np.zeros(self.D)
         self.best_e = ctypes.c_double(np.inf)
         self.best_idx = ctypes.c_int64(-1)
-        self.trial = np.zeros((self.NP, self.D))
+        self.trial = np.zeros((self.NP, self.D)) if trials else None   # full-size runs skip the NP x D capture
         self.trial_e = np.zeros(self.NP)
         self.n_inf = ctypes.c_int64(0)
         self.n_acc = ctypes.c_int64(0)
@@ -139,11 +139,11 @@ class COracle(object):
 
     def step0(self):
         c, n = self.cur, self.cur ^ 1
-        self.trial[:] = self.pop[c]
         self.lib.orc_step0(ctypes.byref(self.cfg), _d(self.pop[c]), _d(self.pop[n]), _d(self.en[n]), _d(self.best_x),
                            ctypes.byref(self.best_e), ctypes.byref(self.best_idx), _d(self.trial_e),
                            ctypes.byref(self.n_inf), ctypes.byref(self.n_acc))
-        self.trial[:] = self.pop[n]
+        if self.trial is not None:
+            self.trial[:] = self.pop[n]
         self._after()
 
     def step(self, replay=None, seed=0, offset=0, keep_trials=True):
@@ -163,7 +163,7 @@ class COracle(object):
                           _d(self.best_x), ctypes.byref(self.best_e), ctypes.byref(self.best_idx),
                           ctypes.c_int(mode), ctypes.c_uint64(seed & 0xFFFFFFFFFFFFFFFF),
                           ctypes.c_uint32(self.generation + 1), ctypes.c_int64(offset), dp, nsp, up,
-                          _d(self.trial) if keep_trials else None, _d(self.trial_e),
+                          _d(self.trial) if (keep_trials and self.trial is not None) else None, _d(self.trial_e),
                           ctypes.byref(self.n_inf), ctypes.byref(self.n_acc))
         self._after()
 
@@ -178,8 +178,11 @@ def init_population(seed, NP, lo, hi, offset=0):
     return pop
 
 
-def time_workload(w, NP, steps, warmup, seed=0x5EED):
-    """bench.py cpu_baseline / --impl reference: -> (cand-evals/s, s/step, kind, cores, sample)"""
+def time_workload(w, NP, steps, warmup, seed=0x5EED, threads=None):
+    """bench.py cpu_baseline / --impl reference: -> (cand-evals/s, s/step, kind, cores, sample).
+    `threads`: OpenMP threads to use (torchrun exports OMP_NUM_THREADS=1; the bench names the count itself)."""
+    if threads:
+        load().orc_set_num_threads(int(threads))
     D = w['dim']
     lo, hi = np.full(D, w['lo']), np.full(D, w['hi'])
     mode = {None: 0, 'reject': 1, 'clamp': 2}[w['bounds']]

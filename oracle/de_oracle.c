@@ -432,6 +432,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py's CPU legs set the thread count themselves: torchrun exports OMP_NUM_THREADS=1 */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 /* generation 0: clip into the strict range (differential_evolution.py:516-520), evaluate, select.
  * pop_next receives the (clipped) population, e_next its energies; trial_e_out [np] scratch/out. */
 int orc_step0(const orc_config* cfg, const double* pop_cur, double* pop_next, double* e_next, double* best_x,

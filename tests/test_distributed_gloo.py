@@ -106,3 +106,39 @@ def test_two_ranks_agree_and_match_single_process_emulation():
         assert hist == a['energy_history']
         assert evals == a['evals']
         assert np.array_equal(engs[0].population(), a['pop']) and np.array_equal(engs[1].population(), b['pop'])
+
+
+def _worker_unseeded(rank, world, port, out):
+    sys.path.insert(0, REPO)
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    import random
+    from mystic_b200 import DifferentialEvolutionSolver2, models, termination
+    from tests._oracle_engine import OracleEngine
+    random.seed(1000 + rank)        # every rank's private generator differs
+    s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=None, distributed=True, engine=OracleEngine, strategy='Best1Bin')
+    s.SetRandomInitialPoints([-3.] * D, [3.] * D)
+    s.SetStrictRanges([-3.] * D, [3.] * D, tight=True)
+    s.SetTermination(termination.VTR(-1.0))
+    s.SetEvaluationLimits(generations=10 ** 6)
+    s.Step(models.rosen)
+    for _ in range(3):
+        s.Step()
+    # mid-run SetStrictRanges re-decorates: the member kept (clipped) is the GLOBAL best, which one shard holds
+    gbest = s._last[2]
+    s.SetStrictRanges([-1.5] * D, [1.5] * D, tight=True)
+    before = s.population.copy()
+    s.Step()
+    out[rank] = dict(seed=s._seed, gbest=gbest, offset=s._offset, np_local=s._np_local, before=before,
+                     engine_seed=s._engine.seed)
+    dist.destroy_process_group()
+
+
+def test_unseeded_sharded_run_shares_one_key():
+    """with seed=None every rank drew its own Philox key; rank 0's is now broadcast"""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker_unseeded, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a['seed'] == b['seed'] == a['engine_seed'] == b['engine_seed'] and a['gbest'] == b['gbest'] >= 0

@@ -22,3 +22,16 @@ def test_peer_exchange_between_two_processes_on_one_gpu():
     assert proc.returncode == 0, proc.stdout[-3000:]
     assert 'multi-gpu parity ok (world 2)' in proc.stdout, proc.stdout[-3000:]
     assert proc.stdout.count('batched Solve == stepwise Solve: True') == 2, proc.stdout[-3000:]
+
+
+@pytest.mark.parametrize('mode', ['step', 'batch'])
+def test_a_silent_peer_fails_the_step_and_the_batched_solve(mode):
+    """the epilogue's wait times out, the stale mailbox is not merged, and both mb2_read_result (per-generation
+    path) and mb2_run_result (device-resident loop) report it"""
+    env = dict(os.environ, MB2_EXCHANGE='peer', MB2_EXCHANGE_TIMEOUT_MS='300')
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2', '--master-addr', '127.0.0.1',
+           '--master-port', '29573' if mode == 'step' else '29575', os.path.join(REPO, 'tests', 'dist_gpu_timeout.py'), mode]
+    proc = subprocess.run(cmd, cwd=REPO, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, universal_newlines=True,
+                          timeout=240)
+    assert proc.returncode == 0, proc.stdout[-3000:]
+    assert 'timeout detected' in proc.stdout and 'NO ERROR RAISED' not in proc.stdout, proc.stdout[-3000:]

@@ -76,3 +76,37 @@ def test_nested_class_takes_the_ensemble_settings_and_errors_are_raised():
         BuckshotSolver(2, 2, engine=OracleEngine).Solve(lambda x: sum(x))     # python costs cannot run on the device
     with pytest.raises(ValueError):
         s.SetInitialPoints([[1., 1.]])
+
+
+def test_zero_start_coordinates_are_spread_like_the_reference():
+    """abstract_solver.py:499-502: x0[j] == 0 -> members drawn from [-radius, +radius] in that coordinate (a lattice
+    over symmetric bounds with an odd number of bins has such centres; x0*(1 +- radius) would pin the coordinate)"""
+    random.seed(5)
+    ens = LatticeSolver(3, (2, 1, 1), engine=OracleEngine, seed=3)
+    ens.SetNestedSolver(DifferentialEvolutionSolver2(3, 20, strategy='Best1Exp'))
+    ens.SetStrictRanges([-2.] * 3, [2.] * 3)
+    ens.SetEvaluationLimits(generations=200)
+    ens.Solve(models.rosen, termination.VTR(1e-6))
+    pop0 = ens._engine._pop
+    for s in range(2):
+        rows = pop0[s * 20:(s + 1) * 20]
+        assert list(rows[0]) == list(ens._init_solution[s])               # member 0 is the start point itself
+        assert np.abs(rows[1:, 1:]).max() <= 0.05 and np.abs(rows[1:, 1:]).min() > 0.0
+        assert len(set(rows[1:, 1])) == 19                                 # not pinned to one value
+    assert ens.bestEnergy < 1e-6                                           # every coordinate was explored
+
+
+@pytest.mark.parametrize('make', [lambda: LatticeSolver(4, engine=OracleEngine, seed=1),
+                                  lambda: BuckshotSolver(4, 1, engine=OracleEngine, seed=1)])
+def test_an_ensemble_of_one_nested_solver_runs(make):
+    """LatticeSolver(dim >= 4) with the default nbins = 8 has one bin per dimension, i.e. ONE nested solver"""
+    random.seed(9)
+    ens = make()
+    assert ens._npts == 1
+    ens.SetNestedSolver(DifferentialEvolutionSolver2(4, 24, strategy='Best1Bin'))
+    ens.SetStrictRanges([-3.] * 4, [3.] * 4)
+    ens.SetEvaluationLimits(generations=25)
+    ens.Solve(models.rosen, termination.VTR(1e-9))
+    assert len(ens._all_iters) == 1 and 1 <= ens.generations <= 25
+    assert ens.bestEnergy == ens._all_bestEnergy[0] and len(ens.bestSolution) == 4
+    assert ens.Terminated(info=True)
