@@ -28,7 +28,9 @@
 extern "C" {
 #endif
 
-#define MB2_ABI_VERSION 1
+/* 2: draw protocol 2 of the Philox mode (csrc/philox.cuh): one geometric draw for the exponential crossover
+ * length, 16-bit fields for the binomial decisions.  Signatures are those of version 1. */
+#define MB2_ABI_VERSION 2
 
 /* error codes */
 #define MB2_OK 0

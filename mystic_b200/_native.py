@@ -94,7 +94,7 @@ def _load():
         fn = getattr(lib, name)  # AttributeError if the library does not export it
         fn.restype = res
         fn.argtypes = args
-    if lib.mb2_abi_version() != 1:
+    if lib.mb2_abi_version() != 2:
         raise ImportError('mystic_b200: ABI version mismatch in %s' % LIBPATH)
     return lib
 

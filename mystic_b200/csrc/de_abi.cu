@@ -97,6 +97,11 @@ struct mb2_ctx {
   int strategy = MB2_BEST1BIN;
   StrategyInfo sinfo = {BASE_BEST1, XOVER_BIN, 2};
   double F = 0.8, CR = 0.9;
+  // exponential crossover length table of the current CR (philox.cuh, protocol 2): T[1..nmax] on the device
+  uint32_t* xlen_tab = nullptr;
+  int xlen_nmax = -1;
+  float xlen_c = 0.f;
+  uint64_t xlen_thr = ~0ull;  // threshold the table was built for
   int bounds_mode = BOUNDS_NONE;
   int bounds_uniform = 0;
   // every row of the current population lies inside [lo, hi]: generation 0 clipped it with these
@@ -217,6 +222,31 @@ int host_alloc(mb2_ctx* c, size_t bytes, void** out) {
   }
   CUDA_TRY(cudaMallocHost(out, need));
   c->owned_host.push_back(*out);
+  return MB2_OK;
+}
+
+// exponential crossover: the length table of the geometric draw for CrossProbability `cross`
+// (philox.cuh, protocol 2), rebuilt when the probability changes
+int ensure_exp_length_table(mb2_ctx* c, double cross) {
+  const uint64_t thr = crossover_threshold(cross);
+  if (thr == c->xlen_thr) return MB2_OK;
+  ENTER_DEVICE(c->device);
+  std::vector<uint32_t> tab((size_t)c->dim);
+  const int nmax = build_exp_length_table(thr, c->dim, tab.data());
+  if (c->xlen_tab == nullptr) {
+    void* p = nullptr;
+    if (int rc = dev_alloc(c, sizeof(uint32_t) * (size_t)c->dim, &p)) return rc;
+    c->xlen_tab = (uint32_t*)p;
+  }
+  if (nmax > 0) {
+    if (c->generation >= 0) CUDA_TRY(cudaDeviceSynchronize());  // kernels in flight may still read the old table
+    CUDA_TRY(cudaMemcpy(c->xlen_tab, tab.data(), sizeof(uint32_t) * (size_t)nmax, cudaMemcpyHostToDevice));
+  }
+  c->xlen_nmax = nmax;
+  // first guess of the length: log2(2^32 / w) / -log2(CR), CR as the kernels see it (thr / 2^32)
+  const double l2 = (thr > 0) ? -std::log2((double)thr / 4294967296.0) : INFINITY;
+  c->xlen_c = (thr > 0 && l2 > 0.0) ? (float)(1.0 / l2) : 0.f;
+  c->xlen_thr = thr;
   return MB2_OK;
 }
 
@@ -669,7 +699,8 @@ void fill_params(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, 
   P.key0 = (uint32_t)(c->seed & 0xffffffffu);
   P.key1 = (uint32_t)(c->seed >> 32);
   P.generation = (uint32_t)(c->generation + 1);
-  P.thr = crossover_threshold(c->CR);
+  P.thr16 = crossover_threshold16(c->CR);
+  P.xlen = {c->xlen_tab, c->xlen_nmax, c->xlen_c};
   P.r_donors = c->r_donors;
   P.r_nstart = c->r_nstart;
   P.r_uni = c->r_uni;
@@ -718,7 +749,7 @@ const char* mb2_last_error(void) { return g_err; }
 int64_t mb2_workspace_bytes(int32_t dim, int64_t* host_bytes) {
   if (host_bytes) *host_bytes = 4096 + (int64_t)sizeof(double) * dim;
   // state, best, bounds (x4 rows), partials for 148*32 CTAs, tables for the common costs
-  return 262144 + 64 * (int64_t)dim;
+  return 262144 + 72 * (int64_t)dim;
 }
 
 int mb2_create_ws(int device, int64_t np_local, int32_t dim, int64_t np_global, int64_t global_offset,
@@ -767,6 +798,7 @@ int mb2_create_ws(int device, int64_t np_local, int32_t dim, int64_t np_global, 
   if (!rc) rc = host_alloc(c, sizeof(DeviceState), &p), c->h_st = (DeviceState*)p;
   if (!rc) rc = host_alloc(c, sizeof(double) * dim, &p), c->h_best_x = (double*)p;
   if (!rc) rc = ensure_parts(c, 1);
+  if (!rc) rc = ensure_exp_length_table(c, c->CR);
   if (!rc) {
     DeviceState init = {INFINITY, -1, 0, 0, -1};
     if (cudaMemcpy(c->st, &init, sizeof(init), cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -841,6 +873,7 @@ int mb2_set_strategy(mb2_ctx* c, int strategy, double scale, double cross) {
   if (c->np < s.k + 1)
     return fail(MB2_EINVAL, "strategy needs %d distinct donors but the shard has only %lld other members", s.k,
                 (long long)(c->np - 1));
+  if (int rc = ensure_exp_length_table(c, cross)) return rc;
   c->strategy = strategy;
   c->sinfo = s;
   c->F = scale;

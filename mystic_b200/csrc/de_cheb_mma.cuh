@@ -104,15 +104,16 @@ __global__ void __launch_bounds__(kChebWarps * 32, MB2_CHEB_MINBLOCKS)
         int64_t r[5] = {0, 0, 0, 0, 0};
         int nstart;
         const uint32_t cand_g = (uint32_t)(P.global_offset + c);
+        uint32_t xword = 0;  // low half of the start-index word: the geometric draw of the crossover length
         if (P.replay) {
           for (int j = 0; j < ndonors; ++j) r[j] = __ldg(P.r_donors + c * 5 + j);
           nstart = __ldg(P.r_nstart + c);
         } else {
           switch (ndonors) {
-            case 2: draw_donors<2>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
-            case 3: draw_donors<3>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
-            case 4: draw_donors<4>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
-            default: draw_donors<5>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart); break;
+            case 2: draw_donors<2>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart, &xword); break;
+            case 3: draw_donors<3>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart, &xword); break;
+            case 4: draw_donors<4>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart, &xword); break;
+            default: draw_donors<5>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart, &xword); break;
           }
         }
         // crossover decisions as a bit mask over the D <= 17 dimensions
@@ -125,14 +126,13 @@ __global__ void __launch_bounds__(kChebWarps * 32, MB2_CHEB_MINBLOCKS)
             if (P.replay) {
               hit = __ldg(u + i) < P.CR;
             } else {
-              if ((i & 3) == 0) w = philox4x32_10((uint32_t)(i >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-              const uint32_t word = (i & 3) == 0 ? w.x : ((i & 3) == 1 ? w.y : ((i & 3) == 2 ? w.z : w.w));
-              hit = (uint64_t)word < P.thr;
+              if ((i & 7) == 0) w = philox4x32_10((uint32_t)(i >> 3), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+              hit = xover_field(w, i & 7) < P.thr16;
             }
             if (hit || i == nstart) cmask |= 1u << i;
           }
         } else {
-          const int L = exp_length_thread(P, cand_g, c, D);
+          const int L = exp_length_thread(P, xword, c, D);
           for (int j = 0; j < L; ++j) {
             int i = nstart + j;
             if (i >= D) i -= D;

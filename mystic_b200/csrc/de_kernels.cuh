@@ -67,7 +67,8 @@ struct StepParams {
   // RNG
   int replay;  // 1: consume recorded draws
   uint32_t key0, key1, generation;
-  uint64_t thr;  // crossover threshold on 32-bit words
+  uint32_t thr16;  // binomial crossover: threshold on the 16-bit fields of stream 1 (philox.cuh, protocol 2)
+  ExpLength xlen;  // exponential crossover: length table of the geometric draw
   const int32_t* r_donors;  // [np,5]
   const int32_t* r_nstart;  // [np]
   const double* r_uni;      // [np, dim+1]
@@ -112,49 +113,16 @@ __device__ __forceinline__ int exp_length_replay(const double* __restrict__ uni,
   return D;
 }
 
-// Same length computed by ONE thread for its own candidate (thread- and group-per-row kernels):
-// a whole Philox block (4 words) per iteration, no per-word branches.
-__device__ __forceinline__ int exp_length_thread(const StepParams& P, uint32_t cand, int64_t c, int D) {
-  int L = 0;
+// Same length for ONE thread's own candidate (thread- and group-per-row kernels).  Philox mode: the
+// geometric draw from `xword`, the low half of the start-index word (philox.cuh, protocol 2).
+__device__ __forceinline__ int exp_length_thread(const StepParams& P, uint32_t xword, int64_t c, int D) {
   if (P.replay) {
+    int L = 0;
     const double* u = P.r_uni + c * (int64_t)(D + 1);
     while (L < D && (__ldg(u + L) < P.CR)) ++L;  // NaN (not drawn) -> stop
     return L;
   }
-  for (int b = 0; L < D; ++b) {
-    const u32x4 w = philox4x32_10((uint32_t)b, cand, P.generation, STREAM_XOVER, P.key0, P.key1);
-    const unsigned ok = ((uint64_t)w.x < P.thr ? 1u : 0u) | ((uint64_t)w.y < P.thr ? 2u : 0u) |
-                        ((uint64_t)w.z < P.thr ? 4u : 0u) | ((uint64_t)w.w < P.thr ? 8u : 0u);
-    const int run = __ffs(~ok) - 1;  // leading successes in this block (4 when ok == 0xF)
-    L += run;
-    if (run < 4) break;
-  }
-  return L < D ? L : D;
-}
-
-__device__ __forceinline__ int exp_length_philox(uint32_t k0, uint32_t k1, uint32_t gen, uint32_t cand, int D,
-                                                 uint64_t thr, int lane) {
-  for (int base = 0; base < D; base += 128) {
-    const int i0 = base + 4 * lane;
-    int first = 4;  // first failing word of this lane's block
-    if (i0 < D) {
-      const u32x4 w = philox4x32_10((uint32_t)(i0 >> 2), cand, gen, STREAM_XOVER, k0, k1);
-      if (!((uint64_t)w.w < thr)) first = 3;
-      if (!((uint64_t)w.z < thr)) first = 2;
-      if (!((uint64_t)w.y < thr)) first = 1;
-      if (!((uint64_t)w.x < thr)) first = 0;
-    } else {
-      first = 0;
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, first < 4);
-    if (m) {
-      const int src = __ffs(m) - 1;
-      const int f = __shfl_sync(0xffffffffu, first, src);
-      const int L = base + 4 * src + f;
-      return L < D ? L : D;
-    }
-  }
-  return D;
+  return exp_length_v2(xword, P.xlen, D);
 }
 
 template <int BASE, int XOVER, int COST, bool VEC>
@@ -193,18 +161,18 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
       // ---- random draws for this candidate
       int64_t r[5] = {0, 0, 0, 0, 0};
       int nstart;
+      uint32_t xword = 0;
       const uint32_t cand_g = (uint32_t)(P.global_offset + c);
       if (P.replay) {
 #pragma unroll
         for (int j = 0; j < K; ++j) r[j] = __ldg(P.r_donors + c * 5 + j);
         nstart = __ldg(P.r_nstart + c);
       } else {
-        draw_donors<K>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart);
+        draw_donors<K>(P.key0, P.key1, P.generation, cand_g, c, P.np, D, r, &nstart, &xword);
       }
       int L = 0;
       if (XOVER == XOVER_EXP) {
-        L = P.replay ? exp_length_replay(P.r_uni + c * (int64_t)(D + 1), D, P.CR, lane)
-                     : exp_length_philox(P.key0, P.key1, P.generation, cand_g, D, P.thr, lane);
+        L = P.replay ? exp_length_replay(P.r_uni + c * (int64_t)(D + 1), D, P.CR, lane) : exp_length_v2(xword, P.xlen, D);
       }
       const double* __restrict__ d0 = P.pop_cur + r[0] * D;
       const double* __restrict__ d1 = P.pop_cur + r[1] * D;
@@ -224,11 +192,13 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
 #pragma unroll
             for (int e = 0; e < 4; ++e) cross[e] = (i0 + e < D) && ((i0 + e == nstart) || (__ldg(u + e) < P.CR));
           } else {
-            const u32x4 w = philox4x32_10((uint32_t)(i0 >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-            cross[0] = (i0 == nstart) || ((uint64_t)w.x < P.thr);
-            cross[1] = (i0 + 1 < D) && ((i0 + 1 == nstart) || ((uint64_t)w.y < P.thr));
-            cross[2] = (i0 + 2 < D) && ((i0 + 2 == nstart) || ((uint64_t)w.z < P.thr));
-            cross[3] = (i0 + 3 < D) && ((i0 + 3 == nstart) || ((uint64_t)w.w < P.thr));
+            // block i0/8 decides dimensions 8q..8q+7; this lane's four are its low or high pair of words
+            const u32x4 w = philox4x32_10((uint32_t)(i0 >> 3), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+            const uint32_t wa = (i0 & 4) ? w.z : w.x, wb = (i0 & 4) ? w.w : w.y;
+            cross[0] = (i0 == nstart) || field_lo_hit(wa, P.thr16);
+            cross[1] = (i0 + 1 < D) && ((i0 + 1 == nstart) || field_hi_hit(wa, P.thr16));
+            cross[2] = (i0 + 2 < D) && ((i0 + 2 == nstart) || field_lo_hit(wb, P.thr16));
+            cross[3] = (i0 + 3 < D) && ((i0 + 3 == nstart) || field_hi_hit(wb, P.thr16));
           }
         } else {
 #pragma unroll

@@ -167,16 +167,6 @@ __device__ __forceinline__ double rows_penalty(const double* xs, int D, int NQ, 
   return total;
 }
 
-// index of the first word of a crossover block that is not a success (4: all four succeed)
-__device__ __forceinline__ int first_failure(const u32x4& w, uint64_t thr) {
-  int first = 4;
-  if (!((uint64_t)w.w < thr)) first = 3;
-  if (!((uint64_t)w.z < thr)) first = 2;
-  if (!((uint64_t)w.y < thr)) first = 1;
-  if (!((uint64_t)w.x < thr)) first = 0;
-  return first;
-}
-
 // the draws of one candidate (strategy.py:27,42,48-56)
 template <int K>
 struct RowDraws {
@@ -188,7 +178,6 @@ struct RowDraws {
 // Warp-collective: every lane of the warp calls it for the row of its group.
 template <int LPR, int K>
 __device__ __forceinline__ void rows_draw(const StepParams& P, int xover, int64_t cc, int sub, int gbase, RowDraws<K>& d) {
-  constexpr unsigned LMASK = (1u << LPR) - 1u;
   constexpr int NB = (K + 2) / 2;  // Philox blocks of the donor stream (K donors + start index)
   const int D = P.dim;
   const uint32_t cand_g = (uint32_t)(P.global_offset + cc);
@@ -198,12 +187,13 @@ __device__ __forceinline__ void rows_draw(const StepParams& P, int xover, int64_
 #pragma unroll
     for (int j = 0; j < K; ++j) d.r[j] = __ldg(P.r_donors + cc * 5 + j);
     d.nstart = __ldg(P.r_nstart + cc);
-    if (xover == XOVER_EXP) d.L = exp_length_thread(P, cand_g, cc, D);
+    if (xover == XOVER_EXP) d.L = exp_length_thread(P, 0u, cc, D);
     return;
   }
-  const bool donor_lane = sub < NB;
-  u32x4 v = philox4x32_10((uint32_t)(donor_lane ? sub : sub - NB), cand_g, P.generation,
-                          donor_lane ? STREAM_DONORS : STREAM_XOVER, P.key0, P.key1);
+  // lane `sub` of the row's group evaluates block `sub` of the donor stream (NB <= 3 <= LPR blocks: donors,
+  // start index and -- in its low half -- the geometric draw of the crossover length); ONE Philox evaluation
+  // per lane makes all the draws of the row
+  u32x4 v = philox4x32_10((uint32_t)(sub < NB ? sub : 0), cand_g, P.generation, STREAM_DONORS, P.key0, P.key1);
   const uint64_t even = ((uint64_t)v.x << 32) | v.y, odd = ((uint64_t)v.z << 32) | v.w;
   uint64_t rw[2 * NB];
 #pragma unroll
@@ -212,39 +202,11 @@ __device__ __forceinline__ void rows_draw(const StepParams& P, int xover, int64_
     rw[2 * b + 1] = __shfl_sync(0xffffffffu, odd, gbase + b);
   }
   int64_t r64[K];
-  resolve_donors<K>(rw, cc, P.np, D, r64, &d.nstart);
+  uint32_t xword;
+  resolve_donors<K>(rw, cc, P.np, D, r64, &d.nstart, &xword);
 #pragma unroll
   for (int j = 0; j < K; ++j) d.r[j] = (int)r64[j];
-  if (xover == XOVER_EXP) {
-    // L = number of leading successes, at most D
-    int first = donor_lane ? 4 : first_failure(v, P.thr);
-    int done = LPR - NB;  // crossover blocks examined so far
-    int L = 0;
-    bool resolved = false;
-    {
-      const unsigned seg = (__ballot_sync(0xffffffffu, first < 4) >> gbase) & LMASK;
-      const int src = seg ? (__ffs(seg) - 1) : sub;
-      const int f = __shfl_sync(0xffffffffu, first, gbase + src);
-      if (seg) {
-        L = 4 * (src - NB) + f;
-        resolved = true;
-      }
-    }
-    while (__any_sync(0xffffffffu, !resolved && 4 * done < D)) {
-      v = philox4x32_10((uint32_t)(done + sub), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-      first = first_failure(v, P.thr);
-      const unsigned seg = (__ballot_sync(0xffffffffu, first < 4) >> gbase) & LMASK;
-      const int src = seg ? (__ffs(seg) - 1) : sub;
-      const int f = __shfl_sync(0xffffffffu, first, gbase + src);
-      if (!resolved && seg) {
-        L = 4 * (done + src) + f;
-        resolved = true;
-      }
-      done += LPR;
-    }
-    if (!resolved || L > D) L = D;
-    d.L = L;
-  }
+  if (xover == XOVER_EXP) d.L = exp_length_v2(xword, P.xlen, D);
 }
 
 // the K donor segments of one 4-element chunk
@@ -279,11 +241,13 @@ __device__ __forceinline__ bool rows_mutate_chunk(const StepParams& P, int base,
 #pragma unroll
       for (int e = 0; e < 4; ++e) cross[e] = (i0 + e == d.nstart) || (__ldg(u + e) < P.CR);
     } else {
-      const u32x4 wv = philox4x32_10((uint32_t)q, (uint32_t)(P.global_offset + cc), P.generation, STREAM_XOVER, P.key0, P.key1);
-      cross[0] = (i0 == d.nstart) || ((uint64_t)wv.x < P.thr);
-      cross[1] = (i0 + 1 == d.nstart) || ((uint64_t)wv.y < P.thr);
-      cross[2] = (i0 + 2 == d.nstart) || ((uint64_t)wv.z < P.thr);
-      cross[3] = (i0 + 3 == d.nstart) || ((uint64_t)wv.w < P.thr);
+      // block q/2 decides the 8 dimensions of chunks 2*(q/2) and 2*(q/2)+1: the even chunk reads words x, y
+      const u32x4 wv = philox4x32_10((uint32_t)(q >> 1), (uint32_t)(P.global_offset + cc), P.generation, STREAM_XOVER, P.key0, P.key1);
+      const uint32_t wa = (q & 1) ? wv.z : wv.x, wb = (q & 1) ? wv.w : wv.y;
+      cross[0] = (i0 == d.nstart) || field_lo_hit(wa, P.thr16);
+      cross[1] = (i0 + 1 == d.nstart) || field_hi_hit(wa, P.thr16);
+      cross[2] = (i0 + 2 == d.nstart) || field_lo_hit(wb, P.thr16);
+      cross[3] = (i0 + 3 == d.nstart) || field_hi_hit(wb, P.thr16);
     }
   } else {
     int rel = i0 - d.nstart;

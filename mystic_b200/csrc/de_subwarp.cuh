@@ -176,20 +176,20 @@ __device__ __forceinline__ void subwarp_body(const StepParams& P, int base, int 
       int64_t r[5] = {0, 0, 0, 0, 0};
       int nstart;
       const uint32_t cand_g = (uint32_t)(P.global_offset + cc);
+      uint32_t xword = 0;  // low half of the start-index word: the geometric draw of the crossover length
       if (P.replay) {
         for (int j = 0; j < ndonors; ++j) r[j] = __ldg(P.r_donors + cc * 5 + j);
         nstart = __ldg(P.r_nstart + cc);
       } else {
         switch (ndonors) {
-          case 2: draw_donors<2>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
-          case 3: draw_donors<3>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
-          case 4: draw_donors<4>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
-          default: draw_donors<5>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart); break;
+          case 2: draw_donors<2>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart, &xword); break;
+          case 3: draw_donors<3>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart, &xword); break;
+          case 4: draw_donors<4>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart, &xword); break;
+          default: draw_donors<5>(P.key0, P.key1, P.generation, cand_g, cc, P.np, D, r, &nstart, &xword); break;
         }
       }
-      // exponential crossover length (strategy.py:48-56): every lane of the group scans the same
-      // Philox blocks (D <= 128: at most 32, on average 1/(4(1-CR)))
-      const int L = (xover == XOVER_EXP) ? exp_length_thread(P, cand_g, cc, D) : 0;
+      // exponential crossover length (strategy.py:48-56): one geometric draw (philox.cuh, protocol 2)
+      const int L = (xover == XOVER_EXP) ? exp_length_thread(P, xword, cc, D) : 0;
       const double* __restrict__ d0 = P.pop_cur + r[0] * D;
       const double* __restrict__ d1 = P.pop_cur + r[1] * D;
       const double* __restrict__ d2 = P.pop_cur + r[2] * D;
@@ -206,11 +206,12 @@ __device__ __forceinline__ void subwarp_body(const StepParams& P, int base, int 
 #pragma unroll
             for (int e = 0; e < 4; ++e) cross[e] = (i0 + e < D) && ((i0 + e == nstart) || (__ldg(u + e) < P.CR));
           } else {
-            const u32x4 w = philox4x32_10((uint32_t)(i0 >> 2), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-            cross[0] = (i0 == nstart) || ((uint64_t)w.x < P.thr);
-            cross[1] = (i0 + 1 < D) && ((i0 + 1 == nstart) || ((uint64_t)w.y < P.thr));
-            cross[2] = (i0 + 2 < D) && ((i0 + 2 == nstart) || ((uint64_t)w.z < P.thr));
-            cross[3] = (i0 + 3 < D) && ((i0 + 3 == nstart) || ((uint64_t)w.w < P.thr));
+            const u32x4 w = philox4x32_10((uint32_t)(i0 >> 3), cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+            const uint32_t wa = (i0 & 4) ? w.z : w.x, wb = (i0 & 4) ? w.w : w.y;
+            cross[0] = (i0 == nstart) || field_lo_hit(wa, P.thr16);
+            cross[1] = (i0 + 1 < D) && ((i0 + 1 == nstart) || field_hi_hit(wa, P.thr16));
+            cross[2] = (i0 + 2 < D) && ((i0 + 2 == nstart) || field_lo_hit(wb, P.thr16));
+            cross[3] = (i0 + 3 < D) && ((i0 + 3 == nstart) || field_hi_hit(wb, P.thr16));
           }
         } else {
 #pragma unroll

@@ -180,66 +180,77 @@ __global__ void __launch_bounds__(MAXT, 1)
     group_wait_stage(grp, bars + s, parity);
     const int nstart = s_nstart[group * kTmaMaxStages + s];
 
-    // ---- trial vector (strategy.py:77-85), two conflict-free double2 chunks per thread per trip:
-    //      chunk pA = base + tig and pB = pA + gthreads.  Crossover words: Philox block q covers
-    //      dims 4q..4q+3, i.e. chunks 2q and 2q+1, so the thread pair (2m, 2m+1) shares blocks qA and
-    //      qB; the even thread computes qA, the odd thread qB, and they swap halves by shuffle.
+    // ---- trial vector (strategy.py:77-85), four conflict-free double2 chunks per thread per trip: chunk
+    //      p_j = base + j*gthreads + tig, j = 0..3.  Crossover decisions (philox.cuh, protocol 2): Philox block q
+    //      holds eight 16-bit fields = dims 8q..8q+7 = chunks 4q..4q+3, i.e. word t of block q decides chunk 4q+t.
+    //      The four threads of a quad (4m..4m+3) own, for every j, the four chunks of ONE block q_j; thread t
+    //      evaluates block q_t and the quad transposes the 4x4 words by three xor-shuffles, so one Philox
+    //      evaluation per thread covers its eight dimensions and no evaluation is duplicated.
     bool oob = false;
+    const int tq = tig & 3;
+    const bool tq0 = (tq & 1) != 0, tq1 = (tq & 2) != 0;
     auto trip = [&](int base, auto guard) {
       constexpr bool GUARD = decltype(guard)::value;
-        const int pA = base + tig, pB = base + gthreads + tig;
-        bool cx[4];  // crossover decisions for dims 2pA, 2pA+1, 2pB, 2pB+1
-        if (P.replay) {
-          const double* u = P.r_uni + c * (int64_t)(D + 1);
-          cx[0] = (!GUARD || pA < npairs) && ((2 * pA == nstart) || (__ldg(u + 2 * pA) < P.CR));
-          cx[1] = (!GUARD || pA < npairs) && ((2 * pA + 1 == nstart) || (__ldg(u + 2 * pA + 1) < P.CR));
-          cx[2] = (!GUARD || pB < npairs) && ((2 * pB == nstart) || (__ldg(u + 2 * pB) < P.CR));
-          cx[3] = (!GUARD || pB < npairs) && ((2 * pB + 1 == nstart) || (__ldg(u + 2 * pB + 1) < P.CR));
-        } else {
-          const int q = ((tig & 1) ? pB : pA) >> 1;  // even thread: qA, odd thread: qB
-          const u32x4 w = philox4x32_10((uint32_t)q, cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
-          // even thread keeps (x,y) of qA for pA and needs (x,y) of qB from its odd neighbour;
-          // odd thread keeps (z,w) of qB for pB and needs (z,w) of qA from its even neighbour.
-          const uint32_t send0 = (tig & 1) ? w.x : w.z;
-          const uint32_t send1 = (tig & 1) ? w.y : w.w;
-          const uint32_t got0 = __shfl_xor_sync(0xffffffffu, send0, 1);
-          const uint32_t got1 = __shfl_xor_sync(0xffffffffu, send1, 1);
-          const uint32_t a0 = (tig & 1) ? got0 : w.x, a1 = (tig & 1) ? got1 : w.y;  // words for chunk pA
-          const uint32_t b0 = (tig & 1) ? w.z : got0, b1 = (tig & 1) ? w.w : got1;  // words for chunk pB
-          cx[0] = (!GUARD || pA < npairs) && ((2 * pA == nstart) || ((uint64_t)a0 < P.thr));
-          cx[1] = (!GUARD || pA < npairs) && ((2 * pA + 1 == nstart) || ((uint64_t)a1 < P.thr));
-          cx[2] = (!GUARD || pB < npairs) && ((2 * pB == nstart) || ((uint64_t)b0 < P.thr));
-          cx[3] = (!GUARD || pB < npairs) && ((2 * pB + 1 == nstart) || ((uint64_t)b1 < P.thr));
-        }
+      bool cx[8];  // crossover decisions of dims 2p_j, 2p_j+1, j = 0..3
+      if (P.replay) {
+        const double* u = P.r_uni + c * (int64_t)(D + 1);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int p = h ? pB : pA;
-          if (!GUARD || p < npairs) {
-            double2 x = s_par[p];
-            const double2 a = s_d0[p], b = s_d1[p], bs = s_b2[p];
-            if (cx[2 * h]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
-            if (cx[2 * h + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
-            if (P.bounds_mode != BOUNDS_NONE) {
-              const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p + 1);
-              const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p + 1);
-              if (P.bounds_mode == BOUNDS_CLAMP) {
-                x.x = (x.x > l0) ? x.x : l0;
-                x.x = (x.x < h0) ? x.x : h0;
-                x.y = (x.y > l1) ? x.y : l1;
-                x.y = (x.y < h1) ? x.y : h1;
-              } else {
-                oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);  // nothing is out of range after a clamp
-              }
-            }
-            s_d0[p] = x;
-          }
+        for (int j = 0; j < 4; ++j) {
+          const int p = base + j * gthreads + tig;
+          cx[2 * j] = (!GUARD || p < npairs) && ((2 * p == nstart) || (__ldg(u + 2 * p) < P.CR));
+          cx[2 * j + 1] = (!GUARD || p < npairs) && ((2 * p + 1 == nstart) || (__ldg(u + 2 * p + 1) < P.CR));
         }
+      } else {
+        const int q = ((base + tq * gthreads + tig) >> 2);
+        const u32x4 w = philox4x32_10((uint32_t)q, cand_g, P.generation, STREAM_XOVER, P.key0, P.key1);
+        // 4x4 transpose over the quad: in round k thread t hands partner t^k the word of the partner's chunk
+        // (word t^k of its block) and receives word t of the partner's block
+        const uint32_t w01 = tq0 ? w.y : w.x, w23 = tq0 ? w.w : w.z;   // words (t&1), 2+(t&1)
+        const uint32_t x01 = tq0 ? w.x : w.y, x23 = tq0 ? w.z : w.w;   // words (t&1)^1, 2+((t&1)^1)
+        uint32_t recv[4];
+        recv[0] = tq1 ? w23 : w01;                                                // word t
+        recv[1] = __shfl_xor_sync(0xffffffffu, tq1 ? x23 : x01, 1);              // send word t^1
+        recv[2] = __shfl_xor_sync(0xffffffffu, tq1 ? w01 : w23, 2);              // send word t^2
+        recv[3] = __shfl_xor_sync(0xffffffffu, tq1 ? x01 : x23, 3);              // send word t^3
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // block q_j was evaluated by quad member j = partner t^(j^t): the word is recv[j ^ t]
+          const bool b0 = ((j & 1) != 0) != tq0, b1 = ((j & 2) != 0) != tq1;
+          const uint32_t lo = b0 ? recv[1] : recv[0], hi = b0 ? recv[3] : recv[2];
+          const uint32_t word = b1 ? hi : lo;
+          const int p = base + j * gthreads + tig;
+          cx[2 * j] = (!GUARD || p < npairs) && ((2 * p == nstart) || field_lo_hit(word, P.thr16));
+          cx[2 * j + 1] = (!GUARD || p < npairs) && ((2 * p + 1 == nstart) || field_hi_hit(word, P.thr16));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int p = base + j * gthreads + tig;
+        if (!GUARD || p < npairs) {
+          double2 x = s_par[p];
+          const double2 a = s_d0[p], b = s_d1[p], bs = s_b2[p];
+          if (cx[2 * j]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
+          if (cx[2 * j + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
+          if (P.bounds_mode != BOUNDS_NONE) {
+            const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p + 1);
+            const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p + 1);
+            if (P.bounds_mode == BOUNDS_CLAMP) {
+              x.x = (x.x > l0) ? x.x : l0;
+              x.x = (x.x < h0) ? x.x : h0;
+              x.y = (x.y > l1) ? x.y : l1;
+              x.y = (x.y < h1) ? x.y : h1;
+            } else {
+              oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);  // nothing is out of range after a clamp
+            }
+          }
+          s_d0[p] = x;
+        }
+      }
     };
-    if (npairs % (2 * gthreads) == 0) {  // whole trips only: no per-chunk guards
-#pragma unroll 2
-      for (int base = 0; base < npairs; base += 2 * gthreads) trip(base, std::false_type());
+    if (npairs % (4 * gthreads) == 0) {  // whole trips only: no per-chunk guards
+      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type());
     } else {
-      for (int base = 0; base < npairs; base += 2 * gthreads) trip(base, std::true_type());
+      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::true_type());
     }
     oob = group_any(grp, oob);  // also the barrier that publishes the trial vector to the group
 

@@ -43,7 +43,7 @@ __device__ __forceinline__ double mutant_rt(int base, double t, double b, const 
 // donors + start index for a run-time donor count; collective over the calling warp, same
 // results as draw_donors<K>
 __device__ __forceinline__ void draw_donors_warp_rt(const StepParams& P, int kdon, int64_t c, int lane, int64_t (&r)[5],
-                                                    int* nstart) {
+                                                    int* nstart, uint32_t* xword) {
   if (P.replay) {
 #pragma unroll
     for (int j = 0; j < 5; ++j) r[j] = (j < kdon) ? (int64_t)__ldg(P.r_donors + c * 5 + j) : 0;
@@ -61,10 +61,10 @@ __device__ __forceinline__ void draw_donors_warp_rt(const StepParams& P, int kdo
 #pragma unroll
   for (int j = 0; j < 5; ++j) r[j] = 0;
   switch (kdon) {
-    case 2: resolve_donors<2>(w, c, P.np, P.dim, r, nstart); break;
-    case 3: resolve_donors<3>(w, c, P.np, P.dim, r, nstart); break;
-    case 4: resolve_donors<4>(w, c, P.np, P.dim, r, nstart); break;
-    default: resolve_donors<5>(w, c, P.np, P.dim, r, nstart); break;
+    case 2: resolve_donors<2>(w, c, P.np, P.dim, r, nstart, xword); break;
+    case 3: resolve_donors<3>(w, c, P.np, P.dim, r, nstart, xword); break;
+    case 4: resolve_donors<4>(w, c, P.np, P.dim, r, nstart, xword); break;
+    default: resolve_donors<5>(w, c, P.np, P.dim, r, nstart, xword); break;
   }
 }
 
@@ -131,9 +131,9 @@ __global__ void __launch_bounds__(MAXT, 1)
     }
     int64_t r[5];
     int nstart;
-    draw_donors_warp_rt(P, kdon, c, lane, r, &nstart);
-    const int L = P.replay ? exp_length_replay(P.r_uni + c * (int64_t)(D + 1), D, P.CR, lane)
-                           : exp_length_philox(P.key0, P.key1, P.generation, (uint32_t)(P.global_offset + c), D, P.thr, lane);
+    uint32_t xword = 0;
+    draw_donors_warp_rt(P, kdon, c, lane, r, &nstart, &xword);
+    const int L = P.replay ? exp_length_replay(P.r_uni + c * (int64_t)(D + 1), D, P.CR, lane) : exp_length_v2(xword, P.xlen, D);
     // 16-byte aligned cover of the window [nstart, nstart+L) mod D: [a1, a1+n1) and, wrapped, [0, n2)
     int a1 = nstart & ~1;
     const int end = nstart + L;

@@ -86,7 +86,7 @@ static void philox(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t 
 static uint64_t mulhi64(uint64_t a, uint64_t b) { return (uint64_t)(((unsigned __int128)a * b) >> 64); }
 
 static void draw_donors(uint64_t seed, uint32_t gen, uint32_t cand_global, int64_t cand, int64_t np, int dim, int k,
-                        int64_t* donors, int* nstart) {
+                        int64_t* donors, int* nstart, uint32_t* xword) {
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
   uint64_t r[6];
   for (int b = 0; b < (k + 2) / 2; ++b) {
@@ -112,12 +112,45 @@ static void draw_donors(uint64_t seed, uint32_t gen, uint32_t cand_global, int64
     ++nex;
   }
   *nstart = (int)mulhi64(r[k], (uint64_t)dim);
+  *xword = (uint32_t)r[k]; /* low half: the geometric draw of the exponential crossover length (protocol 2) */
 }
 
 static uint64_t crossover_threshold(double cr) {
   if (!(cr > 0.0)) return 0;
   if (cr >= 1.0) return 4294967296ull;
   return (uint64_t)floor(cr * 4294967296.0);
+}
+
+/* binomial crossover, protocol 2 (mystic_b200/csrc/philox.cuh): Bernoulli(CR) on 16-bit fields */
+static uint32_t crossover_threshold16(double cr) {
+  if (!(cr > 0.0)) return 0;
+  if (cr >= 1.0) return 65536u;
+  return (uint32_t)floor(cr * 65536.0);
+}
+
+/* exponential crossover, protocol 2: T[1..nmax] with T[0] = 2^32, T[l] = (T[l-1] * thr) >> 32;
+ * tab[l-1] = T[l]; returns nmax, or -1 when every draw succeeds (CR >= 1) */
+static int build_exp_length_table(uint64_t thr, int dim, uint32_t* tab) {
+  if (thr >= 4294967296ull) return -1;
+  uint64_t t = 4294967296ull;
+  int n = 0;
+  while (n < dim) {
+    t = (t * thr) >> 32;
+    if (t == 0) break;
+    tab[n++] = (uint32_t)t;
+  }
+  return n;
+}
+
+/* L = #{l in 1..nmax : w < T[l]} */
+static int exp_length(uint32_t w, const uint32_t* tab, int nmax, int dim) {
+  if (nmax < 0) return dim;
+  int lo = 0, hi = nmax; /* invariant: w < T[l] for l <= lo, w >= T[l] for l > hi */
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (w < tab[mid - 1]) lo = mid; else hi = mid - 1;
+  }
+  return lo;
 }
 
 /* ---------------------------------------------------------------- costs */
@@ -485,7 +518,9 @@ int orc_step(const orc_config* cfg, const double* pop_cur, double* pop_next, con
   int base, xover, k;
   strategy_info(cfg->strategy, &base, &xover, &k);
   const double F = cfg->F, CR = cfg->CR;
-  const uint64_t thr = crossover_threshold(CR);
+  const uint32_t thr16 = crossover_threshold16(CR);
+  uint32_t* xtab = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(D > 0 ? D : 1));
+  const int xnmax = build_exp_length_table(crossover_threshold(CR), D, xtab);
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma omp parallel
   {
@@ -496,41 +531,37 @@ int orc_step(const orc_config* cfg, const double* pop_cur, double* pop_next, con
     for (int64_t c = 0; c < np; ++c) {
       int64_t r[5] = {0, 0, 0, 0, 0};
       int n;
+      uint32_t xword = 0;
       const uint32_t cg = (uint32_t)(offset + c);
       if (rng_mode == 1) {
         for (int j = 0; j < k; ++j) r[j] = r_donors[c * 5 + j];
         n = r_nstart[c];
       } else {
-        draw_donors(seed, generation, cg, c, np, D, k, r, &n);
+        draw_donors(seed, generation, cg, c, np, D, k, r, &n, &xword);
       }
       /* crossover mask */
       if (xover == XOVER_BIN) {
         /* strategy.py:79-85 */
+        uint32_t v[4] = {0, 0, 0, 0};
         for (int i = 0; i < D; ++i) {
           int hit;
           if (rng_mode == 1) {
             hit = r_uni[c * (int64_t)(D + 1) + i] < CR;
           } else {
-            uint32_t v[4];
-            philox((uint32_t)(i >> 2), cg, generation, 1u, k0, k1, v);
-            hit = (uint64_t)v[i & 3] < thr;
+            /* dimension 8q+e: bits 16*(e&1)..+15 of word e>>1 of block q */
+            if ((i & 7) == 0) philox((uint32_t)(i >> 3), cg, generation, 1u, k0, k1, v);
+            const uint32_t word = v[(i & 7) >> 1];
+            hit = ((i & 1) ? (word >> 16) : (word & 0xffffu)) < thr16;
           }
           mask[i] = (unsigned char)(hit || i == n);
         }
       } else {
         /* strategy.py:48-56: L leading successes, capped at D */
         int L = 0;
-        uint32_t v[4];
-        while (L < D) {
-          int ok;
-          if (rng_mode == 1) {
-            ok = r_uni[c * (int64_t)(D + 1) + L] < CR;
-          } else {
-            if ((L & 3) == 0) philox((uint32_t)(L >> 2), cg, generation, 1u, k0, k1, v);
-            ok = (uint64_t)v[L & 3] < thr;
-          }
-          if (!ok) break;
-          ++L;
+        if (rng_mode == 1) {
+          while (L < D && r_uni[c * (int64_t)(D + 1) + L] < CR) ++L;
+        } else {
+          L = exp_length(xword, xtab, xnmax, D); /* one geometric draw (protocol 2) */
         }
         memset(mask, 0, D);
         for (int j = 0; j < L; ++j) mask[(n + j) % D] = 1;
@@ -570,6 +601,7 @@ int orc_step(const orc_config* cfg, const double* pop_cur, double* pop_next, con
     free(scratch);
     free(mask);
   }
+  free(xtab);
   select_best(np, D, trial_e_out, e_cur, pop_next, best_e, best_idx, best_x, n_inf, n_acc);
   return 0;
 }

@@ -529,7 +529,7 @@ def _mulhi64(a, b):
     return mid >> np.uint64(32)
 
 
-def philox_donors(seed, generation, cand, NP, D, k, offset=0):
+def philox_donors(seed, generation, cand, NP, D, k, offset=0, with_xword=False):
     """Donor indices [n,k] (distinct, != cand, uniform over ordered k-tuples) and start index.
 
     stream STREAM_DONORS, counter (block, cand, generation, stream); block b supplies the
@@ -561,23 +561,65 @@ def philox_donors(seed, generation, cand, NP, D, k, offset=0):
         excl[:, i + 1] = idx
         excl.sort(axis=1)
     nstart = _mulhi64(words[k], D).astype(np.int64)
+    if with_xword:   # low half of the start-index word: the geometric draw of the exponential crossover length
+        return donors, nstart, (words[k] & _MASK32).astype(np.uint32)
     return donors, nstart
 
 
+RNG_PROTOCOL = 2   # mystic_b200/csrc/philox.cuh kRngProtocol
+
+
 def crossover_threshold(CR):
-    """Bernoulli(CR) as `x < thr` on a 32-bit Philox word, thr in [0, 2^32] (64-bit compare)."""
+    """floor(CR * 2^32) in [0, 2^32]: the success probability of the exponential crossover's length table"""
     cr = min(max(float(CR), 0.0), 1.0)
     return int(math.floor(cr * 4294967296.0))
 
 
-def philox_xover_words(seed, generation, cand, D):
-    """[n, 4*ceil(D/4)] uint32 crossover words: word i = block i//4, lane i%4 of stream 1."""
+def crossover_threshold16(CR):
+    """Bernoulli(CR) as `field < thr16` on a 16-bit field of a Philox word (binomial crossover), thr16 in [0, 2^16]"""
+    cr = min(max(float(CR), 0.0), 1.0)
+    return int(math.floor(cr * 65536.0))
+
+
+def exp_length_table(CR, D):
+    """T[1..nmax] of the geometric draw (philox.cuh, protocol 2): T[0] = 2^32, T[l] = (T[l-1] * thr) >> 32 in integer
+    arithmetic, thr = floor(CR * 2^32); nmax = min(D, last l with T[l] > 0).  None when CR >= 1 (length D)."""
+    thr = crossover_threshold(CR)
+    if thr >= 1 << 32:
+        return None
+    tab, t = [], 1 << 32
+    while len(tab) < D:
+        t = (t * thr) >> 32
+        if t == 0:
+            break
+        tab.append(t)
+    return np.asarray(tab, dtype=np.uint64)
+
+
+def exp_length(xword, CR, D):
+    """exponential crossover length (strategy.py:48-56: number of leading draws below CR, at most D) as ONE geometric
+    draw: L = #{l >= 1 : w < T[l]}, w = low 32 bits of the start-index word"""
+    tab = exp_length_table(CR, D)
+    w = np.asarray(xword, dtype=np.uint64)
+    if tab is None:
+        return np.full(w.shape, D, dtype=np.int64)
+    if tab.size == 0:
+        return np.zeros(w.shape, dtype=np.int64)
+    # T decreases: count the entries above w
+    return (tab.size - np.searchsorted(tab[::-1], w, side='right')).astype(np.int64)
+
+
+def philox_xover_fields(seed, generation, cand, D):
+    """[n, 8*ceil(D/8)] crossover fields of stream 1 (binomial crossover): dimension 8q+e reads bits
+    16*(e&1)..16*(e&1)+15 of word e>>1 of block q"""
     cand = np.asarray(cand, dtype=np.int64)
     k0, k1 = np.uint32(seed & 0xFFFFFFFF), np.uint32((seed >> 32) & 0xFFFFFFFF)
-    nblk = (D + 3) // 4
+    nblk = (D + 7) // 8
     b = np.arange(nblk, dtype=np.uint32)[None, :]
     x = philox4x32(b, cand.astype(np.uint32)[:, None], np.uint32(generation), np.uint32(STREAM_XOVER), k0, k1)
-    return np.stack(x, axis=-1).reshape(cand.shape[0], nblk * 4)
+    words = np.stack(x, axis=-1)                                   # [n, nblk, 4]
+    fields = np.stack([words & np.uint32(0xFFFF), words >> np.uint32(16)], axis=-1)   # [n, nblk, 4, 2]
+    return fields.reshape(cand.shape[0], nblk * 8)
 
 
 def philox_init_population(seed, NP, lo, hi, offset=0):
@@ -618,15 +660,13 @@ def crossover_mask_replay(xover, D, nstart, uni, CR):
     return rel < L[:, None]
 
 
-def crossover_mask_philox(xover, D, nstart, words, CR):
-    thr = np.uint64(crossover_threshold(CR))
-    ok = words.astype(np.uint64) < thr
-    n = nstart.shape[0]
+def crossover_mask_philox(xover, D, nstart, CR, fields=None, xword=None):
+    """Bin: i == n or field_i < thr16 (fields from philox_xover_fields).  Exp: the window of exp_length(xword) dims"""
     idx = np.arange(D)[None, :]
     if xover == XOVER_BIN:
-        return (idx == nstart[:, None]) | ok[:, :D]
-    okD = ok[:, :D]
-    L = np.where(okD.all(axis=1), D, np.argmin(okD, axis=1))
+        ok = fields[:, :D].astype(np.uint32) < np.uint32(crossover_threshold16(CR))
+        return (idx == nstart[:, None]) | ok
+    L = exp_length(xword, CR, D)
     rel = (idx - nstart[:, None]) % D
     return rel < L[:, None]
 
@@ -735,9 +775,10 @@ def step(state, strategy, CR, F, cost, penalty_terms=(), replay=None, philox=Non
         mask = crossover_mask_replay(xover, D, nstart, np.asarray(replay['uni']), CR)
     else:
         cand = np.arange(NP, dtype=np.int64) + int(philox.get('offset', 0))
-        donors, nstart = philox_donors(philox['seed'], g, cand, NP, D, k, offset=int(philox.get('offset', 0)))
-        words = philox_xover_words(philox['seed'], g, cand, D)
-        mask = crossover_mask_philox(xover, D, nstart, words, CR)
+        donors, nstart, xword = philox_donors(philox['seed'], g, cand, NP, D, k, offset=int(philox.get('offset', 0)),
+                                              with_xword=True)
+        fields = philox_xover_fields(philox['seed'], g, cand, D) if xover == XOVER_BIN else None
+        mask = crossover_mask_philox(xover, D, nstart, CR, fields=fields, xword=xword)
     mutant = mutate(base, pop, state.bestSolution, donors, F)
     trial = np.where(mask, mutant, pop)
     trial = apply_bounds(trial, state)

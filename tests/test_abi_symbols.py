@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), 'missing export %s' % n
     from mystic_b200 import _native
     assert sorted(_native.EXPORTS) == names
-    assert _native.lib.mb2_abi_version() == 1
+    assert _native.lib.mb2_abi_version() == 2
 
 
 def test_product_does_not_import_the_oracle():

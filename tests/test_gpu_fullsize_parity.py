@@ -3,7 +3,10 @@ only covered by property tests, a wrong donor index at row 40 000 would have pas
 
 The device (Philox mode, through the C ABI) and the C/OpenMP oracle port run generation 0 and two
 generations from the same seed; after every generation the WHOLE population and the best member must be
-bit-identical, the energies within 1e-12, and the counters equal.  The launch geometry is the one the
+bit-identical, the energies within 1e-12, and the counters equal -- with one documented exception, selections of
+trials whose energy ties with the parent's to within that 1e-12 (see the loop below; at config 4 one row in two
+million: a trial that swaps -1000 and +1000 on two columns has the parent's cost exactly, and only the rounding of
+the penalty's running sum tells them apart).  The launch geometry is the one the
 bench uses (148 persistent CTAs, every stage of the rings reused many times)."""
 import numpy as np
 import pytest
@@ -52,6 +55,7 @@ def _run(NP, D, strategy, cost, extra, lo, hi, bounds, CR, F, pen, family, gens=
                        trials=False)
     _bits_equal(eng.population(), o.population, 'initial population')
     accepted = 0
+    ties = []
     for g in range(gens + 1):
         if g == 0:
             eng.eval_initial()
@@ -61,19 +65,46 @@ def _run(NP, D, strategy, cost, extra, lo, hi, bounds, CR, F, pen, family, gens=
             o.step(seed=seed, keep_trials=False)
         best_e, best_idx, n_inf, n_acc, gen, best_x = eng.read_result()
         pop = eng.population()
+        en = eng.energies()
+        # Near-ties.  Energies agree to 1e-12, not bit for bit (the device sums in its canonical tree, the reference
+        # left to right), so where a trial's energy equals its parent's to within that tolerance the strict `<` of
+        # the selection (differential_evolution.py:604) may legitimately fall the other way.  Such rows are verified
+        # one by one -- the device kept exactly the parent or took a trial with the oracle's trial energy -- counted,
+        # and the oracle's copy is aligned with the device so that later generations compare like with like.
+        differ = np.flatnonzero((pop.view(np.uint64) != o.population.view(np.uint64)).any(axis=1))
+        assert len(differ) <= 8, '%s generation %d: %d rows differ' % (cost, g, len(differ))
+        for c in differ:
+            assert g > 0
+            parent, e_par = o.pop[o.cur ^ 1][c], o.en[o.cur ^ 1][c]
+            te = o.trial_e[c]
+            assert abs(te - e_par) <= 1e-12 * max(abs(e_par), 1.0), \
+                '%s generation %d row %d differs and is no near-tie: parent %r trial %r' % (cost, g, c, e_par, te)
+            if np.array_equal(pop[c], parent):       # the device rejected what the oracle accepted
+                assert abs(en[c] - e_par) <= 1e-12 * max(abs(e_par), 1.0)
+                n_acc += 1
+            else:                                     # the device accepted what the oracle rejected
+                assert np.array_equal(o.population[c], parent) and abs(en[c] - te) <= 1e-12 * max(abs(te), 1.0)
+                n_acc -= 1
+            o.population[c] = pop[c]
+            o.popEnergy[c] = en[c]
+            ties.append((g, int(c)))
         _bits_equal(pop, o.population, '%s generation %d population' % (cost, g))
-        energy_close(eng.energies(), o.popEnergy, pop if cost == 'griewangk' else None, cost, '%s generation %d energies' % (cost, g))
-        _bits_equal(best_x, o.best_x, 'generation %d best member' % g)
-        assert best_idx == o.best_idx.value and n_inf == o.n_inf.value and n_acc == o.n_acc.value, \
-            (g, best_idx, o.best_idx.value, n_inf, o.n_inf.value, n_acc, o.n_acc.value)
+        energy_close(en, o.popEnergy, pop if cost == 'griewangk' else None, cost, '%s generation %d energies' % (cost, g))
+        if not differ.size:
+            _bits_equal(best_x, o.best_x, 'generation %d best member' % g)
+        # the port reports the member that became best in THIS generation (-1: none did), the device the member
+        # that last became best
+        assert (o.best_idx.value < 0 or differ.size or best_idx == o.best_idx.value) and n_inf == o.n_inf.value \
+            and n_acc == o.n_acc.value, (g, best_idx, o.best_idx.value, n_inf, o.n_inf.value, n_acc, o.n_acc.value)
         assert abs(best_e - o.bestEnergy) <= 1e-12 * max(1.0, abs(o.bestEnergy))
         if g:
             accepted += n_acc
         del pop
     assert eng.kernel_family() == family, eng.kernel_family()
     grid, block, smem = eng.launch_info()
-    print('%s %s D=%d NP=%d: %d generations bit-identical to the C oracle port; %d trials accepted; grid %d x %d'
-          % (strategy, cost, D, NP, gens, accepted, grid, block))
+    print('%s %s D=%d NP=%d: %d generations bit-identical to the C oracle port%s; %d trials accepted; grid %d x %d'
+          % (strategy, cost, D, NP, gens, (' but for %d near-tie selections %s' % (len(ties), ties)) if ties else '', accepted,
+             grid, block))
     eng.close()
     return accepted
 

@@ -116,3 +116,40 @@ def test_philox_donors_are_valid_and_uniform():
     off = counts[~np.eye(NP, dtype=bool)]
     assert abs(off.mean() - 399 / 10.) < 1e-9
     assert off.min() > 15 and off.max() < 70
+
+
+# ---- draw protocol 2 of the Philox mode (mystic_b200/csrc/philox.cuh): known answers and distributions ----
+def test_exponential_length_is_a_count_of_leading_zero_bits_at_cr_one_half():
+    """CR = 0.5: thr = 2^31, T[l] = 2^(32-l), so L = #{l : w < 2^(32-l)} = number of leading zero bits of w"""
+    tab = orc.exp_length_table(0.5, 1000)
+    assert [int(t) for t in tab] == [1 << (32 - l) for l in range(1, 33)]
+    w = np.array([0xFFFFFFFF, 0x80000000, 0x7FFFFFFF, 0x40000000, 0x3FFFFFFF, 1, 0], dtype=np.uint32)
+    assert orc.exp_length(w, 0.5, 1000).tolist() == [0, 0, 1, 1, 2, 31, 32]
+    assert orc.exp_length(w, 0.5, 5).tolist() == [0, 0, 1, 1, 2, 5, 5]          # capped at D
+    assert orc.exp_length(w, 1.0, 7).tolist() == [7] * 7 and orc.exp_length(w, 0.0, 7).tolist() == [0] * 7
+
+
+def test_exponential_length_follows_the_reference_loop_distribution():
+    """strategy.py:48-56 draws random() < CR until the first failure: P(L >= l) = CR^l, capped at D"""
+    rng = np.random.default_rng(3)
+    w = rng.integers(0, 1 << 32, size=400000, dtype=np.uint64).astype(np.uint32)
+    for CR, D in ((0.9, 64), (0.9, 1024), (0.5, 9), (0.97, 30)):
+        L = orc.exp_length(w, CR, D)
+        assert L.min() >= 0 and L.max() <= D
+        for l in (1, 2, 5, 10, 20, 40):
+            if l <= D:
+                assert abs((L >= l).mean() - CR ** l) < 4e-3, (CR, D, l)
+        assert abs(L.mean() - CR * (1 - CR ** D) / (1 - CR)) < 0.05
+
+
+def test_binomial_fields_are_bernoulli_cr_and_cover_every_dimension_once():
+    f = orc.philox_xover_fields(0x1234, 7, np.arange(2000), 100)
+    assert f.shape == (2000, 104) and f.max() < 65536
+    for CR in (0.9, 0.25):
+        hit = f[:, :100] < orc.crossover_threshold16(CR)
+        assert abs(hit.mean() - CR) < 4e-3
+    # dimension 8q+e reads bits 16*(e&1).. of word e>>1 of block q
+    x = orc.philox4x32(np.uint32(3), np.uint32(5), np.uint32(7), np.uint32(orc.STREAM_XOVER), np.uint32(0x1234), np.uint32(0))
+    words = [int(np.asarray(v).ravel()[0]) for v in x]
+    want = [(words[e >> 1] >> (16 * (e & 1))) & 0xFFFF for e in range(8)]
+    assert f[5, 24:32].tolist() == want
