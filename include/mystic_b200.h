@@ -102,7 +102,12 @@ enum mb2_penalty {
   MB2_PEN_QUADRATIC_EQUALITY = 0,   /* penalty.py:41-98   : k*pf^2        */
   MB2_PEN_LINEAR_EQUALITY = 1,      /* penalty.py:100-157 : k*|pf|        */
   MB2_PEN_QUADRATIC_INEQUALITY = 2, /* penalty.py:341-398 : 2k*max(0,pf)^2 */
-  MB2_PEN_LINEAR_INEQUALITY = 3     /* penalty.py:400-457 : 2k*|max(0,pf)| */
+  MB2_PEN_LINEAR_INEQUALITY = 3,    /* penalty.py:400-457 : 2k*|max(0,pf)| */
+  MB2_PEN_UNIFORM_EQUALITY = 4,     /* penalty.py:159-216 : k if pf else 0   (k may be inf)          */
+  MB2_PEN_UNIFORM_INEQUALITY = 5,   /* penalty.py:218-274 : k if pf > 0 else 0                       */
+  MB2_PEN_BARRIER_INEQUALITY = 6,   /* penalty.py:276-339 : inf if pf > 0 else -.5/k*log(-pf)        */
+  MB2_PEN_LAGRANGE_INEQUALITY = 7,  /* penalty.py:459-530 : k*mpf^2 + beta*mpf, mpf = max(-beta/(2k), pf) */
+  MB2_PEN_LAGRANGE_EQUALITY = 8     /* penalty.py:532-601 : k*pf^2 + lam*pf                          */
 };
 
 typedef struct mb2_ctx mb2_ctx;
@@ -155,6 +160,12 @@ int mb2_set_cost(mb2_ctx* ctx, int cost, const double* params_host, int32_t npar
  * kscale[i] = k*h**n (the decorator's current multiplier before the inequality factor 2) */
 int mb2_set_penalty(mb2_ctx* ctx, int32_t nterms, const int32_t* ptype_host, const double* G_host,
                     const double* h_host, const double* kscale_host);
+/* The same with per-term multipliers: the lagrange kinds accumulate beta / lambda over the values `store(x)`
+ * recorded at earlier penalty iterations (penalty.py:511-515, 579-582 -- host state, a handful of scalars);
+ * mult_host[i] is that sum for term i (ignored by the other kinds; NULL = all zero).  kscale[i] is the
+ * multiplier k*h**n after the same loop. */
+int mb2_set_penalty_ex(mb2_ctx* ctx, int32_t nterms, const int32_t* ptype_host, const double* G_host,
+                       const double* h_host, const double* kscale_host, const double* mult_host);
 
 /* Random draws.  Philox4x32-10 counter RNG keyed by `seed`, counter = (block, global candidate,
  * generation, stream) -- replaces random.sample / random.randrange / random.random of

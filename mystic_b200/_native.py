@@ -19,7 +19,7 @@ EXPORTS = [
     'mb2_eval_initial', 'mb2_step', 'mb2_pack_best', 'mb2_merge_best', 'mb2_read_result', 'mb2_eval_cost',
     'mb2_launch_info', 'mb2_launch_count', 'mb2_kernel_family', 'mb2_selftest_division', 'mb2_selftest_cosine', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
     'mb2_set_termination', 'mb2_run', 'mb2_run_result', 'mb2_set_islands', 'mb2_read_islands', 'mb2_exchange_open', 'mb2_exchange_connect', 'mb2_exchange_connected', 'mb2_exchange_reset', 'mb2_exchange_best',
-    'mb2_probe_fp64_peak',
+    'mb2_probe_fp64_peak', 'mb2_set_penalty_ex',
 ]
 
 
@@ -61,6 +61,7 @@ def _load():
         'mb2_set_bounds': (ctypes.c_int, [vp, ctypes.c_int, c_double_p, c_double_p]),
         'mb2_set_cost': (ctypes.c_int, [vp, ctypes.c_int, c_double_p, i32]),
         'mb2_set_penalty': (ctypes.c_int, [vp, i32, c_int32_p, c_double_p, c_double_p, c_double_p]),
+        'mb2_set_penalty_ex': (ctypes.c_int, [vp, i32, c_int32_p, c_double_p, c_double_p, c_double_p, c_double_p]),
         'mb2_set_rng_philox': (ctypes.c_int, [vp, u64]),
         'mb2_set_rng_replay': (ctypes.c_int, [vp, vp, vp, vp]),
         'mb2_init_population': (ctypes.c_int, [vp, u64, c_double_p, c_double_p, vp]),

@@ -123,8 +123,9 @@ struct mb2_ctx {
   int cheb_ks = 0;
   double* cheb_x = nullptr;
   double2* grw_tab = nullptr;
-  PenaltyParams pp = {0, nullptr, nullptr, nullptr, nullptr};
+  PenaltyParams pp = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
   int* pen_type = nullptr;
+  double* pen_mult = nullptr;
   double* pen_G = nullptr;
   double* pen_h = nullptr;
   double* pen_k = nullptr;
@@ -441,6 +442,7 @@ bool rows_bulk_geometry(int dim, int lpr, int k, int* warps, BulkRowsLayout* L, 
   L->stage_bytes = (unsigned)((rows + (size_t)k * pool_b + meta + 127) & ~(size_t)127);
   L->undo_bytes = (unsigned)((pool_b + 127) & ~(size_t)127);
   L->warp_bytes = L->undo_bytes + (unsigned)st * L->stage_bytes;
+  L->donors_ldgsts = env_int("MB2_RB_LDGSTS", 0) != 0 ? 1 : 0;  // measured on B200 at C4: 0.303 ms vs 0.297 ms with bulk requests (profiles/README.md)
   *warps = w;
   *smem = (int)(best + (size_t)w * L->warp_bytes);
   return true;
@@ -1089,18 +1091,22 @@ int mb2_selftest_cosine(mb2_ctx* c, int64_t n, uint64_t seed, double span, doubl
   return MB2_OK;
 }
 
-int mb2_set_penalty(mb2_ctx* c, int32_t nterms, const int32_t* ptype, const double* G, const double* h,
-                    const double* kscale) {
+int mb2_set_penalty_ex(mb2_ctx* c, int32_t nterms, const int32_t* ptype, const double* G, const double* h,
+                       const double* kscale, const double* mult) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
   if (nterms < 0) return fail(MB2_EINVAL, "nterms < 0");
   ENTER_DEVICE(c->device);
   if (c->generation >= 0) CUDA_TRY(cudaDeviceSynchronize());  // kernels of a non-blocking stream may still read the terms
-  c->pp = {0, nullptr, nullptr, nullptr, nullptr};
+  c->pp = {0, nullptr, nullptr, nullptr, nullptr, nullptr};
   if (nterms == 0) return MB2_OK;
   if (!ptype || !G || !h || !kscale) return fail(MB2_EINVAL, "penalty arrays are NULL");
-  for (int i = 0; i < nterms; ++i)
-    if (ptype[i] < 0 || ptype[i] > 3) return fail(MB2_EINVAL, "unknown penalty type %d", ptype[i]);
-  const size_t pen_bytes = ((sizeof(int) * nterms + 255) & ~(size_t)255) + sizeof(double) * nterms * (c->dim + 2);
+  for (int i = 0; i < nterms; ++i) {
+    if (ptype[i] < MB2_PEN_QUADRATIC_EQUALITY || ptype[i] > MB2_PEN_LAGRANGE_EQUALITY)
+      return fail(MB2_EINVAL, "unknown penalty type %d", ptype[i]);
+    if (ptype[i] >= MB2_PEN_LAGRANGE_INEQUALITY && mult == nullptr)
+      return fail(MB2_EINVAL, "lagrange penalties need their multipliers (mb2_set_penalty_ex)");
+  }
+  const size_t pen_bytes = ((sizeof(int) * nterms + 255) & ~(size_t)255) + sizeof(double) * nterms * (c->dim + 3);
   if (c->cap_pen < pen_bytes) {
     void* p = nullptr;
     if (int rc = dev_alloc(c, pen_bytes, &p)) return rc;
@@ -1110,12 +1116,21 @@ int mb2_set_penalty(mb2_ctx* c, int32_t nterms, const int32_t* ptype, const doub
   c->pen_G = reinterpret_cast<double*>(reinterpret_cast<char*>(c->pen_type) + ((sizeof(int) * nterms + 255) & ~(size_t)255));
   c->pen_h = c->pen_G + (size_t)nterms * c->dim;
   c->pen_k = c->pen_h + nterms;
+  c->pen_mult = c->pen_k + nterms;
+  std::vector<double> m((size_t)nterms, 0.0);
+  if (mult != nullptr) m.assign(mult, mult + nterms);
   CUDA_TRY(cudaMemcpy(c->pen_type, ptype, sizeof(int) * nterms, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->pen_G, G, sizeof(double) * nterms * c->dim, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->pen_h, h, sizeof(double) * nterms, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMemcpy(c->pen_k, kscale, sizeof(double) * nterms, cudaMemcpyHostToDevice));
-  c->pp = {nterms, c->pen_type, c->pen_G, c->pen_h, c->pen_k};
+  CUDA_TRY(cudaMemcpy(c->pen_mult, m.data(), sizeof(double) * nterms, cudaMemcpyHostToDevice));
+  c->pp = {nterms, c->pen_type, c->pen_G, c->pen_h, c->pen_k, c->pen_mult};
   return MB2_OK;
+}
+
+int mb2_set_penalty(mb2_ctx* c, int32_t nterms, const int32_t* ptype, const double* G, const double* h,
+                    const double* kscale) {
+  return mb2_set_penalty_ex(c, nterms, ptype, G, h, kscale, nullptr);
 }
 
 int mb2_set_rng_philox(mb2_ctx* c, uint64_t seed) {

@@ -312,14 +312,7 @@ __global__ void __launch_bounds__(kChebWarps * 32, MB2_CHEB_MINBLOCKS)
         double acc = 0.0;
         for (int j = 0; j < D; ++j) acc = dadd(acc, dmul(__ldg(g + j), row[j]));
         const double pf = dsub(acc, __ldg(P.pen.h + t));
-        const double k = __ldg(P.pen.kscale + t);
-        const int ty = __ldg(P.pen.ptype + t);
-        const double mpos = (pf > 0.0) ? pf : 0.0;
-        double v;
-        if (ty == 0) v = dmul(k, dmul(pf, pf));
-        else if (ty == 1) v = dmul(k, fabs(pf));
-        else if (ty == 2) v = dmul(2.0 * k, dmul(mpos, mpos));
-        else v = dmul(2.0 * k, fabs(mpos));
+        const double v = penalty_term(__ldg(P.pen.ptype + t), __ldg(P.pen.kscale + t), __ldg(P.pen.mult + t), pf);
         pen = dadd(v, pen);
       }
       E = dadd(E, pen);

@@ -609,7 +609,34 @@ struct PenaltyParams {
   const double* G;      // [n, D]
   const double* h;      // [n]
   const double* kscale; // [n]  k*h**n
+  const double* mult;   // [n]  lagrange kinds: the multiplier accumulated from the stored iterations (beta / lambda)
 };
+
+// one penalty term of the stack for the condition value pf = G.x - h (mystic/penalty.py; k = k*h**n):
+//   0 quadratic_equality :88    k*pf**2            1 linear_equality :147    k*|pf|
+//   2 quadratic_inequality :388 2k*max(0,pf)**2    3 linear_inequality :447  2k*|max(0,pf)|
+//   4 uniform_equality :208     k if pf else 0     5 uniform_inequality :266 k if pf > 0 else 0
+//   6 barrier_inequality :326   inf if pf > 0 else -.5/k*log(-pf)   (numpy.log: log(0) = -inf, so pf == 0 gives +inf)
+//   7 lagrange_inequality :517  k*mpf**2 + beta*mpf, mpf = max(-beta/(2k), pf)     8 lagrange_equality :585  k*pf**2 + lam*pf
+// Python's max(a, b) keeps a unless b > a.
+__device__ __forceinline__ double penalty_term(int ty, double k, double mult, double pf) {
+  const double mpos = (pf > 0.0) ? pf : 0.0;
+  switch (ty) {
+    case 0: return dmul(k, dmul(pf, pf));
+    case 1: return dmul(k, fabs(pf));
+    case 2: return dmul(2.0 * k, dmul(mpos, mpos));
+    case 3: return dmul(2.0 * k, fabs(mpos));
+    case 4: return (pf != 0.0) ? k : 0.0;
+    case 5: return (pf > 0.0) ? k : 0.0;
+    case 6: return (pf > 0.0) ? CUDART_INF : dmul(__ddiv_rn(-0.5, k), log(-pf));
+    case 7: {
+      const double floor_ = __ddiv_rn(-mult, dmul(2.0, k));
+      const double mpf = (pf > floor_) ? pf : floor_;
+      return dadd(dmul(k, dmul(mpf, mpf)), dmul(mult, mpf));
+    }
+    default: return dadd(dmul(k, dmul(pf, pf)), dmul(mult, pf));
+  }
+}
 
 // term 0 innermost; value = t_{n-1} + (... + (t_0 + 0.0))  (penalty.py:88,147,388,447)
 template <int GW>
@@ -630,20 +657,7 @@ __device__ __forceinline__ double group_penalty(const Group<GW>& g, const double
       }
     }
     const double pf = dsub(group_reduce<false, GW>(g, acc, 0), __ldg(pp.h + t));
-    const double k = __ldg(pp.kscale + t);
-    const int ty = __ldg(pp.ptype + t);
-    double v;
-    if (ty == 0) {
-      v = dmul(k, dmul(pf, pf));
-    } else if (ty == 1) {
-      v = dmul(k, fabs(pf));
-    } else if (ty == 2) {
-      const double m = (pf > 0.0) ? pf : 0.0;  // python max(0., pf)
-      v = dmul(2.0 * k, dmul(m, m));
-    } else {
-      const double m = (pf > 0.0) ? pf : 0.0;
-      v = dmul(2.0 * k, fabs(m));
-    }
+    const double v = penalty_term(__ldg(pp.ptype + t), __ldg(pp.kscale + t), __ldg(pp.mult + t), pf);
     total = dadd(v, total);
   }
   return total;

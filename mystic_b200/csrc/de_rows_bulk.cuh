@@ -29,6 +29,9 @@ namespace mb2 {
 #ifndef MB2_RB_MAXWARPS
 #define MB2_RB_MAXWARPS 24
 #endif
+#ifndef MB2_RB_BATCH_DRAWS
+#define MB2_RB_BATCH_DRAWS 1
+#endif
 constexpr int kBulkRowsMaxWarps = MB2_RB_MAXWARPS;  // 24 warps: 80 registers per thread (no spills)
 constexpr int kBulkRowsMaxStages = 4;
 
@@ -52,7 +55,15 @@ struct BulkRowsLayout {
   unsigned stage_bytes;  // rounded to 128
   unsigned undo_bytes;   // the warp's undo pool, rounded to 128
   unsigned warp_bytes;   // undo_bytes + stages * stage_bytes
+  int donors_ldgsts;     // 1: donor windows by per-lane 16-byte cp.async (LDGSTS), 0: by cp.async.bulk requests
 };
+
+// 16-byte asynchronous global -> shared copy through the LSU path (SASS LDGSTS.E.BYPASS.128): no registers held,
+// completion by cp.async.wait_all of the issuing thread
+__device__ __forceinline__ void ldgsts16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ldgsts_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 template <int COST, int LPR, int K>
 __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
@@ -101,6 +112,11 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
   const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
   const int64_t nw = (int64_t)gridDim.x * wpc;
 
+  // draws of the next stages, made 16 rows at a time (strategies with two donor-stream blocks per row; one stage
+  // per warp, so that the warp's stages are ch, ch + nw, ... in issue order)
+  constexpr bool kBatchDraws = ((K + 2) / 2 == 2) && MB2_RB_BATCH_DRAWS;
+  uint64_t dc_even = 0, dc_odd = 0;
+  int dc_left = 0;  // stages still served by the cached words
   // ---- draws + loads of the rows of chunk `ch` into the stage at `st` (whole warp)
   auto issue = [&](int64_t ch, unsigned char* st, uint64_t* bar) {
     const int64_t c = ch * RPW + grp;
@@ -113,7 +129,35 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
       bulk_g2s(st, P.pop_cur + ch * RPW * D, nlive * row_bytes, bar);
     }
     RowDraws<K> dr;
-    rows_draw<LPR, K>(P, XOVER_EXP, cc, sub, gbase, dr);
+    if (kBatchDraws && !P.replay) {
+      // one Philox evaluation of the warp makes the draws of 16 rows = 16 / RPW consecutive stages of this warp
+      // (lane l: block l & 1 of row (l >> 1) & (RPW - 1) of stage (l >> 1) / RPW ahead); same counters and words
+      // as rows_draw
+      if (dc_left == 0) {
+        const int64_t chl = ch + (int64_t)((lane >> 1) / RPW) * nw;  // the warp issues chunks ch, ch + nw, ... whatever the ring depth
+        int64_t cr = chl * RPW + ((lane >> 1) & (RPW - 1));
+        if (cr >= P.np) cr = P.np - 1;  // idle groups shadow the last row, as below
+        const u32x4 v = philox4x32_10((uint32_t)(lane & 1), (uint32_t)(P.global_offset + cr), P.generation, STREAM_DONORS, P.key0, P.key1);
+        dc_even = ((uint64_t)v.x << 32) | v.y;
+        dc_odd = ((uint64_t)v.z << 32) | v.w;
+        dc_left = 16 / RPW;
+      }
+      const int src = 2 * ((16 / RPW - dc_left) * RPW + grp);
+      uint64_t rw[4];
+      rw[0] = __shfl_sync(0xffffffffu, dc_even, src);
+      rw[1] = __shfl_sync(0xffffffffu, dc_odd, src);
+      rw[2] = __shfl_sync(0xffffffffu, dc_even, src + 1);
+      rw[3] = __shfl_sync(0xffffffffu, dc_odd, src + 1);
+      --dc_left;
+      int64_t r64[K];
+      uint32_t xword;
+      resolve_donors<K>(rw, cc, P.np, D, r64, &dr.nstart, &xword);
+#pragma unroll
+      for (int j = 0; j < K; ++j) dr.r[j] = (int)r64[j];
+      dr.L = exp_length_v2(xword, P.xlen, D);
+    } else {
+      rows_draw<LPR, K>(P, XOVER_EXP, cc, sub, gbase, dr);
+    }
     const int q0 = dr.nstart >> 2;
     int nq = (dr.L > 0) ? (((dr.nstart + dr.L - 1) >> 2) - q0 + 1) : 0;
     if (nq > NQ) nq = NQ;  // a full-length window that starts inside a chunk: each chunk once
@@ -137,9 +181,30 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
       m->off = off;
 #pragma unroll
       for (int j = 0; j < K; ++j) m->r[j] = dr.r[j];
-      mbar_expect_tx(bar, fits ? (unsigned)(K * nq) * 32u : 0u);  // the arrive of this row: meta is published with it
+      // the arrive of this row: meta is published with it
+      mbar_expect_tx(bar, (fits && !G.donors_ldgsts) ? (unsigned)(K * nq) * 32u : 0u);
     }
     __syncwarp();
+    if (G.donors_ldgsts) {
+      // Donor windows through the LSU path: the bulk-copy engine takes ~20 cycles per request whatever its size
+      // (the C4 pattern is ~3 requests of ~100 bytes per row: request-rate bound, ncu shows the warps queueing on
+      // UBLKCP), and a request costs an elect loop of ~10 instructions.  Here lane `sub` of the row's group copies
+      // the 16-byte halves sub, sub+LPR, ... of the window's chunks, donor by donor; one instruction serves the
+      // RPW rows of the warp.  Completion: cp.async.wait_all + __syncwarp before the stage is read.
+      if (fits) {
+#pragma unroll
+        for (int j = 0; j < K; ++j) {
+          const double* srow = P.pop_cur + (int64_t)dr.r[j] * D;
+          double* pool = reinterpret_cast<double*>(st + G.rows_bytes + (unsigned)j * G.pool_bytes) + 4 * off;
+          for (int t = sub; t < 2 * nq; t += LPR) {
+            int q = q0 + (t >> 1);
+            if (q >= NQ) q -= NQ;
+            ldgsts16(pool + 2 * t, srow + 4 * q + 2 * (t & 1));
+          }
+        }
+      }
+      return;
+    }
     // one copy instruction serves the whole warp: lane 1 + j of a row's group requests the window's cover
     // of donor j (a second instruction for the wrapped parts; further rounds when K > LPR - 1)
     const int n1 = (q0 + nq <= NQ) ? nq : (NQ - q0);  // chunks before the wrap
@@ -181,6 +246,10 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
     const double e_old = __ldg(P.e_cur + cc);  // in flight while the warp waits for its stage
 
     mbar_wait(bars + s, parity);
+    if (G.donors_ldgsts) {
+      ldgsts_wait_all();  // this lane's donor pieces have landed ...
+      __syncwarp();       // ... and so have the other lanes'
+    }
     const BulkRowMeta* m = reinterpret_cast<const BulkRowMeta*>(st + G.meta_off) + grp;
     RowDraws<K> dr;
     dr.nstart = m->nstart;

@@ -129,14 +129,7 @@ __device__ __forceinline__ double thread_penalty(const double* x, int D, const P
     double acc = 0.0;
     for (int j = 0; j < D; ++j) acc = dadd(acc, dmul(__ldg(g + j), x[j]));
     const double pf = dsub(acc, __ldg(pp.h + t));
-    const double k = __ldg(pp.kscale + t);
-    const int ty = __ldg(pp.ptype + t);
-    const double mpos = (pf > 0.0) ? pf : 0.0;
-    double v;
-    if (ty == 0) v = dmul(k, dmul(pf, pf));
-    else if (ty == 1) v = dmul(k, fabs(pf));
-    else if (ty == 2) v = dmul(2.0 * k, dmul(mpos, mpos));
-    else v = dmul(2.0 * k, fabs(mpos));
+    const double v = penalty_term(__ldg(pp.ptype + t), __ldg(pp.kscale + t), __ldg(pp.mult + t), pf);
     pen = dadd(v, pen);
   }
   return pen;

@@ -117,14 +117,7 @@ __device__ __forceinline__ double seg_penalty(const double* xs, int D, int sub, 
     double acc = 0.0;
     for (int i = sub; i < D; i += LPR) acc = dadd(acc, dmul(__ldg(g + i), xs[i]));
     const double pf = dsub(seg_reduce<LPR, false>(acc), __ldg(pp.h + t));
-    const double k = __ldg(pp.kscale + t);
-    const int ty = __ldg(pp.ptype + t);
-    const double m = (pf > 0.0) ? pf : 0.0;
-    double v;
-    if (ty == 0) v = dmul(k, dmul(pf, pf));
-    else if (ty == 1) v = dmul(k, fabs(pf));
-    else if (ty == 2) v = dmul(2.0 * k, dmul(m, m));
-    else v = dmul(2.0 * k, fabs(m));
+    const double v = penalty_term(__ldg(pp.ptype + t), __ldg(pp.kscale + t), __ldg(pp.mult + t), pf);
     total = dadd(v, total);
   }
   return total;

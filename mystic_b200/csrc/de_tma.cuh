@@ -138,10 +138,32 @@ __global__ void __launch_bounds__(MAXT, 1)
   // once, here; the start index travels to the group through shared memory (published by the
   // release of the mbarrier arrive, acquired by the group's wait on the same barrier).
   // called by the whole leader WARP of the group (tig < 32): collective draws, lane 0 issues
+  // The group's rows are issued in the order g0, g0 + ng, g0 + 2 ng, ...: ONE Philox evaluation of the leader
+  // warp makes the donor / start-index words of the next 16 of them (lane l: block l & 1 of row (l >> 1) ahead),
+  // kept in two registers per lane and handed out by shuffle -- instead of one evaluation per row in which 30 of
+  // the 32 lanes idle.  Same counters, same words as draw_donors<2>.
+  uint64_t dc_even = 0, dc_odd = 0;
+  int dc_pos = 16;  // next cached row (16: the cache is empty)
   auto issue = [&](int64_t c, int s) {
     int64_t r[2];
     int nstart;
-    best1_draws(P, c, lane, r, &nstart);
+    if (P.replay) {
+      best1_draws(P, c, lane, r, &nstart);
+    } else {
+      if (dc_pos == 16) {
+        const int64_t cr = c + (int64_t)(lane >> 1) * ng;  // rows past the end: evaluated, never handed out
+        const u32x4 v = philox4x32_10((uint32_t)(lane & 1), (uint32_t)(P.global_offset + cr), P.generation, STREAM_DONORS, P.key0, P.key1);
+        dc_even = ((uint64_t)v.x << 32) | v.y;
+        dc_odd = ((uint64_t)v.z << 32) | v.w;
+        dc_pos = 0;
+      }
+      uint64_t w[3];
+      w[0] = __shfl_sync(0xffffffffu, dc_even, 2 * dc_pos);
+      w[1] = __shfl_sync(0xffffffffu, dc_odd, 2 * dc_pos);
+      w[2] = __shfl_sync(0xffffffffu, dc_even, 2 * dc_pos + 1);
+      resolve_donors<2>(w, c, P.np, D, r, &nstart);
+      ++dc_pos;
+    }
     if (leader) {
       s_nstart[group * kTmaMaxStages + s] = nstart;
       unsigned char* buf = s_ring + (unsigned)s * 3u * row_stride;
@@ -189,8 +211,9 @@ __global__ void __launch_bounds__(MAXT, 1)
     bool oob = false;
     const int tq = tig & 3;
     const bool tq0 = (tq & 1) != 0, tq1 = (tq & 2) != 0;
-    auto trip = [&](int base, auto guard) {
+    auto trip = [&](int base, auto guard, auto uclamp) {
       constexpr bool GUARD = decltype(guard)::value;
+      constexpr bool UCLAMP = decltype(uclamp)::value;  // clamp to one [lo_s, hi_s] for every dimension, known outside the loop
       bool cx[8];  // crossover decisions of dims 2p_j, 2p_j+1, j = 0..3
       if (P.replay) {
         const double* u = P.r_uni + c * (int64_t)(D + 1);
@@ -231,7 +254,12 @@ __global__ void __launch_bounds__(MAXT, 1)
           const double2 a = s_d0[p], b = s_d1[p], bs = s_b2[p];
           if (cx[2 * j]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
           if (cx[2 * j + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
-          if (P.bounds_mode != BOUNDS_NONE) {
+          if (UCLAMP) {
+            x.x = (x.x > P.lo_s) ? x.x : P.lo_s;
+            x.x = (x.x < P.hi_s) ? x.x : P.hi_s;
+            x.y = (x.y > P.lo_s) ? x.y : P.lo_s;
+            x.y = (x.y < P.hi_s) ? x.y : P.hi_s;
+          } else if (P.bounds_mode != BOUNDS_NONE) {
             const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p + 1);
             const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p + 1);
             if (P.bounds_mode == BOUNDS_CLAMP) {
@@ -248,9 +276,13 @@ __global__ void __launch_bounds__(MAXT, 1)
       }
     };
     if (npairs % (4 * gthreads) == 0) {  // whole trips only: no per-chunk guards
-      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type());
+      if (uni_b && P.bounds_mode == BOUNDS_CLAMP) {
+        for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::true_type());
+      } else {
+        for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::false_type());
+      }
     } else {
-      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::true_type());
+      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::true_type(), std::false_type());
     }
     oob = group_any(grp, oob);  // also the barrier that publishes the trial vector to the group
 

@@ -100,7 +100,8 @@ class DeviceEngine(object):
         p = np.ascontiguousarray(params, dtype=np.float64)
         check(lib.mb2_set_cost(self._ctx, int(cost_id), _dptr(p) if p.size else None, int(p.size)))
 
-    def set_penalty(self, ptypes=(), G=(), h=(), kscale=()):
+    def set_penalty(self, ptypes=(), G=(), h=(), kscale=(), mult=None):
+        """stacked penalty terms (innermost first); `mult`: the lagrange kinds' accumulated multipliers"""
         n = len(ptypes)
         if n == 0:
             check(lib.mb2_set_penalty(self._ctx, 0, None, None, None, None))
@@ -109,7 +110,9 @@ class DeviceEngine(object):
         Gm = np.ascontiguousarray(G, dtype=np.float64).reshape(n, self.dim)
         hv = np.ascontiguousarray(h, dtype=np.float64)
         kv = np.ascontiguousarray(kscale, dtype=np.float64)
-        check(lib.mb2_set_penalty(self._ctx, n, pt.ctypes.data_as(_native.c_int32_p), _dptr(Gm), _dptr(hv), _dptr(kv)))
+        mv = np.zeros(n, dtype=np.float64) if mult is None else np.ascontiguousarray(mult, dtype=np.float64)
+        check(lib.mb2_set_penalty_ex(self._ctx, n, pt.ctypes.data_as(_native.c_int32_p), _dptr(Gm), _dptr(hv), _dptr(kv),
+                                     _dptr(mv)))
 
     def set_rng_philox(self, seed):
         check(lib.mb2_set_rng_philox(self._ctx, int(seed) & 0xFFFFFFFFFFFFFFFF))

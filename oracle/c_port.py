@@ -21,7 +21,7 @@ class Config(ctypes.Structure):
                 ('cheb_order', ctypes.c_int32), ('cheb_target', _dp), ('n_pen', ctypes.c_int32),
                 ('pad_', ctypes.c_int32), ('pen_type', _ip), ('pen_G', _dp), ('pen_h', _dp), ('pen_k', _dp),
                 ('fit_M', ctypes.c_int32), ('pad2_', ctypes.c_int32), ('fit_pts', _dp), ('fit_obs', _dp),
-                ('fit_sigma', ctypes.c_double), ('fit_sigma_v', _dp)]
+                ('fit_sigma', ctypes.c_double), ('fit_sigma_v', _dp), ('pen_mult', _dp)]
 
 
 _lib = None
@@ -113,11 +113,23 @@ class COracle(object):
             self._pt = np.ascontiguousarray([orc.PTYPES[t['ptype']] for t in penalty], dtype=np.int32)
             self._G = np.ascontiguousarray([t['G'] for t in penalty], dtype=np.float64)
             self._h = np.ascontiguousarray([t['h'] for t in penalty], dtype=np.float64)
-            self._k = np.ascontiguousarray([t.get('k', 100) * pow(t.get('hpow', 5), t.get('n', 0)) for t in penalty],
-                                           dtype=np.float64)
+            ks, ms = [], []
+            for t in penalty:
+                if 'kscale' in t:
+                    ks.append(t['kscale'])
+                    ms.append(t.get('mult', 0.0))
+                elif t['ptype'] in ('lagrange_inequality', 'lagrange_equality'):
+                    k_, m_ = orc.lagrange_state(t['ptype'], t.get('k', 20), t.get('hpow', 5), t.get('n', 0), t.get('stored', ()))
+                    ks.append(k_)
+                    ms.append(m_)
+                else:
+                    ks.append(t.get('k', 100) * pow(t.get('hpow', 5), t.get('n', 0)))
+                    ms.append(0.0)
+            self._k = np.ascontiguousarray(ks, dtype=np.float64)
+            self._m = np.ascontiguousarray(ms, dtype=np.float64)
             cfg.n_pen = len(penalty)
             cfg.pen_type = self._pt.ctypes.data_as(_ip)
-            cfg.pen_G, cfg.pen_h, cfg.pen_k = _d(self._G), _d(self._h), _d(self._k)
+            cfg.pen_G, cfg.pen_h, cfg.pen_k, cfg.pen_mult = _d(self._G), _d(self._h), _d(self._k), _d(self._m)
         self.cfg = cfg
 
     @property

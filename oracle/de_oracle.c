@@ -56,6 +56,7 @@ typedef struct {
   const double* fit_obs;
   double fit_sigma;
   const double* fit_sigma_v; /* per-point sigma (models/br8.py:47), NULL: the scalar */
+  const double* pen_mult;    /* lagrange penalties: accumulated multiplier per term (beta / lam), NULL: zeros */
 } orc_config;
 
 /* strategy id -> base, crossover, donors (strategy.py:34-311; only Best1Bin is binomial) */
@@ -389,11 +390,22 @@ static double penalty_value(const double* x, int D, const orc_config* cfg) {
     for (int j = 0; j < D; ++j) acc = acc + g[j] * x[j];
     double pf = acc - cfg->pen_h[t];
     double k = cfg->pen_k[t], v;
+    const double mult = cfg->pen_mult ? cfg->pen_mult[t] : 0.0;
     switch (cfg->pen_type[t]) {
       case 0: v = k * pow(pf, 2); break;                        /* penalty.py:88  */
       case 1: v = k * fabs(pf); break;                          /* penalty.py:147 */
       case 2: { double m = pf > 0. ? pf : 0.; v = (2 * k) * pow(m, 2); break; }  /* :388 */
-      default: { double m = pf > 0. ? pf : 0.; v = (2 * k) * fabs(m); break; }   /* :447 */
+      case 3: { double m = pf > 0. ? pf : 0.; v = (2 * k) * fabs(m); break; }    /* :447 */
+      case 4: v = (pf != 0.) ? k : 0.; break;                   /* :208 uniform_equality: _k if pf else 0.0 */
+      case 5: v = (pf > 0.) ? k : 0.; break;                    /* :266 uniform_inequality */
+      case 6: v = (pf > 0.) ? INFINITY : (-.5 / k) * log(-pf); break; /* :322-326 barrier (numpy.log: log(0) = -inf) */
+      case 7: {                                                 /* :516-517 lagrange_inequality */
+        const double lo = -mult / (2. * k);
+        const double mpf = (pf > lo) ? pf : lo;                 /* Python max(lo, pf) */
+        v = k * pow(mpf, 2) + mult * mpf;
+        break;
+      }
+      default: v = k * pow(pf, 2) + mult * pf; break;           /* :583 lagrange_equality */
     }
     total = v + total;
   }

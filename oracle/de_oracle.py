@@ -42,7 +42,9 @@ STRATEGIES = {
 BOUNDS_NONE, BOUNDS_REJECT, BOUNDS_CLAMP = 0, 1, 2
 
 PTYPES = {'quadratic_equality': 0, 'linear_equality': 1,
-          'quadratic_inequality': 2, 'linear_inequality': 3}
+          'quadratic_inequality': 2, 'linear_inequality': 3,
+          'uniform_equality': 4, 'uniform_inequality': 5, 'barrier_inequality': 6,
+          'lagrange_inequality': 7, 'lagrange_equality': 8}
 
 
 # ----------------------------------------------------------------------------------------
@@ -455,8 +457,22 @@ def make_cost(name, extra_args=()):
 
 
 # ----------------------------------------------------------------------------------------
-# penalty (a5): mystic/penalty.py:41-157, 341-457 stacked decorators; tools.py:380-389
+# penalty (a5): mystic/penalty.py:41-601 stacked decorators; tools.py:380-389
 # ----------------------------------------------------------------------------------------
+def lagrange_state(ptype, k, h, n, stored):
+    """(_k, multiplier) after the decorator's loop over the first n stored condition values:
+    penalty.py:511-515 (beta of lagrange_inequality), :579-582 (lam of lagrange_equality)"""
+    mult, _k = 0., k
+    for i in range(n):
+        y = stored[i] if i < len(stored) else 0.0     # stored(i) answers 0.0 past the end (:503-506)
+        if ptype == 'lagrange_inequality':
+            mult += 2. * _k * max(-mult / (2. * _k), y)
+        else:
+            mult += 2. * _k * y
+        _k *= h
+    return _k, mult
+
+
 def penalty_value(x, terms):
     """terms[0] is the innermost decorator.  Outermost is evaluated first and the inner
     result is added to it: t_last + (... + (t_0 + 0.0)).  condition = sequential dot - h
@@ -470,8 +486,13 @@ def penalty_value(x, terms):
         for j in range(D):
             acc = acc + G[j] * x[:, j]
         pf = acc - float(t['h'])
-        _k = t.get('k', 100) * pow(t.get('hpow', 5), t.get('n', 0))
         ptype = t['ptype']
+        if 'kscale' in t:                      # as handed to the device: multiplier and accumulated lagrange multiplier
+            _k, mult = t['kscale'], t.get('mult', 0.0)
+        elif ptype in ('lagrange_inequality', 'lagrange_equality'):
+            _k, mult = lagrange_state(ptype, t.get('k', 20), t.get('hpow', 5), t.get('n', 0), t.get('stored', ()))
+        else:
+            _k, mult = t.get('k', 100) * pow(t.get('hpow', 5), t.get('n', 0)), 0.0
         if ptype == 'quadratic_equality':      # penalty.py:88
             v = float(_k) * _pow(pf, 2).astype(np.float64)
         elif ptype == 'linear_equality':       # penalty.py:147
@@ -480,6 +501,19 @@ def penalty_value(x, terms):
             v = float(2 * _k) * _pow(np.maximum(0., pf), 2).astype(np.float64)
         elif ptype == 'linear_inequality':     # penalty.py:447
             v = float(2 * _k) * np.abs(np.maximum(0., pf))
+        elif ptype == 'uniform_equality':      # penalty.py:208: _k if pf else 0.0
+            v = np.where(pf != 0.0, float(_k), 0.0)
+        elif ptype == 'uniform_inequality':    # penalty.py:266: _k if pf > 0 else 0.0
+            v = np.where(pf > 0.0, float(_k), 0.0)
+        elif ptype == 'barrier_inequality':    # penalty.py:322-326: inf if pf > 0 else -.5/_k*log(-pf) (numpy.log)
+            with np.errstate(divide='ignore', invalid='ignore'):
+                v = np.where(pf > 0.0, np.inf, -.5 / _k * np.log(-np.where(pf > 0.0, -1.0, pf)))
+        elif ptype == 'lagrange_inequality':   # penalty.py:516-517: mpf = max(-beta/(2.*_k), pf); Python max keeps the first unless the second is larger
+            lo_ = -mult / (2. * _k)
+            mpf = np.where(pf > lo_, pf, lo_)
+            v = float(_k) * _pow(mpf, 2).astype(np.float64) + mult * mpf
+        elif ptype == 'lagrange_equality':     # penalty.py:583
+            v = float(_k) * _pow(pf, 2).astype(np.float64) + mult * pf
         else:
             raise KeyError(ptype)
         total = v + total

@@ -45,4 +45,22 @@ def build_reference_penalty(terms):
         dec = getattr(mp, t['ptype'])(HostLinearCondition(t['G'], t['h']),
                                       k=t.get('k', 100), h=t.get('hpow', 5))
         f = dec(f)
+    # penalty iterations done before the run (the lagrange decorators accumulate their multiplier from the
+    # condition values `store(x, i)` recorded at each: penalty.py:489-500, 511-515).  `store_points` of a term:
+    # one point per iteration; the resulting values go back into the term as 'stored' so that the oracle and
+    # the device can be handed the same numbers.
+    n = max([t.get('n', 0) for t in terms] or [0])
+    if n:
+        g = f
+        for t in reversed(terms):      # outermost first
+            for i, x in enumerate(t.get('store_points', ())):
+                g.store(x, i)          # (passes through to the wrapped functions as well; each keeps its own list)
+            g = dict(zip(g.__code__.co_freevars, (c.cell_contents for c in g.__closure__)))['f']
+        f.iter(n)
+        g = f
+        for t in reversed(terms):
+            if t['ptype'].startswith('lagrange'):
+                t['stored'] = list(g.stored())
+            t['n'] = n
+            g = dict(zip(g.__code__.co_freevars, (c.cell_contents for c in g.__closure__)))['f']
     return f

@@ -314,6 +314,30 @@ def cases():
                                              dict(ptype='quadratic_equality', G=[0., 0., 1., 0., 0., -2.], h=0.5, k=50, hpow=5),
                                              dict(ptype='linear_inequality', G=[0., 0., 0., 1., 1., 0.], h=1., k=100, hpow=5)],
                                     maxgen=10)
+    # the other penalty kinds over linear conditions (penalty.py:159-339, 459-601); the lagrange kinds after two
+    # penalty iterations with stored condition values
+    cs['pen_uniform_rosen4'] = dict(dim=4, NP=20, strategy='Best1Exp', cost='rosen', CR=0.9, F=0.8, seed=501,
+                                    init=('random', [-2.] * 4, [2.] * 4),
+                                    penalty=[dict(ptype='uniform_inequality', G=[1., 1., 1., 1.], h=3., k=1e3, hpow=5),
+                                             dict(ptype='uniform_equality', G=[1., -1., 0., 0.], h=0., k=0.5, hpow=5)],
+                                    maxgen=10)
+    cs['pen_barrier_rosen4'] = dict(dim=4, NP=20, strategy='Rand1Exp', cost='rosen', CR=0.9, F=0.8, seed=502,
+                                    init=('random', [-1.] * 4, [1.] * 4),
+                                    penalty=[dict(ptype='barrier_inequality', G=[1., 1., 1., 1.], h=3., k=100, hpow=5)],
+                                    maxgen=10)
+    cs['pen_lagrange_rosen5'] = dict(dim=5, NP=25, strategy='RandToBest1Exp', cost='rosen', CR=0.9, F=0.8, seed=503,
+                                     init=('random', [-2.] * 5, [2.] * 5),
+                                     penalty=[dict(ptype='lagrange_inequality', G=[1., 1., 1., 1., 1.], h=2., k=20, hpow=5, n=2,
+                                                   store_points=[[1., 1., 1., 0., 0.], [0.5, 0.5, 0.5, 0.5, 0.25]]),
+                                              dict(ptype='lagrange_equality', G=[1., -2., 0., 0., 1.], h=0.25, k=20, hpow=5, n=2,
+                                                   store_points=[[1., 0., 0., 0., 0.], [0.5, 0.2, 0., 0., 0.1]])],
+                                     maxgen=10)
+    cs['pen_lagrange_corana64_rand1exp'] = dict(dim=64, NP=64, strategy='Rand1Exp', cost='corana', CR=0.9, F=0.8, seed=504,
+                                                init=('random', [-1000.] * 64, [1000.] * 64),
+                                                bounds=([-1000.] * 64, [1000.] * 64, True),
+                                                penalty=[dict(ptype='lagrange_inequality', G=[1.] * 64, h=100., k=20, hpow=5, n=1,
+                                                              store_points=[[10.] * 64])],
+                                                maxgen=4)
     # edge cases: CR extremes, SetInitialPoints, NP raised to max(NP, dim, 4)
     cs['edge_cr0_best1bin'] = dict(dim=5, NP=12, strategy='Best1Bin', cost='rosen', CR=0.0, F=0.8,
                                    seed=61, init=('random', [-2.] * 5, [2.] * 5), maxgen=6)

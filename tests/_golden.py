@@ -76,3 +76,26 @@ def restore_mt_state(z):
     """put stdlib `random` into the state the reference had right before Solve()"""
     import random
     random.setstate((3, tuple(int(v) for v in z['mt_state']), None))
+
+
+def device_penalty_of(meta):
+    """the recorded run's penalty stack built with mystic_b200.penalty's decorators, penalty iterations included:
+    the same store(x, i) / iter(n) calls oracle/host_callables.build_reference_penalty made on the reference's
+    decorators (outermost term first; a store passes through to the wrapped terms, which then store their own points)"""
+    from mystic_b200 import penalty
+
+    def pen(x):
+        return 0.0
+    for t in meta['penalty']:
+        pen = getattr(penalty, t['ptype'])(penalty.linear(t['G'], t['h']), k=t['k'], h=t['hpow'])(pen)
+    n = max([t.get('n', 0) for t in meta['penalty']] or [0])
+    if n:
+        for ti in reversed(range(len(meta['penalty']))):
+            sub = penalty.DevicePenalty(pen.terms[:ti + 1])
+            for i, x in enumerate(meta['penalty'][ti].get('store_points', ())):
+                sub.store(x, i)
+        pen.iter(n)
+        for t, d in zip(meta['penalty'], pen.terms):
+            if t['ptype'].startswith('lagrange'):
+                assert d['y'] == t['stored'], (d['y'], t['stored'])   # the host's condition values equal the reference's
+    return pen

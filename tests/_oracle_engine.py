@@ -58,9 +58,10 @@ class OracleEngine(object):
             M, order = int(params[0]), int(params[1])
             self.cost = orc.make_cost('chebyshev%dcost' % order, (M,))
 
-    def set_penalty(self, ptypes=(), G=(), h=(), kscale=()):
-        self.pen = [dict(ptype=_PTYPE_BY_ID[int(p)], G=list(g), h=float(hh), k=float(k), hpow=1, n=0)
-                    for p, g, hh, k in zip(ptypes, G, h, kscale)]
+    def set_penalty(self, ptypes=(), G=(), h=(), kscale=(), mult=None):
+        mult = [0.0] * len(ptypes) if mult is None else mult
+        self.pen = [dict(ptype=_PTYPE_BY_ID[int(p)], G=list(g), h=float(hh), kscale=float(k), mult=float(m))
+                    for p, g, hh, k, m in zip(ptypes, G, h, kscale, mult)]
 
     def set_rng_philox(self, seed):
         self.seed = int(seed)

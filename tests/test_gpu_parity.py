@@ -49,11 +49,7 @@ def configure(eng, meta, z=None):
     cost = G.device_cost_of(meta, z)
     eng.set_cost(cost.cost_id, cost.params(tuple(meta.get('ExtraArgs') or ())))
     if meta.get('penalty'):
-        def pen(x):
-            return 0.0
-        for t in meta['penalty']:
-            pen = getattr(penalty, t['ptype'])(penalty.linear(t['G'], t['h']), k=t['k'], h=t['hpow'])(pen)
-        eng.set_penalty(*pen.device_terms(meta['dim']))
+        eng.set_penalty(*G.device_penalty_of(meta).device_terms(meta['dim']))
     sid = orc.STRATEGIES[meta['strategy']][0]
     eng.set_strategy(sid, meta['F_eff'], meta['CR_eff'])
 

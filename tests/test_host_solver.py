@@ -28,11 +28,7 @@ def make_solver(meta, z, rng, engine=OracleEngine, **extra):
         else:
             s.SetStrictRanges(lo, hi)
     if meta.get('penalty'):
-        def pen(x):
-            return 0.0
-        for t in meta['penalty']:
-            pen = getattr(penalty, t['ptype'])(penalty.linear(t['G'], t['h']), k=t['k'], h=t['hpow'])(pen)
-        s.SetPenalty(pen)
+        s.SetPenalty(G.device_penalty_of(meta))
     s.SetEvaluationLimits(generations=meta['maxgen'])
     return s
 

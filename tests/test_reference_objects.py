@@ -82,6 +82,32 @@ def test_reference_penalty_decorator_with_linear_condition():
     G.assert_bits_equal(s.population, z['pop'][-1], 'population')
 
 
+def test_reference_lagrange_decorators_with_stored_iterations():
+    """mystic.penalty's own lagrange decorators over linear conditions, after two penalty iterations made with the
+    reference's store(x, i) / iter(n): the solver reads k, h, n and the stored condition values out of them"""
+    meta, z = G.load('pen_lagrange_rosen5')
+    pen = lambda x: 0.0   # noqa: E731
+    for t in meta['penalty']:
+        pen = getattr(mystic.penalty, t['ptype'])(penalty.linear(t['G'], t['h']), k=t['k'], h=t['hpow'])(pen)
+    g = pen
+    for t in reversed(meta['penalty']):
+        for i, x in enumerate(t['store_points']):
+            g.store(x, i)
+        g = dict(zip(g.__code__.co_freevars, (c.cell_contents for c in g.__closure__)))['f']
+    pen.iter(2)
+    dev = penalty.resolve(pen)
+    assert [t['y'] for t in dev.terms] == [t['stored'] for t in meta['penalty']] and [t['n'] for t in dev.terms] == [2, 2]
+    random.seed(meta['seed'])
+    s = DifferentialEvolutionSolver2(5, 25, rng='replay', engine=OracleEngine, CrossProbability=meta['CR'], ScalingFactor=meta['F'])
+    s.SetPopulation(z['pop0'])
+    s.SetPenalty(pen)
+    s.SetReplayDraws((z['donors'][k], z['nstart'][k], z['uni'][k]) for k in range(z['donors'].shape[0]))
+    s.SetEvaluationLimits(generations=meta['maxgen'])
+    s.Solve(mystic.models.rosen, mystic.termination.VTR(-1.0), strategy=getattr(mystic.strategy, meta['strategy']))
+    G.assert_bits_equal(np.array(s.energy_history), z['energy_history'], 'energy history')
+    G.assert_bits_equal(s.population, z['pop'][-1], 'population')
+
+
 def test_host_callables_are_rejected():
     s = DifferentialEvolutionSolver2(3, 8, engine=OracleEngine)
     with pytest.raises(TypeError):
