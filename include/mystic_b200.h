@@ -228,6 +228,13 @@ int mb2_set_termination(mb2_ctx* ctx, const mb2_termination* t, const double* hi
 int mb2_run(mb2_ctx* ctx, int32_t max_steps, double* log_dev, void* stream);
 /* synchronise; number of generations actually executed and whether a condition stopped the batch */
 int mb2_run_result(mb2_ctx* ctx, int32_t* executed, int32_t* stopped, void* stream);
+/* The same loop for a batch of solvers (mb2_set_islands; the ensemble solvers of abstract_ensemble_solver.py:737-826
+ * run N nested solvers, each to ITS OWN termination): mb2_set_termination -- after mb2_set_islands, before generation 0,
+ * history_len 0 -- installs the condition for every island; mb2_run then takes log_dev [n_islands, max_steps, dim+4],
+ * starts with generation 0 when it has not run yet, and every island logs and stops on its own (a stopped island keeps
+ * its rows, energies and best member while the others go on).  mb2_run_result_islands synchronises and returns, per
+ * island, the generations logged in the batch and whether the island has met its condition. */
+int mb2_run_result_islands(mb2_ctx* ctx, int32_t* executed, int32_t* stopped, void* stream);
 
 /* multi-GPU best exchange (Best and RandToBest strategies read the global best,
  * strategy.py:52,83,137,164,247,274): pack this shard's [best_energy, best_index(global),
@@ -263,11 +270,17 @@ int mb2_exchange_best(mb2_ctx* ctx, void* stream);
  * The `np_local` rows of the context are n_islands populations of np_local / n_islands members laid
  * side by side; every island draws its donors among its own members (its rows key the Philox
  * counters), follows its own best member and reports its own result: island i behaves exactly like
- * shard i of a sharded population without the best exchange.  Rows of at most 128 dimensions;
+ * shard i of a sharded population without the best exchange.  Rows of at most ~3200 dimensions (shared-memory bound);
  * mb2_eval_initial / mb2_step advance all islands, mb2_read_islands returns n_islands results and
  * best members ([n_islands, dim], may be NULL).  Call before mb2_eval_initial. */
 int mb2_set_islands(mb2_ctx* ctx, int32_t n_islands);
 int mb2_read_islands(mb2_ctx* ctx, mb2_result* out, double* x_host, void* stream);
+/* Islands that share their best member within groups of `group_size` consecutive islands (after mb2_set_islands,
+ * before mb2_eval_initial): every generation ends with the group's winner -- lowest energy, ties to the lowest
+ * global index, the rule of mb2_merge_best -- installed in each island of the group.  A group is then exactly a
+ * population sharded over group_size ranks (shard-local donors drawn per strategy.py:27 from the shard, global best
+ * for the Best / RandToBest strategies), on one GPU; 1 = independent islands. */
+int mb2_set_island_groups(mb2_ctx* ctx, int32_t group_size);
 
 /* synchronises `stream`, then returns the generation result and bestSolution (dim doubles;
  * x_host may be NULL) */

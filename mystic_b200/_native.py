@@ -19,7 +19,7 @@ EXPORTS = [
     'mb2_eval_initial', 'mb2_step', 'mb2_pack_best', 'mb2_merge_best', 'mb2_read_result', 'mb2_eval_cost',
     'mb2_launch_info', 'mb2_launch_count', 'mb2_kernel_family', 'mb2_selftest_division', 'mb2_selftest_cosine', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
     'mb2_set_termination', 'mb2_run', 'mb2_run_result', 'mb2_set_islands', 'mb2_read_islands', 'mb2_exchange_open', 'mb2_exchange_connect', 'mb2_exchange_connected', 'mb2_exchange_reset', 'mb2_exchange_best',
-    'mb2_probe_fp64_peak', 'mb2_set_penalty_ex',
+    'mb2_probe_fp64_peak', 'mb2_set_penalty_ex', 'mb2_set_island_groups', 'mb2_run_result_islands',
 ]
 
 
@@ -79,6 +79,8 @@ def _load():
         'mb2_selftest_division': (ctypes.c_int, [vp, i64, u64, dbl, c_int64_p]),
         'mb2_set_islands': (ctypes.c_int, [vp, i32]),
         'mb2_read_islands': (ctypes.c_int, [vp, ctypes.c_void_p, c_double_p, vp]),
+        'mb2_set_island_groups': (ctypes.c_int, [vp, i32]),
+        'mb2_run_result_islands': (ctypes.c_int, [vp, c_int32_p, c_int32_p, vp]),
         'mb2_exchange_open': (ctypes.c_int, [vp, i32, i32, vp, i32]),
         'mb2_exchange_connect': (ctypes.c_int, [vp, vp, i32]),
         'mb2_exchange_best': (ctypes.c_int, [vp, vp]),

@@ -177,6 +177,13 @@ struct mb2_ctx {
   // batch of independent solvers (mb2_set_islands): n_islands populations of np / n_islands rows
   // side by side in the buffers, each with its own best member and DeviceState
   int n_islands = 1;
+  int island_group = 1;  // islands share their best member within groups of this many consecutive islands
+  // device-side termination of a batch of solvers: one RunState per island
+  RunState* run_isl = nullptr;
+  int run_isl_cap = 0;
+  int run_isl_set = 0;      // mb2_set_termination has installed a condition for the islands
+  int* isl_status = nullptr;    // device [2 * n_islands]
+  int* h_isl_status = nullptr;  // pinned
   DeviceState* st_isl = nullptr;
   double* best_x_isl = nullptr;
   DeviceState* h_st_isl = nullptr;  // pinned
@@ -456,7 +463,6 @@ void fill_params(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, 
 // (grid.y = island) of the rows-per-warp kernel with run-time strategy (rows of <= 128 dimensions)
 int launch_step_islands(mb2_ctx* c, int mode, cudaStream_t stream) {
   const int64_t inp = c->np / c->n_islands;
-  if (c->dim > kSubMaxDim) return fail(MB2_EINVAL, "batched solvers support rows of at most %d dimensions", kSubMaxDim);
   if (c->cost == MB2_COST_CHEBYSHEV_MMA || c->cost == MB2_COST_POLYFIT_MMA)
     return fail(MB2_EINVAL, "batched solvers use the Horner / elementwise cost variants");
   const double* in_rows = c->pop[c->cur];
@@ -470,7 +476,10 @@ int launch_step_islands(mb2_ctx* c, int mode, cudaStream_t stream) {
                                                                    : get_subwarp_islands_kernel(c->cost, lpr, vec));
   if (k == nullptr) return fail(MB2_EINVAL, "no batched kernel for cost %d", c->cost);
   const int rows_per_cta = kSubWarps * (32 / lpr);
-  const int smem = (int)(sizeof(double) * (size_t)(1 + kSubWarps * (32 / lpr)) * c->dim_pad);
+  const size_t smem_need = sizeof(double) * (size_t)(1 + kSubWarps * (32 / lpr)) * c->dim_pad;
+  // rows longer than 256 dimensions take a whole warp each (lpr = 32): the best member and 8 rows live in shared memory
+  if (smem_need > 227 * 1024) return fail(MB2_EINVAL, "batched solvers support rows of at most %d dimensions", (227 * 1024 / 72) & ~3);
+  const int smem = (int)smem_need;
   CUDA_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   int64_t gx = (inp + rows_per_cta - 1) / rows_per_cta;
   if (gx > 64) gx = 64;  // the CTAs of an island stride over its rows
@@ -479,7 +488,7 @@ int launch_step_islands(mb2_ctx* c, int mode, cudaStream_t stream) {
   fill_params(c, mode, in_rows, out_rows, c->en[c->cur], c->en[c->cur ^ 1], inp, &P);
   P.best_x = c->best_x_isl;
   P.rows_in_range = 0;
-  P.stop = nullptr;
+  P.stop = (c->run_active && c->run_isl != nullptr) ? &c->run_isl[0].stop : nullptr;  // per island: stride sizeof(RunState)
   c->wpc = kSubWarps;
   c->grid = (int)gx;
   c->smem = smem;
@@ -726,9 +735,16 @@ int launch_finalize(mb2_ctx* c, int gen0, cudaStream_t stream) {
   if (c->n_islands > 1) {
     de_finalize_islands_kernel<<<(unsigned)c->n_islands, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
                                                                            c->pop[c->cur ^ 1], c->np / c->n_islands, c->dim, c->offset, gen0,
-                                                                           c->generation + 1, c->best_x_isl, c->st_isl);
+                                                                           c->generation + 1, c->best_x_isl, c->st_isl,
+                                                                           c->run_active ? c->run_isl : nullptr);
     CUDA_TRY(cudaGetLastError());
     ++c->launches;
+    if (c->island_group > 1) {
+      islands_share_best_kernel<<<(unsigned)(c->n_islands / c->island_group), 256, 0, stream>>>(c->island_group, c->dim, c->best_x_isl,
+                                                                                               c->st_isl);
+      CUDA_TRY(cudaGetLastError());
+      ++c->launches;
+    }
     return MB2_OK;
   }
   de_finalize_kernel<<<1, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
@@ -840,6 +856,7 @@ int mb2_destroy(mb2_ctx* c) {
       cudaFree(c->mailbox);
     }
   }
+  if (c->run_isl != nullptr) cudaFree(c->run_isl);
   for (void* p : c->owned_dev) cudaFree(p);
   for (void* p : c->owned_host) cudaFreeHost(p);
   delete c;
@@ -1249,6 +1266,10 @@ int mb2_set_termination(mb2_ctx* c, const mb2_termination* t, const double* hist
   if (t->lookback < 0 || t->lookback >= kHistMax) return fail(MB2_EINVAL, "lookback must be in [0, %d)", kHistMax);
   if (history_len < 0 || (history_len > 0 && history_host == nullptr)) return fail(MB2_EINVAL, "bad history");
   ENTER_DEVICE(c->device);
+  if (c->n_islands > 1 && (history_len != 0 || c->generation >= 0))
+    return fail(MB2_EINVAL, "batched solvers take their condition before generation 0 (the device keeps every island's history)");
+  if (c->n_islands > 1 && c->island_group > 1)
+    return fail(MB2_EINVAL, "islands that share their best member are stepped with mb2_step");
   if (c->run == nullptr) {
     void* p = nullptr;
     if (int rc = dev_alloc(c, sizeof(RunState), &p)) return rc;
@@ -1277,18 +1298,60 @@ int mb2_set_termination(mb2_ctx* c, const mb2_termination* t, const double* hist
     for (int64_t i = first; i < history_len; ++i) r->hist[i % kHistMax] = history_host[i];
   }
   CUDA_TRY(cudaMemcpy(c->run, r, sizeof(RunState), cudaMemcpyHostToDevice));
+  if (c->n_islands > 1) {
+    // one RunState per island, all starting from the same description (each island counts its own evaluations)
+    const int n = c->n_islands;
+    if (c->run_isl_cap < n) {
+      if (c->run_isl != nullptr) cudaFree(c->run_isl);  // (not from the workspace: kilobytes per island)
+      c->run_isl = nullptr;
+      CUDA_TRY(cudaMalloc((void**)&c->run_isl, sizeof(RunState) * (size_t)n));
+      c->run_isl_cap = n;
+      void* p = nullptr;
+      if (int rc = dev_alloc(c, sizeof(int) * 2 * (size_t)n, &p)) return rc;
+      c->isl_status = (int*)p;
+      if (int rc = host_alloc(c, sizeof(int) * 2 * (size_t)n, &p)) return rc;
+      c->h_isl_status = (int*)p;
+    }
+    r->np_eval = c->np / n;
+    for (int i = 0; i < n; ++i)
+      CUDA_TRY(cudaMemcpy(c->run_isl + i, r, offsetof(RunState, hist), cudaMemcpyHostToDevice));
+    c->run_isl_set = 1;
+  }
   return MB2_OK;
 }
 
 int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
   if (c == nullptr || c->pop[0] == nullptr) return fail(MB2_ESTATE, "no buffers bound");
   if (c->run == nullptr) return fail(MB2_ESTATE, "mb2_set_termination must run before mb2_run");
-  if (c->n_islands > 1) return fail(MB2_EINVAL, "batched solvers are stepped with mb2_step (their termination lives on the host)");
-  if (c->generation < 0) return fail(MB2_ESTATE, "mb2_eval_initial must run before mb2_run");
   if (max_steps < 1 || log_dev == nullptr) return fail(MB2_EINVAL, "bad argument");
   if (c->replay) return fail(MB2_EINVAL, "batch stepping needs the Philox generator (replayed draws are per generation)");
   ENTER_DEVICE(c->device);
   cudaStream_t s = (cudaStream_t)stream;
+  if (c->n_islands > 1) {
+    // batch of solvers: every island logs into its own [max_steps, dim+4] block of log_dev and stops on its own
+    // condition; generation 0 is the first "step" of the first batch
+    if (!c->run_isl_set) return fail(MB2_ESTATE, "mb2_set_termination must run (after mb2_set_islands) before mb2_run");
+    const int n = c->n_islands;
+    islands_arm_kernel<<<(n + 127) / 128, 128, 0, s>>>(c->run_isl, n, log_dev, (long long)max_steps, c->dim);
+    CUDA_TRY(cudaGetLastError());
+    ++c->launches;
+    c->run_active = 1;
+    c->run_enqueued = max_steps;
+    int rc = MB2_OK;
+    for (int k = 0; k < max_steps && rc == MB2_OK; ++k) {
+      const int gen0 = c->generation < 0 ? 1 : 0;
+      rc = launch_step(c, gen0 ? MODE_GEN0 : MODE_STEP, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s);
+      if (rc == MB2_OK) rc = launch_finalize(c, gen0, s);
+      if (rc == MB2_OK) {
+        c->cur ^= 1;
+        c->generation += 1;
+        if (gen0) c->rows_in_range = (c->bounds_mode != BOUNDS_NONE) ? 1 : 0;
+      }
+    }
+    c->run_active = 0;
+    return rc;
+  }
+  if (c->generation < 0) return fail(MB2_ESTATE, "mb2_eval_initial must run before mb2_run");
   // arm the log for this batch (stream ordered: the previous batch has been read back by mb2_run_result)
   struct { long long count, cap; double* log; } arm = {0, max_steps, log_dev};
   CUDA_TRY(cudaMemcpyAsync(&c->run->log_count, &arm, sizeof(arm), cudaMemcpyHostToDevice, s));
@@ -1329,6 +1392,24 @@ int mb2_run_result(mb2_ctx* c, int32_t* executed, int32_t* stopped, void* stream
   if (c->h_run->stop == 2) {  // log full without a termination: clear the flag for the next batch
     int zero = 0;
     CUDA_TRY(cudaMemcpy(&c->run->stop, &zero, sizeof(int), cudaMemcpyHostToDevice));
+  }
+  return MB2_OK;
+}
+
+int mb2_run_result_islands(mb2_ctx* c, int32_t* executed, int32_t* stopped, void* stream) {
+  if (c == nullptr || executed == nullptr || stopped == nullptr) return fail(MB2_EINVAL, "bad argument");
+  if (c->n_islands < 2 || !c->run_isl_set) return fail(MB2_ESTATE, "no batch of solvers with a device-side condition");
+  ENTER_DEVICE(c->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int n = c->n_islands;
+  islands_status_kernel<<<(n + 127) / 128, 128, 0, s>>>(c->run_isl, n, c->isl_status);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  CUDA_TRY(cudaMemcpyAsync(c->h_isl_status, c->isl_status, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  for (int i = 0; i < n; ++i) {
+    executed[i] = c->h_isl_status[2 * i];
+    stopped[i] = (c->h_isl_status[2 * i + 1] == 1) ? 1 : 0;
   }
   return MB2_OK;
 }
@@ -1378,6 +1459,17 @@ int mb2_set_islands(mb2_ctx* c, int32_t n_islands) {
     CUDA_TRY(cudaMemset(c->best_x_isl, 0, sizeof(double) * (size_t)n_islands * c->dim));
   }
   c->n_islands = n_islands;
+  c->island_group = 1;
+  c->run_isl_set = 0;
+  return MB2_OK;
+}
+
+int mb2_set_island_groups(mb2_ctx* c, int32_t group_size) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (group_size < 1 || c->n_islands % group_size != 0)
+    return fail(MB2_EINVAL, "%d islands do not split into groups of %d", c->n_islands, group_size);
+  if (c->generation >= 0) return fail(MB2_ESTATE, "mb2_set_island_groups must come before mb2_eval_initial");
+  c->island_group = group_size;
   return MB2_OK;
 }
 

@@ -199,7 +199,7 @@ __device__ __forceinline__ void finalize_body(const double* __restrict__ part_e,
   if (threadIdx.x == 0) {
     rs->log_count = slot + 1;
     rs->evaluations += rs->np_eval - st->n_inf;        // differential_evolution.py:601
-    rs->generations += 1;
+    if (!gen0) rs->generations += 1;                    // (generation 0 is logged by batches of solvers only)
     const double e = st->best_e;                        // stepmon(bestSolution, bestEnergy) (:617)
     if (rs->hist_count == 0) rs->hist0 = e;
     rs->hist[rs->hist_count % kHistMax] = e;
@@ -254,13 +254,73 @@ __global__ void __launch_bounds__(256)
                                const unsigned long long* __restrict__ part_ninf,
                                const unsigned long long* __restrict__ part_nacc, int nparts,
                                const double* __restrict__ pop_next, int64_t island_np, int D, int64_t global_offset,
-                               int gen0, int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st) {
+                               int gen0, int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
+                               RunState* __restrict__ rs) {
   const int64_t isl = blockIdx.x;
   ExchangeParams none;
   none.world = 1;
   finalize_body(part_e + isl * nparts, part_idx + isl * nparts, part_ninf + isl * nparts, part_nacc + isl * nparts, nparts,
                 pop_next + isl * island_np * D, D, global_offset + isl * island_np, gen0, generation, best_x + isl * D,
-                st + isl, nullptr, none);
+                st + isl, rs != nullptr ? rs + isl : nullptr, none);
+}
+
+// batch of solvers with device-side termination: point every island's log at its block of the batch log
+// [n_islands, max_steps, D+4] and clear a "log full" stop of the previous batch
+__global__ void islands_arm_kernel(RunState* __restrict__ rs, int n, double* log, long long max_steps, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rs[i].log = log + (size_t)i * max_steps * (D + 4);
+  rs[i].log_count = 0;
+  rs[i].log_cap = max_steps;
+  if (rs[i].stop == 2) rs[i].stop = 0;
+}
+
+// (generations logged in this batch, stop flag) of every island
+__global__ void islands_status_kernel(const RunState* __restrict__ rs, int n, int* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  out[2 * i] = (int)rs[i].log_count;
+  out[2 * i + 1] = rs[i].stop;
+}
+
+// Islands that share their best member within groups of `gsize` consecutive islands (blockIdx.x = group): after the
+// per-island epilogue the group's winner -- lowest energy, ties to the lowest global index, the rule of the
+// sharded best exchange above -- is installed in every island of the group.  A group is then EXACTLY a population
+// sharded over `gsize` ranks (shard-local donors, global best), all on one GPU: what the statistics tests use to
+// validate that deviation from the reference's global donor pool over many seeds in one launch per generation.
+__global__ void __launch_bounds__(256)
+    islands_share_best_kernel(int gsize, int D, double* __restrict__ best_x, DeviceState* __restrict__ st) {
+  __shared__ int sh_w;
+  const int first = blockIdx.x * gsize;
+  if (threadIdx.x == 0) {
+    int w = -1;
+    double be = CUDART_INF;
+    int64_t bi = 0;
+    for (int r = 0; r < gsize; ++r) {
+      const DeviceState& s = st[first + r];
+      if (s.best_idx < 0) continue;  // island has no best yet
+      if (w < 0 || s.best_e < be || (s.best_e == be && s.best_idx < bi)) {
+        w = r;
+        be = s.best_e;
+        bi = s.best_idx;
+      }
+    }
+    if (w >= 0)
+      for (int r = 0; r < gsize; ++r) {
+        st[first + r].best_e = be;
+        st[first + r].best_idx = bi;
+      }
+    sh_w = w;
+  }
+  __syncthreads();
+  const int w = sh_w;
+  if (w < 0) return;
+  const double* src = best_x + (size_t)(first + w) * D;
+  for (int r = 0; r < gsize; ++r) {
+    if (r == w) continue;
+    double* dst = best_x + (size_t)(first + r) * D;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) dst[i] = src[i];
+  }
 }
 
 // K0: device-side SetRandomInitialPoints (abstract_solver.py:532-534): pop[c][j] = lo + (hi-lo)*u

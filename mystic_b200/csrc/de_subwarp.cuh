@@ -392,6 +392,21 @@ __global__ void __launch_bounds__(kSubWarps * 32)
   if (Q.pop_next != nullptr) Q.pop_next += row0 * P.dim;
   if (Q.e_cur != nullptr) Q.e_cur += row0;
   Q.e_next += row0;
+  if (P.stop != nullptr) {
+    // device-side termination of a batch of solvers: P.stop is the stop flag of island 0's RunState.  An island that has
+    // met its condition keeps the state it stopped with (abstract_ensemble_solver.py: a nested solver returns when ITS
+    // Solve() ends) while the others go on: its rows and energies pass to the next buffer unchanged.
+    const int* stop = reinterpret_cast<const int*>(reinterpret_cast<const char*>(P.stop) + isl * (int64_t)sizeof(RunState));
+    if (*stop) {
+      if (Q.pop_next != nullptr && Q.e_cur != nullptr) {
+        const int64_t n = P.np * P.dim, step = (int64_t)gridDim.x * blockDim.x;
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += step) Q.pop_next[t] = Q.pop_cur[t];
+        for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < P.np; t += step) Q.e_next[t] = Q.e_cur[t];
+      }
+      return;
+    }
+    Q.stop = nullptr;
+  }
   Q.best_x += isl * P.dim;
   Q.global_offset += row0;
   if (Q.r_donors != nullptr) {

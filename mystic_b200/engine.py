@@ -208,10 +208,44 @@ class DeviceEngine(object):
         return self._log_host[:n].numpy().copy(), bool(stopped.value)
 
     # ---- batch of independent solvers -------------------------------------------------------
-    def set_islands(self, n_islands):
-        """the rows become n_islands independent populations advanced by the same launches"""
+    def set_islands(self, n_islands, share_best_within=1):
+        """the rows become n_islands independent populations advanced by the same launches; with
+        share_best_within = w > 1, groups of w consecutive islands share their best member every generation
+        (a group = one population sharded over w ranks, on this GPU)"""
         check(lib.mb2_set_islands(self._ctx, int(n_islands)))
         self.n_islands = int(n_islands)
+        if share_best_within != 1:
+            check(lib.mb2_set_island_groups(self._ctx, int(share_best_within)))
+
+    def set_islands_termination(self, term, max_generations, max_evaluations):
+        """install a device-side termination condition for every island (after set_islands, before generation 0);
+        `term` as for run()"""
+        t = _native.Termination()
+        t.kind, t.lookback = int(term['kind']), int(term.get('lookback', 0))
+        t.tolerance, t.target, t.gtol = float(term.get('tolerance', 0.0)), float(term.get('target', 0.0)), float(term.get('gtol', 0.0))
+        t.term_generations = int(term.get('term_generations', -1))
+        t.term_evaluations = int(term.get('term_evaluations', -1))
+        t.max_generations = -1 if max_generations is None else int(max_generations)
+        t.max_evaluations = -1 if max_evaluations is None else int(max_evaluations)
+        t.generations, t.evaluations = 0, 0
+        check(lib.mb2_set_termination(self._ctx, ctypes.byref(t), None, 0))
+
+    def run_islands(self, max_steps):
+        """enqueue up to max_steps generations of every island (generation 0 first when it has not run), each island
+        logging and stopping on its own condition -> (records [n_islands, max_steps, dim+4], executed[n], stopped[n])"""
+        n = self.n_islands
+        shape = (n, int(max_steps), self.dim + 4)
+        if self._log is None or tuple(self._log.shape) != shape:
+            self._log = torch.empty(shape, dtype=torch.float64, device=self.device)
+            self._log_host = torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        check(lib.mb2_run(self._ctx, int(max_steps), self._log.data_ptr(), self._stream()))
+        done = np.zeros(n, dtype=np.int32)
+        stopped = np.zeros(n, dtype=np.int32)
+        check(lib.mb2_run_result_islands(self._ctx, done.ctypes.data_as(_native.c_int32_p), stopped.ctypes.data_as(_native.c_int32_p),
+                                         self._stream()))
+        self._log_host.copy_(self._log)
+        self._replay = None
+        return self._log_host.numpy().copy(), done, stopped.astype(bool)
 
     def read_islands(self):
         """-> (best_energy[n], best_index[n], n_inf[n], n_accepted[n], generation, bestSolution[n, dim]); synchronises"""

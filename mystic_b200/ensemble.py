@@ -6,8 +6,11 @@ The reference launches N nested solvers through `map` (abstract_ensemble_solver.
 nested solver gets `SetInitialPoints(x0_k)`, the strict range, and runs `Solve()` to ITS OWN
 termination; the ensemble then reports the nested solver with the lowest energy).  Here the N
 nested DifferentialEvolutionSolver2 populations live side by side in one device buffer and every
-generation of all of them is ONE launch (include/mystic_b200.h mb2_set_islands); termination is
-evaluated per nested solver on the host, a terminated one keeps the state it stopped with.
+generation of all of them is ONE launch (include/mystic_b200.h mb2_set_islands); a terminated nested
+solver keeps the state it stopped with while the others go on.  Conditions the device can evaluate
+(VTR, ChangeOverGeneration, NormalizedChangeOverGeneration, VTRChangeOverGeneration, EvaluationLimits and the
+nested solver's own limits) are tested per nested solver inside the argmin epilogue, 64 generations per host
+round trip (mb2_run / mb2_run_result_islands); anything else is evaluated on the host every generation.
 
     solver = BuckshotSolver(dim, npts=64)
     solver.SetNestedSolver(DifferentialEvolutionSolver2(dim, 40))      # instance or class
@@ -56,6 +59,8 @@ class _Member(object):
 
 
 class _EnsembleOfDE(object):
+    _batch_generations = 64   # generations per host round trip when the device can test the condition (0: every generation)
+
     def __init__(self, dim, npts, **kwds):
         self.nDim = int(dim)
         self._npts = int(npts)
@@ -194,38 +199,68 @@ class _EnsembleOfDE(object):
             eng.set_islands(S)     # S == 1 (e.g. LatticeSolver(dim >= 4) with the default nbins): one plain population
 
         self._members = [_Member(self, s) for s in range(S)]
-        active = list(range(S))
         term = self._termination
-        first = True
-        while active:
-            if first:
-                eng.eval_initial()
-            else:
-                eng.step()
-            if S > 1:
-                be, bi, ninf, nacc, gen, bx = eng.read_islands()
-            else:
-                r = eng.read_result()
-                be, bi, ninf, nacc, gen, bx = [r[0]], [r[1]], [r[2]], [r[3]], [r[4]], np.asarray(r[5]).reshape(1, D)
-            still = []
-            for s in active:
-                m = self._members[s]
-                m._fcalls[0] += NP - int(ninf[s])          # differential_evolution.py:601
-                m.bestEnergy = float(be[s])
-                m.bestSolution = bx[s].copy()
-                m.energy_history.append(m.bestEnergy)
-                m.solution_history.append(m.bestSolution)
-                msg = None
-                if term(m):
-                    msg = term(m, info=True)
-                elif m.evaluations >= self._maxfun or m.generations >= self._maxiter:   # abstract_solver.py:703-711
-                    msg = 'EvaluationLimits with %s' % {'evaluations': self._maxfun, 'generations': self._maxiter}
-                if msg:
-                    m.message = str(msg)
+
+        def absorb(m, be, ninf, bx):
+            """one generation of nested solver m -> its stop message or None (differential_evolution.py:601, 617;
+            abstract_solver.py:703-711)"""
+            m._fcalls[0] += NP - int(ninf)
+            m.bestEnergy = float(be)
+            m.bestSolution = np.array(bx, dtype=np.float64)
+            m.energy_history.append(m.bestEnergy)
+            m.solution_history.append(m.bestSolution)
+            if term(m):
+                return str(term(m, info=True))
+            if m.evaluations >= self._maxfun or m.generations >= self._maxiter:
+                return 'EvaluationLimits with %s' % {'evaluations': self._maxfun, 'generations': self._maxiter}
+            return None
+
+        desc = _termination.device_descriptor(term) if self._batch_generations else None
+        if desc is not None and S > 1 and hasattr(eng, 'run_islands'):
+            # every nested solver's condition is tested on the device; the host replays the batch log
+            eng.set_islands_termination(desc, self._maxiter, self._maxfun)
+            active = set(range(S))
+            while active:
+                recs, done, stopped = eng.run_islands(self._batch_generations)
+                progressed = False
+                for s in sorted(active):
+                    m = self._members[s]
+                    for k in range(int(done[s])):
+                        progressed = True
+                        rec = recs[s, k]
+                        msg = absorb(m, rec[0], rec[2], rec[4:4 + D])
+                        if msg:
+                            m.message = msg
+                            break
+                    if m.message:
+                        active.discard(s)
+                    elif stopped[s]:
+                        raise RuntimeError('nested solver %d stopped on the device but not on the host' % s)
+                if not progressed and active:
+                    raise RuntimeError('batched nested solvers made no progress')
+        else:
+            active = list(range(S))
+            first = True
+            while active:
+                if first:
+                    eng.eval_initial()
                 else:
-                    still.append(s)
-            active = still
-            first = False
+                    eng.step()
+                if S > 1:
+                    be, bi, ninf, nacc, gen, bx = eng.read_islands()
+                else:
+                    r = eng.read_result()
+                    be, bi, ninf, nacc, gen, bx = [r[0]], [r[1]], [r[2]], [r[3]], [r[4]], np.asarray(r[5]).reshape(1, D)
+                still = []
+                for s in active:
+                    m = self._members[s]
+                    msg = absorb(m, be[s], ninf[s], bx[s])
+                    if msg:
+                        m.message = msg
+                    else:
+                        still.append(s)
+                active = still
+                first = False
         # the nested solver with the lowest energy (abstract_ensemble_solver.py:465-478: `<=`, the later one wins ties)
         best = self._members[0]
         for m in self._members:

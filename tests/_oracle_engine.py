@@ -87,12 +87,32 @@ class OracleEngine(object):
         self.best_idx = int(best_index)
 
     # ---- batch of independent solvers: island i is shard i of the rows, without a best exchange
-    def set_islands(self, n):
+    def set_islands(self, n, share_best_within=1):
         n = int(n)
         if n < 1 or self.np_local % n:
             raise ValueError('%d rows do not split into %d equal populations' % (self.np_local, n))
+        if share_best_within < 1 or n % share_best_within:
+            raise ValueError('%d islands do not split into groups of %d' % (n, share_best_within))
         self.n_islands = n
+        self.island_group = int(share_best_within)
         self._isl = None
+
+    def _share(self):
+        """islands_share_best_kernel (mystic_b200/csrc/de_misc.cuh): the group's winner goes to every island"""
+        w = getattr(self, 'island_group', 1)
+        if w <= 1:
+            return
+        isl = self._islands()
+        for g0 in range(0, len(isl), w):
+            grp = [e for e in isl[g0:g0 + w] if e.best_idx >= 0]
+            if not grp:
+                continue
+            win = min(grp, key=lambda e: (e.state.bestEnergy, e.best_idx))
+            for e in isl[g0:g0 + w]:
+                if e is not win:
+                    e.state.bestEnergy = win.state.bestEnergy
+                    e.state.bestSolution = win.state.bestSolution.copy()
+                    e.best_idx = win.best_idx
 
     def _islands(self):
         if getattr(self, '_isl', None) is None:
@@ -140,6 +160,7 @@ class OracleEngine(object):
         if getattr(self, 'n_islands', 1) > 1:
             for e in self._islands():
                 e.eval_initial()
+            self._share()
             self.launches += 2
             return
         mode, lo, hi = self.bounds
@@ -153,6 +174,7 @@ class OracleEngine(object):
             for e in self._islands():
                 e.strategy, e.F, e.CR = self.strategy, self.F, self.CR
                 e.step()
+            self._share()
             self.launches += 2
             return
         st = self.state
@@ -203,6 +225,62 @@ class OracleEngine(object):
                 stopped = True
                 break
         return np.array(recs).reshape(len(recs), self.dim + 4), stopped
+
+    @staticmethod
+    def _met(term, hist, gens, evals, max_generations, max_evaluations):
+        """the termination rules of de_finalize_kernel (mystic_b200/csrc/de_misc.cuh)"""
+        g = int(term.get('lookback', 0))
+        lg, h1 = len(hist), hist[-1]
+        hg = (hist[-g] if g else hist[0]) if lg > g else h1
+        kind = term['kind']
+        met = False
+        if kind == 1:
+            met = abs(h1 - term['target']) <= term['tolerance']
+        elif kind == 2:
+            met = lg > g and ((hg - h1) <= term['tolerance'] or hg == h1)
+        elif kind == 3:
+            met = lg > g and (hg == h1 or 2.0 * (hg - h1) <= term['tolerance'] * (abs(hg) + abs(h1)) + 1e-20)
+        elif kind == 4:
+            met = (lg > g and ((hg - h1) <= term['gtol'] or hg == h1)) or abs(h1 - term['target']) <= term['tolerance']
+        elif kind == 5:
+            met = (term['term_evaluations'] >= 0 and evals >= term['term_evaluations']) or \
+                  (term['term_generations'] >= 0 and gens >= term['term_generations'])
+        if max_evaluations is not None and evals >= max_evaluations:
+            met = True
+        if max_generations is not None and gens >= max_generations:
+            met = True
+        return met
+
+    def set_islands_termination(self, term, max_generations, max_evaluations):
+        self._isl_term = (dict(term), max_generations, max_evaluations)
+        self._isl_run = [dict(hist=[], gens=0, evals=0, stopped=False) for _ in range(self.n_islands)]
+
+    def run_islands(self, max_steps):
+        """CPU twin of DeviceEngine.run_islands: every island logs and stops on its own condition"""
+        term, maxgen, maxfun = self._isl_term
+        isl = self._islands()
+        n = len(isl)
+        recs = np.zeros((n, max_steps, self.dim + 4))
+        done = np.zeros(n, dtype=np.int32)
+        for _ in range(max_steps):
+            for i, e in enumerate(isl):
+                r = self._isl_run[i]
+                if r['stopped']:
+                    continue
+                if e.state is None:
+                    e.eval_initial()
+                else:
+                    e.strategy, e.F, e.CR = self.strategy, self.F, self.CR
+                    e.step()
+                    r['gens'] += 1
+                st = e.state
+                recs[i, done[i]] = np.concatenate([[st.bestEnergy, float(e.best_idx), float(e.n_inf), float(e.n_acc)], st.bestSolution])
+                done[i] += 1
+                r['evals'] += e.np_local - e.n_inf
+                r['hist'].append(st.bestEnergy)
+                r['stopped'] = self._met(term, r['hist'], r['gens'], r['evals'], maxgen, maxfun)
+            self.launches += 2
+        return recs, done, np.array([r['stopped'] for r in self._isl_run])
 
     def pack_best(self):
         st = self.state

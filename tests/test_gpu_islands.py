@@ -93,13 +93,74 @@ def test_islands_reject_what_they_cannot_do():
         eng.set_islands(6)            # 5 members cannot supply 5 distinct donors besides the candidate
     eng.set_islands(3)
     eng.close()
-    wide = DeviceEngine(40, 200)
+    wide = DeviceEngine(40, 4000)
     wide.set_cost(models.rosen.cost_id, [])
     wide.set_islands(2)
-    wide.init_population(1, np.full(200, -1.), np.full(200, 1.))
+    wide.init_population(1, np.full(4000, -1.), np.full(4000, 1.))
     with pytest.raises(NativeError):
-        wide.eval_initial()           # rows of more than 128 dimensions
+        wide.eval_initial()           # the best member and a warp's rows no longer fit in shared memory
     wide.close()
+
+
+@pytest.mark.parametrize('D,strat,cost', [(200, 'Best1Exp', 'rosen'), (1024, 'Best1Bin', 'rosen'), (300, 'Rand1Exp', 'griewangk'),
+                                          (130, 'RandToBest1Bin', 'corana')])
+def test_islands_of_long_rows_equal_the_oracle_shards(D, strat, cost):
+    """batched solvers of more than 128 dimensions (a warp per row): every island equals the oracle's stand-alone shard"""
+    from mystic_b200 import models
+    from mystic_b200.engine import DeviceEngine
+    from tests._oracle_engine import OracleEngine
+    S, inp, seed = 3, 12, 0x1512 + D
+    lo, hi = np.full(D, -4.), np.full(D, 4.)
+    engs = []
+    for E in (DeviceEngine, OracleEngine):
+        e = E(S * inp, D)
+        e.set_cost(getattr(models, cost).cost_id)
+        e.set_bounds(orc.BOUNDS_CLAMP, lo, hi)
+        e.set_rng_philox(seed)
+        e.init_population(seed, lo, hi)
+        e.set_islands(S)
+        e.eval_initial()
+        engs.append(e)
+    for g in range(4):
+        for e in engs:
+            e.set_strategy(orc.STRATEGIES[strat][0], 0.8, 0.9)
+            e.step()
+        rd, ro = engs[0].read_islands(), engs[1].read_islands()
+        assert np.array_equal(engs[0].population(), engs[1].population()), g
+        assert np.array_equal(rd[5], ro[5]) and np.array_equal(rd[2], ro[2]) and np.array_equal(rd[3], ro[3])
+        scale = np.maximum(np.abs(ro[0]), (engs[1].population() ** 2).sum(axis=1).max() / 4000. + 2.0 if cost == 'griewangk' else 0.0)
+        assert (np.abs(rd[0] - ro[0]) <= 1e-12 * scale).all()
+    engs[0].close()
+
+
+@pytest.mark.parametrize('term', [('VTR', 1e-4), ('ChangeOverGeneration', 1e-4, 8), ('EvaluationLimits', None, 1500)])
+def test_device_side_termination_of_nested_solvers(term):
+    """BuckshotSolver with the condition tested inside the argmin epilogue (64 generations per host round trip) against
+    the per-generation host loop on the device and against the oracle engine: same stop generations, messages, members"""
+    import random
+    from mystic_b200 import DifferentialEvolutionSolver2, models, termination
+    from mystic_b200.ensemble import BuckshotSolver
+    from tests._oracle_engine import OracleEngine
+    runs = []
+    for engine, batch in ((None, 64), (None, 0), (OracleEngine, 64)):
+        random.seed(21)
+        s = BuckshotSolver(4, 12, engine=engine, seed=99)
+        s._batch_generations = batch
+        s.SetNestedSolver(DifferentialEvolutionSolver2(4, 24, strategy='Best1Exp'))
+        s.SetStrictRanges([-2.] * 4, [2.] * 4)
+        s.SetEvaluationLimits(generations=150)
+        s.Solve(models.rosen, getattr(termination, term[0])(*term[1:]))
+        runs.append(s)
+    batched, stepped, ref = runs
+    for other in (stepped, ref):
+        assert batched._all_iters == other._all_iters and batched._all_evals == other._all_evals
+        assert batched.Terminated(info=True, all=True) == other.Terminated(info=True, all=True)
+        for a, b in zip(batched._all_bestSolution, other._all_bestSolution):
+            assert np.array_equal(a, b)
+        assert np.allclose(batched._all_bestEnergy, other._all_bestEnergy, rtol=1e-12, atol=0)
+    assert len(set(batched._all_iters)) > 1 or term[0] == 'EvaluationLimits'
+    # the batched run synchronises once per 64 generations: far fewer host round trips than generations
+    assert batched._engine.launch_count() < stepped._engine.launch_count() + 2 * 64 + 16
 
 
 def test_buckshot_on_device_equals_the_oracle_ensemble():
@@ -125,5 +186,42 @@ def test_buckshot_on_device_equals_the_oracle_ensemble():
         assert np.array_equal(a, b)
     assert np.allclose(dev._all_bestEnergy, ref._all_bestEnergy, rtol=1e-12, atol=0)
     assert np.array_equal(dev.bestSolution, ref.bestSolution) and dev.Terminated(info=True) == ref.Terminated(info=True)
-    # the energy fill of the upload, then ONE fused launch + one epilogue per generation for all members together
-    assert dev._engine.launch_count() == 1 + 2 * (max(dev._all_iters) + 1)
+    # the energy fill of the upload, then ONE fused launch + one epilogue per generation for all members together, in
+    # batches of 64 generations (arm + status kernels per batch; the launches after the last stop copy rows through)
+    nb = -(-(max(dev._all_iters) + 1) // 64)
+    assert dev._engine.launch_count() == 1 + nb * (2 * 64 + 2)
+
+
+def test_islands_sharing_their_best_are_a_sharded_population():
+    """mb2_set_island_groups: groups of w islands whose best member is merged every generation equal the oracle's
+    emulation of a population sharded over w ranks (the emulation tests/dist_gpu_check.py holds real ranks to)"""
+    import numpy as np
+    from mystic_b200 import models
+    from mystic_b200.engine import DeviceEngine
+    from oracle import de_oracle as orc
+    from tests._oracle_engine import OracleEngine
+    for strat, cost, D, inp, w, groups, mode in (('Best1Exp', 'rosen', 6, 10, 4, 3, orc.BOUNDS_CLAMP),
+                                                 ('RandToBest1Bin', 'griewangk', 30, 12, 2, 5, orc.BOUNDS_REJECT),
+                                                 ('Best1Bin', 'rosen', 64, 16, 8, 2, orc.BOUNDS_CLAMP)):
+        NP, seed = inp * w * groups, 0x15A + D
+        lo, hi = np.full(D, -3.), np.full(D, 3.)
+        engs = []
+        for E in (DeviceEngine, OracleEngine):
+            e = E(NP, D)
+            e.set_cost(getattr(models, cost).cost_id)
+            e.set_bounds(mode, lo, hi)
+            e.set_rng_philox(seed)
+            e.init_population(seed, lo, hi)
+            e.set_islands(w * groups, share_best_within=w)
+            e.eval_initial()
+            engs.append(e)
+        for g in range(6):
+            for e in engs:
+                e.set_strategy(orc.STRATEGIES[strat][0], 0.8, 0.9)
+                e.step()
+            rd, ro = engs[0].read_islands(), engs[1].read_islands()
+            assert np.array_equal(engs[0].population(), engs[1].population()), (strat, g)
+            assert np.array_equal(rd[5], ro[5]) and np.array_equal(rd[1], ro[1]), (strat, g)
+            assert np.allclose(rd[0], ro[0], rtol=1e-12, atol=0)
+            assert (rd[0].reshape(groups, w) == rd[0].reshape(groups, w)[:, :1]).all()   # one best per group
+        engs[0].close()

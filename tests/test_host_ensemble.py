@@ -110,3 +110,24 @@ def test_an_ensemble_of_one_nested_solver_runs(make):
     assert len(ens._all_iters) == 1 and 1 <= ens.generations <= 25
     assert ens.bestEnergy == ens._all_bestEnergy[0] and len(ens.bestSolution) == 4
     assert ens.Terminated(info=True)
+
+
+@pytest.mark.parametrize('term', [('VTR', 1e-3), ('ChangeOverGeneration', 1e-4, 8), ('NormalizedChangeOverGeneration', 1e-3, 6),
+                                  ('EvaluationLimits', None, 900)])
+def test_batched_termination_equals_the_per_generation_loop(term):
+    """conditions the device can test run 64 generations per host round trip, every nested solver stopping on its own:
+    same stop generations, messages, histories and best members as testing on the host after every generation"""
+    runs = []
+    for batch in (64, 7, 0):
+        random.seed(21)
+        ens = BuckshotSolver(3, 7, engine=OracleEngine, seed=5)
+        ens._batch_generations = batch
+        ens.SetNestedSolver(DifferentialEvolutionSolver2(3, 20, strategy='Best1Exp'))
+        ens.SetStrictRanges([-2.] * 3, [2.] * 3)
+        ens.SetEvaluationLimits(generations=150)
+        cond = getattr(termination, term[0])(*term[1:])
+        ens.Solve(models.rosen, cond)
+        runs.append((ens._all_iters, ens._all_evals, ens._all_bestEnergy, [list(x) for x in ens._all_bestSolution],
+                     ens.Terminated(info=True, all=True), [m.energy_history for m in ens._members]))
+    assert runs[0] == runs[2] and runs[1] == runs[2]
+    assert len(set(runs[0][0])) > 1 or term[0] == 'EvaluationLimits'      # the nested solvers stop at different generations
