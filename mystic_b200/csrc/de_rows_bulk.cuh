@@ -29,9 +29,6 @@ namespace mb2 {
 #ifndef MB2_RB_MAXWARPS
 #define MB2_RB_MAXWARPS 24
 #endif
-#ifndef MB2_RB_BATCH_DRAWS
-#define MB2_RB_BATCH_DRAWS 1
-#endif
 constexpr int kBulkRowsMaxWarps = MB2_RB_MAXWARPS;  // 24 warps: 80 registers per thread (no spills)
 constexpr int kBulkRowsMaxStages = 4;
 
@@ -112,11 +109,6 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
   const int64_t gw = (int64_t)blockIdx.x * wpc + warp;
   const int64_t nw = (int64_t)gridDim.x * wpc;
 
-  // draws of the next stages, made 16 rows at a time (strategies with two donor-stream blocks per row; one stage
-  // per warp, so that the warp's stages are ch, ch + nw, ... in issue order)
-  constexpr bool kBatchDraws = ((K + 2) / 2 == 2) && MB2_RB_BATCH_DRAWS;
-  uint64_t dc_even = 0, dc_odd = 0;
-  int dc_left = 0;  // stages still served by the cached words
   // ---- draws + loads of the rows of chunk `ch` into the stage at `st` (whole warp)
   auto issue = [&](int64_t ch, unsigned char* st, uint64_t* bar) {
     const int64_t c = ch * RPW + grp;
@@ -129,35 +121,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
       bulk_g2s(st, P.pop_cur + ch * RPW * D, nlive * row_bytes, bar);
     }
     RowDraws<K> dr;
-    if (kBatchDraws && !P.replay) {
-      // one Philox evaluation of the warp makes the draws of 16 rows = 16 / RPW consecutive stages of this warp
-      // (lane l: block l & 1 of row (l >> 1) & (RPW - 1) of stage (l >> 1) / RPW ahead); same counters and words
-      // as rows_draw
-      if (dc_left == 0) {
-        const int64_t chl = ch + (int64_t)((lane >> 1) / RPW) * nw;  // the warp issues chunks ch, ch + nw, ... whatever the ring depth
-        int64_t cr = chl * RPW + ((lane >> 1) & (RPW - 1));
-        if (cr >= P.np) cr = P.np - 1;  // idle groups shadow the last row, as below
-        const u32x4 v = philox4x32_10((uint32_t)(lane & 1), (uint32_t)(P.global_offset + cr), P.generation, STREAM_DONORS, P.key0, P.key1);
-        dc_even = ((uint64_t)v.x << 32) | v.y;
-        dc_odd = ((uint64_t)v.z << 32) | v.w;
-        dc_left = 16 / RPW;
-      }
-      const int src = 2 * ((16 / RPW - dc_left) * RPW + grp);
-      uint64_t rw[4];
-      rw[0] = __shfl_sync(0xffffffffu, dc_even, src);
-      rw[1] = __shfl_sync(0xffffffffu, dc_odd, src);
-      rw[2] = __shfl_sync(0xffffffffu, dc_even, src + 1);
-      rw[3] = __shfl_sync(0xffffffffu, dc_odd, src + 1);
-      --dc_left;
-      int64_t r64[K];
-      uint32_t xword;
-      resolve_donors<K>(rw, cc, P.np, D, r64, &dr.nstart, &xword);
-#pragma unroll
-      for (int j = 0; j < K; ++j) dr.r[j] = (int)r64[j];
-      dr.L = exp_length_v2(xword, P.xlen, D);
-    } else {
-      rows_draw<LPR, K>(P, XOVER_EXP, cc, sub, gbase, dr);
-    }
+    rows_draw<LPR, K>(P, XOVER_EXP, cc, sub, gbase, dr);
     const int q0 = dr.nstart >> 2;
     int nq = (dr.L > 0) ? (((dr.nstart + dr.L - 1) >> 2) - q0 + 1) : 0;
     if (nq > NQ) nq = NQ;  // a full-length window that starts inside a chunk: each chunk once
