@@ -268,7 +268,7 @@ typedef void (*ExpTmaKernel)(const StepParams, int, int, int, int);
 namespace mb2 {
 StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
-ExpTmaKernel get_exp_tma_kernel(int cost, int gwarps);
+ExpTmaKernel get_exp_tma_kernel(int cost, int gwarps, int threads);
 ThreadRowKernel get_small_kernel(int cost);
 ThreadRowKernel get_cheb_mma_kernel(int ksteps, bool resid);
 StepKernel get_datafit_ldg_kernel(int base, int xover, int cost);
@@ -351,6 +351,11 @@ bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
   int gw = 1;
   while (gw < 8 && g * (gw * 2) * 32 <= kTmaMaxThreads && (gw * 2) * 32 * 8 <= dim) gw <<= 1;
   if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
+  // One-warp groups (D < 512): 16 groups in a 512-thread CTA -- the 128-register build; the 64 registers of a
+  // 1024-thread CTA make the griewangk body spill -- with the ring as deep as shared memory allows.  B200 sweep at
+  // BASELINE config 5 (profiles/README.md): 16 x 1 warp x 2 stages 3.25-3.32 ms, 24 x 1 x 1 (768 threads, 80 registers)
+  // 3.35-3.37, 32 x 1 x 1 (round 1's choice) 3.57-3.59.
+  if (gw == 1 && g > 16) g = 16;
   int st = 1;
   while (st < kTmaMaxStages && (size_t)g * (st * 2) <= slots) st *= 2;
   const int eg = env_int("MB2_TMA_GROUPS", 0), ew = env_int("MB2_TMA_GWARPS", 0), es = env_int("MB2_TMA_STAGES", 0);
@@ -586,7 +591,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   int xcap = 0;
   if (mode == MODE_STEP && s.xover == XOVER_EXP && vec && env_int("MB2_TMA_EXP", 1) != 0 && !datafit && !cheb_mma &&
       ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, &tg, &tw, &ts, &xcap, &tsmem))
-    kx = get_exp_tma_kernel(c->cost, tw);
+    kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32);
 
   int wpc, smem;
   int occ = 0;

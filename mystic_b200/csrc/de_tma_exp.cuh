@@ -122,6 +122,11 @@ __global__ void __launch_bounds__(MAXT, 1)
   // Draws of candidate c and its loads into stage s.  Called by the whole leader WARP of the group
   // (tig < 32): the draws are collective, lane 0 loads the parent row, lanes 1..k / 9..8+k the first /
   // wrapped segment of donor lane-1 / lane-9.
+  // The group's rows are issued in the order g0, g0 + ng, ...: one Philox evaluation of the leader warp makes the
+  // donor-stream blocks of the next 10 of them (lane l: block l % 3 of the row l / 3 ahead; three blocks cover
+  // every donor count), handed out by shuffle -- same counters and words as draw_donors<K>.
+  uint64_t dc_even = 0, dc_odd = 0;
+  int dc_pos = 10;  // next cached row (10: the cache is empty)
   auto issue = [&](int64_t c, int s) {
     uint64_t* bar = bars + s;
     // the parent row does not depend on the draws: its copy flies while they are made
@@ -132,7 +137,32 @@ __global__ void __launch_bounds__(MAXT, 1)
     int64_t r[5];
     int nstart;
     uint32_t xword = 0;
-    draw_donors_warp_rt(P, kdon, c, lane, r, &nstart, &xword);
+    if (P.replay) {
+      draw_donors_warp_rt(P, kdon, c, lane, r, &nstart, &xword);
+    } else {
+      if (dc_pos == 10) {
+        const int64_t cr = c + (int64_t)(lane / 3) * ng;  // rows past the end (and lanes 30, 31): evaluated, never handed out
+        const u32x4 v = philox4x32_10((uint32_t)(lane % 3), (uint32_t)(P.global_offset + cr), P.generation, STREAM_DONORS, P.key0, P.key1);
+        dc_even = ((uint64_t)v.x << 32) | v.y;
+        dc_odd = ((uint64_t)v.z << 32) | v.w;
+        dc_pos = 0;
+      }
+      uint64_t w[6];
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        w[2 * b] = __shfl_sync(0xffffffffu, dc_even, 3 * dc_pos + b);
+        w[2 * b + 1] = __shfl_sync(0xffffffffu, dc_odd, 3 * dc_pos + b);
+      }
+      ++dc_pos;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) r[j] = 0;
+      switch (kdon) {
+        case 2: resolve_donors<2>(w, c, P.np, D, r, &nstart, &xword); break;
+        case 3: resolve_donors<3>(w, c, P.np, D, r, &nstart, &xword); break;
+        case 4: resolve_donors<4>(w, c, P.np, D, r, &nstart, &xword); break;
+        default: resolve_donors<5>(w, c, P.np, D, r, &nstart, &xword); break;
+      }
+    }
     const int L = P.replay ? exp_length_replay(P.r_uni + c * (int64_t)(D + 1), D, P.CR, lane) : exp_length_v2(xword, P.xlen, D);
     // 16-byte aligned cover of the window [nstart, nstart+L) mod D: [a1, a1+n1) and, wrapped, [0, n2)
     int a1 = nstart & ~1;

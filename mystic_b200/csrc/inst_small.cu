@@ -8,8 +8,13 @@ typedef void (*TmaKernel)(const StepParams, int);
 typedef void (*ThreadRowKernel)(const StepParams, int, int, int);
 TmaKernel get_tma_kernel_512(int cost, int gwarps);
 TmaKernel get_tma_kernel_1024(int cost, int gwarps);
+TmaKernel get_tma_kernel_768(int cost, int gwarps);
 
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads) {
+  if (threads > 512 && threads <= 768) {
+    TmaKernel k = get_tma_kernel_768(cost, gwarps);
+    if (k != nullptr) return k;
+  }
   return threads > 512 ? get_tma_kernel_1024(cost, gwarps) : get_tma_kernel_512(cost, gwarps);
 }
 
