@@ -619,7 +619,8 @@ def shard_parity(rig):
     from oracle import de_oracle as orc
     from tests.dist_gpu_check import emulate
     ok = True
-    for strategy, cost, D, NP, lo, hi in (('Best1Bin', 'rosen', 256, 64 * rig.world + 3, -5., 5.),
+    # (populations larger than the dimension: the solver raises NP to max(NP, dim) like the reference does)
+    for strategy, cost, D, NP, lo, hi in (('Best1Bin', 'rosen', 256, 64 * rig.world + 259, -5., 5.),
                                           ('Rand1Exp', 'corana', 64, 96 * rig.world + 5, -1000., 1000.)):
         seed, gens = 0xD15C0 + D, 4
         s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=seed, distributed=True, strategy=strategy)

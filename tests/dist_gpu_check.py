@@ -70,7 +70,9 @@ def main():
                                                   # sharded runs of the bulk-copy kernels: short rows (de_rows_bulk.cuh) and
                                                   # long rows with the exchanged best member (de_tma_exp.cuh)
                                                   ('Rand1Exp', 'corana', 64, 2003, orc.BOUNDS_CLAMP, -1000., 1000.),
-                                                  ('Best1Exp', 'rosen', 200, 303, orc.BOUNDS_CLAMP, -5., 5.)]:
+                                                  ('Best1Exp', 'rosen', 200, 303, orc.BOUNDS_CLAMP, -5., 5.),
+                                                  # the headline kernel (de_tma.cuh, one-warp groups with a two-stage ring) on shards
+                                                  ('Best1Bin', 'rosen', 256, 64 * world + 259, orc.BOUNDS_CLAMP, -5., 5.)]:
         seed, gens = 0xD15C0 + D, 6
         s = DifferentialEvolutionSolver2(D, NP, rng='philox', seed=seed, distributed=True, strategy=strategy)
         if os.environ.get('MB2_EXCHANGE', 'peer') == 'peer':
