@@ -12,7 +12,8 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 @pytest.mark.parametrize('script,expect', [('rosenbrock3.py', 'generations 39, evaluations 1600'),
                                            ('corana_penalty.py', 'bestEnergy'),
                                            ('chebyshev8_dmma.py', 'fitted'),
-                                           ('sharded_griewangk.py', '1 GPUs')])
+                                           ('sharded_griewangk.py', '1 GPUs'),
+                                           ('lagrange_multipliers.py', 'constraints met')])
 def test_example_runs(script, expect):
     proc = subprocess.run([sys.executable, os.path.join(REPO, 'examples', script)], cwd=REPO, stdout=subprocess.PIPE,
                           stderr=subprocess.STDOUT, universal_newlines=True, timeout=280,

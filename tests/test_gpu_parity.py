@@ -690,6 +690,16 @@ def test_abi_rejects_malformed_requests():
     with pytest.raises(NativeError, match='mb2_eval_initial must run before'):
         eng.set_cost(models.rosen.cost_id, ())
         eng.step()
+    with pytest.raises(NativeError, match='unknown penalty type'):
+        eng.set_penalty([9], [[1., 1., 1.]], [0.], [1.])
+    with pytest.raises(NativeError, match='do not split into groups'):
+        eng.set_islands(4, share_best_within=3)
+    eng.set_islands(1)
+    with pytest.raises(NativeError, match='no batch of solvers'):
+        import ctypes
+        from mystic_b200._native import check, lib
+        a = (ctypes.c_int32 * 4)()
+        check(lib.mb2_run_result_islands(eng._ctx, a, a, None))
     eng.set_cost(models.ellipsoid.cost_id, ())       # any number of variables
     eng.set_rng_philox(1)
     eng.init_population(1, np.full(3, -1.), np.full(3, 1.))
