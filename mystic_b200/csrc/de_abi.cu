@@ -592,6 +592,14 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   if (mode == MODE_STEP && s.xover == XOVER_EXP && vec && env_int("MB2_TMA_EXP", 1) != 0 && !datafit && !cheb_mma &&
       ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, &tg, &tw, &ts, &xcap, &tsmem))
     kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32);
+  // generation 0 of long rows is a read-clip-evaluate-write stream: the same staged kernel without draws or donors
+  // (every strategy; the warp-per-row kernel needed 0.31 ms for it at BASELINE config 2)
+  int gen0_k = 0;
+  if (mode == MODE_GEN0 && vec && env_int("MB2_TMA_GEN0", 1) != 0 && !datafit && !cheb_mma && ks == nullptr && kw == nullptr &&
+      out_rows != nullptr && exp_tma_geometry(c->dim, 2, 0.0, &tg, &tw, &ts, &xcap, &tsmem)) {
+    kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32);
+    gen0_k = 2;
+  }
 
   int wpc, smem;
   int occ = 0;
@@ -670,7 +678,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   else if (kt != nullptr)
     kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
   else if (kx != nullptr)
-    kx<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts, xcap, s.base, s.k);
+    kx<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts, xcap, gen0_k ? BASE_RAND1 : s.base, gen0_k ? gen0_k : s.k);
   else
     k<<<(unsigned)grid, wpc * 32, smem, stream>>>(P);
   CUDA_TRY(cudaGetLastError());

@@ -134,6 +134,19 @@ __global__ void __launch_bounds__(MAXT, 1)
       mbar_expect_tx_only(bar, row_bytes);
       bulk_g2s(stage_row(s), P.pop_cur + c * D, row_bytes, bar);
     }
+    if (P.mode == MODE_GEN0) {  // generation 0: the row is only clipped and evaluated -- no draws, no donors
+      if (leader) {
+        ExpStageMeta* m = stage_meta(s);
+        m->nstart = 0;
+        m->L = 0;
+        m->fits = 0;
+        m->a1 = 0;
+        m->n1 = 0;
+        mbar_expect_tx(bar, 0u);  // the arrive
+      }
+      __syncwarp();
+      return;
+    }
     int64_t r[5];
     int nstart;
     uint32_t xword = 0;
@@ -211,8 +224,9 @@ __global__ void __launch_bounds__(MAXT, 1)
   int64_t g_best_idx = INT64_MAX;
   unsigned long long g_ninf = 0, g_nacc = 0;
   const bool uni_b = P.bounds_uniform != 0;
+  const bool gen0 = (P.mode == MODE_GEN0);
   // rows of this generation are known to lie inside the strict range: only the window can leave it
-  const bool window_only = (P.bounds_mode == BOUNDS_NONE) || (P.rows_in_range != 0);
+  const bool window_only = gen0 || (P.bounds_mode == BOUNDS_NONE) || (P.rows_in_range != 0);
 
   int s = 0;
   unsigned parity = 0;
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     double* s_row = stage_row(s);
     double* s_undo = stage_undo(s);
     const ExpStageMeta* meta = stage_meta(s);
-    const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
+    const double e_old = gen0 ? CUDART_INF : __ldg(P.e_cur + c);  // in flight while the group waits for its rows
 
     group_wait_stage(grp, bars + s, parity);
     const int nstart = meta->nstart, L = meta->L, a1 = meta->a1, n1 = meta->n1;
@@ -257,6 +271,16 @@ __global__ void __launch_bounds__(MAXT, 1)
       if (fits) s_undo[w] = t;
       s_row[i] = x;
     }
+    if (gen0 && P.bounds_mode != BOUNDS_NONE) {
+      // generation 0 clips the initial population into the strict range (differential_evolution.py:516-520)
+      for (int i = tig; i < D; i += gthreads) {
+        const double l = uni_b ? P.lo_s : __ldg(P.lo + i);
+        const double h = uni_b ? P.hi_s : __ldg(P.hi + i);
+        const double x = fmin(fmax(s_row[i], l), h);
+        oob |= (x < l) || (x > h);
+        s_row[i] = x;
+      }
+    }
     if (!window_only) {
       // rows this context has not checked against the range: the reference clamps / tests every
       // element of the trial, untouched ones included
@@ -286,7 +310,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     }
 
     const bool acc = E < e_old;
-    if (!acc) {
+    if (!acc && !gen0) {  // (generation 0 keeps the clipped row whatever its energy)
       // every thread has read the trial (costs without a group reduction and the capture end
       // without a barrier) before a rejected one is undone
       if (COST == COST_CORANA || COST == COST_ZIMMERMANN || P.cap_trial != nullptr) group_sync(grp);
