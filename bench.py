@@ -131,14 +131,19 @@ def ncu_traffic(workload):
     return None, None
 
 
-def algorithmic_bytes_per_candidate(w):
+def algorithmic_bytes_per_candidate(w, in_place=False, accept=0.0):
     """population double buffered; parent + k donor rows read, new row written,
-    energy read + written.  Exponential crossover reads only E[L] donor elements."""
+    energy read + written.  Exponential crossover reads only E[L] donor elements.
+    in_place (the reference's own population + trialSolution layout, mb2_set_commit_mode): a rejected row is not
+    written -- parent + donors read, energy read + written, and the accepted fraction `accept` of the rows written
+    once; what de_commit_accepted_kernel moves on top of that (an accepted row read and written once more, the
+    energies scanned) is overhead of the implementation and not counted."""
     D, k, CR = w['dim'], w['k'], w['CR']
+    row_out = 8.0 * D * (accept if in_place else 1.0)
     if w['strategy'] in BIN_STRATEGIES:
-        return 8.0 * D * (k + 2) + 16.0
+        return 8.0 * D * (k + 1) + row_out + 16.0
     EL = float(D) if CR >= 1.0 else CR * (1.0 - CR ** D) / (1.0 - CR)
-    return 16.0 * D + 8.0 * k * EL + 16.0
+    return 8.0 * D + row_out + 8.0 * k * EL + 16.0
 
 
 def algorithmic_flops_per_candidate(w):
@@ -486,11 +491,13 @@ def device_leg(rig, name, w):
     launches0 = eng.launch_count()
     dev_ms = timed(steps)                        # the reported value: K generations under sustained load
     launches = eng.launch_count() - launches0
+    in_place = eng.last_commit_in_place()
     res = s._engine.read_result()
     clocks = sampler.stop() if sampler else None
     out = dict(name=name, w=w, NP_local=NP_local, NP_global=NP_global, dev_ms=dev_ms, burst_ms=burst_ms, launches=int(launches),
-               clocks=clocks, grid=grid, block=block, smem=smem, family=family,
-               inf_fraction=res[2] / float(NP_local), accept_fraction=res[3] / float(NP_local))
+               clocks=clocks, grid=grid, block=block, smem=smem, family=family, in_place=in_place,
+               inf_fraction=res[2] / float(NP_global if distributed else NP_local),
+               accept_fraction=res[3] / float(NP_global if distributed else NP_local))   # (sharded: the counters are sums over the shards)
     del s, eng
     gc.collect()
     torch.cuda.empty_cache()
@@ -500,7 +507,9 @@ def device_leg(rig, name, w):
 def roofline_of(rig, leg):
     w, name, NP_local = leg['w'], leg['name'], leg['NP_local']
     peaks = rig.peaks
-    bpc = algorithmic_bytes_per_candidate(w)
+    in_place = bool(leg.get('in_place'))
+    bpc = algorithmic_bytes_per_candidate(w, in_place, leg['accept_fraction'])
+    bpc_db = algorithmic_bytes_per_candidate(w)   # SURVEY 8(d)'s double-buffer figure (round 1's denominator)
     step_s = leg['dev_ms'] * 1e-3 / rig.steps
     burst_s = leg['burst_ms'] * 1e-3 / rig.steps
     achieved = bpc * NP_local / step_s / 1e9
@@ -512,7 +521,17 @@ def roofline_of(rig, leg):
                 'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': rig.peaks_src, 'frac_burst': bpc * NP_local / burst_s / 1e9 / peaks['hbm_gbs'],
                 'algorithmic_bytes_per_candidate': bpc, 'algorithmic_bytes_per_launch': bpc * NP_local,
-                'kernel': 'fused generation kernel (%s) + de_finalize_kernel, per generation, per GPU' % leg['family']}
+                'commit': 'in_place' if in_place else 'double_buffer',
+                'kernel': 'fused generation kernel (%s)%s + de_finalize_kernel, per generation, per GPU'
+                          % (leg['family'], ' + de_commit_accepted_kernel' if in_place else '')}
+    if in_place:
+        # continuity with round 1 / SURVEY 8(d): the same step time against the bytes a double-buffered generation
+        # would move (every row written); above 1 = faster than that design can be
+        roofline['double_buffer_model'] = {'algorithmic_bytes_per_candidate': bpc_db,
+                                           'frac': bpc_db * NP_local / step_s / 1e9 / peaks['hbm_gbs']}
+        # the committed ncu summaries are of the double-buffered kernel unless their name says otherwise
+        if traffic_src and 'inplace' not in traffic_src:
+            roofline['traffic_note'] = 'captured with the double buffer (every row written)'
     flops = algorithmic_flops_per_candidate(w)
     if flops:
         # the Chebyshev / polynomial contraction is FP64-pipe bound; DMMA and DFMA share that pipe on B200, so the

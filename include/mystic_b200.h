@@ -326,6 +326,21 @@ enum mb2_kernel_family_id {
 };
 int mb2_kernel_family(mb2_ctx* ctx);
 
+/* How a generation's rows leave the fused kernel.  The reference keeps ONE population and a trialSolution
+ * list and copies the accepted trials over their parents after the whole generation has been evaluated
+ * (mystic/differential_evolution.py:603-609).  MB2_COMMIT_IN_PLACE is that layout on the device: the kernels
+ * of rows of 16 dimensions and more (MB2_KERNEL_TMA_BIN / TMA_EXP / ROWS_BULK / ROWS / WARP_PER_ROW) write only
+ * ACCEPTED trials to the other buffer and de_commit_accepted_kernel moves them over their parents once every
+ * row has read its donors; a rejected row is never written.  MB2_COMMIT_DOUBLE_BUFFER writes every selected row
+ * to the other buffer and swaps (the only mode of the rows-per-warp, thread-per-row, DMMA and batched kernels).  MB2_COMMIT_AUTO (default) commits in place while the
+ * accepted fraction of the last generation the host read back is below 0.30 -- in place moves
+ * (1 + k + 3a) rows per candidate, the double buffer (2 + k).  Results are bit-identical in every mode.
+ * The environment variable MB2_COMMIT_MODE (0, 1, 2) overrides the context's setting. */
+enum mb2_commit_mode_id { MB2_COMMIT_AUTO = 0, MB2_COMMIT_DOUBLE_BUFFER = 1, MB2_COMMIT_IN_PLACE = 2 };
+int mb2_set_commit_mode(mb2_ctx* ctx, int mode);
+/* 1 when the last generation was committed in place, 0 when the buffers were swapped */
+int mb2_last_commit_in_place(mb2_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,6 +20,7 @@ EXPORTS = [
     'mb2_launch_info', 'mb2_launch_count', 'mb2_kernel_family', 'mb2_selftest_division', 'mb2_selftest_cosine', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
     'mb2_set_termination', 'mb2_run', 'mb2_run_result', 'mb2_set_islands', 'mb2_read_islands', 'mb2_exchange_open', 'mb2_exchange_connect', 'mb2_exchange_connected', 'mb2_exchange_reset', 'mb2_exchange_best',
     'mb2_probe_fp64_peak', 'mb2_set_penalty_ex', 'mb2_set_island_groups', 'mb2_run_result_islands',
+    'mb2_set_commit_mode', 'mb2_last_commit_in_place',
 ]
 
 
@@ -92,6 +93,8 @@ def _load():
         'mb2_run': (ctypes.c_int, [vp, i32, vp, vp]),
         'mb2_run_result': (ctypes.c_int, [vp, c_int32_p, c_int32_p, vp]),
         'mb2_probe_fp64_peak': (ctypes.c_int, [ctypes.c_int, i32, c_double_p, c_double_p, vp]),
+        'mb2_set_commit_mode': (ctypes.c_int, [vp, ctypes.c_int]),
+        'mb2_last_commit_in_place': (ctypes.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)  # AttributeError if the library does not export it

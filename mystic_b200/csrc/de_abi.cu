@@ -189,6 +189,14 @@ struct mb2_ctx {
   DeviceState* h_st_isl = nullptr;  // pinned
   double* h_best_isl = nullptr;     // pinned
   int xchg_connected = 0;
+  int counts_global = 0;  // DeviceState counters are sums over the shards (peer exchange or mb2_merge_best)
+  // how a generation leaves the fused kernel: every row into the other buffer + swap (double buffer), or accepted
+  // rows only + de_commit_accepted_kernel (in place); auto = in place while the accepted fraction the host last
+  // saw is below kInPlaceMaxAccept (a rejected row then costs no write, an accepted one three row transfers)
+  int commit_mode = MB2_COMMIT_AUTO;
+  double acc_hint = -1.0;  // accepted fraction of the last generation read back (-1: none yet)
+  int last_sparse = 0;     // the last fused launch wrote accepted rows only
+  int run_sparse = 0;      // ... and so did the launches of the current batch (mb2_run)
   int xchg_no_adopt = 0;  // after mb2_exchange_reset: open a fresh mailbox
   int* h_xerr = nullptr;  // pinned
 };
@@ -333,6 +341,21 @@ TmaKernel pick_tma_kernel(int cost, int gwarps, int threads) { return get_tma_ke
 int env_int(const char* name, int dflt) {
   const char* v = getenv(name);
   return (v && *v) ? atoi(v) : dflt;
+}
+
+// in-place commit pays while fewer than a third of the trials are accepted: per row it moves
+// (1 + k + a) rows + 2a in the commit against (2 + k) with the double buffer
+constexpr double kInPlaceMaxAccept = 0.30;
+bool want_in_place(const mb2_ctx* c) {
+  int mode = env_int("MB2_COMMIT_MODE", -1);
+  if (mode < MB2_COMMIT_AUTO || mode > MB2_COMMIT_IN_PLACE) mode = c->commit_mode;
+  if (mode == MB2_COMMIT_DOUBLE_BUFFER) return false;
+  if (mode == MB2_COMMIT_IN_PLACE) return true;
+  return c->acc_hint < kInPlaceMaxAccept;  // (no generation read back yet: in place)
+}
+void note_accepted(mb2_ctx* c, int64_t n_acc) {
+  const int64_t denom = (c->xchg_connected || c->counts_global) ? c->np_global : c->np;
+  c->acc_hint = (denom > 0 && n_acc >= 0) ? (double)n_acc / (double)denom : -1.0;
 }
 
 // Ring geometry of the TMA kernel: groups per CTA, warps per group, stages per group, dynamic
@@ -498,6 +521,7 @@ int launch_step_islands(mb2_ctx* c, int mode, cudaStream_t stream) {
   c->grid = (int)gx;
   c->smem = smem;
   c->family = MB2_KERNEL_ISLANDS;
+  c->last_sparse = 0;
   const StrategyInfo s = c->sinfo;
   k<<<dim3((unsigned)gx, (unsigned)c->n_islands), kSubWarps * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   CUDA_TRY(cudaGetLastError());
@@ -662,6 +686,17 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
 
   StepParams P;
   fill_params(c, mode, in_rows, out_rows, e_in, e_out, np, &P);
+  // the staged kernels can leave rejected rows where they are (the caller then commits the accepted ones in place)
+  // (kernels that honour StepParams::sparse: K2f, K2d, K2a, K2e and the warp-per-row kernel K2b; the launch order
+  // below decides which one runs)
+  const bool by_rows = kc == nullptr && (kb != nullptr || (kw != nullptr && kw == kr));
+  const bool by_groups = kc == nullptr && kb == nullptr && kw == nullptr && ks == nullptr;   // kt, kx or k
+  const bool staged = by_rows || (by_groups && !(kt == nullptr && kx != nullptr && gen0_k));
+  const bool sparse = mode == MODE_STEP && staged &&
+                      in_rows == c->pop[c->cur] && out_rows == c->pop[c->cur ^ 1] && e_in == c->en[c->cur] && e_out == c->en[c->cur ^ 1] &&
+                      want_in_place(c);
+  P.sparse = sparse ? 1 : 0;
+  c->last_sparse = P.sparse;
   c->wpc = wpc;
   c->grid = (int)grid;
   c->smem = smem;
@@ -742,6 +777,22 @@ void fill_params(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, 
   P.stop = (c->run_active && mode == MODE_STEP) ? &c->run->stop : nullptr;
 
   *out = P;
+}
+
+// sparse generation: accepted rows and energies from the other buffers into the current ones, in place
+int launch_commit(mb2_ctx* c, cudaStream_t stream) {
+  double* pop = c->pop[c->cur];
+  const double* trial = c->pop[c->cur ^ 1];
+  const int vec = ((c->dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(pop) & 15) == 0) && ((reinterpret_cast<uintptr_t>(trial) & 15) == 0)) ? 1 : 0;
+  int64_t grid = (c->np + 255) / 256;  // a warp per 32 rows
+  const int64_t cap = (int64_t)c->sm_count * 8;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  de_commit_accepted_kernel<<<(unsigned)grid, 256, 0, stream>>>(c->run_active ? &c->run->stop : nullptr, pop, trial, c->en[c->cur],
+                                                                c->en[c->cur ^ 1], c->np, c->dim, vec);
+  CUDA_TRY(cudaGetLastError());
+  ++c->launches;
+  return MB2_OK;
 }
 
 int launch_finalize(mb2_ctx* c, int gen0, cudaStream_t stream) {
@@ -1208,6 +1259,7 @@ int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const doubl
   c->generation = -1;
   c->rows_in_range = 0;
   c->rows_checked = 0;
+  c->acc_hint = -1.0;
   return MB2_OK;
 }
 
@@ -1226,6 +1278,7 @@ int mb2_upload_population(mb2_ctx* c, const double* pop_host, void* stream) {
   c->generation = -1;
   c->rows_in_range = 0;
   c->rows_checked = 0;
+  c->acc_hint = -1.0;
   return MB2_OK;
 }
 
@@ -1242,6 +1295,7 @@ int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy,
   c->generation = generation;
   c->rows_in_range = 0;  // the caller installed rows this context has not checked
   c->rows_checked = 0;
+  c->acc_hint = -1.0;
   return MB2_OK;
 }
 
@@ -1266,8 +1320,11 @@ int mb2_step(mb2_ctx* c, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   if (int rc = launch_step(c, MODE_STEP, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s))
     return rc;
-  if (int rc = launch_finalize(c, 0, s)) return rc;
-  c->cur ^= 1;
+  if (c->last_sparse) {
+    if (int rc = launch_commit(c, s)) return rc;
+  }
+  if (int rc = launch_finalize(c, 0, s)) return rc;  // (reads the best member from the other buffer in both modes)
+  if (!c->last_sparse) c->cur ^= 1;
   c->generation += 1;
   c->replay = 0;  // recorded draws are consumed by exactly one generation
   return MB2_OK;
@@ -1373,11 +1430,15 @@ int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
   c->run_gen0 = c->generation;
   c->run_enqueued = max_steps;
   int rc = MB2_OK;
+  c->run_sparse = 0;
   for (int k = 0; k < max_steps && rc == MB2_OK; ++k) {
     rc = launch_step(c, MODE_STEP, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s);
+    if (rc == MB2_OK && k == 0) c->run_sparse = c->last_sparse;
+    if (rc == MB2_OK && c->last_sparse != c->run_sparse) rc = fail(MB2_ESTATE, "commit mode changed inside a batch");
+    if (rc == MB2_OK && c->last_sparse) rc = launch_commit(c, s);
     if (rc == MB2_OK) rc = launch_finalize(c, 0, s);
     if (rc == MB2_OK) {
-      c->cur ^= 1;
+      if (!c->last_sparse) c->cur ^= 1;
       c->generation += 1;
     }
   }
@@ -1391,12 +1452,15 @@ int mb2_run_result(mb2_ctx* c, int32_t* executed, int32_t* stopped, void* stream
   cudaStream_t s = (cudaStream_t)stream;
   if (c->xchg_connected) CUDA_TRY(cudaMemcpyAsync(c->h_xerr, c->xp.error, sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaMemcpyAsync(c->h_run, c->run, offsetof(RunState, hist0), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(c->h_st, c->st, sizeof(DeviceState), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   const int done = (int)c->h_run->log_count;
   *executed = done;
   *stopped = (c->h_run->stop == 1) ? 1 : 0;
+  if (done > 0) note_accepted(c, c->h_st->n_acc);
   // generations after the stop were no-ops: put the double buffer and the counter where the device is
-  c->cur = c->run_cur0 ^ (done & 1);
+  // (a batch committed in place never swapped)
+  c->cur = c->run_cur0 ^ (c->run_sparse ? 0 : (done & 1));
   c->generation = c->run_gen0 + done;
   // a sharded batch whose best exchange timed out: the shards' bests (and stop decisions) may differ across ranks
   if ((c->xchg_connected && *c->h_xerr != 0) || c->h_run->stop == 3)
@@ -1442,8 +1506,18 @@ int mb2_merge_best(mb2_ctx* c, const double* records, int32_t world, void* strea
   merge_best_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(records, world, c->dim, c->best_x, c->st);
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
+  c->counts_global = world > 1 ? 1 : 0;
   return MB2_OK;
 }
+
+int mb2_set_commit_mode(mb2_ctx* c, int mode) {
+  if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
+  if (mode < MB2_COMMIT_AUTO || mode > MB2_COMMIT_IN_PLACE) return fail(MB2_EINVAL, "unknown commit mode %d", mode);
+  c->commit_mode = mode;
+  return MB2_OK;
+}
+
+int mb2_last_commit_in_place(mb2_ctx* c) { return (c != nullptr && c->last_sparse) ? 1 : 0; }
 
 int mb2_set_islands(mb2_ctx* c, int32_t n_islands) {
   if (c == nullptr) return fail(MB2_EINVAL, "ctx is NULL");
@@ -1625,6 +1699,7 @@ int mb2_read_result(mb2_ctx* c, mb2_result* out, double* x_host, void* stream) {
   out->n_inf = c->h_st->n_inf;
   out->n_accepted = c->h_st->n_acc;
   out->generation = c->h_st->generation;
+  if (c->h_st->generation > 0) note_accepted(c, c->h_st->n_acc);  // (generation 0 "accepts" every row)
   if (x_host) memcpy(x_host, c->h_best_x, sizeof(double) * c->dim);
   return MB2_OK;
 }

@@ -59,6 +59,11 @@ struct StepParams {
   int dim;
   int dim_pad;  // dim rounded up to a multiple of 4
   int mode;     // MODE_*
+  // 1 (MODE_STEP of the staged kernels): only ACCEPTED trials are written to pop_next (e_next gets every row's
+  // energy); de_commit_accepted_kernel then moves them into pop_cur in place and the buffers are not swapped --
+  // the reference's own layout (population + trialSolution, differential_evolution.py:603-609), and a rejected
+  // row costs no write
+  int sparse;
   int bounds_mode;
   int bounds_uniform;  // 1: every dimension has the same [lo_s, hi_s] (no per-dimension loads)
   int rows_in_range;   // 1: every row of pop_cur is known to lie inside [lo, hi] (generation 0 clipped it)
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(kWarpsPerCtaMax * 32)
           for (int e = 0; e < 4; ++e) x[e] = s_trial[i0 + e];
           store4<VEC>(nrow, i0, D, x);
         }
-      } else {
+      } else if (!P.sparse) {  // (sparse: a rejected row stays where it is, de_commit_accepted_kernel moves the accepted ones)
         for (int i0 = lane * 4; i0 < D; i0 += 128) {
           double x[4];
           load4<VEC>(prow, i0, D, x);

@@ -323,6 +323,54 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// K4 (sparse generations, StepParams::sparse): the fused kernel wrote only the accepted trials (rows of `trial`,
+// the other population buffer) and every row's new energy (`e_new`); this moves the accepted rows into the
+// population IN PLACE -- the reference's `self.population[candidate][:] = self.trialSolution[candidate]`
+// (differential_evolution.py:603-609) -- after every row of the generation has read its donors from the old
+// one.  A row was accepted iff its new energy is lower (the fused kernel stores `acc ? E : e_old`), so a second
+// run over the same buffers changes nothing: the no-op launches after a batch's stop flag are harmless.
+// A warp scans 32 energies at a time and copies the accepted rows among them one by one.
+__global__ void __launch_bounds__(256)
+    de_commit_accepted_kernel(const int* __restrict__ stop, double* __restrict__ pop, const double* __restrict__ trial,
+                              double* __restrict__ e, const double* __restrict__ e_new, int64_t np, int D, int vec) {
+  if (stop != nullptr && *stop) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t base = gw * 32; base < np; base += nw * 32) {
+    const int64_t c = base + lane;
+    bool a = false;
+    double en = 0.0;
+    if (c < np) {
+      en = e_new[c];
+      a = en < e[c];
+    }
+    unsigned m = __ballot_sync(0xffffffffu, a);
+    if (a) e[c] = en;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      const int64_t r = base + b;
+      if (vec) {  // D even, 16-byte aligned buffers
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(trial + r * D);
+        double2* __restrict__ dst = reinterpret_cast<double2*>(pop + r * D);
+        const int n2 = D >> 1;
+        int i = lane;
+        for (; i + 96 < n2; i += 128) {
+          const double2 v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
+          dst[i] = v0;
+          dst[i + 32] = v1;
+          dst[i + 64] = v2;
+          dst[i + 96] = v3;
+        }
+        for (; i < n2; i += 32) dst[i] = src[i];
+      } else {
+        for (int i = lane; i < D; i += 32) pop[r * D + i] = trial[r * D + i];
+      }
+    }
+  }
+}
+
 // K0: device-side SetRandomInitialPoints (abstract_solver.py:532-534): pop[c][j] = lo + (hi-lo)*u
 __global__ void __launch_bounds__(256)
     de_init_population_kernel(double* __restrict__ pop, double* __restrict__ energy, int64_t np, int D,

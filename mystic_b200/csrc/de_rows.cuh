@@ -489,10 +489,11 @@ __global__ void __launch_bounds__(kRowsWarps * 32, MB2_ROWS_MINBLOCKS)
       const bool acc = E < e_old;
       const bool keep = acc || P.mode == MODE_GEN0;
       double* __restrict__ nrow = P.pop_next + c * D;
+      const bool store = keep || !P.sparse;  // sparse: a rejected row is not written
 #pragma unroll
       for (int t = 0; t < 2 * kRowsTrips; ++t) {
         const int i = 2 * (t * LPR + sub);  // 16-byte piece of chunk i/4
-        if (i < D) {
+        if (store && i < D) {
           int rq = (i >> 2) - q0;
           if (rq < 0) rq += NQ;
           // a rejected trial: chunks the window (or the clamp of the whole row) replaced come from the undo tile

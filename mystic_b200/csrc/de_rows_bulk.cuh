@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
       } else {
         rows_load_donors<K>(P.pop_cur, dr, D, q << 2, dc);
       }
-      oob |= rows_mutate_chunk<K>(P, base, XOVER_EXP, dr, cc, q, dc, s_best, t_row, fits ? s_undo + 4 * (off + w) : nullptr);
+      oob |= rows_mutate_chunk<K>(P, base, XOVER_EXP, dr, cc, q, dc, s_best, t_row, (fits && !P.sparse) ? s_undo + 4 * (off + w) : nullptr);
     }
     oob = ((__ballot_sync(0xffffffffu, oob) >> gbase) & LMASK) != 0;
     __syncwarp();
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
 
     // ---- selection (differential_evolution.py:603-613): a rejected trial is undone in the tile
     const bool acc = E < e_old;
-    if (!acc) {
+    if (!acc && !P.sparse) {
       for (int w = sub; w < nq; w += LPR) {
         int q = q0 + w;
         if (q >= NQ) q -= NQ;
@@ -280,13 +280,14 @@ __global__ void __launch_bounds__(kBulkRowsMaxWarps * 32, 1)
     }
     fence_proxy_async();  // generic-proxy writes of the tile -> visible to the bulk store; reads of the stage done
     __syncwarp();
-    const bool whole = (ch + 1) * RPW <= P.np;  // every row of the stage is live: one store for all of them
+    // sparse: only accepted rows leave, one store each (they are rare when this mode is chosen)
+    const bool whole = !P.sparse && (ch + 1) * RPW <= P.np;  // every row of the stage is live: one store for all of them
     if (lane == 0 && whole) {
       bulk_s2g(P.pop_next + ch * RPW * D, st, RPW * row_bytes);
       bulk_commit();
     }
     if (sub == 0 && live) {
-      if (!whole) {
+      if (!whole && (acc || !P.sparse)) {
         bulk_s2g(P.pop_next + c * D, t_row, row_bytes);
         bulk_commit();
       }

@@ -310,10 +310,13 @@ __global__ void __launch_bounds__(MAXT, 1)
     if (isinf(E)) ++g_ninf;
     if (tig < 32) {
       if (leader) {
-        bulk_s2g(P.pop_next + c * D, acc ? (const void*)s_d0 : (const void*)s_par, row_bytes);
-        bulk_commit();
+        const bool store = acc || !P.sparse;  // sparse: a rejected row stays where it is (pop_cur is committed in place)
+        if (store) {
+          bulk_s2g(P.pop_next + c * D, acc ? (const void*)s_d0 : (const void*)s_par, row_bytes);
+          bulk_commit();
+        }
         P.e_next[c] = acc ? E : e_old;
-        bulk_wait_read0();  // the store has finished reading the stage
+        if (store) bulk_wait_read0();  // the store has finished reading the stage
       }
       __syncwarp();
       // refill this stage with the row it serves next

@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(MAXT, 1)
     }
 
     const bool acc = E < e_old;
-    if (!acc && !gen0) {  // (generation 0 keeps the clipped row whatever its energy)
+    if (!acc && !gen0 && !P.sparse) {  // (generation 0 keeps the clipped row whatever its energy; sparse: a rejected row is not stored)
       // every thread has read the trial (costs without a group reduction and the capture end
       // without a barrier) before a rejected one is undone
       if (COST == COST_CORANA || COST == COST_ZIMMERMANN || P.cap_trial != nullptr) group_sync(grp);
@@ -338,10 +338,13 @@ __global__ void __launch_bounds__(MAXT, 1)
     if (isinf(E)) ++g_ninf;
     if (tig < 32) {
       if (leader) {
-        bulk_s2g(P.pop_next + c * D, s_row, row_bytes);
-        bulk_commit();
+        const bool store = acc || gen0 || !P.sparse;
+        if (store) {
+          bulk_s2g(P.pop_next + c * D, s_row, row_bytes);
+          bulk_commit();
+        }
         P.e_next[c] = acc ? E : e_old;
-        bulk_wait_read0();  // the store has finished reading the stage
+        if (store) bulk_wait_read0();  // the store has finished reading the stage
       }
       __syncwarp();
       // refill this stage with the row it serves next

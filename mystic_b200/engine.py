@@ -324,6 +324,17 @@ class DeviceEngine(object):
         """kernel family of the last fused launch (mb2_kernel_family)"""
         return self.KERNEL_FAMILIES[int(lib.mb2_kernel_family(self._ctx))]
 
+    COMMIT_MODES = {'auto': 0, 'double_buffer': 1, 'in_place': 2}
+
+    def set_commit_mode(self, mode):
+        """'auto' | 'double_buffer' | 'in_place' (mb2_set_commit_mode): whether a generation writes every selected row
+        to the other buffer and swaps, or only the accepted trials, which are then moved over their parents in place --
+        the reference's population / trialSolution layout (differential_evolution.py:603-609).  Same results."""
+        check(lib.mb2_set_commit_mode(self._ctx, self.COMMIT_MODES[mode] if isinstance(mode, str) else int(mode)))
+
+    def last_commit_in_place(self):
+        return bool(lib.mb2_last_commit_in_place(self._ctx))
+
     def launch_count(self):
         return int(lib.mb2_launch_count(self._ctx))
 
