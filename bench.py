@@ -67,6 +67,13 @@ WORKLOADS = {
     'x2': dict(desc='Rosenbrock 1024-D, NP=65536/GPU, Rand1Exp CR=0.9 F=0.8, SetStrictRanges(+-5, tight=True) (exponential crossover, long rows)',
                cost='rosen', extra=(), dim=1024, np=65536, strategy='Rand1Exp', CR=0.9, F=0.8, lo=-5., hi=5.,
                bounds='clamp', penalty=None, k=3),
+    # rows of odd length (not 16-byte multiples: no bulk copies) stay on the warp-per-row kernel K2b
+    'o2': dict(desc='Rosenbrock 1023-D, NP=65536/GPU, Best1Bin CR=0.9 F=0.8, SetStrictRanges(+-5, tight=True) (odd row length)',
+               cost='rosen', extra=(), dim=1023, np=65536, strategy='Best1Bin', CR=0.9, F=0.8, lo=-5., hi=5.,
+               bounds='clamp', penalty=None, k=2),
+    'ox2': dict(desc='Rosenbrock 1023-D, NP=65536/GPU, Rand1Exp CR=0.9 F=0.8, SetStrictRanges(+-5, tight=True) (odd row length)',
+                cost='rosen', extra=(), dim=1023, np=65536, strategy='Rand1Exp', CR=0.9, F=0.8, lo=-5., hi=5.,
+                bounds='clamp', penalty=None, k=3),
     # data-fit residual costs of forward_model.CostFactory (extra = points/observations, made in main)
     'f2': dict(desc='polynomial least-squares fit (poly.CostFactory2), 9 coeffs x 4096 points, NP=1048576/GPU, Best1Exp CR=1.0 '
                     'F=0.9, init +-100 (FP64 DMMA)',

@@ -276,7 +276,11 @@ typedef void (*ExpTmaKernel)(const StepParams, int, int, int, int);
 namespace mb2 {
 StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
-ExpTmaKernel get_exp_tma_kernel(int cost, int gwarps, int threads);
+ExpTmaKernel get_exp_tma_kernel_even(int cost, int gwarps, int threads);
+ExpTmaKernel get_exp_tma_kernel_odd(int cost, int gwarps, int threads);  // rows of odd length
+inline ExpTmaKernel get_exp_tma_kernel(int cost, int gwarps, int threads, int dim) {
+  return (dim & 1) ? get_exp_tma_kernel_odd(cost, gwarps, threads) : get_exp_tma_kernel_even(cost, gwarps, threads);
+}
 ThreadRowKernel get_small_kernel(int cost);
 ThreadRowKernel get_cheb_mma_kernel(int ksteps, bool resid);
 StepKernel get_datafit_ldg_kernel(int base, int xover, int cost);
@@ -363,7 +367,7 @@ void note_accepted(mb2_ctx* c, int64_t n_acc) {
 // Measured on B200 at D=1024 (profiles/README.md): concurrency across rows matters most (8 groups
 // beat 4 groups with deeper rings), then warps per row, then stages.
 bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
-  const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
+  const size_t row = (((size_t)(dim + (dim & 1)) * 8) + 127) & ~(size_t)127;  // (rows of odd length: the 16-byte aligned cover, dim + 1 elements)
   const size_t budget = 220 * 1024;
   if (row * 4 > budget) return false;
   const size_t slots = (budget - row) / (3 * row);  // (group, stage) buffers that fit on one SM
@@ -399,13 +403,16 @@ bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
 // undo buffer and k donor-segment buffers of `cap` elements each; cap covers the crossover window
 // (plus alignment slack) with probability >= 0.999: P(L > n) = CR^n.  In-flight bytes per SM are what
 // matter (a stage carries one row), so the ring is as deep as the shared memory allows.
-bool exp_tma_geometry(int dim, int k, double CR, int* groups, int* gwarps, int* stages, int* cap, int* smem) {
+bool exp_tma_geometry(int dim_in, int k, double CR, int* groups, int* gwarps, int* stages, int* cap, int* smem) {
+  // rows of odd length: buffers hold 16-byte aligned covers -- dim + 1 elements for a row, up to two more than the
+  // window for a donor segment
+  const int dim = dim_in + (dim_in & 1);
   const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
   const size_t budget = 220 * 1024;
   int want = dim;
   if (CR < 1.0) {
     const double n = (CR > 0.0) ? std::ceil(std::log(1e-3) / std::log(CR)) : 1.0;
-    if (n + 3.0 < (double)dim) want = (int)n + 3;
+    if (n + 3.0 + 2.0 * (dim_in & 1) < (double)dim) want = (int)n + 3 + 2 * (dim_in & 1);
   }
   want = (want + 1) & ~1;
   if (want < 8) want = 8;
@@ -556,8 +563,11 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     c->rows_checked = 1;
     c->rows_in_range = outside ? 0 : 1;
   }
-  const bool vec = (c->dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(in_rows) & 15) == 0) &&
-                   (out_rows == nullptr || (reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
+  const bool al16 = ((reinterpret_cast<uintptr_t>(in_rows) & 15) == 0) && (out_rows == nullptr || (reinterpret_cast<uintptr_t>(out_rows) & 15) == 0);
+  const bool vec = (c->dim % 2 == 0) && al16;
+  // the staged long-row kernels also take rows of odd length (16-byte aligned covers, de_tma.cuh); MB2_TMA_ODD=0
+  // sends those to the warp-per-row kernel as before
+  const bool bulk_ok = al16 && (c->dim % 2 == 0 || env_int("MB2_TMA_ODD", 1) != 0);
   StrategyInfo s = c->sinfo;
   if (mode != MODE_STEP) s = {BASE_RAND1, XOVER_EXP, 3};  // no best/donors needed; any instance
   const bool cheb_mma = (c->cost == MB2_COST_CHEBYSHEV_MMA || c->cost == MB2_COST_POLYFIT_MMA);
@@ -607,21 +617,21 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
-  if (mode == MODE_STEP && s.xover == XOVER_BIN && vec && env_int("MB2_TMA", 1) != 0 && !datafit &&
+  if (mode == MODE_STEP && s.xover == XOVER_BIN && bulk_ok && env_int("MB2_TMA", 1) != 0 && !datafit &&
       !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
   // the other strategies read a short window of the donors: K2e keeps long rows in a TMA ring
   ExpTmaKernel kx = nullptr;
   int xcap = 0;
-  if (mode == MODE_STEP && s.xover == XOVER_EXP && vec && env_int("MB2_TMA_EXP", 1) != 0 && !datafit && !cheb_mma &&
+  if (mode == MODE_STEP && s.xover == XOVER_EXP && bulk_ok && env_int("MB2_TMA_EXP", 1) != 0 && !datafit && !cheb_mma &&
       ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, &tg, &tw, &ts, &xcap, &tsmem))
-    kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32);
+    kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32, c->dim);
   // generation 0 of long rows is a read-clip-evaluate-write stream: the same staged kernel without draws or donors
   // (every strategy; the warp-per-row kernel needed 0.31 ms for it at BASELINE config 2)
   int gen0_k = 0;
-  if (mode == MODE_GEN0 && vec && env_int("MB2_TMA_GEN0", 1) != 0 && !datafit && !cheb_mma && ks == nullptr && kw == nullptr &&
+  if (mode == MODE_GEN0 && bulk_ok && env_int("MB2_TMA_GEN0", 1) != 0 && !datafit && !cheb_mma && ks == nullptr && kw == nullptr &&
       out_rows != nullptr && exp_tma_geometry(c->dim, 2, 0.0, &tg, &tw, &ts, &xcap, &tsmem)) {
-    kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32);
+    kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32, c->dim);
     gen0_k = 2;
   }
 

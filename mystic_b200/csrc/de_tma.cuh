@@ -96,7 +96,14 @@ __device__ __forceinline__ void best1_draws(const StepParams& P, int64_t c, int 
   }
 }
 
-// requires: dim even (rows are 16-byte multiples), MODE_STEP.  blockDim = groups * GW * 32 <= MAXT.
+// requires: MODE_STEP, 16-byte aligned population buffers.  blockDim = groups * GW * 32 <= MAXT.
+// Rows of ODD length (8*D is not a multiple of 16, every other row starts 8 bytes off a 16-byte boundary): a buffer
+// holds the 16-byte aligned COVER of its row, D + 1 elements starting `ph` = (row index & 1) elements before the row
+// (the last element of the previous row; past the row's end for even rows: the first element of the next one), so
+// element i of the row sits at slot ph + i.  The three rows of a stage have their own phases: the trial loop then
+// uses 8-byte shared-memory accesses, and the selected row leaves by plain stores of the whole group.  The one
+// cover that would reach past the end of the buffer (the last row when the row count is odd) is copied two
+// elements short and completed by a plain load of the leader.
 template <int COST, int GW, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
     de_step_best1bin_tma_kernel(const __grid_constant__ StepParams P, int stages) {
@@ -110,8 +117,9 @@ __global__ void __launch_bounds__(MAXT, 1)
   __shared__ unsigned long long sh_ninf[kTmaMaxGroups], sh_nacc[kTmaMaxGroups];
 
   const int D = P.dim;
+  const bool odd = (D & 1) != 0;
   const unsigned row_bytes = (unsigned)D * 8u;
-  const unsigned row_stride = (row_bytes + 127u) & ~127u;  // keep every buffer 128-B aligned (32-bit offsets: cheap to rematerialise)
+  const unsigned row_stride = (row_bytes + (odd ? 8u : 0u) + 127u) & ~127u;  // keep every buffer 128-B aligned (32-bit offsets: cheap to rematerialise)
   constexpr int gthreads = GW * 32;
   const int group = threadIdx.x / gthreads;
   const int ngroups = blockDim.x / gthreads;
@@ -165,12 +173,33 @@ __global__ void __launch_bounds__(MAXT, 1)
       ++dc_pos;
     }
     if (leader) {
-      s_nstart[group * kTmaMaxStages + s] = nstart;
       unsigned char* buf = s_ring + (unsigned)s * 3u * row_stride;
-      mbar_expect_tx(bars + s, 3u * row_bytes);
-      bulk_g2s(buf, P.pop_cur + c * D, row_bytes, bars + s);
-      bulk_g2s(buf + row_stride, P.pop_cur + r[0] * D, row_bytes, bars + s);
-      bulk_g2s(buf + 2 * row_stride, P.pop_cur + r[1] * D, row_bytes, bars + s);
+      if (!odd) {
+        s_nstart[group * kTmaMaxStages + s] = nstart;
+        mbar_expect_tx(bars + s, 3u * row_bytes);
+        bulk_g2s(buf, P.pop_cur + c * D, row_bytes, bars + s);
+        bulk_g2s(buf + row_stride, P.pop_cur + r[0] * D, row_bytes, bars + s);
+        bulk_g2s(buf + 2 * row_stride, P.pop_cur + r[1] * D, row_bytes, bars + s);
+      } else {
+        const int64_t rr[3] = {c, r[0], r[1]};
+        unsigned bytes[3], total = 0;
+        int phases = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int ph = (int)(rr[k] & 1);  // (row * D) & 1 with D odd
+          phases |= ph << k;
+          const bool short_cover = (ph == 0) && (rr[k] == P.np - 1);  // the cover would end one element past the buffer
+          bytes[k] = short_cover ? row_bytes - 8u : row_bytes + 8u;
+          total += bytes[k];
+          if (short_cover)  // its last element by a plain load (at most one row of a population)
+            reinterpret_cast<double*>(buf + (unsigned)k * row_stride)[D - 1] = __ldg(P.pop_cur + rr[k] * D + (D - 1));
+        }
+        s_nstart[group * kTmaMaxStages + s] = nstart | (phases << 16);
+        mbar_expect_tx(bars + s, total);  // (the arrive also publishes the plain store above and s_nstart)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+          bulk_g2s(buf + (unsigned)k * row_stride, P.pop_cur + rr[k] * D - (rr[k] & 1), bytes[k], bars + s);
+      }
     }
   };
 
@@ -184,7 +213,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   double g_best_e = CUDART_INF;
   int64_t g_best_idx = INT64_MAX;
   unsigned long long g_ninf = 0, g_nacc = 0;
-  const int npairs = D >> 1;  // double2 chunks per row
+  const int npairs = (D + 1) >> 1;  // double2 chunks per row (the last one of an odd row holds one element)
   const bool uni_b = P.bounds_uniform != 0;
 
   int s = 0;
@@ -200,7 +229,12 @@ __global__ void __launch_bounds__(MAXT, 1)
     const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
 
     group_wait_stage(grp, bars + s, parity);
-    const int nstart = s_nstart[group * kTmaMaxStages + s];
+    const int nstart_ph = s_nstart[group * kTmaMaxStages + s];
+    const int nstart = nstart_ph & 0xffff;
+    // odd rows: element i of the parent / first donor (trial) / second donor sits at slot ph + i of its buffer
+    const double* o_par = reinterpret_cast<const double*>(buf) + ((nstart_ph >> 16) & 1);
+    double* o_d0 = reinterpret_cast<double*>(buf + row_stride) + ((nstart_ph >> 17) & 1);
+    const double* o_d1 = reinterpret_cast<const double*>(buf + 2 * row_stride) + ((nstart_ph >> 18) & 1);
 
     // ---- trial vector (strategy.py:77-85), four conflict-free double2 chunks per thread per trip: chunk
     //      p_j = base + j*gthreads + tig, j = 0..3.  Crossover decisions (philox.cuh, protocol 2): Philox block q
@@ -211,9 +245,10 @@ __global__ void __launch_bounds__(MAXT, 1)
     bool oob = false;
     const int tq = tig & 3;
     const bool tq0 = (tq & 1) != 0, tq1 = (tq & 2) != 0;
-    auto trip = [&](int base, auto guard, auto uclamp) {
+    auto trip = [&](int base, auto guard, auto uclamp, auto oddrow) {
       constexpr bool GUARD = decltype(guard)::value;
       constexpr bool UCLAMP = decltype(uclamp)::value;  // clamp to one [lo_s, hi_s] for every dimension, known outside the loop
+      constexpr bool ODD = decltype(oddrow)::value;     // 8-byte accesses at the buffers' phases; the last chunk holds one element
       bool cx[8];  // crossover decisions of dims 2p_j, 2p_j+1, j = 0..3
       if (P.replay) {
         const double* u = P.r_uni + c * (int64_t)(D + 1);
@@ -250,8 +285,16 @@ __global__ void __launch_bounds__(MAXT, 1)
       for (int j = 0; j < 4; ++j) {
         const int p = base + j * gthreads + tig;
         if (!GUARD || p < npairs) {
-          double2 x = s_par[p];
-          const double2 a = s_d0[p], b = s_d1[p], bs = s_b2[p];
+          double2 x, a, b, bs;
+          const bool second = !ODD || 2 * p + 1 < D;
+          if (ODD) {
+            x.x = o_par[2 * p], a.x = o_d0[2 * p], b.x = o_d1[2 * p], bs.x = s_best[2 * p];
+            x.y = a.y = b.y = bs.y = 0.0;
+            if (second) x.y = o_par[2 * p + 1], a.y = o_d0[2 * p + 1], b.y = o_d1[2 * p + 1], bs.y = s_best[2 * p + 1];
+          } else {
+            x = s_par[p];
+            a = s_d0[p], b = s_d1[p], bs = s_b2[p];
+          }
           if (cx[2 * j]) x.x = dadd(bs.x, dmul(P.F, dsub(a.x, b.x)));
           if (cx[2 * j + 1]) x.y = dadd(bs.y, dmul(P.F, dsub(a.y, b.y)));
           if (UCLAMP) {
@@ -260,33 +303,40 @@ __global__ void __launch_bounds__(MAXT, 1)
             x.y = (x.y > P.lo_s) ? x.y : P.lo_s;
             x.y = (x.y < P.hi_s) ? x.y : P.hi_s;
           } else if (P.bounds_mode != BOUNDS_NONE) {
-            const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p + 1);
-            const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p + 1);
+            const double l0 = uni_b ? P.lo_s : __ldg(P.lo + 2 * p), l1 = (uni_b || !second) ? P.lo_s : __ldg(P.lo + 2 * p + 1);
+            const double h0 = uni_b ? P.hi_s : __ldg(P.hi + 2 * p), h1 = (uni_b || !second) ? P.hi_s : __ldg(P.hi + 2 * p + 1);
             if (P.bounds_mode == BOUNDS_CLAMP) {
               x.x = (x.x > l0) ? x.x : l0;
               x.x = (x.x < h0) ? x.x : h0;
               x.y = (x.y > l1) ? x.y : l1;
               x.y = (x.y < h1) ? x.y : h1;
             } else {
-              oob |= (x.x < l0) || (x.x > h0) || (x.y < l1) || (x.y > h1);  // nothing is out of range after a clamp
+              oob |= (x.x < l0) || (x.x > h0) || (second && ((x.y < l1) || (x.y > h1)));  // nothing is out of range after a clamp
             }
           }
-          s_d0[p] = x;
+          if (ODD) {
+            o_d0[2 * p] = x.x;
+            if (second) o_d0[2 * p + 1] = x.y;
+          } else {
+            s_d0[p] = x;
+          }
         }
       }
     };
-    if (npairs % (4 * gthreads) == 0) {  // whole trips only: no per-chunk guards
+    if (odd) {
+      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::true_type(), std::false_type(), std::true_type());
+    } else if (npairs % (4 * gthreads) == 0) {  // whole trips only: no per-chunk guards
       if (uni_b && P.bounds_mode == BOUNDS_CLAMP) {
-        for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::true_type());
+        for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::true_type(), std::false_type());
       } else {
-        for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::false_type());
+        for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::false_type(), std::false_type());
       }
     } else {
-      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::true_type(), std::false_type());
+      for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::true_type(), std::false_type(), std::false_type());
     }
     oob = group_any(grp, oob);  // also the barrier that publishes the trial vector to the group
 
-    const double* s_trial = reinterpret_cast<const double*>(s_d0);
+    const double* s_trial = o_d0;  // (even rows: phase 0, the first donor's buffer)
     double E = CUDART_INF;
     if (!oob) E = group_cost<COST, GW>(grp, s_trial, D, P.cost);
     E = dadd(E, group_penalty(grp, s_trial, D, P.pen));
@@ -308,9 +358,16 @@ __global__ void __launch_bounds__(MAXT, 1)
       }
     }
     if (isinf(E)) ++g_ninf;
+    if (odd && (acc || !P.sparse)) {
+      // rows of odd length leave by plain stores of the whole group (8-byte aligned on both sides)
+      const double* src = acc ? s_trial : o_par;
+      double* __restrict__ nrow = P.pop_next + c * D;
+      for (int i = tig; i < D; i += gthreads) nrow[i] = src[i];
+      group_sync(grp);  // the stage has been read before it is refilled
+    }
     if (tig < 32) {
       if (leader) {
-        const bool store = acc || !P.sparse;  // sparse: a rejected row stays where it is (pop_cur is committed in place)
+        const bool store = !odd && (acc || !P.sparse);  // sparse: a rejected row stays where it is (pop_cur is committed in place)
         if (store) {
           bulk_s2g(P.pop_next + c * D, acc ? (const void*)s_d0 : (const void*)s_par, row_bytes);
           bulk_commit();

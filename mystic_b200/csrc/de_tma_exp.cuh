@@ -25,9 +25,16 @@ namespace mb2 {
 
 struct ExpStageMeta {  // written by the leader before the mbarrier arrive, read by the group after the wait
   int nstart, L, fits, a1, n1;
-  int pad_[3];
+  int phases;  // rows of odd length: bit 0 the parent's phase, bit 1 + j donor j's (slot of element i = phase + i)
+  int pad_[2];
   long long r[5];
 };
+
+// Rows of odd length: the 16-byte aligned cover of elements [lo, hi) of a row whose phase (row index & 1 = parity
+// of its first element's index in the buffer) is `ph`: it starts at the largest s <= lo and ends at the smallest
+// t >= hi with the parity of ph (s may be -1: the last element of the previous row; t may be D + 1: the first of the next)
+__device__ __forceinline__ int odd_cover_start(int lo, int ph) { return lo - ((lo - ph) & 1); }
+__device__ __forceinline__ int odd_cover_end(int hi, int ph) { return hi + ((hi - ph) & 1); }
 static_assert(sizeof(ExpStageMeta) <= 128, "stage meta must fit its 128-byte slot");
 
 __device__ __forceinline__ double mutant_rt(int base, double t, double b, const double (&p)[5], double F) {
@@ -68,8 +75,11 @@ __device__ __forceinline__ void draw_donors_warp_rt(const StepParams& P, int kdo
   }
 }
 
-// requires: dim even (rows are 16-byte multiples), cap even, MODE_STEP.  blockDim = groups * GW * 32 <= MAXT.
-template <int COST, int GW, int MAXT>
+// requires: cap even, 16-byte aligned population buffers, MODE_STEP or MODE_GEN0.  blockDim = groups * GW * 32 <= MAXT.
+// Rows of ODD length (de_tma.cuh explains the phases): the row buffer holds the aligned cover of the parent (D + 1
+// elements, the row at slot `phase`), every donor's window cover is aligned for THAT donor's phase (so the donors'
+// segments start up to one element apart), and the selected row leaves by plain stores of the group.
+template <int COST, int GW, int MAXT, bool ODD = false>  // ODD: rows of odd length (its own build: the even one pays nothing for the phases)
 __global__ void __launch_bounds__(MAXT, 1)
     de_step_exp_tma_kernel(const __grid_constant__ StepParams P, int stages, int cap, int base, int kdon) {
   if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
@@ -81,8 +91,9 @@ __global__ void __launch_bounds__(MAXT, 1)
   __shared__ unsigned long long sh_ninf[kTmaMaxGroups], sh_nacc[kTmaMaxGroups];
 
   const int D = P.dim;
+  constexpr bool odd = ODD;  // (the host picks the build by D & 1)
   const unsigned row_bytes = (unsigned)D * 8u;
-  const unsigned row_stride = (row_bytes + 127u) & ~127u;  // keep every buffer 128-B aligned (32-bit offsets: cheap to rematerialise)
+  const unsigned row_stride = (row_bytes + (odd ? 8u : 0u) + 127u) & ~127u;  // keep every buffer 128-B aligned (32-bit offsets: cheap to rematerialise)
   const unsigned seg_stride = (unsigned)cap * 8u;                        // one donor's (or the undo) buffer
   const unsigned stage_stride = (row_stride + (unsigned)(kdon + 1) * seg_stride + 128u + 127u) & ~127u;
   constexpr int gthreads = GW * 32;
@@ -130,9 +141,19 @@ __global__ void __launch_bounds__(MAXT, 1)
   auto issue = [&](int64_t c, int s) {
     uint64_t* bar = bars + s;
     // the parent row does not depend on the draws: its copy flies while they are made
+    const int php = odd ? (int)(c & 1) : 0;
     if (leader) {
-      mbar_expect_tx_only(bar, row_bytes);
-      bulk_g2s(stage_row(s), P.pop_cur + c * D, row_bytes, bar);
+      if (!odd) {
+        mbar_expect_tx_only(bar, row_bytes);
+        bulk_g2s(stage_row(s), P.pop_cur + c * D, row_bytes, bar);
+      } else {
+        // the cover of the last row of an odd number of rows would end past the buffer: two elements short + a plain load
+        const bool short_cover = (php == 0) && (c == P.np - 1);
+        const unsigned bytes = short_cover ? row_bytes - 8u : row_bytes + 8u;
+        if (short_cover) stage_row(s)[D - 1] = __ldg(P.pop_cur + c * D + (D - 1));  // (published by the arrive below)
+        mbar_expect_tx_only(bar, bytes);
+        bulk_g2s(stage_row(s), P.pop_cur + c * D - php, bytes, bar);
+      }
     }
     if (P.mode == MODE_GEN0) {  // generation 0: the row is only clipped and evaluated -- no draws, no donors
       if (leader) {
@@ -142,6 +163,7 @@ __global__ void __launch_bounds__(MAXT, 1)
         m->fits = 0;
         m->a1 = 0;
         m->n1 = 0;
+        m->phases = php;
         mbar_expect_tx(bar, 0u);  // the arrive
       }
       __syncwarp();
@@ -187,7 +209,53 @@ __global__ void __launch_bounds__(MAXT, 1)
       n1 = D;
       n2 = 0;
     }
-    const bool fits = (L > 0) && (n1 + n2 <= cap);
+    bool fits = (L > 0) && (n1 + n2 <= cap);
+    if (odd) {
+      // per donor: first segment = cover of [lo1, hi1), wrapped segment = cover of [0, hi2); lo1 is also the
+      // threshold `a1` that tells the two apart when an element is looked up
+      const int lo1 = (L >= D) ? 0 : nstart, hi1 = (end < D) ? end : D, hi2 = (L < D && end > D) ? end - D : 0;
+      int phases = php, total = 0;
+      bool ok = L > 0;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if (j < kdon) {
+          const int ph = (int)(r[j] & 1);
+          phases |= ph << (1 + j);
+          const int t1 = odd_cover_end(hi1, ph);
+          const int m1 = t1 - odd_cover_start(lo1, ph), m2 = hi2 > 0 ? odd_cover_end(hi2, ph) + ph : 0;
+          total += m1 + m2;
+          ok = ok && (m1 + m2 <= cap) && !(r[j] == P.np - 1 && (t1 > D || (hi2 > 0 && odd_cover_end(hi2, ph) > D)));  // (a cover past the end of the buffer)
+        }
+      }
+      fits = ok;
+      if (leader) {
+        ExpStageMeta* m = stage_meta(s);
+        m->nstart = nstart;
+        m->L = L;
+        m->fits = fits ? 1 : 0;
+        m->a1 = lo1;
+        m->n1 = hi1;
+        m->phases = phases;
+#pragma unroll
+        for (int j = 0; j < 5; ++j) m->r[j] = r[j];
+        mbar_expect_tx(bar, fits ? (unsigned)total * 8u : 0u);  // the arrive: meta is published with it
+      }
+      __syncwarp();
+      if (fits) {
+        const int j1 = lane - 1, j2 = lane - 9;
+        if (j1 >= 0 && j1 < kdon) {
+          const int64_t rj = (j1 == 0) ? r[0] : (j1 == 1) ? r[1] : (j1 == 2) ? r[2] : (j1 == 3) ? r[3] : r[4];
+          const int ph = (int)(rj & 1), s1 = odd_cover_start(lo1, ph);
+          bulk_g2s(stage_don(s, j1), P.pop_cur + rj * D + s1, (unsigned)(odd_cover_end(hi1, ph) - s1) * 8u, bar);
+        }
+        if (hi2 > 0 && j2 >= 0 && j2 < kdon) {
+          const int64_t rj = (j2 == 0) ? r[0] : (j2 == 1) ? r[1] : (j2 == 2) ? r[2] : (j2 == 3) ? r[3] : r[4];
+          const int ph = (int)(rj & 1), m1 = odd_cover_end(hi1, ph) - odd_cover_start(lo1, ph);
+          bulk_g2s(stage_don(s, j2) + m1, P.pop_cur + rj * D - ph, (unsigned)(odd_cover_end(hi2, ph) + ph) * 8u, bar);
+        }
+      }
+      return;
+    }
     if (leader) {
       ExpStageMeta* m = stage_meta(s);
       m->nstart = nstart;
@@ -195,6 +263,7 @@ __global__ void __launch_bounds__(MAXT, 1)
       m->fits = fits ? 1 : 0;
       m->a1 = a1;
       m->n1 = n1;
+      m->phases = 0;
 #pragma unroll
       for (int j = 0; j < 5; ++j) m->r[j] = r[j];
       mbar_expect_tx(bar, fits ? (unsigned)(kdon * (n1 + n2)) * 8u : 0u);  // the arrive: meta is published with it
@@ -239,6 +308,10 @@ __global__ void __launch_bounds__(MAXT, 1)
     group_wait_stage(grp, bars + s, parity);
     const int nstart = meta->nstart, L = meta->L, a1 = meta->a1, n1 = meta->n1;
     const bool fits = meta->fits != 0;
+    // rows of odd length: the row starts at slot `phase` of its buffer; donor j's segments are the covers for ITS
+    // phase (a1 / n1 carry the first segment's first element and end: [a1, n1), the wrapped one starts at element 0)
+    const int phases = odd ? meta->phases : 0;
+    if (odd) s_row += phases & 1;
 
     // ---- trial vector in place (strategy.py:48-56): window element w is dimension (nstart + w) mod D
     bool oob = false;
@@ -247,7 +320,14 @@ __global__ void __launch_bounds__(MAXT, 1)
       if (i >= D) i -= D;
       const double t = s_row[i];
       double p[5] = {0., 0., 0., 0., 0.};
-      if (fits) {
+      if (fits && odd) {
+#pragma unroll
+        for (int j = 0; j < 5; ++j)
+          if (j < kdon) {
+            const int ph = (phases >> (1 + j)) & 1, s1 = odd_cover_start(a1, ph);
+            p[j] = stage_don(s, j)[(i >= a1) ? (i - s1) : (odd_cover_end(n1, ph) - s1 + i + ph)];
+          }
+      } else if (fits) {
         const int off = (i >= a1) ? (i - a1) : (n1 + i);
 #pragma unroll
         for (int j = 0; j < 5; ++j)
@@ -336,9 +416,15 @@ __global__ void __launch_bounds__(MAXT, 1)
       }
     }
     if (isinf(E)) ++g_ninf;
+    if (odd && (acc || gen0 || !P.sparse)) {
+      // rows of odd length leave by plain stores of the whole group (8-byte aligned on both sides)
+      double* __restrict__ nrow = P.pop_next + c * D;
+      for (int i = tig; i < D; i += gthreads) nrow[i] = s_row[i];
+      group_sync(grp);  // the stage has been read before it is refilled
+    }
     if (tig < 32) {
       if (leader) {
-        const bool store = acc || gen0 || !P.sparse;
+        const bool store = !odd && (acc || gen0 || !P.sparse);
         if (store) {
           bulk_s2g(P.pop_next + c * D, s_row, row_bytes);
           bulk_commit();

@@ -31,8 +31,10 @@ CASES = [
     (32, 333, 'Best1Exp', 'rosen', (-2., 2., orc.BOUNDS_CLAMP), None, 0.5, 0.5, 12, 'rows_bulk'),          # last warp partly idle
     (64, 301, 'Best1Bin', 'rosen', (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 8, 'rows'),                # K2d: binomial crossover on short rows
     (128, 90, 'Best1Bin', 'griewangk', (-400., 400., orc.BOUNDS_REJECT), None, 0.3, 0.5, 8, 'rows'),
-    (301, 64, 'Rand1Exp', 'rosen', (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 6, 'warp_per_row'),        # K2b: odd row length
+    (301, 64, 'Rand1Exp', 'rosen', (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 6, 'warp_per_row'),        # K2b (MB2_TMA_ODD=0 below)
     (1001, 40, 'Best1Bin', 'griewangk', (-400., 400., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5, 'warp_per_row'),
+    (301, 65, 'Rand1Exp', 'rosen', (-5., 5., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 6, 'tma_exp'),             # odd row length, staged
+    (1001, 41, 'Best1Bin', 'griewangk', (-400., 400., orc.BOUNDS_CLAMP), None, 0.9, 0.8, 5, 'tma_bin'),
 ]
 MODES = ['in_place', 'double_buffer', 'auto']
 
@@ -66,6 +68,7 @@ def _check(eng, st, cost, tag):
 def test_step_by_step_equals_the_oracle_in_every_commit_mode(case, mode, monkeypatch):
     monkeypatch.delenv('MB2_COMMIT_MODE', raising=False)
     dim, NP, strat, cost, bounds, pen, CR, F, gens, family = case
+    monkeypatch.setenv('MB2_TMA_ODD', '0' if family == 'warp_per_row' else '1')
     seed = 0xC0117000 + dim * 7 + NP
     eng, st = _start(case, mode, seed)
     ocost = orc.make_cost(cost, ())
