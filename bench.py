@@ -566,6 +566,7 @@ def leg_record(rig, leg):
             'ms_per_step': leg['dev_ms'] / steps, 'burst_ms_per_step': leg['burst_ms'] / steps, 'steps': steps,
             'roofline': roofline_of(rig, leg), 'clocks': leg['clocks'], 'gpu_launches': leg['launches'],
             'kernel_family': leg['family'], 'grid': leg['grid'], 'block': leg['block'], 'smem_bytes': leg['smem'],
+            'commit': 'in_place' if leg.get('in_place') else 'double_buffer',
             'inf_fraction': leg['inf_fraction'], 'accept_fraction': leg['accept_fraction']}
 
 
@@ -746,6 +747,8 @@ def main():
         'config': workload_config(w, NP_local, NP_global),
         'details': {'rng': 'philox4x32-10 in-kernel', 'grid': leg['grid'], 'block': leg['block'], 'smem_bytes': leg['smem'],
                     'kernel_family': leg['family'], 'inf_fraction': leg['inf_fraction'], 'accept_fraction': leg['accept_fraction'],
+                    'commit': 'in_place (accepted trials only are written, de_commit_accepted_kernel moves them over their parents)'
+                              if leg.get('in_place') else 'double_buffer (every selected row is written, buffers swapped)',
                     'sustain_s_before_timing': args.sustain, 'burst_ms_per_step': leg['burst_ms'] / steps,
                     'e2e_host_numa_node': e2e['numa_node'] if e2e else None,
                     'parallelism': (('candidate-sharded x%d, ' % world) + (

@@ -403,7 +403,7 @@ bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
 // undo buffer and k donor-segment buffers of `cap` elements each; cap covers the crossover window
 // (plus alignment slack) with probability >= 0.999: P(L > n) = CR^n.  In-flight bytes per SM are what
 // matter (a stage carries one row), so the ring is as deep as the shared memory allows.
-bool exp_tma_geometry(int dim_in, int k, double CR, int* groups, int* gwarps, int* stages, int* cap, int* smem) {
+bool exp_tma_geometry(int dim_in, int k, double CR, bool in_place, int* groups, int* gwarps, int* stages, int* cap, int* smem) {
   // rows of odd length: buffers hold 16-byte aligned covers -- dim + 1 elements for a row, up to two more than the
   // window for a donor segment
   const int dim = dim_in + (dim_in & 1);
@@ -428,10 +428,14 @@ bool exp_tma_geometry(int dim_in, int k, double CR, int* groups, int* gwarps, in
   const size_t slots = (budget - row) / stage;  // (group, stage) buffers that fit on one SM
   // B200 sweep at D=1024 (profiles/README.md): rows in flight matter most -- 15 groups x 2 warps x 1 stage
   // 0.210 ms, 8 groups x 4 warps x 2 stages 0.301 ms.  As many groups as fit, then >= 16 dimensions per thread.
+  // Generations committed in place (no row leaves a stage unless its trial is accepted) are bound by the rows in
+  // flight alone: >= 32 dimensions per thread, i.e. 20 one-warp groups at D=1024 -- 0.183 ms against 0.207 ms with
+  // 15 x 2 (with the double buffer the same geometry loses: 0.217 against 0.210).
+  const int per_thread = in_place ? 32 : 16;
   int g = (int)slots;
   if (g > kTmaMaxGroups) g = kTmaMaxGroups;
   int gw = 1;
-  while (gw < 8 && (gw * 2) * 32 * 16 <= dim && (g > 15 ? 15 : g) * (gw * 2) * 32 <= kTmaMaxThreads) gw <<= 1;
+  while (gw < 8 && (gw * 2) * 32 * per_thread <= dim && (g > 15 ? 15 : g) * (gw * 2) * 32 <= kTmaMaxThreads) gw <<= 1;
   if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
   if (g * gw * 32 > kTmaMaxThreads) g = kTmaMaxThreads / (gw * 32);
   int st = (int)(slots / g);
@@ -624,13 +628,13 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   ExpTmaKernel kx = nullptr;
   int xcap = 0;
   if (mode == MODE_STEP && s.xover == XOVER_EXP && bulk_ok && env_int("MB2_TMA_EXP", 1) != 0 && !datafit && !cheb_mma &&
-      ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, &tg, &tw, &ts, &xcap, &tsmem))
+      ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, want_in_place(c), &tg, &tw, &ts, &xcap, &tsmem))
     kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32, c->dim);
   // generation 0 of long rows is a read-clip-evaluate-write stream: the same staged kernel without draws or donors
   // (every strategy; the warp-per-row kernel needed 0.31 ms for it at BASELINE config 2)
   int gen0_k = 0;
   if (mode == MODE_GEN0 && bulk_ok && env_int("MB2_TMA_GEN0", 1) != 0 && !datafit && !cheb_mma && ks == nullptr && kw == nullptr &&
-      out_rows != nullptr && exp_tma_geometry(c->dim, 2, 0.0, &tg, &tw, &ts, &xcap, &tsmem)) {
+      out_rows != nullptr && exp_tma_geometry(c->dim, 2, 0.0, false, &tg, &tw, &ts, &xcap, &tsmem)) {
     kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32, c->dim);
     gen0_k = 2;
   }
