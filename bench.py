@@ -118,10 +118,19 @@ NCU_SUMMARIES = {
 _UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
 
 
-def ncu_traffic(workload):
+# the same kernels committing the generation in place (accepted trials only are written)
+NCU_SUMMARIES_IN_PLACE = {
+    'c2': ('profiles/r2_c2_inplace_ncu_full_summary.csv',),
+    'x2': ('profiles/r2_x2_inplace_ncu_full_summary.csv',),
+    'c4': ('profiles/r2_c4_inplace_ncu_full_summary.csv',),
+    'c5': ('profiles/r2_c5_inplace_ncu_full_summary.csv',),
+}
+
+
+def ncu_traffic(workload, in_place=False):
     """-> (DRAM bytes read + written by one launch of the fused kernel, summary file) or (None, None)"""
     import csv
-    for rel in NCU_SUMMARIES.get(workload, ()):
+    for rel in (NCU_SUMMARIES_IN_PLACE if in_place else NCU_SUMMARIES).get(workload, ()):
         path = os.path.join(REPO, rel)
         if not os.path.exists(path):
             continue
@@ -523,7 +532,7 @@ def roofline_of(rig, leg):
     base = name.rstrip('s') if name == 'c5s' else name
     traffic, traffic_src = (None, None)
     if NP_local == WORKLOADS.get(base, {}).get('np'):
-        traffic, traffic_src = ncu_traffic(base)
+        traffic, traffic_src = ncu_traffic(base, in_place)
     roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                 'frac': achieved / peaks['hbm_gbs'], 'traffic': traffic, 'traffic_source': traffic_src,
                 'peak_source': rig.peaks_src, 'frac_burst': bpc * NP_local / burst_s / 1e9 / peaks['hbm_gbs'],
@@ -536,9 +545,7 @@ def roofline_of(rig, leg):
         # would move (every row written); above 1 = faster than that design can be
         roofline['double_buffer_model'] = {'algorithmic_bytes_per_candidate': bpc_db,
                                            'frac': bpc_db * NP_local / step_s / 1e9 / peaks['hbm_gbs']}
-        # the committed ncu summaries are of the double-buffered kernel unless their name says otherwise
-        if traffic_src and 'inplace' not in traffic_src:
-            roofline['traffic_note'] = 'captured with the double buffer (every row written)'
+
     flops = algorithmic_flops_per_candidate(w)
     if flops:
         # the Chebyshev / polynomial contraction is FP64-pipe bound; DMMA and DFMA share that pipe on B200, so the

@@ -333,8 +333,8 @@ int mb2_kernel_family(mb2_ctx* ctx);
  * ACCEPTED trials to the other buffer and de_commit_accepted_kernel moves them over their parents once every
  * row has read its donors; a rejected row is never written.  MB2_COMMIT_DOUBLE_BUFFER writes every selected row
  * to the other buffer and swaps (the only mode of the rows-per-warp, thread-per-row, DMMA and batched kernels).  MB2_COMMIT_AUTO (default) commits in place while the
- * accepted fraction of the last generation the host read back is below 0.30 -- in place moves
- * (1 + k + 3a) rows per candidate, the double buffer (2 + k).  Results are bit-identical in every mode.
+ * accepted fraction of the last generation the host read back is below 0.30 (0.12 for rows of up to 128
+ * dimensions) -- in place moves (1 + k + 3a) rows per candidate, the double buffer (2 + k).  Results are bit-identical in every mode.
  * The environment variable MB2_COMMIT_MODE (0, 1, 2) overrides the context's setting. */
 enum mb2_commit_mode_id { MB2_COMMIT_AUTO = 0, MB2_COMMIT_DOUBLE_BUFFER = 1, MB2_COMMIT_IN_PLACE = 2 };
 int mb2_set_commit_mode(mb2_ctx* ctx, int mode);

@@ -350,12 +350,16 @@ int env_int(const char* name, int dflt) {
 // in-place commit pays while fewer than a third of the trials are accepted: per row it moves
 // (1 + k + a) rows + 2a in the commit against (2 + k) with the double buffer
 constexpr double kInPlaceMaxAccept = 0.30;
+// ... for long rows; rows of up to 128 dimensions leave their kernels a stage of several rows at a time with ONE
+// copy request, which in place becomes a request per accepted row: measured break-even near 0.15 (bench.py g128 at
+// 0.145: 0.678 ms either way; r32 at 0.178: 0.440 ms in place, 0.417 ms with the double buffer)
+constexpr double kInPlaceMaxAcceptShortRows = 0.12;
 bool want_in_place(const mb2_ctx* c) {
   int mode = env_int("MB2_COMMIT_MODE", -1);
   if (mode < MB2_COMMIT_AUTO || mode > MB2_COMMIT_IN_PLACE) mode = c->commit_mode;
   if (mode == MB2_COMMIT_DOUBLE_BUFFER) return false;
   if (mode == MB2_COMMIT_IN_PLACE) return true;
-  return c->acc_hint < kInPlaceMaxAccept;  // (no generation read back yet: in place)
+  return c->acc_hint < (c->dim > 128 ? kInPlaceMaxAccept : kInPlaceMaxAcceptShortRows);  // (no generation read back yet: in place)
 }
 void note_accepted(mb2_ctx* c, int64_t n_acc) {
   const int64_t denom = (c->xchg_connected || c->counts_global) ? c->np_global : c->np;
@@ -798,7 +802,7 @@ int launch_commit(mb2_ctx* c, cudaStream_t stream) {
   double* pop = c->pop[c->cur];
   const double* trial = c->pop[c->cur ^ 1];
   const int vec = ((c->dim % 2 == 0) && ((reinterpret_cast<uintptr_t>(pop) & 15) == 0) && ((reinterpret_cast<uintptr_t>(trial) & 15) == 0)) ? 1 : 0;
-  int64_t grid = (c->np + 255) / 256;  // a warp per 32 rows
+  int64_t grid = (c->np + 255) / 256;  // a CTA per 256 rows
   const int64_t cap = (int64_t)c->sm_count * 8;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;

@@ -329,45 +329,107 @@ __global__ void __launch_bounds__(256)
 // (differential_evolution.py:603-609) -- after every row of the generation has read its donors from the old
 // one.  A row was accepted iff its new energy is lower (the fused kernel stores `acc ? E : e_old`), so a second
 // run over the same buffers changes nothing: the no-op launches after a batch's stop flag are harmless.
-// A warp scans 32 energies at a time and copies the accepted rows among them one by one.
+// A CTA scans 256 energies at a time (a warp 32), queues the accepted rows in shared memory and copies them with all
+// its warps, round robin -- a warp that copied only the rows it found itself would make the kernel as slow as the
+// unluckiest warp (binomial tail: 43 us instead of ~15 at BASELINE config 2's shape with 13 % of the trials accepted).
+__device__ __forceinline__ void commit_copy_row(double* __restrict__ pop, const double* __restrict__ trial, int64_t r, int D, int vec,
+                                                int lane) {
+  if (vec) {  // D even, 16-byte aligned buffers: eight 16-byte pieces per lane in flight (4 KB per warp)
+    const double2* __restrict__ src = reinterpret_cast<const double2*>(trial + r * D);
+    double2* __restrict__ dst = reinterpret_cast<double2*>(pop + r * D);
+    const int n2 = D >> 1;
+    for (int i = lane; i < n2; i += 256) {
+      double2 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i + 32 * u < n2) v[u] = src[i + 32 * u];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (i + 32 * u < n2) dst[i + 32 * u] = v[u];
+    }
+  } else {
+    for (int i = lane; i < D; i += 128) {
+      double v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + 32 * u < D) v[u] = trial[r * D + i + 32 * u];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (i + 32 * u < D) pop[r * D + i + 32 * u] = v[u];
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256)
     de_commit_accepted_kernel(const int* __restrict__ stop, double* __restrict__ pop, const double* __restrict__ trial,
                               double* __restrict__ e, const double* __restrict__ e_new, int64_t np, int D, int vec) {
   if (stop != nullptr && *stop) return;
-  const int lane = threadIdx.x & 31;
-  const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  for (int64_t base = gw * 32; base < np; base += nw * 32) {
-    const int64_t c = base + lane;
+  __shared__ int s_rows[256];  // accepted rows of the CTA's current 256 (offsets from its first row)
+  __shared__ int s_count;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (vec && D <= 128) {
+    // short rows (<= 64 16-byte pieces): every warp copies the rows it finds among its own 32, four at a time so
+    // that four rows' loads are in flight before the first store needs its data (no CTA-wide barriers: with 2 M
+    // rows of 32 dimensions the queue below costs more than the imbalance it removes)
+    const int n2 = D >> 1;
+    const int64_t gw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t base = gw * 32; base < np; base += nw * 32) {
+      const int64_t c = base + lane;
+      bool a = false;
+      double en = 0.0;
+      if (c < np) {
+        en = e_new[c];
+        a = en < e[c];
+      }
+      unsigned m = __ballot_sync(0xffffffffu, a);
+      if (a) e[c] = en;
+      while (m) {
+        double2 v[4][2];
+        int64_t r[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          r[k] = -1;
+          if (m) {
+            r[k] = base + (__ffs(m) - 1);
+            m &= m - 1;
+            const double2* __restrict__ src = reinterpret_cast<const double2*>(trial + r[k] * D);
+            if (lane < n2) v[k][0] = src[lane];
+            if (lane + 32 < n2) v[k][1] = src[lane + 32];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (r[k] >= 0) {
+            double2* __restrict__ dst = reinterpret_cast<double2*>(pop + r[k] * D);
+            if (lane < n2) dst[lane] = v[k][0];
+            if (lane + 32 < n2) dst[lane + 32] = v[k][1];
+          }
+        }
+      }
+    }
+    return;
+  }
+  for (int64_t first = (int64_t)blockIdx.x * 256; first < np; first += (int64_t)gridDim.x * 256) {
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    const int64_t c = first + threadIdx.x;
     bool a = false;
     double en = 0.0;
     if (c < np) {
       en = e_new[c];
       a = en < e[c];
     }
-    unsigned m = __ballot_sync(0xffffffffu, a);
+    const unsigned m = __ballot_sync(0xffffffffu, a);
     if (a) e[c] = en;
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      const int64_t r = base + b;
-      if (vec) {  // D even, 16-byte aligned buffers
-        const double2* __restrict__ src = reinterpret_cast<const double2*>(trial + r * D);
-        double2* __restrict__ dst = reinterpret_cast<double2*>(pop + r * D);
-        const int n2 = D >> 1;
-        int i = lane;
-        for (; i + 96 < n2; i += 128) {
-          const double2 v0 = src[i], v1 = src[i + 32], v2 = src[i + 64], v3 = src[i + 96];
-          dst[i] = v0;
-          dst[i + 32] = v1;
-          dst[i + 64] = v2;
-          dst[i + 96] = v3;
-        }
-        for (; i < n2; i += 32) dst[i] = src[i];
-      } else {
-        for (int i = lane; i < D; i += 32) pop[r * D + i] = trial[r * D + i];
-      }
-    }
+    int slot = 0;
+    if (lane == 0 && m) slot = atomicAdd(&s_count, __popc(m));
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (a) s_rows[slot + __popc(m & ((1u << lane) - 1u))] = threadIdx.x;
+    __syncthreads();
+    const int n = s_count;
+    for (int k = warp; k < n; k += 8) commit_copy_row(pop, trial, first + s_rows[k], D, vec, lane);
+    __syncthreads();  // the queue is reused by the CTA's next 256 rows
   }
 }
 

@@ -82,7 +82,7 @@ def test_step_by_step_equals_the_oracle_in_every_commit_mode(case, mode, monkeyp
         assert eng.kernel_family() == family
         in_place = eng.last_commit_in_place()
         if mode == 'auto':
-            assert in_place == (frac is None or frac < 0.30), (g, frac)
+            assert in_place == (frac is None or frac < (0.30 if dim > 128 else 0.12)), (g, frac)
         else:
             assert in_place == (mode == 'in_place')
         seen.add(in_place)
