@@ -370,7 +370,7 @@ void note_accepted(mb2_ctx* c, int64_t n_acc) {
 // smem.  Returns false when a row does not fit (the LDG kernel is used instead).
 // Measured on B200 at D=1024 (profiles/README.md): concurrency across rows matters most (8 groups
 // beat 4 groups with deeper rings), then warps per row, then stages.
-bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
+bool tma_geometry(int dim, bool in_place, int* groups, int* gwarps, int* stages, int* smem) {
   const size_t row = (((size_t)(dim + (dim & 1)) * 8) + 127) & ~(size_t)127;  // (rows of odd length: the 16-byte aligned cover, dim + 1 elements)
   const size_t budget = 220 * 1024;
   if (row * 4 > budget) return false;
@@ -381,6 +381,10 @@ bool tma_geometry(int dim, int* groups, int* gwarps, int* stages, int* smem) {
   // more warps per row only add barrier and per-warp overhead once the CTA is full)
   int gw = 1;
   while (gw < 8 && g * (gw * 2) * 32 <= kTmaMaxThreads && (gw * 2) * 32 * 8 <= dim) gw <<= 1;
+  // Generations committed in place are no longer bound by HBM but by the groups' own instruction streams: half as
+  // many warps per row when that brings the CTA down to 512 threads, i.e. into the 128-register build (BASELINE
+  // config 2, 8 groups: 2 warps per row 0.295 / 0.273 ms sustained / burst against 0.305 / 0.278 with 4)
+  if (in_place && gw >= 2 && g * gw * 32 > 512 && g * (gw / 2) * 32 <= 512) gw >>= 1;
   if (gw > 1 && g > 15) g = 15;  // groups of several warps synchronise on named barriers 1..15
   // One-warp groups (D < 512): 16 groups in a 512-thread CTA -- the 128-register build; the 64 registers of a
   // 1024-thread CTA make the griewangk body spill -- with the ring as deep as shared memory allows.  B200 sweep at
@@ -626,7 +630,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   TmaKernel kt = nullptr;
   int tg = 0, tw = 0, ts = 0, tsmem = 0;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && bulk_ok && env_int("MB2_TMA", 1) != 0 && !datafit &&
-      !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, &tg, &tw, &ts, &tsmem))
+      !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, want_in_place(c), &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
   // the other strategies read a short window of the donors: K2e keeps long rows in a TMA ring
   ExpTmaKernel kx = nullptr;
