@@ -195,6 +195,12 @@ struct mb2_ctx {
   // saw is below kInPlaceMaxAccept (a rejected row then costs no write, an accepted one three row transfers)
   int commit_mode = MB2_COMMIT_AUTO;
   double acc_hint = -1.0;  // accepted fraction of the last generation read back (-1: none yet)
+  // the epilogue kernel also writes the accepted count of every generation into pinned host memory (no
+  // synchronisation: the value is a few launches old at worst and only steers a choice between two equivalent paths),
+  // so `auto` follows the run even when the host never reads a result (mb2_step loops)
+  long long* h_hint = nullptr;  // pinned, mapped: accepted count of the last generation finalised, -1 = none yet
+  long long* d_hint = nullptr;  // the same location as the device sees it
+  int batch_in_place = -1;      // mb2_run: the decision taken for the whole batch (-1: none)
   int last_sparse = 0;     // the last fused launch wrote accepted rows only
   int run_sparse = 0;      // ... and so did the launches of the current batch (mb2_run)
   int xchg_no_adopt = 0;  // after mb2_exchange_reset: open a fresh mailbox
@@ -359,7 +365,18 @@ bool want_in_place(const mb2_ctx* c) {
   if (mode < MB2_COMMIT_AUTO || mode > MB2_COMMIT_IN_PLACE) mode = c->commit_mode;
   if (mode == MB2_COMMIT_DOUBLE_BUFFER) return false;
   if (mode == MB2_COMMIT_IN_PLACE) return true;
-  return c->acc_hint < (c->dim > 128 ? kInPlaceMaxAccept : kInPlaceMaxAcceptShortRows);  // (no generation read back yet: in place)
+  if (c->batch_in_place >= 0) return c->batch_in_place != 0;  // one decision per batch of generations (mb2_run)
+  double hint = c->acc_hint;
+  if (c->h_hint != nullptr) {
+    const long long n = *reinterpret_cast<volatile long long*>(c->h_hint);
+    const int64_t denom = c->xchg_connected ? c->np_global : c->np;  // (the fused exchange sums the shards' counts)
+    if (n >= 0 && denom > 0) hint = (double)n / (double)denom;
+  }
+  return hint < (c->dim > 128 ? kInPlaceMaxAccept : kInPlaceMaxAcceptShortRows);  // (no generation finalised yet: in place)
+}
+void reset_hint(mb2_ctx* c) {
+  c->acc_hint = -1.0;
+  if (c->h_hint != nullptr) *c->h_hint = -1;
 }
 void note_accepted(mb2_ctx* c, int64_t n_acc) {
   const int64_t denom = (c->xchg_connected || c->counts_global) ? c->np_global : c->np;
@@ -836,7 +853,7 @@ int launch_finalize(mb2_ctx* c, int gen0, cudaStream_t stream) {
   de_finalize_kernel<<<1, 256, 0, stream>>>(c->part_e, c->part_idx, c->part_ninf, c->part_nacc, c->grid,
                                             c->pop[c->cur ^ 1], c->dim, c->offset, gen0, c->generation + 1,
                                             c->best_x, c->st, (c->run_active && !gen0) ? c->run : nullptr,
-                                            next_exchange(c));
+                                            next_exchange(c), gen0 ? nullptr : c->d_hint);
   CUDA_TRY(cudaGetLastError());
   ++c->launches;
   return MB2_OK;
@@ -900,6 +917,17 @@ int mb2_create_ws(int device, int64_t np_local, int32_t dim, int64_t np_global, 
   if (!rc) rc = dev_alloc(c, sizeof(double) * dim, &p), c->init_lo = (double*)p;
   if (!rc) rc = dev_alloc(c, sizeof(double) * dim, &p), c->init_hi = (double*)p;
   if (!rc) rc = host_alloc(c, sizeof(DeviceState), &p), c->h_st = (DeviceState*)p;
+  if (!rc) {
+    void* hp = nullptr;
+    void* dp = nullptr;
+    if (host_alloc(c, 64, &hp) == MB2_OK && cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
+      c->h_hint = (long long*)hp;
+      c->d_hint = (long long*)dp;
+      *c->h_hint = -1;
+    } else {
+      cudaGetLastError();  // (pinned memory the device cannot address: `auto` follows the host's reads only)
+    }
+  }
   if (!rc) rc = host_alloc(c, sizeof(double) * dim, &p), c->h_best_x = (double*)p;
   if (!rc) rc = ensure_parts(c, 1);
   if (!rc) rc = ensure_exp_length_table(c, c->CR);
@@ -1281,7 +1309,7 @@ int mb2_init_population(mb2_ctx* c, uint64_t seed, const double* lo, const doubl
   c->generation = -1;
   c->rows_in_range = 0;
   c->rows_checked = 0;
-  c->acc_hint = -1.0;
+  reset_hint(c);
   return MB2_OK;
 }
 
@@ -1300,7 +1328,7 @@ int mb2_upload_population(mb2_ctx* c, const double* pop_host, void* stream) {
   c->generation = -1;
   c->rows_in_range = 0;
   c->rows_checked = 0;
-  c->acc_hint = -1.0;
+  reset_hint(c);
   return MB2_OK;
 }
 
@@ -1317,7 +1345,7 @@ int mb2_restore_state(mb2_ctx* c, const double* energy_host, double best_energy,
   c->generation = generation;
   c->rows_in_range = 0;  // the caller installed rows this context has not checked
   c->rows_checked = 0;
-  c->acc_hint = -1.0;
+  reset_hint(c);
   return MB2_OK;
 }
 
@@ -1453,6 +1481,8 @@ int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
   c->run_enqueued = max_steps;
   int rc = MB2_OK;
   c->run_sparse = 0;
+  c->batch_in_place = -1;
+  c->batch_in_place = want_in_place(c) ? 1 : 0;  // (the asynchronous hint may move while the batch is enqueued)
   for (int k = 0; k < max_steps && rc == MB2_OK; ++k) {
     rc = launch_step(c, MODE_STEP, c->pop[c->cur], c->pop[c->cur ^ 1], c->en[c->cur], c->en[c->cur ^ 1], c->np, s);
     if (rc == MB2_OK && k == 0) c->run_sparse = c->last_sparse;
@@ -1464,6 +1494,7 @@ int mb2_run(mb2_ctx* c, int32_t max_steps, double* log_dev, void* stream) {
       c->generation += 1;
     }
   }
+  c->batch_in_place = -1;
   c->run_active = 0;
   return rc;
 }

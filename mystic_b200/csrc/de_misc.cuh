@@ -113,7 +113,7 @@ __device__ __forceinline__ void finalize_body(const double* __restrict__ part_e,
                                               const unsigned long long* __restrict__ part_nacc, int nparts,
                                               const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
                                               int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
-                                              RunState* __restrict__ rs, const ExchangeParams& X) {
+                                              RunState* __restrict__ rs, const ExchangeParams& X, long long* hint = nullptr) {
   if (rs != nullptr && rs->stop) return;  // batch mode: this generation was not run
   __shared__ double sh_e[256];
   __shared__ int64_t sh_i[256];
@@ -182,6 +182,9 @@ __device__ __forceinline__ void finalize_body(const double* __restrict__ part_e,
       return;
     }
   }
+  // the accepted count of this generation for the host's choice of the commit mode (pinned host memory, no fence:
+  // a stale value is as good as a fresh one)
+  if (hint != nullptr && threadIdx.x == 0) *reinterpret_cast<volatile long long*>(hint) = st->n_acc;  // (thread 0 wrote st->n_acc)
   if (rs == nullptr) return;
   __syncthreads();
   // ---- batch mode: log the generation, then the host part of Step(): counters and termination
@@ -243,8 +246,8 @@ __global__ void __launch_bounds__(256)
                        const unsigned long long* __restrict__ part_nacc, int nparts,
                        const double* __restrict__ pop_next, int D, int64_t global_offset, int gen0,
                        int64_t generation, double* __restrict__ best_x, DeviceState* __restrict__ st,
-                       RunState* __restrict__ rs, const __grid_constant__ ExchangeParams X) {
-  finalize_body(part_e, part_idx, part_ninf, part_nacc, nparts, pop_next, D, global_offset, gen0, generation, best_x, st, rs, X);
+                       RunState* __restrict__ rs, const __grid_constant__ ExchangeParams X, long long* hint) {
+  finalize_body(part_e, part_idx, part_ninf, part_nacc, nparts, pop_next, D, global_offset, gen0, generation, best_x, st, rs, X, hint);
 }
 
 // Batch of independent solvers: one CTA per island (blockIdx.x), each with its own partials
