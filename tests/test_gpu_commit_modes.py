@@ -159,3 +159,32 @@ def test_other_kernel_families_keep_the_double_buffer(monkeypatch):
         assert eng.kernel_family() in ('rows_per_warp', 'thread_per_row')
         assert not eng.last_commit_in_place()
         eng.close()
+
+
+def test_auto_follows_the_accepted_fraction_without_host_reads(monkeypatch):
+    """mb2_step loops that never read a result: the epilogue kernel leaves every generation's accepted count in pinned
+    host memory, and the next launch commits in place iff that fraction is below the threshold (0.12 for these short
+    rows) -- checked against the oracle's accepted counts, generation by generation"""
+    import torch
+    monkeypatch.delenv('MB2_COMMIT_MODE', raising=False)
+    case = (32, 333, 'Best1Exp', 'rosen', (-2., 2., orc.BOUNDS_CLAMP), None, 0.5, 0.5, 40, 'rows_bulk')
+    dim, NP, strat, cost, bounds, pen, CR, F, gens, family = case
+    seed = 0xA0700000
+    eng, st = _start(case, 'auto', seed)
+    ocost = orc.make_cost(cost, ())
+    eng.eval_initial()
+    orc.step0(st, ocost, ())
+    torch.cuda.synchronize()
+    prev = None
+    seen = set()
+    for g in range(1, gens + 1):
+        eng.step()
+        torch.cuda.synchronize()   # (not a read of the result: the hint is whatever the epilogue wrote)
+        expect = prev is None or prev / NP < 0.12
+        assert eng.last_commit_in_place() == expect, (g, prev)
+        seen.add(expect)
+        orc.step(st, strat, CR, F, ocost, (), philox=dict(seed=seed, offset=0))
+        prev = int(st.accepted.sum())
+    assert seen == {True, False}, 'the case should cross the threshold (accepted counts: last %d of %d)' % (prev, NP)
+    _check(eng, st, cost, 'after %d generations without reads' % gens)
+    eng.close()
