@@ -190,6 +190,82 @@ static void run_bulk(const double* in, double* out, int64_t np, int D, int seg) 
          K, seg, ST, WARPS, R, occ, best, bytes / 1e9, bytes / 1e6 / best);
 }
 
+// Whole-row reads of an IN-PLACE generation of the full-row strategies (BASELINE configs 2 and 5): per candidate the
+// parent row and K random donor rows come in by bulk copies, nothing goes out.  A warp owns a ring of ST stages of
+// (1 + K) rows -- the fused kernel's groups x stages -- and touches one element per row.
+template <int K, int ST, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) rows_in_kernel(const double* __restrict__ in, double* __restrict__ out, int64_t np, int D,
+                                                             uint32_t salt) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bars[WARPS * ST];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned rowb = (unsigned)D * 8u;
+  const size_t stage_bytes = (size_t)(1 + K) * rowb;
+  unsigned char* my = smem + (size_t)warp * ST * stage_bytes;
+  uint64_t* bar = bars + warp * ST;
+  if (lane == 0)
+    for (int s = 0; s < ST; ++s) mbar_init(bar + s, 1);
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncwarp();
+  const int64_t gw = (int64_t)blockIdx.x * WARPS + warp, nw = (int64_t)gridDim.x * WARPS;
+  auto issue = [&](int64_t c, int s) {
+    unsigned char* st = my + (size_t)s * stage_bytes;
+    if (lane == 0) mbar_expect_tx(bar + s, (unsigned)stage_bytes);
+    __syncwarp();
+    if (lane <= K) {
+      const uint32_t h = mix((uint32_t)c * 0x9E3779B9u + salt);
+      const int64_t r = lane == 0 ? c : (int64_t)(mix(h + 0x51ED270Bu * lane) % (uint32_t)np);
+      bulk_g2s(st + (size_t)lane * rowb, in + r * D, rowb, bar + s);
+    }
+  };
+  for (int s = 0; s < ST; ++s)
+    if (gw + s * nw < np) issue(gw + s * nw, s);
+  int s = 0;
+  unsigned parity = 0;
+  double acc = 0.0;
+  for (int64_t c = gw; c < np; c += nw) {
+    unsigned char* st = my + (size_t)s * stage_bytes;
+    mbar_wait(bar + s, parity);
+    if (lane <= K) acc += *reinterpret_cast<double*>(st + (size_t)lane * rowb);
+    __syncwarp();
+    if (c + (int64_t)ST * nw < np) issue(c + (int64_t)ST * nw, s);
+    if (++s == ST) {
+      s = 0;
+      parity ^= 1u;
+    }
+  }
+  if (acc == 12345.678) out[0] = acc;
+}
+
+template <int K, int ST, int WARPS>
+static void run_rows_in(const double* in, double* out, int64_t np, int D) {
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const size_t smem = (size_t)WARPS * ST * (1 + K) * (size_t)D * 8;
+  cudaFuncSetAttribute(rows_in_kernel<K, ST, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int occ = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rows_in_kernel<K, ST, WARPS>, WARPS * 32, smem);
+  if (occ < 1) {
+    printf("{\"rows_in\": true, \"error\": \"does not fit\", \"smem\": %zu}\n", smem);
+    return;
+  }
+  const int grid = 148 * occ;
+  float best = 1e30f;
+  for (int rep = 0; rep < 12; ++rep) {
+    cudaEventRecord(e0);
+    rows_in_kernel<K, ST, WARPS><<<grid, WARPS * 32, smem>>>(in, out, np, D, 17u * rep + 1u);
+    cudaEventRecord(e1);
+    cudaEventSynchronize(e1);
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep >= 2 && ms < best) best = ms;
+  }
+  const double bytes = (double)np * (1.0 + K) * D * 8.0;
+  printf("{\"rows_in\": true, \"donors\": %d, \"stages\": %d, \"warps\": %d, \"ctas_per_sm\": %d, \"rows_in_flight_per_sm\": %d, \"ms\": %.4f, \"requested_GB\": %.4f, \"GBps\": %.1f}\n",
+         K, ST, WARPS, occ, occ * WARPS * ST * (1 + K), best, bytes / 1e9, bytes / 1e6 / best);
+}
+
 template <int K>
 static void run(const double* in, double* out, int64_t np, int D, int seg, int ctas_per_sm) {
   cudaEvent_t e0, e1;
@@ -219,6 +295,23 @@ int main(int argc, char** argv) {
   cudaMalloc(&b, sizeof(double) * np * D);
   cudaMemset(a, 0, sizeof(double) * np * D);
   cudaMemset(b, 0, sizeof(double) * np * D);
+  if (argc > 3 && argv[3][0] == 'r') {  // `rows`: whole-row reads of an in-place generation (parent + 2 donors in, nothing out)
+    if (D >= 512) {
+      run_rows_in<2, 1, 8>(a, b, np, D);    // the fused kernel's ring at config 2: 8 groups x 1 stage x 3 rows
+      run_rows_in<2, 1, 6>(a, b, np, D);
+      run_rows_in<2, 1, 4>(a, b, np, D);
+      run_rows_in<2, 2, 4>(a, b, np, D);
+      run_rows_in<0, 1, 24>(a, b, np, D);   // contiguous rows only: the streaming-read ceiling of the mechanism
+      run_rows_in<0, 2, 12>(a, b, np, D);
+    } else {
+      run_rows_in<2, 2, 16>(a, b, np, D);   // config 5: 16 groups x 2 stages x 3 rows
+      run_rows_in<2, 1, 32>(a, b, np, D);
+      run_rows_in<2, 3, 10>(a, b, np, D);
+      run_rows_in<0, 4, 24>(a, b, np, D);
+    }
+    cudaDeviceSynchronize();
+    return 0;
+  }
   if (D >= 512) {  // long rows (x2: Rosenbrock 1024-D, exponential crossover): one row per stage
     run_bulk<0, 1, 16, 1>(a, b, np, D, 0);
     run_bulk<0, 2, 8, 1>(a, b, np, D, 0);
