@@ -16,6 +16,7 @@
 #include "de_kernels.cuh"
 #include "de_misc.cuh"
 #include "de_tma.cuh"
+#include "de_tma_pool.cuh"
 #include "de_cheb_mma.cuh"
 #include "de_small.cuh"
 #include "de_subwarp.cuh"
@@ -282,6 +283,8 @@ typedef void (*ExpTmaKernel)(const StepParams, int, int, int, int);
 namespace mb2 {
 StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
+typedef void (*PoolKernel)(const StepParams, int, int);
+PoolKernel get_pool_kernel(int cost);  // K2p: de_tma_pool.cuh
 ExpTmaKernel get_exp_tma_kernel_even(int cost, int gwarps, int threads);
 ExpTmaKernel get_exp_tma_kernel_odd(int cost, int gwarps, int threads);  // rows of odd length
 inline ExpTmaKernel get_exp_tma_kernel(int cost, int gwarps, int threads, int dim) {
@@ -421,6 +424,31 @@ bool tma_geometry(int dim, bool in_place, int* groups, int* gwarps, int* stages,
   *gwarps = gw;
   *stages = st;
   *smem = (int)(row + (size_t)g * st * 3 * row);
+  return true;
+}
+
+// Pool geometry of K2p (de_tma_pool.cuh: in-place Best1Bin generations of rows whose K2a ring has one stage): P pairs +
+// Q first-donor buffers out of the row buffers that fit beside bestSolution; 8 consumer groups of 2 warps.
+bool pool_geometry(int dim, int* pairs, int* d0s, int* groups, int* smem) {
+  if (dim % 2 != 0 || dim < 768 || dim > 1536 || env_int("MB2_TMA_POOL", 1) == 0) return false;
+  const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
+  const size_t budget = 220 * 1024;
+  const int slots = (int)((budget - row) / row);
+  // a pair lives from its request to the end of the trial loop, a first-donor buffer until its row is selected
+  // (about 3 : 2 with the cost evaluation of rosen at 1024 dimensions): Q ~ 0.4 of the buffers
+  int q = (slots * 2 + 2) / 5, p = (slots - q) / 2, g = 8;
+  const int ep = env_int("MB2_POOL_P", 0), eq = env_int("MB2_POOL_Q", 0), egp = env_int("MB2_POOL_G", 0);
+  if (ep >= 1 && eq >= 1 && 2 * ep + eq <= slots && ep <= kPoolMaxRing && eq <= kPoolMaxRing) p = ep, q = eq;
+  if (egp >= 1 && egp <= 8) g = egp;
+  // a consumer group looks at the `full` barrier of its NEXT row (k + G, slot (k + G) mod Q) as soon as it is done with
+  // row k; the parity test only tells phase n from phase n - 1, so that slot's previous row (k + G - Q) must have been
+  // issued by then: Q >= G
+  if (g > q) g = q;
+  if (p < 2 || q < 2 || p > kPoolMaxRing || q > kPoolMaxRing) return false;
+  *pairs = p;
+  *d0s = q;
+  *groups = g;
+  *smem = (int)(row * (size_t)(1 + 2 * p + q));
   return true;
 }
 
@@ -643,17 +671,28 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
                    : (separable ? get_separable_subwarp_kernel(lpr, vec) : get_subwarp_kernel(c->cost, lpr, vec));
   }
 
+  // a generation of the context's own buffers may be committed in place (decided before the geometries: K2a / K2e / K2p
+  // size their rings for it)
+  const bool in_place_req = mode == MODE_STEP && in_rows == c->pop[c->cur] && out_rows == c->pop[c->cur ^ 1] && e_in == c->en[c->cur] &&
+                            e_out == c->en[c->cur ^ 1] && want_in_place(c);
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
-  int tg = 0, tw = 0, ts = 0, tsmem = 0;
+  PoolKernel kp = nullptr;
+  int tg = 0, tw = 0, ts = 0, tsmem = 0, pool_p = 0, pool_q = 0;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && bulk_ok && env_int("MB2_TMA", 1) != 0 && !datafit &&
-      !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, want_in_place(c), &tg, &tw, &ts, &tsmem))
+      !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, in_place_req, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
+  // in place, one-stage rings: the pooled producer / consumer kernel
+  if (kt != nullptr && in_place_req && ts == 1 && pool_geometry(c->dim, &pool_p, &pool_q, &tg, &tsmem)) {
+    kp = get_pool_kernel(c->cost);
+    if (kp != nullptr) tw = 2;
+    else tma_geometry(c->dim, in_place_req, &tg, &tw, &ts, &tsmem);  // (no instantiation for this cost: K2a's geometry again)
+  }
   // the other strategies read a short window of the donors: K2e keeps long rows in a TMA ring
   ExpTmaKernel kx = nullptr;
   int xcap = 0;
   if (mode == MODE_STEP && s.xover == XOVER_EXP && bulk_ok && env_int("MB2_TMA_EXP", 1) != 0 && !datafit && !cheb_mma &&
-      ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, want_in_place(c), &tg, &tw, &ts, &xcap, &tsmem))
+      ks == nullptr && kw == nullptr && exp_tma_geometry(c->dim, s.k, c->CR, in_place_req, &tg, &tw, &ts, &xcap, &tsmem))
     kx = get_exp_tma_kernel(c->cost, tw, tg * tw * 32, c->dim);
   // generation 0 of long rows is a read-clip-evaluate-write stream: the same staged kernel without draws or donors
   // (every strategy; the warp-per-row kernel needed 0.31 ms for it at BASELINE config 2)
@@ -697,6 +736,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     smem = (int)(sizeof(double) * (size_t)kSmallWarps * 32 * (c->dim | 1));
     CUDA_TRY(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, wpc * 32, smem));
+  } else if (kp != nullptr) {
+    wpc = tg * tw + 1;  // (+ the producer warp)
+    rows_per_cta = tg;
+    smem = tsmem;
+    CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, wpc * 32, smem));
   } else if (kt != nullptr) {
     wpc = tg * tw;
     rows_per_cta = tg;
@@ -731,9 +776,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   const bool by_rows = kc == nullptr && (kb != nullptr || (kw != nullptr && kw == kr));
   const bool by_groups = kc == nullptr && kb == nullptr && kw == nullptr && ks == nullptr;   // kt, kx or k
   const bool staged = by_rows || (by_groups && !(kt == nullptr && kx != nullptr && gen0_k));
-  const bool sparse = mode == MODE_STEP && staged &&
-                      in_rows == c->pop[c->cur] && out_rows == c->pop[c->cur ^ 1] && e_in == c->en[c->cur] && e_out == c->en[c->cur ^ 1] &&
-                      want_in_place(c);
+  const bool sparse = in_place_req && staged;
   P.sparse = sparse ? 1 : 0;
   c->last_sparse = P.sparse;
   c->wpc = wpc;
@@ -749,6 +792,8 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     kw<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (ks != nullptr)
     ks<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
+  else if (kp != nullptr)
+    kp<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, pool_p, pool_q);
   else if (kt != nullptr)
     kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
   else if (kx != nullptr)
