@@ -120,7 +120,7 @@ _UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9, 'Tbyte': 1e12}
 
 # the same kernels committing the generation in place (accepted trials only are written)
 NCU_SUMMARIES_IN_PLACE = {
-    'c2': ('profiles/r2_c2_inplace_ncu_full_summary.csv',),
+    'c2': ('profiles/r2_c2_pool_ncu_full_summary.csv', 'profiles/r2_c2_inplace_ncu_full_summary.csv'),
     'x2': ('profiles/r2_x2_inplace_ncu_full_summary.csv',),
     'c4': ('profiles/r2_c4_inplace_ncu_full_summary.csv',),
     'c5': ('profiles/r2_c5_inplace_ncu_full_summary.csv',),
@@ -520,6 +520,13 @@ def device_leg(rig, name, w):
     return out
 
 
+def kernel_name(leg):
+    """family of the fused kernel; K2p (de_tma_pool.cuh) is told from K2a by its producer warp (an odd warp count)"""
+    if leg['family'] == 'tma_bin' and (leg['block'] // 32) % 2 == 1:
+        return 'tma_bin: de_step_best1bin_pool_kernel'
+    return leg['family']
+
+
 def roofline_of(rig, leg):
     w, name, NP_local = leg['w'], leg['name'], leg['NP_local']
     peaks = rig.peaks
@@ -539,7 +546,7 @@ def roofline_of(rig, leg):
                 'algorithmic_bytes_per_candidate': bpc, 'algorithmic_bytes_per_launch': bpc * NP_local,
                 'commit': 'in_place' if in_place else 'double_buffer',
                 'kernel': 'fused generation kernel (%s)%s + de_finalize_kernel, per generation, per GPU'
-                          % (leg['family'], ' + de_commit_accepted_kernel' if in_place else '')}
+                          % (kernel_name(leg), ' + de_commit_accepted_kernel' if in_place else '')}
     if in_place:
         # continuity with round 1 / SURVEY 8(d): the same step time against the bytes a double-buffered generation
         # would move (every row written); above 1 = faster than that design can be

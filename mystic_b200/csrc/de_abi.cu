@@ -284,7 +284,7 @@ namespace mb2 {
 StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
 typedef void (*PoolKernel)(const StepParams, int, int);
-PoolKernel get_pool_kernel(int cost);  // K2p: de_tma_pool.cuh
+PoolKernel get_pool_kernel(int cost, int gwarps);  // K2p: de_tma_pool.cuh
 ExpTmaKernel get_exp_tma_kernel_even(int cost, int gwarps, int threads);
 ExpTmaKernel get_exp_tma_kernel_odd(int cost, int gwarps, int threads);  // rows of odd length
 inline ExpTmaKernel get_exp_tma_kernel(int cost, int gwarps, int threads, int dim) {
@@ -429,17 +429,20 @@ bool tma_geometry(int dim, bool in_place, int* groups, int* gwarps, int* stages,
 
 // Pool geometry of K2p (de_tma_pool.cuh: in-place Best1Bin generations of rows whose K2a ring has one stage): P pairs +
 // Q first-donor buffers out of the row buffers that fit beside bestSolution; 8 consumer groups of 2 warps.
-bool pool_geometry(int dim, int* pairs, int* d0s, int* groups, int* smem) {
+bool pool_geometry(int dim, int* pairs, int* d0s, int* groups, int* gwarps, int* smem) {
   if (dim % 2 != 0 || dim < 768 || dim > 1536 || env_int("MB2_TMA_POOL", 1) == 0) return false;
   const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
   const size_t budget = 220 * 1024;
   const int slots = (int)((budget - row) / row);
-  // a pair lives from its request to the end of the trial loop, a first-donor buffer until its row is selected
-  // (about 3 : 2 with the cost evaluation of rosen at 1024 dimensions): Q ~ 0.4 of the buffers
-  int q = (slots * 2 + 2) / 5, p = (slots - q) / 2, g = 8;
+  // a pair lives from its request to the end of the trial loop, a first-donor buffer until its row is selected; B200 sweep
+  // at 1024 dimensions (26 buffers, tools/k2p_ab.sh): 7 groups, 7 pairs + 12 buffers 0.237 ms, 8 / 7 + 12 0.240, 7 / 8 + 10
+  // 0.242, 8 / 8 + 10 0.246, 8 / 6 + 14 0.251, 6 / 7 + 12 0.257 (K2a: 0.274)
+  int q = (slots * 12 + 13) / 26, p = (slots - q) / 2;
+  int gw = env_int("MB2_POOL_GW", 2) == 4 ? 4 : 2;
+  int g = gw == 4 ? 4 : 7;
   const int ep = env_int("MB2_POOL_P", 0), eq = env_int("MB2_POOL_Q", 0), egp = env_int("MB2_POOL_G", 0);
   if (ep >= 1 && eq >= 1 && 2 * ep + eq <= slots && ep <= kPoolMaxRing && eq <= kPoolMaxRing) p = ep, q = eq;
-  if (egp >= 1 && egp <= 8) g = egp;
+  if (egp >= 1 && egp * gw <= 16) g = egp;
   // a consumer group looks at the `full` barrier of its NEXT row (k + G, slot (k + G) mod Q) as soon as it is done with
   // row k; the parity test only tells phase n from phase n - 1, so that slot's previous row (k + G - Q) must have been
   // issued by then: Q >= G
@@ -448,6 +451,7 @@ bool pool_geometry(int dim, int* pairs, int* d0s, int* groups, int* smem) {
   *pairs = p;
   *d0s = q;
   *groups = g;
+  *gwarps = gw;
   *smem = (int)(row * (size_t)(1 + 2 * p + q));
   return true;
 }
@@ -683,10 +687,9 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
       !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, in_place_req, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
   // in place, one-stage rings: the pooled producer / consumer kernel
-  if (kt != nullptr && in_place_req && ts == 1 && pool_geometry(c->dim, &pool_p, &pool_q, &tg, &tsmem)) {
-    kp = get_pool_kernel(c->cost);
-    if (kp != nullptr) tw = 2;
-    else tma_geometry(c->dim, in_place_req, &tg, &tw, &ts, &tsmem);  // (no instantiation for this cost: K2a's geometry again)
+  if (kt != nullptr && in_place_req && ts == 1 && pool_geometry(c->dim, &pool_p, &pool_q, &tg, &tw, &tsmem)) {
+    kp = get_pool_kernel(c->cost, tw);
+    if (kp == nullptr) tma_geometry(c->dim, in_place_req, &tg, &tw, &ts, &tsmem);  // (no instantiation for this cost: K2a's geometry again)
   }
   // the other strategies read a short window of the donors: K2e keeps long rows in a TMA ring
   ExpTmaKernel kx = nullptr;

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_full[kPoolMaxRing], s_pair_free[kPoolMaxRing], s_d0_free[kPoolMaxRing];
   __shared__ double s_scratch[kPoolMaxGroups * 16];
-  __shared__ int s_nstart[kPoolMaxRing];
+  __shared__ int2 s_nstart[kPoolMaxRing];  // {crossover start index, row number k} of the row in each first-donor slot
   __shared__ double sh_e[kPoolMaxGroups];
   __shared__ int64_t sh_i[kPoolMaxGroups];
   __shared__ unsigned long long sh_ninf[kPoolMaxGroups], sh_nacc[kPoolMaxGroups];
@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(MAXT, 1)
           const int64_t c = c0 + k * cstep;
           if (k >= PR) mbar_wait(s_pair_free + p, pphase);
           if (k >= QR) mbar_wait(s_d0_free + q, qphase);
-          s_nstart[q] = nsj;
+          s_nstart[q] = make_int2(nsj, (int)k);
           unsigned char* pb = s_pairs + (unsigned)(2 * p) * row_stride;
           mbar_expect_tx(s_full + q, 3u * row_bytes);  // (the arrive publishes s_nstart)
           bulk_g2s(pb, P.pop_cur + c * D, row_bytes, s_full + q);
@@ -155,8 +155,19 @@ __global__ void __launch_bounds__(MAXT, 1)
       const uint32_t cand_g = (uint32_t)(P.global_offset + c);
       const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
 
-      group_wait_stage(grp, s_full + q, fparity);
-      const int nstart = s_nstart[q];
+      // A parity test tells phase n from phase n - 1 only: were the slot still loading its PREVIOUS row (k - Q, issued
+      // before any row this group has finished, but not necessarily landed), the test would pass one phase early.  The
+      // producer therefore publishes the row number with the start index, and a group that finds another row's number
+      // waits again (never seen in practice: a row's copies would have to outlast the whole processing of a later row).
+      if (GW == 1 || grp.wig == 0) {  // (the group's first warp polls, the others block on the named barrier: group_wait_stage)
+        int seen;
+        do {
+          mbar_wait(s_full + q, fparity);
+          seen = reinterpret_cast<volatile int2*>(s_nstart + q)->y;
+        } while (seen != (int)k);
+      }
+      if (GW > 1) group_sync(grp);
+      const int nstart = s_nstart[q].x;
 
       // ---- trial vector (strategy.py:77-85): K2a's loop (de_tma.cuh), rows of even length
       bool oob = false;

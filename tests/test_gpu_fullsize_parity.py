@@ -30,7 +30,7 @@ def _bits_equal(a, b, what):
                              % (what, len(bad), a.size, tuple(bad[0]), a[tuple(bad[0])], b[tuple(bad[0])]))
 
 
-def _run(NP, D, strategy, cost, extra, lo, hi, bounds, CR, F, pen, family, gens=2, tensor_cores=False, seed=0x5EED):
+def _run(NP, D, strategy, cost, extra, lo, hi, bounds, CR, F, pen, family, gens=2, tensor_cores=False, seed=0x5EED, check=None):
     from mystic_b200 import models, penalty
     from mystic_b200.engine import DeviceEngine
     if not c_port.available():
@@ -101,6 +101,8 @@ def _run(NP, D, strategy, cost, extra, lo, hi, bounds, CR, F, pen, family, gens=
             accepted += n_acc
         del pop
     assert eng.kernel_family() == family, eng.kernel_family()
+    if check is not None:
+        check(eng)
     grid, block, smem = eng.launch_info()
     print('%s %s D=%d NP=%d: %d generations bit-identical to the C oracle port%s; %d trials accepted; grid %d x %d'
           % (strategy, cost, D, NP, gens, (' but for %d near-tie selections %s' % (len(ties), ties)) if ties else '', accepted,
