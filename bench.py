@@ -521,9 +521,9 @@ def device_leg(rig, name, w):
 
 
 def kernel_name(leg):
-    """family of the fused kernel; K2p (de_tma_pool.cuh) is told from K2a by its producer warp (an odd warp count)"""
-    if leg['family'] == 'tma_bin' and (leg['block'] // 32) % 2 == 1:
-        return 'tma_bin: de_step_best1bin_pool_kernel'
+    """family of the fused kernel, with the kernel's name where the family has one kernel"""
+    if leg['family'] == 'tma_pool':
+        return 'tma_pool: de_step_best1bin_pool_kernel'
     return leg['family']
 
 

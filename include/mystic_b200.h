@@ -322,7 +322,8 @@ enum mb2_kernel_family_id {
   MB2_KERNEL_THREAD_PER_ROW = 6, /* de_small.cuh */
   MB2_KERNEL_DMMA = 7,           /* de_cheb_mma.cuh: FP64 tensor-core contraction */
   MB2_KERNEL_ISLANDS = 8,        /* batch of solvers, grid.y = island */
-  MB2_KERNEL_ROWS_BULK = 9       /* de_rows_bulk.cuh: the rows kernel's step with cp.async.bulk staging */
+  MB2_KERNEL_ROWS_BULK = 9,      /* de_rows_bulk.cuh: the rows kernel's step with cp.async.bulk staging */
+  MB2_KERNEL_TMA_POOL = 10       /* de_tma_pool.cuh: Best1Bin committed in place, row buffers pooled behind producer warps */
 };
 int mb2_kernel_family(mb2_ctx* ctx);
 

@@ -16,7 +16,7 @@ LIBDIR = os.path.join(HERE, '_lib')
 OBJDIR = os.path.join(LIBDIR, 'obj')
 LIBPATH = os.path.join(LIBDIR, 'libmystic_b200.so')
 
-SOURCES = ['de_abi.cu', 'inst_ldg_exp.cu', 'inst_ldg_bin.cu', 'inst_tma_512.cu', 'inst_tma_1024.cu', 'inst_tma_768.cu', 'inst_tma_exp.cu', 'inst_tma_exp_odd.cu', 'inst_tma_pool.cu', 'inst_tma_pool4.cu', 'inst_small.cu', 'inst_subwarp.cu',
+SOURCES = ['de_abi.cu', 'inst_ldg_exp.cu', 'inst_ldg_bin.cu', 'inst_tma_512.cu', 'inst_tma_1024.cu', 'inst_tma_768.cu', 'inst_tma_exp.cu', 'inst_tma_exp_odd.cu', 'inst_tma_pool.cu', 'inst_tma_pool4.cu', 'inst_tma_pool1.cu', 'inst_small.cu', 'inst_subwarp.cu',
            'inst_rows_rosen.cu', 'inst_rows_corana.cu', 'inst_rows_griewangk.cu', 'inst_rows_bulk_rosen.cu', 'inst_rows_bulk_corana.cu', 'inst_rows_bulk_griewangk.cu', 'inst_datafit.cu', 'inst_separable.cu', 'probe.cu']
 HEADERS = ['philox.cuh', 'de_device.cuh', 'de_kernels.cuh', 'de_misc.cuh', 'de_tma.cuh', 'de_tma_pool.cuh', 'de_tma_exp.cuh', 'de_cheb_mma.cuh', 'de_small.cuh', 'de_subwarp.cuh', 'de_rows.cuh', 'de_rows_bulk.cuh',
            os.path.join('..', '..', 'include', 'mystic_b200.h')]

@@ -283,7 +283,7 @@ typedef void (*ExpTmaKernel)(const StepParams, int, int, int, int);
 namespace mb2 {
 StepKernel get_ldg_kernel(int base, int xover, int cost, bool vec);
 TmaKernel get_tma_kernel(int cost, int gwarps, int threads);
-typedef void (*PoolKernel)(const StepParams, int, int);
+typedef void (*PoolKernel)(const StepParams, int, int, int);
 PoolKernel get_pool_kernel(int cost, int gwarps);  // K2p: de_tma_pool.cuh
 ExpTmaKernel get_exp_tma_kernel_even(int cost, int gwarps, int threads);
 ExpTmaKernel get_exp_tma_kernel_odd(int cost, int gwarps, int threads);  // rows of odd length
@@ -429,29 +429,46 @@ bool tma_geometry(int dim, bool in_place, int* groups, int* gwarps, int* stages,
 
 // Pool geometry of K2p (de_tma_pool.cuh: in-place Best1Bin generations of rows whose K2a ring has one stage): P pairs +
 // Q first-donor buffers out of the row buffers that fit beside bestSolution; 8 consumer groups of 2 warps.
-bool pool_geometry(int dim, int* pairs, int* d0s, int* groups, int* gwarps, int* smem) {
-  if (dim % 2 != 0 || dim < 768 || dim > 1536 || env_int("MB2_TMA_POOL", 1) == 0) return false;
+bool pool_geometry(int dim, int* pairs, int* d0s, int* groups, int* gwarps, int* nprod, int* smem) {
+  if (env_int("MB2_TMA_POOL", 1) == 0 || dim % 2 != 0 || dim > 1536) return false;
+  // rows of 256 .. 766 dimensions (K2a: one-warp groups with rings of two stages, BASELINE config 5): one-warp consumer
+  // groups and two producer warps
+  const bool short_rows = dim < 768;
+  if (short_rows && (dim < 256 || env_int("MB2_POOL_SHORT", 0) == 0)) return false;
   const size_t row = (((size_t)dim * 8) + 127) & ~(size_t)127;
-  const size_t budget = 220 * 1024;
-  const int slots = (int)((budget - row) / row);
+  const size_t budget = 218 * 1024;
+  int slots = (int)((budget - row) / row);
+  if (slots > 2 * kPoolMaxRing) slots = 2 * kPoolMaxRing;
   // a pair lives from its request to the end of the trial loop, a first-donor buffer until its row is selected; B200 sweep
   // at 1024 dimensions (26 buffers, tools/k2p_ab.sh): 7 groups, 7 pairs + 12 buffers 0.237 ms, 8 / 7 + 12 0.240, 7 / 8 + 10
-  // 0.242, 8 / 8 + 10 0.246, 8 / 6 + 14 0.251, 6 / 7 + 12 0.257 (K2a: 0.274)
+  // 0.242, 8 / 8 + 10 0.246, 8 / 6 + 14 0.251, 6 / 7 + 12 0.257 (K2a: 0.274); groups of 4 warps: 4 / 9 + 8 0.290
   int q = (slots * 12 + 13) / 26, p = (slots - q) / 2;
-  int gw = env_int("MB2_POOL_GW", 2) == 4 ? 4 : 2;
-  int g = gw == 4 ? 4 : 7;
+  int gw = short_rows ? 1 : 2;
+  const int egw = env_int("MB2_POOL_GW", 0);
+  if (egw == 1 || egw == 2 || egw == 4) gw = egw;
+  int np_ = 2;   // (config 2: 0.2384 ms with two producer warps, 0.2438 with one)
+  const int enp = env_int("MB2_POOL_NPROD", 0);
+  if (enp == 1 || enp == 2) np_ = enp;
+  const int max_warps = (gw == 1) ? 20 : 17;   // (the builds' __launch_bounds__: 640 / 544 threads; 5 warps per scheduler = 96 registers)
+  int g = gw == 4 ? 4 : gw == 2 ? 7 : 17;
   const int ep = env_int("MB2_POOL_P", 0), eq = env_int("MB2_POOL_Q", 0), egp = env_int("MB2_POOL_G", 0);
   if (ep >= 1 && eq >= 1 && 2 * ep + eq <= slots && ep <= kPoolMaxRing && eq <= kPoolMaxRing) p = ep, q = eq;
-  if (egp >= 1 && egp * gw <= 16) g = egp;
+  if (egp >= 1) g = egp;
+  while (g > 1 && g * gw + np_ > max_warps) --g;
+  if (gw > 1 && g > 15) g = 15;   // named barriers 1..15
+  if (g > kPoolMaxGroups) g = kPoolMaxGroups;
   // a consumer group looks at the `full` barrier of its NEXT row (k + G, slot (k + G) mod Q) as soon as it is done with
-  // row k; the parity test only tells phase n from phase n - 1, so that slot's previous row (k + G - Q) must have been
-  // issued by then: Q >= G
+  // row k; the parity test only tells phase n from phase n - 1, so that slot's previous row (k + G - Q) should have been
+  // issued by then (Q >= G; the row tag in the slot catches what is left)
   if (g > q) g = q;
-  if (p < 2 || q < 2 || p > kPoolMaxRing || q > kPoolMaxRing) return false;
+  if (p > kPoolMaxRing) p = kPoolMaxRing;
+  if (q > kPoolMaxRing) q = kPoolMaxRing;
+  if (p < 2 || q < 2) return false;
   *pairs = p;
   *d0s = q;
   *groups = g;
   *gwarps = gw;
+  *nprod = np_;
   *smem = (int)(row * (size_t)(1 + 2 * p + q));
   return true;
 }
@@ -682,12 +699,12 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   // Best1Bin reads whole donor rows: stage them with TMA bulk copies when rows are 16-B multiples
   TmaKernel kt = nullptr;
   PoolKernel kp = nullptr;
-  int tg = 0, tw = 0, ts = 0, tsmem = 0, pool_p = 0, pool_q = 0;
+  int tg = 0, tw = 0, ts = 0, tsmem = 0, pool_p = 0, pool_q = 0, pool_np = 1;
   if (mode == MODE_STEP && s.xover == XOVER_BIN && bulk_ok && env_int("MB2_TMA", 1) != 0 && !datafit &&
       !cheb_mma && ks == nullptr && kw == nullptr && tma_geometry(c->dim, in_place_req, &tg, &tw, &ts, &tsmem))
     kt = pick_tma_kernel(c->cost, tw, tg * tw * 32);
   // in place, one-stage rings: the pooled producer / consumer kernel
-  if (kt != nullptr && in_place_req && ts == 1 && pool_geometry(c->dim, &pool_p, &pool_q, &tg, &tw, &tsmem)) {
+  if (kt != nullptr && in_place_req && (ts == 1 || c->dim < 768) && pool_geometry(c->dim, &pool_p, &pool_q, &tg, &tw, &pool_np, &tsmem)) {
     kp = get_pool_kernel(c->cost, tw);
     if (kp == nullptr) tma_geometry(c->dim, in_place_req, &tg, &tw, &ts, &tsmem);  // (no instantiation for this cost: K2a's geometry again)
   }
@@ -740,7 +757,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
     CUDA_TRY(cudaFuncSetAttribute(ks, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, ks, wpc * 32, smem));
   } else if (kp != nullptr) {
-    wpc = tg * tw + 1;  // (+ the producer warp)
+    wpc = tg * tw + pool_np;  // (+ the producer warps)
     rows_per_cta = tg;
     smem = tsmem;
     CUDA_TRY(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -786,7 +803,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   c->grid = (int)grid;
   c->smem = smem;
   c->family = kc ? MB2_KERNEL_DMMA : kb ? MB2_KERNEL_ROWS_BULK : kr ? MB2_KERNEL_ROWS : kw ? MB2_KERNEL_ROWS_PER_WARP : ks ? MB2_KERNEL_THREAD_PER_ROW
-              : kt ? MB2_KERNEL_TMA_BIN : kx ? MB2_KERNEL_TMA_EXP : MB2_KERNEL_WARP_PER_ROW;
+              : kp ? MB2_KERNEL_TMA_POOL : kt ? MB2_KERNEL_TMA_BIN : kx ? MB2_KERNEL_TMA_EXP : MB2_KERNEL_WARP_PER_ROW;
   if (kc != nullptr)
     kc<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (kb != nullptr)
@@ -796,7 +813,7 @@ int launch_step(mb2_ctx* c, int mode, const double* in_rows, double* out_rows, c
   else if (ks != nullptr)
     ks<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, s.base, s.xover, s.k);
   else if (kp != nullptr)
-    kp<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, pool_p, pool_q);
+    kp<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, pool_p, pool_q, pool_np);
   else if (kt != nullptr)
     kt<<<(unsigned)grid, wpc * 32, smem, stream>>>(P, ts);
   else if (kx != nullptr)

@@ -23,18 +23,18 @@
 
 namespace mb2 {
 
-constexpr int kPoolMaxGroups = 15;   // consumer groups (named barriers 1..15)
-constexpr int kPoolMaxRing = 32;     // P, Q <= 32
+constexpr int kPoolMaxGroups = 24;   // consumer groups (groups of several warps: named barriers 1..15)
+constexpr int kPoolMaxRing = 64;     // P, Q <= 64
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// requires: D even, MODE_STEP, StepParams::sparse (in place), 16-byte aligned buffers.  blockDim = (G * GW + 1) * 32: the last warp is
-// the producer.
+// requires: D even, MODE_STEP, StepParams::sparse (in place), 16-byte aligned buffers.  blockDim = (G * GW + nprod) * 32: the last nprod (1 or 2)
+// warps are producers.
 template <int COST, int GW, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1)
-    de_step_best1bin_pool_kernel(const __grid_constant__ StepParams P, int npairs_ring, int nd0_ring) {
+    de_step_best1bin_pool_kernel(const __grid_constant__ StepParams P, int npairs_ring, int nd0_ring, int nprod) {
   if (P.stop != nullptr && *P.stop) return;  // batch mode: a termination condition was met earlier
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t s_full[kPoolMaxRing], s_pair_free[kPoolMaxRing], s_d0_free[kPoolMaxRing];
@@ -48,9 +48,9 @@ __global__ void __launch_bounds__(MAXT, 1)
   const unsigned row_bytes = (unsigned)D * 8u;
   const unsigned row_stride = (row_bytes + 127u) & ~127u;
   constexpr int gthreads = GW * 32;
-  const int ngroups = (blockDim.x / 32 - 1) / GW;
+  const int ngroups = (blockDim.x / 32 - nprod) / GW;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool producer = warp == ngroups * GW;
+  const bool producer = warp >= ngroups * GW;
   const int PR = npairs_ring, QR = nd0_ring;
 
   double* s_best = reinterpret_cast<double*>(smem_raw);
@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(MAXT, 1)
   for (int i = threadIdx.x; i < D; i += blockDim.x) s_best[i] = __ldg(P.best_x + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < QR; ++i) {
-      mbar_init(s_full + i, 1);
+      mbar_init(s_full + i, nprod);  // every producer warp arrives with the bytes of its copies
       mbar_init(s_d0_free + i, 1);
     }
     for (int i = 0; i < PR; ++i) mbar_init(s_pair_free + i, 1);
@@ -78,6 +78,14 @@ __global__ void __launch_bounds__(MAXT, 1)
     // lane 0 waits for each row's buffers in turn and issues its copies, so the serial chain per row is five shuffles, two
     // mbarrier tests, one expect_tx and three requests (the per-row resolve of a warp-uniform loop made the producer the
     // bottleneck: its ~150 instructions per row compete with 16 consumer warps for issue slots).
+    // Two producer warps (short rows, where one warp's serial chain per row would bound the kernel) split the COPIES, not
+    // the rows: the first serves the pair ring (parent + second donor), the second the first-donor ring and the row's
+    // tag; every ring then has ONE sequential writer, which is what keeps a parity test from passing a phase early.  The
+    // first also waits for the row's first-donor slot (a non-destructive test): its arrive on `full` must not fall into
+    // the slot's previous phase.
+    const int pw = warp - ngroups * GW;
+    const bool do_pairs = (pw == 0), do_d0 = (pw == nprod - 1);
+    const unsigned my_bytes = (do_pairs ? 2u * row_bytes : 0u) + (do_d0 ? row_bytes : 0u);
     int p = 0, q = 0;
     unsigned pphase = 0, qphase = 0;  // parity of the release a re-used ring slot waits for: ((k / ring) - 1) & 1
     for (int64_t kb = 0; kb < nrows; kb += 16) {
@@ -103,18 +111,21 @@ __global__ void __launch_bounds__(MAXT, 1)
         const int64_t k = kb + j;
         // row j's draws to every lane (warp-uniform from here: one lane issues, the others fall through to the
         // __syncwarp -- a lane-divergent spin on the mbarriers must not be left to the scheduler)
-        const int64_t rj0 = __shfl_sync(0xffffffffu, r[0], j), rj1 = __shfl_sync(0xffffffffu, r[1], j);
+        const int64_t rj = __shfl_sync(0xffffffffu, do_d0 ? r[0] : r[1], j);
         const int nsj = __shfl_sync(0xffffffffu, nstart, j);
+        const int64_t rj1 = (nprod == 1) ? __shfl_sync(0xffffffffu, r[1], j) : rj;
         if (lane == 0) {
           const int64_t c = c0 + k * cstep;
-          if (k >= PR) mbar_wait(s_pair_free + p, pphase);
+          if (do_pairs && k >= PR) mbar_wait(s_pair_free + p, pphase);
           if (k >= QR) mbar_wait(s_d0_free + q, qphase);
-          s_nstart[q] = make_int2(nsj, (int)k);
-          unsigned char* pb = s_pairs + (unsigned)(2 * p) * row_stride;
-          mbar_expect_tx(s_full + q, 3u * row_bytes);  // (the arrive publishes s_nstart)
-          bulk_g2s(pb, P.pop_cur + c * D, row_bytes, s_full + q);
-          bulk_g2s(s_d0s + (unsigned)q * row_stride, P.pop_cur + rj0 * D, row_bytes, s_full + q);
-          bulk_g2s(pb + row_stride, P.pop_cur + rj1 * D, row_bytes, s_full + q);
+          if (do_d0) s_nstart[q] = make_int2(nsj, (int)k);
+          mbar_expect_tx(s_full + q, my_bytes);  // (the arrive publishes s_nstart)
+          if (do_pairs) {
+            unsigned char* pb = s_pairs + (unsigned)(2 * p) * row_stride;
+            bulk_g2s(pb, P.pop_cur + c * D, row_bytes, s_full + q);
+            bulk_g2s(pb + row_stride, P.pop_cur + rj1 * D, row_bytes, s_full + q);
+          }
+          if (do_d0) bulk_g2s(s_d0s + (unsigned)q * row_stride, P.pop_cur + rj * D, row_bytes, s_full + q);
         }
         __syncwarp();
         if (++p == PR) {

@@ -3,7 +3,7 @@
 #include "de_tma_pool.cuh"
 
 namespace mb2 {
-typedef void (*PoolKernel)(const StepParams, int, int);
+typedef void (*PoolKernel)(const StepParams, int, int, int);
 
 // K2p: <= 4 consumer groups of 4 warps + the producer warp = 544 threads (120 registers)
 PoolKernel get_pool_kernel4(int cost) {

@@ -318,7 +318,7 @@ class DeviceEngine(object):
         check(lib.mb2_launch_info(self._ctx, ctypes.byref(g), ctypes.byref(b), ctypes.byref(s)))
         return g.value, b.value, s.value
 
-    KERNEL_FAMILIES = ('none', 'warp_per_row', 'tma_bin', 'tma_exp', 'rows', 'rows_per_warp', 'thread_per_row', 'dmma', 'islands', 'rows_bulk')
+    KERNEL_FAMILIES = ('none', 'warp_per_row', 'tma_bin', 'tma_exp', 'rows', 'rows_per_warp', 'thread_per_row', 'dmma', 'islands', 'rows_bulk', 'tma_pool')
 
     def kernel_family(self):
         """kernel family of the last fused launch (mb2_kernel_family)"""

@@ -82,7 +82,7 @@ def test_python_constants_match_the_header():
     names = DeviceEngine.KERNEL_FAMILIES
     assert len(names) == len(fam)
     alias = {'warp_per_row': 'warp_per_row', 'tma_bin': 'tma_bin', 'tma_exp': 'tma_exp', 'rows': 'rows', 'rows_per_warp': 'rows_per_warp',
-             'thread_per_row': 'thread_per_row', 'dmma': 'dmma', 'islands': 'islands', 'rows_bulk': 'rows_bulk', 'none': 'none'}
+             'thread_per_row': 'thread_per_row', 'dmma': 'dmma', 'islands': 'islands', 'rows_bulk': 'rows_bulk', 'none': 'none', 'tma_pool': 'tma_pool'}
     for i, n in enumerate(names):
         assert fam[alias[n]] == i, n
 

@@ -100,7 +100,7 @@ def _run(NP, D, strategy, cost, extra, lo, hi, bounds, CR, F, pen, family, gens=
         if g:
             accepted += n_acc
         del pop
-    assert eng.kernel_family() == family, eng.kernel_family()
+    assert eng.kernel_family() in (family if isinstance(family, tuple) else (family,)), eng.kernel_family()
     if check is not None:
         check(eng)
     grid, block, smem = eng.launch_info()
@@ -112,8 +112,9 @@ def _run(NP, D, strategy, cost, extra, lo, hi, bounds, CR, F, pen, family, gens=
 
 
 def test_config2_rosenbrock_1024d_np65536_best1bin():
-    """BASELINE config 2 on K2a (8 groups x 4 warps): every one of the 65 536 rows, every generation"""
-    _run(65536, 1024, 'Best1Bin', 'rosen', (), -5., 5., orc.BOUNDS_CLAMP, 0.9, 0.8, None, 'tma_bin')
+    """BASELINE config 2 on K2p (in place: 7 consumer groups x 2 warps + the producer warp) or K2a (double buffer, when
+    more than 0.30 of the trials were accepted): every one of the 65 536 rows, every generation"""
+    _run(65536, 1024, 'Best1Bin', 'rosen', (), -5., 5., orc.BOUNDS_CLAMP, 0.9, 0.8, None, ('tma_pool', 'tma_bin'))
 
 
 def test_config2_shape_rand1exp():

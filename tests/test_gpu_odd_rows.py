@@ -170,5 +170,5 @@ def test_every_supported_odd_row_length_launches_and_matches(dim, strat, CR, mon
         eng.step()
         orc.step(st, strat, CR, F, ocost, (), philox=dict(seed=seed, offset=0))
         _compare(eng, st, cost, 'D=%d %s gen %d (%s)' % (dim, strat, g, eng.kernel_family()))
-    assert eng.kernel_family() in ('tma_exp', 'tma_bin', 'warp_per_row')
+    assert eng.kernel_family() in ('tma_exp', 'tma_bin', 'tma_pool', 'warp_per_row')
     eng.close()

@@ -20,13 +20,15 @@ from tests.test_gpu_parity import energy_close
 
 pytestmark = pytest.mark.gpu
 
-POOL_ENV = ('MB2_TMA_POOL', 'MB2_POOL_P', 'MB2_POOL_Q', 'MB2_POOL_G', 'MB2_POOL_GW', 'MB2_COMMIT_MODE')
+POOL_ENV = ('MB2_TMA_POOL', 'MB2_POOL_P', 'MB2_POOL_Q', 'MB2_POOL_G', 'MB2_POOL_GW', 'MB2_POOL_NPROD', 'MB2_POOL_SHORT', 'MB2_COMMIT_MODE')
 
 GEOMETRIES = {
     'default': {},
     'small_rings': {'MB2_POOL_P': '2', 'MB2_POOL_Q': '3', 'MB2_POOL_G': '8'},       # G is clipped to Q; constant back-pressure
     'eight_groups': {'MB2_POOL_P': '8', 'MB2_POOL_Q': '10', 'MB2_POOL_G': '8'},
     'four_warps': {'MB2_POOL_GW': '4'},
+    'one_producer': {'MB2_POOL_NPROD': '1'},
+    'one_warp_groups': {'MB2_POOL_GW': '1', 'MB2_POOL_G': '11'},
     'one_group': {'MB2_POOL_G': '1', 'MB2_POOL_P': '3', 'MB2_POOL_Q': '2'},
 }
 
@@ -41,8 +43,7 @@ def geometry(request, monkeypatch):
 
 
 def _is_pool(eng):
-    grid, block, smem = eng.launch_info()
-    return (block // 32) % 2 == 1   # consumer groups of 2 or 4 warps + the producer warp
+    return eng.kernel_family() == 'tma_pool'
 
 
 @pytest.mark.parametrize('D,NP,cost,lo,hi,bounds', [
@@ -55,7 +56,7 @@ def test_full_grid_trajectory_equals_the_c_oracle(D, NP, cost, lo, hi, bounds, g
     """every CTA of a full grid revolves its rings several times; three generations against the C oracle port"""
     monkeypatch.setenv('MB2_COMMIT_MODE', '2')   # in place whatever the accepted fraction (`auto` leaves it above 0.30)
     seen = []
-    _run(NP, D, 'Best1Bin', cost, (), lo, hi, bounds, 0.9, 0.8, None, 'tma_bin', gens=3, check=lambda eng: seen.append(_is_pool(eng)))
+    _run(NP, D, 'Best1Bin', cost, (), lo, hi, bounds, 0.9, 0.8, None, 'tma_pool', gens=3, check=lambda eng: seen.append(_is_pool(eng)))
     assert seen == [True]
 
 
@@ -74,7 +75,7 @@ def test_pool_and_k2a_give_identical_bits(monkeypatch):
         eng.eval_initial()
         for g in range(gens):
             eng.step()
-            assert eng.kernel_family() == 'tma_bin' and _is_pool(eng) == (pool == '1')
+            assert eng.kernel_family() == ('tma_pool' if pool == '1' else 'tma_bin')
         out[pool] = (eng.population(), eng.energies(), eng.read_result())
         eng.close()
     G.assert_bits_equal(out['0'][0], out['1'][0], 'population')
@@ -92,7 +93,7 @@ def test_double_buffer_keeps_k2a(monkeypatch):
     eng.init_population(3, lo, hi)
     eng.eval_initial()
     eng.step()
-    assert eng.kernel_family() == 'tma_bin' and not _is_pool(eng)
+    assert eng.kernel_family() == 'tma_bin'
     eng.close()
 
 
@@ -122,7 +123,7 @@ def test_replayed_draws_through_the_pool(geometry):
         uni = rng.uniform(0.0, 1.0, size=(NP, D + 1))
         eng.set_rng_replay(donors, nstart, uni)
         eng.step()
-        assert eng.kernel_family() == 'tma_bin' and _is_pool(eng)
+        assert _is_pool(eng)
         orc.step(st, 'Best1Bin', CR, F, ocost, (), replay=dict(donors=donors, nstart=nstart, uni=uni))
         best_e, best_idx, n_inf, n_acc, gen, best_x = eng.read_result()
         pop = eng.population()

@@ -2,7 +2,7 @@
 qb() {  # one compact device-timed line, bounded
   for spec in "$@"; do
     envs=$(echo "${spec#*:}" | tr ',' ' ')
-    env $envs timeout 90 python bench.py --workload c2 --also none --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
+    env $envs timeout 90 python bench.py --workload ${spec%%:*} --also none --steps 20 --warmup 5 --no-cpu-baseline 2>/dev/null | python -c "
 import json,sys
 try:
     d=json.loads(sys.stdin.read()); print('$spec', 'ms %.4f burst %.4f frac %.4f burst_frac %.4f sm_mhz %s' % (d['ms_per_step'], d['details']['burst_ms_per_step'], d['roofline']['frac'], d['roofline'].get('frac_burst', 0), d['clocks']['sm_mhz']))

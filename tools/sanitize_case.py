@@ -15,7 +15,8 @@ CASES = [  # (NP, D, strategy id, cost, penalty?, expected family); strategy ids
     (200, 300, 0, models.rosen, False, 'tma_exp'),        # Best1Exp
     (150, 256, 5, models.corana, False, 'tma_exp'),       # Rand2Exp: a cost without a group reduction
     (180, 256, 1, models.griewangk, False, 'tma_bin'),    # Best1Bin, one-warp groups with a two-stage ring
-    (170, 1024, 1, models.rosen, False, 'tma_bin'),       # Best1Bin, four warps per row (quad transpose of the crossover words)
+    (170, 1024, 1, models.rosen, False, 'tma_pool'),      # Best1Bin in place: pooled row buffers behind two producer warps
+    (2400, 1024, 1, models.rosen, False, 'tma_pool'),     # ... with rings that revolve (16 rows per CTA)
     (90, 1030, 2, models.rosen, False, 'tma_exp'),        # Rand1Exp, ragged row length
 ]
 for NP, D, sid, cost, pen, family in CASES:
