@@ -21,6 +21,10 @@
 
 #include "de_tma.cuh"
 
+#ifndef MB2_POOL_EARLY_DRAWS
+#define MB2_POOL_EARLY_DRAWS 1
+#endif
+
 namespace mb2 {
 
 constexpr int kPoolMaxGroups = 24;   // consumer groups (groups of several warps: named barriers 1..15)
@@ -166,33 +170,21 @@ __global__ void __launch_bounds__(MAXT, 1)
       const uint32_t cand_g = (uint32_t)(P.global_offset + c);
       const double e_old = __ldg(P.e_cur + c);  // in flight while the group waits for its rows
 
-      // A parity test tells phase n from phase n - 1 only: were the slot still loading its PREVIOUS row (k - Q, issued
-      // before any row this group has finished, but not necessarily landed), the test would pass one phase early.  The
-      // producer therefore publishes the row number with the start index, and a group that finds another row's number
-      // waits again (never seen in practice: a row's copies would have to outlast the whole processing of a later row).
-      if (GW == 1 || grp.wig == 0) {  // (the group's first warp polls, the others block on the named barrier: group_wait_stage)
-        int seen;
-        do {
-          mbar_wait(s_full + q, fparity);
-          seen = reinterpret_cast<volatile int2*>(s_nstart + q)->y;
-        } while (seen != (int)k);
-      }
-      if (GW > 1) group_sync(grp);
-      const int nstart = s_nstart[q].x;
-
-      // ---- trial vector (strategy.py:77-85): K2a's loop (de_tma.cuh), rows of even length
-      bool oob = false;
-      auto trip = [&](int base, auto guard, auto uclamp) {
+      // ---- the row's crossover decisions, BEFORE the wait for its buffers: they depend on the row number only (Philox
+      // counters / the recorded uniforms), so the ten Philox rounds and the quad transposes of every trip run while the
+      // copies fly instead of after them.  8 bits per trip (4 chunks of 2 dimensions per thread), up to 8 trips.
+      auto draw_bits = [&](int base, auto guard) -> uint32_t {
         constexpr bool GUARD = decltype(guard)::value;
-        constexpr bool UCLAMP = decltype(uclamp)::value;
-        bool cx[8];
+        uint32_t bits = 0;
         if (P.replay) {
           const double* u = P.r_uni + c * (int64_t)(D + 1);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int pp = base + j * gthreads + tig;
-            cx[2 * j] = (!GUARD || pp < npairs) && ((2 * pp == nstart) || (__ldg(u + 2 * pp) < P.CR));
-            cx[2 * j + 1] = (!GUARD || pp < npairs) && ((2 * pp + 1 == nstart) || (__ldg(u + 2 * pp + 1) < P.CR));
+            if (!GUARD || pp < npairs) {
+              bits |= (__ldg(u + 2 * pp) < P.CR ? 1u : 0u) << (2 * j);
+              bits |= (__ldg(u + 2 * pp + 1) < P.CR ? 1u : 0u) << (2 * j + 1);
+            }
           }
         } else {
           const int qq = ((base + tq * gthreads + tig) >> 2);
@@ -209,10 +201,48 @@ __global__ void __launch_bounds__(MAXT, 1)
             const bool b0 = ((j & 1) != 0) != tq0, b1 = ((j & 2) != 0) != tq1;
             const uint32_t lo = b0 ? recv[1] : recv[0], hi = b0 ? recv[3] : recv[2];
             const uint32_t word = b1 ? hi : lo;
-            const int pp = base + j * gthreads + tig;
-            cx[2 * j] = (!GUARD || pp < npairs) && ((2 * pp == nstart) || field_lo_hit(word, P.thr16));
-            cx[2 * j + 1] = (!GUARD || pp < npairs) && ((2 * pp + 1 == nstart) || field_hi_hit(word, P.thr16));
+            bits |= (field_lo_hit(word, P.thr16) ? 1u : 0u) << (2 * j);
+            bits |= (field_hi_hit(word, P.thr16) ? 1u : 0u) << (2 * j + 1);
           }
+        }
+        return bits;
+      };
+      uint64_t xmask = 0;
+      auto draw_row = [&]() {
+        if (npairs % (4 * gthreads) == 0) {
+          for (int base = 0, t = 0; base < npairs; base += 4 * gthreads, ++t) xmask |= (uint64_t)draw_bits(base, std::false_type()) << (8 * t);
+        } else {
+          for (int base = 0, t = 0; base < npairs; base += 4 * gthreads, ++t) xmask |= (uint64_t)draw_bits(base, std::true_type()) << (8 * t);
+        }
+      };
+      if (MB2_POOL_EARLY_DRAWS) draw_row();
+
+      // A parity test tells phase n from phase n - 1 only: were the slot still loading its PREVIOUS row (k - Q, issued
+      // before any row this group has finished, but not necessarily landed), the test would pass one phase early.  The
+      // producer therefore publishes the row number with the start index, and a group that finds another row's number
+      // waits again (never seen in practice: a row's copies would have to outlast the whole processing of a later row).
+      if (GW == 1 || grp.wig == 0) {  // (the group's first warp polls, the others block on the named barrier: group_wait_stage)
+        int seen;
+        do {
+          mbar_wait(s_full + q, fparity);
+          seen = reinterpret_cast<volatile int2*>(s_nstart + q)->y;
+        } while (seen != (int)k);
+      }
+      if (GW > 1) group_sync(grp);
+      const int nstart = s_nstart[q].x;
+      if (!MB2_POOL_EARLY_DRAWS) draw_row();  // (A/B build: the draws after the wait, as K2a makes them)
+
+      // ---- trial vector (strategy.py:77-85): K2a's loop (de_tma.cuh), rows of even length
+      bool oob = false;
+      auto trip = [&](int base, uint32_t bits, auto guard, auto uclamp) {
+        constexpr bool GUARD = decltype(guard)::value;
+        constexpr bool UCLAMP = decltype(uclamp)::value;
+        bool cx[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int pp = base + j * gthreads + tig;
+          cx[2 * j] = (!GUARD || pp < npairs) && ((2 * pp == nstart) || ((bits >> (2 * j)) & 1u) != 0);
+          cx[2 * j + 1] = (!GUARD || pp < npairs) && ((2 * pp + 1 == nstart) || ((bits >> (2 * j + 1)) & 1u) != 0);
         }
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -245,12 +275,15 @@ __global__ void __launch_bounds__(MAXT, 1)
       };
       if (npairs % (4 * gthreads) == 0) {
         if (uni_b && P.bounds_mode == BOUNDS_CLAMP) {
-          for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::true_type());
+          for (int base = 0, t = 0; base < npairs; base += 4 * gthreads, ++t)
+            trip(base, (uint32_t)(xmask >> (8 * t)) & 0xffu, std::false_type(), std::true_type());
         } else {
-          for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::false_type(), std::false_type());
+          for (int base = 0, t = 0; base < npairs; base += 4 * gthreads, ++t)
+            trip(base, (uint32_t)(xmask >> (8 * t)) & 0xffu, std::false_type(), std::false_type());
         }
       } else {
-        for (int base = 0; base < npairs; base += 4 * gthreads) trip(base, std::true_type(), std::false_type());
+        for (int base = 0, t = 0; base < npairs; base += 4 * gthreads, ++t)
+          trip(base, (uint32_t)(xmask >> (8 * t)) & 0xffu, std::true_type(), std::false_type());
       }
       oob = group_any(grp, oob);  // also the barrier that publishes the trial vector to the group
       // every thread of the group has read the parent and the second donor: their buffers go back to the producer
