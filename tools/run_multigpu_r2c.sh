@@ -1,0 +1,14 @@
+#!/bin/bash
+# Multi-GPU check after K2p (under `gpurun --gpus N`): shard parity (tests/dist_gpu_check.py) and the default bench line at N
+N=${1:-2}
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511"
+echo "== dist check"; timeout 200 $TR tests/dist_gpu_check.py 2>&1 | grep -v "^W1\|^\*\*\*\|OMP_NUM" | tail -3 | tee gpurun_out/r2c_dist_check_${N}.log
+echo "== bench N=$N"; timeout 400 $TR bench.py --gpus $N --steps 20 --warmup 5 2>gpurun_out/r2c_bench_n${N}.err | tail -1 > gpurun_out/r2c_bench_n${N}.json
+python - <<PY
+import json
+d=json.load(open('gpurun_out/r2c_bench_n${N}.json'))
+print('c2', d['n_gpus'], 'ms %.4f' % d['ms_per_step'], 'value %.4g' % d['value'], 'e2e %.4g' % d['e2e']['value'], 'parity', d.get('shard_parity'), d['clocks'], d['roofline'].get('kernel'))
+for k, v in d.get('also', {}).items():
+    print(k, v.get('ms_per_step'), '%.4g' % v.get('value', 0), v.get('roofline', {}).get('frac'), v.get('error'))
+PY
+tail -c 400 gpurun_out/r2c_bench_n${N}.err
