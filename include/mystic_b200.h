@@ -306,6 +306,15 @@ int mb2_selftest_cosine(mb2_ctx* ctx, int64_t n, uint64_t seed, double span, dou
  * population) by the DMMA figure instead of a constant.  Synchronises `stream`; no context needed. */
 int mb2_probe_fp64_peak(int device, int32_t iters, double* dfma_tflops, double* dmma_tflops, void* stream);
 
+/* Geometry the host would give the pooled producer / consumer kernel K2p (de_tma_pool.cuh: Best1Bin generations of
+ * `dim`-dimensional rows committed in place -- the reference's population + trialSolution layout,
+ * mystic/differential_evolution.py:585-609) with the MB2_POOL_* environment overrides applied:
+ * out[0..5] = {parent + second-donor pairs P, first-donor buffers Q, consumer groups G, warps per group, producer warps,
+ * dynamic shared memory in bytes}.  MB2_EINVAL (out zeroed) when K2p does not take such rows.  A pure host function:
+ * no device, no context -- the CPU tests check the invariants the kernel's mbarrier protocol relies on (Q >= G,
+ * 2P + Q row buffers + bestSolution within a CTA's shared memory, the builds' thread bounds). */
+int mb2_probe_pool_geometry(int32_t dim, int32_t* out);
+
 /* launch geometry of the fused kernel (for bench.py / profiling): CTAs, threads, dynamic smem */
 int mb2_launch_info(mb2_ctx* ctx, int32_t* grid, int32_t* block, int32_t* smem_bytes);
 /* number of kernels this library has launched through the context (bench.py gpu_launches) */

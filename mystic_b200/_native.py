@@ -20,7 +20,7 @@ EXPORTS = [
     'mb2_launch_info', 'mb2_launch_count', 'mb2_kernel_family', 'mb2_selftest_division', 'mb2_selftest_cosine', 'mb2_restore_state', 'mb2_create_ws', 'mb2_workspace_bytes',
     'mb2_set_termination', 'mb2_run', 'mb2_run_result', 'mb2_set_islands', 'mb2_read_islands', 'mb2_exchange_open', 'mb2_exchange_connect', 'mb2_exchange_connected', 'mb2_exchange_reset', 'mb2_exchange_best',
     'mb2_probe_fp64_peak', 'mb2_set_penalty_ex', 'mb2_set_island_groups', 'mb2_run_result_islands',
-    'mb2_set_commit_mode', 'mb2_last_commit_in_place',
+    'mb2_set_commit_mode', 'mb2_last_commit_in_place', 'mb2_probe_pool_geometry',
 ]
 
 
@@ -75,6 +75,7 @@ def _load():
         'mb2_read_result': (ctypes.c_int, [vp, ctypes.POINTER(Result), c_double_p, vp]),
         'mb2_eval_cost': (ctypes.c_int, [vp, vp, i64, vp, vp]),
         'mb2_launch_info': (ctypes.c_int, [vp, c_int32_p, c_int32_p, c_int32_p]),
+        'mb2_probe_pool_geometry': (ctypes.c_int, [i32, c_int32_p]),
         'mb2_launch_count': (i64, [vp]),
         'mb2_kernel_family': (ctypes.c_int, [vp]),
         'mb2_selftest_division': (ctypes.c_int, [vp, i64, u64, dbl, c_int64_p]),

@@ -1846,6 +1846,20 @@ int mb2_launch_info(mb2_ctx* c, int32_t* grid, int32_t* block, int32_t* smem) {
 
 int64_t mb2_launch_count(mb2_ctx* c) { return c ? c->launches : 0; }
 
+int mb2_probe_pool_geometry(int32_t dim, int32_t* out) {
+  if (out == nullptr) return fail(MB2_EINVAL, "out is NULL");
+  int p = 0, q = 0, g = 0, gw = 0, np_ = 0, smem = 0;
+  for (int i = 0; i < 6; ++i) out[i] = 0;
+  if (!pool_geometry((int)dim, &p, &q, &g, &gw, &np_, &smem)) return MB2_EINVAL;  // (no message: "K2a runs these rows" is an answer)
+  out[0] = p;
+  out[1] = q;
+  out[2] = g;
+  out[3] = gw;
+  out[4] = np_;
+  out[5] = smem;
+  return MB2_OK;
+}
+
 int mb2_kernel_family(mb2_ctx* c) { return c ? c->family : MB2_KERNEL_NONE; }
 
 }  // extern "C"
