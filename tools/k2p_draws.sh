@@ -1,4 +1,5 @@
 # K2p: crossover draws before (product build) or after (-DMB2_POOL_EARLY_DRAWS=0) the wait for the row's buffers
+# (the late-draws build: python -c "from mystic_b200 import build; build.build(extra_flags=('-DMB2_POOL_EARLY_DRAWS=0',), out='mystic_b200/_lib/libmystic_b200_latedraws.so')")
 . tools/k2p_ab.sh.inc
 qb "c2:MB2_TMA_POOL=1" | tee /tmp/first.txt
 if grep -q FAILED /tmp/first.txt; then echo "pool kernel failed or hung: stop"; exit 1; fi
